@@ -1,0 +1,161 @@
+"""ctypes binding for the CPU oracle (oracle/liborc.so).  TEST INFRASTRUCTURE ONLY.
+
+Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs;
+never by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB_PATH = os.path.join(_ORACLE_DIR, "liborc.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _ORACLE_DIR])
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        build()
+    return C.CDLL(_LIB_PATH)
+
+
+lib = _load()
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int)
+_f32p = C.POINTER(C.c_float)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+lib.orc_extractor_create.restype = C.c_void_p
+lib.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+lib.orc_extractor_destroy.argtypes = [C.c_void_p]
+lib.orc_extractor_run.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _u8p, C.c_int]
+lib.orc_extractor_tables.argtypes = [C.c_void_p] + [_f32p] * 4 + [_i32p] * 2
+lib.orc_extractor_level_dims.argtypes = [C.c_void_p, C.c_int, _i32p, _i32p]
+lib.orc_extractor_level_copy.argtypes = [C.c_void_p, C.c_int, _u8p]
+lib.orc_extractor_candidates.argtypes = [C.c_void_p, C.c_int, _i32p, C.c_int]
+lib.orc_extractor_level_count.argtypes = [C.c_void_p, C.c_int]
+lib.orc_ic_angle.restype = C.c_float
+lib.orc_ic_angle.argtypes = [_u8p, C.c_int]
+lib.orc_orb_descriptor.argtypes = [C.c_float, _u8p, C.c_int, _u8p]
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib.orc_resize_linear_u8(_p(src, _u8p), src.shape[1], src.shape[0], src.strides[0], _p(dst, _u8p), dw, dh, dw)
+    return dst
+
+
+def border_reflect101(src, b):
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.empty((h + 2 * b, w + 2 * b), np.uint8)
+    lib.orc_border_reflect101(_p(src, _u8p), w, h, src.strides[0], _p(dst, _u8p), b, w + 2 * b)
+    return dst
+
+
+def gaussian_blur7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.empty((h, w), np.uint8)
+    lib.orc_gaussian_blur7(_p(src, _u8p), w, h, src.strides[0], _p(dst, _u8p), w)
+    return dst
+
+
+def fast_nms(img, th):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.empty((w * h, 3), np.int32)
+    n = lib.orc_fast_nms(_p(img, _u8p), w, h, img.strides[0], th, _p(out, _i32p), w * h)
+    return out[:n].copy()
+
+
+def fast_score_map(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.empty((h, w), np.int16)
+    lib.orc_fast_score_map(_p(img, _u8p), w, h, img.strides[0], out.ctypes.data_as(C.POINTER(C.c_int16)))
+    return out
+
+
+def fast_atan2(y, x):
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(y)
+    lib.orc_fast_atan2(_p(y, _f32p), _p(x, _f32p), _p(out, _f32p), y.size)
+    return out
+
+
+def ic_angle(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    ptr = C.cast(img.ctypes.data + y * img.strides[0] + x, _u8p)
+    return np.float32(lib.orc_ic_angle(ptr, img.strides[0]))
+
+
+def orb_descriptor(img, x, y, angle):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(32, np.uint8)
+    ptr = C.cast(img.ctypes.data + y * img.strides[0] + x, _u8p)
+    lib.orc_orb_descriptor(C.c_float(angle), ptr, img.strides[0], _p(out, _u8p))
+    return out
+
+
+class Extractor:
+    """Oracle ORBextractor (reference: src/ORBextractor.cc)."""
+
+    def __init__(self, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = lib.orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        sc, inv, sg, isg = (np.empty(nlevels, np.float32) for _ in range(4))
+        q = np.empty(nlevels, np.int32)
+        um = np.empty(16, np.int32)
+        lib.orc_extractor_tables(self.h, _p(sc, _f32p), _p(inv, _f32p), _p(sg, _f32p), _p(isg, _f32p),
+                                 _p(q, _i32p), _p(um, _i32p))
+        self.scale, self.inv_scale, self.sigma2, self.inv_sigma2, self.quota, self.umax = sc, inv, sg, isg, q, um
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.orc_extractor_destroy(self.h)
+            self.h = None
+
+    def __call__(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures + 64 * self.nlevels + 4096
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = lib.orc_extractor_run(self.h, _p(img, _u8p), img.shape[1], img.shape[0], img.strides[0],
+                                  kps.ctypes.data, _p(desc, _u8p), cap)
+        if n < 0:
+            raise ValueError("oracle extractor: input the reference cannot process")
+        assert n <= cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l):
+        """Bordered pyramid level (h+38, w+38)."""
+        w, h = C.c_int(), C.c_int()
+        lib.orc_extractor_level_dims(self.h, l, C.byref(w), C.byref(h))
+        out = np.empty((h.value + 38, w.value + 38), np.uint8)
+        lib.orc_extractor_level_copy(self.h, l, _p(out, _u8p))
+        return out
+
+    def candidates(self, l):
+        n = lib.orc_extractor_candidates(self.h, l, None, 0)
+        out = np.empty((max(n, 1), 3), np.int32)
+        lib.orc_extractor_candidates(self.h, l, _p(out, _i32p), n)
+        return out[:n]
+
+    def level_counts(self):
+        return np.array([lib.orc_extractor_level_count(self.h, l) for l in range(self.nlevels)], np.int32)
