@@ -1,0 +1,149 @@
+/* sdyn — B200-native tracking front end for li-guihai/slam-dynamic: the C-ABI drop-in boundary.
+ *
+ * This is the ONLY interface between the reference-facing C++ adapter classes
+ * (slam-dynamic_b200/host/: ORB_SLAM2::ORBextractor, ORBmatcher, Frame helpers — same signatures
+ * as the reference) and the hand-written sm_100a CUDA kernels (slam-dynamic_b200/csrc/).
+ * Plain C types only: int, float, pointers, POD structs.  Every function returns 0 on success and a
+ * negative sdyn_status on failure; nothing throws, nothing calls exit().  There is no CPU fallback:
+ * when no CUDA device is usable sdyn_create() fails with SDYN_ERR_CUDA.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference tree).
+ */
+#ifndef SDYN_H_
+#define SDYN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDYN_MAX_LEVELS 16
+#define SDYN_EDGE 19            /* EDGE_THRESHOLD, src/ORBextractor.cc:74 — border of every pyramid level */
+#define SDYN_GRID_COLS 64       /* FRAME_GRID_COLS, include/Frame.h:40 */
+#define SDYN_GRID_ROWS 48       /* FRAME_GRID_ROWS, include/Frame.h:39 */
+#define SDYN_TH_HIGH 100        /* ORBmatcher::TH_HIGH, src/ORBmatcher.cc:37 */
+#define SDYN_TH_LOW 50          /* ORBmatcher::TH_LOW,  src/ORBmatcher.cc:38 */
+#define SDYN_HISTO_LENGTH 30    /* ORBmatcher::HISTO_LENGTH, src/ORBmatcher.cc:39 */
+
+typedef enum {
+    SDYN_OK = 0,
+    SDYN_ERR_ARG = -1,          /* bad argument (null pointer, size out of the limits given to sdyn_create) */
+    SDYN_ERR_CUDA = -2,         /* CUDA runtime error or no device; sdyn_last_error() has the text */
+    SDYN_ERR_CAPACITY = -3,     /* caller's output capacity too small; required count is still reported */
+    SDYN_ERR_GEOMETRY = -4,     /* image shape on which the reference itself is undefined */
+    SDYN_ERR_NOMEM = -5
+} sdyn_status;
+
+/* Layout-identical to cv::KeyPoint (28 bytes): the adapter reinterpret_casts between the two. */
+typedef struct {
+    float x, y;                 /* pt, level-0 coordinates */
+    float size;                 /* int(31 * scale[octave]) */
+    float angle;                /* degrees, [0,360) */
+    float response;             /* FAST score */
+    int32_t octave;
+    int32_t class_id;           /* -1 out of the extractor */
+} sdyn_keypoint;
+
+/* Constructor arguments of ORBextractor (include/ORBextractor.h:51-52). */
+typedef struct {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+} sdyn_orb_params;
+
+/* Values of the getters GetScaleFactors()/GetInverseScaleFactors()/GetScaleSigmaSquares()/
+ * GetInverseScaleSigmaSquares() (include/ORBextractor.h:60-78) and of mnFeaturesPerLevel. */
+typedef struct {
+    int32_t nlevels;
+    float scale[SDYN_MAX_LEVELS];
+    float inv_scale[SDYN_MAX_LEVELS];
+    float sigma2[SDYN_MAX_LEVELS];
+    float inv_sigma2[SDYN_MAX_LEVELS];
+    int32_t features_per_level[SDYN_MAX_LEVELS];
+} sdyn_scale_info;
+
+/* Geometry of one pyramid level for the current image size (ComputePyramid, src/ORBextractor.cc:1107-1132). */
+typedef struct {
+    int32_t width, height;      /* un-bordered level size */
+    int32_t pitch;              /* bytes per row of the bordered device buffer */
+    int32_t reserved;
+    size_t offset;              /* byte offset of bordered pixel (-19,-19) inside one frame's pyramid block */
+} sdyn_level_info;
+
+typedef struct sdyn_ctx sdyn_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------
+ * One context per ORBextractor instance (the reference runs the left and right instances on two
+ * threads, src/Frame.cc:151-154: use two contexts).  Owns its device buffers, pinned staging and
+ * stream; after sdyn_create nothing is allocated per frame.  max_batch = frames processed per call
+ * by the *_batch entry points (1 for the plain drop-in). */
+int sdyn_create(const sdyn_orb_params* params, int max_width, int max_height, int max_batch,
+                int device, sdyn_ctx** out);
+int sdyn_destroy(sdyn_ctx* ctx);
+/* Text of the last error on this context (never NULL).  sdyn_create failures: pass NULL. */
+const char* sdyn_last_error(const sdyn_ctx* ctx);
+int sdyn_scale_info_get(const sdyn_ctx* ctx, sdyn_scale_info* out);
+/* Capacity needed for the keypoint / descriptor outputs of one frame: the extractor can return a few
+ * more than nfeatures (the octree overshoots by up to 3 per level). */
+int sdyn_max_keypoints(const sdyn_ctx* ctx);
+
+/* Pinned host memory helpers (optional; any host pointer works, pinned ones copy asynchronously). */
+int sdyn_host_alloc(void** ptr, size_t bytes);
+int sdyn_host_free(void* ptr);
+
+/* ---- ORBextractor::operator() -----------------------------------------------------------------
+ * Replaces ORBextractor::operator()(image, mask, keypoints, descriptors), src/ORBextractor.cc:1043-1105.
+ * gray: 8-bit single channel, `stride` bytes per row (host memory).  Writes at most `cap` keypoints
+ * (level-major, octree list order) and 32-byte descriptors; *n_out receives the true count.
+ * An empty image (w==0 || h==0 || gray==NULL) is a silent no-op with *n_out = 0, as in the reference.
+ * pyr_out (nullable): SDYN_MAX_LEVELS host pointers, each receiving the bordered level
+ * ((w_l+38) x (h_l+38), tightly packed) — the public mvImagePyramid member (include/ORBextractor.h:85). */
+int sdyn_extract(sdyn_ctx* ctx, const uint8_t* gray, int width, int height, int stride,
+                 sdyn_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out,
+                 uint8_t* const* pyr_out);
+
+/* Batched form: nframes (<= max_batch) images of identical size, frame f at gray + f*frame_stride.
+ * Outputs: frame f at kp_out + f*cap and desc_out + f*cap*32; n_out[f]. */
+int sdyn_extract_batch(sdyn_ctx* ctx, int nframes, const uint8_t* gray, size_t frame_stride,
+                       int width, int height, int stride,
+                       sdyn_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out);
+
+/* Device-resident form: d_gray is a device pointer; results stay on the device (see
+ * sdyn_device_results) until sdyn_fetch_results.  `stream` is a cudaStream_t (NULL = the context's own
+ * stream); the call only enqueues work. */
+int sdyn_extract_batch_device(sdyn_ctx* ctx, int nframes, const uint8_t* d_gray, size_t frame_stride,
+                              int width, int height, int stride, void* stream);
+typedef struct {
+    const sdyn_keypoint* kp;    /* [max_batch][cap] */
+    const uint8_t* desc;        /* [max_batch][cap][32] */
+    const int32_t* count;       /* [max_batch] */
+    const int32_t* level_count; /* [max_batch][SDYN_MAX_LEVELS] keypoints kept per level */
+    const uint8_t* pyramid;     /* [max_batch] frames of `pyramid_frame_bytes`, levels at sdyn_level_info.offset */
+    const uint8_t* blurred;     /* same geometry, GaussianBlur(7x7, sigma 2) of every level (interior only) */
+    size_t pyramid_frame_bytes;
+    int32_t cap;
+    int32_t nlevels;
+    sdyn_level_info level[SDYN_MAX_LEVELS];
+} sdyn_device_view;
+int sdyn_device_results(const sdyn_ctx* ctx, sdyn_device_view* out);
+int sdyn_fetch_results(sdyn_ctx* ctx, int nframes, sdyn_keypoint* kp_out, uint8_t* desc_out, int cap,
+                       int* n_out, void* stream);
+/* Copies bordered level `level` of frame `frame` of the last batch to host, tightly packed. */
+int sdyn_fetch_level(sdyn_ctx* ctx, int frame, int level, uint8_t* out, int* width, int* height);
+/* Stage-level introspection for parity tests: FAST candidates of (frame, level) after the per-cell
+ * threshold fallback, as (x, y, response) int triples in level coordinates relative to the FAST window
+ * origin (minBorderX/Y = 16).  Order is unspecified (the selection stage is order-independent). */
+int sdyn_fetch_candidates(sdyn_ctx* ctx, int frame, int level, int32_t* xyv, int cap, int* n_out);
+/* Blocks until all work enqueued on the context's stream has finished. */
+int sdyn_sync(sdyn_ctx* ctx);
+/* Number of kernel launches enqueued by this context since creation (bench.py's gpu_launches). */
+long long sdyn_launch_count(const sdyn_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDYN_H_ */

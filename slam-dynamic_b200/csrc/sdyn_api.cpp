@@ -1,0 +1,346 @@
+/* C-ABI of libsdyn: context management and the ORBextractor::operator() replacement.
+ * See include/sdyn.h for the contract; kernels live in k_*.cu. */
+#include "sdyn_internal.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+using namespace sdyn;
+
+namespace {
+
+thread_local std::string g_createError = "";
+
+int fail(sdyn_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_createError = msg;
+    return code;
+}
+
+int cuda_fail(sdyn_ctx* c, cudaError_t e, const char* what)
+{
+    return fail(c, SDYN_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(c, call)                                                   \
+    do {                                                              \
+        cudaError_t e_ = (call);                                      \
+        if (e_ != cudaSuccess) return cuda_fail((c), e_, #call);      \
+    } while (0)
+
+template <class T>
+cudaError_t dalloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T)); }
+
+void build_tiles(const Geom& g, std::vector<TileRef>& fast, std::vector<TileRef>& blur)
+{
+    fast.clear(); blur.clear();
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.L[l];
+        for (int ty = 0; ty * kFastTileH < L.fh; ++ty)
+            for (int tx = 0; tx * kFastTileW < L.fw; ++tx) fast.push_back({(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
+        for (int ty = 0; ty * kBlurTileH < L.h; ++ty)
+            for (int tx = 0; tx * kBlurTileW < L.w; ++tx) blur.push_back({(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
+    }
+}
+
+/* (Re)computes geometry when the image size changes; device buffers were sized for (maxW, maxH). */
+int ensure_geometry(sdyn_ctx* c, int W, int H)
+{
+    if (c->geomValid && c->geom.W == W && c->geom.H == H) return SDYN_OK;
+    if (W > c->maxW || H > c->maxH) return fail(c, SDYN_ERR_ARG, "image larger than the size given to sdyn_create");
+    Geom g; std::vector<uint8_t> tables;
+    int rc = compute_geometry(c->params, c->scales, W, H, g, tables);
+    if (rc != SDYN_OK)
+        return fail(c, rc, "image shape unsupported: a pyramid level is too small for the 30-px FAST grid / octree "
+                           "(the reference divides by zero here)");
+    if ((size_t)g.frameBytes > c->pyrFrameCap || g.cellsPerFrame > c->cellCap || g.candPerFrame > c->candCap ||
+        g.kpPerFrame > c->levelKpCap || tables.size() > c->tablesCap)
+        return fail(c, SDYN_ERR_ARG, "internal: geometry exceeds the buffers sized at sdyn_create");
+    std::vector<TileRef> ft, bt;
+    build_tiles(g, ft, bt);
+    /* the previous geometry may still be in use by enqueued kernels */
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(c->dTables, tables.data(), tables.size(), cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->dFastTiles, ft.data(), ft.size() * sizeof(TileRef), cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->dBlurTiles, bt.data(), bt.size() * sizeof(TileRef), cudaMemcpyHostToDevice));
+    c->geom = g; c->nFastTiles = (int)ft.size(); c->nBlurTiles = (int)bt.size();
+    c->geomValid = true;
+    return SDYN_OK;
+}
+
+/* Enqueues the whole extraction pipeline for nframes frames already resident in device memory. */
+int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride, int rowStride, cudaStream_t st)
+{
+    const Geom& g = c->geom;
+    const sdyn_orb_params& p = c->params;
+    CU(c, cudaMemsetAsync(c->dCandCount, 0, sizeof(int32_t) * SDYN_MAX_LEVELS * nframes, st));
+    CU(c, cudaMemsetAsync(c->dCellFlag, 0, (size_t)g.cellsPerFrame * nframes, st));
+    CU(c, launch_level0(g, dGray, frameStride, rowStride, c->dPyr, nframes, st));
+    for (int l = 1; l < g.nlevels; ++l) CU(c, launch_resize(g, l, c->dTables, c->dPyr, nframes, st));
+    CU(c, launch_fast(g, c->dFastTiles, c->nFastTiles, c->dPyr, p.ini_th_fast, p.min_th_fast, c->dCellFlag,
+                      c->dCand, c->dCandCount, nframes, st));
+    CU(c, launch_octree(g, p.ini_th_fast, p.min_th_fast, c->dCellFlag, c->dCand, c->dCandCount, c->dCandNode,
+                        c->dSelCount, c->dLevelKp, c->dLevelCount, c->dStatus, nframes, st));
+    CU(c, launch_blur(g, c->dBlurTiles, c->nBlurTiles, c->dPyr, c->dBlur, nframes, st));
+    CU(c, launch_orient_describe(g, c->dPyr, c->dBlur, c->dLevelKp, c->dLevelCount, c->dKp, c->dDesc, c->dCount,
+                                 c->maxKp, nframes, st));
+    c->launches += 2 + 1 + (g.nlevels - 1) + 4;
+    return SDYN_OK;
+}
+
+void free_all(sdyn_ctx* c)
+{
+    cudaFree(c->dFastTiles); cudaFree(c->dBlurTiles); cudaFree(c->dTables); cudaFree(c->dIn); cudaFree(c->dPyr);
+    cudaFree(c->dBlur); cudaFree(c->dCellFlag); cudaFree(c->dCand); cudaFree(c->dCandNode); cudaFree(c->dCandCount); cudaFree(c->dSelCount);
+    cudaFree(c->dLevelKp); cudaFree(c->dLevelCount); cudaFree(c->dCount); cudaFree(c->dStatus); cudaFree(c->dKp);
+    cudaFree(c->dDesc);
+    cudaFreeHost(c->hKp); cudaFreeHost(c->hDesc); cudaFreeHost(c->hCount); cudaFreeHost(c->hStatus);
+    if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdyn_create(const sdyn_orb_params* params, int maxW, int maxH, int maxBatch, int device, sdyn_ctx** out)
+{
+    if (!params || !out) return fail(nullptr, SDYN_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (params->nlevels < 1 || params->nlevels > SDYN_MAX_LEVELS || params->nfeatures < 1 ||
+        !(params->scale_factor > 1.0f) || params->ini_th_fast < 1 || params->min_th_fast < 1 ||
+        params->ini_th_fast > 255 || params->min_th_fast > 255 || maxBatch < 1 || maxW < 1 || maxH < 1)
+        return fail(nullptr, SDYN_ERR_ARG, "bad ORB parameters or limits");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SDYN_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, SDYN_ERR_ARG, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+
+    sdyn_ctx* c = new (std::nothrow) sdyn_ctx();
+    if (!c) return fail(nullptr, SDYN_ERR_NOMEM, "out of host memory");
+    c->params = *params; c->maxW = maxW; c->maxH = maxH; c->maxBatch = maxBatch; c->device = device;
+    compute_scale_info(c->params, c->scales, c->umax);
+    c->maxKp = max_keypoints_per_frame(c->params, c->scales, maxW, maxH);
+
+    /* size every buffer with the geometry of the largest image */
+    Geom g; std::vector<uint8_t> tables;
+    int rc = compute_geometry(c->params, c->scales, maxW, maxH, g, tables);
+    if (rc != SDYN_OK) { delete c; return fail(nullptr, rc, "max_width x max_height is too small for this pyramid"); }
+    std::vector<TileRef> ft, bt;
+    build_tiles(g, ft, bt);
+    const size_t B = (size_t)maxBatch;
+    /* smaller images of another aspect ratio can need slightly different per-level splits: 12% headroom */
+    auto room = [](size_t v) { return v + v / 8 + 4096; };
+    c->pyrFrameCap = room((size_t)g.frameBytes);
+    c->cellCap = (int)room(g.cellsPerFrame); c->candCap = (int)room(g.candPerFrame);
+    c->levelKpCap = (int)room(g.kpPerFrame); c->tablesCap = room(tables.size());
+    c->inFrameCap = (size_t)maxW * maxH;
+    const size_t tileCap = room(std::max(ft.size(), bt.size()));
+
+    cudaError_t ce = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (ce == cudaSuccess) ce = r; };
+    A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    A(dalloc(&c->dFastTiles, tileCap)); A(dalloc(&c->dBlurTiles, tileCap));
+    A(dalloc(&c->dTables, c->tablesCap));
+    A(dalloc(&c->dIn, c->inFrameCap * B));
+    A(dalloc(&c->dPyr, c->pyrFrameCap * B)); A(dalloc(&c->dBlur, c->pyrFrameCap * B));
+    A(dalloc(&c->dCellFlag, (size_t)c->cellCap * B));
+    A(dalloc(&c->dCand, (size_t)c->candCap * B)); A(dalloc(&c->dCandNode, (size_t)c->candCap * B));
+    A(dalloc(&c->dCandCount, SDYN_MAX_LEVELS * B)); A(dalloc(&c->dSelCount, SDYN_MAX_LEVELS * B));
+    A(dalloc(&c->dLevelKp, (size_t)c->levelKpCap * B));
+    A(dalloc(&c->dLevelCount, SDYN_MAX_LEVELS * B));
+    A(dalloc(&c->dCount, B)); A(dalloc(&c->dStatus, B));
+    A(dalloc(&c->dKp, (size_t)c->maxKp * B)); A(dalloc(&c->dDesc, (size_t)c->maxKp * 32 * B));
+    A(cudaMallocHost(reinterpret_cast<void**>(&c->hKp), sizeof(sdyn_keypoint) * c->maxKp * B));
+    A(cudaMallocHost(reinterpret_cast<void**>(&c->hDesc), (size_t)32 * c->maxKp * B));
+    A(cudaMallocHost(reinterpret_cast<void**>(&c->hCount), sizeof(int32_t) * B));
+    A(cudaMallocHost(reinterpret_cast<void**>(&c->hStatus), sizeof(int32_t) * B));
+    if (ce == cudaSuccess) ce = cudaMemset(c->dStatus, 0, sizeof(int32_t) * B);
+    if (ce == cudaSuccess) ce = cudaMemset(c->dBlur, 0, c->pyrFrameCap * B);
+    if (ce == cudaSuccess) ce = cudaMemset(c->dPyr, 0, c->pyrFrameCap * B);
+    if (ce != cudaSuccess) {
+        std::string msg = std::string("allocation failed: ") + cudaGetErrorString(ce);
+        free_all(c); delete c;
+        return fail(nullptr, ce == cudaErrorMemoryAllocation ? SDYN_ERR_NOMEM : SDYN_ERR_CUDA, msg);
+    }
+    c->geomValid = false;
+    *out = c;
+    return SDYN_OK;
+}
+
+int sdyn_destroy(sdyn_ctx* c)
+{
+    if (!c) return SDYN_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_all(c);
+    delete c;
+    return SDYN_OK;
+}
+
+const char* sdyn_last_error(const sdyn_ctx* c) { return c ? c->err.c_str() : g_createError.c_str(); }
+
+int sdyn_scale_info_get(const sdyn_ctx* c, sdyn_scale_info* out)
+{
+    if (!c || !out) return SDYN_ERR_ARG;
+    *out = c->scales;
+    return SDYN_OK;
+}
+
+int sdyn_max_keypoints(const sdyn_ctx* c) { return c ? c->maxKp : SDYN_ERR_ARG; }
+
+int sdyn_host_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr) return SDYN_ERR_ARG;
+    return cudaMallocHost(ptr, bytes) == cudaSuccess ? SDYN_OK : SDYN_ERR_NOMEM;
+}
+
+int sdyn_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? SDYN_OK : SDYN_ERR_CUDA; }
+
+int sdyn_extract_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride,
+                              int W, int H, int stride, void* stream)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (nframes < 1 || nframes > c->maxBatch || !dGray || W < 1 || H < 1 || stride < W)
+        return fail(c, SDYN_ERR_ARG, "sdyn_extract_batch_device: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_geometry(c, W, H);
+    if (rc != SDYN_OK) return rc;
+    return enqueue_extract(c, nframes, dGray, frameStride, stride, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int sdyn_fetch_results(sdyn_ctx* c, int nframes, sdyn_keypoint* kpOut, uint8_t* descOut, int cap, int* nOut, void* stream)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (nframes < 1 || nframes > c->maxBatch || !nOut || cap < 0 || (cap > 0 && (!kpOut || !descOut)))
+        return fail(c, SDYN_ERR_ARG, "sdyn_fetch_results: bad argument");
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    CU(c, cudaSetDevice(c->device));
+    /* one D2H per array into pinned staging, then scatter into the caller's layout */
+    CU(c, cudaMemcpyAsync(c->hCount, c->dCount, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(c->hStatus, c->dStatus, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(c->hKp, c->dKp, sizeof(sdyn_keypoint) * (size_t)c->maxKp * nframes, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(c->hDesc, c->dDesc, (size_t)32 * c->maxKp * nframes, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    int rc = SDYN_OK;
+    for (int f = 0; f < nframes; ++f) {
+        if (c->hStatus[f]) return fail(c, SDYN_ERR_CAPACITY, "internal candidate/node capacity exceeded");
+        const int n = c->hCount[f];
+        nOut[f] = n;
+        const int m = std::min(n, cap);
+        if (n > cap) rc = SDYN_ERR_CAPACITY;
+        if (m > 0) {
+            std::memcpy(kpOut + (size_t)f * cap, c->hKp + (size_t)f * c->maxKp, sizeof(sdyn_keypoint) * m);
+            std::memcpy(descOut + (size_t)f * cap * 32, c->hDesc + (size_t)f * c->maxKp * 32, (size_t)32 * m);
+        }
+    }
+    if (rc != SDYN_OK) fail(c, rc, "output capacity too small (see sdyn_max_keypoints)");
+    return rc;
+}
+
+int sdyn_extract_batch(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frameStride, int W, int H, int stride,
+                       sdyn_keypoint* kpOut, uint8_t* descOut, int cap, int* nOut)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (!nOut) return fail(c, SDYN_ERR_ARG, "n_out is null");
+    if (!gray || W <= 0 || H <= 0) {               /* empty image: the reference returns silently */
+        for (int f = 0; f < std::max(nframes, 0); ++f) nOut[f] = 0;
+        return SDYN_OK;
+    }
+    if (nframes < 1 || nframes > c->maxBatch || stride < W)
+        return fail(c, SDYN_ERR_ARG, "sdyn_extract_batch: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_geometry(c, W, H);
+    if (rc != SDYN_OK) return rc;
+    /* H2D: rows are packed to W on the device */
+    for (int f = 0; f < nframes; ++f)
+        CU(c, cudaMemcpy2DAsync(c->dIn + (size_t)f * W * H, W, gray + (size_t)f * frameStride, stride, W, H,
+                                cudaMemcpyHostToDevice, c->stream));
+    rc = enqueue_extract(c, nframes, c->dIn, (size_t)W * H, W, c->stream);
+    if (rc != SDYN_OK) return rc;
+    return sdyn_fetch_results(c, nframes, kpOut, descOut, cap, nOut, nullptr);
+}
+
+int sdyn_fetch_level(sdyn_ctx* c, int frame, int level, uint8_t* out, int* width, int* height)
+{
+    if (!c || !c->geomValid) return SDYN_ERR_ARG;
+    if (frame < 0 || frame >= c->maxBatch || level < 0 || level >= c->geom.nlevels || !out)
+        return fail(c, SDYN_ERR_ARG, "sdyn_fetch_level: bad argument");
+    const LevelGeom& L = c->geom.L[level];
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const uint8_t* src = c->dPyr + (size_t)frame * c->geom.frameBytes + L.off - (long long)kEdge * L.pitch - kEdge;
+    CU(c, cudaMemcpy2D(out, L.w + 2 * kEdge, src, L.pitch, L.w + 2 * kEdge, L.h + 2 * kEdge, cudaMemcpyDeviceToHost));
+    if (width) *width = L.w;
+    if (height) *height = L.h;
+    return SDYN_OK;
+}
+
+int sdyn_extract(sdyn_ctx* c, const uint8_t* gray, int W, int H, int stride, sdyn_keypoint* kpOut, uint8_t* descOut,
+                 int cap, int* nOut, uint8_t* const* pyrOut)
+{
+    int rc = sdyn_extract_batch(c, 1, gray, 0, W, H, stride, kpOut, descOut, cap, nOut);
+    if ((rc == SDYN_OK || rc == SDYN_ERR_CAPACITY) && pyrOut && gray && W > 0 && H > 0) {
+        for (int l = 0; l < c->geom.nlevels; ++l) {
+            if (!pyrOut[l]) continue;
+            int r2 = sdyn_fetch_level(c, 0, l, pyrOut[l], nullptr, nullptr);
+            if (r2 != SDYN_OK) return r2;
+        }
+    }
+    return rc;
+}
+
+int sdyn_device_results(const sdyn_ctx* c, sdyn_device_view* out)
+{
+    if (!c || !out || !c->geomValid) return SDYN_ERR_ARG;
+    std::memset(out, 0, sizeof(*out));
+    out->kp = c->dKp; out->desc = c->dDesc; out->count = c->dCount; out->level_count = c->dLevelCount;
+    out->pyramid = c->dPyr; out->blurred = c->dBlur;
+    out->pyramid_frame_bytes = (size_t)c->geom.frameBytes;
+    out->cap = c->maxKp; out->nlevels = c->geom.nlevels;
+    for (int l = 0; l < c->geom.nlevels; ++l) {
+        const LevelGeom& L = c->geom.L[l];
+        out->level[l].width = L.w; out->level[l].height = L.h; out->level[l].pitch = L.pitch;
+        out->level[l].offset = (size_t)(L.off - (long long)kEdge * L.pitch - kEdge);
+    }
+    return SDYN_OK;
+}
+
+int sdyn_fetch_candidates(sdyn_ctx* c, int frame, int level, int32_t* xyv, int cap, int* nOut)
+{
+    if (!c || !c->geomValid || !nOut) return SDYN_ERR_ARG;
+    if (frame < 0 || frame >= c->maxBatch || level < 0 || level >= c->geom.nlevels)
+        return fail(c, SDYN_ERR_ARG, "sdyn_fetch_candidates: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    /* the octree kernel applies the per-cell threshold fallback and compacts the survivors to the front of
+     * the level's candidate slice; their number is left in dSelCount */
+    const LevelGeom& L = c->geom.L[level];
+    int32_t n = 0;
+    CU(c, cudaMemcpy(&n, c->dSelCount + frame * SDYN_MAX_LEVELS + level, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> k((size_t)std::max(n, 1));
+    CU(c, cudaMemcpy(k.data(), c->dCand + (size_t)frame * c->geom.candPerFrame + L.candOff, sizeof(uint32_t) * n,
+                     cudaMemcpyDeviceToHost));
+    *nOut = n;
+    for (int i = 0; i < std::min(n, cap); ++i) {
+        xyv[3 * i] = (int32_t)(k[i] & 4095);
+        xyv[3 * i + 1] = (int32_t)((k[i] >> 12) & 4095);
+        xyv[3 * i + 2] = (int32_t)(k[i] >> 24);
+    }
+    return n > cap ? SDYN_ERR_CAPACITY : SDYN_OK;
+}
+
+int sdyn_sync(sdyn_ctx* c)
+{
+    if (!c) return SDYN_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SDYN_OK;
+}
+
+long long sdyn_launch_count(const sdyn_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+/* Internal declarations shared by the host side of libsdyn and its CUDA kernels. */
+#pragma once
+#include "../../include/sdyn.h"
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace sdyn {
+
+constexpr int kEdge = SDYN_EDGE;
+constexpr int kFastBorder = kEdge - 3;     /* minBorderX/Y = 16, src/ORBextractor.cc:773-774 */
+constexpr int kRowAlign = 32;              /* interior column 0 of every level row is 32-byte aligned */
+constexpr int kLeftPad = 32;               /* bytes before interior column 0 (19 of them are the border) */
+
+/* Geometry of one level, valid for one input size.  Passed to kernels by value inside Geom. */
+struct LevelGeom {
+    int w, h;                /* level size  (ComputePyramid, src/ORBextractor.cc:1111-1112) */
+    int pitch;               /* row pitch in bytes */
+    int pad0;
+    long long off;           /* byte offset, inside one frame's pyramid block, of interior pixel (0,0) */
+    /* FAST window (ComputeKeyPointsOctTree, src/ORBextractor.cc:773-787) */
+    int fw, fh;              /* maxBorder - minBorder */
+    int nCols, nRows, wCell, hCell;
+    int cellOff;             /* first cell flag of this level in the per-frame flag array */
+    int candOff, candCap;    /* slice of the per-frame candidate array */
+    /* octree (DistributeOctTree, :539-763) */
+    int quota, nIni, nodeCap;
+    float hX;
+    int kpOff;               /* slice of the per-frame level-keypoint scratch (nodeCap entries) */
+    /* keypoint post-processing (:835-846, :1095-1101) */
+    float scale;
+    float patchSize;
+    /* resize tables (level > 0): byte offsets into the table blob */
+    int xtab, ytab;
+};
+
+struct Geom {
+    int nlevels, W, H, pad;
+    long long frameBytes;    /* pyramid block per frame */
+    int cellsPerFrame, candPerFrame, kpPerFrame, maxNodeCap;
+    LevelGeom L[SDYN_MAX_LEVELS];
+};
+
+/* One column / row of the bilinear resize (cv::resize INTER_LINEAR 8-bit path, SURVEY A-2),
+ * indexed by BORDERED destination coordinate so the REFLECT_101 frame is produced in the same pass. */
+struct ResizeTap {
+    int16_t s0, s1;          /* the two source indices */
+    int16_t c0, c1;          /* 11-bit fixed-point coefficients */
+};
+
+struct TileRef { int16_t level, tx, ty, pad; };
+
+struct Candidate {           /* 4 bytes: x:12 | y:12 | score:8, window-relative */
+    uint32_t v;
+};
+
+struct LevelKp {             /* output of the octree stage, per (frame, level, slot) */
+    int16_t x, y;            /* level coordinates (border added) */
+    int32_t score;
+};
+
+}  // namespace sdyn
+
+struct sdyn_ctx {
+    sdyn_orb_params params;
+    sdyn_scale_info scales;
+    int umax[16];
+    int maxW, maxH, maxBatch, device;
+    int maxKp;                         /* per-frame output capacity */
+    cudaStream_t stream;
+    std::string err;
+    long long launches;
+
+    /* geometry for the current image size */
+    sdyn::Geom geom;
+    bool geomValid;
+    std::vector<sdyn::TileRef> fastTiles, blurTiles;
+    sdyn::TileRef* dFastTiles; sdyn::TileRef* dBlurTiles;
+    int nFastTiles, nBlurTiles;
+    uint8_t* dTables; size_t tablesCap;
+
+    /* device buffers sized at create() for (maxW, maxH, maxBatch) */
+    uint8_t* dIn;  size_t inFrameCap;          /* staged input frames (host entry points) */
+    uint8_t* dPyr; uint8_t* dBlur; size_t pyrFrameCap;
+    uint8_t* dCellFlag; int cellCap;           /* per frame */
+    uint32_t* dCand; int32_t* dCandNode; int candCap;   /* per frame */
+    int32_t* dCandCount;                       /* [maxBatch][SDYN_MAX_LEVELS] maxima emitted by FAST */
+    int32_t* dSelCount;                        /* [maxBatch][SDYN_MAX_LEVELS] survivors of the per-cell threshold rule */
+    sdyn::LevelKp* dLevelKp; int levelKpCap;   /* per frame */
+    int32_t* dLevelCount;                      /* [maxBatch][SDYN_MAX_LEVELS] */
+    int32_t* dCount;                           /* [maxBatch] */
+    int32_t* dStatus;                          /* [maxBatch] sticky per-frame error flags */
+    sdyn_keypoint* dKp; uint8_t* dDesc;        /* [maxBatch][maxKp] */
+    /* pinned staging */
+    sdyn_keypoint* hKp; uint8_t* hDesc; int32_t* hCount; int32_t* hStatus;
+};
+
+namespace sdyn {
+
+/* geometry.cpp */
+void compute_scale_info(const sdyn_orb_params& p, sdyn_scale_info& s, int umax[16]);
+/* Fills g and the resize tables for image size W x H.  Returns SDYN_OK or SDYN_ERR_GEOMETRY. */
+int compute_geometry(const sdyn_orb_params& p, const sdyn_scale_info& s, int W, int H,
+                     Geom& g, std::vector<uint8_t>& tables);
+int max_keypoints_per_frame(const sdyn_orb_params& p, const sdyn_scale_info& s, int maxW, int maxH);
+
+/* kernels (each returns the cudaError_t of its launch) */
+cudaError_t launch_level0(const Geom& g, const uint8_t* dIn, size_t inFrameStride, int inRowStride,
+                          uint8_t* dPyr, int nframes, cudaStream_t st);
+cudaError_t launch_resize(const Geom& g, int level, const uint8_t* dTables, uint8_t* dPyr,
+                          int nframes, cudaStream_t st);
+cudaError_t launch_fast(const Geom& g, const TileRef* tiles, int ntiles, const uint8_t* dPyr,
+                        int iniTh, int minTh, uint8_t* dCellFlag, uint32_t* dCand, int32_t* dCandCount,
+                        int nframes, cudaStream_t st);
+cudaError_t launch_octree(const Geom& g, int iniTh, int minTh, const uint8_t* dCellFlag, uint32_t* dCand,
+                          const int32_t* dCandCount, int32_t* dCandNode, int32_t* dSelCount, LevelKp* dLevelKp,
+                          int32_t* dLevelCount, int32_t* dStatus, int nframes, cudaStream_t st);
+cudaError_t launch_blur(const Geom& g, const TileRef* tiles, int ntiles, const uint8_t* dPyr,
+                        uint8_t* dBlur, int nframes, cudaStream_t st);
+cudaError_t launch_orient_describe(const Geom& g, const uint8_t* dPyr, const uint8_t* dBlur,
+                                   const LevelKp* dLevelKp, const int32_t* dLevelCount,
+                                   sdyn_keypoint* dKp, uint8_t* dDesc, int32_t* dCount, int maxKp,
+                                   int nframes, cudaStream_t st);
+size_t octree_smem_bytes(int nodeCap);
+
+constexpr int kFastTileW = 64, kFastTileH = 16;
+constexpr int kBlurTileW = 64, kBlurTileH = 32;
+
+}  // namespace sdyn

@@ -1,0 +1,248 @@
+"""ctypes binding of the sdyn C-ABI (include/sdyn.h) for tests and bench.py.
+
+This is plumbing: it loads slam-dynamic_b200/libsdyn.so (hand-written sm_100a kernels behind a C ABI)
+and raises if the library is missing or a call fails — there is no CPU or eager fallback.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libsdyn.so")
+SYNTH_PATH = os.path.join(_PKG, "synth", "libsdyn_synth.so")
+
+MAX_LEVELS = 16
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+class ScaleInfo(C.Structure):
+    _fields_ = [("nlevels", C.c_int32), ("scale", C.c_float * MAX_LEVELS), ("inv_scale", C.c_float * MAX_LEVELS),
+                ("sigma2", C.c_float * MAX_LEVELS), ("inv_sigma2", C.c_float * MAX_LEVELS),
+                ("features_per_level", C.c_int32 * MAX_LEVELS)]
+
+
+class LevelInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("pitch", C.c_int32), ("reserved", C.c_int32),
+                ("offset", C.c_size_t)]
+
+
+class DeviceView(C.Structure):
+    _fields_ = [("kp", C.c_void_p), ("desc", C.c_void_p), ("count", C.c_void_p), ("level_count", C.c_void_p),
+                ("pyramid", C.c_void_p), ("blurred", C.c_void_p), ("pyramid_frame_bytes", C.c_size_t),
+                ("cap", C.c_int32), ("nlevels", C.c_int32), ("level", LevelInfo * MAX_LEVELS)]
+
+
+class SdynError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sdyn error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Loads libsdyn.so; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libsdyn.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "or `make -C slam-dynamic_b200`")
+        L = C.CDLL(LIB_PATH)
+        L.sdyn_last_error.restype = C.c_char_p
+        L.sdyn_last_error.argtypes = [C.c_void_p]
+        L.sdyn_create.argtypes = [C.POINTER(OrbParams), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.sdyn_destroy.argtypes = [C.c_void_p]
+        L.sdyn_scale_info_get.argtypes = [C.c_void_p, C.POINTER(ScaleInfo)]
+        L.sdyn_max_keypoints.argtypes = [C.c_void_p]
+        L.sdyn_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.sdyn_host_free.argtypes = [C.c_void_p]
+        L.sdyn_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.POINTER(C.c_int), C.c_void_p]
+        L.sdyn_extract_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sdyn_extract_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                                C.c_int, C.c_void_p]
+        L.sdyn_device_results.argtypes = [C.c_void_p, C.POINTER(DeviceView)]
+        L.sdyn_fetch_results.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.sdyn_fetch_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.sdyn_fetch_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.sdyn_sync.argtypes = [C.c_void_p]
+        L.sdyn_launch_count.restype = C.c_longlong
+        L.sdyn_launch_count.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+_synth = None
+
+
+def synth():
+    global _synth
+    if _synth is None:
+        S = C.CDLL(SYNTH_PATH)
+        S.sdyn_synth_frame.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_int]
+        S.sdyn_synth_boxes.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_int]
+        _synth = S
+    return _synth
+
+
+def synth_frame(seq_seed, frame_seed, w, h, nrect, ox=0, oy=0, t=0, out=None):
+    """Seeded integer-only synthetic frame."""
+    if out is None:
+        out = np.empty((h, w), np.uint8)
+    synth().sdyn_synth_frame(seq_seed, frame_seed, w, h, nrect, ox, oy, t, out.ctypes.data, out.strides[0])
+    return out
+
+
+def synth_boxes(seq_seed, w, h, nrect, ox=0, oy=0, t=0, margin=6, cap=64):
+    b = np.zeros((cap, 4), np.float64)
+    n = synth().sdyn_synth_boxes(seq_seed, w, h, nrect, ox, oy, t, margin, b.ctypes.data, cap)
+    return b[:n].copy()
+
+
+class PinnedArray:
+    """numpy view over cudaMallocHost memory (pinned), freed with the object."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        rc = lib().sdyn_host_alloc(C.byref(p), max(nbytes, 1))
+        if rc != 0:
+            raise SdynError(rc, "pinned allocation of %d bytes failed" % nbytes)
+        self.ptr = p
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def __del__(self):
+        if getattr(self, "ptr", None) is not None and self.ptr.value:
+            self.array = None
+            lib().sdyn_host_free(self.ptr)
+            self.ptr = None
+
+
+class Extractor:
+    """Mirror of ORB_SLAM2::ORBextractor (include/ORBextractor.h:45-111) over the C ABI.
+
+    __call__(image) -> (keypoints[KP_DTYPE], descriptors[n,32]) like operator()(image, mask, keypoints,
+    descriptors); GetLevels()/GetScaleFactors()/... return the same values as the reference getters.
+    """
+
+    def __init__(self, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
+                 max_width=1241, max_height=376, max_batch=1, device=0):
+        self._h = C.c_void_p()
+        p = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        rc = lib().sdyn_create(C.byref(p), max_width, max_height, max_batch, device, C.byref(self._h))
+        if rc != 0:
+            raise SdynError(rc, lib().sdyn_last_error(None).decode())
+        self.max_batch = max_batch
+        self.nlevels = nlevels
+        si = ScaleInfo()
+        self._check(lib().sdyn_scale_info_get(self._h, C.byref(si)))
+        self.mvScaleFactor = np.array(si.scale[:nlevels], np.float32)
+        self.mvInvScaleFactor = np.array(si.inv_scale[:nlevels], np.float32)
+        self.mvLevelSigma2 = np.array(si.sigma2[:nlevels], np.float32)
+        self.mvInvLevelSigma2 = np.array(si.inv_sigma2[:nlevels], np.float32)
+        self.mnFeaturesPerLevel = np.array(si.features_per_level[:nlevels], np.int32)
+        self.scaleFactor = float(np.float32(scale_factor))
+        self.cap = lib().sdyn_max_keypoints(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().sdyn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SdynError(rc, lib().sdyn_last_error(self._h).decode())
+
+    # reference getters
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactor(self): return self.scaleFactor
+    def GetScaleFactors(self): return self.mvScaleFactor.copy()
+    def GetInverseScaleFactors(self): return self.mvInvScaleFactor.copy()
+    def GetScaleSigmaSquares(self): return self.mvLevelSigma2.copy()
+    def GetInverseScaleSigmaSquares(self): return self.mvInvLevelSigma2.copy()
+
+    def __call__(self, image, want_pyramid=False):
+        if image is None or image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (ORBextractor.cc:1050)"
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        h, w = image.shape
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n = C.c_int(0)
+        self._check(lib().sdyn_extract(self._h, image.ctypes.data, w, h, image.strides[0], kps.ctypes.data,
+                                       desc.ctypes.data, self.cap, C.byref(n), None))
+        out = kps[:n.value].copy(), desc[:n.value].copy()
+        if want_pyramid:
+            return out + ([self.level(0, l) for l in range(self.nlevels)],)
+        return out
+
+    def extract_batch(self, images, kps=None, desc=None, counts=None):
+        """images: [B,H,W] uint8 (pinned or pageable host memory). Returns (kps[B,cap], desc[B,cap,32], n[B])."""
+        b, h, w = images.shape
+        if kps is None:
+            kps = np.zeros((b, self.cap), KP_DTYPE)
+            desc = np.zeros((b, self.cap, 32), np.uint8)
+            counts = np.zeros(b, np.int32)
+        self._check(lib().sdyn_extract_batch(self._h, b, images.ctypes.data, images.strides[0], w, h,
+                                             images.strides[1], kps.ctypes.data, desc.ctypes.data, self.cap,
+                                             counts.ctypes.data))
+        return kps, desc, counts
+
+    def extract_batch_device(self, dptr, nframes, frame_stride, w, h, row_stride, stream=None):
+        """Enqueue extraction of frames already in device memory (dptr = integer device address)."""
+        self._check(lib().sdyn_extract_batch_device(self._h, nframes, C.c_void_p(dptr), frame_stride, w, h,
+                                                    row_stride, C.c_void_p(stream) if stream else None))
+
+    def fetch(self, nframes, stream=None, kps=None, desc=None, counts=None):
+        if kps is None:
+            kps = np.zeros((nframes, self.cap), KP_DTYPE)
+            desc = np.zeros((nframes, self.cap, 32), np.uint8)
+            counts = np.zeros(nframes, np.int32)
+        self._check(lib().sdyn_fetch_results(self._h, nframes, kps.ctypes.data, desc.ctypes.data, self.cap,
+                                             counts.ctypes.data, C.c_void_p(stream) if stream else None))
+        return kps, desc, counts
+
+    def device_view(self):
+        v = DeviceView()
+        self._check(lib().sdyn_device_results(self._h, C.byref(v)))
+        return v
+
+    def level(self, frame, l):
+        """Bordered pyramid level l of `frame` of the last call: (h+38, w+38) uint8 (mvImagePyramid[l])."""
+        v = self.device_view()
+        w, h = v.level[l].width, v.level[l].height
+        out = np.empty((h + 38, w + 38), np.uint8)
+        self._check(lib().sdyn_fetch_level(self._h, frame, l, out.ctypes.data, None, None))
+        return out
+
+    def candidates(self, frame, l):
+        n = C.c_int(0)
+        v = self.device_view()
+        cap = v.level[l].width * v.level[l].height // 4 + 16
+        out = np.zeros((cap, 3), np.int32)
+        self._check(lib().sdyn_fetch_candidates(self._h, frame, l, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def sync(self):
+        self._check(lib().sdyn_sync(self._h))
+
+    def launch_count(self):
+        return lib().sdyn_launch_count(self._h)
