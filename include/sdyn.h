@@ -143,6 +143,18 @@ int sdyn_sync(sdyn_ctx* ctx);
 /* Number of kernel launches enqueued by this context since creation (bench.py's gpu_launches). */
 long long sdyn_launch_count(const sdyn_ctx* ctx);
 
+/* ---- per-stage device timing (CUDA events on the launching stream) -------------------------------
+ * While enabled, every enqueue brackets each stage with events; sdyn_profile_read synchronises and
+ * returns the accumulated milliseconds and launch counts since the last read. */
+enum { SDYN_STAGE_PYRAMID = 0, SDYN_STAGE_FAST, SDYN_STAGE_OCTREE, SDYN_STAGE_BLUR, SDYN_STAGE_DESCRIBE,
+       SDYN_STAGE_MATCH, SDYN_STAGE_DYNAMIC, SDYN_STAGE_COUNT };
+typedef struct {
+    double ms[SDYN_STAGE_COUNT];
+    long long calls[SDYN_STAGE_COUNT];
+} sdyn_stage_times;
+int sdyn_profile_enable(sdyn_ctx* ctx, int on);
+int sdyn_profile_read(sdyn_ctx* ctx, sdyn_stage_times* out);
+
 #ifdef __cplusplus
 }
 #endif

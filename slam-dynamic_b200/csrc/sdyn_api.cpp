@@ -69,22 +69,72 @@ int ensure_geometry(sdyn_ctx* c, int W, int H)
     return SDYN_OK;
 }
 
+cudaEvent_t take_event(sdyn_ctx* c)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->evPool.empty()) { e = c->evPool.back(); c->evPool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
+/* Collects finished spans into c->acc (synchronises on the events). */
+void drain_spans(sdyn_ctx* c)
+{
+    for (auto& s : c->spans) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+            c->acc.ms[s.stage] += ms;
+            c->acc.calls[s.stage] += 1;
+        }
+        c->evPool.push_back(s.a); c->evPool.push_back(s.b);
+    }
+    c->spans.clear();
+}
+
+struct StageTimer {
+    sdyn_ctx* c; cudaStream_t st; int stage; cudaEvent_t a;
+    StageTimer(sdyn_ctx* c_, cudaStream_t st_, int stage_) : c(c_), st(st_), stage(stage_), a(nullptr)
+    {
+        if (c->profiling) { a = take_event(c); cudaEventRecord(a, st); }
+    }
+    ~StageTimer()
+    {
+        if (a) { cudaEvent_t b = take_event(c); cudaEventRecord(b, st); c->spans.push_back({a, b, stage}); }
+    }
+};
+
 /* Enqueues the whole extraction pipeline for nframes frames already resident in device memory. */
 int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride, int rowStride, cudaStream_t st)
 {
     const Geom& g = c->geom;
     const sdyn_orb_params& p = c->params;
-    CU(c, cudaMemsetAsync(c->dCandCount, 0, sizeof(int32_t) * SDYN_MAX_LEVELS * nframes, st));
-    CU(c, cudaMemsetAsync(c->dCellFlag, 0, (size_t)g.cellsPerFrame * nframes, st));
-    CU(c, launch_level0(g, dGray, frameStride, rowStride, c->dPyr, nframes, st));
-    for (int l = 1; l < g.nlevels; ++l) CU(c, launch_resize(g, l, c->dTables, c->dPyr, nframes, st));
-    CU(c, launch_fast(g, c->dFastTiles, c->nFastTiles, c->dPyr, p.ini_th_fast, p.min_th_fast, c->dCellFlag,
-                      c->dCand, c->dCandCount, nframes, st));
-    CU(c, launch_octree(g, p.ini_th_fast, p.min_th_fast, c->dCellFlag, c->dCand, c->dCandCount, c->dCandNode,
-                        c->dSelCount, c->dLevelKp, c->dLevelCount, c->dStatus, nframes, st));
-    CU(c, launch_blur(g, c->dBlurTiles, c->nBlurTiles, c->dPyr, c->dBlur, nframes, st));
-    CU(c, launch_orient_describe(g, c->dPyr, c->dBlur, c->dLevelKp, c->dLevelCount, c->dKp, c->dDesc, c->dCount,
-                                 c->maxKp, nframes, st));
+    if (c->spans.size() > 4096) drain_spans(c);
+    {
+        StageTimer t(c, st, SDYN_STAGE_PYRAMID);
+        CU(c, cudaMemsetAsync(c->dCandCount, 0, sizeof(int32_t) * SDYN_MAX_LEVELS * nframes, st));
+        CU(c, cudaMemsetAsync(c->dCellFlag, 0, (size_t)g.cellsPerFrame * nframes, st));
+        CU(c, launch_level0(g, dGray, frameStride, rowStride, c->dPyr, nframes, st));
+        for (int l = 1; l < g.nlevels; ++l) CU(c, launch_resize(g, l, c->dTables, c->dPyr, nframes, st));
+    }
+    {
+        StageTimer t(c, st, SDYN_STAGE_FAST);
+        CU(c, launch_fast(g, c->dFastTiles, c->nFastTiles, c->dPyr, p.ini_th_fast, p.min_th_fast, c->dCellFlag,
+                          c->dCand, c->dCandCount, nframes, st));
+    }
+    {
+        StageTimer t(c, st, SDYN_STAGE_OCTREE);
+        CU(c, launch_octree(g, p.ini_th_fast, p.min_th_fast, c->dCellFlag, c->dCand, c->dCandCount, c->dCandNode,
+                            c->dSelCount, c->dLevelKp, c->dLevelCount, c->dStatus, nframes, st));
+    }
+    {
+        StageTimer t(c, st, SDYN_STAGE_BLUR);
+        CU(c, launch_blur(g, c->dBlurTiles, c->nBlurTiles, c->dPyr, c->dBlur, nframes, st));
+    }
+    {
+        StageTimer t(c, st, SDYN_STAGE_DESCRIBE);
+        CU(c, launch_orient_describe(g, c->dPyr, c->dBlur, c->dLevelKp, c->dLevelCount, c->dKp, c->dDesc, c->dCount,
+                                     c->maxKp, nframes, st));
+    }
     c->launches += 2 + 1 + (g.nlevels - 1) + 4;
     return SDYN_OK;
 }
@@ -96,6 +146,8 @@ void free_all(sdyn_ctx* c)
     cudaFree(c->dLevelKp); cudaFree(c->dLevelCount); cudaFree(c->dCount); cudaFree(c->dStatus); cudaFree(c->dKp);
     cudaFree(c->dDesc);
     cudaFreeHost(c->hKp); cudaFreeHost(c->hDesc); cudaFreeHost(c->hCount); cudaFreeHost(c->hStatus);
+    for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : c->evPool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -166,7 +218,7 @@ int sdyn_create(const sdyn_orb_params* params, int maxW, int maxH, int maxBatch,
         free_all(c); delete c;
         return fail(nullptr, ce == cudaErrorMemoryAllocation ? SDYN_ERR_NOMEM : SDYN_ERR_CUDA, msg);
     }
-    c->geomValid = false;
+    c->geomValid = false; c->profiling = false; std::memset(&c->acc, 0, sizeof(c->acc));
     *out = c;
     return SDYN_OK;
 }
@@ -342,5 +394,25 @@ int sdyn_sync(sdyn_ctx* c)
 }
 
 long long sdyn_launch_count(const sdyn_ctx* c) { return c ? c->launches : 0; }
+
+int sdyn_profile_enable(sdyn_ctx* c, int on)
+{
+    if (!c) return SDYN_ERR_ARG;
+    cudaSetDevice(c->device);
+    drain_spans(c);
+    c->profiling = on != 0;
+    std::memset(&c->acc, 0, sizeof(c->acc));
+    return SDYN_OK;
+}
+
+int sdyn_profile_read(sdyn_ctx* c, sdyn_stage_times* out)
+{
+    if (!c || !out) return SDYN_ERR_ARG;
+    cudaSetDevice(c->device);
+    drain_spans(c);
+    *out = c->acc;
+    std::memset(&c->acc, 0, sizeof(c->acc));
+    return SDYN_OK;
+}
 
 }  // extern "C"

@@ -92,6 +92,12 @@ struct sdyn_ctx {
     int32_t* dCount;                           /* [maxBatch] */
     int32_t* dStatus;                          /* [maxBatch] sticky per-frame error flags */
     sdyn_keypoint* dKp; uint8_t* dDesc;        /* [maxBatch][maxKp] */
+    /* per-stage profiling */
+    bool profiling;
+    std::vector<cudaEvent_t> evPool;           /* free events */
+    struct Span { cudaEvent_t a, b; int stage; };
+    std::vector<Span> spans;                   /* recorded, not yet read */
+    sdyn_stage_times acc;
     /* pinned staging */
     sdyn_keypoint* hKp; uint8_t* hDesc; int32_t* hCount; int32_t* hStatus;
 };

@@ -39,6 +39,13 @@ class DeviceView(C.Structure):
                 ("cap", C.c_int32), ("nlevels", C.c_int32), ("level", LevelInfo * MAX_LEVELS)]
 
 
+STAGES = ["pyramid", "fast", "octree", "blur", "describe", "match", "dynamic"]
+
+
+class StageTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * len(STAGES)), ("calls", C.c_longlong * len(STAGES))]
+
+
 class SdynError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("sdyn error %d: %s" % (code, msg))
@@ -75,6 +82,8 @@ def lib():
         L.sdyn_fetch_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.sdyn_fetch_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.sdyn_sync.argtypes = [C.c_void_p]
+        L.sdyn_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.sdyn_profile_read.argtypes = [C.c_void_p, C.POINTER(StageTimes)]
         L.sdyn_launch_count.restype = C.c_longlong
         L.sdyn_launch_count.argtypes = [C.c_void_p]
         _lib = L
@@ -243,6 +252,15 @@ class Extractor:
 
     def sync(self):
         self._check(lib().sdyn_sync(self._h))
+
+    def profile(self, on):
+        self._check(lib().sdyn_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """{stage: (ms, calls)} accumulated since the last read (device time, CUDA events on the stream)."""
+        t = StageTimes()
+        self._check(lib().sdyn_profile_read(self._h, C.byref(t)))
+        return {s: (t.ms[i], t.calls[i]) for i, s in enumerate(STAGES)}
 
     def launch_count(self):
         return lib().sdyn_launch_count(self._h)
