@@ -143,6 +143,107 @@ int sdyn_sync(sdyn_ctx* ctx);
 /* Number of kernel launches enqueued by this context since creation (bench.py's gpu_launches). */
 long long sdyn_launch_count(const sdyn_ctx* ctx);
 
+/* ---- ORBmatcher ----------------------------------------------------------------------------------
+ * Pointers of the reference become indices across the ABI: Frame::mvpMapPoints[i] is `assign[i]`
+ * (-1 = NULL, otherwise the index of the query that claimed keypoint i) and "the occupant has
+ * Observations() > 0" (src/ORBmatcher.cc:87-89, :1560-1562) is `locked[i]`.  Both arrays are in/out:
+ * the adapter fills them from the frame before the call and maps indices back to MapPoint* after it. */
+
+/* What the searches read from a Frame (include/Frame.h:49-211). */
+typedef struct {
+    int32_t n;                      /* N */
+    int32_t nlevels;                /* mnScaleLevels */
+    const sdyn_keypoint* keys;      /* mvKeys */
+    const sdyn_keypoint* keys_un;   /* mvKeysUn */
+    const uint8_t* desc;            /* mDescriptors, n x 32 */
+    const float* u_right;           /* mvuRight, or NULL (monocular: all -1) */
+    const float* scale_factors;     /* mvScaleFactors */
+    float min_x, min_y, max_x, max_y;   /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+    float fx, fy, cx, cy, bf, b;    /* fx, fy, cx, cy, mbf, mb */
+    float tcw[12];                  /* rows 0..2 of mTcw, row-major */
+} sdyn_frame_view;
+
+/* MapPoint fields read by SearchByProjection(Frame&, vector<MapPoint*>&, th), src/ORBmatcher.cc:45-129 */
+typedef struct {
+    float proj_x, proj_y, proj_xr;  /* mTrackProjX, mTrackProjY, mTrackProjXR */
+    float view_cos;                 /* mTrackViewCos */
+    int32_t level;                  /* mnTrackScaleLevel */
+    uint8_t track_in_view, bad, obs_positive, pad;   /* mbTrackInView, isBad(), Observations() > 0 */
+    uint8_t desc[32];               /* GetDescriptor() */
+} sdyn_mappoint_query;
+
+/* Per keypoint of LastFrame, read by SearchByProjection(Cur, Last, th, bMono), src/ORBmatcher.cc:1485-1627 */
+typedef struct {
+    uint8_t has_mp, outlier, obs_positive, pad;   /* mvpMapPoints[i] != NULL, mvbOutlier[i], Observations() > 0 */
+    float world[3];                 /* pMP->GetWorldPos() */
+    uint8_t desc[32];               /* pMP->GetDescriptor() */
+} sdyn_last_point;
+
+/* DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>, Thirdparty/DBoW2/DBoW2/FeatureVector.h:22)
+ * flattened to CSR with ascending node ids. */
+typedef struct {
+    int32_t nnodes;
+    const uint32_t* node_id;
+    const int32_t* offset;          /* nnodes + 1 */
+    const uint32_t* index;
+} sdyn_feature_vector;
+
+/* ORBmatcher::DescriptorDistance (static, src/ORBmatcher.cc:1804-1820): 256-bit Hamming distance of one pair.
+ * Host-side popcount — the static member is called pair-at-a-time by MapPoint.cc:281 and friends; the
+ * searches below do their distance work on the device. */
+int sdyn_hamming(const uint8_t* a, const uint8_t* b);
+
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th),
+ * src/ORBmatcher.cc:45-129.  *nmatches = return value. */
+int sdyn_match_projection_map(sdyn_ctx* ctx, const sdyn_frame_view* frame, const sdyn_mappoint_query* mps,
+                              int nmp, float th, float nnratio, int32_t* assign, uint8_t* locked, int* nmatches);
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+ * src/ORBmatcher.cc:1485-1627, and the fork's overload with two extra vector<cv::Point2f>& outputs
+ * (:407-559) when pairs != NULL: pairs receives (last.x, last.y, cur.x, cur.y) per accepted match, in
+ * query order, appended before the rotation cull; capacity 4 * last->n floats. */
+int sdyn_match_projection_frame(sdyn_ctx* ctx, const sdyn_frame_view* cur, const sdyn_frame_view* last,
+                                const sdyn_last_point* last_points, float th, int mono, int check_orientation,
+                                int32_t* assign, uint8_t* locked, int* nmatches, float* pairs, int* npairs);
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:562-677.
+ * prev_matched: f1->n x 2 floats, updated in place; matches12: f1->n. */
+int sdyn_match_init(sdyn_ctx* ctx, const sdyn_frame_view* f1, const sdyn_frame_view* f2, float* prev_matched,
+                    int32_t* matches12, int window_size, float nnratio, int check_orientation, int* nmatches);
+
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches), src/ORBmatcher.cc:159-288.
+ * kf_valid[i] = keyframe keypoint i has a non-bad MapPoint; assign[f_idx] = kf_idx | -1 (f->n entries). */
+int sdyn_match_bow(sdyn_ctx* ctx, const sdyn_frame_view* kf, const uint8_t* kf_valid,
+                   const sdyn_feature_vector* kf_fv, const sdyn_frame_view* f, const sdyn_feature_vector* f_fv,
+                   float nnratio, int check_orientation, int32_t* assign, int* nmatches);
+
+/* ---- dynamic-keypoint rejection ---------------------------------------------------------------------
+ * Frame::firstSeparate's keypoint-in-box test (src/Frame.cc:555-572): bit b of mask[i] is set iff
+ * cv::Rect2d boxes[b] contains keys[i].pt (x <= px < x+w, y <= py < y+h, doubles).  nboxes <= 64.
+ * The reorder / per-box bookkeeping that follows is host code in the Frame adapter. */
+int sdyn_dyn_box_mask(sdyn_ctx* ctx, const sdyn_keypoint* keys, int n, const double* boxes_xywh, int nboxes,
+                      uint64_t* mask);
+
+/* One (current box, reference box) pair of Tracking::Separate (src/Tracking.cc:1093-1239). */
+typedef struct {
+    int32_t nq, nt;                 /* keypoints in the current / reference box */
+    const uint8_t* q_desc;          /* mdynDescriptors[n_box], nq x 32 */
+    const uint8_t* t_desc;          /* mRefFrame->mdynDescriptors[ref_idx], nt x 32 */
+    const float* q_xy;              /* mvdynKeysUn[n_box][k].pt, nq x 2 */
+    const float* t_xy;              /* nt x 2 */
+    int32_t* match_query;           /* out, capacity nq: cv::DMatch::queryIdx of match m */
+    int32_t* match_train;           /* out: trainIdx */
+    int32_t* match_dist;            /* out: Hamming distance */
+    int32_t* false_dyn;             /* out: classifyF/H result per match: queryIdx (static) or -1 */
+    int32_t nmatches;               /* out */
+} sdyn_box_pair;
+
+/* cv::BFMatcher(NORM_HAMMING, crossCheck=true).match (Tracking.cc:1096,1122) followed by classifyF
+ * (mode 0, F21, threshold 5.841, Tracking.cc:1311-1367) or classifyH (mode 1, H21 and its inverse,
+ * threshold 5.991, :1241-1309) for every pair.  m3x3: row-major float.  The >=3 / 20 % gates and the box
+ * status logic stay in the adapter. */
+int sdyn_dyn_separate(sdyn_ctx* ctx, sdyn_box_pair* pairs, int npairs, const float* m3x3, int mode);
+
 /* ---- per-stage device timing (CUDA events on the launching stream) -------------------------------
  * While enabled, every enqueue brackets each stage with events; sdyn_profile_read synchronises and
  * returns the accumulated milliseconds and launch counts since the last read. */

@@ -2,6 +2,9 @@
  * Flat C entry points so tests/ and bench.py's cpu_baseline leg can drive the oracle through ctypes. */
 #include "orc_prims.h"
 #include "orc_extractor.h"
+#include "orc_matcher.h"
+#include "orc_dynamic.h"
+#include "../include/sdyn.h"   /* POD layouts of the C ABI only (no product code is linked) */
 #include <cstring>
 #include <algorithm>
 
@@ -74,5 +77,147 @@ float orc_ic_angle(const uint8_t* center, int stride)
 { static Extractor E(1000, 1.2f, 8, 20, 7); return ic_angle(center, stride, E.umax); }
 
 void orc_orb_descriptor(float angle, const uint8_t* center, int stride, uint8_t* out) { orb_descriptor(angle, center, stride, out); }
+
+/* ---- matchers ------------------------------------------------------------------------------------ */
+static_assert(sizeof(MapPointQuery) == sizeof(sdyn_mappoint_query), "layout");
+static_assert(sizeof(LastFramePoint) == sizeof(sdyn_last_point), "layout");
+static_assert(sizeof(KeyPoint) == sizeof(sdyn_keypoint), "layout");
+
+static FrameView view_of(const sdyn_frame_view* v)
+{
+    FrameView f;
+    f.N = v->n; f.nlevels = v->nlevels;
+    f.keys = reinterpret_cast<const KeyPoint*>(v->keys);
+    f.keysUn = reinterpret_cast<const KeyPoint*>(v->keys_un);
+    f.desc = v->desc; f.uRight = v->u_right; f.scaleFactors = v->scale_factors;
+    f.minX = v->min_x; f.minY = v->min_y; f.maxX = v->max_x; f.maxY = v->max_y;
+    f.fx = v->fx; f.fy = v->fy; f.cx = v->cx; f.cy = v->cy; f.bf = v->bf; f.b = v->b;
+    for (int i = 0; i < 12; ++i) f.Tcw[i] = v->tcw[i];
+    grid_bounds(f);
+    return f;
+}
+
+int orc_hamming(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+/* Frame::GetFeaturesInArea on a freshly built grid (stage-level test of the grid semantics) */
+int orc_features_in_area(const sdyn_frame_view* v, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap)
+{
+    FrameView f = view_of(v); Grid g; assign_features_to_grid(f, g);
+    std::vector<int> r_ = features_in_area(f, g, x, y, r, minLevel, maxLevel);
+    for (int i = 0; i < (int)r_.size() && i < cap; ++i) out[i] = r_[i];
+    return (int)r_.size();
+}
+
+int orc_match_projection_map(const sdyn_frame_view* v, const sdyn_mappoint_query* mps, int nmp, float th, float nnratio,
+                             int32_t* assign, uint8_t* locked)
+{
+    FrameView f = view_of(v); Grid g; assign_features_to_grid(f, g);
+    return search_by_projection_map(f, g, reinterpret_cast<const MapPointQuery*>(mps), nmp, th, nnratio, assign, locked);
+}
+
+int orc_match_projection_frame(const sdyn_frame_view* cur, const sdyn_frame_view* last, const sdyn_last_point* lp, float th,
+                               int mono, int checkOri, int32_t* assign, uint8_t* locked, float* pairs, int* npairs)
+{
+    FrameView c = view_of(cur), l = view_of(last); Grid g; assign_features_to_grid(c, g);
+    std::vector<float> pr;
+    int n = search_by_projection_frame(c, g, l, reinterpret_cast<const LastFramePoint*>(lp), th, mono != 0, checkOri != 0,
+                                       assign, locked, pairs ? &pr : nullptr);
+    if (pairs) { std::copy(pr.begin(), pr.end(), pairs); if (npairs) *npairs = (int)pr.size() / 4; }
+    return n;
+}
+
+int orc_match_init(const sdyn_frame_view* f1, const sdyn_frame_view* f2, float* prev, int32_t* m12, int window, float nnratio,
+                   int checkOri)
+{
+    FrameView a = view_of(f1), b = view_of(f2); Grid g; assign_features_to_grid(b, g);
+    return search_for_initialization(a, b, g, prev, m12, window, nnratio, checkOri != 0);
+}
+
+int orc_match_bow(const sdyn_frame_view* kf, const uint8_t* kfValid, const sdyn_feature_vector* fa, const sdyn_frame_view* f,
+                  const sdyn_feature_vector* fb, float nnratio, int checkOri, int32_t* assign)
+{
+    FrameView a = view_of(kf), b = view_of(f);
+    FeatureVec va{fa->nnodes, fa->node_id, fa->offset, fa->index}, vb{fb->nnodes, fb->node_id, fb->offset, fb->index};
+    return search_by_bow(a, kfValid, va, b, vb, nnratio, checkOri != 0, assign);
+}
+
+/* ---- dynamic ----------------------------------------------------------------------------------- */
+void orc_box_mask(const sdyn_keypoint* keys, int n, const double* boxes, int nboxes, uint64_t* mask)
+{
+    for (int i = 0; i < n; ++i) {
+        uint64_t m = 0;
+        for (int b = 0; b < nboxes; ++b) {
+            const double x = boxes[4 * b], y = boxes[4 * b + 1], w = boxes[4 * b + 2], h = boxes[4 * b + 3];
+            const double px = keys[i].x, py = keys[i].y;
+            if (x <= px && px < x + w && y <= py && py < y + h) m |= 1ull << b;
+        }
+        mask[i] = m;
+    }
+}
+
+void orc_separate_pairs(sdyn_box_pair* pairs, int npairs, const float* M, int mode)
+{
+    for (int p = 0; p < npairs; ++p) {
+        sdyn_box_pair& P = pairs[p];
+        std::vector<Match> m = bf_match_crosscheck(P.q_desc, P.nq, P.t_desc, P.nt);
+        std::vector<int> fd(m.size(), -1);
+        if (mode == 1) classify_h(M, P.q_xy, P.t_xy, m, fd); else classify_f(M, P.q_xy, P.t_xy, m, fd);
+        P.nmatches = (int)m.size();
+        for (size_t i = 0; i < m.size(); ++i) {
+            P.match_query[i] = m[i].queryIdx; P.match_train[i] = m[i].trainIdx; P.match_dist[i] = m[i].dist; P.false_dyn[i] = fd[i];
+        }
+    }
+}
+
+void orc_invert3x3(const float* m, float* out) { invert3x3(m, out); }
+
+/* Frame::boxTrack on flat arrays.  boxes: in/out (capacity cap), returns the new box count. */
+int orc_box_track(double* boxes, int nboxes, int cap, const double* lastObjects, const int* lastBoxIdx, const uint8_t* lastOmit,
+                  const double* lastVel, int nlast, int imgW, int imgH, int* boxIdx, uint8_t* omit, double* vel)
+{
+    std::vector<Rect> b(nboxes);
+    for (int i = 0; i < nboxes; ++i) b[i] = {boxes[4 * i], boxes[4 * i + 1], boxes[4 * i + 2], boxes[4 * i + 3]};
+    BoxState last, cur;
+    for (int i = 0; i < nlast; ++i) {
+        last.objects.push_back({lastObjects[4 * i], lastObjects[4 * i + 1], lastObjects[4 * i + 2], lastObjects[4 * i + 3]});
+        last.box_idx.push_back(lastBoxIdx[i]); last.omit.push_back(lastOmit[i]);
+        last.vel.push_back(lastVel[2 * i]); last.vel.push_back(lastVel[2 * i + 1]);
+    }
+    box_track(b, last, imgW, imgH, cur);
+    const int n = std::min((int)b.size(), cap);
+    for (int i = 0; i < n; ++i) {
+        boxes[4 * i] = b[i].x; boxes[4 * i + 1] = b[i].y; boxes[4 * i + 2] = b[i].w; boxes[4 * i + 3] = b[i].h;
+        boxIdx[i] = cur.box_idx[i]; omit[i] = cur.omit[i]; vel[2 * i] = cur.vel[2 * i]; vel[2 * i + 1] = cur.vel[2 * i + 1];
+    }
+    return (int)b.size();
+}
+
+/* Frame::firstSeparate + tail split on flat arrays.
+ *   boxes/boxIdx: in/out, compacted exactly as the reference erases them; returns the remaining box count.
+ *   order[N]: new keypoint order; classId[N] (per ORIGINAL index); *nDyn = N_d;
+ *   dynBox/dynKey: flattened (box, original keypoint index) pairs of the per-box arrays, *nDynPairs of them,
+ *   in push order per box (box-major). */
+int orc_first_separate(const sdyn_keypoint* keys, int N, double* boxes, int* boxIdx, int nboxes, int* order, int* classId,
+                       int* nDyn, int* dynBox, int* dynKey, int cap, int* nDynPairs)
+{
+    std::vector<Rect> b(nboxes);
+    BoxState cur;
+    for (int i = 0; i < nboxes; ++i) {
+        b[i] = {boxes[4 * i], boxes[4 * i + 1], boxes[4 * i + 2], boxes[4 * i + 3]};
+        cur.box_idx.push_back(boxIdx[i]); cur.omit.push_back(0); cur.vel.push_back(0); cur.vel.push_back(0);
+    }
+    SplitResult R = first_separate(reinterpret_cast<const KeyPoint*>(keys), N, b, cur);
+    for (int i = 0; i < N; ++i) { order[i] = R.order[i]; classId[i] = R.class_id[i]; }
+    *nDyn = R.N_d;
+    int k = 0;
+    for (size_t bx = 0; bx < R.dynKeys.size(); ++bx)
+        for (int id : R.dynKeys[bx]) { if (k < cap) { dynBox[k] = (int)bx; dynKey[k] = id; } ++k; }
+    *nDynPairs = k;
+    for (size_t i = 0; i < b.size(); ++i) {
+        boxes[4 * i] = b[i].x; boxes[4 * i + 1] = b[i].y; boxes[4 * i + 2] = b[i].w; boxes[4 * i + 3] = b[i].h;
+        boxIdx[i] = cur.box_idx[i];
+    }
+    return (int)b.size();
+}
 
 }  // extern "C"

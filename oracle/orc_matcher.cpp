@@ -1,0 +1,331 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY (see orc_prims.h).
+ * Restatement of the hot-path ORBmatcher searches and Frame grid (reference lines cited per function).
+ * The reference has no tests or golden vectors for these: parity is pinned by the literal,
+ * line-by-line structure below plus brute-force cross-checks in tests/test_oracle_matcher.py.
+ * Float arithmetic is evaluated without FMA contraction (build flag -ffp-contract=off, Appendix B-3). */
+#include "orc_matcher.h"
+#include <algorithm>
+#include <climits>
+#include <cmath>
+
+namespace orc {
+
+/* ORBmatcher.cc:1804-1820 (SWAR popcount over 8 x 32 bit) */
+int descriptor_distance(const uint8_t* a, const uint8_t* b)
+{
+    const uint32_t* pa = reinterpret_cast<const uint32_t*>(a);
+    const uint32_t* pb = reinterpret_cast<const uint32_t*>(b);
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t v = pa[i] ^ pb[i];
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+    }
+    return dist;
+}
+
+/* Frame.cc:383-385 */
+void grid_bounds(FrameView& f)
+{
+    f.gridWInv = static_cast<float>(GRID_COLS) / static_cast<float>(f.maxX - f.minX);
+    f.gridHInv = static_cast<float>(GRID_ROWS) / static_cast<float>(f.maxY - f.minY);
+}
+
+/* Frame.cc:790-800 */
+static bool pos_in_grid(const FrameView& f, const KeyPoint& kp, int& px, int& py)
+{
+    px = (int)std::round((kp.x - f.minX) * f.gridWInv);
+    py = (int)std::round((kp.y - f.minY) * f.gridHInv);
+    return !(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS);
+}
+
+/* Frame.cc:463-478 (from = 0) and UpdateFeaturesToGrid :643-653 (from = N_ori) */
+void assign_features_to_grid(const FrameView& f, Grid& g, int from)
+{
+    for (int i = from; i < f.N; ++i) {
+        int px, py;
+        if (pos_in_grid(f, f.keysUn[i], px, py)) g.cell[px][py].push_back(i);
+    }
+}
+
+/* Frame.cc:735-788 */
+std::vector<int> features_in_area(const FrameView& f, const Grid& g, float x, float y, float r,
+                                  int minLevel, int maxLevel)
+{
+    std::vector<int> out;
+    const int nMinCellX = std::max(0, (int)std::floor((x - f.minX - r) * f.gridWInv));
+    if (nMinCellX >= GRID_COLS) return out;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - f.minX + r) * f.gridWInv));
+    if (nMaxCellX < 0) return out;
+    const int nMinCellY = std::max(0, (int)std::floor((y - f.minY - r) * f.gridHInv));
+    if (nMinCellY >= GRID_ROWS) return out;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - f.minY + r) * f.gridHInv));
+    if (nMaxCellY < 0) return out;
+    const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+        for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+            for (int id : g.cell[ix][iy]) {
+                const KeyPoint& kp = f.keysUn[id];
+                if (checkLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                const float dx = kp.x - x, dy = kp.y - y;
+                if (std::fabs(dx) < r && std::fabs(dy) < r) out.push_back(id);
+            }
+    return out;
+}
+
+/* ORBmatcher.cc:1758-1799 */
+void compute_three_maxima(const int* h, int L, int& ind1, int& ind2, int& ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; ++i) {
+        const int s = h[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+static inline int rot_bin(float rot)
+{
+    const float factor = 1.0f / HISTO_LENGTH;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+/* ORBmatcher.cc:45-129 */
+int search_by_projection_map(const FrameView& F, const Grid& g, const MapPointQuery* mps, int nmp, float th,
+                             float nnratio, int32_t* assign, uint8_t* locked)
+{
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    for (int iMP = 0; iMP < nmp; ++iMP) {
+        const MapPointQuery& mp = mps[iMP];
+        if (!mp.trackInView) continue;
+        if (mp.bad) continue;
+        const int level = mp.level;
+        float r = ((double)mp.viewCos > 0.998) ? 2.5f : 4.0f;      /* RadiusByViewingCos :131-137 */
+        if (bFactor) r *= th;
+        const float win = r * F.scaleFactors[level];
+        const std::vector<int> cand = features_in_area(F, g, mp.projX, mp.projY, win, level - 1, level);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : cand) {
+            if (assign[idx] != -1 && locked[idx]) continue;       /* occupant with Observations() > 0 */
+            if (F.uRight && F.uRight[idx] > 0) {
+                const float er = std::fabs(mp.projXR - F.uRight[idx]);
+                if (er > win) continue;
+            }
+            const int dist = descriptor_distance(mp.desc, F.desc + 32 * (size_t)idx);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = F.keysUn[idx].octave;
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = F.keysUn[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            assign[bestIdx] = iMP;
+            locked[bestIdx] = mp.obsPositive;
+            ++nmatches;
+        }
+    }
+    return nmatches;
+}
+
+/* y = R*x + t the way cv::Mat evaluates `R*x+t` for 3x3 * 3x1 CV_32F: float products summed left to
+ * right, then the addend (pinned against cv2.gemm in tests/test_oracle_matcher.py). */
+static inline void rx_plus_t(const float* T, const float* x, float* y)
+{
+    for (int r = 0; r < 3; ++r) {
+        const float s = T[4 * r] * x[0] + T[4 * r + 1] * x[1] + T[4 * r + 2] * x[2];
+        y[r] = s + T[4 * r + 3];
+    }
+}
+
+/* tlc of ORBmatcher.cc:1497-1503: twc = -Rcw^T tcw (generic gemm path: double accumulation, alpha = -1),
+ * tlc = Rlw twc + tlw (3x3 small-matrix path). */
+void motion_tlc(const float* Tcw, const float* Tlw, float* tlc)
+{
+    float twc[3];
+    for (int r = 0; r < 3; ++r) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += (double)Tcw[4 * k + r] * (double)Tcw[4 * k + 3];
+        twc[r] = (float)(-1.0 * s);
+    }
+    rx_plus_t(Tlw, twc, tlc);
+}
+
+/* ORBmatcher.cc:1485-1627 / :407-559 */
+int search_by_projection_frame(const FrameView& Cur, const Grid& gCur, const FrameView& Last,
+                               const LastFramePoint* lp, float th, bool mono, bool checkOri,
+                               int32_t* assign, uint8_t* locked, std::vector<float>* pairs)
+{
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    float tlc[3];
+    motion_tlc(Cur.Tcw, Last.Tcw, tlc);
+    const bool bForward = tlc[2] > Cur.b && !mono;
+    const bool bBackward = -tlc[2] > Cur.b && !mono;
+
+    for (int i = 0; i < Last.N; ++i) {
+        if (!lp[i].hasMP) continue;
+        if (lp[i].outlier) continue;
+        float pc[3];
+        rx_plus_t(Cur.Tcw, lp[i].world, pc);
+        const float xc = pc[0], yc = pc[1];
+        const float invzc = (float)(1.0 / pc[2]);
+        if (invzc < 0) continue;
+        const float u = Cur.fx * xc * invzc + Cur.cx;
+        const float v = Cur.fy * yc * invzc + Cur.cy;
+        if (u < Cur.minX || u > Cur.maxX) continue;
+        if (v < Cur.minY || v > Cur.maxY) continue;
+        const int nLastOctave = Last.keys[i].octave;
+        const float radius = th * Cur.scaleFactors[nLastOctave];
+        std::vector<int> cand;
+        if (bForward) cand = features_in_area(Cur, gCur, u, v, radius, nLastOctave, -1);
+        else if (bBackward) cand = features_in_area(Cur, gCur, u, v, radius, 0, nLastOctave);
+        else cand = features_in_area(Cur, gCur, u, v, radius, nLastOctave - 1, nLastOctave + 1);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : cand) {
+            if (assign[i2] != -1 && locked[i2]) continue;
+            if (Cur.uRight && Cur.uRight[i2] > 0) {
+                const float ur = u - Cur.bf * invzc;
+                const float er = std::fabs(ur - Cur.uRight[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = descriptor_distance(lp[i].desc, Cur.desc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            assign[bestIdx2] = i;
+            locked[bestIdx2] = lp[i].obsPositive;
+            ++nmatches;
+            if (pairs) {
+                pairs->push_back(Last.keysUn[i].x); pairs->push_back(Last.keysUn[i].y);
+                pairs->push_back(Cur.keysUn[bestIdx2].x); pairs->push_back(Cur.keysUn[bestIdx2].y);
+            }
+            if (checkOri) rotHist[rot_bin(Last.keysUn[i].angle - Cur.keysUn[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { assign[idx] = -1; locked[idx] = 0; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+/* ORBmatcher.cc:562-677 */
+int search_for_initialization(const FrameView& F1, const FrameView& F2, const Grid& g2, float* prevMatched,
+                              int32_t* m12, int windowSize, float nnratio, bool checkOri)
+{
+    int nmatches = 0;
+    std::fill(m12, m12 + F1.N, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> matchedDistance(F2.N, INT_MAX), m21(F2.N, -1);
+    for (int i1 = 0; i1 < F1.N; ++i1) {
+        const int level1 = F1.keysUn[i1].octave;
+        if (level1 > 0) continue;
+        const std::vector<int> cand = features_in_area(F2, g2, prevMatched[2 * i1], prevMatched[2 * i1 + 1],
+                                                       (float)windowSize, level1, level1);
+        if (cand.empty()) continue;
+        const uint8_t* d1 = F1.desc + 32 * (size_t)i1;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int i2 : cand) {
+            const int dist = descriptor_distance(d1, F2.desc + 32 * (size_t)i2);
+            if (matchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; --nmatches; }
+                m12[i1] = bestIdx2;
+                m21[bestIdx2] = i1;
+                matchedDistance[bestIdx2] = bestDist;
+                ++nmatches;
+                if (checkOri) rotHist[rot_bin(F1.keysUn[i1].angle - F2.keysUn[bestIdx2].angle)].push_back(i1);
+            }
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i])
+                if (m12[idx1] >= 0) { m12[idx1] = -1; --nmatches; }
+        }
+    }
+    for (int i1 = 0; i1 < F1.N; ++i1)
+        if (m12[i1] >= 0) { prevMatched[2 * i1] = F2.keysUn[m12[i1]].x; prevMatched[2 * i1 + 1] = F2.keysUn[m12[i1]].y; }
+    return nmatches;
+}
+
+/* ORBmatcher.cc:159-288 */
+int search_by_bow(const FrameView& KF, const uint8_t* kfValid, const FeatureVec& a, const FrameView& F,
+                  const FeatureVec& b, float nnratio, bool checkOri, int32_t* assign)
+{
+    std::fill(assign, assign + F.N, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0;
+    int ia = 0, ib = 0;
+    while (ia < a.nnodes && ib < b.nnodes) {
+        if (a.nodeId[ia] == b.nodeId[ib]) {
+            for (int p = a.offset[ia]; p < a.offset[ia + 1]; ++p) {
+                const unsigned kfIdx = a.index[p];
+                if (!kfValid[kfIdx]) continue;
+                const uint8_t* dKF = KF.desc + 32 * (size_t)kfIdx;
+                int best1 = 256, bestIdxF = -1, best2 = 256;
+                for (int q = b.offset[ib]; q < b.offset[ib + 1]; ++q) {
+                    const unsigned fIdx = b.index[q];
+                    if (assign[fIdx] != -1) continue;
+                    const int dist = descriptor_distance(dKF, F.desc + 32 * (size_t)fIdx);
+                    if (dist < best1) { best2 = best1; best1 = dist; bestIdxF = (int)fIdx; }
+                    else if (dist < best2) best2 = dist;
+                }
+                if (best1 <= TH_LOW) {
+                    if (static_cast<float>(best1) < nnratio * static_cast<float>(best2)) {
+                        assign[bestIdxF] = (int)kfIdx;
+                        if (checkOri) rotHist[rot_bin(KF.keysUn[kfIdx].angle - F.keys[bestIdxF].angle)].push_back(bestIdxF);
+                        ++nmatches;
+                    }
+                }
+            }
+            ++ia; ++ib;
+        } else if (a.nodeId[ia] < b.nodeId[ib]) {
+            ia = (int)(std::lower_bound(a.nodeId, a.nodeId + a.nnodes, b.nodeId[ib]) - a.nodeId);
+        } else {
+            ib = (int)(std::lower_bound(b.nodeId, b.nodeId + b.nnodes, a.nodeId[ia]) - b.nodeId);
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { assign[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+}  // namespace orc

@@ -1,0 +1,86 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY (see orc_prims.h).
+ * CPU restatement of the ORBmatcher searches on the hot path and of the Frame grid they use
+ * (reference: src/ORBmatcher.cc, src/Frame.cc).  Pointers of the reference become indices:
+ *   MapPoint* stored in Frame::mvpMapPoints[i]   ->  assign[i]  (-1 = NULL, >= 0 = index of the query)
+ *   pMP->Observations() > 0                      ->  a per-query flag; locked[i] mirrors it for the occupant
+ */
+#pragma once
+#include "orc_extractor.h"
+#include <cstdint>
+#include <vector>
+
+namespace orc {
+
+constexpr int GRID_COLS = 64, GRID_ROWS = 48;   /* include/Frame.h:39-40 */
+constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;   /* src/ORBmatcher.cc:37-39 */
+
+int descriptor_distance(const uint8_t* a, const uint8_t* b);   /* src/ORBmatcher.cc:1804-1820 */
+
+/* What the searches read from a Frame. */
+struct FrameView {
+    int N = 0;
+    const KeyPoint* keys = nullptr;      /* mvKeys */
+    const KeyPoint* keysUn = nullptr;    /* mvKeysUn */
+    const uint8_t* desc = nullptr;       /* mDescriptors, N x 32 */
+    const float* uRight = nullptr;       /* mvuRight (nullptr = all -1, monocular) */
+    float minX = 0, minY = 0, maxX = 0, maxY = 0;   /* mnMinX .. mnMaxY */
+    float gridWInv = 0, gridHInv = 0;    /* mfGridElementWidthInv / HeightInv */
+    int nlevels = 0;
+    const float* scaleFactors = nullptr; /* mvScaleFactors */
+    float fx = 0, fy = 0, cx = 0, cy = 0, bf = 0, b = 0;   /* fx, fy, cx, cy, mbf, mb */
+    float Tcw[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};  /* rows 0..2 of mTcw, row-major */
+};
+
+struct Grid {
+    std::vector<int> cell[GRID_COLS][GRID_ROWS];   /* mGrid[x][y] */
+};
+
+void grid_bounds(FrameView& f);                                       /* Frame.cc:383-385: inverse cell sizes */
+void assign_features_to_grid(const FrameView& f, Grid& g, int from = 0);   /* Frame.cc:463-478, 643-653 */
+std::vector<int> features_in_area(const FrameView& f, const Grid& g, float x, float y, float r,
+                                  int minLevel, int maxLevel);      /* Frame.cc:735-788 */
+
+struct MapPointQuery {          /* the MapPoint fields SearchByProjection(F, vpMapPoints) reads */
+    float projX, projY, projXR; /* mTrackProjX / Y / XR */
+    float viewCos;              /* mTrackViewCos */
+    int32_t level;              /* mnTrackScaleLevel */
+    uint8_t trackInView, bad, obsPositive, pad;
+    uint8_t desc[32];           /* GetDescriptor() */
+};
+
+/* ORBmatcher.cc:45-129 */
+int search_by_projection_map(const FrameView& F, const Grid& g, const MapPointQuery* mps, int nmp, float th,
+                             float nnratio, int32_t* assign, uint8_t* locked);
+
+struct LastFramePoint {         /* per keypoint of LastFrame */
+    uint8_t hasMP, outlier, obsPositive, pad;   /* mvpMapPoints[i] != NULL, mvbOutlier[i], Observations()>0 */
+    float world[3];             /* pMP->GetWorldPos() */
+    uint8_t desc[32];           /* pMP->GetDescriptor() */
+};
+
+/* ORBmatcher.cc:1485-1627 and the fork's overload :407-559 (pairs != nullptr).  pairs receives
+ * (last.x, last.y, cur.x, cur.y) per accepted match, appended BEFORE the rotation cull (Appendix B-8). */
+int search_by_projection_frame(const FrameView& Cur, const Grid& gCur, const FrameView& Last,
+                               const LastFramePoint* lp, float th, bool mono, bool checkOri,
+                               int32_t* assign, uint8_t* locked, std::vector<float>* pairs);
+
+/* ORBmatcher.cc:562-677.  prevMatched: N1 x 2 floats, updated in place. */
+int search_for_initialization(const FrameView& F1, const FrameView& F2, const Grid& g2, float* prevMatched,
+                              int32_t* matches12, int windowSize, float nnratio, bool checkOri);
+
+struct FeatureVec {             /* DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>> as CSR */
+    int nnodes = 0;
+    const uint32_t* nodeId = nullptr;   /* ascending */
+    const int32_t* offset = nullptr;    /* nnodes + 1 */
+    const uint32_t* index = nullptr;
+};
+
+/* ORBmatcher.cc:159-288.  kfValid[i] = (pMP != NULL && !pMP->isBad()) for keyframe keypoint i.
+ * assign[fIdx] = kfIdx | -1. */
+int search_by_bow(const FrameView& KF, const uint8_t* kfValid, const FeatureVec& fvKF, const FrameView& F,
+                  const FeatureVec& fvF, float nnratio, bool checkOri, int32_t* assign);
+
+/* ORBmatcher.cc:1758-1799 */
+void compute_three_maxima(const int* histoSizes, int L, int& ind1, int& ind2, int& ind3);
+
+}  // namespace orc

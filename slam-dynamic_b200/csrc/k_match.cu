@@ -1,0 +1,404 @@
+/* Hamming search kernels behind ORBmatcher (K7/K8).
+ *   reference: Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea   src/Frame.cc:463-478, 735-800
+ *              ORBmatcher::SearchByProjection(F, MapPoints)                  src/ORBmatcher.cc:45-129
+ *              ORBmatcher::SearchByProjection(Cur, Last[, pairs])            src/ORBmatcher.cc:1485-1627, 407-559
+ *              ORBmatcher::SearchForInitialization                           src/ORBmatcher.cc:562-677
+ *              ORBmatcher::SearchByBoW(KF, F)                                src/ORBmatcher.cc:159-288
+ *              ORBmatcher::DescriptorDistance / ComputeThreeMaxima           src/ORBmatcher.cc:1804-1820, 1758-1799
+ *
+ * Every search in the reference mutates its outputs while iterating (query k sees the claims of queries
+ * < k), and breaks distance ties by candidate enumeration order.  The work is therefore split in three:
+ *
+ *  k_grid_build        the 64x48 grid as a CSR: keypoints sorted by (cell = ix*48+iy, index).  Because
+ *                      GetFeaturesInArea walks ix outer / iy inner / in-cell insertion order, the candidates
+ *                      of one ix are ONE contiguous CSR span, already in reference order.
+ *  k_match_candidates  data-parallel, one warp per query: project, window, level / stereo gates, then
+ *                      __popc over the 256-bit descriptors (8 x 32 bit, query held in registers).  Emits each
+ *                      query's candidate list IN REFERENCE ORDER as packed records idx:16|dist:9|level:5.
+ *                      This is where the integer / popc work is.
+ *  k_match_resolve     one warp per search walks the queries in order; lanes scan the cached list, drop
+ *                      candidates excluded by earlier claims, and a shuffle reduction yields the two smallest
+ *                      (distance, position) keys — exactly the reference's first-strict-less best / second
+ *                      best.  Ratio / threshold tests, claims, the rotation histogram and its three-maxima
+ *                      cull follow the reference literally.
+ */
+#include "match_internal.h"
+
+namespace sdyn {
+
+constexpr int kPoolLevelBits = 5, kPoolDistBits = 9;
+
+__device__ __forceinline__ uint32_t pack_rec(int idx, int dist, int level)
+{ return (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)level << 25); }
+__device__ __forceinline__ int rec_idx(uint32_t r) { return r & 0xffff; }
+__device__ __forceinline__ int rec_dist(uint32_t r) { return (r >> 16) & 0x1ff; }
+__device__ __forceinline__ int rec_level(uint32_t r) { return (r >> 25) & 0x1f; }
+
+__device__ __forceinline__ int job_n(const MatchJob& J) { return J.nPtr ? min(*J.nPtr, J.n) : J.n; }
+__device__ __forceinline__ int job_nq(const MatchJob& J) { return J.nqPtr ? min(*J.nqPtr, J.nq) : J.nq; }
+
+/* ---------------------------------------------------------------------------------------------------- grid */
+__global__ void __launch_bounds__(256)
+k_grid_build(const MatchJob* __restrict__ jobs)
+{
+    const MatchJob& J = jobs[blockIdx.x];
+    if (J.mode == MM_BOW) return;
+    __shared__ int cnt[kGridCells];
+    __shared__ int warpSum[8];
+    const int tid = threadIdx.x, n = job_n(J);
+    for (int c = tid; c < kGridCells; c += 256) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const sdyn_keypoint kp = J.keysUn[i];
+        /* PosInGrid: round() is half-away-from-zero; keypoints outside the grid are not indexed */
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, J.minX), J.gridWInv));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, J.minY), J.gridHInv));
+        int c = -1;
+        if (px >= 0 && px < SDYN_GRID_COLS && py >= 0 && py < SDYN_GRID_ROWS) {
+            c = px * SDYN_GRID_ROWS + py;
+            atomicAdd(&cnt[c], 1);
+        }
+        J.cellOf[i] = c;
+    }
+    __syncthreads();
+    /* exclusive scan of 3072 counters: 12 per thread */
+    constexpr int PER = kGridCells / 256;
+    int local[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { local[k] = cnt[tid * PER + k]; sum += local[k]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+    if ((tid & 31) == 31) warpSum[tid >> 5] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < (tid >> 5); ++w) base += warpSum[w];
+    int run = base + incl - sum;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { J.cellOff[tid * PER + k] = run; cnt[tid * PER + k] = run; run += local[k]; }
+    if (tid == 255) J.cellOff[kGridCells] = run;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int c = J.cellOf[i];
+        if (c >= 0) J.sorted[atomicAdd(&cnt[c], 1)] = i;
+    }
+    __syncthreads();
+    /* in-cell order = insertion order of AssignFeaturesToGrid = ascending index */
+    for (int c = tid; c < kGridCells; c += 256) {
+        const int b = J.cellOff[c], e = cnt[c];
+        for (int i = b + 1; i < e; ++i) {
+            const int v = J.sorted[i];
+            int j = i - 1;
+            while (j >= b && J.sorted[j] > v) { J.sorted[j + 1] = J.sorted[j]; --j; }
+            J.sorted[j + 1] = v;
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- candidates */
+__device__ __forceinline__ int hamming256(const uint32_t (&q)[8], const uint8_t* d)
+{
+    const uint4 a = *reinterpret_cast<const uint4*>(d), b = *reinterpret_cast<const uint4*>(d + 16);
+    return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
+           __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+}
+
+__device__ __forceinline__ void load_desc(const uint8_t* p, uint32_t (&q)[8])
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);   /* 4-byte aligned in every query layout */
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = w[k];
+}
+
+constexpr int CW = 8;   /* warps per CTA in k_match_candidates */
+
+__global__ void __launch_bounds__(CW * 32)
+k_match_candidates(const MatchJob* __restrict__ jobs)
+{
+    const MatchJob& J = jobs[blockIdx.y];
+    const int q = blockIdx.x * CW + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int nq = job_nq(J);
+    if (q >= nq) return;
+
+    uint32_t qd[8];
+    bool active = true;
+    float x = 0.f, y = 0.f, r = 0.f, gate = 0.f, gateX = 0.f;   /* window centre / radius, stereo gate */
+    int minLevel = 0, maxLevel = -1;
+
+    if (J.mode == MM_BOW) {
+        const BowQuery bq = reinterpret_cast<const BowQuery*>(J.queries)[q];
+        load_desc(J.qDesc + 32 * (size_t)bq.kfIdx, qd);
+        int off = 0;
+        if (lane == 0) off = atomicAdd(J.poolUsed, bq.fCnt);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (off + bq.fCnt > J.poolCap) { if (lane == 0) { J.result[2] = 1; J.qspan[q] = make_int2(0, 0); } return; }
+        for (int k = lane; k < bq.fCnt; k += 32) {
+            const int idx = (int)J.fIndex[bq.fOff + k];
+            J.pool[off + k] = pack_rec(idx, hamming256(qd, J.desc + 32 * (size_t)idx), 0);
+        }
+        if (lane == 0) J.qspan[q] = make_int2(off, bq.fCnt);
+        return;
+    }
+
+    if (J.mode == MM_FRAME) {
+        const sdyn_last_point* lp = reinterpret_cast<const sdyn_last_point*>(J.queries) + q;
+        active = lp->has_mp && !lp->outlier;
+        if (active) {
+            /* x3Dc = Rcw*x3Dw + tcw, evaluated like cv::Mat's 3x3 float product: left-to-right, no FMA */
+            float pc[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float s = __fadd_rn(__fadd_rn(__fmul_rn(J.Tcw[4 * k], lp->world[0]), __fmul_rn(J.Tcw[4 * k + 1], lp->world[1])),
+                                          __fmul_rn(J.Tcw[4 * k + 2], lp->world[2]));
+                pc[k] = __fadd_rn(s, J.Tcw[4 * k + 3]);
+            }
+            const float invzc = (float)(1.0 / (double)pc[2]);
+            if (invzc < 0) active = false;
+            x = __fadd_rn(__fmul_rn(__fmul_rn(J.fx, pc[0]), invzc), J.cx);
+            y = __fadd_rn(__fmul_rn(__fmul_rn(J.fy, pc[1]), invzc), J.cy);
+            if (x < J.minX || x > J.maxX || y < J.minY || y > J.maxY) active = false;
+            const int oct = J.qKeys[q].octave;
+            r = __fmul_rn(J.th, J.scale[oct]);
+            if (J.forward) { minLevel = oct; maxLevel = -1; }
+            else if (J.backward) { minLevel = 0; maxLevel = oct; }
+            else { minLevel = oct - 1; maxLevel = oct + 1; }
+            gate = r;
+            gateX = __fsub_rn(x, __fmul_rn(J.bf, invzc));    /* ur = u - mbf*invzc */
+            load_desc(lp->desc, qd);
+        }
+    } else if (J.mode == MM_MAP) {
+        const sdyn_mappoint_query* mp = reinterpret_cast<const sdyn_mappoint_query*>(J.queries) + q;
+        active = mp->track_in_view && !mp->bad;
+        if (active) {
+            float rr = ((double)mp->view_cos > 0.998) ? 2.5f : 4.0f;      /* RadiusByViewingCos */
+            if (J.th != 1.0f) rr = __fmul_rn(rr, J.th);
+            r = __fmul_rn(rr, J.scale[mp->level]);
+            x = mp->proj_x; y = mp->proj_y;
+            minLevel = mp->level - 1; maxLevel = mp->level;
+            gate = r; gateX = mp->proj_xr;
+            load_desc(mp->desc, qd);
+        }
+    } else {   /* MM_INIT */
+        const sdyn_keypoint kp = J.qKeys[q];
+        active = !(kp.octave > 0);
+        if (active) {
+            x = J.prevMatched[2 * q]; y = J.prevMatched[2 * q + 1];
+            r = (float)J.window;
+            minLevel = kp.octave; maxLevel = kp.octave;
+            load_desc(J.qDesc + 32 * (size_t)q, qd);
+        }
+    }
+
+    int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+    if (active) {
+        cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, J.minX), r), J.gridWInv)));
+        cx1 = min(SDYN_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, J.minX), r), J.gridWInv)));
+        cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, J.minY), r), J.gridHInv)));
+        cy1 = min(SDYN_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, J.minY), r), J.gridHInv)));
+        if (cx0 >= SDYN_GRID_COLS || cx1 < 0 || cy0 >= SDYN_GRID_ROWS || cy1 < 0) active = false;
+    }
+    if (!active) { if (lane == 0) J.qspan[q] = make_int2(0, 0); return; }
+
+    /* reserve the upper bound (all keypoints of the touched cells), then emit in enumeration order */
+    int bound = 0;
+    for (int ix = cx0 + lane; ix <= cx1; ix += 32)
+        bound += J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1] - J.cellOff[ix * SDYN_GRID_ROWS + cy0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bound += __shfl_xor_sync(0xffffffffu, bound, o);
+    int off = 0;
+    if (lane == 0) off = atomicAdd(J.poolUsed, bound);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (off + bound > J.poolCap) { if (lane == 0) { J.result[2] = 1; J.qspan[q] = make_int2(0, 0); } return; }
+
+    const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+    int cnt = 0;
+    for (int ix = cx0; ix <= cx1; ++ix) {
+        const int b = J.cellOff[ix * SDYN_GRID_ROWS + cy0], e = J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1];
+        for (int p0 = b; p0 < e; p0 += 32) {
+            const int p = p0 + lane;
+            bool ok = p < e;
+            int idx = 0, dist = 0, oct = 0;
+            if (ok) {
+                idx = J.sorted[p];
+                const sdyn_keypoint kp = J.keysUn[idx];
+                oct = kp.octave;
+                if (checkLevels) {
+                    if (oct < minLevel) ok = false;
+                    if (maxLevel >= 0 && oct > maxLevel) ok = false;
+                }
+                if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) ok = false;
+                if (ok && J.mode != MM_INIT && J.uRight) {
+                    const float ur = J.uRight[idx];
+                    if (ur > 0 && fabsf(__fsub_rn(gateX, ur)) > gate) ok = false;
+                }
+                if (ok) dist = hamming256(qd, J.desc + 32 * (size_t)idx);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) J.pool[off + cnt + __popc(m & ((1u << lane) - 1))] = pack_rec(idx, dist, oct);
+            cnt += __popc(m);
+        }
+    }
+    if (lane == 0) J.qspan[q] = make_int2(off, cnt);
+}
+
+/* ------------------------------------------------------------------------------------------------- resolve */
+struct Top2 { uint32_t a, b; };   /* keys (dist << 20 | position); a <= b */
+
+__device__ __forceinline__ Top2 warp_top2(uint32_t a, uint32_t b)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t oa = __shfl_xor_sync(0xffffffffu, a, o), ob = __shfl_xor_sync(0xffffffffu, b, o);
+        const uint32_t lo = min(a, oa), hi = max(a, oa);
+        b = min(hi, min(b, ob));
+        a = lo;
+    }
+    return {a, b};
+}
+
+__global__ void __launch_bounds__(32)
+k_match_resolve(const MatchJob* __restrict__ jobs)
+{
+    const MatchJob& J = jobs[blockIdx.x];
+    const int lane = threadIdx.x;
+    const int nq = job_nq(J);
+    __shared__ int hist[SDYN_HISTO_LENGTH];
+    __shared__ int keep[3];
+    constexpr uint32_t NONE = 0xffffffffu;
+    int nmatches = 0, npairs = 0;
+    volatile int32_t* assign = J.assign;
+    volatile uint8_t* locked = J.locked;
+    volatile int32_t* mdist = J.matchedDist;
+    volatile int32_t* m21 = J.m21;
+    const float histFactor = 1.0f / SDYN_HISTO_LENGTH;
+
+    for (int q = 0; q < nq; ++q) {
+        const int2 span = J.qspan[q];
+        uint32_t a = NONE, b = NONE;
+        for (int p = lane; p < span.y; p += 32) {
+            const uint32_t rec = J.pool[span.x + p];
+            const int idx = rec_idx(rec), dist = rec_dist(rec);
+            bool ok;
+            if (J.mode == MM_INIT) ok = !(mdist[idx] <= dist);
+            else if (J.mode == MM_BOW) ok = assign[idx] == -1;
+            else ok = !(assign[idx] != -1 && locked[idx]);
+            if (ok) {
+                const uint32_t key = ((uint32_t)dist << 20) | (uint32_t)p;
+                if (key < a) { b = a; a = key; } else if (key < b) b = key;
+            }
+        }
+        const Top2 t = warp_top2(a, b);
+        int accepted = -1, bin = 0;
+        if (t.a != NONE) {
+            const uint32_t r1 = J.pool[span.x + (t.a & 0xfffff)];
+            const int bestDist = (int)(t.a >> 20), bestIdx = rec_idx(r1);
+            /* second best: the reference starts from 256 (INT_MAX in SearchForInitialization), level -1 */
+            int bestDist2 = J.mode == MM_INIT ? 0x7fffffff : 256, bestLevel2 = -1;
+            if (t.b != NONE) { bestDist2 = (int)(t.b >> 20); bestLevel2 = rec_level(J.pool[span.x + (t.b & 0xfffff)]); }
+            bool ok;
+            if (J.mode == MM_FRAME) ok = bestDist <= SDYN_TH_HIGH;
+            else if (J.mode == MM_MAP)
+                ok = bestDist <= SDYN_TH_HIGH &&
+                     !(rec_level(r1) == bestLevel2 && (float)bestDist > __fmul_rn(J.nnratio, (float)bestDist2));
+            else if (J.mode == MM_INIT) ok = bestDist <= SDYN_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, J.nnratio);
+            else ok = bestDist <= SDYN_TH_LOW && (float)bestDist < __fmul_rn(J.nnratio, (float)bestDist2);
+            if (ok) {
+                accepted = bestIdx;
+                float rot = 0.f;
+                if (lane == 0) {
+                    if (J.mode == MM_FRAME) {
+                        const sdyn_last_point* lp = reinterpret_cast<const sdyn_last_point*>(J.queries) + q;
+                        assign[bestIdx] = q; locked[bestIdx] = lp->obs_positive;
+                        if (J.pairs) {
+                            J.pairs[4 * npairs] = J.qKeysUn[q].x; J.pairs[4 * npairs + 1] = J.qKeysUn[q].y;
+                            J.pairs[4 * npairs + 2] = J.keysUn[bestIdx].x; J.pairs[4 * npairs + 3] = J.keysUn[bestIdx].y;
+                        }
+                    } else if (J.mode == MM_MAP) {
+                        const sdyn_mappoint_query* mp = reinterpret_cast<const sdyn_mappoint_query*>(J.queries) + q;
+                        assign[bestIdx] = q; locked[bestIdx] = mp->obs_positive;
+                    } else if (J.mode == MM_INIT) {
+                        const int prev = m21[bestIdx];
+                        if (prev >= 0) { assign[prev] = -1; --nmatches; }
+                        assign[q] = bestIdx; m21[bestIdx] = q; mdist[bestIdx] = bestDist;
+                    } else {
+                        assign[bestIdx] = reinterpret_cast<const BowQuery*>(J.queries)[q].kfIdx;
+                    }
+                }
+                ++nmatches; ++npairs;
+                if (J.checkOri && J.mode != MM_MAP) {
+                    if (J.mode == MM_FRAME) rot = __fsub_rn(J.qKeysUn[q].angle, J.keysUn[bestIdx].angle);
+                    else if (J.mode == MM_INIT) rot = __fsub_rn(J.qKeys[q].angle, J.keysUn[bestIdx].angle);
+                    else rot = __fsub_rn(J.qKeys[reinterpret_cast<const BowQuery*>(J.queries)[q].kfIdx].angle, J.keysUn[bestIdx].angle);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    bin = (int)roundf(__fmul_rn(rot, histFactor));
+                    if (bin == SDYN_HISTO_LENGTH) bin = 0;
+                }
+            }
+        }
+        if (lane == 0) { J.qAccepted[q] = accepted; J.qBin[q] = bin; }
+        __syncwarp();
+    }
+
+    /* rotation-consistency cull (ComputeThreeMaxima) */
+    if (J.checkOri && J.mode != MM_MAP) {
+        for (int i = lane; i < SDYN_HISTO_LENGTH; i += 32) hist[i] = 0;
+        __syncwarp();
+        for (int q = lane; q < nq; q += 32) if (J.qAccepted[q] >= 0) atomicAdd(&hist[J.qBin[q]], 1);
+        __syncwarp();
+        if (lane == 0) {
+            int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < SDYN_HISTO_LENGTH; ++i) {
+                const int s = hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+                else if (s > max3) { max3 = s; i3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) i3 = -1;
+            keep[0] = i1; keep[1] = i2; keep[2] = i3;
+        }
+        __syncwarp();
+        int dec = 0;
+        for (int q = lane; q < nq; q += 32) {
+            const int acc = J.qAccepted[q];
+            if (acc < 0) continue;
+            const int bin = J.qBin[q];
+            if (bin == keep[0] || bin == keep[1] || bin == keep[2]) continue;
+            if (J.mode == MM_INIT) { if (J.assign[q] >= 0) { J.assign[q] = -1; ++dec; } }
+            else { J.assign[acc] = -1; if (J.locked) J.locked[acc] = 0; ++dec; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dec += __shfl_xor_sync(0xffffffffu, dec, o);
+        nmatches -= dec;
+    }
+    __syncwarp();
+    if (J.mode == MM_INIT) {   /* update vbPrevMatched (:671-674) */
+        for (int q = lane; q < nq; q += 32) {
+            const int m = J.assign[q];
+            if (m >= 0) { J.prevMatched[2 * q] = J.keysUn[m].x; J.prevMatched[2 * q + 1] = J.keysUn[m].y; }
+        }
+    }
+    if (lane == 0) { J.result[0] = nmatches; J.result[1] = npairs; }
+}
+
+cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, cudaStream_t st)
+{
+    k_grid_build<<<njobs, 256, 0, st>>>(dJobs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQueries, cudaStream_t st)
+{
+    if (maxQueries <= 0) return cudaSuccess;
+    dim3 grid((maxQueries + CW - 1) / CW, njobs);
+    k_match_candidates<<<grid, CW * 32, 0, st>>>(dJobs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, cudaStream_t st)
+{
+    k_match_resolve<<<njobs, 32, 0, st>>>(dJobs);
+    return cudaGetLastError();
+}
+
+}  // namespace sdyn

@@ -1,0 +1,76 @@
+/* Device-side job descriptors of the matcher kernels (k_match.cu) — shared with the host glue. */
+#pragma once
+#include "sdyn_internal.h"
+
+namespace sdyn {
+
+constexpr int kGridCells = SDYN_GRID_COLS * SDYN_GRID_ROWS;   /* 3072 */
+
+enum MatchMode { MM_FRAME = 0, MM_MAP = 1, MM_INIT = 2, MM_BOW = 3 };
+
+/* query of the BoW search: one keyframe feature against the frame features of the same vocabulary node */
+struct BowQuery { int32_t kfIdx, fOff, fCnt; };
+
+/* One search call.  All pointers are device pointers.  Several jobs run per launch (blockIdx.y). */
+struct MatchJob {
+    int mode;
+    /* frame that is searched (CurrentFrame / F / F2 / F) */
+    const sdyn_keypoint* keysUn;
+    const uint8_t* desc;
+    const float* uRight;             /* may be null */
+    const int32_t* nPtr;             /* device-resident keypoint count, or null -> n */
+    int n;
+    float minX, minY, maxX, maxY, gridWInv, gridHInv;
+    float scale[SDYN_MAX_LEVELS];
+    /* grid CSR built by k_grid_build: keypoints sorted by (cell = ix*48+iy, index) */
+    int32_t* cellOff;                /* kGridCells + 1 */
+    int32_t* sorted;                 /* n */
+    int32_t* cellOf;                 /* n, scratch */
+    /* queries */
+    const void* queries;             /* sdyn_mappoint_query / sdyn_last_point / F1 keypoints / BowQuery */
+    const sdyn_keypoint* qKeys;      /* FRAME: LastFrame.mvKeys (octave), INIT: F1.mvKeysUn, BOW: KF.mvKeysUn */
+    const sdyn_keypoint* qKeysUn;    /* FRAME: LastFrame.mvKeysUn (angle, pt for pairs) */
+    const uint8_t* qDesc;            /* INIT: F1 descriptors, BOW: KF descriptors */
+    const uint32_t* fIndex;          /* BOW: F feature-vector index array */
+    const int32_t* nqPtr;            /* device-resident query count, or null -> nq */
+    int nq;
+    float* prevMatched;              /* INIT: in/out, nq x 2 */
+    /* parameters */
+    float th, nnratio;
+    int checkOri, forward, backward, window;
+    float Tcw[12], fx, fy, cx, cy, bf;
+    /* state / outputs */
+    int32_t* assign;                 /* FRAME/MAP/BOW: per searched keypoint; INIT: matches12 per query */
+    uint8_t* locked;                 /* FRAME/MAP */
+    int32_t* matchedDist;            /* INIT: per F2 keypoint */
+    int32_t* m21;                    /* INIT */
+    int32_t* result;                 /* [0] nmatches, [1] npairs, [2] status (1 = pool overflow) */
+    float* pairs;                    /* FRAME (fork overload), may be null */
+    /* scratch */
+    int2* qspan;                     /* per query: (offset into pool, count) */
+    int32_t* qAccepted;              /* per query: claimed index or -1 */
+    int32_t* qBin;                   /* per query: rotation-histogram bin */
+    uint32_t* pool;                  /* candidate records: idx:16 | dist:9 | level:5 */
+    int poolCap;
+    int32_t* poolUsed;
+};
+
+cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, cudaStream_t st);
+cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQueries, cudaStream_t st);
+cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, cudaStream_t st);
+
+/* dynamic-keypoint kernels (k_dynamic.cu) */
+struct BoxPairJob {
+    int nq, nt;
+    const uint8_t* qDesc; const uint8_t* tDesc;
+    const float* qXY; const float* tXY;
+    int32_t* nnQ; int32_t* dQ; int32_t* nnT;          /* scratch: nq, nq, nt */
+    int32_t* outQuery; int32_t* outTrain; int32_t* outDist; int32_t* outFalseDyn; int32_t* outCount;
+};
+cudaError_t launch_box_mask(const sdyn_keypoint* dKeys, const int32_t* nPtr, int n, int keyStride,
+                            const double* dBoxes, const int32_t* nBoxesPtr, int nboxes, int boxStride,
+                            uint64_t* dMask, int njobs, cudaStream_t st);
+cudaError_t launch_box_pairs(const BoxPairJob* dJobs, int njobs, const float* dM, const float* dMinv, int mode,
+                             cudaStream_t st);
+
+}  // namespace sdyn

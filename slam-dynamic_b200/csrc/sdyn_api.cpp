@@ -144,7 +144,7 @@ void free_all(sdyn_ctx* c)
     cudaFree(c->dFastTiles); cudaFree(c->dBlurTiles); cudaFree(c->dTables); cudaFree(c->dIn); cudaFree(c->dPyr);
     cudaFree(c->dBlur); cudaFree(c->dCellFlag); cudaFree(c->dCand); cudaFree(c->dCandNode); cudaFree(c->dCandCount); cudaFree(c->dSelCount);
     cudaFree(c->dLevelKp); cudaFree(c->dLevelCount); cudaFree(c->dCount); cudaFree(c->dStatus); cudaFree(c->dKp);
-    cudaFree(c->dDesc);
+    cudaFree(c->dDesc); cudaFree(c->dArena);
     cudaFreeHost(c->hKp); cudaFreeHost(c->hDesc); cudaFreeHost(c->hCount); cudaFreeHost(c->hStatus);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->evPool) cudaEventDestroy(e);

@@ -92,6 +92,8 @@ struct sdyn_ctx {
     int32_t* dCount;                           /* [maxBatch] */
     int32_t* dStatus;                          /* [maxBatch] sticky per-frame error flags */
     sdyn_keypoint* dKp; uint8_t* dDesc;        /* [maxBatch][maxKp] */
+    /* matcher / dynamic-mask arena (grown on demand, reused across calls) */
+    uint8_t* dArena; size_t arenaCap;
     /* per-stage profiling */
     bool profiling;
     std::vector<cudaEvent_t> evPool;           /* free events */

@@ -264,3 +264,189 @@ class Extractor:
 
     def launch_count(self):
         return lib().sdyn_launch_count(self._h)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ORBmatcher / dynamic-keypoint entry points
+# ---------------------------------------------------------------------------------------------------
+class FrameViewC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("nlevels", C.c_int32), ("keys", C.c_void_p), ("keys_un", C.c_void_p),
+                ("desc", C.c_void_p), ("u_right", C.c_void_p), ("scale_factors", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("b", C.c_float), ("tcw", C.c_float * 12)]
+
+
+class FeatureVectorC(C.Structure):
+    _fields_ = [("nnodes", C.c_int32), ("node_id", C.c_void_p), ("offset", C.c_void_p), ("index", C.c_void_p)]
+
+
+class BoxPairC(C.Structure):
+    _fields_ = [("nq", C.c_int32), ("nt", C.c_int32), ("q_desc", C.c_void_p), ("t_desc", C.c_void_p),
+                ("q_xy", C.c_void_p), ("t_xy", C.c_void_p), ("match_query", C.c_void_p), ("match_train", C.c_void_p),
+                ("match_dist", C.c_void_p), ("false_dyn", C.c_void_p), ("nmatches", C.c_int32)]
+
+
+MAPPOINT_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"),
+                           ("level", "<i4"), ("track_in_view", "u1"), ("bad", "u1"), ("obs_positive", "u1"),
+                           ("pad", "u1"), ("desc", "u1", (32,))])
+LASTPOINT_DTYPE = np.dtype([("has_mp", "u1"), ("outlier", "u1"), ("obs_positive", "u1"), ("pad", "u1"),
+                            ("world", "<f4", (3,)), ("desc", "u1", (32,))])
+assert MAPPOINT_DTYPE.itemsize == 56 and LASTPOINT_DTYPE.itemsize == 48
+
+
+class FrameView:
+    """The Frame members the searches read (include/Frame.h), kept alive next to their C struct."""
+
+    def __init__(self, keys, desc, scale_factors, bounds, keys_un=None, u_right=None,
+                 cam=(0., 0., 0., 0., 0., 0.), tcw=None):
+        self.keys = np.ascontiguousarray(keys, KP_DTYPE)
+        self.keys_un = self.keys if keys_un is None else np.ascontiguousarray(keys_un, KP_DTYPE)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.u_right = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        self.scale = np.ascontiguousarray(scale_factors, np.float32)
+        self.bounds = tuple(float(v) for v in bounds)          # mnMinX, mnMinY, mnMaxX, mnMaxY
+        self.cam = tuple(float(v) for v in cam)                # fx, fy, cx, cy, mbf, mb
+        self.tcw = np.ascontiguousarray(np.eye(4, dtype=np.float32)[:3] if tcw is None else tcw, np.float32).reshape(12)
+        c = FrameViewC()
+        c.n = len(self.keys); c.nlevels = len(self.scale)
+        c.keys = self.keys.ctypes.data; c.keys_un = self.keys_un.ctypes.data; c.desc = self.desc.ctypes.data
+        c.u_right = self.u_right.ctypes.data if self.u_right is not None else None
+        c.scale_factors = self.scale.ctypes.data
+        c.min_x, c.min_y, c.max_x, c.max_y = self.bounds
+        c.fx, c.fy, c.cx, c.cy, c.bf, c.b = self.cam
+        for i in range(12):
+            c.tcw[i] = float(self.tcw[i])
+        self.c = c
+
+    @property
+    def n(self):
+        return len(self.keys)
+
+
+class FeatureVector:
+    """DBoW2::FeatureVector as CSR (ascending node ids)."""
+
+    def __init__(self, node_of_feature):
+        node_of_feature = np.asarray(node_of_feature)
+        order = np.argsort(node_of_feature, kind="stable")
+        ids, counts = np.unique(node_of_feature, return_counts=True)
+        self.node_id = np.ascontiguousarray(ids, np.uint32)
+        self.offset = np.ascontiguousarray(np.concatenate([[0], np.cumsum(counts)]), np.int32)
+        self.index = np.ascontiguousarray(order, np.uint32)
+        c = FeatureVectorC()
+        c.nnodes = len(ids); c.node_id = self.node_id.ctypes.data; c.offset = self.offset.ctypes.data
+        c.index = self.index.ctypes.data
+        self.c = c
+
+
+def _bind_match(L):
+    if getattr(L, "_match_bound", False):
+        return L
+    vp = C.c_void_p
+    L.sdyn_hamming.argtypes = [vp, vp]
+    L.sdyn_match_projection_map.argtypes = [vp, C.POINTER(FrameViewC), vp, C.c_int, C.c_float, C.c_float, vp, vp,
+                                            C.POINTER(C.c_int)]
+    L.sdyn_match_projection_frame.argtypes = [vp, C.POINTER(FrameViewC), C.POINTER(FrameViewC), vp, C.c_float, C.c_int,
+                                              C.c_int, vp, vp, C.POINTER(C.c_int), vp, C.POINTER(C.c_int)]
+    L.sdyn_match_init.argtypes = [vp, C.POINTER(FrameViewC), C.POINTER(FrameViewC), vp, vp, C.c_int, C.c_float, C.c_int,
+                                  C.POINTER(C.c_int)]
+    L.sdyn_match_bow.argtypes = [vp, C.POINTER(FrameViewC), vp, C.POINTER(FeatureVectorC), C.POINTER(FrameViewC),
+                                 C.POINTER(FeatureVectorC), C.c_float, C.c_int, vp, C.POINTER(C.c_int)]
+    L.sdyn_dyn_box_mask.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp]
+    L.sdyn_dyn_separate.argtypes = [vp, C.POINTER(BoxPairC), C.c_int, vp, C.c_int]
+    L._match_bound = True
+    return L
+
+
+class Matcher:
+    """Mirror of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:41-95) over the C ABI.  Pointers become indices:
+    mvpMapPoints -> `assign` (-1 = NULL), "occupant has Observations()>0" -> `locked`."""
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30
+
+    def __init__(self, ctx, nnratio=0.6, check_orientation=True):
+        self.ex = ctx                       # an Extractor: owns the sdyn context (device, stream, arenas)
+        self.h = ctx._h
+        self.nnratio = float(nnratio)
+        self.check = bool(check_orientation)
+        self.L = _bind_match(lib())
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return _bind_match(lib()).sdyn_hamming(a.ctypes.data, b.ctypes.data)
+
+    def SearchByProjectionMap(self, F, mappoints, th, assign=None, locked=None):
+        mp = np.ascontiguousarray(mappoints, MAPPOINT_DTYPE)
+        assign = np.full(F.n, -1, np.int32) if assign is None else np.ascontiguousarray(assign, np.int32).copy()
+        locked = np.zeros(F.n, np.uint8) if locked is None else np.ascontiguousarray(locked, np.uint8).copy()
+        n = C.c_int(0)
+        self.ex._check(self.L.sdyn_match_projection_map(self.h, C.byref(F.c), mp.ctypes.data, len(mp), th, self.nnratio,
+                                                        assign.ctypes.data, locked.ctypes.data, C.byref(n)))
+        return n.value, assign, locked
+
+    def SearchByProjectionFrame(self, cur, last, last_points, th, mono, assign=None, locked=None, want_pairs=False):
+        lp = np.ascontiguousarray(last_points, LASTPOINT_DTYPE)
+        assign = np.full(cur.n, -1, np.int32) if assign is None else np.ascontiguousarray(assign, np.int32).copy()
+        locked = np.zeros(cur.n, np.uint8) if locked is None else np.ascontiguousarray(locked, np.uint8).copy()
+        n, npairs = C.c_int(0), C.c_int(0)
+        pairs = np.zeros((max(last.n, 1), 4), np.float32) if want_pairs else None
+        self.ex._check(self.L.sdyn_match_projection_frame(
+            self.h, C.byref(cur.c), C.byref(last.c), lp.ctypes.data, th, int(mono), int(self.check), assign.ctypes.data,
+            locked.ctypes.data, C.byref(n), pairs.ctypes.data if want_pairs else None, C.byref(npairs) if want_pairs else None))
+        if want_pairs:
+            return n.value, assign, locked, pairs[:npairs.value].copy()
+        return n.value, assign, locked
+
+    def SearchForInitialization(self, F1, F2, prev_matched, window=100):
+        prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+        m12 = np.full(F1.n, -1, np.int32)
+        n = C.c_int(0)
+        self.ex._check(self.L.sdyn_match_init(self.h, C.byref(F1.c), C.byref(F2.c), prev.ctypes.data, m12.ctypes.data,
+                                              window, self.nnratio, int(self.check), C.byref(n)))
+        return n.value, m12, prev
+
+    def SearchByBoW(self, KF, kf_valid, fv_kf, F, fv_f):
+        kv = np.ascontiguousarray(kf_valid, np.uint8)
+        assign = np.full(F.n, -1, np.int32)
+        n = C.c_int(0)
+        self.ex._check(self.L.sdyn_match_bow(self.h, C.byref(KF.c), kv.ctypes.data, C.byref(fv_kf.c), C.byref(F.c),
+                                             C.byref(fv_f.c), self.nnratio, int(self.check), assign.ctypes.data, C.byref(n)))
+        return n.value, assign
+
+
+def box_mask(ctx, keys, boxes):
+    """Frame::firstSeparate's keypoint-in-box test: uint64 bitmask per keypoint."""
+    L = _bind_match(lib())
+    keys = np.ascontiguousarray(keys, KP_DTYPE)
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
+    mask = np.zeros(len(keys), np.uint64)
+    ctx._check(L.sdyn_dyn_box_mask(ctx._h, keys.ctypes.data, len(keys), boxes.ctypes.data, len(boxes), mask.ctypes.data))
+    return mask
+
+
+def separate_pairs(ctx, pairs, M, mode, fn=None):
+    """pairs: list of (q_desc[nq,32], q_xy[nq,2], t_desc[nt,32], t_xy[nt,2]).  Returns per pair
+    (query, train, dist, false_dyn) arrays — BFMatcher(crossCheck) + classifyF (mode 0) / classifyH (mode 1)."""
+    L = _bind_match(lib())
+    arr = (BoxPairC * max(len(pairs), 1))()
+    keep = []
+    for i, (qd, qx, td, tx) in enumerate(pairs):
+        qd = np.ascontiguousarray(qd, np.uint8).reshape(-1, 32); td = np.ascontiguousarray(td, np.uint8).reshape(-1, 32)
+        qx = np.ascontiguousarray(qx, np.float32).reshape(-1, 2); tx = np.ascontiguousarray(tx, np.float32).reshape(-1, 2)
+        outs = [np.full(max(len(qd), 1), -9, np.int32) for _ in range(4)]
+        keep.append((qd, qx, td, tx, outs))
+        p = arr[i]
+        p.nq, p.nt = len(qd), len(td)
+        p.q_desc, p.t_desc, p.q_xy, p.t_xy = qd.ctypes.data, td.ctypes.data, qx.ctypes.data, tx.ctypes.data
+        p.match_query, p.match_train, p.match_dist, p.false_dyn = (o.ctypes.data for o in outs)
+    M = np.ascontiguousarray(M, np.float32).reshape(9)
+    if fn is None:
+        ctx._check(L.sdyn_dyn_separate(ctx._h, arr, len(pairs), M.ctypes.data, mode))
+    else:
+        fn(arr, len(pairs), M.ctypes.data, mode)
+    res = []
+    for i, (_, _, _, _, outs) in enumerate(keep):
+        n = arr[i].nmatches
+        res.append(tuple(o[:n].copy() for o in outs))
+    return res

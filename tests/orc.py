@@ -159,3 +159,124 @@ class Extractor:
 
     def level_counts(self):
         return np.array([lib.orc_extractor_level_count(self.h, l) for l in range(self.nlevels)], np.int32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# matcher / dynamic oracle entry points (same POD layouts as include/sdyn.h; structs come from pysdyn's
+# ctypes definitions, which only describe the ABI — no product code runs here)
+# ---------------------------------------------------------------------------------------------------
+def _structs():
+    import pysdyn
+    return pysdyn
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib.orc_hamming(_p(a, _u8p), _p(b, _u8p))
+
+
+def features_in_area(F, x, y, r, min_level, max_level):
+    out = np.zeros(max(F.n, 1), np.int32)
+    lib.orc_features_in_area.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _i32p, C.c_int]
+    n = lib.orc_features_in_area(C.byref(F.c), x, y, r, min_level, max_level, _p(out, _i32p), len(out))
+    return out[:n].copy()
+
+
+def match_projection_map(F, mappoints, th, nnratio, assign=None, locked=None):
+    S = _structs()
+    mp = np.ascontiguousarray(mappoints, S.MAPPOINT_DTYPE)
+    assign = np.full(F.n, -1, np.int32) if assign is None else np.ascontiguousarray(assign, np.int32).copy()
+    locked = np.zeros(F.n, np.uint8) if locked is None else np.ascontiguousarray(locked, np.uint8).copy()
+    lib.orc_match_projection_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    n = lib.orc_match_projection_map(C.byref(F.c), mp.ctypes.data, len(mp), th, nnratio, assign.ctypes.data, locked.ctypes.data)
+    return n, assign, locked
+
+
+def match_projection_frame(cur, last, last_points, th, mono, check_ori, assign=None, locked=None, want_pairs=False):
+    S = _structs()
+    lp = np.ascontiguousarray(last_points, S.LASTPOINT_DTYPE)
+    assign = np.full(cur.n, -1, np.int32) if assign is None else np.ascontiguousarray(assign, np.int32).copy()
+    locked = np.zeros(cur.n, np.uint8) if locked is None else np.ascontiguousarray(locked, np.uint8).copy()
+    pairs = np.zeros((max(last.n, 1), 4), np.float32)
+    npairs = C.c_int(0)
+    lib.orc_match_projection_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    n = lib.orc_match_projection_frame(C.byref(cur.c), C.byref(last.c), lp.ctypes.data, th, int(mono), int(check_ori),
+                                       assign.ctypes.data, locked.ctypes.data,
+                                       pairs.ctypes.data if want_pairs else None, C.byref(npairs))
+    if want_pairs:
+        return n, assign, locked, pairs[:npairs.value].copy()
+    return n, assign, locked
+
+
+def match_init(F1, F2, prev_matched, window, nnratio, check_ori):
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.full(F1.n, -1, np.int32)
+    lib.orc_match_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
+    n = lib.orc_match_init(C.byref(F1.c), C.byref(F2.c), prev.ctypes.data, m12.ctypes.data, window, nnratio, int(check_ori))
+    return n, m12, prev
+
+
+def match_bow(KF, kf_valid, fv_kf, F, fv_f, nnratio, check_ori):
+    kv = np.ascontiguousarray(kf_valid, np.uint8)
+    assign = np.full(F.n, -1, np.int32)
+    lib.orc_match_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+    n = lib.orc_match_bow(C.byref(KF.c), kv.ctypes.data, C.byref(fv_kf.c), C.byref(F.c), C.byref(fv_f.c), nnratio,
+                          int(check_ori), assign.ctypes.data)
+    return n, assign
+
+
+def box_mask(keys, boxes):
+    keys = np.ascontiguousarray(keys, KP_DTYPE)
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
+    mask = np.zeros(len(keys), np.uint64)
+    lib.orc_box_mask.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.orc_box_mask(keys.ctypes.data, len(keys), boxes.ctypes.data, len(boxes), mask.ctypes.data)
+    return mask
+
+
+def separate_pairs(pairs, M, mode):
+    S = _structs()
+    lib.orc_separate_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    return S.separate_pairs(None, pairs, M, mode, fn=lambda arr, n, m, md: lib.orc_separate_pairs(arr, n, m, md))
+
+
+def invert3x3(m):
+    m = np.ascontiguousarray(m, np.float32).reshape(9)
+    out = np.zeros(9, np.float32)
+    lib.orc_invert3x3.argtypes = [C.c_void_p, C.c_void_p]
+    lib.orc_invert3x3(m.ctypes.data, out.ctypes.data)
+    return out.reshape(3, 3)
+
+
+def box_track(boxes, last_objects, last_box_idx, last_omit, last_vel, img_w, img_h):
+    """Frame::boxTrack. Returns (boxes, box_idx, omit, velocity)."""
+    cap = len(boxes) + len(last_objects) + 1
+    b = np.zeros((cap, 4), np.float64); b[:len(boxes)] = np.asarray(boxes, np.float64).reshape(-1, 4)
+    lo = np.ascontiguousarray(last_objects, np.float64).reshape(-1, 4)
+    li = np.ascontiguousarray(last_box_idx, np.int32); lom = np.ascontiguousarray(last_omit, np.uint8)
+    lv = np.ascontiguousarray(last_vel, np.float64).reshape(-1, 2)
+    bi = np.zeros(cap, np.int32); om = np.zeros(cap, np.uint8); vel = np.zeros((cap, 2), np.float64)
+    lib.orc_box_track.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = lib.orc_box_track(b.ctypes.data, len(boxes), cap, lo.ctypes.data, li.ctypes.data, lom.ctypes.data, lv.ctypes.data,
+                          len(lo), img_w, img_h, bi.ctypes.data, om.ctypes.data, vel.ctypes.data)
+    return b[:n].copy(), bi[:n].copy(), om[:n].copy(), vel[:n].copy()
+
+
+def first_separate(keys, boxes, box_idx):
+    """Frame::firstSeparate + tail split.  Returns dict(order, class_id, n_dyn, boxes, box_idx, dyn=[(box, key)])."""
+    keys = np.ascontiguousarray(keys, KP_DTYPE)
+    b = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4).copy()
+    bi = np.ascontiguousarray(box_idx, np.int32).copy()
+    n = len(keys)
+    order = np.zeros(max(n, 1), np.int32); cid = np.zeros(max(n, 1), np.int32)
+    cap = max(n * max(len(b), 1), 1)
+    db = np.zeros(cap, np.int32); dk = np.zeros(cap, np.int32)
+    nd, npairs = C.c_int(0), C.c_int(0)
+    lib.orc_first_separate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    nb = lib.orc_first_separate(keys.ctypes.data, n, b.ctypes.data, bi.ctypes.data, len(b), order.ctypes.data, cid.ctypes.data,
+                                C.byref(nd), db.ctypes.data, dk.ctypes.data, cap, C.byref(npairs))
+    return {"order": order[:n].copy(), "class_id": cid[:n].copy(), "n_dyn": nd.value, "boxes": b[:nb].copy(),
+            "box_idx": bi[:nb].copy(), "dyn": list(zip(db[:npairs.value].tolist(), dk[:npairs.value].tolist()))}

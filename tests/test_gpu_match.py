@@ -1,0 +1,198 @@
+"""Parity of the CUDA matcher and dynamic-mask kernels (through the C ABI) against the CPU oracle.
+Bar: match index arrays, lock flags, match counts, point pairs and the dynamic mask are bit-exact."""
+import numpy as np
+import pytest
+
+import common
+import orc
+import pysdyn
+import scenario
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    ex = pysdyn.Extractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=1)
+    yield ex
+    ex.close()
+
+
+def pair(cfg, shift=(4, 1)):
+    W, H, _, nf, ini, mn = common.CONFIGS[cfg]
+    E = orc.Extractor(nf, 1.2, 8, ini, mn)
+    k0, d0 = E(common.frame(cfg, 0))
+    k1, d1 = E(common.frame(cfg, 1, ox=shift[0], oy=shift[1], t=1))
+    return dict(W=W, H=H, scale=E.scale, k0=k0, d0=d0, k1=k1, d1=d1, shift=shift)
+
+
+@pytest.fixture(scope="module")
+def tum():
+    return pair("tum")
+
+
+@pytest.fixture(scope="module")
+def kitti():
+    return pair("kitti", (3, 2))
+
+
+def views(p, stereo, tcw=None, d0=None, d1=None):
+    cur = scenario.frame_view(p["k1"], p["d1"] if d1 is None else d1, p["scale"], p["W"], p["H"], stereo=stereo, seed=1, tcw=tcw)
+    last = scenario.frame_view(p["k0"], p["d0"] if d0 is None else d0, p["scale"], p["W"], p["H"], stereo=stereo, seed=0)
+    return cur, last
+
+
+def test_descriptor_distance():
+    r = np.random.default_rng(0)
+    a = r.integers(0, 256, (64, 32), dtype=np.uint8); b = r.integers(0, 256, (64, 32), dtype=np.uint8)
+    for x, y in zip(a, b):
+        assert pysdyn.Matcher.DescriptorDistance(x, y) == orc.hamming(x, y)
+
+
+@pytest.mark.parametrize("data", ["tum", "kitti"])
+@pytest.mark.parametrize("stereo,th,tz", [(True, 7.0, 0.0), (False, 15.0, 0.0), (True, 7.0, 1.5), (True, 7.0, -1.5)])
+def test_search_by_projection_frame(ctx, request, data, stereo, th, tz):
+    p = request.getfixturevalue(data)
+    tcw = np.eye(4, dtype=np.float32)[:3].copy(); tcw[2, 3] = tz
+    cur, last = views(p, stereo, tcw)
+    lp = scenario.last_points(p["k0"], p["d0"], p["shift"], seed=7)
+    m = pysdyn.Matcher(ctx, 0.9, True)
+    got = m.SearchByProjectionFrame(cur, last, lp, th, not stereo, want_pairs=True)
+    ref = orc.match_projection_frame(cur, last, lp, th, not stereo, True, want_pairs=True)
+    assert got[0] == ref[0] and got[0] > 50
+    assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2]) and np.array_equal(got[3], ref[3])
+    # no orientation check + pre-occupied keypoints (locked and unlocked)
+    r = np.random.default_rng(5)
+    a0 = np.where(r.random(cur.n) < 0.2, -2, -1).astype(np.int32); l0 = (r.random(cur.n) < 0.5).astype(np.uint8)
+    m2 = pysdyn.Matcher(ctx, 0.9, False)
+    got = m2.SearchByProjectionFrame(cur, last, lp, th, not stereo, a0, l0)
+    ref = orc.match_projection_frame(cur, last, lp, th, not stereo, False, a0, l0)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+def test_search_by_projection_frame_tie_heavy(ctx, tum):
+    p = tum
+    d0 = scenario.degenerate_descriptors(len(p["k0"]), 1); d1 = scenario.degenerate_descriptors(len(p["k1"]), 2)
+    cur, last = views(p, True, d0=d0, d1=d1)
+    for p_obs in (0.5, 1.0, 0.0):
+        lp = scenario.last_points(p["k0"], d0, p["shift"], seed=9, p_obs=p_obs, noise_bits=0)
+        got = pysdyn.Matcher(ctx, 0.9, True).SearchByProjectionFrame(cur, last, lp, 15.0, False, want_pairs=True)
+        ref = orc.match_projection_frame(cur, last, lp, 15.0, False, True, want_pairs=True)
+        assert got[0] == ref[0]
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2]) and np.array_equal(got[3], ref[3])
+
+
+@pytest.mark.parametrize("data", ["tum", "kitti"])
+@pytest.mark.parametrize("th", [1.0, 3.0, 5.0])
+def test_search_by_projection_map(ctx, request, data, th):
+    p = request.getfixturevalue(data)
+    cur, _ = views(p, True)
+    mp = scenario.map_queries(p["k1"], p["d1"], 8, seed=3, count=3000)
+    r = np.random.default_rng(6)
+    a0 = np.where(r.random(cur.n) < 0.3, -2, -1).astype(np.int32); l0 = (r.random(cur.n) < 0.7).astype(np.uint8)
+    for nnratio in (0.8, 0.6):
+        got = pysdyn.Matcher(ctx, nnratio).SearchByProjectionMap(cur, mp, th, a0, l0)
+        ref = orc.match_projection_map(cur, mp, th, nnratio, a0, l0)
+        assert got[0] == ref[0] and got[0] > 50
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+def test_search_by_projection_map_tie_heavy(ctx, tum):
+    p = tum
+    d1 = scenario.degenerate_descriptors(len(p["k1"]), 2)
+    cur, _ = views(p, False, d1=d1)
+    mp = scenario.map_queries(p["k1"], d1, 8, seed=4, count=2500, jitter=6.0)
+    mp["desc"] = d1[np.random.default_rng(8).integers(0, len(d1), len(mp))]
+    mp["obs_positive"] = np.random.default_rng(9).random(len(mp)) < 0.5
+    got = pysdyn.Matcher(ctx, 0.8).SearchByProjectionMap(cur, mp, 5.0)
+    ref = orc.match_projection_map(cur, mp, 5.0, 0.8)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+@pytest.mark.parametrize("data", ["tum", "kitti"])
+def test_search_for_initialization(ctx, request, data):
+    p = request.getfixturevalue(data)
+    cur, last = views(p, False)
+    prev = np.stack([p["k0"]["x"], p["k0"]["y"]], 1)
+    for check in (True, False):
+        got = pysdyn.Matcher(ctx, 0.9, check).SearchForInitialization(last, cur, prev, 100)
+        ref = orc.match_init(last, cur, prev, 100, 0.9, check)
+        assert got[0] == ref[0] and got[0] > 30
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    # tie-heavy: stealing (vnMatches21) and the matched-distance gate are exercised constantly
+    d0 = scenario.degenerate_descriptors(len(p["k0"]), 11, 40); d1 = scenario.degenerate_descriptors(len(p["k1"]), 12, 40)
+    d1[: len(d1) // 2] = d0[: len(d1) // 2][: len(d1[: len(d1) // 2])] if len(d0) >= len(d1) // 2 else d1[: len(d1) // 2]
+    cur, last = views(p, False, d0=d0, d1=d1)
+    got = pysdyn.Matcher(ctx, 0.9, True).SearchForInitialization(last, cur, prev, 100)
+    ref = orc.match_init(last, cur, prev, 100, 0.9, True)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+@pytest.mark.parametrize("data", ["tum", "kitti"])
+def test_search_by_bow(ctx, request, data):
+    p = request.getfixturevalue(data)
+    cur, last = views(p, False)
+    fa = pysdyn.FeatureVector(scenario.bow_nodes(p["d0"])); fb = pysdyn.FeatureVector(scenario.bow_nodes(p["d1"]))
+    valid = (np.random.default_rng(2).random(last.n) < 0.8).astype(np.uint8)
+    for check in (True, False):
+        got = pysdyn.Matcher(ctx, 0.7, check).SearchByBoW(last, valid, fa, cur, fb)
+        ref = orc.match_bow(last, valid, fa, cur, fb, 0.7, check)
+        assert got[0] == ref[0] and got[0] > 30 and np.array_equal(got[1], ref[1])
+    d0 = scenario.degenerate_descriptors(last.n, 21, 30); d1 = scenario.degenerate_descriptors(cur.n, 22, 30)
+    cur, last = views(p, False, d0=d0, d1=d1)
+    fa = pysdyn.FeatureVector(scenario.bow_nodes(d0, 3)); fb = pysdyn.FeatureVector(scenario.bow_nodes(d1, 3))
+    got = pysdyn.Matcher(ctx, 0.95, True).SearchByBoW(last, valid, fa, cur, fb)
+    ref = orc.match_bow(last, valid, fa, cur, fb, 0.95, True)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1])
+
+
+def test_empty_inputs(ctx, tum):
+    p = tum
+    cur, last = views(p, False)
+    m = pysdyn.Matcher(ctx)
+    n, a, l = m.SearchByProjectionMap(cur, np.zeros(0, pysdyn.MAPPOINT_DTYPE), 3.0)
+    assert n == 0 and (a == -1).all()
+    empty = scenario.frame_view(p["k0"][:0], p["d0"][:0], p["scale"], p["W"], p["H"])
+    n, a, l = m.SearchByProjectionFrame(cur, empty, np.zeros(0, pysdyn.LASTPOINT_DTYPE), 7.0, True)
+    assert n == 0 and (a == -1).all()
+    n, m12, prev = m.SearchForInitialization(empty, cur, np.zeros((0, 2), np.float32))
+    assert n == 0 and len(m12) == 0
+
+
+def test_box_mask(ctx, kitti):
+    p = kitti
+    boxes = pysdyn.synth_boxes(7, p["W"], p["H"], 160, 3, 2, 1, margin=10)
+    assert len(boxes) >= 3
+    boxes = np.concatenate([boxes, [[100.0, 50.0, 0.0, 0.0], [p["k1"]["x"][0], p["k1"]["y"][0], 1.0, 1.0]]])  # empty box; box edge on a keypoint
+    got = pysdyn.box_mask(ctx, p["k1"], boxes)
+    ref = orc.box_mask(p["k1"], boxes)
+    assert np.array_equal(got, ref) and (ref != 0).sum() > 10
+    assert np.array_equal(pysdyn.box_mask(ctx, p["k1"], np.zeros((0, 4))), np.zeros(len(p["k1"]), np.uint64))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_separate_pairs(ctx, kitti, mode):
+    """BFMatcher(crossCheck) + classifyF / classifyH per box pair."""
+    p = kitti
+    r = np.random.default_rng(3)
+    pairs = []
+    for b in range(6):
+        qi = r.choice(len(p["k1"]), int(r.integers(0, 120)), replace=False)
+        ti = r.choice(len(p["k0"]), int(r.integers(0, 120)), replace=False)
+        qd, td = p["d1"][qi], p["d0"][ti]
+        if b == 4:
+            qd = scenario.degenerate_descriptors(len(qi), 5, 4); td = scenario.degenerate_descriptors(len(ti), 6, 4)
+        qx = np.stack([p["k1"]["x"][qi], p["k1"]["y"][qi]], 1); tx = np.stack([p["k0"]["x"][ti], p["k0"]["y"][ti]], 1)
+        if b == 5 and len(ti):
+            tx = qx[: len(ti)] + np.float32([3, 2]) if len(qi) >= len(ti) else tx      # geometrically consistent pairs
+        pairs.append((qd, qx, td, tx))
+    if mode == 0:   # F of a pure image translation (3, 2): x2^T F x1 = 0 for x2 = x1 - t
+        M = np.float32([[0, 0, 2], [0, 0, -3], [-2, 3, 0]])
+    else:
+        M = np.float32([[1, 0, -3], [0, 1, -2], [1e-5, 0, 1]])
+    got = pysdyn.separate_pairs(ctx, pairs, M, mode)
+    ref = orc.separate_pairs(pairs, M, mode)
+    for g, e in zip(got, ref):
+        for a, b in zip(g, e):
+            assert np.array_equal(a, b)
+    assert sum(len(g[0]) for g in got) > 20

@@ -1,0 +1,222 @@
+"""Pins for the oracle's matcher / dynamic-mask restatement (CPU only).
+The reference ships no tests; these check the oracle against cv2 4.13.0 where OpenCV is the
+dependency (BFMatcher, invert, gemm) and against independent brute-force re-statements elsewhere."""
+import math
+import numpy as np
+import pytest
+
+import common
+import orc
+import pysdyn
+import scenario
+
+cv2 = pytest.importorskip("cv2")
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def tum_pair():
+    W, H, _, nf, ini, mn = common.CONFIGS["tum"]
+    E = orc.Extractor(nf, 1.2, 8, ini, mn)
+    k0, d0 = E(common.frame("tum", 0))
+    k1, d1 = E(common.frame("tum", 1, ox=4, oy=1, t=1))
+    return dict(W=W, H=H, scale=E.scale, k0=k0, d0=d0, k1=k1, d1=d1)
+
+
+def test_hamming_matches_numpy_popcount():
+    r = np.random.default_rng(1)
+    a = r.integers(0, 256, (200, 32), dtype=np.uint8); b = r.integers(0, 256, (200, 32), dtype=np.uint8)
+    ref = np.unpackbits(a ^ b, axis=1).sum(1)
+    assert [orc.hamming(x, y) for x, y in zip(a, b)] == ref.tolist()
+    assert orc.hamming(a[0], a[0]) == 0 and orc.hamming(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+def py_features_in_area(F, x, y, r, min_level, max_level):
+    """Independent re-statement of Frame::GetFeaturesInArea + AssignFeaturesToGrid (Frame.cc:463-478, 735-800)."""
+    minx, miny, maxx, maxy = (f32(v) for v in F.bounds)
+    winv, hinv = f32(64) / f32(maxx - minx), f32(48) / f32(maxy - miny)
+    grid = {}
+    for i, kp in enumerate(F.keys_un):
+        px = f32(f32(kp["x"] - minx) * winv); py = f32(f32(kp["y"] - miny) * hinv)
+        gx = int(math.floor(abs(px) + 0.5)) * (1 if px >= 0 else -1)      # C round(): half away from zero
+        gy = int(math.floor(abs(py) + 0.5)) * (1 if py >= 0 else -1)
+        if 0 <= gx < 64 and 0 <= gy < 48:
+            grid.setdefault((gx, gy), []).append(i)
+    x, y, r = f32(x), f32(y), f32(r)
+    cx0 = max(0, int(math.floor(f32(f32(f32(x - minx) - r) * winv))))
+    cx1 = min(63, int(math.ceil(f32(f32(f32(x - minx) + r) * winv))))
+    cy0 = max(0, int(math.floor(f32(f32(f32(y - miny) - r) * hinv))))
+    cy1 = min(47, int(math.ceil(f32(f32(f32(y - miny) + r) * hinv))))
+    if cx0 >= 64 or cx1 < 0 or cy0 >= 48 or cy1 < 0:
+        return []
+    check = min_level > 0 or max_level >= 0
+    out = []
+    for ix in range(cx0, cx1 + 1):
+        for iy in range(cy0, cy1 + 1):
+            for i in grid.get((ix, iy), []):
+                kp = F.keys_un[i]
+                if check and (kp["octave"] < min_level or (max_level >= 0 and kp["octave"] > max_level)):
+                    continue
+                if abs(f32(kp["x"] - x)) < r and abs(f32(kp["y"] - y)) < r:
+                    out.append(i)
+    return out
+
+
+def test_features_in_area_order_and_filters(tum_pair):
+    p = tum_pair
+    F = scenario.frame_view(p["k1"], p["d1"], p["scale"], p["W"], p["H"])
+    r = np.random.default_rng(2)
+    for _ in range(60):
+        x, y = float(r.uniform(-30, p["W"] + 30)), float(r.uniform(-30, p["H"] + 30))
+        rad = float(r.choice([3.0, 7.0, 25.0, 100.0]))
+        lv = [(-1, -1), (0, 0), (2, -1), (0, 3), (1, 2), (-1, 0)][int(r.integers(0, 6))]
+        assert orc.features_in_area(F, x, y, rad, *lv).tolist() == py_features_in_area(F, x, y, rad, *lv)
+
+
+def test_bf_crosscheck_equals_cv2_bfmatcher():
+    """SURVEY A-7: BFMatcher(NORM_HAMMING, crossCheck=True) = strict mutual NN, lowest index on ties."""
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING, True)
+    for seed in range(25):
+        r = np.random.default_rng(seed)
+        nq, nt = int(r.integers(1, 40)), int(r.integers(1, 40))
+        q = scenario.degenerate_descriptors(nq, seed, 6); t = scenario.degenerate_descriptors(nt, seed + 1, 6)
+        if seed % 3 == 0:
+            q = r.integers(0, 256, (nq, 32), dtype=np.uint8); t = r.integers(0, 256, (nt, 32), dtype=np.uint8)
+        ref = [(m.queryIdx, m.trainIdx, int(m.distance)) for m in bf.match(q, t)]
+        xy = np.zeros((max(nq, nt), 2), np.float32)
+        mq, mt, md, _ = orc.separate_pairs([(q, xy[:nq], t, xy[:nt])], np.eye(3), 0)[0]
+        assert list(zip(mq.tolist(), mt.tolist(), md.tolist())) == ref
+
+
+def test_invert3x3_equals_cv2():
+    r = np.random.default_rng(3)
+    for _ in range(300):
+        H = (np.eye(3) + r.normal(size=(3, 3)) * 0.2).astype(np.float32)
+        assert np.array_equal(cv2.invert(H)[1], orc.invert3x3(H))
+
+
+def test_cv_gemm_3x3_is_sequential_float():
+    """The projection Rcw*x3Dw+tcw in ORBmatcher.cc:1519 runs OpenCV's small-matrix path: float products
+    summed left to right, then the addend — the semantics the oracle and the kernel both restate."""
+    r = np.random.default_rng(4)
+    for _ in range(500):
+        R = r.normal(size=(3, 3)).astype(np.float32); x = (r.normal(size=(3, 1)) * 10).astype(np.float32)
+        t = r.normal(size=(3, 1)).astype(np.float32)
+        ref = cv2.gemm(R, x, 1.0, t, 1.0)
+        mine = np.array([[f32(f32(f32(f32(R[i, 0] * x[0, 0]) + f32(R[i, 1] * x[1, 0])) + f32(R[i, 2] * x[2, 0])) + t[i, 0])]
+                         for i in range(3)], np.float32)
+        assert np.array_equal(ref, mine)
+
+
+def py_search_frame(cur, last, lp, th, mono, check_ori):
+    """Independent Python re-statement of SearchByProjection(Cur, Last, th, bMono), ORBmatcher.cc:1485-1627."""
+    T = cur.tcw.reshape(3, 4); Tl = last.tcw.reshape(3, 4)
+    fx, fy, cx, cy, bf, b = (f32(v) for v in cur.cam)
+    twc = [f32(-1.0 * sum(float(T[k, r]) * float(T[k, 3]) for k in range(3))) for r in range(3)]
+    tlc = [f32(f32(f32(f32(Tl[r, 0] * twc[0]) + f32(Tl[r, 1] * twc[1])) + f32(Tl[r, 2] * twc[2])) + Tl[r, 3]) for r in range(3)]
+    fwd = tlc[2] > b and not mono; bwd = -tlc[2] > b and not mono
+    assign = np.full(cur.n, -1, np.int32); locked = np.zeros(cur.n, np.uint8)
+    hist = [[] for _ in range(30)]
+    n = 0
+    for i in range(last.n):
+        if not lp["has_mp"][i] or lp["outlier"][i]:
+            continue
+        w = lp["world"][i]
+        pc = [f32(f32(f32(f32(T[r, 0] * w[0]) + f32(T[r, 1] * w[1])) + f32(T[r, 2] * w[2])) + T[r, 3]) for r in range(3)]
+        invz = f32(1.0 / float(pc[2]))
+        if invz < 0:
+            continue
+        u = f32(f32(f32(fx * pc[0]) * invz) + cx); v = f32(f32(f32(fy * pc[1]) * invz) + cy)
+        if u < cur.bounds[0] or u > cur.bounds[2] or v < cur.bounds[1] or v > cur.bounds[3]:
+            continue
+        oc = int(last.keys["octave"][i])
+        radius = f32(f32(th) * cur.scale[oc])
+        lv = (oc, -1) if fwd else ((0, oc) if bwd else (oc - 1, oc + 1))
+        best, bi = 256, -1
+        for i2 in py_features_in_area(cur, u, v, radius, *lv):
+            if assign[i2] != -1 and locked[i2]:
+                continue
+            if cur.u_right is not None and cur.u_right[i2] > 0:
+                ur = f32(u - f32(bf * invz))
+                if abs(f32(ur - cur.u_right[i2])) > radius:
+                    continue
+            d = int(np.unpackbits(lp["desc"][i] ^ cur.desc[i2]).sum())
+            if d < best:
+                best, bi = d, i2
+        if best <= 100:
+            assign[bi] = i; locked[bi] = lp["obs_positive"][i]; n += 1
+            if check_ori:
+                rot = f32(last.keys_un["angle"][i] - cur.keys_un["angle"][bi])
+                if rot < 0:
+                    rot = f32(rot + f32(360))
+                bn = int(math.floor(float(f32(rot * f32(1.0 / 30))) + 0.5))
+                hist[0 if bn == 30 else bn].append(bi)
+    if check_ori:
+        sizes = [len(h) for h in hist]
+        m1 = m2 = m3 = 0; i1 = i2_ = i3 = -1
+        for i, s in enumerate(sizes):
+            if s > m1:
+                m3, m2, m1, i3, i2_, i1 = m2, m1, s, i2_, i1, i
+            elif s > m2:
+                m3, m2, i3, i2_ = m2, s, i2_, i
+            elif s > m3:
+                m3, i3 = s, i
+        if m2 < f32(0.1) * f32(m1):
+            i2_ = i3 = -1
+        elif m3 < f32(0.1) * f32(m1):
+            i3 = -1
+        for i, h in enumerate(hist):
+            if i in (i1, i2_, i3):
+                continue
+            for idx in h:
+                assign[idx] = -1; locked[idx] = 0; n -= 1
+    return n, assign, locked
+
+
+@pytest.mark.parametrize("stereo,th,tz", [(True, 7.0, 0.0), (False, 15.0, 0.0), (True, 7.0, 1.5), (True, 7.0, -1.5)])
+def test_search_frame_oracle_vs_python(tum_pair, stereo, th, tz):
+    p = tum_pair
+    tcw = np.eye(4, dtype=np.float32)[:3].copy(); tcw[2, 3] = tz       # forward / backward motion branches
+    cur = scenario.frame_view(p["k1"], p["d1"], p["scale"], p["W"], p["H"], stereo=stereo, seed=1, tcw=tcw)
+    last = scenario.frame_view(p["k0"], p["d0"], p["scale"], p["W"], p["H"], stereo=stereo, seed=0)
+    lp = scenario.last_points(p["k0"], p["d0"], (4, 1), seed=7)
+    ref = py_search_frame(cur, last, lp, th, not stereo, True)
+    got = orc.match_projection_frame(cur, last, lp, th, not stereo, True)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    assert got[0] > 100
+
+
+def test_search_frame_tie_heavy(tum_pair):
+    """Few distinct descriptors + unlocked (Observations()==0) claims: ties, overwrites and stale histogram
+    entries all occur; oracle and the independent Python re-statement must still agree."""
+    p = tum_pair
+    d0 = scenario.degenerate_descriptors(len(p["k0"]), 1); d1 = scenario.degenerate_descriptors(len(p["k1"]), 2)
+    cur = scenario.frame_view(p["k1"], d1, p["scale"], p["W"], p["H"], stereo=True, seed=1)
+    last = scenario.frame_view(p["k0"], d0, p["scale"], p["W"], p["H"], stereo=True, seed=0)
+    lp = scenario.last_points(p["k0"], d0, (4, 1), seed=9, p_obs=0.5, noise_bits=0)
+    ref = py_search_frame(cur, last, lp, 15.0, False, True)
+    got = orc.match_projection_frame(cur, last, lp, 15.0, False, True)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+def test_first_separate_erase_skip_bug():
+    """Appendix B-4, literally: boxes are erased while iterating without --i and hasKpts is not erased in step,
+    so with boxes [A(kp), B(empty), C(empty), D(kp)] the loop erases B, then tests hasKpts[2] (C's flag) against
+    the box that slid into slot 2 (D) and erases D: the empty C survives and the occupied D is dropped."""
+    keys = np.zeros(3, orc.KP_DTYPE); keys["class_id"] = -1
+    keys["x"] = [10, 50, 200]; keys["y"] = [10, 50, 200]
+    boxes = [[0, 0, 20, 20], [300, 300, 5, 5], [310, 310, 5, 5], [190, 190, 20, 20]]
+    r = orc.first_separate(keys, boxes, [0, 1, 2, 3])
+    assert r["n_dyn"] == 2 and r["order"].tolist() == [1, 0, 2]
+    assert r["boxes"].tolist() == [[0, 0, 20, 20], [310, 310, 5, 5]] and r["box_idx"].tolist() == [0, 2]
+    assert r["class_id"].tolist() == [0, -1, 2]
+    assert r["dyn"] == [(0, 0), (1, 2)]              # index 3 - (two empty boxes before it) = 1
+
+
+def test_box_track_assigns_ids_and_carries_boxes():
+    b, idx, omit, vel = orc.box_track([[10, 10, 50, 50]], [], [], [], [], 640, 480)
+    assert idx.tolist() == [0]
+    last = [[12, 11, 50, 50], [300, 200, 40, 40]]
+    b, idx, omit, vel = orc.box_track([[14, 12, 50, 50]], last, [0, 1], [0, 0], [[0, 0], [5, 0]], 640, 480)
+    assert idx.tolist() == [0, 1] and omit.tolist() == [0, 1]          # second box carried over with its velocity
+    assert np.allclose(b[1], [305, 200, 40, 40]) and np.allclose(vel[0], [2, 1])
