@@ -244,6 +244,51 @@ typedef struct {
  * status logic stay in the adapter. */
 int sdyn_dyn_separate(sdyn_ctx* ctx, sdyn_box_pair* pairs, int npairs, const float* m3x3, int mode);
 
+/* ---- batched front end: extract + track + dynamic mask, device-resident ---------------------------------
+ * One call processes nframes independent frames (frame / sequence sharding is the caller's: there is no
+ * cross-frame or cross-GPU exchange).  Per frame f, in this order on one stream:
+ *   1. ORBextractor::operator()                                   (as sdyn_extract_batch_device)
+ *   2. SearchByProjection(CurrentFrame, LastFrame, th, bMono)     src/ORBmatcher.cc:1485  (TrackWithMotionModel)
+ *   3. SearchByProjection(CurrentFrame, vpMapPoints, th)          src/ORBmatcher.cc:45    (SearchLocalPoints),
+ *      on the mvpMapPoints left by step 2
+ *   4. dynamic mask: Frame::firstSeparate's box test, Tracking::Separate's per-box BFMatcher + classifyF and
+ *      Frame::UpdateFrame's re-admission:  mask[i] = in_box(i) && !readmitted(i)
+ * Searches see every extracted keypoint (the stereo constructor's behaviour, where firstSeparate is disabled,
+ * src/Frame.cc:166).  All pointers are DEVICE pointers; per-frame arrays are `*_stride` elements apart. */
+typedef struct {
+    /* LastFrame of every current frame */
+    const sdyn_last_point* last_points; const sdyn_keypoint* last_keys; const sdyn_keypoint* last_keys_un;
+    const int32_t* n_last; int32_t last_stride;
+    /* local map of every current frame */
+    const sdyn_mappoint_query* map_points; const int32_t* n_map; int32_t map_stride;
+    /* detection boxes (cv::Rect2d, 64 x 4 doubles per frame) and, per box, the reference frame's box joined by
+     * Frame::boxTrack (ref_box[f*64+b] = index into that frame's reference boxes or -1) */
+    const double* boxes; const int32_t* n_boxes; const int32_t* ref_box;
+    /* reference frame's per-box dynamic keypoints (mdynDescriptors / mvdynKeysUn): box r of frame f occupies
+     * [ref_off[f*65+r], ref_off[f*65+r+1]) of that frame's ref_desc / ref_xy block */
+    const uint8_t* ref_desc; const float* ref_xy; const int32_t* ref_off; int32_t ref_stride;
+    const float* fmat;              /* F21 per frame, 9 floats (classifyF) */
+    /* camera / pose / search parameters shared by the batch */
+    float min_x, min_y, max_x, max_y, fx, fy, cx, cy, bf, b;
+    float tcw_cur[12], tcw_last[12];
+    float th_frame, th_map, nnratio_map;
+    int32_t mono, check_orientation;
+} sdyn_track_inputs;
+
+typedef struct {
+    const int32_t* assign;          /* [max_batch][cap]: mvpMapPoints after steps 2+3: -1, last index, or n_last + map index */
+    const uint8_t* locked;          /* [max_batch][cap] */
+    const uint8_t* dyn_mask;        /* [max_batch][cap] */
+    const int32_t* counts;          /* [max_batch][4]: nmatches of step 2, nmatches of step 3, #in-box, #masked */
+} sdyn_track_view;
+
+int sdyn_track_batch_device(sdyn_ctx* ctx, int nframes, const uint8_t* d_gray, size_t frame_stride,
+                            int width, int height, int stride, const sdyn_track_inputs* in, void* stream);
+int sdyn_track_results(const sdyn_ctx* ctx, sdyn_track_view* out);
+/* D2H of the step results next to sdyn_fetch_results (host arrays sized [nframes][cap] / [nframes][4]). */
+int sdyn_track_fetch(sdyn_ctx* ctx, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dyn_mask,
+                     int32_t* counts, int cap, void* stream);
+
 /* ---- per-stage device timing (CUDA events on the launching stream) -------------------------------
  * While enabled, every enqueue brackets each stage with events; sdyn_profile_read synchronises and
  * returns the accumulated milliseconds and launch counts since the last read. */

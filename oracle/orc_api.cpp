@@ -109,10 +109,10 @@ int orc_features_in_area(const sdyn_frame_view* v, float x, float y, float r, in
 }
 
 int orc_match_projection_map(const sdyn_frame_view* v, const sdyn_mappoint_query* mps, int nmp, float th, float nnratio,
-                             int32_t* assign, uint8_t* locked)
+                             int32_t* assign, uint8_t* locked, int assignBase)
 {
     FrameView f = view_of(v); Grid g; assign_features_to_grid(f, g);
-    return search_by_projection_map(f, g, reinterpret_cast<const MapPointQuery*>(mps), nmp, th, nnratio, assign, locked);
+    return search_by_projection_map(f, g, reinterpret_cast<const MapPointQuery*>(mps), nmp, th, nnratio, assign, locked, assignBase);
 }
 
 int orc_match_projection_frame(const sdyn_frame_view* cur, const sdyn_frame_view* last, const sdyn_last_point* lp, float th,

@@ -102,7 +102,7 @@ static inline int rot_bin(float rot)
 
 /* ORBmatcher.cc:45-129 */
 int search_by_projection_map(const FrameView& F, const Grid& g, const MapPointQuery* mps, int nmp, float th,
-                             float nnratio, int32_t* assign, uint8_t* locked)
+                             float nnratio, int32_t* assign, uint8_t* locked, int assignBase)
 {
     int nmatches = 0;
     const bool bFactor = th != 1.0;
@@ -135,7 +135,7 @@ int search_by_projection_map(const FrameView& F, const Grid& g, const MapPointQu
         }
         if (bestDist <= TH_HIGH) {
             if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
-            assign[bestIdx] = iMP;
+            assign[bestIdx] = assignBase + iMP;   /* index encoding of `F.mvpMapPoints[bestIdx]=pMP` */
             locked[bestIdx] = mp.obsPositive;
             ++nmatches;
         }

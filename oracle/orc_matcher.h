@@ -50,7 +50,7 @@ struct MapPointQuery {          /* the MapPoint fields SearchByProjection(F, vpM
 
 /* ORBmatcher.cc:45-129 */
 int search_by_projection_map(const FrameView& F, const Grid& g, const MapPointQuery* mps, int nmp, float th,
-                             float nnratio, int32_t* assign, uint8_t* locked);
+                             float nnratio, int32_t* assign, uint8_t* locked, int assignBase = 0);
 
 struct LastFramePoint {         /* per keypoint of LastFrame */
     uint8_t hasMP, outlier, obsPositive, pad;   /* mvpMapPoints[i] != NULL, mvbOutlier[i], Observations()>0 */

@@ -308,14 +308,14 @@ k_match_resolve(const MatchJob* __restrict__ jobs)
                 if (lane == 0) {
                     if (J.mode == MM_FRAME) {
                         const sdyn_last_point* lp = reinterpret_cast<const sdyn_last_point*>(J.queries) + q;
-                        assign[bestIdx] = q; locked[bestIdx] = lp->obs_positive;
+                        assign[bestIdx] = J.assignBase + q; locked[bestIdx] = lp->obs_positive;
                         if (J.pairs) {
                             J.pairs[4 * npairs] = J.qKeysUn[q].x; J.pairs[4 * npairs + 1] = J.qKeysUn[q].y;
                             J.pairs[4 * npairs + 2] = J.keysUn[bestIdx].x; J.pairs[4 * npairs + 3] = J.keysUn[bestIdx].y;
                         }
                     } else if (J.mode == MM_MAP) {
                         const sdyn_mappoint_query* mp = reinterpret_cast<const sdyn_mappoint_query*>(J.queries) + q;
-                        assign[bestIdx] = q; locked[bestIdx] = mp->obs_positive;
+                        assign[bestIdx] = J.assignBase + q; locked[bestIdx] = mp->obs_positive;
                     } else if (J.mode == MM_INIT) {
                         const int prev = m21[bestIdx];
                         if (prev >= 0) { assign[prev] = -1; --nmatches; }

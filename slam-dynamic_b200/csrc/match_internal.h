@@ -38,6 +38,7 @@ struct MatchJob {
     /* parameters */
     float th, nnratio;
     int checkOri, forward, backward, window;
+    int assignBase;                  /* value written to assign[] = assignBase + query index (FRAME / MAP) */
     float Tcw[12], fx, fy, cx, cy, bf;
     /* state / outputs */
     int32_t* assign;                 /* FRAME/MAP/BOW: per searched keypoint; INIT: matches12 per query */
@@ -70,6 +71,10 @@ struct BoxPairJob {
 cudaError_t launch_box_mask(const sdyn_keypoint* dKeys, const int32_t* nPtr, int n, int keyStride,
                             const double* dBoxes, const int32_t* nBoxesPtr, int nboxes, int boxStride,
                             uint64_t* dMask, int njobs, cudaStream_t st);
+cudaError_t launch_dyn_stage(const sdyn_track_inputs& in, const sdyn_keypoint* kp, const uint8_t* desc, const int32_t* count,
+                             int cap, uint64_t* mask, unsigned long long* has, int32_t* boxList, int32_t* nnQ, int32_t* nnT,
+                             int nnTStride, uint8_t* readmit, int32_t* staticExit, uint8_t* dynMask, int32_t* counts,
+                             int nframes, cudaStream_t st);
 cudaError_t launch_box_pairs(const BoxPairJob* dJobs, int njobs, const float* dM, const float* dMinv, int mode,
                              cudaStream_t st);
 

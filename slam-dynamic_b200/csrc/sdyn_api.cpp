@@ -44,6 +44,9 @@ void build_tiles(const Geom& g, std::vector<TileRef>& fast, std::vector<TileRef>
     }
 }
 
+}  // namespace
+
+namespace sdyn {
 /* (Re)computes geometry when the image size changes; device buffers were sized for (maxW, maxH). */
 int ensure_geometry(sdyn_ctx* c, int W, int H)
 {
@@ -69,6 +72,9 @@ int ensure_geometry(sdyn_ctx* c, int W, int H)
     return SDYN_OK;
 }
 
+}  // namespace sdyn
+
+namespace {
 cudaEvent_t take_event(sdyn_ctx* c)
 {
     cudaEvent_t e = nullptr;
@@ -91,17 +97,17 @@ void drain_spans(sdyn_ctx* c)
     c->spans.clear();
 }
 
-struct StageTimer {
-    sdyn_ctx* c; cudaStream_t st; int stage; cudaEvent_t a;
-    StageTimer(sdyn_ctx* c_, cudaStream_t st_, int stage_) : c(c_), st(st_), stage(stage_), a(nullptr)
-    {
-        if (c->profiling) { a = take_event(c); cudaEventRecord(a, st); }
-    }
-    ~StageTimer()
-    {
-        if (a) { cudaEvent_t b = take_event(c); cudaEventRecord(b, st); c->spans.push_back({a, b, stage}); }
-    }
-};
+}  // namespace
+
+namespace sdyn {
+StageTimer::StageTimer(sdyn_ctx* c_, cudaStream_t st_, int stage_) : c(c_), st(st_), stage(stage_), a(nullptr)
+{
+    if (c->profiling) { a = take_event(c); cudaEventRecord(a, st); }
+}
+StageTimer::~StageTimer()
+{
+    if (a) { cudaEvent_t b = take_event(c); cudaEventRecord(b, st); c->spans.push_back({a, b, stage}); }
+}
 
 /* Enqueues the whole extraction pipeline for nframes frames already resident in device memory. */
 int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride, int rowStride, cudaStream_t st)
@@ -139,8 +145,12 @@ int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frame
     return SDYN_OK;
 }
 
+}  // namespace sdyn
+
+namespace {
 void free_all(sdyn_ctx* c)
 {
+    sdyn::free_track_state(c);
     cudaFree(c->dFastTiles); cudaFree(c->dBlurTiles); cudaFree(c->dTables); cudaFree(c->dIn); cudaFree(c->dPyr);
     cudaFree(c->dBlur); cudaFree(c->dCellFlag); cudaFree(c->dCand); cudaFree(c->dCandNode); cudaFree(c->dCandCount); cudaFree(c->dSelCount);
     cudaFree(c->dLevelKp); cudaFree(c->dLevelCount); cudaFree(c->dCount); cudaFree(c->dStatus); cudaFree(c->dKp);

@@ -94,6 +94,7 @@ struct sdyn_ctx {
     sdyn_keypoint* dKp; uint8_t* dDesc;        /* [maxBatch][maxKp] */
     /* matcher / dynamic-mask arena (grown on demand, reused across calls) */
     uint8_t* dArena; size_t arenaCap;
+    void* track;                               /* TrackState of the batched front end (sdyn_track.cpp) */
     /* per-stage profiling */
     bool profiling;
     std::vector<cudaEvent_t> evPool;           /* free events */
@@ -105,6 +106,17 @@ struct sdyn_ctx {
 };
 
 namespace sdyn {
+
+/* sdyn_api.cpp */
+int ensure_geometry(sdyn_ctx* c, int W, int H);
+int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride, int rowStride, cudaStream_t st);
+struct StageTimer {          /* brackets a stage with CUDA events while profiling is enabled */
+    sdyn_ctx* c; cudaStream_t st; int stage; cudaEvent_t a;
+    StageTimer(sdyn_ctx* c, cudaStream_t st, int stage);
+    ~StageTimer();
+};
+/* sdyn_track.cpp */
+void free_track_state(sdyn_ctx* c);
 
 /* geometry.cpp */
 void compute_scale_info(const sdyn_orb_params& p, sdyn_scale_info& s, int umax[16]);

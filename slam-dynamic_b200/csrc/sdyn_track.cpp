@@ -1,0 +1,246 @@
+/* Batched, device-resident front end: extract -> SearchByProjection(cur,last) -> SearchByProjection(F,map)
+ * -> dynamic mask, enqueued on one stream without host synchronisation (include/sdyn.h, "batched front end"). */
+#include "match_internal.h"
+#include <algorithm>
+#include <cstring>
+
+namespace sdyn {
+
+int api_fail(sdyn_ctx* c, int code, const std::string& msg);
+
+struct TrackState {
+    int B = 0, cap = 0, maxQ = 0, refStride = 0, poolPerJob = 0;
+    uint8_t* block = nullptr; size_t bytes = 0;
+    /* carved from block */
+    MatchJob* dJobs; int32_t* cellOff; int32_t* sorted; int32_t* cellOf; int32_t* assign; uint8_t* locked;
+    int2* qspan; int32_t* qAccepted; int32_t* qBin; uint32_t* pool; int32_t* poolUsed; int32_t* result;
+    uint64_t* mask; unsigned long long* has; int32_t* boxList; int32_t* nnQ; int32_t* nnT; uint8_t* readmit;
+    int32_t* staticExit; uint8_t* dynMask; int32_t* counts;
+    size_t zeroFrom = 0, zeroBytes = 0;     /* region cleared at the start of every step */
+    std::vector<MatchJob> hJobs;
+    /* pinned staging for sdyn_track_fetch */
+    int32_t* hAssign = nullptr; uint8_t* hLocked = nullptr; uint8_t* hMask = nullptr; int32_t* hCounts = nullptr; int32_t* hResult = nullptr;
+};
+
+void free_track_state(sdyn_ctx* c)
+{
+    TrackState* t = static_cast<TrackState*>(c->track);
+    if (!t) return;
+    cudaFree(t->block);
+    cudaFreeHost(t->hAssign); cudaFreeHost(t->hLocked); cudaFreeHost(t->hMask); cudaFreeHost(t->hCounts); cudaFreeHost(t->hResult);
+    delete t;
+    c->track = nullptr;
+}
+
+static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
+{
+    TrackState* t = static_cast<TrackState*>(c->track);
+    const int B = c->maxBatch, cap = c->maxKp;
+    if (t && t->maxQ >= maxQ && t->refStride >= refStride) return SDYN_OK;
+    if (t) { cudaStreamSynchronize(c->stream); free_track_state(c); }
+    t = new TrackState();
+    t->B = B; t->cap = cap; t->maxQ = maxQ; t->refStride = refStride;
+    t->poolPerJob = std::max(64 * maxQ, 1 << 16);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t J = 2 * (size_t)B;
+    const size_t oJobs = take(J * sizeof(MatchJob));
+    const size_t oCellOff = take((size_t)B * (kGridCells + 1) * 4), oSorted = take((size_t)B * cap * 4), oCellOf = take((size_t)B * cap * 4);
+    const size_t oQspan = take(J * maxQ * sizeof(int2)), oQAcc = take(J * maxQ * 4), oQBin = take(J * maxQ * 4);
+    const size_t oPool = take(J * (size_t)t->poolPerJob * 4);
+    const size_t oMask = take((size_t)B * cap * 8), oHas = take((size_t)B * 8);
+    const size_t oBoxList = take((size_t)B * 64 * cap * 4), oNnQ = take((size_t)B * 64 * cap * 4);
+    const size_t oNnT = take((size_t)B * 64 * std::max(refStride, 1) * 4);
+    const size_t oDynMask = take((size_t)B * cap);
+    /* cleared every step, contiguous: */
+    const size_t zeroFrom = off;
+    const size_t oAssign = take((size_t)B * cap * 4);      /* set to -1 separately */
+    const size_t oLocked = take((size_t)B * cap);
+    const size_t oPoolUsed = take(J * 4), oResult = take(J * 4 * 4);
+    const size_t oReadmit = take((size_t)B * cap), oStatic = take((size_t)B * 4), oCounts = take((size_t)B * 16);
+    t->zeroFrom = oLocked; t->zeroBytes = off - oLocked;
+    (void)zeroFrom;
+    t->bytes = off;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&t->block), off);
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&t->hAssign), (size_t)B * cap * 4);
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&t->hLocked), (size_t)B * cap);
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&t->hMask), (size_t)B * cap);
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&t->hCounts), (size_t)B * 16);
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&t->hResult), J * 16);
+    if (e != cudaSuccess) {
+        c->track = t; free_track_state(c);
+        return api_fail(c, SDYN_ERR_NOMEM, std::string("track state: ") + cudaGetErrorString(e));
+    }
+    uint8_t* b = t->block;
+    t->dJobs = reinterpret_cast<MatchJob*>(b + oJobs);
+    t->cellOff = reinterpret_cast<int32_t*>(b + oCellOff); t->sorted = reinterpret_cast<int32_t*>(b + oSorted);
+    t->cellOf = reinterpret_cast<int32_t*>(b + oCellOf);
+    t->qspan = reinterpret_cast<int2*>(b + oQspan); t->qAccepted = reinterpret_cast<int32_t*>(b + oQAcc);
+    t->qBin = reinterpret_cast<int32_t*>(b + oQBin); t->pool = reinterpret_cast<uint32_t*>(b + oPool);
+    t->mask = reinterpret_cast<uint64_t*>(b + oMask); t->has = reinterpret_cast<unsigned long long*>(b + oHas);
+    t->boxList = reinterpret_cast<int32_t*>(b + oBoxList); t->nnQ = reinterpret_cast<int32_t*>(b + oNnQ);
+    t->nnT = reinterpret_cast<int32_t*>(b + oNnT); t->dynMask = b + oDynMask;
+    t->assign = reinterpret_cast<int32_t*>(b + oAssign); t->locked = b + oLocked;
+    t->poolUsed = reinterpret_cast<int32_t*>(b + oPoolUsed); t->result = reinterpret_cast<int32_t*>(b + oResult);
+    t->readmit = b + oReadmit; t->staticExit = reinterpret_cast<int32_t*>(b + oStatic);
+    t->counts = reinterpret_cast<int32_t*>(b + oCounts);
+    t->hJobs.resize(J);
+    c->track = t;
+    return SDYN_OK;
+}
+
+__global__ void k_copy_match_counts(const int32_t* __restrict__ result, int B, int nframes, int32_t* __restrict__ counts)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    counts[f * 4] = result[f * 4];                 /* SearchByProjection(cur, last) */
+    counts[f * 4 + 1] = result[(B + f) * 4];       /* SearchByProjection(F, map points) */
+}
+
+}  // namespace sdyn
+
+using namespace sdyn;
+
+#define TCU(c, call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return api_fail((c), SDYN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" {
+
+int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride, int W, int H, int stride,
+                            const sdyn_track_inputs* in, void* stream)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (!in || nframes < 1 || nframes > c->maxBatch || !dGray || W < 1 || H < 1 || stride < W || in->last_stride < 0 ||
+        in->map_stride < 0 || in->ref_stride < 0 || !(in->max_x > in->min_x) || !(in->max_y > in->min_y) ||
+        (in->last_stride > 0 && (!in->last_points || !in->last_keys || !in->last_keys_un || !in->n_last)) ||
+        (in->map_stride > 0 && (!in->map_points || !in->n_map)) || !in->boxes || !in->n_boxes || !in->ref_box ||
+        !in->ref_off || !in->fmat || c->maxKp > 65535)
+        return api_fail(c, SDYN_ERR_ARG, "sdyn_track_batch_device: bad argument");
+    TCU(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    int rc = ensure_geometry(c, W, H);
+    if (rc != SDYN_OK) return rc;
+    rc = ensure_track_state(c, std::max(std::max(in->last_stride, in->map_stride), 1), in->ref_stride);
+    if (rc != SDYN_OK) return rc;
+    TrackState* t = static_cast<TrackState*>(c->track);
+    rc = enqueue_extract(c, nframes, dGray, frameStride, stride, st);
+    if (rc != SDYN_OK) return rc;
+
+    const int B = t->B, cap = t->cap;
+    /* bForward / bBackward of ORBmatcher.cc:1497-1506 */
+    float twc[3], tlc[3];
+    for (int r = 0; r < 3; ++r) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += (double)in->tcw_cur[4 * k + r] * (double)in->tcw_cur[4 * k + 3];
+        twc[r] = (float)(-1.0 * s);
+    }
+    for (int r = 0; r < 3; ++r) {
+        const float* T = in->tcw_last + 4 * r;
+        const float s = T[0] * twc[0] + T[1] * twc[1] + T[2] * twc[2];
+        tlc[r] = s + T[3];
+    }
+    const int forward = (tlc[2] > in->b) && !in->mono, backward = (-tlc[2] > in->b) && !in->mono;
+
+    for (int f = 0; f < nframes; ++f) {
+        MatchJob J; std::memset(&J, 0, sizeof(J));
+        J.keysUn = c->dKp + (size_t)f * cap; J.desc = c->dDesc + (size_t)f * cap * 32; J.uRight = nullptr;
+        J.nPtr = c->dCount + f; J.n = cap;
+        J.minX = in->min_x; J.minY = in->min_y; J.maxX = in->max_x; J.maxY = in->max_y;
+        J.gridWInv = static_cast<float>(SDYN_GRID_COLS) / static_cast<float>(in->max_x - in->min_x);
+        J.gridHInv = static_cast<float>(SDYN_GRID_ROWS) / static_cast<float>(in->max_y - in->min_y);
+        for (int l = 0; l < SDYN_MAX_LEVELS; ++l) J.scale[l] = l < c->scales.nlevels ? c->scales.scale[l] : 1.f;
+        J.cellOff = t->cellOff + (size_t)f * (kGridCells + 1); J.sorted = t->sorted + (size_t)f * cap;
+        J.cellOf = t->cellOf + (size_t)f * cap;
+        J.assign = t->assign + (size_t)f * cap; J.locked = t->locked + (size_t)f * cap;
+        J.poolCap = t->poolPerJob;
+        std::memcpy(J.Tcw, in->tcw_cur, sizeof(J.Tcw));
+        J.fx = in->fx; J.fy = in->fy; J.cx = in->cx; J.cy = in->cy; J.bf = in->bf;
+
+        MatchJob F = J;                      /* SearchByProjection(CurrentFrame, LastFrame, th, bMono) */
+        F.mode = MM_FRAME;
+        F.queries = in->last_points + (size_t)f * in->last_stride;
+        F.qKeys = in->last_keys + (size_t)f * in->last_stride; F.qKeysUn = in->last_keys_un + (size_t)f * in->last_stride;
+        F.nqPtr = in->n_last + f; F.nq = in->last_stride;
+        F.th = in->th_frame; F.checkOri = in->check_orientation; F.forward = forward; F.backward = backward;
+        F.assignBase = 0;
+        const size_t jf = (size_t)f, jm = (size_t)B + f;
+        F.qspan = t->qspan + jf * t->maxQ; F.qAccepted = t->qAccepted + jf * t->maxQ; F.qBin = t->qBin + jf * t->maxQ;
+        F.pool = t->pool + jf * t->poolPerJob; F.poolUsed = t->poolUsed + jf; F.result = t->result + jf * 4;
+        t->hJobs[f] = F;
+
+        MatchJob M = J;                      /* SearchByProjection(Frame, vpMapPoints, th) */
+        M.mode = MM_MAP;
+        M.queries = in->map_points + (size_t)f * in->map_stride;
+        M.nqPtr = in->n_map + f; M.nq = in->map_stride;
+        M.th = in->th_map; M.nnratio = in->nnratio_map; M.assignBase = in->last_stride;
+        M.qspan = t->qspan + jm * t->maxQ; M.qAccepted = t->qAccepted + jm * t->maxQ; M.qBin = t->qBin + jm * t->maxQ;
+        M.pool = t->pool + jm * t->poolPerJob; M.poolUsed = t->poolUsed + jm; M.result = t->result + jm * 4;
+        t->hJobs[B + f] = M;
+    }
+    {
+        StageTimer tm(c, st, SDYN_STAGE_MATCH);
+        TCU(c, cudaMemsetAsync(t->assign, 0xff, (size_t)B * cap * 4, st));
+        TCU(c, cudaMemsetAsync(t->block + t->zeroFrom, 0, t->zeroBytes, st));
+        TCU(c, cudaMemcpyAsync(t->dJobs, t->hJobs.data(), t->hJobs.size() * sizeof(MatchJob), cudaMemcpyHostToDevice, st));
+        TCU(c, launch_grid_build(t->dJobs, nframes, st));
+        if (in->last_stride > 0) {
+            TCU(c, launch_match_candidates(t->dJobs, nframes, in->last_stride, st));
+            TCU(c, launch_match_resolve(t->dJobs, nframes, st));
+        }
+        if (in->map_stride > 0) {
+            TCU(c, launch_match_candidates(t->dJobs + B, nframes, in->map_stride, st));
+            TCU(c, launch_match_resolve(t->dJobs + B, nframes, st));
+        }
+        c->launches += 3 + (in->last_stride > 0 ? 2 : 0) + (in->map_stride > 0 ? 2 : 0);
+    }
+    {
+        StageTimer tm(c, st, SDYN_STAGE_DYNAMIC);
+        TCU(c, launch_dyn_stage(*in, c->dKp, c->dDesc, c->dCount, cap, t->mask, t->has, t->boxList, t->nnQ, t->nnT,
+                                std::max(t->refStride, 1), t->readmit, t->staticExit, t->dynMask, t->counts, nframes, st));
+        k_copy_match_counts<<<(nframes + 63) / 64, 64, 0, st>>>(t->result, B, nframes, t->counts);
+        TCU(c, cudaGetLastError());
+        c->launches += 5;
+    }
+    return SDYN_OK;
+}
+
+int sdyn_track_results(const sdyn_ctx* c, sdyn_track_view* out)
+{
+    if (!c || !out || !c->track) return SDYN_ERR_ARG;
+    const TrackState* t = static_cast<const TrackState*>(c->track);
+    out->assign = t->assign; out->locked = t->locked; out->dyn_mask = t->dynMask; out->counts = t->counts;
+    return SDYN_OK;
+}
+
+int sdyn_track_fetch(sdyn_ctx* c, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dynMask, int32_t* counts, int cap,
+                     void* stream)
+{
+    if (!c) return SDYN_ERR_ARG;
+    TrackState* t = static_cast<TrackState*>(c->track);
+    if (!t || nframes < 1 || nframes > t->B || cap < 0) return api_fail(c, SDYN_ERR_ARG, "sdyn_track_fetch: bad argument");
+    TCU(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const int kc = t->cap;
+    if (assign) TCU(c, cudaMemcpyAsync(t->hAssign, t->assign, (size_t)nframes * kc * 4, cudaMemcpyDeviceToHost, st));
+    if (locked) TCU(c, cudaMemcpyAsync(t->hLocked, t->locked, (size_t)nframes * kc, cudaMemcpyDeviceToHost, st));
+    if (dynMask) TCU(c, cudaMemcpyAsync(t->hMask, t->dynMask, (size_t)nframes * kc, cudaMemcpyDeviceToHost, st));
+    TCU(c, cudaMemcpyAsync(t->hCounts, t->counts, (size_t)nframes * 16, cudaMemcpyDeviceToHost, st));
+    TCU(c, cudaMemcpyAsync(t->hResult, t->result, (size_t)2 * t->B * 16, cudaMemcpyDeviceToHost, st));
+    TCU(c, cudaStreamSynchronize(st));
+    for (int f = 0; f < nframes; ++f)
+        if (t->hResult[f * 4 + 2] || t->hResult[(t->B + f) * 4 + 2])
+            return api_fail(c, SDYN_ERR_CAPACITY, "matcher candidate pool exhausted in the batched front end");
+    const int m = std::min(cap, kc);
+    for (int f = 0; f < nframes; ++f) {
+        if (assign) std::memcpy(assign + (size_t)f * cap, t->hAssign + (size_t)f * kc, (size_t)m * 4);
+        if (locked) std::memcpy(locked + (size_t)f * cap, t->hLocked + (size_t)f * kc, m);
+        if (dynMask) std::memcpy(dynMask + (size_t)f * cap, t->hMask + (size_t)f * kc, m);
+        if (counts) std::memcpy(counts + (size_t)f * 4, t->hCounts + (size_t)f * 4, 16);
+    }
+    return SDYN_OK;
+}
+
+}  // extern "C"

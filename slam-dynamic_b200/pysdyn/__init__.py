@@ -101,6 +101,8 @@ def synth():
                                        C.c_void_p, C.c_int]
         S.sdyn_synth_boxes.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_int]
+        S.sdyn_synth_boxes_ids.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_int]
         _synth = S
     return _synth
 
@@ -117,6 +119,13 @@ def synth_boxes(seq_seed, w, h, nrect, ox=0, oy=0, t=0, margin=6, cap=64):
     b = np.zeros((cap, 4), np.float64)
     n = synth().sdyn_synth_boxes(seq_seed, w, h, nrect, ox, oy, t, margin, b.ctypes.data, cap)
     return b[:n].copy()
+
+
+def synth_boxes_ids(seq_seed, w, h, nrect, ox=0, oy=0, t=0, margin=6, cap=64):
+    b = np.zeros((cap, 4), np.float64)
+    ids = np.zeros(cap, np.int32)
+    n = synth().sdyn_synth_boxes_ids(seq_seed, w, h, nrect, ox, oy, t, margin, b.ctypes.data, ids.ctypes.data, cap)
+    return b[:n].copy(), ids[:n].copy()
 
 
 class PinnedArray:
@@ -450,3 +459,68 @@ def separate_pairs(ctx, pairs, M, mode, fn=None):
         n = arr[i].nmatches
         res.append(tuple(o[:n].copy() for o in outs))
     return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched, device-resident front end
+# ---------------------------------------------------------------------------------------------------
+class TrackInputsC(C.Structure):
+    _fields_ = [("last_points", C.c_void_p), ("last_keys", C.c_void_p), ("last_keys_un", C.c_void_p),
+                ("n_last", C.c_void_p), ("last_stride", C.c_int32),
+                ("map_points", C.c_void_p), ("n_map", C.c_void_p), ("map_stride", C.c_int32),
+                ("boxes", C.c_void_p), ("n_boxes", C.c_void_p), ("ref_box", C.c_void_p),
+                ("ref_desc", C.c_void_p), ("ref_xy", C.c_void_p), ("ref_off", C.c_void_p), ("ref_stride", C.c_int32),
+                ("fmat", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float), ("b", C.c_float),
+                ("tcw_cur", C.c_float * 12), ("tcw_last", C.c_float * 12),
+                ("th_frame", C.c_float), ("th_map", C.c_float), ("nnratio_map", C.c_float),
+                ("mono", C.c_int32), ("check_orientation", C.c_int32)]
+
+
+TRACK_ARRAYS = ["last_points", "last_keys", "last_keys_un", "n_last", "map_points", "n_map", "boxes", "n_boxes",
+                "ref_box", "ref_desc", "ref_xy", "ref_off", "fmat"]
+
+
+def track_inputs(ptrs, frame0, strides, params):
+    """ptrs: {name: (device base address, bytes per frame)}; frame0: first frame of the batch in those arrays."""
+    t = TrackInputsC()
+    for name in TRACK_ARRAYS:
+        base, per_frame = ptrs[name]
+        setattr(t, name, base + frame0 * per_frame)
+    t.last_stride, t.map_stride, t.ref_stride = strides
+    for k, v in params.items():
+        if k in ("tcw_cur", "tcw_last"):
+            arr = getattr(t, k)
+            for i in range(12):
+                arr[i] = float(v[i])
+        else:
+            setattr(t, k, v)
+    return t
+
+
+def _bind_track(L):
+    if getattr(L, "_track_bound", False):
+        return L
+    vp = C.c_void_p
+    L.sdyn_track_batch_device.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(TrackInputsC), vp]
+    L.sdyn_track_fetch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp]
+    L._track_bound = True
+    return L
+
+
+def track_batch_device(ex, nframes, dptr, frame_stride, w, h, row_stride, tin, stream=None):
+    L = _bind_track(lib())
+    ex._check(L.sdyn_track_batch_device(ex._h, nframes, C.c_void_p(dptr), frame_stride, w, h, row_stride, C.byref(tin),
+                                        C.c_void_p(stream) if stream else None))
+
+
+def track_fetch(ex, nframes, stream=None, out=None):
+    L = _bind_track(lib())
+    if out is None:
+        out = (np.zeros((nframes, ex.cap), np.int32), np.zeros((nframes, ex.cap), np.uint8),
+               np.zeros((nframes, ex.cap), np.uint8), np.zeros((nframes, 4), np.int32))
+    a, l, m, c = out
+    ex._check(L.sdyn_track_fetch(ex._h, nframes, a.ctypes.data, l.ctypes.data, m.ctypes.data, c.ctypes.data, ex.cap,
+                                 C.c_void_p(stream) if stream else None))
+    return a, l, m, c

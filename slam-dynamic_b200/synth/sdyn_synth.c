@@ -115,8 +115,17 @@ void sdyn_synth_frame(uint64_t seq_seed, uint64_t frame_seed, int W, int H, int 
     }
 }
 
+int sdyn_synth_boxes_ids(uint64_t seq_seed, int W, int H, int nrect, int ox, int oy, int t, int margin,
+                         double* xywh, int* ids, int cap);
+
 int sdyn_synth_boxes(uint64_t seq_seed, int W, int H, int nrect, int ox, int oy, int t, int margin,
                      double* xywh, int cap)
+{
+    return sdyn_synth_boxes_ids(seq_seed, W, H, nrect, ox, oy, t, margin, xywh, 0, cap);
+}
+
+int sdyn_synth_boxes_ids(uint64_t seq_seed, int W, int H, int nrect, int ox, int oy, int t, int margin,
+                         double* xywh, int* ids, int cap)
 {
     int n = 0;
     for (int r = 0; r < nrect; ++r) {
@@ -133,6 +142,7 @@ int sdyn_synth_boxes(uint64_t seq_seed, int W, int H, int nrect, int ox, int oy,
             xywh[4 * n + 1] = by > 0 ? by : 0;
             xywh[4 * n + 2] = bw;
             xywh[4 * n + 3] = bh;
+            if (ids) ids[n] = r;
         }
         ++n;
     }

@@ -15,6 +15,10 @@ void sdyn_synth_frame(uint64_t seq_seed, uint64_t frame_seed, int W, int H, int 
 int sdyn_synth_boxes(uint64_t seq_seed, int W, int H, int nrect, int ox, int oy, int t, int margin,
                      double* xywh, int cap);
 
+/* Same, also returning the rectangle id of every box (stable across frames: the tracking identity). */
+int sdyn_synth_boxes_ids(uint64_t seq_seed, int W, int H, int nrect, int ox, int oy, int t, int margin,
+                         double* xywh, int* ids, int cap);
+
 uint64_t sdyn_synth_hash(uint64_t seed, uint64_t tag, int64_t a, int64_t b);
 
 #ifdef __cplusplus

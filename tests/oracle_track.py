@@ -1,0 +1,56 @@
+"""Oracle composition of one frame of the batched front end (TEST INFRASTRUCTURE ONLY): the same four steps
+as sdyn_track_batch_device, built from the oracle's restated reference functions."""
+import numpy as np
+
+import orc
+import pysdyn
+import scenario
+
+
+def track_frame(keys, desc, scale, W, H, arrays, f, params, last_stride):
+    """Returns (assign, locked, dyn_mask, counts[4]) for frame f of `arrays` (scenario.build_track_batch)."""
+    cam = scenario.KITTI_CAM
+    cur = pysdyn.FrameView(keys, desc, scale, (0.0, 0.0, float(W), float(H)),
+                           cam=(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["bf"], cam["bf"] / cam["fx"]),
+                           tcw=params["tcw_cur"])
+    n0 = int(arrays["n_last"][f])
+    last = pysdyn.FrameView(arrays["last_keys"][f, :n0], np.zeros((n0, 32), np.uint8), scale,
+                            (0.0, 0.0, float(W), float(H)), keys_un=arrays["last_keys_un"][f, :n0],
+                            cam=cur.cam, tcw=params["tcw_last"])
+    n1, assign, locked = orc.match_projection_frame(cur, last, arrays["last_points"][f, :n0], params["th_frame"],
+                                                    bool(params["mono"]), bool(params["check_orientation"]))
+    nm = int(arrays["n_map"][f])
+    n2, assign, locked = orc.match_projection_map(cur, arrays["map_points"][f, :nm], params["th_map"],
+                                                  params["nnratio_map"], assign, locked, assign_base=last_stride)
+    # dynamic mask: firstSeparate (+ erase bug) -> Separate (BF + classifyF + gates) -> UpdateFrame
+    nb = int(arrays["n_boxes"][f])
+    boxes = arrays["boxes"][f, :nb]
+    in_box = orc.box_mask(keys, boxes) != 0
+    sep = orc.first_separate(keys, boxes, np.arange(nb))
+    slots = {}
+    for s, k in sep["dyn"]:
+        slots.setdefault(s, []).append(k)
+    readmit = np.zeros(len(keys), bool)
+    static_exit = False
+    for s in range(len(sep["boxes"])):
+        surv = int(sep["box_idx"][s])                  # original id of the box now in slot s
+        r = int(arrays["ref_box"][f, surv])
+        ks = slots.get(s, [])
+        if r < 0 or not ks:
+            continue
+        o0, o1 = int(arrays["ref_off"][f, r]), int(arrays["ref_off"][f, r + 1])
+        if o1 == o0:
+            continue
+        qd = desc[ks]; qx = np.stack([keys["x"][ks], keys["y"][ks]], 1)
+        mq, mt, md, fd = orc.separate_pairs([(qd, qx, arrays["ref_desc"][f, o0:o1], arrays["ref_xy"][f, o0:o1])],
+                                            arrays["fmat"][f], 0)[0]
+        good = len(mq)
+        if good < 3 or good < 0.2 * len(ks):
+            continue
+        num0 = int((fd != -1).sum())
+        for q in fd[fd != -1]:
+            readmit[ks[int(q)]] = True
+        if num0 > max(1.0, 0.2 * good):
+            static_exit = True
+    dyn = in_box & ~(readmit & static_exit)
+    return assign, locked, dyn.astype(np.uint8), np.array([n1, n2, int(in_box.sum()), int(dyn.sum())], np.int32)

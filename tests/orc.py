@@ -182,13 +182,13 @@ def features_in_area(F, x, y, r, min_level, max_level):
     return out[:n].copy()
 
 
-def match_projection_map(F, mappoints, th, nnratio, assign=None, locked=None):
+def match_projection_map(F, mappoints, th, nnratio, assign=None, locked=None, assign_base=0):
     S = _structs()
     mp = np.ascontiguousarray(mappoints, S.MAPPOINT_DTYPE)
     assign = np.full(F.n, -1, np.int32) if assign is None else np.ascontiguousarray(assign, np.int32).copy()
     locked = np.zeros(F.n, np.uint8) if locked is None else np.ascontiguousarray(locked, np.uint8).copy()
-    lib.orc_match_projection_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
-    n = lib.orc_match_projection_map(C.byref(F.c), mp.ctypes.data, len(mp), th, nnratio, assign.ctypes.data, locked.ctypes.data)
+    lib.orc_match_projection_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
+    n = lib.orc_match_projection_map(C.byref(F.c), mp.ctypes.data, len(mp), th, nnratio, assign.ctypes.data, locked.ctypes.data, assign_base)
     return n, assign, locked
 
 

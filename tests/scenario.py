@@ -87,3 +87,80 @@ def degenerate_descriptors(n, seed, distinct=12):
     r = rng_for(seed + 303)
     base = r.integers(0, 256, (distinct, 32), dtype=np.uint8)
     return base[r.integers(0, distinct, n)]
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched front-end inputs (sdyn_track_inputs): a sequence of frames, each tracked against its predecessor
+# ---------------------------------------------------------------------------------------------------
+def sequence_offsets(i):
+    """Camera offset of frame i of a synthetic sequence (integer shifts <= 8 px between frames)."""
+    return 3 * i, (i * 5) % 7
+
+
+def translation_fmat(dx, dy):
+    """F21 with x2^T F x1 = 0 for x2 = x1 - (dx, dy): pure image translation (static scene)."""
+    return np.float32([[0, 0, dy], [0, 0, -dx], [-dy, dx, 0]])
+
+
+def build_track_batch(kd, seq_seed, first_index, W, H, nrect, nlevels, last_stride, map_stride, ref_stride,
+                      n_map=3000, seed=0):
+    """kd: list of (keys, desc) for frames first_index-1 .. first_index+B-1 of one sequence (B = len(kd)-1).
+    Returns dict of numpy arrays laid out as sdyn_track_inputs expects ([B, stride, ...])."""
+    B = len(kd) - 1
+    out = {
+        "last_points": np.zeros((B, last_stride), pysdyn.LASTPOINT_DTYPE),
+        "last_keys": np.zeros((B, last_stride), pysdyn.KP_DTYPE),
+        "last_keys_un": np.zeros((B, last_stride), pysdyn.KP_DTYPE),
+        "n_last": np.zeros(B, np.int32),
+        "map_points": np.zeros((B, map_stride), pysdyn.MAPPOINT_DTYPE),
+        "n_map": np.zeros(B, np.int32),
+        "boxes": np.zeros((B, 64, 4), np.float64),
+        "n_boxes": np.zeros(B, np.int32),
+        "ref_box": np.full((B, 64), -1, np.int32),
+        "ref_desc": np.zeros((B, ref_stride, 32), np.uint8),
+        "ref_xy": np.zeros((B, ref_stride, 2), np.float32),
+        "ref_off": np.zeros((B, 65), np.int32),
+        "fmat": np.zeros((B, 9), np.float32),
+    }
+    for f in range(B):
+        i = first_index + f
+        (k0, d0), (k1, d1) = kd[f], kd[f + 1]
+        ox0, oy0 = sequence_offsets(i - 1); ox1, oy1 = sequence_offsets(i)
+        shift = (ox1 - ox0, oy1 - oy0)
+        n0 = min(len(k0), last_stride)
+        out["last_points"][f, :n0] = last_points(k0[:n0], d0[:n0], shift, seed=seed + 31 * i)
+        out["last_keys"][f, :n0] = k0[:n0]; out["last_keys_un"][f, :n0] = k0[:n0]
+        out["n_last"][f] = n0
+        nm = min(n_map, map_stride)
+        out["map_points"][f, :nm] = map_queries(k1, d1, nlevels, seed=seed + 57 * i, count=nm)
+        out["n_map"][f] = nm
+        # detection boxes of the current frame and of the reference (= previous) frame, joined on rectangle id
+        b1, id1 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox1, oy1, i, margin=8)
+        b0, id0 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox0, oy0, i - 1, margin=8)
+        nb = min(len(b1), 62)
+        out["boxes"][f, :nb] = b1[:nb]
+        out["boxes"][f, nb] = [W + 50.0, H + 50.0, 10.0, 10.0]      # a detection without keypoints (gets erased)
+        out["n_boxes"][f] = nb + 1
+        for b in range(nb):
+            hit = np.nonzero(id0 == id1[b])[0]
+            out["ref_box"][f, b] = int(hit[0]) if len(hit) else -1
+        off = 0
+        for r in range(min(len(b0), 64)):
+            x, y, w, h = b0[r]
+            inside = np.nonzero((k0["x"] >= x) & (k0["x"] < x + w) & (k0["y"] >= y) & (k0["y"] < y + h))[0]
+            inside = inside[: max(0, ref_stride - off)]
+            out["ref_off"][f, r] = off
+            out["ref_desc"][f, off:off + len(inside)] = d0[inside]
+            out["ref_xy"][f, off:off + len(inside), 0] = k0["x"][inside]
+            out["ref_xy"][f, off:off + len(inside), 1] = k0["y"][inside]
+            off += len(inside)
+        out["ref_off"][f, min(len(b0), 64):] = off
+        out["fmat"][f] = translation_fmat(*shift).reshape(9)
+    return out
+
+
+def track_params(W, H, cam=KITTI_CAM, th_frame=7.0, th_map=3.0, nnratio_map=0.8, mono=0, check_orientation=1):
+    eye = np.eye(4, dtype=np.float32)[:3].reshape(12)
+    return dict(min_x=0.0, min_y=0.0, max_x=float(W), max_y=float(H), fx=cam["fx"], fy=cam["fy"], cx=cam["cx"],
+                cy=cam["cy"], bf=cam["bf"], b=cam["bf"] / cam["fx"], tcw_cur=eye, tcw_last=eye, th_frame=th_frame,
+                th_map=th_map, nnratio_map=nnratio_map, mono=mono, check_orientation=check_orientation)
