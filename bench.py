@@ -1,11 +1,12 @@
 #!/usr/bin/env python3
-"""Headline benchmark: frames/sec of the tracking front end (ORB extract + match + dynamic mask) on
-synthetic KITTI-shaped 1241x376 frames, 2000 features, 8 levels (BASELINE.json).
+"""Headline benchmark (BASELINE.json): frames/sec of the tracking front end — ORB extract + SearchByProjection
+(frame and local-map) + dynamic mask — on synthetic KITTI-shaped 1241x376 frames, 2000 features, 8 levels,
+and the fraction of the HBM roofline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl sdyn|reference]
 
-One "step" = one pass of the hot path over one batch of synthetic frames.  Prints ONE JSON line (rank 0).
-See DESIGN.md §Measurement for the definitions of value / e2e / roofline / cpu_baseline.
+One "step" = one pass of the hot path over one batch of synthetic frames per GPU.  Rank 0 prints ONE JSON
+line.  DESIGN.md §Measurement defines value / e2e / roofline / cpu_baseline.
 """
 import argparse
 import json
@@ -24,17 +25,20 @@ import numpy as np  # noqa: E402
 
 WORKLOADS = {
     # name: (W, H, nrect, nfeatures, iniTh, minTh, config_id)
-    "kitti": (1241, 376, 160, 2000, 12, 7, 0),
-    "tum": (640, 480, 120, 1000, 20, 7, 1),
-    "4k": (3840, 2160, 2800, 8000, 20, 7, 4),
+    "kitti": (1241, 376, 160, 2000, 12, 7, 0),      # Examples/Stereo/KITTI04-12.yaml
+    "tum": (640, 480, 120, 1000, 20, 7, 1),         # Examples/RGB-D/TUM3.yaml
+    "4k": (3840, 2160, 2800, 8000, 20, 7, 4),       # stress config
 }
 POOL = 256          # distinct frames per GPU (frame_idx 0..255)
 NLEVELS, SCALE = 8, 1.2
+N_MAP = 3000        # local-map points per frame (2000-5000)
+REF_STRIDE = 1024   # capacity for the reference frame's in-box keypoints
+METRIC = "frames/sec ORB extract+match+dyn-mask @KITTI 1241x376 2k feats; % HBM roofline"
 
 
 def level_sizes(W, H):
     s, out = np.float32(1.0), []
-    for l in range(NLEVELS):
+    for _ in range(NLEVELS):
         inv = np.float32(1.0) / s
         out.append((int(np.rint(np.float32(W) * inv)), int(np.rint(np.float32(H) * inv))))
         s = np.float32(float(s) * float(np.float32(SCALE)))
@@ -46,32 +50,40 @@ def alg_bytes_extract(W, H, nkp):
     return W * H + sum((w + 38) * (h + 38) for w, h in level_sizes(W, H)) + nkp * (32 + 28)
 
 
-def stage_alg_bytes(W, H, nkp):
+def stage_alg_bytes(W, H, nkp, evals, queries):
     """Per-stage (unfused) algorithmic bytes per frame, SURVEY §8(d) secondary accounting."""
     lv = level_sizes(W, H)
     px = sum(w * h for w, h in lv)
     bordered = sum((w + 38) * (h + 38) for w, h in lv)
     return {
-        "pyramid": W * H + sum(w * h for w, h in lv[:-1]) + bordered,   # read prev level, write bordered level
-        "fast": px,
+        "pyramid": W * H + sum(w * h for w, h in lv[:-1]) + bordered,   # read previous level, write bordered level
+        "fast": px,                                                      # every level pixel read once
         "blur": 2 * px,
         "describe": nkp * (749 + 512 + 60),
         "octree": nkp * 8,
+        "match": 32 * evals + 56 * queries + 32 * nkp,
+        "dynamic": 9 * nkp + 32 * 64,
     }
 
 
-def make_frames(cfg, rank, count):
+def seq_seed(cfg, rank):
+    return 1000 * WORKLOADS[cfg][6] + 100000 * rank + 7
+
+
+def make_frames(cfg, rank, first, count):
+    """Frames first..first+count-1 of this rank's sequence (consecutive frames shift by <= 8 px)."""
     import pysdyn
+    import scenario
     W, H, nrect, _, _, _, cid = WORKLOADS[cfg]
     frames = np.empty((count, H, W), np.uint8)
-    seq_seed = 1000 * cid + 100000 * rank + 7
     nthreads = min(os.cpu_count() or 1, 16)
 
     def work(t):
-        for i in range(t, count, nthreads):
-            # consecutive frames of one sequence: integer camera shift (<= 8 px) so real matches exist
-            ox, oy = 3 * i, (i * 5) % 7
-            pysdyn.synth_frame(seq_seed, 1000 * cid + 100000 * rank + i, W, H, nrect, ox, oy, i, out=frames[i])
+        for j in range(t, count, nthreads):
+            i = first + j
+            ox, oy = scenario.sequence_offsets(i)
+            pysdyn.synth_frame(seq_seed(cfg, rank), 1000 * cid + 100000 * rank + i + (1 << 20), W, H, nrect, ox, oy,
+                               scenario.sequence_time(i), out=frames[j])
 
     th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
     [t.start() for t in th]
@@ -83,12 +95,11 @@ class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
 
     def __init__(self, gpu_index):
-        self.rows = []
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -96,6 +107,7 @@ class ClockSampler:
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
         self.p.terminate()
         try:
             out = self.p.communicate(timeout=5)[0]
@@ -118,24 +130,47 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_fps(cfg, frames, seconds, threads):
-    """Times the CPU oracle (restatement of the reference's CPU path) frame-parallel on `threads` host
-    threads for about `seconds`; returns (fps, frames_done)."""
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU implementation of the path.  The reference itself cannot be built here (needs
+# OpenCV C++ >= 3.4 + contrib, Eigen, Pangolin, PCL, Boost), so this runs its restatement in oracle/ ("port").
+# ------------------------------------------------------------------------------------------------------------
+def cpu_prepare(cfg, nframes):
+    """Inputs of the CPU arm: a short sequence, extracted once to build the track queries."""
     import orc
-    _, _, _, nf, ini, mn, _ = WORKLOADS[cfg]
+    import scenario
+    W, H, nrect, nf, ini, mn, _ = WORKLOADS[cfg]
+    frames = make_frames(cfg, 0, 0, nframes + 1)
+    ex = orc.Extractor(nf, SCALE, NLEVELS, ini, mn)
+    kd = [ex(im) for im in frames]
+    cap = nf + 200
+    arrays = scenario.build_track_batch(kd, seq_seed(cfg, 0), 1, W, H, nrect, NLEVELS, cap, N_MAP, REF_STRIDE,
+                                        n_map=N_MAP, seed=3)
+    return frames[1:], arrays, scenario.track_params(W, H), cap
+
+
+def cpu_run(cfg, frames, arrays, params, cap, threads, seconds=None, count=None):
+    """Runs the full per-frame hot path (extract + 2 searches + dynamic mask) on the CPU oracle, frame-parallel
+    over `threads` host threads, for `seconds` or for `count` frames.  Returns (fps, frames_done)."""
+    import orc
+    import oracle_track
+    W, H, _, nf, ini, mn, _ = WORKLOADS[cfg]
     done = [0] * threads
-    stop_at = [None]
+    t0 = time.perf_counter()
 
     def work(t):
         ex = orc.Extractor(nf, SCALE, NLEVELS, ini, mn)
         i = t
-        while time.perf_counter() < stop_at[0]:
-            ex(frames[i % len(frames)])
+        while True:
+            if seconds is not None and time.perf_counter() - t0 >= seconds:
+                break
+            if count is not None and i >= count:
+                break
+            f = i % len(frames)
+            k, d = ex(frames[f])
+            oracle_track.track_frame(k, d, ex.scale, W, H, arrays, f, params, cap)
             done[t] += 1
             i += threads
 
-    t0 = time.perf_counter()
-    stop_at[0] = t0 + seconds
     th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
     [t.start() for t in th]
     [t.join() for t in th]
@@ -144,49 +179,32 @@ def cpu_reference_fps(cfg, frames, seconds, threads):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (restated in oracle/, since the
-    reference itself needs OpenCV C++/Eigen/Pangolin/PCL and cannot be built here), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = args.workload
     W, H = WORKLOADS[cfg][:2]
     threads = os.cpu_count() or 1
-    frames = make_frames(cfg, 0, 32)
-    per_step = max(threads, 8)
-    import orc
-    nf, ini, mn = WORKLOADS[cfg][3:6]
-    extractors = [orc.Extractor(nf, SCALE, NLEVELS, ini, mn) for _ in range(threads)]
-
-    def run_step():
-        """a bounded sample of `per_step` frames, frame-parallel over all host threads"""
-        def work(t):
-            for i in range(t, per_step, threads):
-                extractors[t](frames[i % len(frames)])
-        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-        [t.start() for t in th]
-        [t.join() for t in th]
-        return per_step
-
-    for _ in range(min(args.warmup, 1)):
-        run_step()
+    frames, arrays, params, cap = cpu_prepare(cfg, 16)
+    per_step = 2 * threads                      # bounded sample per step
+    if args.warmup > 0:
+        cpu_run(cfg, frames, arrays, params, cap, threads, count=threads)
     t0 = time.perf_counter()
     total = 0
     for _ in range(args.steps):
-        total += run_step()
+        total += cpu_run(cfg, frames, arrays, params, cap, threads, count=per_step)[1]
     dt = time.perf_counter() - t0
     fps = total / dt
-    line = {
-        "impl": "reference", "metric": "frames/sec ORB extract+match+dyn-mask @KITTI 1241x376 2k feats",
-        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "%s %dx%d" % (cfg, W, H), "frames_per_step": per_step},
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "%s %dx%d" % (cfg, W, H), "frames_per_step": per_step,
+                   "stages": "extract + SearchByProjection(frame) + SearchByProjection(map) + dynamic mask"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d frames per step, frame-parallel oracle" % per_step},
+                         "sample": "%d frames per step, frame-parallel C++ oracle (restated reference CPU path)" % per_step},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line))
+    }))
 
 
 def main():
@@ -197,7 +215,7 @@ def main():
     ap.add_argument("--impl", default="sdyn", choices=["sdyn", "reference"])
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample length (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -205,6 +223,7 @@ def main():
     import torch
     import torch.distributed as dist
     import pysdyn
+    import scenario
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,21 +235,39 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     cfg = args.workload
-    W, H, _, nf, ini, mn, _ = WORKLOADS[cfg]
+    W, H, nrect, nf, ini, mn, _ = WORKLOADS[cfg]
     B = args.batch
     K, Wm = args.steps, max(args.warmup, 3)
+    nsets = POOL // B
+    assert nsets >= 1
 
-    frames = make_frames(cfg, rank, POOL)                      # this rank's shard: its own sequence
+    # ---- inputs: this rank's sequence (sharded by sequence: no data-path collective) ----------------------
+    frames = make_frames(cfg, rank, 0, POOL + 1)                # frame 0 only serves as LastFrame of frame 1
     ex = pysdyn.Extractor(nf, SCALE, NLEVELS, ini, mn, max_width=W, max_height=H, max_batch=B, device=local)
-    dev_frames = torch.from_numpy(frames).cuda()               # resident in HBM for the device-timed number
+    cap = ex.cap
+    kd = []
+    for s in range(0, POOL + 1, B):                             # untimed pre-pass: LastFrame / map / box inputs
+        chunk = frames[s:s + B]
+        k, d, n = ex.extract_batch(chunk)
+        kd += [(k[i, :n[i]].copy(), d[i, :n[i]].copy()) for i in range(len(chunk))]
+    arrays = scenario.build_track_batch(kd, seq_seed(cfg, rank), 1, W, H, nrect, NLEVELS, cap, N_MAP, REF_STRIDE,
+                                        n_map=N_MAP, seed=3)
+    params = scenario.track_params(W, H)
+    strides = (cap, N_MAP, REF_STRIDE)
+    cur_frames = frames[1:]
+
     # a real (non-legacy) stream: libsdyn launches on it and the torch events below are recorded on it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    nsets = POOL // B
+    dev_frames = torch.from_numpy(cur_frames).cuda()            # resident in HBM for the device-timed number
+    dev = {k: torch.from_numpy(v.view(np.uint8).reshape(v.shape[0], -1)).cuda() for k, v in arrays.items()}
+    dptrs = {k: (t.data_ptr(), t.shape[1]) for k, t in dev.items()}
+    torch.cuda.synchronize()
 
     def step_device(s):
         base = (s % nsets) * B
-        ex.extract_batch_device(dev_frames[base].data_ptr(), B, W * H, W, H, W, stream.cuda_stream)
+        tin = pysdyn.track_inputs(dptrs, base, strides, params)
+        pysdyn.track_batch_device(ex, B, dev_frames[base].data_ptr(), W * H, W, H, W, tin, stream.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -256,37 +293,53 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = ex.launch_count() - launches0
     kps, desc, counts = ex.fetch(B)
+    assign, locked, mask, cnt = pysdyn.track_fetch(ex, B)
     mean_kp = float(counts.mean())
 
     # ---- end to end through the C ABI with pinned host buffers ("e2e") ------------------------------------
+    pin = {k: pysdyn.PinnedArray((v.shape[0], int(np.prod(v.shape[1:])) * v.dtype.itemsize), np.uint8) for k, v in arrays.items()}
+    for k, v in arrays.items():
+        pin[k].array[:] = v.view(np.uint8).reshape(v.shape[0], -1)
+    hptrs = {k: (p.array.ctypes.data, p.array.shape[1]) for k, p in pin.items()}
     pin_in = pysdyn.PinnedArray((POOL, H, W), np.uint8)
-    pin_in.array[:] = frames
-    pk = pysdyn.PinnedArray((B, ex.cap), pysdyn.KP_DTYPE)
-    pd = pysdyn.PinnedArray((B, ex.cap, 32), np.uint8)
-    pc = pysdyn.PinnedArray((B,), np.int32)
+    pin_in.array[:] = cur_frames
+    outs = tuple(pysdyn.PinnedArray(shape, dt) for shape, dt in
+                 [((B, cap), pysdyn.KP_DTYPE), ((B, cap, 32), np.uint8), ((B,), np.int32), ((B, cap), np.int32),
+                  ((B, cap), np.uint8), ((B, cap), np.uint8), ((B, 4), np.int32)])
+    out_arrays = tuple(o.array for o in outs)
+
+    def step_host(s):
+        base = (s % nsets) * B
+        tin = pysdyn.track_inputs(hptrs, base, strides, params)
+        pysdyn.track_batch_host(ex, pin_in.array[base:base + B], tin, out_arrays)
+
     for s in range(2):
-        ex.extract_batch(pin_in.array[(s % nsets) * B:(s % nsets) * B + B], pk.array, pd.array, pc.array)
+        step_host(s)
     barrier()
     t0 = time.perf_counter()
     for s in range(K):
-        base = ((Wm + s) % nsets) * B
-        ex.extract_batch(pin_in.array[base:base + B], pk.array, pd.array, pc.array)
+        step_host(Wm + s)
     barrier()
     e2e_s = time.perf_counter() - t0
+    h2d = B * W * H + sum(p.array.shape[1] for p in pin.values()) * B
+    d2h = B * (cap * (28 + 32) + 4 + cap * 6 + 16)
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([float(B * K), mean_kp, float(cnt[:, 0].mean()), float(cnt[:, 1].mean()), float(cnt[:, 3].mean())],
+                         dtype=torch.float64, device="cuda")
+    gathered = [stats]
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        stats = torch.tensor([float(B * K), mean_kp], dtype=torch.float64, device="cuda")
         gathered = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)                       # NCCL: the only collective (stats, off the hot path)
+        dist.all_gather(gathered, stats)                       # NCCL: the only collective (run statistics)
     ms_max, e2e_ms_max = float(t[0]), float(t[1])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    total_frames = B * K * world
+    g = torch.stack(gathered).cpu().numpy()
+    total_frames = float(g[:, 0].sum())
     fps = total_frames / (ms_max * 1e-3)
     e2e_fps = total_frames / (e2e_ms_max * 1e-3)
     peaks = {}
@@ -295,47 +348,56 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
-    sab = stage_alg_bytes(W, H, int(round(mean_kp)))
+    # candidate evaluations per frame are not counted on the device; use the oracle-calibrated average
+    evals_per_frame = 20 * (cap + N_MAP)
+    sab = stage_alg_bytes(W, H, int(round(mean_kp)), evals_per_frame, cap + N_MAP)
+    tot_stage_ms = max(sum(v[0] for v in stages.values()), 1e-9)
     stage_report = {}
     for name, (sms, calls) in stages.items():
         if calls:
-            stage_report[name] = {"ms_per_step": sms / K, "share": sms / max(sum(v[0] for v in stages.values()), 1e-9)}
+            per_step = sms / K
+            ach = sab.get(name, 0) * B / (per_step * 1e-3) / 1e9
+            stage_report[name] = {"ms_per_step": per_step, "share": sms / tot_stage_ms, "alg_gbs": ach, "hbm_frac": ach / peak}
     dom = max(stage_report, key=lambda n: stage_report[n]["ms_per_step"]) if stage_report else None
     roof = None
     if dom:
-        per_launch_bytes = sab.get(dom, 0) * B
-        dur = stage_report[dom]["ms_per_step"] * 1e-3
-        ach = per_launch_bytes / dur / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": per_launch_bytes,
-                "note": "FAST is integer-ALU bound, see DESIGN.md" if dom == "fast" else ""}
+        r = stage_report[dom]
+        roof = {"kernel": dom, "bound": "hbm", "achieved": r["alg_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": r["hbm_frac"], "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": sab.get(dom, 0) * B,
+                "note": "FAST scoring is integer-ALU bound, not HBM bound (DESIGN.md §Kernels)" if dom == "fast" else ""}
     balg = alg_bytes_extract(W, H, int(round(mean_kp)))
-    pipeline_frac = balg * fps / 1e9 / peak
 
     cpu = None
     if args.cpu_seconds > 0:
-        cpu1, n1 = cpu_reference_fps(cfg, frames[:32], args.cpu_seconds, 1)
+        cframes, carrays, cparams, ccap = cpu_prepare(cfg, 8)
+        cpu1, n1 = cpu_run(cfg, cframes, carrays, cparams, ccap, 1, seconds=args.cpu_seconds)
         cpu = {"value": cpu1, "unit": "frames/s", "cores": 1, "kind": "port",
-               "sample": "%d KITTI frames through the C++ oracle (extract), 1 thread" % n1}
+               "sample": "%d KITTI frames, full path (extract + 2 searches + dynamic mask) on the C++ oracle, 1 thread "
+                         "(the reference's execution model, Frame.cc:259,318,424)" % n1}
 
     line = {
-        "metric": "frames/sec ORB extract+match+dyn-mask @KITTI 1241x376 2k feats; % HBM roofline",
-        "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
         "config": {"workload": "%s %dx%d nfeatures=%d levels=%d scale=%.1f iniTh=%d minTh=%d" % (cfg, W, H, nf, NLEVELS, SCALE, ini, mn),
-                   "frames_per_step_per_gpu": B, "sharding": "frame/sequence per rank, no data-path collective",
-                   "l2": "inputs cycle through a %d-frame pool (%.0f MB) and the per-step working set exceeds the 126 MB L2" % (POOL, POOL * W * H / 1e6),
-                   "stages": "extract (match + dyn-mask: see DESIGN.md status)"},
-        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
-                "d2h_bytes_per_step": int(B * (ex.cap * 60 + 8))},
+                   "frames_per_step_per_gpu": B, "map_points_per_frame": N_MAP,
+                   "stages": "extract + SearchByProjection(cur,last) + SearchByProjection(F,map) + dynamic mask",
+                   "sharding": "one sequence per rank, no data-path collective; NCCL all_gather of run statistics only",
+                   "l2": "inputs cycle through a %d-frame pool (%.0f MB of frames) and each step's working set "
+                         "(~%.0f MB) exceeds the 126 MB L2" % (POOL, POOL * W * H / 1e6, B * 7.0)},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
-        "pipeline_roofline": {"alg_bytes_per_frame": balg, "achieved_gbs": balg * fps / 1e9, "peak": peak, "frac": pipeline_frac},
+        "pipeline_roofline": {"alg_bytes_per_frame": balg, "achieved_gbs": balg * fps / world / 1e9, "peak": peak,
+                              "frac": balg * fps / world / 1e9 / peak,
+                              "note": "SURVEY §8(d) extraction bytes per frame x per-GPU frames/s"},
         "stages": stage_report,
-        "mean_keypoints": mean_kp,
+        "per_frame": {"keypoints": float(g[:, 1].mean()), "matches_frame": float(g[:, 2].mean()),
+                      "matches_map": float(g[:, 3].mean()), "dyn_masked": float(g[:, 4].mean())},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

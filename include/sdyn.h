@@ -284,6 +284,14 @@ typedef struct {
 
 int sdyn_track_batch_device(sdyn_ctx* ctx, int nframes, const uint8_t* d_gray, size_t frame_stride,
                             int width, int height, int stride, const sdyn_track_inputs* in, void* stream);
+/* Host-buffer form of the same step (what a caller holding frames and map data in host memory uses): every
+ * pointer of `in` and `gray` is HOST memory (pinned memory copies asynchronously), results are written to the
+ * host arrays (kp_out/desc_out: [nframes][cap], n_out: [nframes]; assign/locked/dyn_mask: [nframes][cap];
+ * counts: [nframes][4]; any output may be NULL).  Host->device copies of the frames and of all query arrays
+ * and the device->host copies of the results happen inside the call. */
+int sdyn_track_batch(sdyn_ctx* ctx, int nframes, const uint8_t* gray, size_t frame_stride, int width, int height,
+                     int stride, const sdyn_track_inputs* in, sdyn_keypoint* kp_out, uint8_t* desc_out, int* n_out,
+                     int32_t* assign, uint8_t* locked, uint8_t* dyn_mask, int32_t* counts, int cap);
 int sdyn_track_results(const sdyn_ctx* ctx, sdyn_track_view* out);
 /* D2H of the step results next to sdyn_fetch_results (host arrays sized [nframes][cap] / [nframes][4]). */
 int sdyn_track_fetch(sdyn_ctx* ctx, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dyn_mask,

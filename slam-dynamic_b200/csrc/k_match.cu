@@ -381,6 +381,150 @@ k_match_resolve(const MatchJob* __restrict__ jobs)
     if (lane == 0) { J.result[0] = nmatches; J.result[1] = npairs; }
 }
 
+/* ------------------------------------------------------------------------------- resolve, FRAME / MAP modes
+ * The two per-frame searches only interact through "keypoint already holds a map point with observations"
+ * (src/ORBmatcher.cc:87-89, 1560-1562).  Let T[kp] = the first query that locks kp (-1: locked on entry,
+ * INT_MAX: never).  Query q may take kp iff T[kp] >= q, and T is the minimum over accepted, observed claims:
+ * a monotone system whose unique fixpoint is the sequential result (induction on q: queries < q fix T as seen
+ * by q).  Jacobi iteration from "nothing locked" makes queries 0..t-1 final after sweep t, so it stops after
+ * (longest conflict chain + 1) sweeps — 2-4 on real frames — and every sweep is data-parallel over queries.
+ * One CTA per search; T and the per-query decisions live in shared memory. */
+constexpr int RF = 256;
+
+__global__ void __launch_bounds__(RF)
+k_match_resolve_fix(const MatchJob* __restrict__ jobs)
+{
+    extern __shared__ int smemFix[];
+    const MatchJob& J = jobs[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int n = job_n(J), nq = job_nq(J);
+    int* lockT = smemFix;                 /* n */
+    int* acc = smemFix + J.n;             /* nq: accepted keypoint or -1 */
+    __shared__ int hist[SDYN_HISTO_LENGTH];
+    __shared__ int keep[3];
+    __shared__ int sCount, sDec, warpTot[RF / 32];
+    constexpr uint32_t NONE = 0xffffffffu;
+    const sdyn_last_point* lps = reinterpret_cast<const sdyn_last_point*>(J.queries);
+    const sdyn_mappoint_query* mps = reinterpret_cast<const sdyn_mappoint_query*>(J.queries);
+
+    for (int q = tid; q < nq; q += RF) acc[q] = -2;
+    for (int sweep = 0; sweep <= nq; ++sweep) {
+        /* T from the claims of the previous sweep */
+        for (int k = tid; k < n; k += RF) lockT[k] = (J.assign[k] != -1 && J.locked[k]) ? -1 : 0x7fffffff;
+        __syncthreads();
+        if (sweep > 0)
+            for (int q = tid; q < nq; q += RF) {
+                const int a = acc[q];
+                const bool obs = J.mode == MM_FRAME ? lps[q].obs_positive : mps[q].obs_positive;
+                if (a >= 0 && obs) atomicMin(&lockT[a], q);
+            }
+        __syncthreads();
+        int changed = 0;
+        for (int q = tid; q < nq; q += RF) {
+            const int2 span = J.qspan[q];
+            uint32_t a = NONE, b = NONE;
+            for (int p = 0; p < span.y; ++p) {
+                const uint32_t rec = J.pool[span.x + p];
+                if (lockT[rec_idx(rec)] < q) continue;
+                const uint32_t key = ((uint32_t)rec_dist(rec) << 20) | (uint32_t)p;
+                if (key < a) { b = a; a = key; } else if (key < b) b = key;
+            }
+            int res = -1;
+            if (a != NONE) {
+                const uint32_t r1 = J.pool[span.x + (a & 0xfffff)];
+                const int bestDist = (int)(a >> 20);
+                bool ok = bestDist <= SDYN_TH_HIGH;
+                if (ok && J.mode == MM_MAP) {
+                    int bestDist2 = 256, bestLevel2 = -1;
+                    if (b != NONE) { bestDist2 = (int)(b >> 20); bestLevel2 = rec_level(J.pool[span.x + (b & 0xfffff)]); }
+                    ok = !(rec_level(r1) == bestLevel2 && (float)bestDist > __fmul_rn(J.nnratio, (float)bestDist2));
+                }
+                if (ok) res = rec_idx(r1);
+            }
+            if (res != acc[q]) { acc[q] = res; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+
+    /* final owners: the last accepted claimant of every keypoint */
+    if (tid == 0) { sCount = 0; sDec = 0; }
+    for (int i = tid; i < SDYN_HISTO_LENGTH; i += RF) hist[i] = 0;
+    for (int k = tid; k < n; k += RF) lockT[k] = -1;          /* reuse: max claimant */
+    __syncthreads();
+    int mine = 0;
+    for (int q = tid; q < nq; q += RF) {
+        const int a = acc[q];
+        if (a < 0) { if (J.mode == MM_FRAME) J.qBin[q] = -1; continue; }
+        ++mine;
+        atomicMax(&lockT[a], q);
+        if (J.mode == MM_FRAME && J.checkOri) {
+            float rot = __fsub_rn(J.qKeysUn[q].angle, J.keysUn[a].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, 1.0f / SDYN_HISTO_LENGTH));
+            if (bin == SDYN_HISTO_LENGTH) bin = 0;
+            J.qBin[q] = bin;
+            atomicAdd(&hist[bin], 1);
+        }
+    }
+    atomicAdd(&sCount, mine);
+    __syncthreads();
+    for (int k = tid; k < n; k += RF) {
+        const int q = lockT[k];
+        if (q >= 0) {
+            J.assign[k] = J.assignBase + q;
+            J.locked[k] = J.mode == MM_FRAME ? lps[q].obs_positive : mps[q].obs_positive;
+        }
+    }
+    /* point pairs of the fork's overload, in query order (before the cull, Appendix B-8) */
+    if (J.mode == MM_FRAME && J.pairs) {
+        int base = 0;
+        for (int q0 = 0; q0 < nq; q0 += RF) {
+            const int q = q0 + tid;
+            const bool ok = q < nq && acc[q] >= 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if ((tid & 31) == 0) warpTot[tid >> 5] = __popc(bal);
+            __syncthreads();
+            int pos = base, tot = 0;
+            for (int w = 0; w < RF / 32; ++w) { if (w < (tid >> 5)) pos += warpTot[w]; tot += warpTot[w]; }
+            pos += __popc(bal & ((1u << (tid & 31)) - 1));
+            if (ok) {
+                const int a = acc[q];
+                J.pairs[4 * pos] = J.qKeysUn[q].x; J.pairs[4 * pos + 1] = J.qKeysUn[q].y;
+                J.pairs[4 * pos + 2] = J.keysUn[a].x; J.pairs[4 * pos + 3] = J.keysUn[a].y;
+            }
+            base += tot;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (J.mode == MM_FRAME && J.checkOri) {
+        if (tid == 0) {
+            int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < SDYN_HISTO_LENGTH; ++i) {
+                const int sz = hist[i];
+                if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; i3 = i2; i2 = i1; i1 = i; }
+                else if (sz > max2) { max3 = max2; max2 = sz; i3 = i2; i2 = i; }
+                else if (sz > max3) { max3 = sz; i3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) i3 = -1;
+            keep[0] = i1; keep[1] = i2; keep[2] = i3;
+        }
+        __syncthreads();
+        int dec = 0;
+        for (int q = tid; q < nq; q += RF) {
+            const int a = acc[q];
+            if (a < 0) continue;
+            const int bin = J.qBin[q];
+            if (bin == keep[0] || bin == keep[1] || bin == keep[2]) continue;
+            J.assign[a] = -1; J.locked[a] = 0; ++dec;      /* every histogram entry of a culled bin nulls its keypoint */
+        }
+        atomicAdd(&sDec, dec);
+        __syncthreads();
+    }
+    if (tid == 0) { J.result[0] = sCount - sDec; J.result[1] = sCount; }
+}
+
 cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, cudaStream_t st)
 {
     k_grid_build<<<njobs, 256, 0, st>>>(dJobs);
@@ -395,9 +539,16 @@ cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQue
     return cudaGetLastError();
 }
 
-cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, cudaStream_t st)
+cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st)
 {
-    k_match_resolve<<<njobs, 32, 0, st>>>(dJobs);
+    if (mode == MM_FRAME || mode == MM_MAP) {
+        const size_t smem = (size_t)(maxN + maxQ) * sizeof(int);
+        cudaError_t e = cudaFuncSetAttribute(k_match_resolve_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_match_resolve_fix<<<njobs, RF, smem, st>>>(dJobs);
+    } else {
+        k_match_resolve<<<njobs, 32, 0, st>>>(dJobs);
+    }
     return cudaGetLastError();
 }
 

@@ -58,7 +58,8 @@ struct MatchJob {
 
 cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, cudaStream_t st);
 cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQueries, cudaStream_t st);
-cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, cudaStream_t st);
+/* mode: all jobs of one launch share a mode; maxN / maxQ: largest MatchJob::n / ::nq of the launch */
+cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st);
 
 /* dynamic-keypoint kernels (k_dynamic.cu) */
 struct BoxPairJob {

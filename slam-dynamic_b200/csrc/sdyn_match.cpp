@@ -109,7 +109,7 @@ int run_job(sdyn_ctx* c, size_t fixedBytes, int nq, int poolGuess, int poolMax, 
         MCU(c, cudaMemcpyAsync(dJob, &J, sizeof(J), cudaMemcpyHostToDevice, c->stream));
         MCU(c, launch_grid_build(dJob, 1, c->stream));
         MCU(c, launch_match_candidates(dJob, 1, nq, c->stream));
-        MCU(c, launch_match_resolve(dJob, 1, c->stream));
+        MCU(c, launch_match_resolve(dJob, 1, J.mode, std::max(J.n, 1), std::max(nq, 1), c->stream));
         c->launches += 3;
         int32_t res[4];
         MCU(c, cudaMemcpyAsync(res, J.result, sizeof(res), cudaMemcpyDeviceToHost, c->stream));

@@ -18,6 +18,8 @@ struct TrackState {
     int32_t* staticExit; uint8_t* dynMask; int32_t* counts;
     size_t zeroFrom = 0, zeroBytes = 0;     /* region cleared at the start of every step */
     std::vector<MatchJob> hJobs;
+    /* device staging of host inputs (sdyn_track_batch) */
+    uint8_t* inBlock = nullptr; size_t inBytes = 0;
     /* pinned staging for sdyn_track_fetch */
     int32_t* hAssign = nullptr; uint8_t* hLocked = nullptr; uint8_t* hMask = nullptr; int32_t* hCounts = nullptr; int32_t* hResult = nullptr;
 };
@@ -26,7 +28,7 @@ void free_track_state(sdyn_ctx* c)
 {
     TrackState* t = static_cast<TrackState*>(c->track);
     if (!t) return;
-    cudaFree(t->block);
+    cudaFree(t->block); cudaFree(t->inBlock);
     cudaFreeHost(t->hAssign); cudaFreeHost(t->hLocked); cudaFreeHost(t->hMask); cudaFreeHost(t->hCounts); cudaFreeHost(t->hResult);
     delete t;
     c->track = nullptr;
@@ -188,11 +190,11 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         TCU(c, launch_grid_build(t->dJobs, nframes, st));
         if (in->last_stride > 0) {
             TCU(c, launch_match_candidates(t->dJobs, nframes, in->last_stride, st));
-            TCU(c, launch_match_resolve(t->dJobs, nframes, st));
+            TCU(c, launch_match_resolve(t->dJobs, nframes, MM_FRAME, cap, in->last_stride, st));
         }
         if (in->map_stride > 0) {
             TCU(c, launch_match_candidates(t->dJobs + B, nframes, in->map_stride, st));
-            TCU(c, launch_match_resolve(t->dJobs + B, nframes, st));
+            TCU(c, launch_match_resolve(t->dJobs + B, nframes, MM_MAP, cap, in->map_stride, st));
         }
         c->launches += 3 + (in->last_stride > 0 ? 2 : 0) + (in->map_stride > 0 ? 2 : 0);
     }
@@ -205,6 +207,73 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         c->launches += 5;
     }
     return SDYN_OK;
+}
+
+int sdyn_track_batch(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frameStride, int W, int H, int stride,
+                     const sdyn_track_inputs* in, sdyn_keypoint* kpOut, uint8_t* descOut, int* nOut, int32_t* assign,
+                     uint8_t* locked, uint8_t* dynMask, int32_t* counts, int cap)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (!in || !gray || nframes < 1 || nframes > c->maxBatch || W < 1 || H < 1 || stride < W || W > c->maxW || H > c->maxH)
+        return api_fail(c, SDYN_ERR_ARG, "sdyn_track_batch: bad argument");
+    TCU(c, cudaSetDevice(c->device));
+    int rc = ensure_track_state(c, std::max(std::max(in->last_stride, in->map_stride), 1), in->ref_stride);
+    if (rc != SDYN_OK) return rc;
+    TrackState* t = static_cast<TrackState*>(c->track);
+    /* device staging of the per-frame input arrays */
+    const size_t n = (size_t)nframes, B = (size_t)c->maxBatch;
+    struct Item { const void* src; size_t bytesPerFrame; size_t off; };
+    Item items[] = {
+        {in->last_points, (size_t)in->last_stride * sizeof(sdyn_last_point), 0},
+        {in->last_keys, (size_t)in->last_stride * sizeof(sdyn_keypoint), 0},
+        {in->last_keys_un, (size_t)in->last_stride * sizeof(sdyn_keypoint), 0},
+        {in->n_last, 4, 0},
+        {in->map_points, (size_t)in->map_stride * sizeof(sdyn_mappoint_query), 0},
+        {in->n_map, 4, 0},
+        {in->boxes, 64 * 4 * sizeof(double), 0},
+        {in->n_boxes, 4, 0},
+        {in->ref_box, 64 * 4, 0},
+        {in->ref_desc, (size_t)in->ref_stride * 32, 0},
+        {in->ref_xy, (size_t)in->ref_stride * 8, 0},
+        {in->ref_off, 65 * 4, 0},
+        {in->fmat, 9 * 4, 0},
+    };
+    size_t total = 0;
+    for (auto& it : items) { it.off = total; total += (it.bytesPerFrame * B + 255) / 256 * 256; }
+    if (total > t->inBytes) {
+        TCU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(t->inBlock); t->inBlock = nullptr; t->inBytes = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&t->inBlock), total);
+        if (e != cudaSuccess) return api_fail(c, SDYN_ERR_NOMEM, std::string("track input staging: ") + cudaGetErrorString(e));
+        t->inBytes = total;
+    }
+    for (auto& it : items)
+        if (it.src && it.bytesPerFrame)
+            TCU(c, cudaMemcpyAsync(t->inBlock + it.off, it.src, it.bytesPerFrame * n, cudaMemcpyHostToDevice, c->stream));
+    for (int f = 0; f < nframes; ++f)
+        TCU(c, cudaMemcpy2DAsync(c->dIn + (size_t)f * W * H, W, gray + (size_t)f * frameStride, stride, W, H,
+                                 cudaMemcpyHostToDevice, c->stream));
+    sdyn_track_inputs d = *in;
+    d.last_points = reinterpret_cast<const sdyn_last_point*>(t->inBlock + items[0].off);
+    d.last_keys = reinterpret_cast<const sdyn_keypoint*>(t->inBlock + items[1].off);
+    d.last_keys_un = reinterpret_cast<const sdyn_keypoint*>(t->inBlock + items[2].off);
+    d.n_last = reinterpret_cast<const int32_t*>(t->inBlock + items[3].off);
+    d.map_points = reinterpret_cast<const sdyn_mappoint_query*>(t->inBlock + items[4].off);
+    d.n_map = reinterpret_cast<const int32_t*>(t->inBlock + items[5].off);
+    d.boxes = reinterpret_cast<const double*>(t->inBlock + items[6].off);
+    d.n_boxes = reinterpret_cast<const int32_t*>(t->inBlock + items[7].off);
+    d.ref_box = reinterpret_cast<const int32_t*>(t->inBlock + items[8].off);
+    d.ref_desc = t->inBlock + items[9].off;
+    d.ref_xy = reinterpret_cast<const float*>(t->inBlock + items[10].off);
+    d.ref_off = reinterpret_cast<const int32_t*>(t->inBlock + items[11].off);
+    d.fmat = reinterpret_cast<const float*>(t->inBlock + items[12].off);
+    rc = sdyn_track_batch_device(c, nframes, c->dIn, (size_t)W * H, W, H, W, &d, nullptr);
+    if (rc != SDYN_OK) return rc;
+    if (nOut) {
+        rc = sdyn_fetch_results(c, nframes, kpOut, descOut, (kpOut && descOut) ? cap : 0, nOut, nullptr);
+        if (rc != SDYN_OK && !(rc == SDYN_ERR_CAPACITY && !(kpOut && descOut))) return rc;
+    }
+    return sdyn_track_fetch(c, nframes, assign, locked, dynMask, counts, cap, nullptr);
 }
 
 int sdyn_track_results(const sdyn_ctx* c, sdyn_track_view* out)

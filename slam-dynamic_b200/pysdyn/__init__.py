@@ -505,6 +505,8 @@ def _bind_track(L):
     vp = C.c_void_p
     L.sdyn_track_batch_device.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(TrackInputsC), vp]
     L.sdyn_track_fetch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp]
+    L.sdyn_track_batch.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(TrackInputsC),
+                                   vp, vp, vp, vp, vp, vp, vp, C.c_int]
     L._track_bound = True
     return L
 
@@ -524,3 +526,15 @@ def track_fetch(ex, nframes, stream=None, out=None):
     ex._check(L.sdyn_track_fetch(ex._h, nframes, a.ctypes.data, l.ctypes.data, m.ctypes.data, c.ctypes.data, ex.cap,
                                  C.c_void_p(stream) if stream else None))
     return a, l, m, c
+
+
+def track_batch_host(ex, images, tin, outs):
+    """Host-buffer step: images [B,H,W] uint8 and `tin` pointing at HOST arrays (pinned for async copies).
+    outs = (kps, desc, n, assign, locked, dyn_mask, counts) host arrays, filled in place."""
+    L = _bind_track(lib())
+    b, h, w = images.shape
+    kps, desc, n, assign, locked, mask, counts = outs
+    ex._check(L.sdyn_track_batch(ex._h, b, images.ctypes.data, images.strides[0], w, h, images.strides[1], C.byref(tin),
+                                 kps.ctypes.data, desc.ctypes.data, n.ctypes.data, assign.ctypes.data, locked.ctypes.data,
+                                 mask.ctypes.data, counts.ctypes.data, ex.cap))
+    return outs

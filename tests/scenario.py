@@ -27,11 +27,14 @@ def frame_view(keys, desc, scale, W, H, cam=KITTI_CAM, stereo=False, tcw=None, s
 
 
 def flip_bits(desc, r, nbits):
+    """Flip nbits[i] random bits of descriptor i (vectorised)."""
     d = desc.copy()
-    for i in range(len(d)):
-        for _ in range(int(nbits[i])):
-            k = int(r.integers(0, 256))
-            d[i, k >> 3] ^= np.uint8(1 << (k & 7))
+    nbits = np.asarray(nbits)
+    rows = np.arange(len(d))
+    for j in range(int(nbits.max()) if len(nbits) else 0):
+        sel = rows[nbits > j]
+        pos = r.integers(0, 256, len(sel))
+        np.bitwise_xor.at(d, (sel, pos >> 3), (1 << (pos & 7)).astype(np.uint8))
     return d
 
 
@@ -92,9 +95,21 @@ def degenerate_descriptors(n, seed, distinct=12):
 # ---------------------------------------------------------------------------------------------------
 # batched front-end inputs (sdyn_track_inputs): a sequence of frames, each tracked against its predecessor
 # ---------------------------------------------------------------------------------------------------
+def _tri(i, period):
+    """Triangle wave 0..period..0: keeps the camera (and the moving objects) inside the populated part of the
+    synthetic world however long the sequence is, while consecutive frames still differ by a small shift."""
+    m = i % (2 * period)
+    return m if m <= period else 2 * period - m
+
+
 def sequence_offsets(i):
     """Camera offset of frame i of a synthetic sequence (integer shifts <= 8 px between frames)."""
-    return 3 * i, (i * 5) % 7
+    return 3 * _tri(i, 16), (i * 5) % 7
+
+
+def sequence_time(i):
+    """Time step of the independently moving rectangles at frame i (they oscillate, so they stay in view)."""
+    return _tri(i, 12)
 
 
 def translation_fmat(dx, dy):
@@ -135,8 +150,8 @@ def build_track_batch(kd, seq_seed, first_index, W, H, nrect, nlevels, last_stri
         out["map_points"][f, :nm] = map_queries(k1, d1, nlevels, seed=seed + 57 * i, count=nm)
         out["n_map"][f] = nm
         # detection boxes of the current frame and of the reference (= previous) frame, joined on rectangle id
-        b1, id1 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox1, oy1, i, margin=8)
-        b0, id0 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox0, oy0, i - 1, margin=8)
+        b1, id1 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox1, oy1, sequence_time(i), margin=8)
+        b0, id0 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox0, oy0, sequence_time(i - 1), margin=8)
         nb = min(len(b1), 62)
         out["boxes"][f, :nb] = b1[:nb]
         out["boxes"][f, nb] = [W + 50.0, H + 50.0, 10.0, 10.0]      # a detection without keypoints (gets erased)

@@ -19,7 +19,8 @@ def test_track_batch_matches_oracle(cfg, B):
     cid = common.CONFIG_ID[cfg]
     seq_seed = 1000 * cid + 7
     first = 1
-    frames = np.stack([pysdyn.synth_frame(seq_seed, 1000 * cid + i, W, H, nrect, *scenario.sequence_offsets(i), i)
+    frames = np.stack([pysdyn.synth_frame(seq_seed, 1000 * cid + i, W, H, nrect, *scenario.sequence_offsets(i),
+                                          scenario.sequence_time(i))
                        for i in range(first - 1, first + B)])
     cpu = orc.Extractor(nf, 1.2, 8, ini, mn)
     kd = [cpu(im) for im in frames]
