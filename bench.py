@@ -324,21 +324,19 @@ def main():
     h2d = B * W * H + sum(p.array.shape[1] for p in pin.values()) * B
     d2h = B * (cap * (28 + 32) + 4 + cap * 6 + 16)
 
+    from pysdyn import shard
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    stats = torch.tensor([float(B * K), mean_kp, float(cnt[:, 0].mean()), float(cnt[:, 1].mean()), float(cnt[:, 3].mean())],
-                         dtype=torch.float64, device="cuda")
-    gathered = [stats]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)                       # NCCL: the only collective (run statistics)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)               # timing: max over ranks
+    # NCCL all_gather of the per-rank run statistics: the only collective, off the hot path
+    g = shard.gather_stats([float(B * K), mean_kp, float(cnt[:, 0].mean()), float(cnt[:, 1].mean()), float(cnt[:, 3].mean()),
+                            float(shard.result_hash(counts, cnt))])
     ms_max, e2e_ms_max = float(t[0]), float(t[1])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    g = torch.stack(gathered).cpu().numpy()
     total_frames = float(g[:, 0].sum())
     fps = total_frames / (ms_max * 1e-3)
     e2e_fps = total_frames / (e2e_ms_max * 1e-3)

@@ -91,6 +91,10 @@ int sdyn_scale_info_get(const sdyn_ctx* ctx, sdyn_scale_info* out);
  * more than nfeatures (the octree overshoots by up to 3 per level). */
 int sdyn_max_keypoints(const sdyn_ctx* ctx);
 
+/* Host-only: the tables the ORBextractor constructor builds (src/ORBextractor.cc:410-470) — scale factors,
+ * per-level quotas and the 16 half-widths of the orientation disc.  Needs no device and no context. */
+int sdyn_orb_tables(const sdyn_orb_params* params, sdyn_scale_info* out, int32_t umax[16]);
+
 /* Pinned host memory helpers (optional; any host pointer works, pinned ones copy asynchronously). */
 int sdyn_host_alloc(void** ptr, size_t bytes);
 int sdyn_host_free(void* ptr);

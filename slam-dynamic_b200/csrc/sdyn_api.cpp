@@ -252,6 +252,15 @@ int sdyn_scale_info_get(const sdyn_ctx* c, sdyn_scale_info* out)
     return SDYN_OK;
 }
 
+int sdyn_orb_tables(const sdyn_orb_params* p, sdyn_scale_info* out, int32_t umax[16])
+{
+    if (!p || !out || !umax || p->nlevels < 1 || p->nlevels > SDYN_MAX_LEVELS || !(p->scale_factor > 1.0f)) return SDYN_ERR_ARG;
+    int um[16];
+    compute_scale_info(*p, *out, um);
+    for (int i = 0; i < 16; ++i) umax[i] = um[i];
+    return SDYN_OK;
+}
+
 int sdyn_max_keypoints(const sdyn_ctx* c) { return c ? c->maxKp : SDYN_ERR_ARG; }
 
 int sdyn_host_alloc(void** ptr, size_t bytes)
