@@ -109,6 +109,22 @@ StageTimer::~StageTimer()
     if (a) { cudaEvent_t b = take_event(c); cudaEventRecord(b, st); c->spans.push_back({a, b, stage}); }
 }
 
+/* H2D of the input frames; rows are packed to W on the device.  Contiguous inputs go out as ONE linear copy. */
+cudaError_t upload_frames(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frameStride, int W, int H, int stride,
+                          cudaStream_t st)
+{
+    if (stride == W && (nframes == 1 || frameStride == (size_t)W * H))
+        return cudaMemcpyAsync(c->dIn, gray, (size_t)nframes * W * H, cudaMemcpyHostToDevice, st);
+    for (int f = 0; f < nframes; ++f) {
+        cudaError_t e = stride == W
+            ? cudaMemcpyAsync(c->dIn + (size_t)f * W * H, gray + (size_t)f * frameStride, (size_t)W * H, cudaMemcpyHostToDevice, st)
+            : cudaMemcpy2DAsync(c->dIn + (size_t)f * W * H, W, gray + (size_t)f * frameStride, stride, W, H,
+                                cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 /* Enqueues the whole extraction pipeline for nframes frames already resident in device memory. */
 int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride, int rowStride, cudaStream_t st)
 {
@@ -290,11 +306,15 @@ int sdyn_fetch_results(sdyn_ctx* c, int nframes, sdyn_keypoint* kpOut, uint8_t* 
         return fail(c, SDYN_ERR_ARG, "sdyn_fetch_results: bad argument");
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CU(c, cudaSetDevice(c->device));
-    /* one D2H per array into pinned staging, then scatter into the caller's layout */
     CU(c, cudaMemcpyAsync(c->hCount, c->dCount, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, st));
     CU(c, cudaMemcpyAsync(c->hStatus, c->dStatus, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, st));
-    CU(c, cudaMemcpyAsync(c->hKp, c->dKp, sizeof(sdyn_keypoint) * (size_t)c->maxKp * nframes, cudaMemcpyDeviceToHost, st));
-    CU(c, cudaMemcpyAsync(c->hDesc, c->dDesc, (size_t)32 * c->maxKp * nframes, cudaMemcpyDeviceToHost, st));
+    /* same per-frame capacity as the device arrays: copy straight into the caller's buffers (asynchronous when
+     * they are pinned); otherwise stage in pinned memory and scatter */
+    const bool direct = cap == c->maxKp;
+    if (cap > 0) {
+        CU(c, cudaMemcpyAsync(direct ? kpOut : c->hKp, c->dKp, sizeof(sdyn_keypoint) * (size_t)c->maxKp * nframes, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaMemcpyAsync(direct ? descOut : c->hDesc, c->dDesc, (size_t)32 * c->maxKp * nframes, cudaMemcpyDeviceToHost, st));
+    }
     CU(c, cudaStreamSynchronize(st));
     int rc = SDYN_OK;
     for (int f = 0; f < nframes; ++f) {
@@ -303,7 +323,7 @@ int sdyn_fetch_results(sdyn_ctx* c, int nframes, sdyn_keypoint* kpOut, uint8_t* 
         nOut[f] = n;
         const int m = std::min(n, cap);
         if (n > cap) rc = SDYN_ERR_CAPACITY;
-        if (m > 0) {
+        if (m > 0 && !direct) {
             std::memcpy(kpOut + (size_t)f * cap, c->hKp + (size_t)f * c->maxKp, sizeof(sdyn_keypoint) * m);
             std::memcpy(descOut + (size_t)f * cap * 32, c->hDesc + (size_t)f * c->maxKp * 32, (size_t)32 * m);
         }
@@ -326,10 +346,7 @@ int sdyn_extract_batch(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t fra
     CU(c, cudaSetDevice(c->device));
     int rc = ensure_geometry(c, W, H);
     if (rc != SDYN_OK) return rc;
-    /* H2D: rows are packed to W on the device */
-    for (int f = 0; f < nframes; ++f)
-        CU(c, cudaMemcpy2DAsync(c->dIn + (size_t)f * W * H, W, gray + (size_t)f * frameStride, stride, W, H,
-                                cudaMemcpyHostToDevice, c->stream));
+    CU(c, upload_frames(c, nframes, gray, frameStride, W, H, stride, c->stream));
     rc = enqueue_extract(c, nframes, c->dIn, (size_t)W * H, W, c->stream);
     if (rc != SDYN_OK) return rc;
     return sdyn_fetch_results(c, nframes, kpOut, descOut, cap, nOut, nullptr);

@@ -109,6 +109,8 @@ namespace sdyn {
 
 /* sdyn_api.cpp */
 int ensure_geometry(sdyn_ctx* c, int W, int H);
+cudaError_t upload_frames(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frameStride, int W, int H, int stride,
+                          cudaStream_t st);
 int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride, int rowStride, cudaStream_t st);
 struct StageTimer {          /* brackets a stage with CUDA events while profiling is enabled */
     sdyn_ctx* c; cudaStream_t st; int stage; cudaEvent_t a;
@@ -144,7 +146,7 @@ cudaError_t launch_orient_describe(const Geom& g, const uint8_t* dPyr, const uin
                                    int nframes, cudaStream_t st);
 size_t octree_smem_bytes(int nodeCap);
 
-constexpr int kFastTileW = 64, kFastTileH = 16;
+constexpr int kFastTileW = 128, kFastTileH = 32;
 constexpr int kBlurTileW = 64, kBlurTileH = 32;
 
 }  // namespace sdyn

@@ -250,9 +250,7 @@ int sdyn_track_batch(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frame
     for (auto& it : items)
         if (it.src && it.bytesPerFrame)
             TCU(c, cudaMemcpyAsync(t->inBlock + it.off, it.src, it.bytesPerFrame * n, cudaMemcpyHostToDevice, c->stream));
-    for (int f = 0; f < nframes; ++f)
-        TCU(c, cudaMemcpy2DAsync(c->dIn + (size_t)f * W * H, W, gray + (size_t)f * frameStride, stride, W, H,
-                                 cudaMemcpyHostToDevice, c->stream));
+    TCU(c, upload_frames(c, nframes, gray, frameStride, W, H, stride, c->stream));
     sdyn_track_inputs d = *in;
     d.last_points = reinterpret_cast<const sdyn_last_point*>(t->inBlock + items[0].off);
     d.last_keys = reinterpret_cast<const sdyn_keypoint*>(t->inBlock + items[1].off);
@@ -293,21 +291,23 @@ int sdyn_track_fetch(sdyn_ctx* c, int nframes, int32_t* assign, uint8_t* locked,
     TCU(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const int kc = t->cap;
-    if (assign) TCU(c, cudaMemcpyAsync(t->hAssign, t->assign, (size_t)nframes * kc * 4, cudaMemcpyDeviceToHost, st));
-    if (locked) TCU(c, cudaMemcpyAsync(t->hLocked, t->locked, (size_t)nframes * kc, cudaMemcpyDeviceToHost, st));
-    if (dynMask) TCU(c, cudaMemcpyAsync(t->hMask, t->dynMask, (size_t)nframes * kc, cudaMemcpyDeviceToHost, st));
-    TCU(c, cudaMemcpyAsync(t->hCounts, t->counts, (size_t)nframes * 16, cudaMemcpyDeviceToHost, st));
+    const bool direct = cap == kc;
+    if (assign) TCU(c, cudaMemcpyAsync(direct ? assign : t->hAssign, t->assign, (size_t)nframes * kc * 4, cudaMemcpyDeviceToHost, st));
+    if (locked) TCU(c, cudaMemcpyAsync(direct ? locked : t->hLocked, t->locked, (size_t)nframes * kc, cudaMemcpyDeviceToHost, st));
+    if (dynMask) TCU(c, cudaMemcpyAsync(direct ? dynMask : t->hMask, t->dynMask, (size_t)nframes * kc, cudaMemcpyDeviceToHost, st));
+    TCU(c, cudaMemcpyAsync(counts ? counts : t->hCounts, t->counts, (size_t)nframes * 16, cudaMemcpyDeviceToHost, st));
     TCU(c, cudaMemcpyAsync(t->hResult, t->result, (size_t)2 * t->B * 16, cudaMemcpyDeviceToHost, st));
     TCU(c, cudaStreamSynchronize(st));
     for (int f = 0; f < nframes; ++f)
         if (t->hResult[f * 4 + 2] || t->hResult[(t->B + f) * 4 + 2])
             return api_fail(c, SDYN_ERR_CAPACITY, "matcher candidate pool exhausted in the batched front end");
-    const int m = std::min(cap, kc);
-    for (int f = 0; f < nframes; ++f) {
-        if (assign) std::memcpy(assign + (size_t)f * cap, t->hAssign + (size_t)f * kc, (size_t)m * 4);
-        if (locked) std::memcpy(locked + (size_t)f * cap, t->hLocked + (size_t)f * kc, m);
-        if (dynMask) std::memcpy(dynMask + (size_t)f * cap, t->hMask + (size_t)f * kc, m);
-        if (counts) std::memcpy(counts + (size_t)f * 4, t->hCounts + (size_t)f * 4, 16);
+    if (!direct) {
+        const int m = std::min(cap, kc);
+        for (int f = 0; f < nframes; ++f) {
+            if (assign) std::memcpy(assign + (size_t)f * cap, t->hAssign + (size_t)f * kc, (size_t)m * 4);
+            if (locked) std::memcpy(locked + (size_t)f * cap, t->hLocked + (size_t)f * kc, m);
+            if (dynMask) std::memcpy(dynMask + (size_t)f * cap, t->hMask + (size_t)f * kc, m);
+        }
     }
     return SDYN_OK;
 }

@@ -1,0 +1,191 @@
+/* Glue between the reference's object graph (Frame, KeyFrame, MapPoint — include/Frame.h, KeyFrame.h,
+ * MapPoint.h of the reference) and the index-based sdyn C ABI.  Header-only templates: they compile against
+ * the reference's own classes when dropped into its tree (INTEGRATION.md shows the one-line bodies that
+ * replace the loops in src/ORBmatcher.cc, src/Frame.cc and src/Tracking.cc) and against the small stand-ins of
+ * tests/cpp/ref_stubs.h in this repository.
+ *
+ * Pointer <-> index mapping: Frame::mvpMapPoints[i] == NULL <-> assign[i] == -1; a pre-existing occupant is
+ * passed as -2 with locked[i] = (Observations() > 0); a keypoint claimed by query q comes back as q.
+ */
+#ifndef SDYN_HOST_ADAPTERS_HPP
+#define SDYN_HOST_ADAPTERS_HPP
+
+#include "../../include/sdyn.h"
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace sdyn_host {
+
+/* The Frame members the searches read, gathered into the ABI struct.  FrameT: the reference's Frame. */
+template <class FrameT>
+inline sdyn_frame_view frame_view(const FrameT& F)
+{
+    sdyn_frame_view v;
+    std::memset(&v, 0, sizeof(v));
+    v.n = F.N;
+    v.nlevels = F.mnScaleLevels;
+    v.keys = reinterpret_cast<const sdyn_keypoint*>(F.mvKeys.data());
+    v.keys_un = reinterpret_cast<const sdyn_keypoint*>(F.mvKeysUn.data());
+    v.desc = F.mDescriptors.data;                       /* N x 32 CV_8U, continuous */
+    v.u_right = F.mvuRight.empty() ? nullptr : F.mvuRight.data();
+    v.scale_factors = F.mvScaleFactors.data();
+    v.min_x = FrameT::mnMinX; v.min_y = FrameT::mnMinY; v.max_x = FrameT::mnMaxX; v.max_y = FrameT::mnMaxY;
+    v.fx = FrameT::fx; v.fy = FrameT::fy; v.cx = FrameT::cx; v.cy = FrameT::cy; v.bf = F.mbf; v.b = F.mb;
+    if (!F.mTcw.empty())
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 4; ++c) v.tcw[4 * r + c] = F.mTcw.template at<float>(r, c);
+    return v;
+}
+
+template <class FrameT>
+inline void occupancy(const FrameT& F, std::vector<int32_t>& assign, std::vector<uint8_t>& locked)
+{
+    assign.assign(F.N, -1);
+    locked.assign(F.N, 0);
+    for (int i = 0; i < F.N; ++i)
+        if (F.mvpMapPoints[i]) { assign[i] = -2; locked[i] = F.mvpMapPoints[i]->Observations() > 0; }
+}
+
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th)
+ * reference: src/ORBmatcher.cc:45-129 */
+template <class FrameT, class MapPointT>
+inline int SearchByProjection(sdyn_ctx* ctx, FrameT& F, const std::vector<MapPointT*>& vpMapPoints, float th, float nnratio)
+{
+    std::vector<sdyn_mappoint_query> q(vpMapPoints.size());
+    for (size_t i = 0; i < vpMapPoints.size(); ++i) {
+        MapPointT* p = vpMapPoints[i];
+        sdyn_mappoint_query& m = q[i];
+        std::memset(&m, 0, sizeof(m));
+        m.track_in_view = p->mbTrackInView;
+        m.bad = p->isBad();
+        if (!m.track_in_view || m.bad) continue;
+        m.proj_x = p->mTrackProjX; m.proj_y = p->mTrackProjY; m.proj_xr = p->mTrackProjXR;
+        m.view_cos = p->mTrackViewCos; m.level = p->mnTrackScaleLevel;
+        m.obs_positive = p->Observations() > 0;
+        const cv::Mat d = p->GetDescriptor();
+        std::memcpy(m.desc, d.data, 32);
+    }
+    std::vector<int32_t> assign; std::vector<uint8_t> locked;
+    occupancy(F, assign, locked);
+    sdyn_frame_view v = frame_view(F);
+    int n = 0;
+    if (sdyn_match_projection_map(ctx, &v, q.data(), (int)q.size(), th, nnratio, assign.data(), locked.data(), &n) != SDYN_OK)
+        return 0;
+    for (int i = 0; i < F.N; ++i)
+        if (assign[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[assign[i]];
+    return n;
+}
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+ * and the fork's overload with point-pair outputs — reference: src/ORBmatcher.cc:1485-1627, 407-559 */
+template <class FrameT, class PointT>
+inline int SearchByProjection(sdyn_ctx* ctx, FrameT& Cur, const FrameT& Last, float th, bool bMono, bool checkOrientation,
+                              std::vector<PointT>* pointsLast, std::vector<PointT>* pointsCurrent)
+{
+    std::vector<sdyn_last_point> lp(Last.N);
+    for (int i = 0; i < Last.N; ++i) {
+        sdyn_last_point& p = lp[i];
+        std::memset(&p, 0, sizeof(p));
+        auto* mp = Last.mvpMapPoints[i];
+        if (!mp) continue;
+        p.has_mp = 1; p.outlier = Last.mvbOutlier[i]; p.obs_positive = mp->Observations() > 0;
+        const cv::Mat w = mp->GetWorldPos();
+        for (int k = 0; k < 3; ++k) p.world[k] = w.template at<float>(k, 0);
+        const cv::Mat d = mp->GetDescriptor();
+        std::memcpy(p.desc, d.data, 32);
+    }
+    std::vector<int32_t> assign; std::vector<uint8_t> locked;
+    occupancy(Cur, assign, locked);
+    sdyn_frame_view c = frame_view(Cur), l = frame_view(Last);
+    std::vector<float> pairs(pointsLast ? (size_t)4 * std::max(Last.N, 1) : 0);
+    int n = 0, np = 0;
+    if (sdyn_match_projection_frame(ctx, &c, &l, lp.data(), th, bMono, checkOrientation, assign.data(), locked.data(), &n,
+                                    pointsLast ? pairs.data() : nullptr, pointsLast ? &np : nullptr) != SDYN_OK)
+        return 0;
+    for (int i = 0; i < Cur.N; ++i) {
+        if (assign[i] >= 0) Cur.mvpMapPoints[i] = Last.mvpMapPoints[assign[i]];
+        else if (assign[i] == -1) Cur.mvpMapPoints[i] = nullptr;      /* nulled by the rotation cull */
+    }
+    if (pointsLast && pointsCurrent)
+        for (int k = 0; k < np; ++k) {
+            pointsLast->push_back(PointT(pairs[4 * k], pairs[4 * k + 1]));
+            pointsCurrent->push_back(PointT(pairs[4 * k + 2], pairs[4 * k + 3]));
+        }
+    return n;
+}
+
+/* ORBmatcher::SearchForInitialization — reference: src/ORBmatcher.cc:562-677 */
+template <class FrameT, class PointT>
+inline int SearchForInitialization(sdyn_ctx* ctx, FrameT& F1, FrameT& F2, std::vector<PointT>& vbPrevMatched,
+                                   std::vector<int>& vnMatches12, int windowSize, float nnratio, bool checkOrientation)
+{
+    const int n1 = (int)F1.mvKeysUn.size();
+    vnMatches12.assign(n1, -1);
+    std::vector<float> prev((size_t)2 * n1);
+    for (int i = 0; i < n1; ++i) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+    sdyn_frame_view a = frame_view(F1), b = frame_view(F2);
+    int n = 0;
+    static_assert(sizeof(int) == sizeof(int32_t), "int32 matches");
+    if (sdyn_match_init(ctx, &a, &b, prev.data(), vnMatches12.data(), windowSize, nnratio, checkOrientation, &n) != SDYN_OK)
+        return 0;
+    for (int i = 0; i < n1; ++i) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+    return n;
+}
+
+/* DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>) -> CSR */
+struct FeatureVectorCSR {
+    std::vector<uint32_t> node, index; std::vector<int32_t> offset;
+    sdyn_feature_vector view() const { return {(int32_t)node.size(), node.data(), offset.data(), index.data()}; }
+    template <class MapT> explicit FeatureVectorCSR(const MapT& fv)
+    {
+        offset.push_back(0);
+        for (auto it = fv.begin(); it != fv.end(); ++it) {
+            node.push_back((uint32_t)it->first);
+            for (unsigned v : it->second) index.push_back(v);
+            offset.push_back((int32_t)index.size());
+        }
+    }
+};
+
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)
+ * reference: src/ORBmatcher.cc:159-288 */
+template <class KeyFrameT, class FrameT, class MapPointT>
+inline int SearchByBoW(sdyn_ctx* ctx, KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches, float nnratio,
+                       bool checkOrientation)
+{
+    const std::vector<MapPointT*> kfPoints = pKF->GetMapPointMatches();
+    vpMapPointMatches.assign(F.N, static_cast<MapPointT*>(nullptr));
+    std::vector<uint8_t> valid(kfPoints.size(), 0);
+    for (size_t i = 0; i < kfPoints.size(); ++i) valid[i] = kfPoints[i] && !kfPoints[i]->isBad();
+    sdyn_frame_view kv;
+    std::memset(&kv, 0, sizeof(kv));
+    kv.n = (int)kfPoints.size(); kv.nlevels = F.mnScaleLevels;
+    kv.keys = kv.keys_un = reinterpret_cast<const sdyn_keypoint*>(pKF->mvKeysUn.data());
+    kv.desc = pKF->mDescriptors.data;
+    kv.max_x = kv.max_y = 1.f;
+    sdyn_frame_view fv = frame_view(F);
+    FeatureVectorCSR a(pKF->mFeatVec), b(F.mFeatVec);
+    sdyn_feature_vector av = a.view(), bv = b.view();
+    std::vector<int32_t> assign(F.N, -1);
+    int n = 0;
+    if (sdyn_match_bow(ctx, &kv, valid.data(), &av, &fv, &bv, nnratio, checkOrientation, assign.data(), &n) != SDYN_OK)
+        return 0;
+    for (int i = 0; i < F.N; ++i)
+        if (assign[i] >= 0) vpMapPointMatches[i] = kfPoints[assign[i]];
+    return n;
+}
+
+/* Frame::firstSeparate (src/Frame.cc:555-604): the keypoint-in-box test runs on the device; the reorder and
+ * the reference's box bookkeeping (incl. its erase-while-iterating behaviour) stay host code in Frame. */
+template <class KeyPointT, class RectT>
+inline bool BoxMask(sdyn_ctx* ctx, const std::vector<KeyPointT>& keys, const std::vector<RectT>& boxes, std::vector<uint64_t>& mask)
+{
+    static_assert(sizeof(RectT) == 4 * sizeof(double), "cv::Rect2d layout");
+    mask.assign(keys.size(), 0);
+    return sdyn_dyn_box_mask(ctx, reinterpret_cast<const sdyn_keypoint*>(keys.data()), (int)keys.size(),
+                             reinterpret_cast<const double*>(boxes.data()), (int)boxes.size(), mask.data()) == SDYN_OK;
+}
+
+}  // namespace sdyn_host
+#endif

@@ -1,0 +1,77 @@
+"""The drop-in C++ adapter classes (slam-dynamic_b200/host/: ORB_SLAM2::ORBextractor with the reference's
+signature, and the ORBmatcher glue templates) run on the GPU through a small C++ program; its dumped inputs are
+replayed through the CPU oracle here."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+import pysdyn
+import scenario
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "test_adapter")
+
+
+def read_dump(path):
+    out = {}
+    with open(path, "rb") as f:
+        while True:
+            h = f.read(4)
+            if len(h) < 4:
+                break
+            name = f.read(struct.unpack("<I", h)[0]).decode()
+            nbytes = struct.unpack("<Q", f.read(8))[0]
+            out[name] = f.read(nbytes)
+    return out
+
+
+def test_adapter_library_exports_reference_symbols():
+    """CPU check: the adapter library was built and exports ORB_SLAM2::ORBextractor's constructor and operator()."""
+    lib = os.path.join(ROOT, "slam-dynamic_b200", "libsdyn_host.so")
+    assert os.path.exists(lib), "run __graft_entry__.build()"
+    syms = subprocess.check_output(["nm", "-DC", lib]).decode()
+    assert "ORB_SLAM2::ORBextractor::ORBextractor(int, float, int, int, int)" in syms
+    assert "ORB_SLAM2::ORBextractor::operator()(cv::_InputArray const&, cv::_InputArray const&, std::vector<cv::KeyPoint" in syms
+
+
+@pytest.mark.gpu
+def test_adapter_classes_match_oracle(tmp_path):
+    out = str(tmp_path / "adapter.bin")
+    r = subprocess.run([BIN, out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = read_dump(out)
+    W, H = 640, 480
+    img1 = np.frombuffer(d["img1"], np.uint8).reshape(H, W)
+    E = orc.Extractor(1000, 1.2, 8, 20, 7)
+    k, desc = E(img1)
+    ck = np.frombuffer(d["cur_keys"], pysdyn.KP_DTYPE); cd = np.frombuffer(d["cur_desc"], np.uint8).reshape(-1, 32)
+    assert len(ck) == len(k)
+    for name in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(ck[name], k[name]), name
+    assert np.max(np.abs(ck["angle"] - k["angle"])) <= 1e-3 and (cd == desc).all(1).mean() >= 0.999
+    lw, lh = struct.unpack("<ii", d["level3_dims"])
+    assert np.array_equal(np.frombuffer(d["level3"], np.uint8).reshape(lh, lw), E.level(3)[19:-19, 19:-19])   # mvImagePyramid[3]
+    scale = np.frombuffer(d["scale"], np.float32)
+    assert np.array_equal(scale, E.scale)
+
+    lk = np.frombuffer(d["last_keys"], pysdyn.KP_DTYPE); ld = np.frombuffer(d["last_desc"], np.uint8).reshape(-1, 32)
+    lp = np.frombuffer(d["last_points"], pysdyn.LASTPOINT_DTYPE)
+    cam = scenario.KITTI_CAM
+    camt = (cam["fx"], cam["fy"], cam["cx"], cam["cy"], np.float32(379.8145), np.float32(379.8145) / np.float32(cam["fx"]))
+    cur = pysdyn.FrameView(ck, cd, scale, (0.0, 0.0, float(W), float(H)), u_right=np.full(len(ck), -1, np.float32), cam=camt)
+    last = pysdyn.FrameView(lk, ld, scale, (0.0, 0.0, float(W), float(H)), u_right=np.full(len(lk), -1, np.float32), cam=camt)
+    n1, a1, l1, pairs = orc.match_projection_frame(cur, last, lp, 15.0, True, True, want_pairs=True)
+    assert struct.unpack("<i", d["frame_n"])[0] == n1 and n1 > 100
+    assert np.array_equal(np.frombuffer(d["frame_assign"], np.int32), a1)
+    assert np.array_equal(np.frombuffer(d["frame_pairs"], np.float32).reshape(-1, 4), pairs)
+
+    mp = np.frombuffer(d["map_points"], pysdyn.MAPPOINT_DTYPE)
+    a0 = np.where(a1 >= 0, -2, -1).astype(np.int32)
+    n2, a2, l2 = orc.match_projection_map(cur, mp, 3.0, 0.8, a0, l1)
+    expect = np.where(a2 >= 0, 100000 + a2, np.where(a2 == -2, a1, -1)).astype(np.int32)
+    assert struct.unpack("<i", d["map_n"])[0] == n2 and n2 > 50
+    assert np.array_equal(np.frombuffer(d["map_assign"], np.int32), expect)
