@@ -12,38 +12,59 @@
 namespace sdyn {
 
 constexpr int BW = kBlurTileW, BH = kBlurTileH;
+constexpr int PXB = BW + 32;                 /* staged bytes per row: columns x0-16 .. x0+BW+15, 16-byte aligned */
+static_assert(BW % 16 == 0 && BH % 2 == 0, "tile shape");
 
 __global__ void __launch_bounds__(256)
 k_blur(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const uint8_t* __restrict__ pyr,
        uint8_t* __restrict__ blur)
 {
-    __shared__ uint8_t px[(BH + 6) * (BW + 8)];
-    __shared__ uint16_t hz[(BH + 6) * BW];
+    __shared__ __align__(16) uint8_t px[(BH + 6) * PXB];
+    __shared__ __align__(8) uint16_t hz[(BH + 6) * BW];
     const TileRef t = tiles[blockIdx.x];
     const LevelGeom& L = g.L[t.level];
     const int x0 = t.tx * BW, y0 = t.ty * BH, tid = threadIdx.x;
     const uint8_t* img = pyr + (size_t)blockIdx.y * g.frameBytes + L.off;
-    const int hiX = L.w + kEdge - 1, hiY = L.h + kEdge - 1;
-    for (int i = tid; i < (BH + 6) * (BW + 6); i += 256) {
-        const int yy = i / (BW + 6), xx = i - yy * (BW + 6);
-        const int gx = min(x0 - 3 + xx, hiX), gy = min(y0 - 3 + yy, hiY);
-        px[yy * (BW + 8) + xx] = img[(long long)gy * L.pitch + gx];
+    /* rows y0-3 .. y0+BH+2 (clamped to the bordered extent), 16-byte vector loads; the frame supplies the halo */
+    for (int i = tid; i < (BH + 6) * (PXB / 16); i += 256) {
+        const int yy = i / (PXB / 16), q = i - yy * (PXB / 16);
+        const int gy = min(y0 - 3 + yy, L.h + kEdge - 1);
+        reinterpret_cast<uint4*>(px + yy * PXB)[q] =
+            __ldg(reinterpret_cast<const uint4*>(img + (long long)gy * L.pitch + x0 - 16) + q);
     }
     __syncthreads();
-    for (int i = tid; i < (BH + 6) * BW; i += 256) {
-        const int yy = i / BW, xx = i - yy * BW;
-        const uint8_t* p = &px[yy * (BW + 8) + xx];
-        hz[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    /* horizontal pass: 4 adjacent outputs per thread from 10 staged bytes */
+    for (int i = tid; i < (BH + 6) * (BW / 4); i += 256) {
+        const int yy = i / (BW / 4), xq = i - yy * (BW / 4);
+        const uint8_t* p = &px[yy * PXB + 13 + 4 * xq];           /* column x0 + 4*xq - 3 */
+        int v[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v[k] = p[k];
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            o[k] = 18 * (v[k] + v[k + 6]) + 34 * (v[k + 1] + v[k + 5]) + 48 * (v[k + 2] + v[k + 4]) + 56 * v[k + 3];
+        reinterpret_cast<uint2*>(hz + yy * BW)[xq] = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
     }
     __syncthreads();
+    /* vertical pass: 4 adjacent columns per thread, one aligned 32-bit store */
     uint8_t* out = blur + (size_t)blockIdx.y * g.frameBytes + L.off;
-    for (int i = tid; i < BH * BW; i += 256) {
-        const int yy = i / BW, xx = i - yy * BW;
-        const int gx = x0 + xx, gy = y0 + yy;
+    for (int i = tid; i < BH * (BW / 4); i += 256) {
+        const int yy = i / (BW / 4), xq = i - yy * (BW / 4);
+        const int gx = x0 + 4 * xq, gy = y0 + yy;
         if (gx >= L.w || gy >= L.h) continue;
-        const uint16_t* p = &hz[yy * BW + xx];
-        const int v = 18 * (p[0] + p[6 * BW]) + 34 * (p[BW] + p[5 * BW]) + 48 * (p[2 * BW] + p[4 * BW]) + 56 * p[3 * BW];
-        out[(long long)gy * L.pitch + gx] = (uint8_t)((v + 32768) >> 16);
+        int acc[4] = {0, 0, 0, 0};
+        const int kk[7] = {18, 34, 48, 56, 48, 34, 18};
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const uint2 w = reinterpret_cast<const uint2*>(hz + (yy + r) * BW)[xq];
+            acc[0] += kk[r] * (int)(w.x & 0xffff); acc[1] += kk[r] * (int)(w.x >> 16);
+            acc[2] += kk[r] * (int)(w.y & 0xffff); acc[3] += kk[r] * (int)(w.y >> 16);
+        }
+        const uint32_t o = (uint32_t)((acc[0] + 32768) >> 16) | ((uint32_t)((acc[1] + 32768) >> 16) << 8) |
+                           ((uint32_t)((acc[2] + 32768) >> 16) << 16) | ((uint32_t)((acc[3] + 32768) >> 16) << 24);
+        /* columns past the level's width land in the right frame / pad of the blurred buffer, which nobody reads */
+        *reinterpret_cast<uint32_t*>(out + (long long)gy * L.pitch + gx) = o;
     }
 }
 

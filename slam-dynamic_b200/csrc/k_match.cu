@@ -389,7 +389,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs)
  * by q).  Jacobi iteration from "nothing locked" makes queries 0..t-1 final after sweep t, so it stops after
  * (longest conflict chain + 1) sweeps — 2-4 on real frames — and every sweep is data-parallel over queries.
  * One CTA per search; T and the per-query decisions live in shared memory. */
-constexpr int RF = 256;
+constexpr int RF = 1024;
 
 __global__ void __launch_bounds__(RF)
 k_match_resolve_fix(const MatchJob* __restrict__ jobs)
@@ -423,11 +423,16 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
         for (int q = tid; q < nq; q += RF) {
             const int2 span = J.qspan[q];
             uint32_t a = NONE, b = NONE;
-            for (int p = 0; p < span.y; ++p) {
-                const uint32_t rec = J.pool[span.x + p];
-                if (lockT[rec_idx(rec)] < q) continue;
-                const uint32_t key = ((uint32_t)rec_dist(rec) << 20) | (uint32_t)p;
-                if (key < a) { b = a; a = key; } else if (key < b) b = key;
+            for (int p0 = 0; p0 < span.y; p0 += 8) {
+                uint32_t rec[8];                       /* 8 independent loads in flight per thread */
+#pragma unroll
+                for (int k = 0; k < 8; ++k) rec[k] = p0 + k < span.y ? __ldg(J.pool + span.x + p0 + k) : NONE;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (rec[k] == NONE || lockT[rec_idx(rec[k])] < q) continue;
+                    const uint32_t key = ((uint32_t)rec_dist(rec[k]) << 20) | (uint32_t)(p0 + k);
+                    if (key < a) { b = a; a = key; } else if (key < b) b = key;
+                }
             }
             int res = -1;
             if (a != NONE) {

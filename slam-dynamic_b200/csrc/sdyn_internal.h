@@ -33,6 +33,8 @@ struct LevelGeom {
     float patchSize;
     /* resize tables (level > 0): byte offsets into the table blob */
     int xtab, ytab;
+    /* shared-memory staging of the resize kernel: worst-case source rectangle of a 128 x 16 output tile */
+    int rsPitch, rsRows;
 };
 
 struct Geom {
@@ -147,6 +149,6 @@ cudaError_t launch_orient_describe(const Geom& g, const uint8_t* dPyr, const uin
 size_t octree_smem_bytes(int nodeCap);
 
 constexpr int kFastTileW = 128, kFastTileH = 32;
-constexpr int kBlurTileW = 64, kBlurTileH = 32;
+constexpr int kBlurTileW = 128, kBlurTileH = 32;
 
 }  // namespace sdyn
