@@ -292,6 +292,7 @@ def main():
     ex.profile(False)
     clocks = sampler.stop() if sampler else None
     launches = ex.launch_count() - launches0
+    launches_per_step = launches // max(K, 1)
     kps, desc, counts = ex.fetch(B)
     assign, locked, mask, cnt = pysdyn.track_fetch(ex, B)
     mean_kp = float(counts.mean())
@@ -303,24 +304,39 @@ def main():
     hptrs = {k: (p.array.ctypes.data, p.array.shape[1]) for k, p in pin.items()}
     pin_in = pysdyn.PinnedArray((POOL, H, W), np.uint8)
     pin_in.array[:] = cur_frames
-    outs = tuple(pysdyn.PinnedArray(shape, dt) for shape, dt in
-                 [((B, cap), pysdyn.KP_DTYPE), ((B, cap, 32), np.uint8), ((B,), np.int32), ((B, cap), np.int32),
-                  ((B, cap), np.uint8), ((B, cap), np.uint8), ((B, 4), np.int32)])
-    out_arrays = tuple(o.array for o in outs)
+    # two contexts used alternately: step s+1's PCIe copies overlap step s's kernels (each context has its own stream)
+    ctxs = [ex, pysdyn.Extractor(nf, SCALE, NLEVELS, ini, mn, max_width=W, max_height=H, max_batch=B, device=local)]
+    out_sets = []
+    for _ in ctxs:
+        o = tuple(pysdyn.PinnedArray(shape, dt) for shape, dt in
+                  [((B, cap), pysdyn.KP_DTYPE), ((B, cap, 32), np.uint8), ((B,), np.int32), ((B, cap), np.int32),
+                   ((B, cap), np.uint8), ((B, cap), np.uint8), ((B, 4), np.int32)])
+        out_sets.append((o, tuple(a.array for a in o)))
 
-    def step_host(s):
+    def step_host_async(s):
         base = (s % nsets) * B
         tin = pysdyn.track_inputs(hptrs, base, strides, params)
-        pysdyn.track_batch_host(ex, pin_in.array[base:base + B], tin, out_arrays)
+        pysdyn.track_batch_host_async(ctxs[s % 2], pin_in.array[base:base + B], tin, out_sets[s % 2][1])
 
-    for s in range(2):
-        step_host(s)
+    def run_host(first, count):
+        for s in range(first, first + count):
+            if s >= first + 2:
+                pysdyn.track_wait(ctxs[s % 2])              # the step issued two iterations ago on this context
+            step_host_async(s)
+        for s in range(max(first, first + count - 2), first + count):
+            pysdyn.track_wait(ctxs[s % 2])
+
+    run_host(0, 4)
     barrier()
     t0 = time.perf_counter()
-    for s in range(K):
-        step_host(Wm + s)
+    run_host(Wm, K)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # the e2e outputs of the last step must equal the device-resident run's results for the same frames
+    last = Wm + K - 1
+    if (last % nsets) == ((Wm + K - 1) % nsets):
+        eo = out_sets[last % 2][1]
+        assert np.array_equal(eo[2], counts) and np.array_equal(eo[6], cnt), "e2e and device-resident results differ"
     h2d = B * W * H + sum(p.array.shape[1] for p in pin.values()) * B
     d2h = B * (cap * (28 + 32) + 4 + cap * 6 + 16)
 

@@ -296,6 +296,13 @@ int sdyn_track_batch_device(sdyn_ctx* ctx, int nframes, const uint8_t* d_gray, s
 int sdyn_track_batch(sdyn_ctx* ctx, int nframes, const uint8_t* gray, size_t frame_stride, int width, int height,
                      int stride, const sdyn_track_inputs* in, sdyn_keypoint* kp_out, uint8_t* desc_out, int* n_out,
                      int32_t* assign, uint8_t* locked, uint8_t* dyn_mask, int32_t* counts, int cap);
+/* Asynchronous form: returns once the copies and kernels are enqueued on the context's stream; the output
+ * arrays are valid after sdyn_track_wait().  Two contexts used alternately overlap one step's PCIe transfers
+ * with the other's kernels (pin the host buffers with sdyn_host_alloc for truly asynchronous copies). */
+int sdyn_track_batch_async(sdyn_ctx* ctx, int nframes, const uint8_t* gray, size_t frame_stride, int width, int height,
+                           int stride, const sdyn_track_inputs* in, sdyn_keypoint* kp_out, uint8_t* desc_out, int* n_out,
+                           int32_t* assign, uint8_t* locked, uint8_t* dyn_mask, int32_t* counts, int cap);
+int sdyn_track_wait(sdyn_ctx* ctx);
 int sdyn_track_results(const sdyn_ctx* ctx, sdyn_track_view* out);
 /* D2H of the step results next to sdyn_fetch_results (host arrays sized [nframes][cap] / [nframes][4]). */
 int sdyn_track_fetch(sdyn_ctx* ctx, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dyn_mask,

@@ -125,6 +125,40 @@ cudaError_t upload_frames(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t 
     return cudaSuccess;
 }
 
+/* D2H of the extraction results: enqueue (asynchronous) and finish (after the stream has been synchronised). */
+int fetch_enqueue(sdyn_ctx* c, int nframes, sdyn_keypoint* kpOut, uint8_t* descOut, int cap, cudaStream_t st)
+{
+    CU(c, cudaMemcpyAsync(c->hCount, c->dCount, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(c->hStatus, c->dStatus, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, st));
+    /* same per-frame capacity as the device arrays: copy straight into the caller's buffers (asynchronous when
+     * they are pinned); otherwise stage in pinned memory and scatter in fetch_finish */
+    const bool direct = cap == c->maxKp;
+    if (cap > 0) {
+        CU(c, cudaMemcpyAsync(direct ? kpOut : c->hKp, c->dKp, sizeof(sdyn_keypoint) * (size_t)c->maxKp * nframes, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaMemcpyAsync(direct ? descOut : c->hDesc, c->dDesc, (size_t)32 * c->maxKp * nframes, cudaMemcpyDeviceToHost, st));
+    }
+    return SDYN_OK;
+}
+
+int fetch_finish(sdyn_ctx* c, int nframes, sdyn_keypoint* kpOut, uint8_t* descOut, int cap, int* nOut)
+{
+    const bool direct = cap == c->maxKp;
+    int rc = SDYN_OK;
+    for (int f = 0; f < nframes; ++f) {
+        if (c->hStatus[f]) return fail(c, SDYN_ERR_CAPACITY, "internal candidate/node capacity exceeded");
+        const int n = c->hCount[f];
+        nOut[f] = n;
+        const int m = std::min(n, cap);
+        if (n > cap) rc = SDYN_ERR_CAPACITY;
+        if (m > 0 && !direct) {
+            std::memcpy(kpOut + (size_t)f * cap, c->hKp + (size_t)f * c->maxKp, sizeof(sdyn_keypoint) * m);
+            std::memcpy(descOut + (size_t)f * cap * 32, c->hDesc + (size_t)f * c->maxKp * 32, (size_t)32 * m);
+        }
+    }
+    if (rc != SDYN_OK) fail(c, rc, "output capacity too small (see sdyn_max_keypoints)");
+    return rc;
+}
+
 /* Enqueues the whole extraction pipeline for nframes frames already resident in device memory. */
 int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride, int rowStride, cudaStream_t st)
 {
@@ -306,30 +340,10 @@ int sdyn_fetch_results(sdyn_ctx* c, int nframes, sdyn_keypoint* kpOut, uint8_t* 
         return fail(c, SDYN_ERR_ARG, "sdyn_fetch_results: bad argument");
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaMemcpyAsync(c->hCount, c->dCount, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, st));
-    CU(c, cudaMemcpyAsync(c->hStatus, c->dStatus, sizeof(int32_t) * nframes, cudaMemcpyDeviceToHost, st));
-    /* same per-frame capacity as the device arrays: copy straight into the caller's buffers (asynchronous when
-     * they are pinned); otherwise stage in pinned memory and scatter */
-    const bool direct = cap == c->maxKp;
-    if (cap > 0) {
-        CU(c, cudaMemcpyAsync(direct ? kpOut : c->hKp, c->dKp, sizeof(sdyn_keypoint) * (size_t)c->maxKp * nframes, cudaMemcpyDeviceToHost, st));
-        CU(c, cudaMemcpyAsync(direct ? descOut : c->hDesc, c->dDesc, (size_t)32 * c->maxKp * nframes, cudaMemcpyDeviceToHost, st));
-    }
+    int rc = sdyn::fetch_enqueue(c, nframes, kpOut, descOut, cap, st);
+    if (rc != SDYN_OK) return rc;
     CU(c, cudaStreamSynchronize(st));
-    int rc = SDYN_OK;
-    for (int f = 0; f < nframes; ++f) {
-        if (c->hStatus[f]) return fail(c, SDYN_ERR_CAPACITY, "internal candidate/node capacity exceeded");
-        const int n = c->hCount[f];
-        nOut[f] = n;
-        const int m = std::min(n, cap);
-        if (n > cap) rc = SDYN_ERR_CAPACITY;
-        if (m > 0 && !direct) {
-            std::memcpy(kpOut + (size_t)f * cap, c->hKp + (size_t)f * c->maxKp, sizeof(sdyn_keypoint) * m);
-            std::memcpy(descOut + (size_t)f * cap * 32, c->hDesc + (size_t)f * c->maxKp * 32, (size_t)32 * m);
-        }
-    }
-    if (rc != SDYN_OK) fail(c, rc, "output capacity too small (see sdyn_max_keypoints)");
-    return rc;
+    return sdyn::fetch_finish(c, nframes, kpOut, descOut, cap, nOut);
 }
 
 int sdyn_extract_batch(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frameStride, int W, int H, int stride,

@@ -113,6 +113,8 @@ namespace sdyn {
 int ensure_geometry(sdyn_ctx* c, int W, int H);
 cudaError_t upload_frames(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frameStride, int W, int H, int stride,
                           cudaStream_t st);
+int fetch_enqueue(sdyn_ctx* c, int nframes, sdyn_keypoint* kpOut, uint8_t* descOut, int cap, cudaStream_t st);
+int fetch_finish(sdyn_ctx* c, int nframes, sdyn_keypoint* kpOut, uint8_t* descOut, int cap, int* nOut);
 int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride, int rowStride, cudaStream_t st);
 struct StageTimer {          /* brackets a stage with CUDA events while profiling is enabled */
     sdyn_ctx* c; cudaStream_t st; int stage; cudaEvent_t a;

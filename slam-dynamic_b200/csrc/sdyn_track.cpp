@@ -20,6 +20,9 @@ struct TrackState {
     std::vector<MatchJob> hJobs;
     /* device staging of host inputs (sdyn_track_batch) */
     uint8_t* inBlock = nullptr; size_t inBytes = 0;
+    /* asynchronous step in flight (sdyn_track_batch_async .. sdyn_track_wait) */
+    struct Pending { bool active = false; int nframes = 0, cap = 0; sdyn_keypoint* kp = nullptr; uint8_t* desc = nullptr;
+                     int* nOut = nullptr; int32_t* assign = nullptr; uint8_t* locked = nullptr; uint8_t* mask = nullptr; } pending;
     /* pinned staging for sdyn_track_fetch */
     int32_t* hAssign = nullptr; uint8_t* hLocked = nullptr; uint8_t* hMask = nullptr; int32_t* hCounts = nullptr; int32_t* hResult = nullptr;
 };
@@ -97,6 +100,40 @@ __global__ void k_copy_match_counts(const int32_t* __restrict__ result, int B, i
     if (f >= nframes) return;
     counts[f * 4] = result[f * 4];                 /* SearchByProjection(cur, last) */
     counts[f * 4 + 1] = result[(B + f) * 4];       /* SearchByProjection(F, map points) */
+}
+
+int track_fetch_enqueue(sdyn_ctx* c, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dynMask, int32_t* counts, int cap,
+                        cudaStream_t st)
+{
+    TrackState* t = static_cast<TrackState*>(c->track);
+    const int kc = t->cap;
+    const bool direct = cap == kc;
+#define TQ(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return api_fail(c, SDYN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+    if (assign) TQ(cudaMemcpyAsync(direct ? assign : t->hAssign, t->assign, (size_t)nframes * kc * 4, cudaMemcpyDeviceToHost, st));
+    if (locked) TQ(cudaMemcpyAsync(direct ? locked : t->hLocked, t->locked, (size_t)nframes * kc, cudaMemcpyDeviceToHost, st));
+    if (dynMask) TQ(cudaMemcpyAsync(direct ? dynMask : t->hMask, t->dynMask, (size_t)nframes * kc, cudaMemcpyDeviceToHost, st));
+    TQ(cudaMemcpyAsync(counts ? counts : t->hCounts, t->counts, (size_t)nframes * 16, cudaMemcpyDeviceToHost, st));
+    TQ(cudaMemcpyAsync(t->hResult, t->result, (size_t)2 * t->B * 16, cudaMemcpyDeviceToHost, st));
+#undef TQ
+    return SDYN_OK;
+}
+
+int track_fetch_finish(sdyn_ctx* c, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dynMask, int cap)
+{
+    TrackState* t = static_cast<TrackState*>(c->track);
+    const int kc = t->cap;
+    for (int f = 0; f < nframes; ++f)
+        if (t->hResult[f * 4 + 2] || t->hResult[(t->B + f) * 4 + 2])
+            return api_fail(c, SDYN_ERR_CAPACITY, "matcher candidate pool exhausted in the batched front end");
+    if (cap != kc) {
+        const int m = std::min(cap, kc);
+        for (int f = 0; f < nframes; ++f) {
+            if (assign) std::memcpy(assign + (size_t)f * cap, t->hAssign + (size_t)f * kc, (size_t)m * 4);
+            if (locked) std::memcpy(locked + (size_t)f * cap, t->hLocked + (size_t)f * kc, m);
+            if (dynMask) std::memcpy(dynMask + (size_t)f * cap, t->hMask + (size_t)f * kc, m);
+        }
+    }
+    return SDYN_OK;
 }
 
 }  // namespace sdyn
@@ -213,6 +250,15 @@ int sdyn_track_batch(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frame
                      const sdyn_track_inputs* in, sdyn_keypoint* kpOut, uint8_t* descOut, int* nOut, int32_t* assign,
                      uint8_t* locked, uint8_t* dynMask, int32_t* counts, int cap)
 {
+    int rc = sdyn_track_batch_async(c, nframes, gray, frameStride, W, H, stride, in, kpOut, descOut, nOut, assign, locked,
+                                    dynMask, counts, cap);
+    return rc == SDYN_OK ? sdyn_track_wait(c) : rc;
+}
+
+int sdyn_track_batch_async(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frameStride, int W, int H, int stride,
+                           const sdyn_track_inputs* in, sdyn_keypoint* kpOut, uint8_t* descOut, int* nOut, int32_t* assign,
+                           uint8_t* locked, uint8_t* dynMask, int32_t* counts, int cap)
+{
     if (!c) return SDYN_ERR_ARG;
     if (!in || !gray || nframes < 1 || nframes > c->maxBatch || W < 1 || H < 1 || stride < W || W > c->maxW || H > c->maxH)
         return api_fail(c, SDYN_ERR_ARG, "sdyn_track_batch: bad argument");
@@ -265,13 +311,19 @@ int sdyn_track_batch(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frame
     d.ref_xy = reinterpret_cast<const float*>(t->inBlock + items[10].off);
     d.ref_off = reinterpret_cast<const int32_t*>(t->inBlock + items[11].off);
     d.fmat = reinterpret_cast<const float*>(t->inBlock + items[12].off);
+    if (t->pending.active) return api_fail(c, SDYN_ERR_ARG, "sdyn_track_batch_async: previous step not waited for");
     rc = sdyn_track_batch_device(c, nframes, c->dIn, (size_t)W * H, W, H, W, &d, nullptr);
     if (rc != SDYN_OK) return rc;
+    t = static_cast<TrackState*>(c->track);
     if (nOut) {
-        rc = sdyn_fetch_results(c, nframes, kpOut, descOut, (kpOut && descOut) ? cap : 0, nOut, nullptr);
-        if (rc != SDYN_OK && !(rc == SDYN_ERR_CAPACITY && !(kpOut && descOut))) return rc;
+        rc = fetch_enqueue(c, nframes, kpOut, descOut, (kpOut && descOut) ? cap : 0, c->stream);
+        if (rc != SDYN_OK) return rc;
     }
-    return sdyn_track_fetch(c, nframes, assign, locked, dynMask, counts, cap, nullptr);
+    rc = track_fetch_enqueue(c, nframes, assign, locked, dynMask, counts, cap, c->stream);
+    if (rc != SDYN_OK) return rc;
+    t->pending.active = true; t->pending.nframes = nframes; t->pending.cap = cap; t->pending.kp = kpOut; t->pending.desc = descOut;
+    t->pending.nOut = nOut; t->pending.assign = assign; t->pending.locked = locked; t->pending.mask = dynMask;
+    return SDYN_OK;
 }
 
 int sdyn_track_results(const sdyn_ctx* c, sdyn_track_view* out)
@@ -290,26 +342,27 @@ int sdyn_track_fetch(sdyn_ctx* c, int nframes, int32_t* assign, uint8_t* locked,
     if (!t || nframes < 1 || nframes > t->B || cap < 0) return api_fail(c, SDYN_ERR_ARG, "sdyn_track_fetch: bad argument");
     TCU(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    const int kc = t->cap;
-    const bool direct = cap == kc;
-    if (assign) TCU(c, cudaMemcpyAsync(direct ? assign : t->hAssign, t->assign, (size_t)nframes * kc * 4, cudaMemcpyDeviceToHost, st));
-    if (locked) TCU(c, cudaMemcpyAsync(direct ? locked : t->hLocked, t->locked, (size_t)nframes * kc, cudaMemcpyDeviceToHost, st));
-    if (dynMask) TCU(c, cudaMemcpyAsync(direct ? dynMask : t->hMask, t->dynMask, (size_t)nframes * kc, cudaMemcpyDeviceToHost, st));
-    TCU(c, cudaMemcpyAsync(counts ? counts : t->hCounts, t->counts, (size_t)nframes * 16, cudaMemcpyDeviceToHost, st));
-    TCU(c, cudaMemcpyAsync(t->hResult, t->result, (size_t)2 * t->B * 16, cudaMemcpyDeviceToHost, st));
+    int rc = track_fetch_enqueue(c, nframes, assign, locked, dynMask, counts, cap, st);
+    if (rc != SDYN_OK) return rc;
     TCU(c, cudaStreamSynchronize(st));
-    for (int f = 0; f < nframes; ++f)
-        if (t->hResult[f * 4 + 2] || t->hResult[(t->B + f) * 4 + 2])
-            return api_fail(c, SDYN_ERR_CAPACITY, "matcher candidate pool exhausted in the batched front end");
-    if (!direct) {
-        const int m = std::min(cap, kc);
-        for (int f = 0; f < nframes; ++f) {
-            if (assign) std::memcpy(assign + (size_t)f * cap, t->hAssign + (size_t)f * kc, (size_t)m * 4);
-            if (locked) std::memcpy(locked + (size_t)f * cap, t->hLocked + (size_t)f * kc, m);
-            if (dynMask) std::memcpy(dynMask + (size_t)f * cap, t->hMask + (size_t)f * kc, m);
-        }
+    return track_fetch_finish(c, nframes, assign, locked, dynMask, cap);
+}
+
+int sdyn_track_wait(sdyn_ctx* c)
+{
+    if (!c) return SDYN_ERR_ARG;
+    TrackState* t = static_cast<TrackState*>(c->track);
+    if (!t || !t->pending.active) return api_fail(c, SDYN_ERR_ARG, "sdyn_track_wait: no asynchronous step in flight");
+    TCU(c, cudaSetDevice(c->device));
+    TCU(c, cudaStreamSynchronize(c->stream));
+    const TrackState::Pending p = t->pending;
+    t->pending.active = false;
+    int rc = SDYN_OK;
+    if (p.nOut) {
+        rc = fetch_finish(c, p.nframes, p.kp, p.desc, (p.kp && p.desc) ? p.cap : 0, p.nOut);
+        if (rc != SDYN_OK && !(rc == SDYN_ERR_CAPACITY && !(p.kp && p.desc))) return rc;
     }
-    return SDYN_OK;
+    return track_fetch_finish(c, p.nframes, p.assign, p.locked, p.mask, p.cap);
 }
 
 }  // extern "C"

@@ -507,6 +507,8 @@ def _bind_track(L):
     L.sdyn_track_fetch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp]
     L.sdyn_track_batch.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(TrackInputsC),
                                    vp, vp, vp, vp, vp, vp, vp, C.c_int]
+    L.sdyn_track_batch_async.argtypes = L.sdyn_track_batch.argtypes
+    L.sdyn_track_wait.argtypes = [vp]
     L._track_bound = True
     return L
 
@@ -538,3 +540,18 @@ def track_batch_host(ex, images, tin, outs):
                                  kps.ctypes.data, desc.ctypes.data, n.ctypes.data, assign.ctypes.data, locked.ctypes.data,
                                  mask.ctypes.data, counts.ctypes.data, ex.cap))
     return outs
+
+
+def track_batch_host_async(ex, images, tin, outs):
+    """Asynchronous host-buffer step: enqueues H2D + kernels + D2H on the context's stream and returns;
+    `outs` are valid after track_wait(ex)."""
+    L = _bind_track(lib())
+    b, h, w = images.shape
+    kps, desc, n, assign, locked, mask, counts = outs
+    ex._check(L.sdyn_track_batch_async(ex._h, b, images.ctypes.data, images.strides[0], w, h, images.strides[1], C.byref(tin),
+                                       kps.ctypes.data, desc.ctypes.data, n.ctypes.data, assign.ctypes.data,
+                                       locked.ctypes.data, mask.ctypes.data, counts.ctypes.data, ex.cap))
+
+
+def track_wait(ex):
+    ex._check(_bind_track(lib()).sdyn_track_wait(ex._h))

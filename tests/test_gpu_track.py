@@ -52,4 +52,24 @@ def test_track_batch_matches_oracle(cfg, B):
         total_masked += int(em.sum())
         assert ec[0] > 100 and ec[1] > 50
     assert total_masked > 0
+
+    # host-buffer forms of the same step (sdyn_track_batch and its async + wait split) give identical results
+    hptrs = {k: (v.ctypes.data, int(np.prod(v.shape[1:])) * v.dtype.itemsize) for k, v in arrays.items()}
+    hin = pysdyn.track_inputs(hptrs, 0, (last_stride, map_stride, ref_stride), params)
+    for fn in ("sync", "async"):
+        outs = (np.zeros((B, gpu.cap), pysdyn.KP_DTYPE), np.zeros((B, gpu.cap, 32), np.uint8), np.zeros(B, np.int32),
+                np.zeros((B, gpu.cap), np.int32), np.zeros((B, gpu.cap), np.uint8), np.zeros((B, gpu.cap), np.uint8),
+                np.zeros((B, 4), np.int32))
+        imgs = np.ascontiguousarray(frames[1:])
+        if fn == "sync":
+            pysdyn.track_batch_host(gpu, imgs, hin, outs)
+        else:
+            pysdyn.track_batch_host_async(gpu, imgs, hin, outs)
+            pysdyn.track_wait(gpu)
+        assert np.array_equal(outs[2], counts) and np.array_equal(outs[6], cnt)
+        for f in range(B):
+            n = counts[f]
+            assert np.array_equal(outs[0][f, :n], kps[f, :n]) and np.array_equal(outs[1][f, :n], desc[f, :n])
+            assert np.array_equal(outs[3][f, :n], assign[f, :n]) and np.array_equal(outs[4][f, :n], locked[f, :n])
+            assert np.array_equal(outs[5][f, :n], mask[f, :n])
     gpu.close()
