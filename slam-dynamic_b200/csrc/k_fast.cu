@@ -26,29 +26,34 @@ constexpr int PWB = ((TW + 8 + 15 + 15) / 16) * 16;   /* staged bytes per row: 1
 constexpr int SW = TW + 2, SH = TH + 2;     /* scores: tile + NMS halo */
 constexpr int FT = 256;                     /* threads */
 
-/* V(p) = max over the 16 contiguous 9-arcs of max(min d, min -d) - 1, d_k = I(p) - I(ring_k). */
+/* V(p) = max over the 16 contiguous 9-arcs of max(min d, min -d) - 1, d_k = I(p) - I(ring_k).
+ * Both polarities ride in one register as biased unsigned 16-bit lanes: low = d + 256, high = -d + 256.
+ * With K = 1 - 65536 the pair is (c*K + 0x01000100) + r*0xFFFF — ONE integer multiply-add per ring pixel (FMA
+ * pipe) — and the sliding-window minima / final maximum are 40 three-input VIMNMX3.U16x2 ops (ALU pipe) for both
+ * polarities at once, instead of ~100 scalar min/max. */
 __device__ __forceinline__ int fast_score(const uint8_t* p)
 {
-    const int c = p[0];
-    int d[16];
-    d[0] = c - p[3 * PWB];      d[1] = c - p[3 * PWB + 1];   d[2] = c - p[2 * PWB + 2];   d[3] = c - p[PWB + 3];
-    d[4] = c - p[3];            d[5] = c - p[-PWB + 3];      d[6] = c - p[-2 * PWB + 2];  d[7] = c - p[-3 * PWB + 1];
-    d[8] = c - p[-3 * PWB];     d[9] = c - p[-3 * PWB - 1];  d[10] = c - p[-2 * PWB - 2]; d[11] = c - p[-PWB - 3];
-    d[12] = c - p[-3];          d[13] = c - p[PWB - 3];      d[14] = c - p[2 * PWB - 2];  d[15] = c - p[3 * PWB - 1];
-    /* sliding min / max over windows of 9 via windows of 3: w3[k] = op(d[k], d[k+1], d[k+2]) */
-    int lo3[16], hi3[16];
+    const uint32_t cK = (uint32_t)p[0] * 0xFFFF0001u + 0x01000100u;
+    uint32_t d[16];
+#define RING(k, off) d[k] = (uint32_t)p[off] * 0xFFFFu + cK
+    RING(0, 3 * PWB);      RING(1, 3 * PWB + 1);   RING(2, 2 * PWB + 2);   RING(3, PWB + 3);
+    RING(4, 3);            RING(5, -PWB + 3);      RING(6, -2 * PWB + 2);  RING(7, -3 * PWB + 1);
+    RING(8, -3 * PWB);     RING(9, -3 * PWB - 1);  RING(10, -2 * PWB - 2); RING(11, -PWB - 3);
+    RING(12, -3);          RING(13, PWB - 3);      RING(14, 2 * PWB - 2);  RING(15, 3 * PWB - 1);
+#undef RING
+    uint32_t lo3[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        lo3[k] = min(d[k], min(d[(k + 1) & 15], d[(k + 2) & 15]));
-        hi3[k] = max(d[k], max(d[(k + 1) & 15], d[(k + 2) & 15]));
-    }
-    int best = -256, worst = 256;
+    for (int k = 0; k < 16; ++k) lo3[k] = __vimin3_u16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    uint32_t m9[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        best = max(best, min(lo3[k], min(lo3[(k + 3) & 15], lo3[(k + 6) & 15])));
-        worst = min(worst, max(hi3[k], max(hi3[(k + 3) & 15], hi3[(k + 6) & 15])));
-    }
-    return max(best, -worst) - 1;
+    for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+    uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
+    uint32_t c = __vimax3_u16x2(m9[6], m9[7], m9[8]), e = __vimax3_u16x2(m9[9], m9[10], m9[11]);
+    uint32_t f = __vimax3_u16x2(m9[12], m9[13], m9[14]);
+    a = __vimax3_u16x2(a, b, c);
+    e = __vimax3_u16x2(e, f, m9[15]);
+    a = __vmaxu2(a, e);
+    return (int)max(a & 0xffffu, a >> 16) - 257;
 }
 
 __global__ void __launch_bounds__(FT)

@@ -93,6 +93,14 @@ k_grid_build(const MatchJob* __restrict__ jobs)
             J.sorted[j + 1] = v;
         }
     }
+    __syncthreads();
+    /* everything the window / level gates need, next to each other in enumeration order */
+    const int total = J.cellOff[kGridCells];
+    for (int p = tid; p < total; p += 256) {
+        const int idx = J.sorted[p];
+        const sdyn_keypoint kp = J.keysUn[idx];
+        J.gridEntry[p] = make_float4(kp.x, kp.y, __int_as_float(idx | (kp.octave << 24)), 0.f);
+    }
 }
 
 /* ---------------------------------------------------------------------------------------------- candidates */
@@ -199,34 +207,62 @@ k_match_candidates(const MatchJob* __restrict__ jobs)
     }
     if (!active) { if (lane == 0) J.qspan[q] = make_int2(0, 0); return; }
 
-    /* reserve the upper bound (all keypoints of the touched cells), then emit in enumeration order */
-    int bound = 0;
-    for (int ix = cx0 + lane; ix <= cx1; ix += 32)
-        bound += J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1] - J.cellOff[ix * SDYN_GRID_ROWS + cy0];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bound += __shfl_xor_sync(0xffffffffu, bound, o);
-    int off = 0;
-    if (lane == 0) off = atomicAdd(J.poolUsed, bound);
-    off = __shfl_sync(0xffffffffu, off, 0);
-    if (off + bound > J.poolCap) { if (lane == 0) { J.result[2] = 1; J.qspan[q] = make_int2(0, 0); } return; }
-
+    /* The candidates of grid column ix are ONE contiguous CSR span; lanes own columns, a warp scan turns the
+     * span lengths into offsets of the concatenated (= reference-order) candidate sequence, and the warp then
+     * walks that sequence 32 entries at a time: two dependent loads per candidate (entry, descriptor). */
     const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
-    int cnt = 0;
-    for (int ix = cx0; ix <= cx1; ++ix) {
-        const int b = J.cellOff[ix * SDYN_GRID_ROWS + cy0], e = J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1];
-        for (int p0 = b; p0 < e; p0 += 32) {
-            const int p = p0 + lane;
-            bool ok = p < e;
+    int cnt = 0, off = 0;
+    bool reserved = false;
+    for (int c0 = cx0; c0 <= cx1; c0 += 32) {
+        const int ix = c0 + lane;
+        int b = 0, len = 0;
+        if (ix <= cx1) {
+            b = J.cellOff[ix * SDYN_GRID_ROWS + cy0];
+            len = J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1] - b;
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - len;
+        if (!reserved) {
+            /* upper bound of the list length: all keypoints of the touched cells (all column groups) */
+            int bound = total;
+            for (int c1 = c0 + 32; c1 <= cx1; c1 += 32) {
+                const int jx = c1 + lane;
+                int l2 = 0;
+                if (jx <= cx1) l2 = J.cellOff[jx * SDYN_GRID_ROWS + cy1 + 1] - J.cellOff[jx * SDYN_GRID_ROWS + cy0];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+                bound += l2;
+            }
+            if (lane == 0) off = atomicAdd(J.poolUsed, bound);
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (off + bound > J.poolCap) { if (lane == 0) { J.result[2] = 1; J.qspan[q] = make_int2(0, 0); } return; }
+            reserved = true;
+        }
+        const int ncols = min(32, cx1 - c0 + 1);
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            bool ok = e < total;
+            /* which column does entry e belong to: last column whose exclusive offset is <= e */
+            int pos = 0;
+            {
+                int col = 0;
+                for (int j = 1; j < ncols; ++j) { const int oj = __shfl_sync(0xffffffffu, excl, j); if (oj <= e) col = j; }
+                const int bj = __shfl_sync(0xffffffffu, b, col), oj = __shfl_sync(0xffffffffu, excl, col);
+                pos = bj + (e - oj);
+            }
             int idx = 0, dist = 0, oct = 0;
             if (ok) {
-                idx = J.sorted[p];
-                const sdyn_keypoint kp = J.keysUn[idx];
-                oct = kp.octave;
+                const float4 ge = J.gridEntry[pos];
+                const int io = __float_as_int(ge.z);
+                idx = io & 0xffffff; oct = io >> 24;
                 if (checkLevels) {
                     if (oct < minLevel) ok = false;
                     if (maxLevel >= 0 && oct > maxLevel) ok = false;
                 }
-                if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) ok = false;
+                if (!(fabsf(__fsub_rn(ge.x, x)) < r && fabsf(__fsub_rn(ge.y, y)) < r)) ok = false;
                 if (ok && J.mode != MM_INIT && J.uRight) {
                     const float ur = J.uRight[idx];
                     if (ur > 0 && fabsf(__fsub_rn(gateX, ur)) > gate) ok = false;

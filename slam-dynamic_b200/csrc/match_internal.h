@@ -26,6 +26,7 @@ struct MatchJob {
     int32_t* cellOff;                /* kGridCells + 1 */
     int32_t* sorted;                 /* n */
     int32_t* cellOf;                 /* n, scratch */
+    float4* gridEntry;               /* n: (x, y, bits(index | octave << 24), 0) of sorted[p] — one load per candidate */
     /* queries */
     const void* queries;             /* sdyn_mappoint_query / sdyn_last_point / F1 keypoints / BowQuery */
     const sdyn_keypoint* qKeys;      /* FRAME: LastFrame.mvKeys (octave), INIT: F1.mvKeysUn, BOW: KF.mvKeysUn */

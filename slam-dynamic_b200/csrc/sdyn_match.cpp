@@ -67,6 +67,7 @@ void stage_frame(Arena& A, const sdyn_frame_view* f, MatchJob& J, bool needGrid)
         J.cellOff = A.take<int32_t>(kGridCells + 1);
         J.sorted = A.take<int32_t>(f->n);
         J.cellOf = A.take<int32_t>(f->n);
+        J.gridEntry = A.take<float4>(f->n);
     }
 }
 
@@ -147,7 +148,7 @@ int sdyn_match_projection_map(sdyn_ctx* c, const sdyn_frame_view* f, const sdyn_
     for (int i = 0; i < nmp; ++i)
         if (mps[i].track_in_view && !mps[i].bad && (mps[i].level < 0 || mps[i].level >= f->nlevels))
             return api_fail(c, SDYN_ERR_ARG, "map point with predicted level outside the pyramid");
-    const size_t fixed = (size_t)f->n * 80 + (size_t)nmp * sizeof(sdyn_mappoint_query) + (kGridCells + 1) * 4;
+    const size_t fixed = (size_t)f->n * 100 + (size_t)nmp * sizeof(sdyn_mappoint_query) + (kGridCells + 1) * 4;
     return run_job(c, fixed, nmp, 64 * nmp, (int)std::min<long long>((long long)nmp * f->n, 1 << 30),
         [&](Arena& A, MatchJob& J) {
             J.mode = MM_MAP;
@@ -199,7 +200,7 @@ int sdyn_match_projection_frame(sdyn_ctx* c, const sdyn_frame_view* cur, const s
     }
     const int forward = (tlc[2] > cur->b) && !mono, backward = (-tlc[2] > cur->b) && !mono;
     const int nq = last->n;
-    const size_t fixed = (size_t)cur->n * 80 + (size_t)nq * (sizeof(sdyn_last_point) + 2 * sizeof(sdyn_keypoint) + 16) +
+    const size_t fixed = (size_t)cur->n * 100 + (size_t)nq * (sizeof(sdyn_last_point) + 2 * sizeof(sdyn_keypoint) + 16) +
                          (kGridCells + 1) * 4;
     return run_job(c, fixed, nq, 64 * nq, (int)std::min<long long>((long long)nq * cur->n, 1 << 30),
         [&](Arena& A, MatchJob& J) {
@@ -244,7 +245,7 @@ int sdyn_match_init(sdyn_ctx* c, const sdyn_frame_view* f1, const sdyn_frame_vie
     for (int i = 0; i < f1->n; ++i) matches12[i] = -1;
     if (f1->n == 0 || f2->n == 0) return SDYN_OK;
     const int nq = f1->n;
-    const size_t fixed = (size_t)f2->n * 90 + (size_t)nq * 80 + (kGridCells + 1) * 4;
+    const size_t fixed = (size_t)f2->n * 110 + (size_t)nq * 80 + (kGridCells + 1) * 4;
     return run_job(c, fixed, nq, 512 * nq, (int)std::min<long long>((long long)nq * f2->n, 1 << 30),
         [&](Arena& A, MatchJob& J) {
             J.mode = MM_INIT;
@@ -312,7 +313,7 @@ int sdyn_match_bow(sdyn_ctx* c, const sdyn_frame_view* kf, const uint8_t* kfVali
     for (int i = 0; i < nIndex; ++i)
         if ((int)b->index[i] >= f->n) return api_fail(c, SDYN_ERR_ARG, "feature vector index out of range");
     if (pool > (1ll << 30)) return api_fail(c, SDYN_ERR_CAPACITY, "BoW search too large");
-    const size_t fixed = (size_t)f->n * 80 + (size_t)kf->n * 64 + (size_t)nq * 12 + (size_t)nIndex * 4;
+    const size_t fixed = (size_t)f->n * 100 + (size_t)kf->n * 64 + (size_t)nq * 12 + (size_t)nIndex * 4;
     return run_job(c, fixed, nq, (int)pool + 64, (int)pool + 64,
         [&](Arena& A, MatchJob& J) {
             J.mode = MM_BOW;

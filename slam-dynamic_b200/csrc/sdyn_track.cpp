@@ -12,7 +12,7 @@ struct TrackState {
     int B = 0, cap = 0, maxQ = 0, refStride = 0, poolPerJob = 0;
     uint8_t* block = nullptr; size_t bytes = 0;
     /* carved from block */
-    MatchJob* dJobs; int32_t* cellOff; int32_t* sorted; int32_t* cellOf; int32_t* assign; uint8_t* locked;
+    MatchJob* dJobs; int32_t* cellOff; int32_t* sorted; int32_t* cellOf; float4* gridEntry; int32_t* assign; uint8_t* locked;
     int2* qspan; int32_t* qAccepted; int32_t* qBin; uint32_t* pool; int32_t* poolUsed; int32_t* result;
     uint64_t* mask; unsigned long long* has; int32_t* boxList; int32_t* nnQ; int32_t* nnT; uint8_t* readmit;
     int32_t* staticExit; uint8_t* dynMask; int32_t* counts;
@@ -51,6 +51,7 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     const size_t J = 2 * (size_t)B;
     const size_t oJobs = take(J * sizeof(MatchJob));
     const size_t oCellOff = take((size_t)B * (kGridCells + 1) * 4), oSorted = take((size_t)B * cap * 4), oCellOf = take((size_t)B * cap * 4);
+    const size_t oGridEntry = take((size_t)B * cap * sizeof(float4));
     const size_t oQspan = take(J * maxQ * sizeof(int2)), oQAcc = take(J * maxQ * 4), oQBin = take(J * maxQ * 4);
     const size_t oPool = take(J * (size_t)t->poolPerJob * 4);
     const size_t oMask = take((size_t)B * cap * 8), oHas = take((size_t)B * 8);
@@ -80,6 +81,7 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     t->dJobs = reinterpret_cast<MatchJob*>(b + oJobs);
     t->cellOff = reinterpret_cast<int32_t*>(b + oCellOff); t->sorted = reinterpret_cast<int32_t*>(b + oSorted);
     t->cellOf = reinterpret_cast<int32_t*>(b + oCellOf);
+    t->gridEntry = reinterpret_cast<float4*>(b + oGridEntry);
     t->qspan = reinterpret_cast<int2*>(b + oQspan); t->qAccepted = reinterpret_cast<int32_t*>(b + oQAcc);
     t->qBin = reinterpret_cast<int32_t*>(b + oQBin); t->pool = reinterpret_cast<uint32_t*>(b + oPool);
     t->mask = reinterpret_cast<uint64_t*>(b + oMask); t->has = reinterpret_cast<unsigned long long*>(b + oHas);
@@ -193,6 +195,7 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         for (int l = 0; l < SDYN_MAX_LEVELS; ++l) J.scale[l] = l < c->scales.nlevels ? c->scales.scale[l] : 1.f;
         J.cellOff = t->cellOff + (size_t)f * (kGridCells + 1); J.sorted = t->sorted + (size_t)f * cap;
         J.cellOf = t->cellOf + (size_t)f * cap;
+        J.gridEntry = t->gridEntry + (size_t)f * cap;
         J.assign = t->assign + (size_t)f * cap; J.locked = t->locked + (size_t)f * cap;
         J.poolCap = t->poolPerJob;
         std::memcpy(J.Tcw, in->tcw_cur, sizeof(J.Tcw));
