@@ -18,10 +18,6 @@ __device__ const signed char kBriefPairs[256][4] = {
 #include "../../include/sdyn_brief_pattern.inc"
 };
 
-/* umax[] of ORBextractor.cc:454-469 evaluated for HALF_PATCH_SIZE = 15 (geometry.cpp recomputes it and
- * tests/test_abi.py checks the two agree). */
-__device__ const int kDiscHalfWidth[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 {
     const float p1 = __uint_as_float(0x4265226fu), p3 = __uint_as_float(0xc19556eeu);
@@ -79,14 +75,19 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int au = abs(u);
+        /* half-widths as compile-time constants: the unrolled loop folds them into immediates, and the 31 row
+         * loads are independent, so they are all in flight together */
+        /* umax[] of ORBextractor.cc:454-469 for HALF_PATCH_SIZE = 15 (geometry.cpp recomputes it; tests/test_abi.py
+         * checks the two agree) */
+        constexpr int HW[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+        int vals[31];
 #pragma unroll
-        for (int v = -15; v <= 15; ++v) {
-            if (au <= kDiscHalfWidth[v < 0 ? -v : v]) {
-                const int val = img[(long long)v * L.pitch + u];
-                m10 += u * val;
-                m01 += v * val;
-            }
-        }
+        for (int v = -15; v <= 15; ++v)
+            vals[v + 15] = au <= HW[v < 0 ? -v : v] ? (int)img[(long long)v * L.pitch + u] : 0;
+        int rowsum = 0;
+#pragma unroll
+        for (int v = -15; v <= 15; ++v) { rowsum += vals[v + 15]; m01 += v * vals[v + 15]; }
+        m10 = u * rowsum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

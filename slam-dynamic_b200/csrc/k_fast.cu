@@ -97,12 +97,13 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
             sc[i] = 0;
             if (wx >= 3 && wx < L.fw - 3 && wy >= 3 && wy < L.fh - 3) {
                 const uint8_t* p = &px[(yy + 3) * PWB + shift + xx + 3];
-                const int c = p[0], hi = c + lowTh, lo = c - lowTh;
-                const int n = p[-3 * PWB], s = p[3 * PWB], e = p[3], w = p[-3];
-                /* a contiguous 9-arc contains one pixel of every antipodal pair */
-                const bool bright = ((n > hi) | (s > hi)) & ((e > hi) | (w > hi));
-                const bool dark = ((n < lo) | (s < lo)) & ((e < lo) | (w < lo));
-                cand9 = bright | dark;
+                /* a contiguous 9-arc contains one pixel of every antipodal pair: with the same biased dual-polarity
+                 * packing as fast_score, min(max(N,S), max(E,W)) > th in either 16-bit lane */
+                const uint32_t cK = (uint32_t)p[0] * 0xFFFF0001u + 0x01000100u;
+                const uint32_t pn = (uint32_t)p[-3 * PWB] * 0xFFFFu + cK, ps = (uint32_t)p[3 * PWB] * 0xFFFFu + cK;
+                const uint32_t pe = (uint32_t)p[3] * 0xFFFFu + cK, pw = (uint32_t)p[-3] * 0xFFFFu + cK;
+                const uint32_t m = __vminu2(__vmaxu2(pn, ps), __vmaxu2(pe, pw));
+                cand9 = max(m & 0xffffu, m >> 16) > (uint32_t)(lowTh + 256);
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, cand9);

@@ -228,12 +228,17 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         TCU(c, cudaMemsetAsync(t->block + t->zeroFrom, 0, t->zeroBytes, st));
         TCU(c, cudaMemcpyAsync(t->dJobs, t->hJobs.data(), t->hJobs.size() * sizeof(MatchJob), cudaMemcpyHostToDevice, st));
         TCU(c, launch_grid_build(t->dJobs, nframes, st));
+        /* candidate generation only applies static gates, so both searches of every frame go out in ONE launch
+         * when their jobs are contiguous (full batch); the claims are then resolved frame search first */
+        const bool both = in->last_stride > 0 && in->map_stride > 0 && nframes == B;
+        if (both)
+            TCU(c, launch_match_candidates(t->dJobs, 2 * B, std::max(in->last_stride, in->map_stride), st));
         if (in->last_stride > 0) {
-            TCU(c, launch_match_candidates(t->dJobs, nframes, in->last_stride, st));
+            if (!both) TCU(c, launch_match_candidates(t->dJobs, nframes, in->last_stride, st));
             TCU(c, launch_match_resolve(t->dJobs, nframes, MM_FRAME, cap, in->last_stride, st));
         }
         if (in->map_stride > 0) {
-            TCU(c, launch_match_candidates(t->dJobs + B, nframes, in->map_stride, st));
+            if (!both) TCU(c, launch_match_candidates(t->dJobs + B, nframes, in->map_stride, st));
             TCU(c, launch_match_resolve(t->dJobs + B, nframes, MM_MAP, cap, in->map_stride, st));
         }
         c->launches += 3 + (in->last_stride > 0 ? 2 : 0) + (in->map_stride > 0 ? 2 : 0);

@@ -88,3 +88,38 @@ def test_edge_cases():
     check_frame(k, d, ok, od)
     with pytest.raises(pysdyn.SdynError):                    # level 7 too small for the 30-px grid: error, not UB
         gpu(np.zeros((100, 100), np.uint8))
+
+
+def test_4k_stress_frame():
+    """3840x2160 / 8000 features (BASELINE.json config 5): octree with ~1700-leaf levels, 26k FAST cells."""
+    gpu, cpu = make("4k")
+    img = common.frame("4k", 0)
+    k, d = gpu(img)
+    ok, od = cpu(img)
+    assert len(ok) > 7900
+    for l in (0, 3, 7):
+        assert np.array_equal(gpu.level(0, l), cpu.level(l))
+    check_frame(k, d, ok, od, "4k")
+
+
+def test_stereo_pair_two_contexts_concurrently():
+    """Left and right extractors run on two threads in the reference (src/Frame.cc:151-154): two contexts, two
+    streams, concurrent calls."""
+    import threading
+    w, h, _, nf, ini, mn = common.CONFIGS["kitti"]
+    left, right = common.frame("kitti", 3), common.frame("kitti", 3, ox=11)      # disparity-like shift
+    exs = [pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=w, max_height=h) for _ in range(2)]
+    out = [None, None]
+
+    def run(i, img):
+        for _ in range(3):
+            out[i] = exs[i](img)
+
+    th = [threading.Thread(target=run, args=(i, im)) for i, im in enumerate((left, right))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    cpu = orc.Extractor(nf, 1.2, 8, ini, mn)
+    for i, im in enumerate((left, right)):
+        ok, od = cpu(im)
+        check_frame(out[i][0], out[i][1], ok, od, ("stereo", i))
+    [e.close() for e in exs]
