@@ -56,14 +56,21 @@ __device__ __forceinline__ int fast_score(const uint8_t* p)
     return (int)max(a & 0xffffu, a >> 16) - 257;
 }
 
+constexpr int SWP = 136;                    /* score row pitch: position xx lives at byte xx+3, so tile column 0 is word-aligned */
+constexpr int ROWR = SH / (FT / 32), COLR = SW / 32;   /* score rows per warp, 32-column chunks per row */
+static_assert(SW % 32 == 0 && SH % (FT / 32) == 0, "score positions tile the CTA exactly");
+static_assert(ROWR * COLR <= 32, "per-thread candidate bits must fit one word");
+static_assert(SW + 3 + 1 <= SWP && SWP % 4 == 0, "score row pitch");
+
 __global__ void __launch_bounds__(FT)
 k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const uint8_t* __restrict__ pyr,
        int iniTh, int lowTh, uint8_t* __restrict__ cellFlag, uint32_t* __restrict__ cand,
        int32_t* __restrict__ candCount)
 {
     __shared__ __align__(16) uint8_t px[PH * PWB];
-    __shared__ uint8_t sc[SH * SW];
+    __shared__ __align__(16) uint8_t sc[SH * SWP];
     __shared__ uint16_t list[SH * SW];
+    __shared__ uint16_t colInfo[TW], rowInfo[TH];   /* cell index | hasLow << 14 | hasHigh << 15 */
     __shared__ int nList;
 
     const TileRef t = tiles[blockIdx.x];
@@ -71,7 +78,7 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
     const LevelGeom& L = g.L[t.level];
     const int x0 = t.tx * TW, y0 = t.ty * TH;                 /* window-relative origin of the tile */
     const uint8_t* img = pyr + (size_t)f * g.frameBytes + L.off;   /* interior pixel (0,0): 32-byte aligned */
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
 
     /* stage rows [gy0, gy0+PH) x bytes [ax0, ax0+PWB): ax0 is the 16-byte aligned column at or before the
      * first needed pixel (window x0-4 = interior column 12+x0).  Rows are clamped to the bordered extent;
@@ -85,32 +92,61 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + (long long)gy * L.pitch + ax0) + q);
         reinterpret_cast<uint4*>(px + yy * PWB)[q] = v;
     }
+    for (int i = tid; i < SH * SWP / 4; i += FT) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+    /* which neighbours of a tile column / row lie in the same cell interior (interiors start at 3 + j*wCell):
+     * one runtime division per tile column / row instead of two per pixel */
+    if (tid < TW) {
+        const int w3 = x0 + tid - 3;
+        const int cx = max(w3, 0) / L.wCell, lx = w3 - cx * L.wCell;
+        colInfo[tid] = (uint16_t)(cx | ((lx > 0) << 14) | ((lx < L.wCell - 1) << 15));
+    } else if (tid < TW + TH) {
+        const int r = tid - TW, h3 = y0 + r - 3;
+        const int cy = max(h3, 0) / L.hCell, ly = h3 - cy * L.hCell;
+        rowInfo[r] = (uint16_t)(cy | ((ly > 0) << 14) | ((ly < L.hCell - 1) << 15));
+    }
     __syncthreads();
 
-    /* (A) compass test at the low threshold on [x0-1, x0+TW+1) x [y0-1, y0+TH+1) */
-    for (int i0 = 0; i0 < SH * SW; i0 += FT) {
-        const int i = i0 + tid;
-        bool cand9 = false;
-        if (i < SH * SW) {
-            const int yy = i / SW, xx = i - yy * SW;
-            const int wx = x0 - 1 + xx, wy = y0 - 1 + yy;
-            sc[i] = 0;
-            if (wx >= 3 && wx < L.fw - 3 && wy >= 3 && wy < L.fh - 3) {
-                const uint8_t* p = &px[(yy + 3) * PWB + shift + xx + 3];
+    /* (A) compass test at the low threshold on [x0-1, x0+TW+1) x [y0-1, y0+TH+1).  A thread walks 16
+     * strided positions (conflict-free byte reads, no index arithmetic) and keeps its survivors as bits; ONE warp scan + one shared atomic per warp then reserves list
+     * space for all of them (no per-position vote / atomic traffic). */
+    const int xlo = max(0, 3 - (x0 - 1)), xhi = min(SW, L.fw - 3 - (x0 - 1));    /* valid score columns */
+    const int ylo = max(0, 3 - (y0 - 1)), yhi = min(SH, L.fh - 3 - (y0 - 1));
+    const uint32_t thr = (uint32_t)(lowTh + 256);
+    uint32_t bits = 0;
+    const int warp = tid >> 5;
+#pragma unroll
+    for (int r = 0; r < ROWR; ++r) {
+        const int yy = warp + (FT / 32) * r;
+        const bool rowOk = yy >= ylo && yy < yhi;
+#pragma unroll
+        for (int j = 0; j < COLR; ++j) {
+            const int xx = lane + 32 * j;
+            if (rowOk && xx >= xlo && xx < xhi) {
                 /* a contiguous 9-arc contains one pixel of every antipodal pair: with the same biased dual-polarity
                  * packing as fast_score, min(max(N,S), max(E,W)) > th in either 16-bit lane */
+                const uint8_t* p = &px[(yy + 3) * PWB + shift + xx + 3];
                 const uint32_t cK = (uint32_t)p[0] * 0xFFFF0001u + 0x01000100u;
                 const uint32_t pn = (uint32_t)p[-3 * PWB] * 0xFFFFu + cK, ps = (uint32_t)p[3 * PWB] * 0xFFFFu + cK;
                 const uint32_t pe = (uint32_t)p[3] * 0xFFFFu + cK, pw = (uint32_t)p[-3] * 0xFFFFu + cK;
                 const uint32_t m = __vminu2(__vmaxu2(pn, ps), __vmaxu2(pe, pw));
-                cand9 = max(m & 0xffffu, m >> 16) > (uint32_t)(lowTh + 256);
+                if (max(m & 0xffffu, m >> 16) > thr) bits |= 1u << (r * COLR + j);
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, cand9);
+    }
+    {
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         int base = 0;
-        if ((tid & 31) == 0 && m) base = atomicAdd(&nList, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (cand9) list[base + __popc(m & ((1u << (tid & 31)) - 1))] = (uint16_t)i;
+        if (lane == 31 && incl) base = atomicAdd(&nList, incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int yy = warp + (FT / 32) * (b / COLR), xx = lane + 32 * (b % COLR);
+            list[base++] = (uint16_t)(yy * SW + xx);
+        }
     }
     __syncthreads();
 
@@ -120,33 +156,39 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
         const int i = list[e];
         const int yy = i / SW, xx = i - yy * SW;
         const int v = fast_score(&px[(yy + 3) * PWB + shift + xx + 3]);
-        if (v >= lowTh) sc[i] = (uint8_t)v;
+        if (v >= lowTh) sc[yy * SWP + xx + 3] = (uint8_t)v;
     }
     __syncthreads();
 
-    /* (C) cell-confined 3x3 strict maximum */
+    /* (C) cell-confined 3x3 strict maximum; four tile columns per 32-bit read, all-zero words are skipped */
     uint32_t* out = cand + (size_t)f * g.candPerFrame + L.candOff;
     int32_t* cnt = candCount + f * SDYN_MAX_LEVELS + t.level;
     uint8_t* flags = cellFlag + (size_t)f * g.cellsPerFrame + L.cellOff;
-    for (int i = tid; i < TW * TH; i += FT) {
-        const int yy = i / TW, xx = i - yy * TW;
-        const int s = sc[(yy + 1) * SW + xx + 1];
-        if (s == 0) continue;
-        const int wx = x0 + xx, wy = y0 + yy;                 /* s > 0 implies 3 <= wx < fw-3, 3 <= wy < fh-3 */
-        /* neighbours count only inside the same cell interior: interiors start at 3 + j*wCell */
-        const int cx = (wx - 3) / L.wCell, cy = (wy - 3) / L.hCell;
-        const int lx = wx - 3 - cx * L.wCell, ly = wy - 3 - cy * L.hCell;
-        const bool hasL = lx > 0, hasR = lx < L.wCell - 1, hasU = ly > 0, hasD = ly < L.hCell - 1;
-        const uint8_t* c = &sc[(yy + 1) * SW + xx + 1];
-        int m = 0;
-        if (hasU) { m = max(m, (int)c[-SW]); if (hasL) m = max(m, (int)c[-SW - 1]); if (hasR) m = max(m, (int)c[-SW + 1]); }
-        if (hasD) { m = max(m, (int)c[SW]);  if (hasL) m = max(m, (int)c[SW - 1]);  if (hasR) m = max(m, (int)c[SW + 1]); }
-        if (hasL) m = max(m, (int)c[-1]);
-        if (hasR) m = max(m, (int)c[1]);
-        if (s > m) {
-            if (s >= iniTh) flags[cy * L.nCols + cx] = 1;
-            const int slot = atomicAdd(cnt, 1);
-            if (slot < L.candCap) out[slot] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
+    for (int i = tid; i < TH * 32; i += FT) {
+        const int yy = i >> 5, xq = i & 31;
+        uint32_t word = *reinterpret_cast<const uint32_t*>(&sc[(yy + 1) * SWP + 4 + 4 * xq]);
+        if (4 * xq + 3 >= TW) word &= (4 * xq >= TW) ? 0u : (0xffffffffu >> (8 * (4 * xq + 4 - TW)));   /* neighbour tile's columns */
+        if (word == 0) continue;
+        const uint32_t ri = rowInfo[yy];
+        const bool hasU = ri & 0x4000, hasD = ri & 0x8000;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int s = (word >> (8 * b)) & 0xff;
+            if (s == 0) continue;
+            const int xx = 4 * xq + b;
+            const uint32_t ci = colInfo[xx];
+            const bool hasL = ci & 0x4000, hasR = ci & 0x8000;
+            const uint8_t* c = &sc[(yy + 1) * SWP + 4 + xx];
+            int m = 0;
+            if (hasU) { m = max(m, (int)c[-SWP]); if (hasL) m = max(m, (int)c[-SWP - 1]); if (hasR) m = max(m, (int)c[-SWP + 1]); }
+            if (hasD) { m = max(m, (int)c[SWP]);  if (hasL) m = max(m, (int)c[SWP - 1]);  if (hasR) m = max(m, (int)c[SWP + 1]); }
+            if (hasL) m = max(m, (int)c[-1]);
+            if (hasR) m = max(m, (int)c[1]);
+            if (s > m) {
+                if (s >= iniTh) flags[(ri & 0x3fff) * L.nCols + (ci & 0x3fff)] = 1;
+                const int slot = atomicAdd(cnt, 1);
+                if (slot < L.candCap) out[slot] = (uint32_t)(x0 + xx) | ((uint32_t)(y0 + yy) << 12) | ((uint32_t)s << 24);
+            }
         }
     }
 }

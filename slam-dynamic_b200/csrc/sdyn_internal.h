@@ -150,7 +150,7 @@ cudaError_t launch_orient_describe(const Geom& g, const uint8_t* dPyr, const uin
                                    int nframes, cudaStream_t st);
 size_t octree_smem_bytes(int nodeCap);
 
-constexpr int kFastTileW = 128, kFastTileH = 32;
+constexpr int kFastTileW = 126, kFastTileH = 30;   /* +2 halo = 128 x 32 score positions: 4 x 4 per thread, no idle lanes */
 constexpr int kBlurTileW = 128, kBlurTileH = 32;
 
 }  // namespace sdyn
