@@ -69,9 +69,10 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
 {
     __shared__ __align__(16) uint8_t px[PH * PWB];
     __shared__ __align__(16) uint8_t sc[SH * SWP];
-    __shared__ uint16_t list[SH * SW];
+    __shared__ uint16_t list[SH * SW];          /* survivors of the compass test */
+    __shared__ uint16_t corners[TH * TW];       /* tile positions with V >= lowTh (input of the suppression) */
     __shared__ uint16_t colInfo[TW], rowInfo[TH];   /* cell index | hasLow << 14 | hasHigh << 15 */
-    __shared__ int nList;
+    __shared__ int nList, nCorners;
 
     const TileRef t = tiles[blockIdx.x];
     const int f = blockIdx.y;
@@ -85,7 +86,7 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
      * columns past the row end read pad / next-row bytes that only feed masked-out positions. */
     const int gx0 = kFastBorder + x0 - 4, gy0 = kFastBorder + y0 - 4;
     const int ax0 = gx0 & ~15, shift = gx0 - ax0;
-    if (tid == 0) nList = 0;
+    if (tid == 0) { nList = 0; nCorners = 0; }
     for (int i = tid; i < PH * (PWB / 16); i += FT) {
         const int yy = i / (PWB / 16), q = i - yy * (PWB / 16);
         const int gy = min(gy0 + yy, L.h + kEdge - 1);
@@ -121,16 +122,16 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
 #pragma unroll
         for (int j = 0; j < COLR; ++j) {
             const int xx = lane + 32 * j;
-            if (rowOk && xx >= xlo && xx < xhi) {
-                /* a contiguous 9-arc contains one pixel of every antipodal pair: with the same biased dual-polarity
-                 * packing as fast_score, min(max(N,S), max(E,W)) > th in either 16-bit lane */
-                const uint8_t* p = &px[(yy + 3) * PWB + shift + xx + 3];
-                const uint32_t cK = (uint32_t)p[0] * 0xFFFF0001u + 0x01000100u;
-                const uint32_t pn = (uint32_t)p[-3 * PWB] * 0xFFFFu + cK, ps = (uint32_t)p[3 * PWB] * 0xFFFFu + cK;
-                const uint32_t pe = (uint32_t)p[3] * 0xFFFFu + cK, pw = (uint32_t)p[-3] * 0xFFFFu + cK;
-                const uint32_t m = __vminu2(__vmaxu2(pn, ps), __vmaxu2(pe, pw));
-                if (max(m & 0xffffu, m >> 16) > thr) bits |= 1u << (r * COLR + j);
-            }
+            /* a contiguous 9-arc contains one pixel of every antipodal pair: with the same biased dual-polarity
+             * packing as fast_score, min(max(N,S), max(E,W)) > th in either 16-bit lane.  Every position of the
+             * score window has its ring staged, so out-of-range ones are computed and masked (no branch). */
+            const uint8_t* p = &px[(yy + 3) * PWB + shift + xx + 3];
+            const uint32_t cK = (uint32_t)p[0] * 0xFFFF0001u + 0x01000100u;
+            const uint32_t pn = (uint32_t)p[-3 * PWB] * 0xFFFFu + cK, ps = (uint32_t)p[3 * PWB] * 0xFFFFu + cK;
+            const uint32_t pe = (uint32_t)p[3] * 0xFFFFu + cK, pw = (uint32_t)p[-3] * 0xFFFFu + cK;
+            const uint32_t m = __vminu2(__vmaxu2(pn, ps), __vmaxu2(pe, pw));
+            const bool hit = (max(m & 0xffffu, m >> 16) > thr) & rowOk & (xx >= xlo) & (xx < xhi);
+            bits |= (uint32_t)hit << (r * COLR + j);
         }
     }
     {
@@ -150,45 +151,54 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
     }
     __syncthreads();
 
-    /* (B) full score of the survivors, dense over the list */
+    /* (B) full score of the survivors, dense over the list; corners inside the tile are appended to a second
+     * list so that the suppression below is dense as well */
     const int nl = nList;
-    for (int e = tid; e < nl; e += FT) {
-        const int i = list[e];
-        const int yy = i / SW, xx = i - yy * SW;
-        const int v = fast_score(&px[(yy + 3) * PWB + shift + xx + 3]);
-        if (v >= lowTh) sc[yy * SWP + xx + 3] = (uint8_t)v;
+    for (int e0 = 0; e0 < nl; e0 += FT) {
+        const int e = e0 + tid;
+        bool corner = false;
+        int pos = 0;
+        if (e < nl) {
+            const int i = list[e];
+            const int yy = i / SW, xx = i - yy * SW;
+            const int v = fast_score(&px[(yy + 3) * PWB + shift + xx + 3]);
+            if (v >= lowTh) {
+                sc[yy * SWP + xx + 3] = (uint8_t)v;
+                corner = yy >= 1 && yy <= TH && xx >= 1 && xx <= TW;
+                pos = (yy - 1) * TW + (xx - 1);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, corner);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&nCorners, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (corner) corners[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)pos;
+        }
     }
     __syncthreads();
 
-    /* (C) cell-confined 3x3 strict maximum; four tile columns per 32-bit read, all-zero words are skipped */
+    /* (C) cell-confined 3x3 strict maximum over the corners */
     uint32_t* out = cand + (size_t)f * g.candPerFrame + L.candOff;
     int32_t* cnt = candCount + f * SDYN_MAX_LEVELS + t.level;
     uint8_t* flags = cellFlag + (size_t)f * g.cellsPerFrame + L.cellOff;
-    for (int i = tid; i < TH * 32; i += FT) {
-        const int yy = i >> 5, xq = i & 31;
-        uint32_t word = *reinterpret_cast<const uint32_t*>(&sc[(yy + 1) * SWP + 4 + 4 * xq]);
-        if (4 * xq + 3 >= TW) word &= (4 * xq >= TW) ? 0u : (0xffffffffu >> (8 * (4 * xq + 4 - TW)));   /* neighbour tile's columns */
-        if (word == 0) continue;
-        const uint32_t ri = rowInfo[yy];
-        const bool hasU = ri & 0x4000, hasD = ri & 0x8000;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int s = (word >> (8 * b)) & 0xff;
-            if (s == 0) continue;
-            const int xx = 4 * xq + b;
-            const uint32_t ci = colInfo[xx];
-            const bool hasL = ci & 0x4000, hasR = ci & 0x8000;
-            const uint8_t* c = &sc[(yy + 1) * SWP + 4 + xx];
-            int m = 0;
-            if (hasU) { m = max(m, (int)c[-SWP]); if (hasL) m = max(m, (int)c[-SWP - 1]); if (hasR) m = max(m, (int)c[-SWP + 1]); }
-            if (hasD) { m = max(m, (int)c[SWP]);  if (hasL) m = max(m, (int)c[SWP - 1]);  if (hasR) m = max(m, (int)c[SWP + 1]); }
-            if (hasL) m = max(m, (int)c[-1]);
-            if (hasR) m = max(m, (int)c[1]);
-            if (s > m) {
-                if (s >= iniTh) flags[(ri & 0x3fff) * L.nCols + (ci & 0x3fff)] = 1;
-                const int slot = atomicAdd(cnt, 1);
-                if (slot < L.candCap) out[slot] = (uint32_t)(x0 + xx) | ((uint32_t)(y0 + yy) << 12) | ((uint32_t)s << 24);
-            }
+    const int nc = nCorners;
+    for (int e = tid; e < nc; e += FT) {
+        const int i = corners[e];
+        const int yy = i / TW, xx = i - yy * TW;
+        const uint32_t ri = rowInfo[yy], ci = colInfo[xx];
+        const bool hasU = ri & 0x4000, hasD = ri & 0x8000, hasL = ci & 0x4000, hasR = ci & 0x8000;
+        const uint8_t* c = &sc[(yy + 1) * SWP + 4 + xx];
+        const int s = c[0];
+        int m = 0;
+        if (hasU) { m = max(m, (int)c[-SWP]); if (hasL) m = max(m, (int)c[-SWP - 1]); if (hasR) m = max(m, (int)c[-SWP + 1]); }
+        if (hasD) { m = max(m, (int)c[SWP]);  if (hasL) m = max(m, (int)c[SWP - 1]);  if (hasR) m = max(m, (int)c[SWP + 1]); }
+        if (hasL) m = max(m, (int)c[-1]);
+        if (hasR) m = max(m, (int)c[1]);
+        if (s > m) {
+            if (s >= iniTh) flags[(ri & 0x3fff) * L.nCols + (ci & 0x3fff)] = 1;
+            const int slot = atomicAdd(cnt, 1);
+            if (slot < L.candCap) out[slot] = (uint32_t)(x0 + xx) | ((uint32_t)(y0 + yy) << 12) | ((uint32_t)s << 24);
         }
     }
 }
