@@ -56,7 +56,8 @@ def stage_alg_bytes(W, H, nkp, evals, queries):
     px = sum(w * h for w, h in lv)
     bordered = sum((w + 38) * (h + 38) for w, h in lv)
     return {
-        "pyramid": W * H + sum(w * h for w, h in lv[:-1]) + bordered,   # read previous level, write bordered level
+        "level0": W * H + (lv[0][0] + 38) * (lv[0][1] + 38),            # read input, write bordered level 0
+        "pyramid": sum(w * h for w, h in lv[:-1]) + bordered - (lv[0][0] + 38) * (lv[0][1] + 38),   # resize chain
         "fast": px,                                                      # every level pixel read once
         "blur": 2 * px,
         "describe": nkp * (749 + 512 + 60),
@@ -304,8 +305,10 @@ def main():
     hptrs = {k: (p.array.ctypes.data, p.array.shape[1]) for k, p in pin.items()}
     pin_in = pysdyn.PinnedArray((POOL, H, W), np.uint8)
     pin_in.array[:] = cur_frames
-    # two contexts used alternately: step s+1's PCIe copies overlap step s's kernels (each context has its own stream)
-    ctxs = [ex, pysdyn.Extractor(nf, SCALE, NLEVELS, ini, mn, max_width=W, max_height=H, max_batch=B, device=local)]
+    # NCTX contexts used round-robin: a step's PCIe copies overlap the other contexts' kernels (one stream each)
+    NCTX = 3
+    ctxs = [ex] + [pysdyn.Extractor(nf, SCALE, NLEVELS, ini, mn, max_width=W, max_height=H, max_batch=B, device=local)
+                   for _ in range(NCTX - 1)]
     out_sets = []
     for _ in ctxs:
         o = tuple(pysdyn.PinnedArray(shape, dt) for shape, dt in
@@ -316,17 +319,17 @@ def main():
     def step_host_async(s):
         base = (s % nsets) * B
         tin = pysdyn.track_inputs(hptrs, base, strides, params)
-        pysdyn.track_batch_host_async(ctxs[s % 2], pin_in.array[base:base + B], tin, out_sets[s % 2][1])
+        pysdyn.track_batch_host_async(ctxs[s % NCTX], pin_in.array[base:base + B], tin, out_sets[s % NCTX][1])
 
     def run_host(first, count):
         for s in range(first, first + count):
-            if s >= first + 2:
-                pysdyn.track_wait(ctxs[s % 2])              # the step issued two iterations ago on this context
+            if s >= first + NCTX:
+                pysdyn.track_wait(ctxs[s % NCTX])           # the step issued NCTX iterations ago on this context
             step_host_async(s)
-        for s in range(max(first, first + count - 2), first + count):
-            pysdyn.track_wait(ctxs[s % 2])
+        for s in range(max(first, first + count - NCTX), first + count):
+            pysdyn.track_wait(ctxs[s % NCTX])
 
-    run_host(0, 4)
+    run_host(0, 2 * NCTX)
     barrier()
     t0 = time.perf_counter()
     run_host(Wm, K)
@@ -335,7 +338,7 @@ def main():
     # the e2e outputs of the last step must equal the device-resident run's results for the same frames
     last = Wm + K - 1
     if (last % nsets) == ((Wm + K - 1) % nsets):
-        eo = out_sets[last % 2][1]
+        eo = out_sets[last % NCTX][1]
         assert np.array_equal(eo[2], counts) and np.array_equal(eo[6], cnt), "e2e and device-resident results differ"
     h2d = B * W * H + sum(p.array.shape[1] for p in pin.values()) * B
     d2h = B * (cap * (28 + 32) + 4 + cap * 6 + 16)

@@ -312,7 +312,8 @@ int sdyn_track_fetch(sdyn_ctx* ctx, int nframes, int32_t* assign, uint8_t* locke
  * While enabled, every enqueue brackets each stage with events; sdyn_profile_read synchronises and
  * returns the accumulated milliseconds and launch counts since the last read. */
 enum { SDYN_STAGE_PYRAMID = 0, SDYN_STAGE_FAST, SDYN_STAGE_OCTREE, SDYN_STAGE_BLUR, SDYN_STAGE_DESCRIBE,
-       SDYN_STAGE_MATCH, SDYN_STAGE_DYNAMIC, SDYN_STAGE_COUNT };
+       SDYN_STAGE_MATCH, SDYN_STAGE_DYNAMIC, SDYN_STAGE_LEVEL0 /* clears + level 0; PYRAMID = the resize chain */,
+       SDYN_STAGE_COUNT };
 typedef struct {
     double ms[SDYN_STAGE_COUNT];
     long long calls[SDYN_STAGE_COUNT];

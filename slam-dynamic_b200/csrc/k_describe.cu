@@ -14,7 +14,8 @@
 
 namespace sdyn {
 
-__device__ const signed char kBriefPairs[256][4] = {
+/* the 256 point pairs as floats (x0, y0, x1, y1): the rotation is float arithmetic, so no per-sample I2F */
+__device__ const float4 kBriefPairs[256] = {
 #include "../../include/sdyn_brief_pattern.inc"
 };
 
@@ -47,28 +48,29 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
                   sdyn_keypoint* __restrict__ kpOut, uint8_t* __restrict__ descOut, int32_t* __restrict__ countOut,
                   int maxKp)
 {
-    const int f = blockIdx.y;
+    const int f = blockIdx.z, level = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * DW + (threadIdx.x >> 5);     /* index into the per-frame level-kp scratch */
+    const int k = blockIdx.x * DW + (threadIdx.x >> 5);        /* list position inside the level */
     const int32_t* lc = levelCount + f * SDYN_MAX_LEVELS;
-
-    int level = -1, before = 0, total = 0;
-    for (int l = 0; l < g.nlevels; ++l) {
-        const int c = lc[l];
-        if (slot >= g.L[l].kpOff && slot < g.L[l].kpOff + g.L[l].nodeCap) { level = l; before = total; }
-        total += c;
+    /* output slot = keypoints of the lower levels + list position (level-major concatenation of operator()) */
+    const int mine = lane < g.nlevels ? lc[lane] : 0;
+    int before = lane < level ? mine : 0, total = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
     }
-    if (slot == 0 && lane == 0) countOut[f] = min(total, maxKp);
-    if (level < 0) return;
+    if (k == 0 && level == 0 && lane == 0) countOut[f] = min(total, maxKp);
     const LevelGeom& L = g.L[level];
-    const int k = slot - L.kpOff;
-    if (k >= lc[level]) return;
+    if (k >= __shfl_sync(0xffffffffu, mine, level)) return;
     const int outIdx = before + k;
     if (outIdx >= maxKp) return;
+    const int slot = L.kpOff + k;
 
     const LevelKp kp = levelKp[(size_t)f * g.kpPerFrame + slot];
-    const uint8_t* img = pyr + (size_t)f * g.frameBytes + L.off + (long long)kp.y * L.pitch + kp.x;
-    const uint8_t* bl = blur + (size_t)f * g.frameBytes + L.off + (long long)kp.y * L.pitch + kp.x;
+    const int pitch = L.pitch;
+    const uint8_t* img = pyr + (size_t)f * g.frameBytes + L.off + (long long)kp.y * pitch + kp.x;
+    const uint8_t* bl = blur + (size_t)f * g.frameBytes + L.off + (long long)kp.y * pitch + kp.x;
 
     /* ---- intensity centroid --------------------------------------------------------------------------- */
     const int u = lane - 15;
@@ -83,7 +85,7 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
         int vals[31];
 #pragma unroll
         for (int v = -15; v <= 15; ++v)
-            vals[v + 15] = au <= HW[v < 0 ? -v : v] ? (int)img[(long long)v * L.pitch + u] : 0;
+            vals[v + 15] = au <= HW[v < 0 ? -v : v] ? (int)img[v * pitch + u] : 0;
         int rowsum = 0;
 #pragma unroll
         for (int v = -15; v <= 15; ++v) { rowsum += vals[v + 15]; m01 += v * vals[v + 15]; }
@@ -104,13 +106,12 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     unsigned val = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const signed char* q = kBriefPairs[lane * 8 + j];
-        const float x0 = (float)q[0], y0 = (float)q[1], x1 = (float)q[2], y1 = (float)q[3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = bl[(long long)r0 * L.pitch + c0], t1 = bl[(long long)r1 * L.pitch + c1];
+        const float4 q = kBriefPairs[lane * 8 + j];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, b), __fmul_rn(q.w, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(q.z, a), __fmul_rn(q.w, b)));
+        const int t0 = bl[r0 * pitch + c0], t1 = bl[r1 * pitch + c1];
         val |= (unsigned)(t0 < t1) << j;
     }
     descOut[((size_t)f * maxKp + outIdx) * 32 + lane] = (uint8_t)val;
@@ -133,7 +134,7 @@ cudaError_t launch_orient_describe(const Geom& g, const uint8_t* dPyr, const uin
                                    sdyn_keypoint* dKp, uint8_t* dDesc, int32_t* dCount, int maxKp,
                                    int nframes, cudaStream_t st)
 {
-    dim3 grid((g.kpPerFrame + DW - 1) / DW, nframes);
+    dim3 grid((g.maxNodeCap + DW - 1) / DW, g.nlevels, nframes);
     k_orient_describe<<<grid, DW * 32, 0, st>>>(g, dPyr, dBlur, dLevelKp, dLevelCount, dKp, dDesc, dCount, maxKp);
     return cudaGetLastError();
 }

@@ -166,10 +166,13 @@ int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frame
     const sdyn_orb_params& p = c->params;
     if (c->spans.size() > 4096) drain_spans(c);
     {
-        StageTimer t(c, st, SDYN_STAGE_PYRAMID);
+        StageTimer t(c, st, SDYN_STAGE_LEVEL0);
         CU(c, cudaMemsetAsync(c->dCandCount, 0, sizeof(int32_t) * SDYN_MAX_LEVELS * nframes, st));
         CU(c, cudaMemsetAsync(c->dCellFlag, 0, (size_t)g.cellsPerFrame * nframes, st));
         CU(c, launch_level0(g, dGray, frameStride, rowStride, c->dPyr, nframes, st));
+    }
+    {
+        StageTimer t(c, st, SDYN_STAGE_PYRAMID);
         for (int l = 1; l < g.nlevels; ++l) CU(c, launch_resize(g, l, c->dTables, c->dPyr, nframes, st));
     }
     {
