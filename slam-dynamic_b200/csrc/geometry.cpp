@@ -161,7 +161,7 @@ int compute_geometry(const sdyn_orb_params& p, const sdyn_scale_info& s, int W, 
             };
             L.xtab = build(L.w, P.w, true);
             L.ytab = build(L.h, P.h, false);
-            /* worst-case source rectangle over all 128 x 16 destination tiles (k_resize stages it in shared memory) */
+            /* worst-case source rectangle over all 128 x 32 destination tiles (k_resize stages it in shared memory) */
             auto span = [&](int tabOff, int n, int tile, int lead) {
                 const ResizeTap* t = reinterpret_cast<const ResizeTap*>(tables.data() + tabOff);
                 int worst = 0;
@@ -177,7 +177,7 @@ int compute_geometry(const sdyn_orb_params& p, const sdyn_scale_info& s, int W, 
             };
             /* tiles start at padded column multiples of 128, i.e. bordered column -(kLeftPad-kEdge) + 128k */
             L.rsPitch = (int)align_up((size_t)span(L.xtab, L.w + 2 * kEdge, 128, kLeftPad - kEdge) + 16, 16);
-            L.rsRows = span(L.ytab, L.h + 2 * kEdge, 16, 0) + 16;
+            L.rsRows = span(L.ytab, L.h + 2 * kEdge, 32, 0) + 16;
         }
     }
     g.frameBytes = (long long)align_up(off, 256);

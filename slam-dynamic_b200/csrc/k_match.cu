@@ -123,23 +123,116 @@ constexpr int CW = 8;   /* warps per CTA in k_match_candidates */
 __global__ void __launch_bounds__(CW * 32)
 k_match_candidates(const MatchJob* __restrict__ jobs)
 {
-    const MatchJob& J = jobs[blockIdx.y];
-    const int q = blockIdx.x * CW + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    /* the job descriptor is read dozens of times: one coalesced copy into shared memory per CTA */
+    __shared__ __align__(16) MatchJob sJ;
+    __shared__ int sOff[CW], sOverflow;
+    {
+        const uint32_t* srcw = reinterpret_cast<const uint32_t*>(jobs + blockIdx.y);
+        uint32_t* dstw = reinterpret_cast<uint32_t*>(&sJ);
+        for (int i = threadIdx.x; i < (int)(sizeof(MatchJob) / 4); i += CW * 32) dstw[i] = srcw[i];
+    }
+    __syncthreads();
+    const MatchJob& J = sJ;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * CW + warp;
     const int nq = job_nq(J);
-    if (q >= nq) return;
 
     uint32_t qd[8];
-    bool active = true;
+    bool active = q < nq;
     float x = 0.f, y = 0.f, r = 0.f, gate = 0.f, gateX = 0.f;   /* window centre / radius, stereo gate */
     int minLevel = 0, maxLevel = -1;
+    BowQuery bq = {0, 0, 0};
+
+    if (active) {
+        if (J.mode == MM_BOW) {
+            bq = reinterpret_cast<const BowQuery*>(J.queries)[q];
+            load_desc(J.qDesc + 32 * (size_t)bq.kfIdx, qd);
+        } else if (J.mode == MM_FRAME) {
+            const sdyn_last_point* lp = reinterpret_cast<const sdyn_last_point*>(J.queries) + q;
+            active = lp->has_mp && !lp->outlier;
+            if (active) {
+                /* x3Dc = Rcw*x3Dw + tcw, evaluated like cv::Mat's 3x3 float product: left-to-right, no FMA */
+                float pc[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float s = __fadd_rn(__fadd_rn(__fmul_rn(J.Tcw[4 * k], lp->world[0]), __fmul_rn(J.Tcw[4 * k + 1], lp->world[1])),
+                                              __fmul_rn(J.Tcw[4 * k + 2], lp->world[2]));
+                    pc[k] = __fadd_rn(s, J.Tcw[4 * k + 3]);
+                }
+                const float invzc = (float)(1.0 / (double)pc[2]);
+                if (invzc < 0) active = false;
+                x = __fadd_rn(__fmul_rn(__fmul_rn(J.fx, pc[0]), invzc), J.cx);
+                y = __fadd_rn(__fmul_rn(__fmul_rn(J.fy, pc[1]), invzc), J.cy);
+                if (x < J.minX || x > J.maxX || y < J.minY || y > J.maxY) active = false;
+                const int oct = J.qKeys[q].octave;
+                r = __fmul_rn(J.th, J.scale[oct]);
+                if (J.forward) { minLevel = oct; maxLevel = -1; }
+                else if (J.backward) { minLevel = 0; maxLevel = oct; }
+                else { minLevel = oct - 1; maxLevel = oct + 1; }
+                gate = r;
+                gateX = __fsub_rn(x, __fmul_rn(J.bf, invzc));    /* ur = u - mbf*invzc */
+                load_desc(lp->desc, qd);
+            }
+        } else if (J.mode == MM_MAP) {
+            const sdyn_mappoint_query* mp = reinterpret_cast<const sdyn_mappoint_query*>(J.queries) + q;
+            active = mp->track_in_view && !mp->bad;
+            if (active) {
+                float rr = ((double)mp->view_cos > 0.998) ? 2.5f : 4.0f;      /* RadiusByViewingCos */
+                if (J.th != 1.0f) rr = __fmul_rn(rr, J.th);
+                r = __fmul_rn(rr, J.scale[mp->level]);
+                x = mp->proj_x; y = mp->proj_y;
+                minLevel = mp->level - 1; maxLevel = mp->level;
+                gate = r; gateX = mp->proj_xr;
+                load_desc(mp->desc, qd);
+            }
+        } else {   /* MM_INIT */
+            const sdyn_keypoint kp = J.qKeys[q];
+            active = !(kp.octave > 0);
+            if (active) {
+                x = J.prevMatched[2 * q]; y = J.prevMatched[2 * q + 1];
+                r = (float)J.window;
+                minLevel = kp.octave; maxLevel = kp.octave;
+                load_desc(J.qDesc + 32 * (size_t)q, qd);
+            }
+        }
+    }
+
+    int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+    if (active && J.mode != MM_BOW) {
+        cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, J.minX), r), J.gridWInv)));
+        cx1 = min(SDYN_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, J.minX), r), J.gridWInv)));
+        cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, J.minY), r), J.gridHInv)));
+        cy1 = min(SDYN_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, J.minY), r), J.gridHInv)));
+        if (cx0 >= SDYN_GRID_COLS || cx1 < 0 || cy0 >= SDYN_GRID_ROWS || cy1 < 0) active = false;
+    }
+
+    /* upper bound of this query's list (all keypoints of the touched cells); ONE pool reservation per CTA */
+    int bound = 0;
+    if (active) {
+        if (J.mode == MM_BOW) bound = bq.fCnt;
+        else {
+            for (int ix = cx0 + lane; ix <= cx1; ix += 32)
+                bound += J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1] - J.cellOff[ix * SDYN_GRID_ROWS + cy0];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bound += __shfl_xor_sync(0xffffffffu, bound, o);
+        }
+    }
+    if (lane == 0) sOff[warp] = bound;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < CW; ++w) { const int b = sOff[w]; sOff[w] = tot; tot += b; }
+        const int base = tot ? atomicAdd(J.poolUsed, tot) : 0;
+        sOverflow = base + tot > J.poolCap;
+        if (sOverflow) J.result[2] = 1;
+        for (int w = 0; w < CW; ++w) sOff[w] += base;
+    }
+    __syncthreads();
+    if (q >= nq) return;
+    if (!active || sOverflow) { if (lane == 0) J.qspan[q] = make_int2(0, 0); return; }
+    const int off = sOff[warp];
 
     if (J.mode == MM_BOW) {
-        const BowQuery bq = reinterpret_cast<const BowQuery*>(J.queries)[q];
-        load_desc(J.qDesc + 32 * (size_t)bq.kfIdx, qd);
-        int off = 0;
-        if (lane == 0) off = atomicAdd(J.poolUsed, bq.fCnt);
-        off = __shfl_sync(0xffffffffu, off, 0);
-        if (off + bq.fCnt > J.poolCap) { if (lane == 0) { J.result[2] = 1; J.qspan[q] = make_int2(0, 0); } return; }
         for (int k = lane; k < bq.fCnt; k += 32) {
             const int idx = (int)J.fIndex[bq.fOff + k];
             J.pool[off + k] = pack_rec(idx, hamming256(qd, J.desc + 32 * (size_t)idx), 0);
@@ -148,71 +241,11 @@ k_match_candidates(const MatchJob* __restrict__ jobs)
         return;
     }
 
-    if (J.mode == MM_FRAME) {
-        const sdyn_last_point* lp = reinterpret_cast<const sdyn_last_point*>(J.queries) + q;
-        active = lp->has_mp && !lp->outlier;
-        if (active) {
-            /* x3Dc = Rcw*x3Dw + tcw, evaluated like cv::Mat's 3x3 float product: left-to-right, no FMA */
-            float pc[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float s = __fadd_rn(__fadd_rn(__fmul_rn(J.Tcw[4 * k], lp->world[0]), __fmul_rn(J.Tcw[4 * k + 1], lp->world[1])),
-                                          __fmul_rn(J.Tcw[4 * k + 2], lp->world[2]));
-                pc[k] = __fadd_rn(s, J.Tcw[4 * k + 3]);
-            }
-            const float invzc = (float)(1.0 / (double)pc[2]);
-            if (invzc < 0) active = false;
-            x = __fadd_rn(__fmul_rn(__fmul_rn(J.fx, pc[0]), invzc), J.cx);
-            y = __fadd_rn(__fmul_rn(__fmul_rn(J.fy, pc[1]), invzc), J.cy);
-            if (x < J.minX || x > J.maxX || y < J.minY || y > J.maxY) active = false;
-            const int oct = J.qKeys[q].octave;
-            r = __fmul_rn(J.th, J.scale[oct]);
-            if (J.forward) { minLevel = oct; maxLevel = -1; }
-            else if (J.backward) { minLevel = 0; maxLevel = oct; }
-            else { minLevel = oct - 1; maxLevel = oct + 1; }
-            gate = r;
-            gateX = __fsub_rn(x, __fmul_rn(J.bf, invzc));    /* ur = u - mbf*invzc */
-            load_desc(lp->desc, qd);
-        }
-    } else if (J.mode == MM_MAP) {
-        const sdyn_mappoint_query* mp = reinterpret_cast<const sdyn_mappoint_query*>(J.queries) + q;
-        active = mp->track_in_view && !mp->bad;
-        if (active) {
-            float rr = ((double)mp->view_cos > 0.998) ? 2.5f : 4.0f;      /* RadiusByViewingCos */
-            if (J.th != 1.0f) rr = __fmul_rn(rr, J.th);
-            r = __fmul_rn(rr, J.scale[mp->level]);
-            x = mp->proj_x; y = mp->proj_y;
-            minLevel = mp->level - 1; maxLevel = mp->level;
-            gate = r; gateX = mp->proj_xr;
-            load_desc(mp->desc, qd);
-        }
-    } else {   /* MM_INIT */
-        const sdyn_keypoint kp = J.qKeys[q];
-        active = !(kp.octave > 0);
-        if (active) {
-            x = J.prevMatched[2 * q]; y = J.prevMatched[2 * q + 1];
-            r = (float)J.window;
-            minLevel = kp.octave; maxLevel = kp.octave;
-            load_desc(J.qDesc + 32 * (size_t)q, qd);
-        }
-    }
-
-    int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
-    if (active) {
-        cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, J.minX), r), J.gridWInv)));
-        cx1 = min(SDYN_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, J.minX), r), J.gridWInv)));
-        cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, J.minY), r), J.gridHInv)));
-        cy1 = min(SDYN_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, J.minY), r), J.gridHInv)));
-        if (cx0 >= SDYN_GRID_COLS || cx1 < 0 || cy0 >= SDYN_GRID_ROWS || cy1 < 0) active = false;
-    }
-    if (!active) { if (lane == 0) J.qspan[q] = make_int2(0, 0); return; }
-
     /* The candidates of grid column ix are ONE contiguous CSR span; lanes own columns, a warp scan turns the
      * span lengths into offsets of the concatenated (= reference-order) candidate sequence, and the warp then
      * walks that sequence 32 entries at a time: two dependent loads per candidate (entry, descriptor). */
     const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
-    int cnt = 0, off = 0;
-    bool reserved = false;
+    int cnt = 0;
     for (int c0 = cx0; c0 <= cx1; c0 += 32) {
         const int ix = c0 + lane;
         int b = 0, len = 0;
@@ -225,22 +258,6 @@ k_match_candidates(const MatchJob* __restrict__ jobs)
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         const int excl = incl - len;
-        if (!reserved) {
-            /* upper bound of the list length: all keypoints of the touched cells (all column groups) */
-            int bound = total;
-            for (int c1 = c0 + 32; c1 <= cx1; c1 += 32) {
-                const int jx = c1 + lane;
-                int l2 = 0;
-                if (jx <= cx1) l2 = J.cellOff[jx * SDYN_GRID_ROWS + cy1 + 1] - J.cellOff[jx * SDYN_GRID_ROWS + cy0];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) l2 += __shfl_xor_sync(0xffffffffu, l2, o);
-                bound += l2;
-            }
-            if (lane == 0) off = atomicAdd(J.poolUsed, bound);
-            off = __shfl_sync(0xffffffffu, off, 0);
-            if (off + bound > J.poolCap) { if (lane == 0) { J.result[2] = 1; J.qspan[q] = make_int2(0, 0); } return; }
-            reserved = true;
-        }
         const int ncols = min(32, cx1 - c0 + 1);
         for (int e0 = 0; e0 < total; e0 += 32) {
             const int e = e0 + lane;

@@ -39,16 +39,20 @@ k_level0(const __grid_constant__ Geom g, const uint8_t* __restrict__ in, size_t 
     reinterpret_cast<uint32_t*>(dst)[q] = out;
 }
 
-/* Bilinear resize of one level, tile-staged.  A CTA produces RT_W x RT_H bytes of the bordered (and left-padded)
- * destination; the source rectangle its taps touch — found with a block min/max over the tile's column and row
- * taps, so mirrored border tiles need no special case — is staged in shared memory with aligned 16-byte loads,
- * and every thread then produces 4 adjacent bytes of two rows from shared memory. */
-constexpr int RT_W = 128, RT_H = 16;
+/* Bilinear resize of one level, tile-staged and separable.  A CTA produces RT_W x RT_H bytes of the bordered (and
+ * left-padded) destination:
+ *   1. the source rectangle its taps touch — found with a block min/max over the tile's column and row taps, so
+ *      mirrored border tiles need no special case — is staged in shared memory with aligned 16-byte loads;
+ *   2. horizontal pass ONCE per source row: H = (S[s0]*c0 + S[s1]*c1) >> 4 as uint16 (fits: 255*2048 >> 4);
+ *   3. vertical pass per output: ((b0*H0) >> 16) + ((b1*H1) >> 16) + 2 >> 2, four bytes per 32-bit store.
+ * Consecutive output rows share source rows (scale 1.2), so the horizontal work is 1.2 rows per output row
+ * instead of 2. */
+constexpr int RT_W = 128, RT_H = 32;
 
 __global__ void __launch_bounds__(256)
 k_resize(const __grid_constant__ Geom g, int level, const uint8_t* __restrict__ tables, uint8_t* __restrict__ pyr)
 {
-    extern __shared__ __align__(16) uint8_t src[];
+    extern __shared__ __align__(16) uint8_t smemR[];
     __shared__ ResizeTap sx[RT_W], sy[RT_H];
     __shared__ int sMinC, sMaxC, sMinR, sMaxR;
     const LevelGeom& L = g.L[level];
@@ -57,6 +61,8 @@ k_resize(const __grid_constant__ Geom g, int level, const uint8_t* __restrict__ 
     const int pc0 = blockIdx.x * RT_W, row0 = blockIdx.y * RT_H;     /* padded column / bordered row of the tile */
     const int bw = L.w + 2 * kEdge, bh = L.h + 2 * kEdge;
     const int srcPitch = L.rsPitch;
+    uint8_t* src = smemR;                                             /* rsRows x rsPitch bytes */
+    uint16_t* hz = reinterpret_cast<uint16_t*>(smemR + (size_t)L.rsRows * srcPitch);   /* rsRows x RT_W */
     if (tid == 0) { sMinC = 1 << 30; sMaxC = -1; sMinR = 1 << 30; sMaxR = -1; }
     __syncthreads();
     if (tid < RT_W) {
@@ -83,30 +89,34 @@ k_resize(const __grid_constant__ Geom g, int level, const uint8_t* __restrict__ 
         reinterpret_cast<uint4*>(src + r * srcPitch)[q] = __ldg(reinterpret_cast<const uint4*>(sbase + (long long)r * P.pitch) + q);
     }
     __syncthreads();
+    /* horizontal pass: thread = (column c of the tile, source rows r = tid/128, +2, ...) */
+    {
+        const int c = tid & (RT_W - 1);
+        const ResizeTap t = sx[c];
+        const int o0 = t.s0 - ax0, o1 = t.s1 - ax0, c0 = t.c0, c1 = t.c1;
+        for (int r = tid >> 7; r < nrows; r += 2) {
+            const uint8_t* s = src + r * srcPitch;
+            hz[r * RT_W + c] = (uint16_t)((s[o0] * c0 + s[o1] * c1) >> 4);
+        }
+    }
+    __syncthreads();
+    /* vertical pass: thread = (4 adjacent columns, output rows tid/32, +8, ...) */
     const int gx = tid & 31;
     if (pc0 + gx * 4 >= L.pitch) return;
-    ResizeTap tx[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { tx[i] = sx[gx * 4 + i]; tx[i].s0 -= ax0; tx[i].s1 -= ax0; }
-#pragma unroll
     for (int rr = tid >> 5; rr < RT_H; rr += 8) {
         const int row = row0 + rr;
         if (row >= bh) break;
         const ResizeTap ty = sy[rr];
-        const uint8_t* s0 = src + (ty.s0 - minR) * srcPitch;
-        const uint8_t* s1 = src + (ty.s1 - minR) * srcPitch;
+        const uint2 h0 = *reinterpret_cast<const uint2*>(hz + (ty.s0 - minR) * RT_W + gx * 4);
+        const uint2 h1 = *reinterpret_cast<const uint2*>(hz + (ty.s1 - minR) * RT_W + gx * 4);
         const int b0 = ty.c0, b1 = ty.c1;
-        uint32_t out = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int h0 = s0[tx[i].s0] * tx[i].c0 + s0[tx[i].s1] * tx[i].c1;
-            const int h1 = s1[tx[i].s0] * tx[i].c0 + s1[tx[i].s1] * tx[i].c1;
-            int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            v = max(0, min(v, 255));
-            out |= (uint32_t)v << (8 * i);
-        }
+        const int v0 = (((b0 * (int)(h0.x & 0xffff)) >> 16) + ((b1 * (int)(h1.x & 0xffff)) >> 16) + 2) >> 2;
+        const int v1 = (((b0 * (int)(h0.x >> 16)) >> 16) + ((b1 * (int)(h1.x >> 16)) >> 16) + 2) >> 2;
+        const int v2 = (((b0 * (int)(h0.y & 0xffff)) >> 16) + ((b1 * (int)(h1.y & 0xffff)) >> 16) + 2) >> 2;
+        const int v3 = (((b0 * (int)(h0.y >> 16)) >> 16) + ((b1 * (int)(h1.y >> 16)) >> 16) + 2) >> 2;
+        /* coefficients are non-negative and sum to 2048, so 0 <= v <= 255 without clamping */
         uint8_t* dst = frame + L.off + (long long)(row - kEdge) * L.pitch - kLeftPad + pc0;
-        reinterpret_cast<uint32_t*>(dst)[gx] = out;
+        reinterpret_cast<uint32_t*>(dst)[gx] = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
     }
 }
 
@@ -123,7 +133,7 @@ cudaError_t launch_level0(const Geom& g, const uint8_t* dIn, size_t inFrameStrid
 cudaError_t launch_resize(const Geom& g, int level, const uint8_t* dTables, uint8_t* dPyr, int nframes, cudaStream_t st)
 {
     const LevelGeom& L = g.L[level];
-    const size_t smem = (size_t)L.rsPitch * L.rsRows;
+    const size_t smem = (size_t)L.rsPitch * L.rsRows + (size_t)L.rsRows * RT_W * sizeof(uint16_t);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -33,7 +33,7 @@ struct LevelGeom {
     float patchSize;
     /* resize tables (level > 0): byte offsets into the table blob */
     int xtab, ytab;
-    /* shared-memory staging of the resize kernel: worst-case source rectangle of a 128 x 16 output tile */
+    /* shared-memory staging of the resize kernel: worst-case source rectangle of a 128 x 32 output tile */
     int rsPitch, rsRows;
 };
 
