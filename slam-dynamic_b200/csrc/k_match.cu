@@ -120,7 +120,7 @@ __device__ __forceinline__ void load_desc(const uint8_t* p, uint32_t (&q)[8])
 
 constexpr int CW = 8;   /* warps per CTA in k_match_candidates */
 
-__global__ void __launch_bounds__(CW * 32)
+__global__ void __launch_bounds__(CW * 32, 6)
 k_match_candidates(const MatchJob* __restrict__ jobs)
 {
     /* the job descriptor is read dozens of times: one coalesced copy into shared memory per CTA */
