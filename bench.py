@@ -318,6 +318,7 @@ def main():
     ex.profile(False)
     kps, desc, counts = ex.fetch(B)
     assign, locked, mask, cnt = pysdyn.track_fetch(ex, B)
+    evals = pysdyn.track_stats(ex, B)
     mean_kp = float(counts.mean())
 
     # ---- end to end through the C ABI with pinned host buffers ("e2e") ------------------------------------
@@ -386,8 +387,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
-    # candidate evaluations per frame are not counted on the device; use the oracle-calibrated average
-    evals_per_frame = 20 * (cap + N_MAP)
+    evals_per_frame = sum(evals) / B                       # Hamming evaluations per frame, counted on the device
     sab = stage_alg_bytes(W, H, int(round(mean_kp)), evals_per_frame, cap + N_MAP)
     tot_stage_ms = max(sum(v[0] for v in stages.values()), 1e-9)
     stage_report = {}
@@ -398,10 +398,20 @@ def main():
             stage_report[name] = {"ms_per_step": per_step, "share": sms / tot_stage_ms, "alg_gbs": ach, "hbm_frac": ach / peak}
     dom = max(stage_report, key=lambda n: stage_report[n]["ms_per_step"]) if stage_report else None
     roof = None
+    # DRAM traffic per launch of the stage's main kernel, from the committed ncu --set full capture
+    stage_kernel = {"fast": "k_fast", "match": "k_match_candidates", "describe": "k_orient_describe", "blur": "k_blur",
+                    "pyramid": "k_resize", "octree": "k_octree", "level0": "k_level0", "dynamic": "k_box_stage"}
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if dom and B == 64 and stage_kernel.get(dom) in tj:
+            traffic = tj[stage_kernel[dom]]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     if dom:
         r = stage_report[dom]
         roof = {"kernel": dom, "bound": "hbm", "achieved": r["alg_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": r["hbm_frac"], "traffic": None, "peak_source": peak_src,
+                "frac": r["hbm_frac"], "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": sab.get(dom, 0) * B,
                 "note": "FAST scoring is integer-ALU bound, not HBM bound (DESIGN.md §Kernels)" if dom == "fast" else ""}
     balg = alg_bytes_extract(W, H, int(round(mean_kp)))
@@ -432,7 +442,7 @@ def main():
                               "frac": balg * fps / world / 1e9 / peak,
                               "note": "SURVEY §8(d) extraction bytes per frame x per-GPU frames/s"},
         "stages": stage_report,
-        "per_frame": {"keypoints": float(g[:, 1].mean()), "matches_frame": float(g[:, 2].mean()),
+        "per_frame": {"hamming_evals": evals_per_frame, "keypoints": float(g[:, 1].mean()), "matches_frame": float(g[:, 2].mean()),
                       "matches_map": float(g[:, 3].mean()), "dyn_masked": float(g[:, 4].mean())},
         "cpu_baseline": cpu,
     }

@@ -303,6 +303,9 @@ int sdyn_track_batch_async(sdyn_ctx* ctx, int nframes, const uint8_t* gray, size
                            int stride, const sdyn_track_inputs* in, sdyn_keypoint* kp_out, uint8_t* desc_out, int* n_out,
                            int32_t* assign, uint8_t* locked, uint8_t* dyn_mask, int32_t* counts, int cap);
 int sdyn_track_wait(sdyn_ctx* ctx);
+/* Statistics of the last fetched step: Hamming-distance evaluations of the frame search and of the map search,
+ * summed over the step's frames (the work the popc roofline is computed from). */
+int sdyn_track_stats(const sdyn_ctx* ctx, int nframes, long long evals[2]);
 int sdyn_track_results(const sdyn_ctx* ctx, sdyn_track_view* out);
 /* D2H of the step results next to sdyn_fetch_results (host arrays sized [nframes][cap] / [nframes][4]). */
 int sdyn_track_fetch(sdyn_ctx* ctx, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dyn_mask,

@@ -291,7 +291,7 @@ k_match_candidates(const MatchJob* __restrict__ jobs)
             cnt += __popc(m);
         }
     }
-    if (lane == 0) J.qspan[q] = make_int2(off, cnt);
+    if (lane == 0) { J.qspan[q] = make_int2(off, cnt); atomicAdd(&J.result[3], cnt); }   /* distance evaluations (statistics) */
 }
 
 /* ------------------------------------------------------------------------------------------------- resolve */

@@ -334,6 +334,16 @@ int sdyn_track_batch_async(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t
     return SDYN_OK;
 }
 
+int sdyn_track_stats(const sdyn_ctx* c, int nframes, long long evals[2])
+{
+    if (!c || !c->track || !evals) return SDYN_ERR_ARG;
+    const TrackState* t = static_cast<const TrackState*>(c->track);
+    if (nframes < 1 || nframes > t->B) return SDYN_ERR_ARG;
+    evals[0] = evals[1] = 0;
+    for (int f = 0; f < nframes; ++f) { evals[0] += t->hResult[f * 4 + 3]; evals[1] += t->hResult[(t->B + f) * 4 + 3]; }
+    return SDYN_OK;
+}
+
 int sdyn_track_results(const sdyn_ctx* c, sdyn_track_view* out)
 {
     if (!c || !out || !c->track) return SDYN_ERR_ARG;

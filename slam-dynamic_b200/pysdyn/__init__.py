@@ -509,6 +509,7 @@ def _bind_track(L):
                                    vp, vp, vp, vp, vp, vp, vp, C.c_int]
     L.sdyn_track_batch_async.argtypes = L.sdyn_track_batch.argtypes
     L.sdyn_track_wait.argtypes = [vp]
+    L.sdyn_track_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong * 2)]
     L._track_bound = True
     return L
 
@@ -555,3 +556,10 @@ def track_batch_host_async(ex, images, tin, outs):
 
 def track_wait(ex):
     ex._check(_bind_track(lib()).sdyn_track_wait(ex._h))
+
+
+def track_stats(ex, nframes):
+    """(frame-search, map-search) Hamming evaluations of the last fetched step, summed over its frames."""
+    ev = (C.c_longlong * 2)()
+    ex._check(_bind_track(lib()).sdyn_track_stats(ex._h, nframes, C.byref(ev)))
+    return int(ev[0]), int(ev[1])
