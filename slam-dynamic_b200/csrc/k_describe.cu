@@ -5,9 +5,9 @@
  *   arithmetic: cv::fastAtan2 (SURVEY A-5), cvRound = round-half-even (A-6); float rotate without FMA
  *              contraction (Appendix B-3)
  *
- * Orientation: lane u+15 owns disc column u (31 lanes); rows are walked with coalesced 31-byte reads and
- * the two int32 moments are combined with warp shuffles.  Descriptor: lane i owns byte i (8 point pairs,
- * 16 gathers from the blurred level).  Output slot = (keypoints of lower levels) + list position, which
+ * Orientation: lane u+15 owns disc column u (31 lanes) of a shared-memory copy of the patch and the two int32
+ * moments are combined with warp shuffles.  Descriptor: lane i owns byte i (8 point pairs, 16 gathers from a
+ * shared-memory copy of the blurred patch).  Output slot = (keypoints of lower levels) + list position, which
  * reproduces the reference's level-major concatenation.
  */
 #include "sdyn_internal.h"
@@ -40,17 +40,47 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
-constexpr int DW = 8;   /* warps per CTA */
+constexpr int DW = 8;    /* warps per CTA */
+constexpr int KW = 4;    /* keypoints per warp */
+constexpr int SP = 80;   /* shared patch pitch: 64 staged bytes, 16-byte aligned rows, rows 20 banks apart */
+constexpr int PR_ = 37;  /* patch rows / columns: rotated pattern coordinates reach +-18 (|p| <= 18.39) */
 
+/* Stage rows [y0, y0+nrows) x 64 bytes starting at the 16-byte aligned column ax of one level into a warp's patch
+ * buffer with 16-byte loads.  ax >= -16 and ax+63 <= w+28, i.e. inside the padded row or the next row's left
+ * padding; the patch never touches the last bordered row, so every load is inside the frame's block. */
+__device__ __forceinline__ void stage_patch(const uint8_t* __restrict__ lvl, int pitch, int y0, int ax, int nrows,
+                                            uint8_t* __restrict__ buf, int lane)
+{
+    const uint8_t* base = lvl + (long long)y0 * pitch + ax;
+    for (int i = lane; i < nrows * 4; i += 32) {
+        const int row = i >> 2, q = i & 3;
+        *reinterpret_cast<uint4*>(buf + row * SP + 16 * q) =
+            __ldg(reinterpret_cast<const uint4*>(base + (long long)row * pitch) + q);
+    }
+}
+
+/* A warp owns KW consecutive keypoints of one (frame, level).
+ *   A. per keypoint: the unblurred 31-row patch is staged in shared memory (constant pitch: the 31 disc-row reads
+ *      of a lane are LDS with immediate offsets, no 64-bit address arithmetic) and reduced to (m01, m10);
+ *   B. lanes 0..KW-1 evaluate fastAtan2 / cos / sin for one keypoint each — the scalar tail costs one pass per
+ *      warp instead of one per keypoint;
+ *   C. per keypoint: the blurred 37-row patch is staged and lane i builds descriptor byte i from 16 LDS gathers. */
 __global__ void __launch_bounds__(DW * 32)
 k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                   const LevelKp* __restrict__ levelKp, const int32_t* __restrict__ levelCount,
                   sdyn_keypoint* __restrict__ kpOut, uint8_t* __restrict__ descOut, int32_t* __restrict__ countOut,
                   int maxKp)
 {
+    __shared__ __align__(16) float4 sPat[256];                 /* pair j of descriptor byte i at [j*32 + i] */
+    __shared__ __align__(16) uint8_t sPatch[DW][PR_ * SP];
     const int f = blockIdx.z, level = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * DW + (threadIdx.x >> 5);        /* list position inside the level */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        const int t = threadIdx.x;                               /* pair t = byte (t >> 3), bit (t & 7) */
+        sPat[(t & 7) * 32 + (t >> 3)] = kBriefPairs[t];
+    }
+    __syncthreads();
+    const int k0 = (blockIdx.x * DW + warp) * KW;               /* first list position of this warp */
     const int32_t* lc = levelCount + f * SDYN_MAX_LEVELS;
     /* output slot = keypoints of the lower levels + list position (level-major concatenation of operator()) */
     const int mine = lane < g.nlevels ? lc[lane] : 0;
@@ -60,63 +90,86 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
         before += __shfl_xor_sync(0xffffffffu, before, o);
         total += __shfl_xor_sync(0xffffffffu, total, o);
     }
-    if (k == 0 && level == 0 && lane == 0) countOut[f] = min(total, maxKp);
+    if (k0 == 0 && level == 0 && lane == 0) countOut[f] = min(total, maxKp);
     const LevelGeom& L = g.L[level];
-    if (k >= __shfl_sync(0xffffffffu, mine, level)) return;
-    const int outIdx = before + k;
-    if (outIdx >= maxKp) return;
-    const int slot = L.kpOff + k;
+    int nk = min(KW, __shfl_sync(0xffffffffu, mine, level) - k0);
+    nk = min(nk, maxKp - (before + k0));                         /* output capacity */
+    if (nk <= 0) return;
 
-    const LevelKp kp = levelKp[(size_t)f * g.kpPerFrame + slot];
     const int pitch = L.pitch;
-    const uint8_t* img = pyr + (size_t)f * g.frameBytes + L.off + (long long)kp.y * pitch + kp.x;
-    const uint8_t* bl = blur + (size_t)f * g.frameBytes + L.off + (long long)kp.y * pitch + kp.x;
+    const uint8_t* img = pyr + (size_t)f * g.frameBytes + L.off;
+    const uint8_t* bl = blur + (size_t)f * g.frameBytes + L.off;
+    uint8_t* buf = sPatch[warp];
+    LevelKp kp = {0, 0, 0};
+    if (lane < nk) kp = levelKp[(size_t)f * g.kpPerFrame + L.kpOff + k0 + lane];
 
-    /* ---- intensity centroid --------------------------------------------------------------------------- */
-    const int u = lane - 15;
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int au = abs(u);
-        /* half-widths as compile-time constants: the unrolled loop folds them into immediates, and the 31 row
-         * loads are independent, so they are all in flight together */
-        /* umax[] of ORBextractor.cc:454-469 for HALF_PATCH_SIZE = 15 (geometry.cpp recomputes it; tests/test_abi.py
-         * checks the two agree) */
-        constexpr int HW[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-        int vals[31];
+    /* ---- A. intensity centroid ---------------------------------------------------------------------------- */
+    int my10 = 0, my01 = 0;
+    for (int i = 0; i < nk; ++i) {
+        const int kx = __shfl_sync(0xffffffffu, (int)kp.x, i), ky = __shfl_sync(0xffffffffu, (int)kp.y, i);
+        const int ax = (kx - 18) & ~15, dx = kx - ax;
+        __syncwarp();
+        stage_patch(img, pitch, ky - 15, ax, 31, buf, lane);
+        __syncwarp();
+        const int u = lane - 15;
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            const int au = abs(u);
+            /* umax[] of ORBextractor.cc:454-469 for HALF_PATCH_SIZE = 15 (geometry.cpp recomputes it; tests/test_abi.py
+             * checks the two agree) */
+            constexpr int HW[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+            const uint8_t* c = buf + 15 * SP + dx + u;
+            int rowsum = 0;
 #pragma unroll
-        for (int v = -15; v <= 15; ++v)
-            vals[v + 15] = au <= HW[v < 0 ? -v : v] ? (int)img[v * pitch + u] : 0;
-        int rowsum = 0;
+            for (int v = -15; v <= 15; ++v) {
+                const int val = au <= HW[v < 0 ? -v : v] ? (int)c[v * SP] : 0;
+                rowsum += val; m01 += v * val;
+            }
+            m10 = u * rowsum;
+        }
 #pragma unroll
-        for (int v = -15; v <= 15; ++v) { rowsum += vals[v + 15]; m01 += v * vals[v + 15]; }
-        m10 = u * rowsum;
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        if (lane == i) { my10 = m10; my01 = m01; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    /* ---- rotated BRIEF ------------------------------------------------------------------------------------
+    /* ---- B. angle, rotation (one keypoint per lane) ------------------------------------------------------------
      * The reference evaluates cosf/sinf of the float angle; evaluating in double and rounding once gives
      * the correctly rounded float, which is what glibc returns except for a handful of inputs. */
-    const float rad = __fmul_rn(angle, __uint_as_float(0x3c8efa35u));   /* factorPI = (float)(CV_PI/180.f) */
-    const float a = (float)cos((double)rad), b = (float)sin((double)rad);
-    unsigned val = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 q = kBriefPairs[lane * 8 + j];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, b), __fmul_rn(q.w, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(q.z, a), __fmul_rn(q.w, b)));
-        const int t0 = bl[r0 * pitch + c0], t1 = bl[r1 * pitch + c1];
-        val |= (unsigned)(t0 < t1) << j;
+    float angle = 0.f, ca = 1.f, sb = 0.f;
+    if (lane < nk) {
+        angle = fast_atan2_deg((float)my01, (float)my10);
+        const float rad = __fmul_rn(angle, __uint_as_float(0x3c8efa35u));   /* factorPI = (float)(CV_PI/180.f) */
+        ca = (float)cos((double)rad); sb = (float)sin((double)rad);
     }
-    descOut[((size_t)f * maxKp + outIdx) * 32 + lane] = (uint8_t)val;
 
-    if (lane == 0) {
+    /* ---- C. rotated BRIEF ------------------------------------------------------------------------------------ */
+    const int outBase = before + k0;
+    for (int i = 0; i < nk; ++i) {
+        const int kx = __shfl_sync(0xffffffffu, (int)kp.x, i), ky = __shfl_sync(0xffffffffu, (int)kp.y, i);
+        const float a = __shfl_sync(0xffffffffu, ca, i), b = __shfl_sync(0xffffffffu, sb, i);
+        const int ax = (kx - 18) & ~15, dx = kx - ax;
+        __syncwarp();
+        stage_patch(bl, pitch, ky - 18, ax, PR_, buf, lane);
+        __syncwarp();
+        const uint8_t* c = buf + 18 * SP + dx;
+        unsigned val = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 q = sPat[j * 32 + lane];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q.z, b), __fmul_rn(q.w, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(q.z, a), __fmul_rn(q.w, b)));
+            const int t0 = c[r0 * SP + c0], t1 = c[r1 * SP + c1];
+            val |= (unsigned)(t0 < t1) << j;
+        }
+        descOut[((size_t)f * maxKp + outBase + i) * 32 + lane] = (uint8_t)val;
+    }
+
+    if (lane < nk) {
         sdyn_keypoint o;
         o.x = level ? __fmul_rn((float)kp.x, L.scale) : (float)kp.x;
         o.y = level ? __fmul_rn((float)kp.y, L.scale) : (float)kp.y;
@@ -125,7 +178,7 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
         o.response = (float)kp.score;
         o.octave = level;
         o.class_id = -1;
-        kpOut[(size_t)f * maxKp + outIdx] = o;
+        kpOut[(size_t)f * maxKp + outBase + lane] = o;
     }
 }
 
@@ -134,7 +187,7 @@ cudaError_t launch_orient_describe(const Geom& g, const uint8_t* dPyr, const uin
                                    sdyn_keypoint* dKp, uint8_t* dDesc, int32_t* dCount, int maxKp,
                                    int nframes, cudaStream_t st)
 {
-    dim3 grid((g.maxNodeCap + DW - 1) / DW, g.nlevels, nframes);
+    dim3 grid((g.maxNodeCap + DW * KW - 1) / (DW * KW), g.nlevels, nframes);
     k_orient_describe<<<grid, DW * 32, 0, st>>>(g, dPyr, dBlur, dLevelKp, dLevelCount, dKp, dDesc, dCount, maxKp);
     return cudaGetLastError();
 }

@@ -12,7 +12,7 @@
  *  k_grid_build        the 64x48 grid as a CSR: keypoints sorted by (cell = ix*48+iy, index).  Because
  *                      GetFeaturesInArea walks ix outer / iy inner / in-cell insertion order, the candidates
  *                      of one ix are ONE contiguous CSR span, already in reference order.
- *  k_match_candidates  data-parallel, one warp per query: project, window, level / stereo gates, then
+ *  k_match_candidates  data-parallel, one thread per query: project, window, level / stereo gates, then
  *                      __popc over the 256-bit descriptors (8 x 32 bit, query held in registers).  Emits each
  *                      query's candidate list IN REFERENCE ORDER as packed records idx:16|dist:9|level:5.
  *                      This is where the integer / popc work is.
@@ -118,30 +118,38 @@ __device__ __forceinline__ void load_desc(const uint8_t* p, uint32_t (&q)[8])
     for (int k = 0; k < 8; ++k) q[k] = w[k];
 }
 
-constexpr int CW = 8;   /* warps per CTA in k_match_candidates */
+constexpr int CT = 128;   /* queries (= threads) per CTA in k_match_candidates */
 
-__global__ void __launch_bounds__(CW * 32, 6)
+/* One THREAD per query.  A query touches a handful of grid columns and, after the level / window / stereo gates,
+ * evaluates only a few distances (2-3 on tracking frames), so the cost of a query is a chain of 4-5 dependent
+ * L1/L2 loads, not arithmetic: a warp per query leaves 31 lanes waiting on that chain.  With a thread per query
+ * the chains of 32 queries overlap in one warp and the whole batch fits one resident wave.  A thread walks its
+ * columns in order, so its list comes out in the reference's enumeration order by construction. */
+__global__ void __launch_bounds__(CT)
 k_match_candidates(const MatchJob* __restrict__ jobs)
 {
     /* the job descriptor is read dozens of times: one coalesced copy into shared memory per CTA */
     __shared__ __align__(16) MatchJob sJ;
-    __shared__ int sOff[CW], sOverflow;
+    __shared__ int sWarp[CT / 32], sBase, sOverflow;
     {
         const uint32_t* srcw = reinterpret_cast<const uint32_t*>(jobs + blockIdx.y);
         uint32_t* dstw = reinterpret_cast<uint32_t*>(&sJ);
-        for (int i = threadIdx.x; i < (int)(sizeof(MatchJob) / 4); i += CW * 32) dstw[i] = srcw[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(MatchJob) / 4); i += CT) dstw[i] = srcw[i];
     }
     __syncthreads();
     const MatchJob& J = sJ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * CW + warp;
+    const int q = blockIdx.x * CT + threadIdx.x;
     const int nq = job_nq(J);
+    if (blockIdx.x * CT >= nq) return;      /* whole CTA past the device-resident query count */
 
     uint32_t qd[8];
     bool active = q < nq;
     float x = 0.f, y = 0.f, r = 0.f, gate = 0.f, gateX = 0.f;   /* window centre / radius, stereo gate */
     int minLevel = 0, maxLevel = -1;
     BowQuery bq = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) qd[k] = 0;
 
     if (active) {
         if (J.mode == MM_BOW) {
@@ -210,88 +218,65 @@ k_match_candidates(const MatchJob* __restrict__ jobs)
     int bound = 0;
     if (active) {
         if (J.mode == MM_BOW) bound = bq.fCnt;
-        else {
-            for (int ix = cx0 + lane; ix <= cx1; ix += 32)
+        else
+            for (int ix = cx0; ix <= cx1; ++ix)
                 bound += J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1] - J.cellOff[ix * SDYN_GRID_ROWS + cy0];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) bound += __shfl_xor_sync(0xffffffffu, bound, o);
-        }
     }
-    if (lane == 0) sOff[warp] = bound;
+    int incl = bound;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) sWarp[warp] = incl;
     __syncthreads();
     if (threadIdx.x == 0) {
         int tot = 0;
-        for (int w = 0; w < CW; ++w) { const int b = sOff[w]; sOff[w] = tot; tot += b; }
+        for (int w = 0; w < CT / 32; ++w) { const int b = sWarp[w]; sWarp[w] = tot; tot += b; }
         const int base = tot ? atomicAdd(J.poolUsed, tot) : 0;
+        sBase = base;
         sOverflow = base + tot > J.poolCap;
         if (sOverflow) J.result[2] = 1;
-        for (int w = 0; w < CW; ++w) sOff[w] += base;
     }
     __syncthreads();
-    if (q >= nq) return;
-    if (!active || sOverflow) { if (lane == 0) J.qspan[q] = make_int2(0, 0); return; }
-    const int off = sOff[warp];
-
-    if (J.mode == MM_BOW) {
-        for (int k = lane; k < bq.fCnt; k += 32) {
-            const int idx = (int)J.fIndex[bq.fOff + k];
-            J.pool[off + k] = pack_rec(idx, hamming256(qd, J.desc + 32 * (size_t)idx), 0);
-        }
-        if (lane == 0) J.qspan[q] = make_int2(off, bq.fCnt);
-        return;
-    }
-
-    /* The candidates of grid column ix are ONE contiguous CSR span; lanes own columns, a warp scan turns the
-     * span lengths into offsets of the concatenated (= reference-order) candidate sequence, and the warp then
-     * walks that sequence 32 entries at a time: two dependent loads per candidate (entry, descriptor). */
-    const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+    const bool work = active && !sOverflow;          /* active implies q < nq */
+    const int off = sBase + sWarp[warp] + incl - bound;
+    uint32_t* out = J.pool + off;
     int cnt = 0;
-    for (int c0 = cx0; c0 <= cx1; c0 += 32) {
-        const int ix = c0 + lane;
-        int b = 0, len = 0;
-        if (ix <= cx1) {
-            b = J.cellOff[ix * SDYN_GRID_ROWS + cy0];
-            len = J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1] - b;
+
+    if (!work) {
+    } else if (J.mode == MM_BOW) {
+        for (int k = 0; k < bq.fCnt; ++k) {
+            const int idx = (int)J.fIndex[bq.fOff + k];
+            out[k] = pack_rec(idx, hamming256(qd, J.desc + 32 * (size_t)idx), 0);
         }
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int excl = incl - len;
-        const int ncols = min(32, cx1 - c0 + 1);
-        for (int e0 = 0; e0 < total; e0 += 32) {
-            const int e = e0 + lane;
-            bool ok = e < total;
-            /* which column does entry e belong to: last column whose exclusive offset is <= e */
-            int pos = 0;
-            {
-                int col = 0;
-                for (int j = 1; j < ncols; ++j) { const int oj = __shfl_sync(0xffffffffu, excl, j); if (oj <= e) col = j; }
-                const int bj = __shfl_sync(0xffffffffu, b, col), oj = __shfl_sync(0xffffffffu, excl, col);
-                pos = bj + (e - oj);
-            }
-            int idx = 0, dist = 0, oct = 0;
-            if (ok) {
-                const float4 ge = J.gridEntry[pos];
+        cnt = bq.fCnt;
+    } else {
+        /* The candidates of grid column ix are ONE contiguous CSR span (k_grid_build), already in reference order. */
+        const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+        const bool stereoGate = J.mode != MM_INIT && J.uRight;
+        for (int ix = cx0; ix <= cx1; ++ix) {
+            const int b = J.cellOff[ix * SDYN_GRID_ROWS + cy0], e = J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1];
+            for (int p = b; p < e; ++p) {
+                const float4 ge = J.gridEntry[p];
                 const int io = __float_as_int(ge.z);
-                idx = io & 0xffffff; oct = io >> 24;
+                const int idx = io & 0xffffff, oct = io >> 24;
                 if (checkLevels) {
-                    if (oct < minLevel) ok = false;
-                    if (maxLevel >= 0 && oct > maxLevel) ok = false;
+                    if (oct < minLevel) continue;
+                    if (maxLevel >= 0 && oct > maxLevel) continue;
                 }
-                if (!(fabsf(__fsub_rn(ge.x, x)) < r && fabsf(__fsub_rn(ge.y, y)) < r)) ok = false;
-                if (ok && J.mode != MM_INIT && J.uRight) {
+                if (!(fabsf(__fsub_rn(ge.x, x)) < r && fabsf(__fsub_rn(ge.y, y)) < r)) continue;
+                if (stereoGate) {
                     const float ur = J.uRight[idx];
-                    if (ur > 0 && fabsf(__fsub_rn(gateX, ur)) > gate) ok = false;
+                    if (ur > 0 && fabsf(__fsub_rn(gateX, ur)) > gate) continue;
                 }
-                if (ok) dist = hamming256(qd, J.desc + 32 * (size_t)idx);
+                out[cnt++] = pack_rec(idx, hamming256(qd, J.desc + 32 * (size_t)idx), oct);
             }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) J.pool[off + cnt + __popc(m & ((1u << lane) - 1))] = pack_rec(idx, dist, oct);
-            cnt += __popc(m);
         }
     }
-    if (lane == 0) { J.qspan[q] = make_int2(off, cnt); atomicAdd(&J.result[3], cnt); }   /* distance evaluations (statistics) */
+    if (q < nq) J.qspan[q] = work ? make_int2(off, cnt) : make_int2(0, 0);
+    /* distance evaluations (statistics): one atomic per warp */
+    int ev = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ev += __shfl_xor_sync(0xffffffffu, ev, o);
+    if (lane == 0 && ev) atomicAdd(&J.result[3], ev);
 }
 
 /* ------------------------------------------------------------------------------------------------- resolve */
@@ -592,8 +577,8 @@ cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, cudaStream_t st)
 cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQueries, cudaStream_t st)
 {
     if (maxQueries <= 0) return cudaSuccess;
-    dim3 grid((maxQueries + CW - 1) / CW, njobs);
-    k_match_candidates<<<grid, CW * 32, 0, st>>>(dJobs);
+    dim3 grid((maxQueries + CT - 1) / CT, njobs);
+    k_match_candidates<<<grid, CT, 0, st>>>(dJobs);
     return cudaGetLastError();
 }
 

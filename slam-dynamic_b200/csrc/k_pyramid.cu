@@ -19,24 +19,51 @@ __device__ __forceinline__ int refl(int i, int n)
     return i;
 }
 
+/* Level 0: one thread per 16-byte chunk of a padded destination row.  Chunks that lie inside the image are
+ * realigned copies: the source row starts at an arbitrary byte address (row stride = W for packed frames), so the
+ * chunk is read as aligned 32-bit words and shifted into place with funnel shifts, then stored with one 16-byte
+ * store.  Only the few chunks that touch the REFLECT_101 frame or the padding take the per-byte path. */
 __global__ void __launch_bounds__(256)
 k_level0(const __grid_constant__ Geom g, const uint8_t* __restrict__ in, size_t inFrameStride, int inRowStride,
-         uint8_t* __restrict__ pyr)
+         uint8_t* __restrict__ pyr, int nframes)
 {
     const LevelGeom& L = g.L[0];
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;     /* 4-byte group inside the padded row */
-    const int row = blockIdx.y * blockDim.y + threadIdx.y;   /* bordered row */
-    if (q * 4 >= L.pitch || row >= L.h + 2 * kEdge) return;
+    const int nchunks = L.pitch / 16;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int row = idx / nchunks, c = idx - row * nchunks;   /* bordered row, chunk inside the padded row */
+    if (row >= L.h + 2 * kEdge) return;
     const uint8_t* src = in + (size_t)blockIdx.z * inFrameStride + (size_t)refl(row - kEdge, L.h) * inRowStride;
-    uint32_t out = 0;
+    const int col0 = c * 16 - kLeftPad;                        /* interior coordinate of the chunk's first byte */
+    uint4 out;
+    bool fast = col0 >= 0 && col0 + 16 <= L.w;
+    if (fast) {
+        const uintptr_t s = reinterpret_cast<uintptr_t>(src + col0);
+        const unsigned a = (unsigned)(s & 3);
+        const uintptr_t lo = s - a, hi = lo + (a ? 20 : 16);    /* aligned words actually read */
+        const uintptr_t bufLo = reinterpret_cast<uintptr_t>(in);
+        const uintptr_t bufHi = bufLo + (size_t)(nframes - 1) * inFrameStride + (size_t)(L.h - 1) * inRowStride + L.w;
+        fast = lo >= bufLo && hi <= bufHi;
+        if (fast) {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(lo);
+            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
+            const uint32_t w4 = a ? __ldg(p + 4) : 0u;
+            const unsigned sh = 8 * a;
+            out = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                             __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        }
+    }
+    if (!fast) {
+        uint32_t o[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int col = q * 4 + i - kLeftPad;                       /* interior coordinate */
-        col = max(-kEdge, min(col, L.w + kEdge - 1));          /* padding bytes replicate the frame edge */
-        out |= (uint32_t)__ldg(src + refl(col, L.w)) << (8 * i);
+        for (int i = 0; i < 16; ++i) {
+            int col = col0 + i;
+            col = max(-kEdge, min(col, L.w + kEdge - 1));      /* padding bytes replicate the frame edge */
+            o[i >> 2] |= (uint32_t)__ldg(src + refl(col, L.w)) << (8 * (i & 3));
+        }
+        out = make_uint4(o[0], o[1], o[2], o[3]);
     }
     uint8_t* dst = pyr + (size_t)blockIdx.z * g.frameBytes + L.off + (long long)(row - kEdge) * L.pitch - kLeftPad;
-    reinterpret_cast<uint32_t*>(dst)[q] = out;
+    reinterpret_cast<uint4*>(dst)[c] = out;
 }
 
 /* Bilinear resize of one level, tile-staged and separable.  A CTA produces RT_W x RT_H bytes of the bordered (and
@@ -124,9 +151,9 @@ cudaError_t launch_level0(const Geom& g, const uint8_t* dIn, size_t inFrameStrid
                           uint8_t* dPyr, int nframes, cudaStream_t st)
 {
     const LevelGeom& L = g.L[0];
-    dim3 block(64, 4);
-    dim3 grid((L.pitch / 4 + block.x - 1) / block.x, (L.h + 2 * kEdge + block.y - 1) / block.y, nframes);
-    k_level0<<<grid, block, 0, st>>>(g, dIn, inFrameStride, inRowStride, dPyr);
+    const int items = (L.pitch / 16) * (L.h + 2 * kEdge);
+    dim3 grid((items + 255) / 256, 1, nframes);
+    k_level0<<<grid, 256, 0, st>>>(g, dIn, inFrameStride, inRowStride, dPyr, nframes);
     return cudaGetLastError();
 }
 
