@@ -311,11 +311,35 @@ int sdyn_track_results(const sdyn_ctx* ctx, sdyn_track_view* out);
 int sdyn_track_fetch(sdyn_ctx* ctx, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dyn_mask,
                      int32_t* counts, int cap, void* stream);
 
+/* ---- Frame::ComputeStereoMatches ------------------------------------------------------------------------
+ * Replaces Frame::ComputeStereoMatches (src/Frame.cc:874-1048), the step that follows the two extractions in the
+ * stereo Frame constructor (src/Frame.cc:151-160).  `left` and `right` are the contexts of mpORBextractorLeft /
+ * mpORBextractorRight; the call works on the keypoints, descriptors and pyramids their LAST extraction of
+ * `nframes` frames left on the device (same image size and ORB parameters on both), so no pyramid level travels
+ * to the host.  mb / mbf: Frame::mb, Frame::mbf.  Outputs per left keypoint: mvuRight, mvDepth (-1 = none).
+ * The device form only enqueues on `stream` (NULL = left's stream) after ordering it behind both extractions;
+ * results stay device-resident (sdyn_stereo_results) and can feed sdyn_frame_view.u_right of later searches. */
+typedef struct {
+    const float* u_right;           /* [max_batch][cap]  mvuRight */
+    const float* depth;             /* [max_batch][cap]  mvDepth */
+    const int32_t* kept;            /* [max_batch] stereo points that survive the median cut (:1034-1047) */
+    int32_t cap;
+} sdyn_stereo_view;
+int sdyn_stereo_match_device(sdyn_ctx* left, sdyn_ctx* right, int nframes, float mb, float mbf, void* stream);
+int sdyn_stereo_results(const sdyn_ctx* left, sdyn_stereo_view* out);
+/* D2H of mvuRight / mvDepth: host arrays [nframes][cap]; kept (nullable) [nframes].  Synchronises `stream`.
+ * SDYN_ERR_GEOMETRY if a right keypoint's row band left the image (the reference writes out of bounds there). */
+int sdyn_stereo_fetch(sdyn_ctx* left, int nframes, float* u_right, float* depth, int cap, int32_t* kept, void* stream);
+/* Host-output form: device step + fetch. */
+int sdyn_stereo_match(sdyn_ctx* left, sdyn_ctx* right, int nframes, float mb, float mbf, float* u_right, float* depth,
+                      int cap, int32_t* kept);
+
 /* ---- per-stage device timing (CUDA events on the launching stream) -------------------------------
  * While enabled, every enqueue brackets each stage with events; sdyn_profile_read synchronises and
  * returns the accumulated milliseconds and launch counts since the last read. */
 enum { SDYN_STAGE_PYRAMID = 0, SDYN_STAGE_FAST, SDYN_STAGE_OCTREE, SDYN_STAGE_BLUR, SDYN_STAGE_DESCRIBE,
        SDYN_STAGE_MATCH, SDYN_STAGE_DYNAMIC, SDYN_STAGE_LEVEL0 /* clears + level 0; PYRAMID = the resize chain */,
+       SDYN_STAGE_STEREO,
        SDYN_STAGE_COUNT };
 typedef struct {
     double ms[SDYN_STAGE_COUNT];

@@ -4,6 +4,7 @@
 #include "orc_extractor.h"
 #include "orc_matcher.h"
 #include "orc_dynamic.h"
+#include "orc_stereo.h"
 #include "../include/sdyn.h"   /* POD layouts of the C ABI only (no product code is linked) */
 #include <cstring>
 #include <algorithm>
@@ -72,6 +73,21 @@ int orc_extractor_candidates(void* e, int l, int* xyv, int cap)
 }
 
 int orc_extractor_level_count(void* e, int l) { Extractor* E = (Extractor*)e; return (l < 0 || l >= (int)E->perLevel.size()) ? -1 : E->perLevel[l]; }
+
+/* Frame::ComputeStereoMatches on the pyramids the two extractors hold after run() (src/Frame.cc:874-1048) */
+int orc_stereo_matches(void* eL, void* eR, const KeyPoint* keysL, int N, const uint8_t* descL, const KeyPoint* keysR, int Nr,
+                       const uint8_t* descR, float mb, float mbf, float* uRight, float* depth)
+{
+    Extractor* L = (Extractor*)eL; Extractor* R = (Extractor*)eR;
+    if ((int)L->pyr.size() != L->nlevels || (int)R->pyr.size() != R->nlevels || L->nlevels != R->nlevels) return -2;
+    std::vector<LevelRef> pl(L->nlevels), pr(R->nlevels);
+    for (int l = 0; l < L->nlevels; ++l) {
+        pl[l] = LevelRef{L->pyr[l].roi(), L->pyr[l].w, L->pyr[l].h, L->pyr[l].stride};
+        pr[l] = LevelRef{R->pyr[l].roi(), R->pyr[l].w, R->pyr[l].h, R->pyr[l].stride};
+    }
+    return compute_stereo_matches(keysL, N, descL, keysR, Nr, descR, pl.data(), pr.data(), L->nlevels, L->scale.data(),
+                                  L->invScale.data(), mb, mbf, uRight, depth);
+}
 
 float orc_ic_angle(const uint8_t* center, int stride)
 { static Extractor E(1000, 1.2f, 8, 20, 7); return ic_angle(center, stride, E.umax); }

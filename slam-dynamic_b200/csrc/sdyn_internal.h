@@ -97,6 +97,7 @@ struct sdyn_ctx {
     /* matcher / dynamic-mask arena (grown on demand, reused across calls) */
     uint8_t* dArena; size_t arenaCap;
     void* track;                               /* TrackState of the batched front end (sdyn_track.cpp) */
+    void* stereo;                              /* StereoState of ComputeStereoMatches (sdyn_stereo.cpp) */
     /* per-stage profiling */
     bool profiling;
     std::vector<cudaEvent_t> evPool;           /* free events */
@@ -123,6 +124,8 @@ struct StageTimer {          /* brackets a stage with CUDA events while profilin
 };
 /* sdyn_track.cpp */
 void free_track_state(sdyn_ctx* c);
+/* sdyn_stereo.cpp */
+void free_stereo_state(sdyn_ctx* c);
 
 /* geometry.cpp */
 void compute_scale_info(const sdyn_orb_params& p, sdyn_scale_info& s, int umax[16]);

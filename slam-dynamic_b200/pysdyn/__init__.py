@@ -39,7 +39,7 @@ class DeviceView(C.Structure):
                 ("cap", C.c_int32), ("nlevels", C.c_int32), ("level", LevelInfo * MAX_LEVELS)]
 
 
-STAGES = ["pyramid", "fast", "octree", "blur", "describe", "match", "dynamic", "level0"]
+STAGES = ["pyramid", "fast", "octree", "blur", "describe", "match", "dynamic", "level0", "stereo"]
 
 
 class StageTimes(C.Structure):
@@ -563,3 +563,52 @@ def track_stats(ex, nframes):
     ev = (C.c_longlong * 2)()
     ex._check(_bind_track(lib()).sdyn_track_stats(ex._h, nframes, C.byref(ev)))
     return int(ev[0]), int(ev[1])
+
+
+# ---------------------------------------------------------------------------------------------------
+# Frame::ComputeStereoMatches (src/Frame.cc:874-1048)
+# ---------------------------------------------------------------------------------------------------
+class StereoViewC(C.Structure):
+    _fields_ = [("u_right", C.c_void_p), ("depth", C.c_void_p), ("kept", C.c_void_p), ("cap", C.c_int32)]
+
+
+def _bind_stereo(L):
+    if getattr(L, "_stereo_bound", False):
+        return L
+    L.sdyn_stereo_match_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    L.sdyn_stereo_results.argtypes = [C.c_void_p, C.POINTER(StereoViewC)]
+    L.sdyn_stereo_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.sdyn_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_void_p]
+    L._stereo_bound = True
+    return L
+
+
+def stereo_match_device(left, right, nframes, mb, mbf, stream=None):
+    """Enqueues ComputeStereoMatches for the frames the two Extractors processed last; results stay on the device."""
+    left._check(_bind_stereo(lib()).sdyn_stereo_match_device(left._h, right._h, nframes, mb, mbf, stream))
+
+
+def stereo_view(left):
+    v = StereoViewC()
+    left._check(_bind_stereo(lib()).sdyn_stereo_results(left._h, C.byref(v)))
+    return v
+
+
+def stereo_fetch(left, nframes, stream=None):
+    cap = left.cap
+    ur = np.empty((nframes, cap), np.float32); dp = np.empty((nframes, cap), np.float32)
+    kept = np.empty(nframes, np.int32)
+    left._check(_bind_stereo(lib()).sdyn_stereo_fetch(left._h, nframes, ur.ctypes.data, dp.ctypes.data, cap,
+                                                      kept.ctypes.data, stream))
+    return ur, dp, kept
+
+
+def stereo_match(left, right, nframes, mb, mbf):
+    """Host-output form: (mvuRight [nframes][cap], mvDepth [nframes][cap], kept [nframes])."""
+    cap = left.cap
+    ur = np.empty((nframes, cap), np.float32); dp = np.empty((nframes, cap), np.float32)
+    kept = np.empty(nframes, np.int32)
+    left._check(_bind_stereo(lib()).sdyn_stereo_match(left._h, right._h, nframes, mb, mbf, ur.ctypes.data,
+                                                      dp.ctypes.data, cap, kept.ctypes.data))
+    return ur, dp, kept

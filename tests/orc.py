@@ -280,3 +280,24 @@ def first_separate(keys, boxes, box_idx):
                                 C.byref(nd), db.ctypes.data, dk.ctypes.data, cap, C.byref(npairs))
     return {"order": order[:n].copy(), "class_id": cid[:n].copy(), "n_dyn": nd.value, "boxes": b[:nb].copy(),
             "box_idx": bi[:nb].copy(), "dyn": list(zip(db[:npairs.value].tolist(), dk[:npairs.value].tolist()))}
+
+
+# ---------------------------------------------------------------------------------------------------
+# Frame::ComputeStereoMatches (src/Frame.cc:874-1048)
+# ---------------------------------------------------------------------------------------------------
+lib.orc_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _u8p, C.c_void_p, C.c_int, _u8p,
+                                   C.c_float, C.c_float, _f32p, _f32p]
+
+
+def stereo_matches(ex_left, ex_right, keys_l, desc_l, keys_r, desc_r, mb, mbf):
+    """ex_left / ex_right: oracle Extractors whose LAST call produced the keypoints (their pyramids are read).
+    Returns (mvuRight, mvDepth, kept)."""
+    keys_l = np.ascontiguousarray(keys_l, KP_DTYPE); keys_r = np.ascontiguousarray(keys_r, KP_DTYPE)
+    desc_l = np.ascontiguousarray(desc_l, np.uint8); desc_r = np.ascontiguousarray(desc_r, np.uint8)
+    n = len(keys_l)
+    ur = np.empty(max(n, 1), np.float32); dp = np.empty(max(n, 1), np.float32)
+    rc = lib.orc_stereo_matches(ex_left.h, ex_right.h, keys_l.ctypes.data, n, _p(desc_l, _u8p), keys_r.ctypes.data,
+                                len(keys_r), _p(desc_r, _u8p), mb, mbf, _p(ur, _f32p), _p(dp, _f32p))
+    if rc < 0:
+        raise ValueError("oracle stereo: input the reference cannot process (rc=%d)" % rc)
+    return ur[:n], dp[:n], rc

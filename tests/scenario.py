@@ -179,3 +179,16 @@ def track_params(W, H, cam=KITTI_CAM, th_frame=7.0, th_map=3.0, nnratio_map=0.8,
     return dict(min_x=0.0, min_y=0.0, max_x=float(W), max_y=float(H), fx=cam["fx"], fy=cam["fy"], cx=cam["cx"],
                 cy=cam["cy"], bf=cam["bf"], b=cam["bf"] / cam["fx"], tcw_cur=eye, tcw_last=eye, th_frame=th_frame,
                 th_map=th_map, nnratio_map=nnratio_map, mono=mono, check_orientation=check_orientation)
+
+
+def stereo_pair(cfg, idx, disparities=(5, 11, 23), seq=0):
+    """Rectified left / right frames: the right view shows the left content shifted by a per-band disparity (the
+    image is cut into len(disparities) horizontal bands), plus its own sensor noise."""
+    import common
+    left = common.frame(cfg, idx, seq=seq)
+    right = np.empty_like(left)
+    h = left.shape[0]
+    edges = np.linspace(0, h, len(disparities) + 1).astype(int)
+    for d, y0, y1 in zip(disparities, edges[:-1], edges[1:]):
+        right[y0:y1] = common.frame(cfg, idx + 1000, seq=seq, ox=d)[y0:y1]
+    return left, right
