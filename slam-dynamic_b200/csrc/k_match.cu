@@ -118,30 +118,97 @@ __device__ __forceinline__ void load_desc(const uint8_t* p, uint32_t (&q)[8])
     for (int k = 0; k < 8; ++k) q[k] = w[k];
 }
 
-constexpr int CT = 128;   /* queries (= threads) per CTA in k_match_candidates */
-
-/* One THREAD per query.  A query touches a handful of grid columns and, after the level / window / stereo gates,
- * evaluates only a few distances (2-3 on tracking frames), so the cost of a query is a chain of 4-5 dependent
- * L1/L2 loads, not arithmetic: a warp per query leaves 31 lanes waiting on that chain.  With a thread per query
- * the chains of 32 queries overlap in one warp and the whole batch fits one resident wave.  A thread walks its
- * columns in order, so its list comes out in the reference's enumeration order by construction. */
-__global__ void __launch_bounds__(CT)
-k_match_candidates(const MatchJob* __restrict__ jobs)
+/* ------------------------------------------------------------------------------------------- query order
+ * Counting sort of the map-point queries of a job by search-window size class (level, narrow / wide viewing-cosine
+ * radius), largest windows first, inactive queries last.  Only the visiting order of k_match_candidates changes:
+ * every result is stored under the query's own index. */
+__global__ void __launch_bounds__(256)
+k_query_order(const MatchJob* __restrict__ jobs)
 {
+    const MatchJob& J = jobs[blockIdx.x];
+    if (J.mode != MM_MAP || !J.qperm) return;
+    constexpr int NB = 2 * SDYN_MAX_LEVELS + 1;
+    __shared__ int hist[NB];
+    const int tid = threadIdx.x, nq = job_nq(J);
+    const sdyn_mappoint_query* mps = reinterpret_cast<const sdyn_mappoint_query*>(J.queries);
+    if (tid < NB) hist[tid] = 0;
+    __syncthreads();
+    auto key = [&](int q) {
+        const sdyn_mappoint_query& m = mps[q];
+        if (!m.track_in_view || m.bad) return NB - 1;
+        const int lvl = min(max(m.level, 0), SDYN_MAX_LEVELS - 1);
+        return 2 * (SDYN_MAX_LEVELS - 1 - lvl) + (((double)m.view_cos > 0.998) ? 1 : 0);
+    };
+    for (int q = tid; q < nq; q += 256) atomicAdd(&hist[key(q)], 1);
+    __syncthreads();
+    if (tid == 0) { int run = 0; for (int k = 0; k < NB; ++k) { const int c = hist[k]; hist[k] = run; run += c; } }
+    __syncthreads();
+    for (int q = tid; q < nq; q += 256) J.qperm[atomicAdd(&hist[key(q)], 1)] = q;
+}
+
+constexpr int kCandMaxThreads = 1024;
+constexpr size_t kCandSmemBudget = 200 * 1024;
+constexpr int kCellOffBytes = ((kGridCells + 1) * 4 + 15) / 16 * 16;
+
+/* One THREAD per query; a CTA works through the queries of ONE job (search) in chunks of blockDim.x, gridDim.x
+ * CTAs sharing a job.
+ *  - A query touches a handful of grid columns and, after the level / window / stereo gates, evaluates only a few
+ *    distances (2-3 on tracking frames): its cost is a chain of dependent loads, not arithmetic.  A warp per query
+ *    leaves 31 lanes waiting on that chain; with a thread per query 32 chains overlap in one warp.
+ *  - All queries of a CTA read the same frame, so the frame's grid (cell offsets + entries, ~45 KB) and, when they
+ *    fit, its descriptors (64 KB) are staged in shared memory once per CTA: the ~45 entry reads per query become
+ *    30-cycle shared-memory reads instead of L1-thrashing L2 reads (8 different frames per SM otherwise).
+ *  - A thread walks its columns in order, so its list comes out in the reference's enumeration order by
+ *    construction; candidate space is reserved with one atomic per warp batch. */
+__global__ void __launch_bounds__(kCandMaxThreads)
+k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDesc, int stageCap)
+{
+    extern __shared__ __align__(16) uint8_t smemC[];
     /* the job descriptor is read dozens of times: one coalesced copy into shared memory per CTA */
     __shared__ __align__(16) MatchJob sJ;
-    __shared__ int sWarp[CT / 32], sBase, sOverflow;
+    const int NT = blockDim.x;
     {
         const uint32_t* srcw = reinterpret_cast<const uint32_t*>(jobs + blockIdx.y);
         uint32_t* dstw = reinterpret_cast<uint32_t*>(&sJ);
-        for (int i = threadIdx.x; i < (int)(sizeof(MatchJob) / 4); i += CT) dstw[i] = srcw[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(MatchJob) / 4); i += NT) dstw[i] = srcw[i];
     }
     __syncthreads();
     const MatchJob& J = sJ;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * CT + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const int nq = job_nq(J);
-    if (blockIdx.x * CT >= nq) return;      /* whole CTA past the device-resident query count */
+
+    /* stage the searched frame: cell offsets | grid entries | descriptors */
+    const int32_t* cellOff = J.cellOff;
+    const float4* gridEntry = J.gridEntry;
+    const uint8_t* desc = J.desc;
+    if (J.mode != MM_BOW && stageGrid) {
+        int32_t* sOff = reinterpret_cast<int32_t*>(smemC);
+        float4* sEnt = reinterpret_cast<float4*>(smemC + kCellOffBytes);
+        for (int i = threadIdx.x; i <= kGridCells; i += NT) sOff[i] = J.cellOff[i];
+        const int total = min(J.cellOff[kGridCells], stageCap);
+        for (int i = threadIdx.x; i < total; i += NT) sEnt[i] = J.gridEntry[i];
+        cellOff = sOff; gridEntry = sEnt;
+    }
+    if (stageDesc) {
+        uint4* sDesc = reinterpret_cast<uint4*>(smemC + (stageGrid ? kCellOffBytes + (size_t)stageCap * 16 : 0));
+        const int n2 = min(job_n(J), stageCap) * 2;
+        const uint4* g = reinterpret_cast<const uint4*>(J.desc);
+        for (int i = threadIdx.x; i < n2; i += NT) sDesc[i] = g[i];
+        desc = reinterpret_cast<const uint8_t*>(sDesc);
+    }
+    __syncthreads();
+
+  /* Warps pull batches of 32 queries from the job's counter: no CTA-wide barrier, so a warp with a long walk (large
+   * window in a dense region) delays nobody, and with the largest windows first (k_query_order) the tail is short. */
+  for (;;) {
+    int first = 0;
+    if (lane == 0) first = atomicAdd(J.qNext, 32);
+    first = __shfl_sync(0xffffffffu, first, 0);
+    if (first >= nq) break;
+    const int slot = first + lane;
+    /* queries are independent here, so they can be visited in any order: k_query_order groups queries of similar
+     * window size (= walk length) so that the lanes of a warp finish together */
+    const int q = slot < nq ? (J.qperm ? J.qperm[slot] : slot) : nq;
 
     uint32_t qd[8];
     bool active = q < nq;
@@ -220,24 +287,19 @@ k_match_candidates(const MatchJob* __restrict__ jobs)
         if (J.mode == MM_BOW) bound = bq.fCnt;
         else
             for (int ix = cx0; ix <= cx1; ++ix)
-                bound += J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1] - J.cellOff[ix * SDYN_GRID_ROWS + cy0];
+                bound += cellOff[ix * SDYN_GRID_ROWS + cy1 + 1] - cellOff[ix * SDYN_GRID_ROWS + cy0];
     }
     int incl = bound;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) sWarp[warp] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int w = 0; w < CT / 32; ++w) { const int b = sWarp[w]; sWarp[w] = tot; tot += b; }
-        const int base = tot ? atomicAdd(J.poolUsed, tot) : 0;
-        sBase = base;
-        sOverflow = base + tot > J.poolCap;
-        if (sOverflow) J.result[2] = 1;
-    }
-    __syncthreads();
-    const bool work = active && !sOverflow;          /* active implies q < nq */
-    const int off = sBase + sWarp[warp] + incl - bound;
+    int base = 0;
+    if (lane == 31 && incl) base = atomicAdd(J.poolUsed, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    const bool overflow = base + tot > J.poolCap;
+    if (overflow && lane == 0) J.result[2] = 1;
+    const bool work = active && !overflow;           /* active implies q < nq */
+    const int off = base + incl - bound;
     uint32_t* out = J.pool + off;
     int cnt = 0;
 
@@ -245,30 +307,46 @@ k_match_candidates(const MatchJob* __restrict__ jobs)
     } else if (J.mode == MM_BOW) {
         for (int k = 0; k < bq.fCnt; ++k) {
             const int idx = (int)J.fIndex[bq.fOff + k];
-            out[k] = pack_rec(idx, hamming256(qd, J.desc + 32 * (size_t)idx), 0);
+            out[k] = pack_rec(idx, hamming256(qd, desc + 32 * (size_t)idx), 0);
         }
         cnt = bq.fCnt;
     } else {
         /* The candidates of grid column ix are ONE contiguous CSR span (k_grid_build), already in reference order. */
+        /* bCheckLevels = (minLevel > 0) || (maxLevel >= 0); kept iff oct >= minLevel and (maxLevel < 0 or oct <= maxLevel) */
         const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
-        const bool stereoGate = J.mode != MM_INIT && J.uRight;
+        const int loLevel = checkLevels ? minLevel : -0x7fffffff, hiLevel = (checkLevels && maxLevel >= 0) ? maxLevel : 0x7fffffff;
+        const float* __restrict__ uRight = J.mode != MM_INIT ? J.uRight : nullptr;
+        const bool stereoGate = uRight != nullptr;
+        /* Pass 1: walk the spans and keep what survives the level / window / stereo gates.  The entries of a span are
+         * fetched four at a time before any of them is tested, so four loads are in flight per thread instead of one
+         * dependent load per iteration (the walk is latency bound: ~45 entries per query, 2-3 survivors). */
         for (int ix = cx0; ix <= cx1; ++ix) {
-            const int b = J.cellOff[ix * SDYN_GRID_ROWS + cy0], e = J.cellOff[ix * SDYN_GRID_ROWS + cy1 + 1];
-            for (int p = b; p < e; ++p) {
-                const float4 ge = J.gridEntry[p];
-                const int io = __float_as_int(ge.z);
-                const int idx = io & 0xffffff, oct = io >> 24;
-                if (checkLevels) {
-                    if (oct < minLevel) continue;
-                    if (maxLevel >= 0 && oct > maxLevel) continue;
+            const int b = cellOff[ix * SDYN_GRID_ROWS + cy0], e = cellOff[ix * SDYN_GRID_ROWS + cy1 + 1];
+            for (int p0 = b; p0 < e; p0 += 4) {
+                float4 ge[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ge[k] = gridEntry[min(p0 + k, e - 1)];
+                /* branch-free gates: predicates instead of divergent `continue`s (32 independent walks per warp) */
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int io = __float_as_int(ge[k].z);
+                    const int oct = io >> 24;
+                    bool ok = (p0 + k < e) & (oct >= loLevel) & (oct <= hiLevel) &
+                              (fabsf(__fsub_rn(ge[k].x, x)) < r) & (fabsf(__fsub_rn(ge[k].y, y)) < r);
+                    if (stereoGate) {                       /* uniform over the job */
+                        const float ur = ok ? uRight[io & 0xffffff] : -1.0f;
+                        ok &= !(ur > 0 && fabsf(__fsub_rn(gateX, ur)) > gate);
+                    }
+                    if (ok) out[cnt] = (uint32_t)io;
+                    cnt += ok;
                 }
-                if (!(fabsf(__fsub_rn(ge.x, x)) < r && fabsf(__fsub_rn(ge.y, y)) < r)) continue;
-                if (stereoGate) {
-                    const float ur = J.uRight[idx];
-                    if (ur > 0 && fabsf(__fsub_rn(gateX, ur)) > gate) continue;
-                }
-                out[cnt++] = pack_rec(idx, hamming256(qd, J.desc + 32 * (size_t)idx), oct);
             }
+        }
+        /* Pass 2: distances of the survivors (lanes with survivors left run together) */
+        for (int k = 0; k < cnt; ++k) {
+            const int io = (int)out[k];
+            const int idx = io & 0xffffff;
+            out[k] = pack_rec(idx, hamming256(qd, desc + 32 * (size_t)idx), io >> 24);
         }
     }
     if (q < nq) J.qspan[q] = work ? make_int2(off, cnt) : make_int2(0, 0);
@@ -277,6 +355,7 @@ k_match_candidates(const MatchJob* __restrict__ jobs)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ev += __shfl_xor_sync(0xffffffffu, ev, o);
     if (lane == 0 && ev) atomicAdd(&J.result[3], ev);
+  }
 }
 
 /* ------------------------------------------------------------------------------------------------- resolve */
@@ -574,11 +653,30 @@ cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQueries, cudaStream_t st)
+cudaError_t launch_query_order(const MatchJob* dJobs, int njobs, cudaStream_t st)
+{
+    k_query_order<<<njobs, 256, 0, st>>>(dJobs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQueries, int maxN, cudaStream_t st)
 {
     if (maxQueries <= 0) return cudaSuccess;
-    dim3 grid((maxQueries + CT - 1) / CT, njobs);
-    k_match_candidates<<<grid, CT, 0, st>>>(dJobs);
+    /* many jobs: one 1024-thread CTA per job (one job per SM, everything staged once); few jobs (the single-search
+     * entry points): 256-thread CTAs, one per chunk, so a lone search still spreads over the GPU */
+    const int threads = njobs >= 32 ? kCandMaxThreads : 256;
+    const int ctasPerJob = njobs >= 32 ? 1 : (maxQueries + threads - 1) / threads;
+    const size_t gridBytes = (size_t)kCellOffBytes + (size_t)maxN * 16, descBytes = (size_t)maxN * 32;
+    const int stageGrid = gridBytes <= kCandSmemBudget, stageDesc = (stageGrid ? gridBytes : 0) + descBytes <= kCandSmemBudget;
+    const size_t smem = (stageGrid ? gridBytes : 0) + (stageDesc ? descBytes : 0);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_match_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCandSmemBudget);
+        if (e != cudaSuccess) return e;
+        configured = kCandSmemBudget;
+    }
+    dim3 grid(ctasPerJob, njobs);
+    k_match_candidates<<<grid, threads, smem, st>>>(dJobs, stageGrid, stageDesc, maxN);
     return cudaGetLastError();
 }
 

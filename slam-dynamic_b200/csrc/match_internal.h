@@ -49,16 +49,21 @@ struct MatchJob {
     int32_t* result;                 /* [0] nmatches, [1] npairs, [2] status (1 = pool overflow) */
     float* pairs;                    /* FRAME (fork overload), may be null */
     /* scratch */
+    int32_t* qperm;                  /* visiting order of k_match_candidates (k_query_order), or null = identity */
     int2* qspan;                     /* per query: (offset into pool, count) */
     int32_t* qAccepted;              /* per query: claimed index or -1 */
     int32_t* qBin;                   /* per query: rotation-histogram bin */
     uint32_t* pool;                  /* candidate records: idx:16 | dist:9 | level:5 */
     int poolCap;
     int32_t* poolUsed;
+    int32_t* qNext;                  /* next unvisited query slot (k_match_candidates work counter), zero on entry */
 };
 
 cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, cudaStream_t st);
-cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQueries, cudaStream_t st);
+/* fills MatchJob::qperm of MM_MAP jobs that have one */
+cudaError_t launch_query_order(const MatchJob* dJobs, int njobs, cudaStream_t st);
+/* maxN: largest MatchJob::n of the launch (sizes the shared-memory staging of the searched frame) */
+cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQueries, int maxN, cudaStream_t st);
 /* mode: all jobs of one launch share a mode; maxN / maxQ: largest MatchJob::n / ::nq of the launch */
 cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st);
 

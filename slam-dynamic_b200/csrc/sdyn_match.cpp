@@ -98,18 +98,18 @@ int run_job(sdyn_ctx* c, size_t fixedBytes, int nq, int poolGuess, int poolMax, 
         Arena A(c);
         MatchJob J; std::memset(&J, 0, sizeof(J));
         J.pool = A.take<uint32_t>(pool); J.poolCap = pool;
-        J.poolUsed = A.take<int32_t>(1);
+        J.poolUsed = A.take<int32_t>(2); J.qNext = J.poolUsed + 1;
         J.result = A.take<int32_t>(4);
         J.qspan = A.take<int2>(nq); J.qAccepted = A.take<int32_t>(nq); J.qBin = A.take<int32_t>(nq);
         MatchJob* dJob = A.take<MatchJob>(1);
         rc = fill(A, J);
         if (rc != SDYN_OK) return rc;
         if (A.failed) { rc = ensure_arena(c, A.used + (1 << 20)); if (rc != SDYN_OK) return rc; continue; }
-        MCU(c, cudaMemsetAsync(J.poolUsed, 0, sizeof(int32_t), c->stream));
+        MCU(c, cudaMemsetAsync(J.poolUsed, 0, 2 * sizeof(int32_t), c->stream));
         MCU(c, cudaMemsetAsync(J.result, 0, 4 * sizeof(int32_t), c->stream));
         MCU(c, cudaMemcpyAsync(dJob, &J, sizeof(J), cudaMemcpyHostToDevice, c->stream));
         MCU(c, launch_grid_build(dJob, 1, c->stream));
-        MCU(c, launch_match_candidates(dJob, 1, nq, c->stream));
+        MCU(c, launch_match_candidates(dJob, 1, nq, std::max(J.n, 1), c->stream));
         MCU(c, launch_match_resolve(dJob, 1, J.mode, std::max(J.n, 1), std::max(nq, 1), c->stream));
         c->launches += 3;
         int32_t res[4];

@@ -13,7 +13,7 @@ struct TrackState {
     uint8_t* block = nullptr; size_t bytes = 0;
     /* carved from block */
     MatchJob* dJobs; int32_t* cellOff; int32_t* sorted; int32_t* cellOf; float4* gridEntry; int32_t* assign; uint8_t* locked;
-    int2* qspan; int32_t* qAccepted; int32_t* qBin; uint32_t* pool; int32_t* poolUsed; int32_t* result;
+    int2* qspan; int32_t* qperm; int32_t* qAccepted; int32_t* qBin; uint32_t* pool; int32_t* poolUsed; int32_t* qNext; int32_t* result;
     uint64_t* mask; unsigned long long* has; int32_t* boxList; int32_t* nnQ; int32_t* nnT; uint8_t* readmit;
     int32_t* staticExit; uint8_t* dynMask; int32_t* counts;
     size_t zeroFrom = 0, zeroBytes = 0;     /* region cleared at the start of every step */
@@ -52,6 +52,7 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     const size_t oJobs = take(J * sizeof(MatchJob));
     const size_t oCellOff = take((size_t)B * (kGridCells + 1) * 4), oSorted = take((size_t)B * cap * 4), oCellOf = take((size_t)B * cap * 4);
     const size_t oGridEntry = take((size_t)B * cap * sizeof(float4));
+    const size_t oQperm = take((size_t)B * maxQ * 4);
     const size_t oQspan = take(J * maxQ * sizeof(int2)), oQAcc = take(J * maxQ * 4), oQBin = take(J * maxQ * 4);
     const size_t oPool = take(J * (size_t)t->poolPerJob * 4);
     const size_t oMask = take((size_t)B * cap * 8), oHas = take((size_t)B * 8);
@@ -62,7 +63,7 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     const size_t zeroFrom = off;
     const size_t oAssign = take((size_t)B * cap * 4);      /* set to -1 separately */
     const size_t oLocked = take((size_t)B * cap);
-    const size_t oPoolUsed = take(J * 4), oResult = take(J * 4 * 4);
+    const size_t oPoolUsed = take(J * 4), oQNext = take(J * 4), oResult = take(J * 4 * 4);
     const size_t oReadmit = take((size_t)B * cap), oStatic = take((size_t)B * 4), oCounts = take((size_t)B * 16);
     t->zeroFrom = oLocked; t->zeroBytes = off - oLocked;
     (void)zeroFrom;
@@ -82,13 +83,14 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     t->cellOff = reinterpret_cast<int32_t*>(b + oCellOff); t->sorted = reinterpret_cast<int32_t*>(b + oSorted);
     t->cellOf = reinterpret_cast<int32_t*>(b + oCellOf);
     t->gridEntry = reinterpret_cast<float4*>(b + oGridEntry);
+    t->qperm = reinterpret_cast<int32_t*>(b + oQperm);
     t->qspan = reinterpret_cast<int2*>(b + oQspan); t->qAccepted = reinterpret_cast<int32_t*>(b + oQAcc);
     t->qBin = reinterpret_cast<int32_t*>(b + oQBin); t->pool = reinterpret_cast<uint32_t*>(b + oPool);
     t->mask = reinterpret_cast<uint64_t*>(b + oMask); t->has = reinterpret_cast<unsigned long long*>(b + oHas);
     t->boxList = reinterpret_cast<int32_t*>(b + oBoxList); t->nnQ = reinterpret_cast<int32_t*>(b + oNnQ);
     t->nnT = reinterpret_cast<int32_t*>(b + oNnT); t->dynMask = b + oDynMask;
     t->assign = reinterpret_cast<int32_t*>(b + oAssign); t->locked = b + oLocked;
-    t->poolUsed = reinterpret_cast<int32_t*>(b + oPoolUsed); t->result = reinterpret_cast<int32_t*>(b + oResult);
+    t->poolUsed = reinterpret_cast<int32_t*>(b + oPoolUsed); t->qNext = reinterpret_cast<int32_t*>(b + oQNext); t->result = reinterpret_cast<int32_t*>(b + oResult);
     t->readmit = b + oReadmit; t->staticExit = reinterpret_cast<int32_t*>(b + oStatic);
     t->counts = reinterpret_cast<int32_t*>(b + oCounts);
     t->hJobs.resize(J);
@@ -210,7 +212,7 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         F.assignBase = 0;
         const size_t jf = (size_t)f, jm = (size_t)B + f;
         F.qspan = t->qspan + jf * t->maxQ; F.qAccepted = t->qAccepted + jf * t->maxQ; F.qBin = t->qBin + jf * t->maxQ;
-        F.pool = t->pool + jf * t->poolPerJob; F.poolUsed = t->poolUsed + jf; F.result = t->result + jf * 4;
+        F.pool = t->pool + jf * t->poolPerJob; F.poolUsed = t->poolUsed + jf; F.qNext = t->qNext + jf; F.result = t->result + jf * 4;
         t->hJobs[f] = F;
 
         MatchJob M = J;                      /* SearchByProjection(Frame, vpMapPoints, th) */
@@ -218,8 +220,9 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         M.queries = in->map_points + (size_t)f * in->map_stride;
         M.nqPtr = in->n_map + f; M.nq = in->map_stride;
         M.th = in->th_map; M.nnratio = in->nnratio_map; M.assignBase = in->last_stride;
+        M.qperm = t->qperm + (size_t)f * t->maxQ;
         M.qspan = t->qspan + jm * t->maxQ; M.qAccepted = t->qAccepted + jm * t->maxQ; M.qBin = t->qBin + jm * t->maxQ;
-        M.pool = t->pool + jm * t->poolPerJob; M.poolUsed = t->poolUsed + jm; M.result = t->result + jm * 4;
+        M.pool = t->pool + jm * t->poolPerJob; M.poolUsed = t->poolUsed + jm; M.qNext = t->qNext + jm; M.result = t->result + jm * 4;
         t->hJobs[B + f] = M;
     }
     {
@@ -228,20 +231,21 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         TCU(c, cudaMemsetAsync(t->block + t->zeroFrom, 0, t->zeroBytes, st));
         TCU(c, cudaMemcpyAsync(t->dJobs, t->hJobs.data(), t->hJobs.size() * sizeof(MatchJob), cudaMemcpyHostToDevice, st));
         TCU(c, launch_grid_build(t->dJobs, nframes, st));
+        if (in->map_stride > 0) TCU(c, launch_query_order(t->dJobs + B, nframes, st));
         /* candidate generation only applies static gates, so both searches of every frame go out in ONE launch
          * when their jobs are contiguous (full batch); the claims are then resolved frame search first */
         const bool both = in->last_stride > 0 && in->map_stride > 0 && nframes == B;
         if (both)
-            TCU(c, launch_match_candidates(t->dJobs, 2 * B, std::max(in->last_stride, in->map_stride), st));
+            TCU(c, launch_match_candidates(t->dJobs, 2 * B, std::max(in->last_stride, in->map_stride), cap, st));
         if (in->last_stride > 0) {
-            if (!both) TCU(c, launch_match_candidates(t->dJobs, nframes, in->last_stride, st));
+            if (!both) TCU(c, launch_match_candidates(t->dJobs, nframes, in->last_stride, cap, st));
             TCU(c, launch_match_resolve(t->dJobs, nframes, MM_FRAME, cap, in->last_stride, st));
         }
         if (in->map_stride > 0) {
-            if (!both) TCU(c, launch_match_candidates(t->dJobs + B, nframes, in->map_stride, st));
+            if (!both) TCU(c, launch_match_candidates(t->dJobs + B, nframes, in->map_stride, cap, st));
             TCU(c, launch_match_resolve(t->dJobs + B, nframes, MM_MAP, cap, in->map_stride, st));
         }
-        c->launches += 3 + (in->last_stride > 0 ? 2 : 0) + (in->map_stride > 0 ? 2 : 0);
+        c->launches += 3 + (in->last_stride > 0 ? 2 : 0) + (in->map_stride > 0 ? 3 : 0);
     }
     {
         StageTimer tm(c, st, SDYN_STAGE_DYNAMIC);

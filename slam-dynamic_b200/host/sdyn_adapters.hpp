@@ -176,6 +176,19 @@ inline int SearchByBoW(sdyn_ctx* ctx, KeyFrameT* pKF, FrameT& F, std::vector<Map
     return n;
 }
 
+/* Frame::ComputeStereoMatches() — reference: src/Frame.cc:874-1048.  Called where the reference calls it, right
+ * after the two ExtractORB threads joined (src/Frame.cc:151-160): it works on the keypoints, descriptors and
+ * pyramids the left / right ORBextractor contexts still hold on the device, so mvImagePyramid is not read on the host. */
+template <class FrameT>
+inline bool ComputeStereoMatches(FrameT& F)
+{
+    F.mvuRight.assign(F.N, -1.0f);
+    F.mvDepth.assign(F.N, -1.0f);
+    if (F.N == 0) return true;
+    return sdyn_stereo_match(F.mpORBextractorLeft->Context(), F.mpORBextractorRight->Context(), 1, F.mb, F.mbf,
+                             F.mvuRight.data(), F.mvDepth.data(), F.N, nullptr) == SDYN_OK;
+}
+
 /* Frame::firstSeparate (src/Frame.cc:555-604): the keypoint-in-box test runs on the device; the reorder and
  * the reference's box bookkeeping (incl. its erase-while-iterating behaviour) stay host code in Frame. */
 template <class KeyPointT, class RectT>

@@ -3,6 +3,7 @@
 #pragma once
 #include "opencv2/core/core.hpp"
 #include <map>
+namespace ORB_SLAM2 { class ORBextractor; }
 #include <vector>
 
 namespace ref_stub {
@@ -22,7 +23,10 @@ public:
     int N = 0, mnScaleLevels = 8;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
     cv::Mat mDescriptors, mTcw;
-    std::vector<float> mvuRight, mvScaleFactors;
+    std::vector<float> mvuRight, mvDepth, mvScaleFactors;
+    std::vector<cv::KeyPoint> mvKeysRight;
+    cv::Mat mDescriptorsRight;
+    ORB_SLAM2::ORBextractor* mpORBextractorLeft = nullptr; ORB_SLAM2::ORBextractor* mpORBextractorRight = nullptr;
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<bool> mvbOutlier;
     std::map<unsigned, std::vector<unsigned>> mFeatVec;

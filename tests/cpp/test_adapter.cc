@@ -119,6 +119,21 @@ int main(int argc, char** argv)
         assign2[i] = (p >= mps.data() && p < mps.data() + nmp) ? 100000 + (int)(p - mps.data()) : (int)(p - pts.data());
     }
     dump("map_n", &n2, 4); dump("map_assign", assign2.data(), assign2.size() * 4);
+
+    /* stereo constructor path (src/Frame.cc:151-160): left and right extraction, then ComputeStereoMatches */
+    {
+        cv::Mat imgR(H, W, CV_8UC1);
+        sdyn_synth_frame(1007, 2001, W, H, 120, 4 + 9, 1, 1, imgR.data, W);     /* img1 content, 9 px disparity */
+        ORB_SLAM2::ORBextractor exL(1000, 1.2f, 8, 20, 7), exR(1000, 1.2f, 8, 20, 7);
+        Frame S;
+        fill_frame(S, exL, img1);
+        exR(imgR, cv::Mat(), S.mvKeysRight, S.mDescriptorsRight);
+        S.mpORBextractorLeft = &exL; S.mpORBextractorRight = &exR;
+        if (!sdyn_host::ComputeStereoMatches(S)) { fprintf(stderr, "stereo failed: %s\n", sdyn_last_error(exL.Context())); return 1; }
+        dump("imgR", imgR.data, (size_t)W * H);
+        dump("stereo_uright", S.mvuRight.data(), S.mvuRight.size() * 4);
+        dump("stereo_depth", S.mvDepth.data(), S.mvDepth.size() * 4);
+    }
     fclose(g_out);
     printf("adapter ok: %d keypoints, %d frame matches, %d map matches\n", cur.N, n1, n2);
     return 0;

@@ -75,3 +75,13 @@ def test_adapter_classes_match_oracle(tmp_path):
     expect = np.where(a2 >= 0, 100000 + a2, np.where(a2 == -2, a1, -1)).astype(np.int32)
     assert struct.unpack("<i", d["map_n"])[0] == n2 and n2 > 50
     assert np.array_equal(np.frombuffer(d["map_assign"], np.int32), expect)
+
+    # stereo constructor path: Frame::ComputeStereoMatches through the adapter
+    imgR = np.frombuffer(d["imgR"], np.uint8).reshape(H, W)
+    EL, ER = orc.Extractor(1000, 1.2, 8, 20, 7), orc.Extractor(1000, 1.2, 8, 20, 7)
+    kl, dl = EL(img1); kr, dr = ER(imgR)
+    mbf = np.float32(379.8145); mb = mbf / np.float32(cam["fx"])
+    ur, dp, kept = orc.stereo_matches(EL, ER, kl, dl, kr, dr, float(mb), float(mbf))
+    assert kept > 200
+    assert np.array_equal(np.frombuffer(d["stereo_uright"], np.float32).view(np.uint32), ur.view(np.uint32))
+    assert np.array_equal(np.frombuffer(d["stereo_depth"], np.float32).view(np.uint32), dp.view(np.uint32))
