@@ -260,7 +260,8 @@ int sdyn_dyn_separate(sdyn_ctx* ctx, sdyn_box_pair* pairs, int npairs, const flo
  * Searches see every extracted keypoint (the stereo constructor's behaviour, where firstSeparate is disabled,
  * src/Frame.cc:166).  All pointers are DEVICE pointers; per-frame arrays are `*_stride` elements apart. */
 typedef struct {
-    /* LastFrame of every current frame */
+    /* LastFrame of every current frame.  last_keys_un may be NULL or equal to last_keys (mvKeysUn == mvKeys for an
+     * undistorted camera, src/Frame.cc:814-818): the host-buffer entry points then upload the array once. */
     const sdyn_last_point* last_points; const sdyn_keypoint* last_keys; const sdyn_keypoint* last_keys_un;
     const int32_t* n_last; int32_t last_stride;
     /* local map of every current frame */

@@ -158,7 +158,7 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
     if (!c) return SDYN_ERR_ARG;
     if (!in || nframes < 1 || nframes > c->maxBatch || !dGray || W < 1 || H < 1 || stride < W || in->last_stride < 0 ||
         in->map_stride < 0 || in->ref_stride < 0 || !(in->max_x > in->min_x) || !(in->max_y > in->min_y) ||
-        (in->last_stride > 0 && (!in->last_points || !in->last_keys || !in->last_keys_un || !in->n_last)) ||
+        (in->last_stride > 0 && (!in->last_points || !in->last_keys || !in->n_last)) ||
         (in->map_stride > 0 && (!in->map_points || !in->n_map)) || !in->boxes || !in->n_boxes || !in->ref_box ||
         !in->ref_off || !in->fmat || c->maxKp > 65535)
         return api_fail(c, SDYN_ERR_ARG, "sdyn_track_batch_device: bad argument");
@@ -206,7 +206,8 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         MatchJob F = J;                      /* SearchByProjection(CurrentFrame, LastFrame, th, bMono) */
         F.mode = MM_FRAME;
         F.queries = in->last_points + (size_t)f * in->last_stride;
-        F.qKeys = in->last_keys + (size_t)f * in->last_stride; F.qKeysUn = in->last_keys_un + (size_t)f * in->last_stride;
+        F.qKeys = in->last_keys + (size_t)f * in->last_stride;
+        F.qKeysUn = (in->last_keys_un ? in->last_keys_un : in->last_keys) + (size_t)f * in->last_stride;
         F.nqPtr = in->n_last + f; F.nq = in->last_stride;
         F.th = in->th_frame; F.checkOri = in->check_orientation; F.forward = forward; F.backward = backward;
         F.assignBase = 0;
@@ -284,7 +285,8 @@ int sdyn_track_batch_async(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t
     Item items[] = {
         {in->last_points, (size_t)in->last_stride * sizeof(sdyn_last_point), 0},
         {in->last_keys, (size_t)in->last_stride * sizeof(sdyn_keypoint), 0},
-        {in->last_keys_un, (size_t)in->last_stride * sizeof(sdyn_keypoint), 0},
+        /* mvKeysUn == mvKeys for an undistorted camera (src/Frame.cc:814-818): one upload serves both */
+        {(in->last_keys_un && in->last_keys_un != in->last_keys) ? in->last_keys_un : nullptr, (size_t)in->last_stride * sizeof(sdyn_keypoint), 0},
         {in->n_last, 4, 0},
         {in->map_points, (size_t)in->map_stride * sizeof(sdyn_mappoint_query), 0},
         {in->n_map, 4, 0},
@@ -312,7 +314,7 @@ int sdyn_track_batch_async(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t
     sdyn_track_inputs d = *in;
     d.last_points = reinterpret_cast<const sdyn_last_point*>(t->inBlock + items[0].off);
     d.last_keys = reinterpret_cast<const sdyn_keypoint*>(t->inBlock + items[1].off);
-    d.last_keys_un = reinterpret_cast<const sdyn_keypoint*>(t->inBlock + items[2].off);
+    d.last_keys_un = items[2].src ? reinterpret_cast<const sdyn_keypoint*>(t->inBlock + items[2].off) : d.last_keys;
     d.n_last = reinterpret_cast<const int32_t*>(t->inBlock + items[3].off);
     d.map_points = reinterpret_cast<const sdyn_mappoint_query*>(t->inBlock + items[4].off);
     d.n_map = reinterpret_cast<const int32_t*>(t->inBlock + items[5].off);
