@@ -183,6 +183,33 @@ typedef struct {
     uint8_t desc[32];               /* pMP->GetDescriptor() */
 } sdyn_last_point;
 
+/* MapPoint fields read by the two pose-projection searches (src/ORBmatcher.cc:290-403, 1629-1756). */
+typedef struct {
+    uint8_t valid, pad[3];          /* pMP != NULL && !isBad() && not in sAlreadyFound / spAlreadyFound */
+    float world[3];                 /* GetWorldPos() */
+    float normal[3];                /* GetNormal() (KeyFrame/Scw overload only) */
+    float min_distance, max_distance;   /* GetMinDistanceInvariance(), GetMaxDistanceInvariance() */
+    float max_distance_raw;         /* mfMaxDistance, the numerator of MapPoint::PredictScale (src/MapPoint.cc:385-418) */
+    float angle;                    /* Frame/KeyFrame overload: pKF->mvKeysUn[i].angle */
+    uint8_t desc[32];               /* GetDescriptor() */
+} sdyn_proj_point;
+
+enum { SDYN_PROJ_FRAME_KEYFRAME = 0,   /* SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*>&, th, ORBdist) */
+       SDYN_PROJ_KEYFRAME_SIM3 = 1 };  /* SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vpMatched, th) */
+
+/* Pose and thresholds of one pose-projection search.  rcw / tcw / ow are the values of the reference's own host
+ * expressions (Rcw, tcw, Ow = -Rcw.t()*tcw; for the Scw overload after dividing by the scale, :300-304) — the
+ * adapter evaluates them with cv::Mat exactly as the reference does and passes the floats. */
+typedef struct {
+    float rcw[9], tcw[3], ow[3];
+    float th;                       /* search radius factor (the int th of the Scw overload converted to float) */
+    int32_t max_descriptor_distance;/* ORBdist, or TH_LOW for the Scw overload */
+    int32_t variant;                /* SDYN_PROJ_* */
+    int32_t check_orientation;      /* mbCheckOrientation (Frame/KeyFrame overload only) */
+    float log_scale_factor;         /* mfLogScaleFactor of the searched frame */
+    int32_t nlevels;                /* mnScaleLevels of the searched frame */
+} sdyn_proj_params;
+
 /* DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>, Thirdparty/DBoW2/DBoW2/FeatureVector.h:22)
  * flattened to CSR with ascending node ids. */
 typedef struct {
@@ -210,6 +237,15 @@ int sdyn_match_projection_frame(sdyn_ctx* ctx, const sdyn_frame_view* cur, const
                                 const sdyn_last_point* last_points, float th, int mono, int check_orientation,
                                 int32_t* assign, uint8_t* locked, int* nmatches, float* pairs, int* npairs);
 
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist),
+ * src/ORBmatcher.cc:1629-1756 (relocalisation, Tracking.cc:2323,2337) and
+ * ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th),
+ * src/ORBmatcher.cc:290-403 (loop closing, LoopClosing.cc:376).  target: the frame / keyframe whose keypoints are
+ * searched (grid bounds, intrinsics, mvKeysUn, descriptors).  assign in: -1 = keypoint free, anything else =
+ * occupied (mvpMapPoints[i] / vpMatched[i] != NULL); out: index into pts of the point that took the keypoint. */
+int sdyn_match_projection_pose(sdyn_ctx* ctx, const sdyn_frame_view* target, const sdyn_proj_point* pts, int npts,
+                               const sdyn_proj_params* params, int32_t* assign, int* nmatches);
+
 /* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:562-677.
  * prev_matched: f1->n x 2 floats, updated in place; matches12: f1->n. */
 int sdyn_match_init(sdyn_ctx* ctx, const sdyn_frame_view* f1, const sdyn_frame_view* f2, float* prev_matched,
@@ -220,6 +256,13 @@ int sdyn_match_init(sdyn_ctx* ctx, const sdyn_frame_view* f1, const sdyn_frame_v
 int sdyn_match_bow(sdyn_ctx* ctx, const sdyn_frame_view* kf, const uint8_t* kf_valid,
                    const sdyn_feature_vector* kf_fv, const sdyn_frame_view* f, const sdyn_feature_vector* f_fv,
                    float nnratio, int check_orientation, int32_t* assign, int* nmatches);
+
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12), src/ORBmatcher.cc:679-812
+ * (LoopClosing.cc:266).  valid1[i] / valid2[i]: feature i of that keyframe has a MapPoint that is not bad.
+ * matches12[i1] = index of the matched KeyFrame-2 feature (vpMatches12[i1] = vpMapPoints2[that index]) or -1. */
+int sdyn_match_bow_kf(sdyn_ctx* ctx, const sdyn_frame_view* kf1, const uint8_t* valid1, const sdyn_feature_vector* fv1,
+                      const sdyn_frame_view* kf2, const uint8_t* valid2, const sdyn_feature_vector* fv2, float nnratio,
+                      int check_orientation, int32_t* matches12, int* nmatches);
 
 /* ---- dynamic-keypoint rejection ---------------------------------------------------------------------
  * Frame::firstSeparate's keypoint-in-box test (src/Frame.cc:555-572): bit b of mask[i] is set iff

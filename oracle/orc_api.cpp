@@ -157,6 +157,27 @@ int orc_match_bow(const sdyn_frame_view* kf, const uint8_t* kfValid, const sdyn_
     return search_by_bow(a, kfValid, va, b, vb, nnratio, checkOri != 0, assign);
 }
 
+int orc_match_bow_kf(const sdyn_frame_view* kf1, const uint8_t* valid1, const sdyn_feature_vector* fa, const sdyn_frame_view* kf2,
+                     const uint8_t* valid2, const sdyn_feature_vector* fb, float nnratio, int checkOri, int32_t* matches12)
+{
+    FrameView a = view_of(kf1), b = view_of(kf2);
+    FeatureVec va{fa->nnodes, fa->node_id, fa->offset, fa->index}, vb{fb->nnodes, fb->node_id, fb->offset, fb->index};
+    return search_by_bow_kf(a, valid1, va, b, valid2, vb, nnratio, checkOri != 0, matches12);
+}
+
+static_assert(sizeof(ProjPoint) == sizeof(sdyn_proj_point), "layout");
+int orc_match_projection_pose(const sdyn_frame_view* target, const sdyn_proj_point* pts, int npts, const sdyn_proj_params* prm,
+                              int32_t* assign)
+{
+    FrameView t = view_of(target); Grid g; assign_features_to_grid(t, g);
+    const ProjPoint* pp = reinterpret_cast<const ProjPoint*>(pts);
+    if (prm->variant == SDYN_PROJ_FRAME_KEYFRAME)
+        return search_by_projection_reloc(t, g, pp, npts, prm->rcw, prm->tcw, prm->ow, prm->th, prm->max_descriptor_distance,
+                                          prm->check_orientation != 0, prm->log_scale_factor, prm->nlevels, assign);
+    return search_by_projection_sim3(t, g, pp, npts, prm->rcw, prm->tcw, prm->ow, (int)prm->th, prm->log_scale_factor,
+                                     prm->nlevels, assign);
+}
+
 /* ---- dynamic ----------------------------------------------------------------------------------- */
 void orc_box_mask(const sdyn_keypoint* keys, int n, const double* boxes, int nboxes, uint64_t* mask)
 {

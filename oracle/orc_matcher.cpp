@@ -328,4 +328,162 @@ int search_by_bow(const FrameView& KF, const uint8_t* kfValid, const FeatureVec&
     return nmatches;
 }
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12) — src/ORBmatcher.cc:679-812.
+ * valid1 / valid2 stand for "vpMapPoints[idx] != NULL && !isBad()"; matches12[i1] = index into KeyFrame 2 or -1. */
+int search_by_bow_kf(const FrameView& KF1, const uint8_t* valid1, const FeatureVec& a, const FrameView& KF2,
+                     const uint8_t* valid2, const FeatureVec& b, float nnratio, bool checkOri, int32_t* matches12)
+{
+    std::fill(matches12, matches12 + KF1.N, -1);                       /* :691 */
+    std::vector<bool> vbMatched2(KF2.N, false);                         /* :692 */
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0;
+    int ia = 0, ib = 0;
+    while (ia < a.nnodes && ib < b.nnodes) {                            /* :707 */
+        if (a.nodeId[ia] == b.nodeId[ib]) {
+            for (int p = a.offset[ia]; p < a.offset[ia + 1]; ++p) {
+                const unsigned idx1 = a.index[p];
+                if (!valid1[idx1]) continue;                            /* :715-719 */
+                const uint8_t* d1 = KF1.desc + 32 * (size_t)idx1;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int q = b.offset[ib]; q < b.offset[ib + 1]; ++q) {
+                    const unsigned idx2 = b.index[q];
+                    if (vbMatched2[idx2] || !valid2[idx2]) continue;     /* :733-737 */
+                    const int dist = descriptor_distance(d1, KF2.desc + 32 * (size_t)idx2);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = (int)idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW) {                               /* :755 — strict, unlike the KeyFrame-Frame overload */
+                    if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                        matches12[idx1] = bestIdx2;
+                        vbMatched2[bestIdx2] = true;
+                        if (checkOri) rotHist[rot_bin(KF1.keysUn[idx1].angle - KF2.keysUn[bestIdx2].angle)].push_back((int)idx1);
+                        ++nmatches;
+                    }
+                }
+            }
+            ++ia; ++ib;
+        } else if (a.nodeId[ia] < b.nodeId[ib]) {
+            ia = (int)(std::lower_bound(a.nodeId, a.nodeId + a.nnodes, b.nodeId[ib]) - a.nodeId);
+        } else {
+            ib = (int)(std::lower_bound(b.nodeId, b.nodeId + b.nnodes, a.nodeId[ia]) - b.nodeId);
+        }
+    }
+    if (checkOri) {                                                     /* :790-809 */
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { matches12[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+/* cv::norm(3x1 CV_32F) and Mat::dot of two 3x1 CV_32F: products of the float elements accumulated in double */
+static inline double norm3(const float* p) { double s = 0; for (int k = 0; k < 3; ++k) { const double v = p[k]; s += v * v; } return std::sqrt(s); }
+static inline double dot3(const float* a, const float* b) { double r = 0; for (int k = 0; k < 3; ++k) r += (double)a[k] * b[k]; return r; }
+
+/* MapPoint::PredictScale, src/MapPoint.cc:385-418 (`log` resolves to the float overload) */
+static inline int predict_scale(float mfMaxDistance, float currentDist, float mfLogScaleFactor, int mnScaleLevels)
+{
+    const float ratio = mfMaxDistance / currentDist;
+    int nScale = (int)std::ceil(std::log(ratio) / mfLogScaleFactor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= mnScaleLevels) nScale = mnScaleLevels - 1;
+    return nScale;
+}
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+ * src/ORBmatcher.cc:1629-1756.  Rcw/tcw/Ow: the three cv::Mat values of :1633-1635 as computed by the caller. */
+int search_by_projection_reloc(const FrameView& Cur, const Grid& gCur, const ProjPoint* pts, int npts, const float* Rcw,
+                               const float* tcw, const float* Ow, float th, int ORBdist, bool checkOri,
+                               float mfLogScaleFactor, int mnScaleLevels, int32_t* assign)
+{
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    float T[12];
+    for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) T[4 * r + k] = Rcw[3 * r + k]; T[4 * r + 3] = tcw[r]; }
+    for (int i = 0; i < npts; ++i) {
+        if (!pts[i].valid) continue;                                    /* :1649-1652 */
+        float pc[3];
+        rx_plus_t(T, pts[i].world, pc);                                 /* x3Dc = Rcw*x3Dw+tcw */
+        const float xc = pc[0], yc = pc[1];
+        const float invzc = (float)(1.0 / pc[2]);
+        const float u = Cur.fx * xc * invzc + Cur.cx;
+        const float v = Cur.fy * yc * invzc + Cur.cy;
+        if (u < Cur.minX || u > Cur.maxX) continue;
+        if (v < Cur.minY || v > Cur.maxY) continue;
+        float PO[3];
+        for (int k = 0; k < 3; ++k) PO[k] = pts[i].world[k] - Ow[k];
+        const float dist3D = (float)norm3(PO);                          /* :1672 */
+        if (dist3D < pts[i].minDistance || dist3D > pts[i].maxDistance) continue;
+        const int nPredictedLevel = predict_scale(pts[i].maxDistanceRaw, dist3D, mfLogScaleFactor, mnScaleLevels);
+        const float radius = th * Cur.scaleFactors[nPredictedLevel];
+        const std::vector<int> vIndices2 = features_in_area(Cur, gCur, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1);
+        if (vIndices2.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (assign[i2] != -1) continue;                             /* CurrentFrame.mvpMapPoints[i2] */
+            const int dist = descriptor_distance(pts[i].desc, Cur.desc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= ORBdist) {                                      /* :1716 */
+            assign[bestIdx2] = i;
+            ++nmatches;
+            if (checkOri) rotHist[rot_bin(pts[i].angle - Cur.keysUn[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {                                                     /* :1736-1753 */
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { assign[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)
+ * src/ORBmatcher.cc:290-403.  Rcw/tcw/Ow: the values of :300-304 (sRcw/scw, t/scw, -Rcw.t()*tcw) from the caller.
+ * KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:569-608) is Frame's without a level check. */
+int search_by_projection_sim3(const FrameView& KF, const Grid& gKF, const ProjPoint* pts, int npts, const float* Rcw,
+                              const float* tcw, const float* Ow, int th, float mfLogScaleFactor, int mnScaleLevels, int32_t* assign)
+{
+    int nmatches = 0;
+    float T[12];
+    for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) T[4 * r + k] = Rcw[3 * r + k]; T[4 * r + 3] = tcw[r]; }
+    for (int iMP = 0; iMP < npts; ++iMP) {
+        if (!pts[iMP].valid) continue;                                  /* isBad() || spAlreadyFound.count(pMP), :316 */
+        float p3Dc[3];
+        rx_plus_t(T, pts[iMP].world, p3Dc);
+        if (p3Dc[2] < 0.0) continue;                                    /* :325 */
+        const float invz = 1 / p3Dc[2];
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float u = KF.fx * x + KF.cx, v = KF.fy * y + KF.cy;
+        if (!(u >= KF.minX && u < KF.maxX && v >= KF.minY && v < KF.maxY)) continue;    /* KeyFrame::IsInImage */
+        float PO[3];
+        for (int k = 0; k < 3; ++k) PO[k] = pts[iMP].world[k] - Ow[k];
+        const float dist = (float)norm3(PO);
+        if (dist < pts[iMP].minDistance || dist > pts[iMP].maxDistance) continue;
+        if (dot3(PO, pts[iMP].normal) < 0.5 * dist) continue;           /* :350 */
+        const int nPredictedLevel = predict_scale(pts[iMP].maxDistanceRaw, dist, mfLogScaleFactor, mnScaleLevels);
+        const float radius = th * KF.scaleFactors[nPredictedLevel];
+        const std::vector<int> vIndices = features_in_area(KF, gKF, u, v, radius, -1, -1);
+        if (vIndices.empty()) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (assign[idx] != -1) continue;                            /* vpMatched[idx] */
+            const int kpLevel = KF.keysUn[idx].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const int d = descriptor_distance(pts[iMP].desc, KF.desc + 32 * (size_t)idx);
+            if (d < bestDist) { bestDist = d; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) { assign[bestIdx] = iMP; ++nmatches; }  /* :393 */
+    }
+    return nmatches;
+}
+
 }  // namespace orc

@@ -68,6 +68,22 @@ int search_by_projection_frame(const FrameView& Cur, const Grid& gCur, const Fra
 int search_for_initialization(const FrameView& F1, const FrameView& F2, const Grid& g2, float* prevMatched,
                               int32_t* matches12, int windowSize, float nnratio, bool checkOri);
 
+struct ProjPoint {              /* MapPoint fields of the pose-projection searches; layout of sdyn_proj_point */
+    uint8_t valid, pad[3];
+    float world[3], normal[3];
+    float minDistance, maxDistance; /* GetMinDistanceInvariance(), GetMaxDistanceInvariance() */
+    float maxDistanceRaw;           /* mfMaxDistance */
+    float angle;                    /* pKF->mvKeysUn[i].angle */
+    uint8_t desc[32];
+};
+/* ORBmatcher.cc:1629-1756 */
+int search_by_projection_reloc(const FrameView& Cur, const Grid& gCur, const ProjPoint* pts, int npts, const float* Rcw,
+                               const float* tcw, const float* Ow, float th, int ORBdist, bool checkOri,
+                               float mfLogScaleFactor, int mnScaleLevels, int32_t* assign);
+/* ORBmatcher.cc:290-403 */
+int search_by_projection_sim3(const FrameView& KF, const Grid& gKF, const ProjPoint* pts, int npts, const float* Rcw,
+                              const float* tcw, const float* Ow, int th, float mfLogScaleFactor, int mnScaleLevels, int32_t* assign);
+
 struct FeatureVec {             /* DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>> as CSR */
     int nnodes = 0;
     const uint32_t* nodeId = nullptr;   /* ascending */
@@ -79,6 +95,9 @@ struct FeatureVec {             /* DBoW2::FeatureVector = std::map<NodeId, std::
  * assign[fIdx] = kfIdx | -1. */
 int search_by_bow(const FrameView& KF, const uint8_t* kfValid, const FeatureVec& fvKF, const FrameView& F,
                   const FeatureVec& fvF, float nnratio, bool checkOri, int32_t* assign);
+/* ORBmatcher.cc:679-812 */
+int search_by_bow_kf(const FrameView& KF1, const uint8_t* valid1, const FeatureVec& fv1, const FrameView& KF2,
+                     const uint8_t* valid2, const FeatureVec& fv2, float nnratio, bool checkOri, int32_t* matches12);
 
 /* ORBmatcher.cc:1758-1799 */
 void compute_three_maxima(const int* histoSizes, int L, int& ind1, int& ind2, int& ind3);

@@ -248,6 +248,54 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
                 gateX = __fsub_rn(x, __fmul_rn(J.bf, invzc));    /* ur = u - mbf*invzc */
                 load_desc(lp->desc, qd);
             }
+        } else if (J.mode == MM_POSE) {
+            /* SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist) :1629-1756 (variant 0) and
+             * SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) :290-403 (variant 1) */
+            const sdyn_proj_point* pp = reinterpret_cast<const sdyn_proj_point*>(J.queries) + q;
+            active = pp->valid;
+            if (active) {
+                float pc[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float s = __fadd_rn(__fadd_rn(__fmul_rn(J.Tcw[4 * k], pp->world[0]), __fmul_rn(J.Tcw[4 * k + 1], pp->world[1])),
+                                              __fmul_rn(J.Tcw[4 * k + 2], pp->world[2]));
+                    pc[k] = __fadd_rn(s, J.Tcw[4 * k + 3]);
+                }
+                if (J.poseVariant == SDYN_PROJ_FRAME_KEYFRAME) {
+                    const float invzc = (float)(1.0 / (double)pc[2]);
+                    x = __fadd_rn(__fmul_rn(__fmul_rn(J.fx, pc[0]), invzc), J.cx);
+                    y = __fadd_rn(__fmul_rn(__fmul_rn(J.fy, pc[1]), invzc), J.cy);
+                    if (x < J.minX || x > J.maxX || y < J.minY || y > J.maxY) active = false;
+                } else {
+                    if ((double)pc[2] < 0.0) active = false;
+                    const float invz = __fdiv_rn(1.0f, pc[2]);
+                    x = __fadd_rn(__fmul_rn(J.fx, __fmul_rn(pc[0], invz)), J.cx);
+                    y = __fadd_rn(__fmul_rn(J.fy, __fmul_rn(pc[1], invz)), J.cy);
+                    if (!(x >= J.minX && x < J.maxX && y >= J.minY && y < J.maxY)) active = false;    /* KeyFrame::IsInImage */
+                }
+                /* PO = p3Dw - Ow; cv::norm / Mat::dot accumulate float products in double */
+                const float po0 = __fsub_rn(pp->world[0], J.Ow[0]), po1 = __fsub_rn(pp->world[1], J.Ow[1]), po2 = __fsub_rn(pp->world[2], J.Ow[2]);
+                const double n2 = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)po0), __dmul_rn((double)po1, (double)po1)),
+                                            __dmul_rn((double)po2, (double)po2));
+                const float dist = (float)sqrt(n2);
+                if (dist < pp->min_distance || dist > pp->max_distance) active = false;
+                if (J.poseVariant == SDYN_PROJ_KEYFRAME_SIM3) {
+                    const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)pp->normal[0]), __dmul_rn((double)po1, (double)pp->normal[1])),
+                                                 __dmul_rn((double)po2, (double)pp->normal[2]));
+                    if (dot < 0.5 * (double)dist) active = false;       /* PO.dot(Pn) < 0.5*dist, in double */
+                }
+                if (active) {
+                    /* MapPoint::PredictScale: ceil(log(ratio) / mfLogScaleFactor) in float; the float logarithm is the
+                     * correctly rounded value of the double one (glibc's logf in all but boundary-free cases) */
+                    const float ratio = __fdiv_rn(pp->max_distance_raw, dist);
+                    int nScale = (int)ceilf(__fdiv_rn((float)log((double)ratio), J.logScaleFactor));
+                    nScale = nScale < 0 ? 0 : (nScale >= J.predLevels ? J.predLevels - 1 : nScale);
+                    r = __fmul_rn(J.th, J.scale[nScale]);
+                    minLevel = nScale - 1;
+                    maxLevel = J.poseVariant == SDYN_PROJ_FRAME_KEYFRAME ? nScale + 1 : nScale;
+                    load_desc(pp->desc, qd);
+                }
+            }
         } else if (J.mode == MM_MAP) {
             const sdyn_mappoint_query* mp = reinterpret_cast<const sdyn_mappoint_query*>(J.queries) + q;
             active = mp->track_in_view && !mp->bad;
@@ -315,7 +363,7 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
         /* bCheckLevels = (minLevel > 0) || (maxLevel >= 0); kept iff oct >= minLevel and (maxLevel < 0 or oct <= maxLevel) */
         const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
         const int loLevel = checkLevels ? minLevel : -0x7fffffff, hiLevel = (checkLevels && maxLevel >= 0) ? maxLevel : 0x7fffffff;
-        const float* __restrict__ uRight = J.mode != MM_INIT ? J.uRight : nullptr;
+        const float* __restrict__ uRight = (J.mode == MM_FRAME || J.mode == MM_MAP) ? J.uRight : nullptr;
         const bool stereoGate = uRight != nullptr;
         /* Pass 1: walk the spans and keep what survives the level / window / stereo gates.  The entries of a span are
          * fetched four at a time before any of them is tested, so four loads are in flight per thread instead of one
@@ -418,7 +466,8 @@ k_match_resolve(const MatchJob* __restrict__ jobs)
                 ok = bestDist <= SDYN_TH_HIGH &&
                      !(rec_level(r1) == bestLevel2 && (float)bestDist > __fmul_rn(J.nnratio, (float)bestDist2));
             else if (J.mode == MM_INIT) ok = bestDist <= SDYN_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, J.nnratio);
-            else ok = bestDist <= SDYN_TH_LOW && (float)bestDist < __fmul_rn(J.nnratio, (float)bestDist2);
+            else ok = (J.strictLow ? bestDist < SDYN_TH_LOW : bestDist <= SDYN_TH_LOW) &&
+                      (float)bestDist < __fmul_rn(J.nnratio, (float)bestDist2);
             if (ok) {
                 accepted = bestIdx;
                 float rot = 0.f;
@@ -523,6 +572,11 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
     constexpr uint32_t NONE = 0xffffffffu;
     const sdyn_last_point* lps = reinterpret_cast<const sdyn_last_point*>(J.queries);
     const sdyn_mappoint_query* mps = reinterpret_cast<const sdyn_mappoint_query*>(J.queries);
+    const sdyn_proj_point* pps = reinterpret_cast<const sdyn_proj_point*>(J.queries);
+    const bool frameLike = J.mode == MM_FRAME || J.mode == MM_POSE;      /* best-only acceptance + rotation histogram */
+    /* does query q lock the keypoint it takes (the MapPoint has observations; every claim of the pose searches does) */
+    auto locks = [&](int q) -> bool { return J.mode == MM_FRAME ? lps[q].obs_positive : (J.mode == MM_POSE ? true : mps[q].obs_positive); };
+    auto query_angle = [&](int q) -> float { return J.mode == MM_POSE ? pps[q].angle : J.qKeysUn[q].angle; };
 
     for (int q = tid; q < nq; q += RF) acc[q] = -2;
     for (int sweep = 0; sweep <= nq; ++sweep) {
@@ -532,8 +586,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
         if (sweep > 0)
             for (int q = tid; q < nq; q += RF) {
                 const int a = acc[q];
-                const bool obs = J.mode == MM_FRAME ? lps[q].obs_positive : mps[q].obs_positive;
-                if (a >= 0 && obs) atomicMin(&lockT[a], q);
+                if (a >= 0 && locks(q)) atomicMin(&lockT[a], q);
             }
         __syncthreads();
         int changed = 0;
@@ -555,7 +608,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
             if (a != NONE) {
                 const uint32_t r1 = J.pool[span.x + (a & 0xfffff)];
                 const int bestDist = (int)(a >> 20);
-                bool ok = bestDist <= SDYN_TH_HIGH;
+                bool ok = bestDist <= J.distTh;
                 if (ok && J.mode == MM_MAP) {
                     int bestDist2 = 256, bestLevel2 = -1;
                     if (b != NONE) { bestDist2 = (int)(b >> 20); bestLevel2 = rec_level(J.pool[span.x + (b & 0xfffff)]); }
@@ -576,11 +629,11 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
     int mine = 0;
     for (int q = tid; q < nq; q += RF) {
         const int a = acc[q];
-        if (a < 0) { if (J.mode == MM_FRAME) J.qBin[q] = -1; continue; }
+        if (a < 0) { if (frameLike) J.qBin[q] = -1; continue; }
         ++mine;
         atomicMax(&lockT[a], q);
-        if (J.mode == MM_FRAME && J.checkOri) {
-            float rot = __fsub_rn(J.qKeysUn[q].angle, J.keysUn[a].angle);
+        if (frameLike && J.checkOri) {
+            float rot = __fsub_rn(query_angle(q), J.keysUn[a].angle);
             if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
             int bin = (int)roundf(__fmul_rn(rot, 1.0f / SDYN_HISTO_LENGTH));
             if (bin == SDYN_HISTO_LENGTH) bin = 0;
@@ -594,7 +647,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
         const int q = lockT[k];
         if (q >= 0) {
             J.assign[k] = J.assignBase + q;
-            J.locked[k] = J.mode == MM_FRAME ? lps[q].obs_positive : mps[q].obs_positive;
+            J.locked[k] = locks(q);
         }
     }
     /* point pairs of the fork's overload, in query order (before the cull, Appendix B-8) */
@@ -619,7 +672,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
         }
     }
     __syncthreads();
-    if (J.mode == MM_FRAME && J.checkOri) {
+    if (frameLike && J.checkOri) {
         if (tid == 0) {
             int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
             for (int i = 0; i < SDYN_HISTO_LENGTH; ++i) {
@@ -682,7 +735,7 @@ cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQue
 
 cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st)
 {
-    if (mode == MM_FRAME || mode == MM_MAP) {
+    if (mode == MM_FRAME || mode == MM_MAP || mode == MM_POSE) {
         const size_t smem = (size_t)(maxN + maxQ) * sizeof(int);
         cudaError_t e = cudaFuncSetAttribute(k_match_resolve_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

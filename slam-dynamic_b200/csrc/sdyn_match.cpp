@@ -151,7 +151,7 @@ int sdyn_match_projection_map(sdyn_ctx* c, const sdyn_frame_view* f, const sdyn_
     const size_t fixed = (size_t)f->n * 100 + (size_t)nmp * sizeof(sdyn_mappoint_query) + (kGridCells + 1) * 4;
     return run_job(c, fixed, nmp, 64 * nmp, (int)std::min<long long>((long long)nmp * f->n, 1 << 30),
         [&](Arena& A, MatchJob& J) {
-            J.mode = MM_MAP;
+            J.mode = MM_MAP; J.distTh = SDYN_TH_HIGH;
             stage_frame(A, f, J, true);
             sdyn_mappoint_query* dq = A.take<sdyn_mappoint_query>(nmp);
             J.queries = dq; J.nq = nmp; J.th = th; J.nnratio = nnratio;
@@ -204,7 +204,7 @@ int sdyn_match_projection_frame(sdyn_ctx* c, const sdyn_frame_view* cur, const s
                          (kGridCells + 1) * 4;
     return run_job(c, fixed, nq, 64 * nq, (int)std::min<long long>((long long)nq * cur->n, 1 << 30),
         [&](Arena& A, MatchJob& J) {
-            J.mode = MM_FRAME;
+            J.mode = MM_FRAME; J.distTh = SDYN_TH_HIGH;
             stage_frame(A, cur, J, true);
             sdyn_last_point* dq = A.take<sdyn_last_point>(nq);
             sdyn_keypoint* dk = A.take<sdyn_keypoint>(nq);
@@ -231,6 +231,49 @@ int sdyn_match_projection_frame(sdyn_ctx* c, const sdyn_frame_view* cur, const s
             MCU(c, cudaStreamSynchronize(c->stream));
             *nmatches = res[0];
             if (npairs) *npairs = res[1];
+            return (int)SDYN_OK;
+        });
+}
+
+int sdyn_match_projection_pose(sdyn_ctx* c, const sdyn_frame_view* target, const sdyn_proj_point* pts, int npts,
+                               const sdyn_proj_params* prm, int32_t* assign, int* nmatches)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (bad_view(target) || npts < 0 || (npts > 0 && !pts) || !prm || !assign || !nmatches || !target->scale_factors ||
+        (prm->variant != SDYN_PROJ_FRAME_KEYFRAME && prm->variant != SDYN_PROJ_KEYFRAME_SIM3) || prm->nlevels < 1 ||
+        prm->nlevels > target->nlevels || !(prm->log_scale_factor > 0.0f) || prm->max_descriptor_distance < 0)
+        return api_fail(c, SDYN_ERR_ARG, "sdyn_match_projection_pose: bad argument");
+    *nmatches = 0;
+    if (npts == 0 || target->n == 0) return SDYN_OK;
+    std::vector<uint8_t> locked((size_t)target->n);
+    for (int i = 0; i < target->n; ++i) locked[i] = assign[i] != -1;      /* every occupant blocks (:362, :1701) */
+    const size_t fixed = (size_t)target->n * 100 + (size_t)npts * (sizeof(sdyn_proj_point) + 16) + (kGridCells + 1) * 4;
+    return run_job(c, fixed, npts, 64 * npts, (int)std::min<long long>((long long)npts * target->n, 1 << 30),
+        [&](Arena& A, MatchJob& J) {
+            J.mode = MM_POSE; J.poseVariant = prm->variant; J.distTh = prm->max_descriptor_distance;
+            stage_frame(A, target, J, true);
+            sdyn_proj_point* dq = A.take<sdyn_proj_point>(npts);
+            J.queries = dq; J.nq = npts; J.th = prm->th;
+            J.checkOri = prm->variant == SDYN_PROJ_FRAME_KEYFRAME && prm->check_orientation;
+            for (int r = 0; r < 3; ++r) {
+                for (int k = 0; k < 3; ++k) J.Tcw[4 * r + k] = prm->rcw[3 * r + k];
+                J.Tcw[4 * r + 3] = prm->tcw[r];
+                J.Ow[r] = prm->ow[r];
+            }
+            J.fx = target->fx; J.fy = target->fy; J.cx = target->cx; J.cy = target->cy;
+            J.logScaleFactor = prm->log_scale_factor; J.predLevels = prm->nlevels;
+            J.assign = A.take<int32_t>(target->n); J.locked = A.take<uint8_t>(target->n);
+            if (A.failed) return (int)SDYN_OK;
+            MCU(c, upload_frame(target, J, c->stream));
+            MCU(c, up(dq, pts, npts, c->stream));
+            MCU(c, up(J.assign, assign, target->n, c->stream));
+            MCU(c, up(J.locked, locked.data(), target->n, c->stream));
+            return (int)SDYN_OK;
+        },
+        [&](const MatchJob& J, const int32_t* res) {
+            MCU(c, down(assign, J.assign, target->n, c->stream));
+            MCU(c, cudaStreamSynchronize(c->stream));
+            *nmatches = res[0];
             return (int)SDYN_OK;
         });
 }
@@ -275,16 +318,18 @@ int sdyn_match_init(sdyn_ctx* c, const sdyn_frame_view* f1, const sdyn_frame_vie
         });
 }
 
-int sdyn_match_bow(sdyn_ctx* c, const sdyn_frame_view* kf, const uint8_t* kfValid, const sdyn_feature_vector* a,
-                   const sdyn_frame_view* f, const sdyn_feature_vector* b, float nnratio, int checkOri, int32_t* assign,
-                   int* nmatches)
+/* Shared body of the two BoW searches.  fValid (nullable): searched features that may be matched at all; strictLow:
+ * the KeyFrame-KeyFrame overload accepts bestDist < TH_LOW, the KeyFrame-Frame one bestDist <= TH_LOW. */
+static int bow_search(sdyn_ctx* c, const sdyn_frame_view* kf, const uint8_t* kfValid, const sdyn_feature_vector* a,
+                      const sdyn_frame_view* f, const uint8_t* fValid, const sdyn_feature_vector* b, float nnratio, int checkOri,
+                      int strictLow, int32_t* assign, int* nmatches)
 {
     if (!c) return SDYN_ERR_ARG;
     if (!kf || !f || !a || !b || !assign || !nmatches || kf->n < 0 || f->n < 0 || f->n > 65535 || (kf->n > 0 && (!kfValid || !kf->desc || !kf->keys_un)) ||
         (f->n > 0 && (!f->desc || !f->keys_un)))
         return api_fail(c, SDYN_ERR_ARG, "sdyn_match_bow: bad argument");
     *nmatches = 0;
-    for (int i = 0; i < f->n; ++i) assign[i] = -1;
+    for (int i = 0; i < f->n; ++i) assign[i] = (!fValid || fValid[i]) ? -1 : -3;      /* -3: never a candidate */
     /* merge-join of the two feature vectors on node id (ORBmatcher.cc:182-253) -> one query per valid
      * keyframe feature of every shared node, in reference order */
     std::vector<BowQuery> qs;
@@ -325,7 +370,7 @@ int sdyn_match_bow(sdyn_ctx* c, const sdyn_frame_view* kf, const uint8_t* kfVali
             sdyn_keypoint* dk = A.take<sdyn_keypoint>(kf->n);
             uint8_t* dd = A.take<uint8_t>((size_t)32 * kf->n);
             uint32_t* di = A.take<uint32_t>(nIndex);
-            J.queries = dq; J.qKeys = dk; J.qDesc = dd; J.fIndex = di; J.nq = nq; J.nnratio = nnratio; J.checkOri = checkOri;
+            J.queries = dq; J.qKeys = dk; J.qDesc = dd; J.fIndex = di; J.nq = nq; J.nnratio = nnratio; J.checkOri = checkOri; J.strictLow = strictLow;
             J.assign = A.take<int32_t>(f->n);
             if (A.failed) return (int)SDYN_OK;
             MCU(c, upload_frame(&fv, J, c->stream));
@@ -333,7 +378,7 @@ int sdyn_match_bow(sdyn_ctx* c, const sdyn_frame_view* kf, const uint8_t* kfVali
             MCU(c, up(dk, kf->keys_un, kf->n, c->stream));
             MCU(c, up(dd, kf->desc, (size_t)32 * kf->n, c->stream));
             MCU(c, up(di, b->index, nIndex, c->stream));
-            MCU(c, cudaMemsetAsync(J.assign, 0xff, sizeof(int32_t) * f->n, c->stream));
+            MCU(c, up(J.assign, assign, f->n, c->stream));
             return (int)SDYN_OK;
         },
         [&](const MatchJob& J, const int32_t* res) {
@@ -342,6 +387,30 @@ int sdyn_match_bow(sdyn_ctx* c, const sdyn_frame_view* kf, const uint8_t* kfVali
             *nmatches = res[0];
             return (int)SDYN_OK;
         });
+}
+
+int sdyn_match_bow(sdyn_ctx* c, const sdyn_frame_view* kf, const uint8_t* kfValid, const sdyn_feature_vector* a,
+                   const sdyn_frame_view* f, const sdyn_feature_vector* b, float nnratio, int checkOri, int32_t* assign,
+                   int* nmatches)
+{
+    return bow_search(c, kf, kfValid, a, f, nullptr, b, nnratio, checkOri, 0, assign, nmatches);
+}
+
+int sdyn_match_bow_kf(sdyn_ctx* c, const sdyn_frame_view* kf1, const uint8_t* valid1, const sdyn_feature_vector* fv1,
+                      const sdyn_frame_view* kf2, const uint8_t* valid2, const sdyn_feature_vector* fv2, float nnratio,
+                      int checkOri, int32_t* matches12, int* nmatches)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (!kf1 || !kf2 || !matches12 || kf1->n < 0 || kf2->n < 0 || (kf2->n > 0 && !valid2))
+        return api_fail(c, SDYN_ERR_ARG, "sdyn_match_bow_kf: bad argument");
+    for (int i = 0; i < kf1->n; ++i) matches12[i] = -1;
+    std::vector<int32_t> a2((size_t)std::max(kf2->n, 1));
+    int rc = bow_search(c, kf1, valid1, fv1, kf2, valid2, fv2, nnratio, checkOri, 1, a2.data(), nmatches);
+    if (rc != SDYN_OK) return rc;
+    /* the search records, per KeyFrame-2 feature, the KeyFrame-1 feature that took it: invert into vpMatches12 */
+    for (int i2 = 0; i2 < kf2->n; ++i2)
+        if (a2[i2] >= 0) matches12[a2[i2]] = i2;
+    return SDYN_OK;
 }
 
 int sdyn_dyn_box_mask(sdyn_ctx* c, const sdyn_keypoint* keys, int n, const double* boxes, int nboxes, uint64_t* mask)

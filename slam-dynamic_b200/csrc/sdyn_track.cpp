@@ -199,7 +199,7 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         J.cellOf = t->cellOf + (size_t)f * cap;
         J.gridEntry = t->gridEntry + (size_t)f * cap;
         J.assign = t->assign + (size_t)f * cap; J.locked = t->locked + (size_t)f * cap;
-        J.poolCap = t->poolPerJob;
+        J.poolCap = t->poolPerJob; J.distTh = SDYN_TH_HIGH;
         std::memcpy(J.Tcw, in->tcw_cur, sizeof(J.Tcw));
         J.fx = in->fx; J.fy = in->fy; J.cx = in->cx; J.cy = in->cy; J.bf = in->bf;
 

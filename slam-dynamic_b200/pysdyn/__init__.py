@@ -302,6 +302,28 @@ MAPPOINT_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f
 LASTPOINT_DTYPE = np.dtype([("has_mp", "u1"), ("outlier", "u1"), ("obs_positive", "u1"), ("pad", "u1"),
                             ("world", "<f4", (3,)), ("desc", "u1", (32,))])
 assert MAPPOINT_DTYPE.itemsize == 56 and LASTPOINT_DTYPE.itemsize == 48
+PROJPOINT_DTYPE = np.dtype([("valid", "u1"), ("pad", "u1", (3,)), ("world", "<f4", (3,)), ("normal", "<f4", (3,)),
+                            ("min_distance", "<f4"), ("max_distance", "<f4"), ("max_distance_raw", "<f4"), ("angle", "<f4"),
+                            ("desc", "u1", (32,))])
+assert PROJPOINT_DTYPE.itemsize == 76
+PROJ_FRAME_KEYFRAME, PROJ_KEYFRAME_SIM3 = 0, 1
+
+
+class ProjParamsC(C.Structure):
+    _fields_ = [("rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("ow", C.c_float * 3), ("th", C.c_float),
+                ("max_descriptor_distance", C.c_int32), ("variant", C.c_int32), ("check_orientation", C.c_int32),
+                ("log_scale_factor", C.c_float), ("nlevels", C.c_int32)]
+
+
+def proj_params(rcw, tcw, ow, th, max_dist, variant, check_orientation, log_scale_factor, nlevels):
+    p = ProjParamsC()
+    for i, v in enumerate(np.asarray(rcw, np.float32).reshape(9)):
+        p.rcw[i] = float(v)
+    for i in range(3):
+        p.tcw[i] = float(np.float32(tcw[i])); p.ow[i] = float(np.float32(ow[i]))
+    p.th = th; p.max_descriptor_distance = max_dist; p.variant = variant; p.check_orientation = int(check_orientation)
+    p.log_scale_factor = float(np.float32(log_scale_factor)); p.nlevels = nlevels
+    return p
 
 
 class FrameView:
@@ -407,6 +429,18 @@ class Matcher:
             return n.value, assign, locked, pairs[:npairs.value].copy()
         return n.value, assign, locked
 
+    def SearchByProjectionPose(self, target, points, params, assign=None):
+        """The two pose-projection overloads (ORBmatcher.cc:290-403, 1629-1756): (nmatches, assign)."""
+        pts = np.ascontiguousarray(points, PROJPOINT_DTYPE)
+        assign = np.full(target.n, -1, np.int32) if assign is None else np.ascontiguousarray(assign, np.int32).copy()
+        n = C.c_int(0)
+        vp = C.c_void_p
+        self.L.sdyn_match_projection_pose.argtypes = [vp, C.POINTER(FrameViewC), vp, C.c_int, C.POINTER(ProjParamsC), vp,
+                                                      C.POINTER(C.c_int)]
+        self.ex._check(self.L.sdyn_match_projection_pose(self.h, C.byref(target.c), pts.ctypes.data, len(pts), C.byref(params),
+                                                         assign.ctypes.data, C.byref(n)))
+        return n.value, assign
+
     def SearchForInitialization(self, F1, F2, prev_matched, window=100):
         prev = np.ascontiguousarray(prev_matched, np.float32).copy()
         m12 = np.full(F1.n, -1, np.int32)
@@ -422,6 +456,20 @@ class Matcher:
         self.ex._check(self.L.sdyn_match_bow(self.h, C.byref(KF.c), kv.ctypes.data, C.byref(fv_kf.c), C.byref(F.c),
                                              C.byref(fv_f.c), self.nnratio, int(self.check), assign.ctypes.data, C.byref(n)))
         return n.value, assign
+
+
+    def SearchByBoWKF(self, KF1, valid1, fv1, KF2, valid2, fv2):
+        """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12): (nmatches, matches12[i1] = KeyFrame-2 index or -1)."""
+        v1 = np.ascontiguousarray(valid1, np.uint8); v2 = np.ascontiguousarray(valid2, np.uint8)
+        m12 = np.full(KF1.n, -1, np.int32)
+        n = C.c_int(0)
+        vp = C.c_void_p
+        self.L.sdyn_match_bow_kf.argtypes = [vp, C.POINTER(FrameViewC), vp, C.POINTER(FeatureVectorC), C.POINTER(FrameViewC), vp,
+                                             C.POINTER(FeatureVectorC), C.c_float, C.c_int, vp, C.POINTER(C.c_int)]
+        self.ex._check(self.L.sdyn_match_bow_kf(self.h, C.byref(KF1.c), v1.ctypes.data, C.byref(fv1.c), C.byref(KF2.c),
+                                                v2.ctypes.data, C.byref(fv2.c), self.nnratio, int(self.check), m12.ctypes.data,
+                                                C.byref(n)))
+        return n.value, m12
 
 
 def box_mask(ctx, keys, boxes):

@@ -226,6 +226,23 @@ def match_bow(KF, kf_valid, fv_kf, F, fv_f, nnratio, check_ori):
     return n, assign
 
 
+def match_bow_kf(KF1, valid1, fv1, KF2, valid2, fv2, nnratio, check_ori):
+    v1 = np.ascontiguousarray(valid1, np.uint8); v2 = np.ascontiguousarray(valid2, np.uint8)
+    m12 = np.full(KF1.n, -1, np.int32)
+    lib.orc_match_bow_kf.argtypes = [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_void_p]
+    n = lib.orc_match_bow_kf(C.byref(KF1.c), v1.ctypes.data, C.byref(fv1.c), C.byref(KF2.c), v2.ctypes.data, C.byref(fv2.c),
+                             nnratio, int(check_ori), m12.ctypes.data)
+    return n, m12
+
+
+def match_projection_pose(target, points, params, assign=None):
+    pts = np.ascontiguousarray(points, _structs().PROJPOINT_DTYPE)
+    assign = np.full(target.n, -1, np.int32) if assign is None else np.ascontiguousarray(assign, np.int32).copy()
+    lib.orc_match_projection_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    n = lib.orc_match_projection_pose(C.byref(target.c), pts.ctypes.data, len(pts), C.byref(params), assign.ctypes.data)
+    return n, assign
+
+
 def box_mask(keys, boxes):
     keys = np.ascontiguousarray(keys, KP_DTYPE)
     boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)

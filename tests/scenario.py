@@ -192,3 +192,45 @@ def stereo_pair(cfg, idx, disparities=(5, 11, 23), seq=0):
     for d, y0, y1 in zip(disparities, edges[:-1], edges[1:]):
         right[y0:y1] = common.frame(cfg, idx + 1000, seq=seq, ox=d)[y0:y1]
     return left, right
+
+
+def pose_small(seed=0, angle_deg=1.5, t=(0.05, -0.02, 0.1)):
+    """A small camera motion as the float32 (Rcw, tcw, Ow = -Rcw^T tcw) triple the pose searches take."""
+    r = rng_for(seed + 303)
+    ax = r.normal(size=3); ax /= np.linalg.norm(ax)
+    a = np.deg2rad(angle_deg)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = (np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * K @ K).astype(np.float32)
+    tcw = np.asarray(t, np.float32)
+    ow = (-(R.T.astype(np.float32) @ tcw)).astype(np.float32)
+    return R, tcw, ow
+
+
+def proj_points(keys, desc, scale, R, tcw, ow, cam=KITTI_CAM, seed=0, p_valid=0.85, noise_bits=6, jitter=1.0):
+    """Candidate MapPoints of the pose-projection searches: every keypoint of the searched frame is back-projected at
+    a seeded depth through the given pose, so the point projects next to it; distances / normals follow
+    MapPoint::UpdateNormalAndDepth (mfMaxDistance = dist * scale[octave], mfMinDistance = mfMaxDistance / scale[last])."""
+    r = rng_for(seed + 404)
+    n = len(keys)
+    pp = np.zeros(n, pysdyn.PROJPOINT_DTYPE)
+    pp["valid"] = r.random(n) < p_valid
+    z = r.uniform(4.0, 40.0, n)
+    u = keys["x"].astype(np.float64) + r.normal(0, jitter, n); v = keys["y"].astype(np.float64) + r.normal(0, jitter, n)
+    pc = np.stack([(u - cam["cx"]) * z / cam["fx"], (v - cam["cy"]) * z / cam["fy"], z], 1)
+    behind = r.random(n) < 0.03
+    pc[behind, 2] *= -1                                        # some points behind the camera
+    pw = (pc - tcw.astype(np.float64)) @ R.astype(np.float64)  # Rcw^T (pc - tcw)
+    pp["world"] = pw.astype(np.float32)
+    po = pp["world"].astype(np.float64) - ow.astype(np.float64)
+    dist = np.linalg.norm(po, axis=1)
+    nrm = po / dist[:, None] + r.normal(0, 0.5, (n, 3))        # viewing direction with a spread: some fail the 60 degree test
+    pp["normal"] = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    lvl = np.clip(keys["octave"] + r.integers(-1, 2, n), 0, len(scale) - 1)
+    ref_dist = dist * r.uniform(0.7, 1.4, n)                   # distance at which the point was created
+    raw = (ref_dist * scale[lvl]).astype(np.float32)
+    pp["max_distance_raw"] = raw
+    pp["max_distance"] = np.float32(1.2) * raw
+    pp["min_distance"] = np.float32(0.8) * (raw / scale[-1])
+    pp["angle"] = np.mod(keys["angle"] + r.normal(0, 8.0, n), 360).astype(np.float32)
+    pp["desc"] = flip_bits(desc, r, r.integers(0, noise_bits + 1, n))
+    return pp

@@ -146,6 +146,51 @@ def test_search_by_bow(ctx, request, data):
     assert got[0] == ref[0] and np.array_equal(got[1], ref[1])
 
 
+@pytest.mark.parametrize("data", ["tum", "kitti"])
+def test_search_by_bow_keyframes(ctx, request, data):
+    """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), src/ORBmatcher.cc:679-812 (loop detection)."""
+    p = request.getfixturevalue(data)
+    kf2, kf1 = views(p, False)
+    fa = pysdyn.FeatureVector(scenario.bow_nodes(p["d0"])); fb = pysdyn.FeatureVector(scenario.bow_nodes(p["d1"]))
+    r = np.random.default_rng(5)
+    v1 = (r.random(kf1.n) < 0.8).astype(np.uint8); v2 = (r.random(kf2.n) < 0.7).astype(np.uint8)
+    for check in (True, False):
+        got = pysdyn.Matcher(ctx, 0.75, check).SearchByBoWKF(kf1, v1, fa, kf2, v2, fb)
+        ref = orc.match_bow_kf(kf1, v1, fa, kf2, v2, fb, 0.75, check)
+        assert got[0] == ref[0] and got[0] > 30 and np.array_equal(got[1], ref[1])
+        assert (v1[got[1] >= 0] == 1).all() and (v2[got[1][got[1] >= 0]] == 1).all()
+    # tie-heavy descriptors, best distance exactly TH_LOW must be rejected (strict <)
+    d0 = scenario.degenerate_descriptors(kf1.n, 21, 30); d1 = scenario.degenerate_descriptors(kf2.n, 22, 30)
+    kf2, kf1 = views(p, False, d0=d0, d1=d1)
+    fa = pysdyn.FeatureVector(scenario.bow_nodes(d0, 3)); fb = pysdyn.FeatureVector(scenario.bow_nodes(d1, 3))
+    got = pysdyn.Matcher(ctx, 0.95, True).SearchByBoWKF(kf1, v1, fa, kf2, v2, fb)
+    ref = orc.match_bow_kf(kf1, v1, fa, kf2, v2, fb, 0.95, True)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1])
+
+
+@pytest.mark.parametrize("data", ["tum", "kitti"])
+@pytest.mark.parametrize("variant,th,maxd", [(pysdyn.PROJ_FRAME_KEYFRAME, 10.0, 100), (pysdyn.PROJ_FRAME_KEYFRAME, 3.0, 64),
+                                             (pysdyn.PROJ_KEYFRAME_SIM3, 10.0, 50)])
+def test_search_by_projection_pose(ctx, request, data, variant, th, maxd):
+    """SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist) :1629-1756 and SearchByProjection(KeyFrame*, Scw, ...) :290-403."""
+    p = request.getfixturevalue(data)
+    target, _ = views(p, False)
+    R, tcw, ow = scenario.pose_small(seed=3)
+    pts = scenario.proj_points(p["k1"], p["d1"], p["scale"], R, tcw, ow, seed=11)
+    prm = pysdyn.proj_params(R, tcw, ow, th, maxd, variant, True, np.log(np.float32(1.2)), 8)
+    occ = np.where(np.random.default_rng(4).random(target.n) < 0.1, -2, -1).astype(np.int32)   # already matched keypoints
+    got = pysdyn.Matcher(ctx, 0.9, True).SearchByProjectionPose(target, pts, prm, occ)
+    ref = orc.match_projection_pose(target, pts, prm, occ)
+    assert got[0] == ref[0] and got[0] > 100 and np.array_equal(got[1], ref[1])
+    # tie-heavy descriptors: claims and the rotation cull interact
+    dd = scenario.degenerate_descriptors(target.n, 5, 30)
+    target2, _ = views(p, False, d1=dd)
+    pts2 = scenario.proj_points(p["k1"], dd, p["scale"], R, tcw, ow, seed=12, noise_bits=0)
+    got = pysdyn.Matcher(ctx, 0.9, True).SearchByProjectionPose(target2, pts2, prm)
+    ref = orc.match_projection_pose(target2, pts2, prm)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1])
+
+
 def test_empty_inputs(ctx, tum):
     p = tum
     cur, last = views(p, False)

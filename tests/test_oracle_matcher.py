@@ -220,3 +220,168 @@ def test_box_track_assigns_ids_and_carries_boxes():
     b, idx, omit, vel = orc.box_track([[14, 12, 50, 50]], last, [0, 1], [0, 0], [[0, 0], [5, 0]], 640, 480)
     assert idx.tolist() == [0, 1] and omit.tolist() == [0, 1]          # second box carried over with its velocity
     assert np.allclose(b[1], [305, 200, 40, 40]) and np.allclose(vel[0], [2, 1])
+
+
+def py_three_maxima(sizes):
+    m1 = m2 = m3 = 0; i1 = i2 = i3 = -1
+    for i, s in enumerate(sizes):
+        if s > m1:
+            m3, m2, m1, i3, i2, i1 = m2, m1, s, i2, i1, i
+        elif s > m2:
+            m3, m2, i3, i2 = m2, s, i2, i
+        elif s > m3:
+            m3, i3 = s, i
+    if m2 < f32(0.1) * f32(m1):
+        i2 = i3 = -1
+    elif m3 < f32(0.1) * f32(m1):
+        i3 = -1
+    return i1, i2, i3
+
+
+def py_rot_bin(a, b):
+    rot = f32(a - b)
+    if rot < 0:
+        rot = f32(rot + f32(360))
+    bn = int(math.floor(float(f32(rot * f32(1.0 / 30))) + 0.5))
+    return 0 if bn == 30 else bn
+
+
+def py_search_bow_kf(kf1, v1, nodes1, kf2, v2, nodes2, ratio, check_ori):
+    """Independent Python re-statement of SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), ORBmatcher.cc:679-812:
+    std::map iteration = ascending node id, in-node order = feature index order."""
+    def fmap(nodes):
+        m = {}
+        for i, nd in enumerate(nodes):
+            m.setdefault(int(nd), []).append(i)
+        return m
+    f1, f2 = fmap(nodes1), fmap(nodes2)
+    m12 = np.full(kf1.n, -1, np.int32); matched2 = np.zeros(kf2.n, bool)
+    hist = [[] for _ in range(30)]
+    n = 0
+    for node in sorted(set(f1) & set(f2)):
+        for i1 in f1[node]:
+            if not v1[i1]:
+                continue
+            b1, bi, b2 = 256, -1, 256
+            for i2 in f2[node]:
+                if matched2[i2] or not v2[i2]:
+                    continue
+                d = int(np.unpackbits(kf1.desc[i1] ^ kf2.desc[i2]).sum())
+                if d < b1:
+                    b2, b1, bi = b1, d, i2
+                elif d < b2:
+                    b2 = d
+            if b1 < 50 and f32(b1) < f32(ratio) * f32(b2):
+                m12[i1] = bi; matched2[bi] = True; n += 1
+                if check_ori:
+                    hist[py_rot_bin(kf1.keys_un["angle"][i1], kf2.keys_un["angle"][bi])].append(i1)
+    if check_ori:
+        keep = py_three_maxima([len(h) for h in hist])
+        for i, h in enumerate(hist):
+            if i in keep:
+                continue
+            for idx in h:
+                m12[idx] = -1; n -= 1
+    return n, m12
+
+
+@pytest.mark.parametrize("check", [True, False])
+def test_search_bow_keyframes_oracle_vs_python(tum_pair, check):
+    p = tum_pair
+    kf1 = scenario.frame_view(p["k0"], p["d0"], p["scale"], p["W"], p["H"])
+    kf2 = scenario.frame_view(p["k1"], p["d1"], p["scale"], p["W"], p["H"])
+    n1, n2 = scenario.bow_nodes(p["d0"]), scenario.bow_nodes(p["d1"])
+    r = np.random.default_rng(5)
+    v1 = (r.random(kf1.n) < 0.8).astype(np.uint8); v2 = (r.random(kf2.n) < 0.7).astype(np.uint8)
+    got = orc.match_bow_kf(kf1, v1, pysdyn.FeatureVector(n1), kf2, v2, pysdyn.FeatureVector(n2), 0.75, check)
+    ref = py_search_bow_kf(kf1, v1, n1, kf2, v2, n2, 0.75, check)
+    assert got[0] == ref[0] and got[0] > 30 and np.array_equal(got[1], ref[1])
+    # tie-heavy
+    d0 = scenario.degenerate_descriptors(kf1.n, 21, 30); d1 = scenario.degenerate_descriptors(kf2.n, 22, 30)
+    kf1 = scenario.frame_view(p["k0"], d0, p["scale"], p["W"], p["H"]); kf2 = scenario.frame_view(p["k1"], d1, p["scale"], p["W"], p["H"])
+    n1, n2 = scenario.bow_nodes(d0, 3), scenario.bow_nodes(d1, 3)
+    got = orc.match_bow_kf(kf1, v1, pysdyn.FeatureVector(n1), kf2, v2, pysdyn.FeatureVector(n2), 0.95, check)
+    ref = py_search_bow_kf(kf1, v1, n1, kf2, v2, n2, 0.95, check)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1])
+
+
+def py_predict_scale(raw, dist, log_sf, nlevels):
+    ratio = f32(f32(raw) / f32(dist))
+    n = int(math.ceil(float(f32(f32(math.log(float(ratio))) / f32(log_sf)))))     # logf = rounded double log
+    return 0 if n < 0 else (nlevels - 1 if n >= nlevels else n)
+
+
+def py_search_pose(target, pts, R, tcw, ow, th, maxd, variant, check_ori, log_sf, nlevels, occ):
+    """Independent Python re-statement of the two pose-projection searches (ORBmatcher.cc:1629-1756 / :290-403);
+    Rcw*x+tcw, cv::norm and Mat::dot run through cv2 itself."""
+    fx, fy, cx, cy = (f32(v) for v in target.cam[:4])
+    assign = np.asarray(occ, np.int32).copy()
+    hist = [[] for _ in range(30)]
+    n = 0
+    R = np.ascontiguousarray(R, np.float32); t = np.asarray(tcw, np.float32).reshape(3, 1); o = np.asarray(ow, np.float32).reshape(3, 1)
+    for i, p in enumerate(pts):
+        if not p["valid"]:
+            continue
+        xw = p["world"].reshape(3, 1).astype(np.float32)
+        pc = cv2.gemm(R, xw, 1.0, t, 1.0).reshape(3)
+        if variant == pysdyn.PROJ_FRAME_KEYFRAME:
+            invz = f32(1.0 / float(pc[2]))
+            u = f32(f32(f32(fx * pc[0]) * invz) + cx); v = f32(f32(f32(fy * pc[1]) * invz) + cy)
+            if u < target.bounds[0] or u > target.bounds[2] or v < target.bounds[1] or v > target.bounds[3]:
+                continue
+        else:
+            if pc[2] < 0.0:
+                continue
+            invz = f32(f32(1) / pc[2])
+            u = f32(f32(fx * f32(pc[0] * invz)) + cx); v = f32(f32(fy * f32(pc[1] * invz)) + cy)
+            if not (u >= target.bounds[0] and u < target.bounds[2] and v >= target.bounds[1] and v < target.bounds[3]):
+                continue
+        po = cv2.subtract(xw, o)
+        dist = f32(cv2.norm(po))
+        if dist < p["min_distance"] or dist > p["max_distance"]:
+            continue
+        if variant == pysdyn.PROJ_KEYFRAME_SIM3 and float(po.reshape(3).astype(np.float64) @ p["normal"].astype(np.float64)) < 0.5 * float(dist):
+            continue
+        lvl = py_predict_scale(p["max_distance_raw"], dist, log_sf, nlevels)
+        radius = f32(f32(th) * target.scale[lvl])
+        if variant == pysdyn.PROJ_FRAME_KEYFRAME:
+            cand = py_features_in_area(target, u, v, radius, lvl - 1, lvl + 1)
+        else:
+            cand = [j for j in py_features_in_area(target, u, v, radius, -1, -1)]
+        best, bi = 256, -1
+        for j in cand:
+            if assign[j] != -1:
+                continue
+            if variant == pysdyn.PROJ_KEYFRAME_SIM3 and not (lvl - 1 <= target.keys_un["octave"][j] <= lvl):
+                continue
+            d = int(np.unpackbits(p["desc"] ^ target.desc[j]).sum())
+            if d < best:
+                best, bi = d, j
+        if best <= maxd:
+            assign[bi] = i; n += 1
+            if check_ori and variant == pysdyn.PROJ_FRAME_KEYFRAME:
+                hist[py_rot_bin(p["angle"], target.keys_un["angle"][bi])].append(bi)
+    if check_ori and variant == pysdyn.PROJ_FRAME_KEYFRAME:
+        keep = py_three_maxima([len(h) for h in hist])
+        for i, h in enumerate(hist):
+            if i in keep:
+                continue
+            for idx in h:
+                assign[idx] = -1; n -= 1
+    return n, assign
+
+
+@pytest.mark.parametrize("variant,th,maxd", [(0, 10.0, 100), (1, 10.0, 50)])
+def test_search_pose_oracle_vs_python(tum_pair, variant, th, maxd):
+    p = tum_pair
+    target = scenario.frame_view(p["k1"], p["d1"], p["scale"], p["W"], p["H"])
+    R, tcw, ow = scenario.pose_small(seed=3)
+    pts = scenario.proj_points(p["k1"], p["d1"], p["scale"], R, tcw, ow, seed=11)
+    log_sf = np.log(np.float32(1.2))
+    prm = pysdyn.proj_params(R, tcw, ow, th, maxd, variant, True, log_sf, 8)
+    occ = np.where(np.random.default_rng(4).random(target.n) < 0.1, -2, -1).astype(np.int32)
+    got = orc.match_projection_pose(target, pts, prm, occ)
+    ref = py_search_pose(target, pts, R, tcw, ow, th, maxd, variant, True, log_sf, 8, occ)
+    assert got[0] == ref[0] and got[0] > 100 and np.array_equal(got[1], ref[1])
+    # every gate of the reference must actually fire in this scenario
+    assert (~pts["valid"].astype(bool)).any() and (got[1] == -2).any()
