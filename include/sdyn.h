@@ -355,6 +355,19 @@ int sdyn_track_results(const sdyn_ctx* ctx, sdyn_track_view* out);
 int sdyn_track_fetch(sdyn_ctx* ctx, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dyn_mask,
                      int32_t* counts, int cap, void* stream);
 
+/* ---- Frame::UndistortKeyPoints / ComputeImageBounds -----------------------------------------------------------
+ * Camera of the context: mK = (fx, fy, cx, cy) and mDistCoef = (k1, k2, p1, p2[, k3]) as floats (ncoef = 4 or 5; 0
+ * = no distortion).  With k1 != 0 (the reference's test, src/Frame.cc:814,846) every extraction also produces
+ * mvKeysUn on the device — cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) per keypoint — and the
+ * batched front end searches the undistorted keypoints; otherwise mvKeysUn == mvKeys. */
+int sdyn_set_camera(sdyn_ctx* ctx, float fx, float fy, float cx, float cy, const float* dist_coef, int ncoef);
+/* mvKeysUn of the last extraction: [nframes][cap] (equals the keypoints when the camera has no distortion). */
+int sdyn_fetch_keypoints_un(sdyn_ctx* ctx, int nframes, sdyn_keypoint* kp_out, int cap, void* stream);
+/* n (x, y) float pairs through the same device routine (host arrays). */
+int sdyn_undistort_points(sdyn_ctx* ctx, const float* xy, int n, float* out_xy);
+/* Frame::ComputeImageBounds (src/Frame.cc:844-872): bounds = {mnMinX, mnMinY, mnMaxX, mnMaxY}. */
+int sdyn_image_bounds(sdyn_ctx* ctx, int width, int height, float bounds[4]);
+
 /* ---- Frame::ComputeStereoMatches ------------------------------------------------------------------------
  * Replaces Frame::ComputeStereoMatches (src/Frame.cc:874-1048), the step that follows the two extractions in the
  * stereo Frame constructor (src/Frame.cc:151-160).  `left` and `right` are the contexts of mpORBextractorLeft /

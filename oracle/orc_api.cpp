@@ -36,6 +36,9 @@ void orc_fast_score_map(const uint8_t* img, int w, int h, int stride, int16_t* o
 void orc_fast_atan2(const float* y, const float* x, float* out, int n)
 { for (int i = 0; i < n; ++i) out[i] = fast_atan2(y[i], x[i]); }
 
+void orc_undistort_points(const float* src, int n, float fx, float fy, float cx, float cy, const float* dist, int ndist, float* dst)
+{ undistort_points(src, n, fx, fy, cx, cy, dist, ndist, dst); }
+
 void* orc_extractor_create(int nf, float sf, int nl, int ini, int mn) { return new Extractor(nf, sf, nl, ini, mn); }
 void orc_extractor_destroy(void* e) { delete (Extractor*)e; }
 

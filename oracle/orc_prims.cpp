@@ -167,3 +167,32 @@ float fast_atan2(float y, float x)
 }
 
 }  // namespace orc
+
+namespace orc {
+void undistort_points(const float* srcXY, int n, float fxf, float fyf, float cxf, float cyf, const float* dist, int ndist, float* dstXY)
+{
+    double k[5] = {0, 0, 0, 0, 0};                           /* k1 k2 p1 p2 k3 */
+    for (int i = 0; i < ndist && i < 5; ++i) k[i] = dist[i];
+    const double fx = fxf, fy = fyf, cx = cxf, cy = cyf;
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; ++i) {
+        double x = srcXY[2 * i], y = srcXY[2 * i + 1];
+        const double u = x, v = y;
+        x = (x - cx) * ifx; y = (y - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            /* rational coefficients k4..k6 are zero: numerator 1 + ((0*r2 + 0)*r2 + 0)*r2 = 1 */
+            const double icdist = (1 + ((0. * r2 + 0.) * r2 + 0.) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + 0. * r2 + 0. * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + 0. * r2 + 0. * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        /* R = I, P = K: RR = K; xx = fx*x + 0*y + cx, ww = 1/(0*x + 0*y + 1) */
+        const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+        dstXY[2 * i] = (float)(xx * ww); dstXY[2 * i + 1] = (float)(yy * ww);
+    }
+}
+}  // namespace orc

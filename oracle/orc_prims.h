@@ -52,3 +52,11 @@ int fast_nms(const uint8_t* img, int w, int h, int stride, int th, int* xyv, int
 float fast_atan2(float y, float x);
 
 }  // namespace orc
+
+namespace orc {
+/* cv::undistortPoints(src, dst, K, distCoeffs, noArray(), K) as Frame::UndistortKeyPoints / ComputeImageBounds call
+ * it (src/Frame.cc:812-872): 2-channel float points, float K = (fx, fy, cx, cy), float distortion (k1, k2, p1, p2[, k3]),
+ * default termination = 5 fixed-point iterations, all arithmetic in double (OpenCV calib3d, un-vendored; pinned
+ * against cv2 4.13 by tests/test_oracle_prims.py). */
+void undistort_points(const float* srcXY, int n, float fx, float fy, float cx, float cy, const float* dist, int ndist, float* dstXY);
+}

@@ -195,6 +195,11 @@ int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frame
                                      c->maxKp, nframes, st));
     }
     c->launches += 2 + 1 + (g.nlevels - 1) + 4;
+    if (c->camera.enabled) {          /* Frame::UndistortKeyPoints follows ExtractORB in every Frame constructor */
+        StageTimer t(c, st, SDYN_STAGE_DESCRIBE);
+        CU(c, launch_undistort(c->camera, c->dKp, c->dCount, c->maxKp, c->dKpUn, nframes, st));
+        c->launches += 1;
+    }
     return SDYN_OK;
 }
 
@@ -208,7 +213,7 @@ void free_all(sdyn_ctx* c)
     cudaFree(c->dFastTiles); cudaFree(c->dBlurTiles); cudaFree(c->dTables); cudaFree(c->dIn); cudaFree(c->dPyr);
     cudaFree(c->dBlur); cudaFree(c->dCellFlag); cudaFree(c->dCand); cudaFree(c->dCandNode); cudaFree(c->dCandCount); cudaFree(c->dSelCount);
     cudaFree(c->dLevelKp); cudaFree(c->dLevelCount); cudaFree(c->dCount); cudaFree(c->dStatus); cudaFree(c->dKp);
-    cudaFree(c->dDesc); cudaFree(c->dArena);
+    cudaFree(c->dDesc); cudaFree(c->dArena); cudaFree(c->dKpUn);
     cudaFreeHost(c->hKp); cudaFreeHost(c->hDesc); cudaFreeHost(c->hCount); cudaFreeHost(c->hStatus);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->evPool) cudaEventDestroy(e);
@@ -312,6 +317,75 @@ int sdyn_orb_tables(const sdyn_orb_params* p, sdyn_scale_info* out, int32_t umax
     int um[16];
     compute_scale_info(*p, *out, um);
     for (int i = 0; i < 16; ++i) umax[i] = um[i];
+    return SDYN_OK;
+}
+
+int sdyn_set_camera(sdyn_ctx* c, float fx, float fy, float cx, float cy, const float* dist, int ncoef)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (!(fx > 0.0f) || !(fy > 0.0f) || ncoef < 0 || ncoef > 5 || (ncoef > 0 && !dist))
+        return fail(c, SDYN_ERR_ARG, "sdyn_set_camera: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CameraModel m; std::memset(&m, 0, sizeof(m));
+    m.fx = fx; m.fy = fy; m.cx = cx; m.cy = cy;
+    for (int i = 0; i < ncoef; ++i) m.k[i] = dist[i];
+    m.enabled = ncoef > 0 && dist[0] != 0.0f;
+    if (m.enabled && !c->dKpUn) {
+        cudaError_t e = dalloc(&c->dKpUn, (size_t)c->maxKp * c->maxBatch);
+        if (e != cudaSuccess) return fail(c, SDYN_ERR_NOMEM, std::string("undistorted keypoints: ") + cudaGetErrorString(e));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->camera = m;
+    return SDYN_OK;
+}
+
+int sdyn_fetch_keypoints_un(sdyn_ctx* c, int nframes, sdyn_keypoint* kpOut, int cap, void* stream)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (nframes < 1 || nframes > c->maxBatch || !kpOut || cap < 0) return fail(c, SDYN_ERR_ARG, "sdyn_fetch_keypoints_un: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const sdyn_keypoint* src = c->camera.enabled ? c->dKpUn : c->dKp;      /* mvKeysUn = mvKeys without distortion */
+    const int m = std::min(cap, c->maxKp);
+    CU(c, cudaMemcpy2DAsync(kpOut, (size_t)cap * sizeof(sdyn_keypoint), src, (size_t)c->maxKp * sizeof(sdyn_keypoint),
+                            (size_t)m * sizeof(sdyn_keypoint), nframes, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    return SDYN_OK;
+}
+
+int sdyn_undistort_points(sdyn_ctx* c, const float* xy, int n, float* out)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (n < 0 || (n > 0 && (!xy || !out))) return fail(c, SDYN_ERR_ARG, "sdyn_undistort_points: bad argument");
+    if (n == 0) return SDYN_OK;
+    if (!c->camera.enabled) { std::memcpy(out, xy, (size_t)n * 8); return SDYN_OK; }
+    CU(c, cudaSetDevice(c->device));
+    float* d = nullptr;
+    cudaError_t e = dalloc(&d, (size_t)n * 4);
+    if (e != cudaSuccess) return fail(c, SDYN_ERR_NOMEM, std::string("sdyn_undistort_points: ") + cudaGetErrorString(e));
+    e = cudaMemcpyAsync(d, xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = launch_undistort_xy(c->camera, d, n, d + (size_t)2 * n, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + (size_t)2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(c, e, "sdyn_undistort_points");
+    c->launches += 1;
+    return SDYN_OK;
+}
+
+int sdyn_image_bounds(sdyn_ctx* c, int width, int height, float bounds[4])
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (!bounds || width < 1 || height < 1) return fail(c, SDYN_ERR_ARG, "sdyn_image_bounds: bad argument");
+    if (!c->camera.enabled) { bounds[0] = 0.0f; bounds[1] = 0.0f; bounds[2] = (float)width; bounds[3] = (float)height; return SDYN_OK; }
+    const float corners[8] = {0.0f, 0.0f, (float)width, 0.0f, 0.0f, (float)height, (float)width, (float)height};
+    float u[8];
+    int rc = sdyn_undistort_points(c, corners, 4, u);
+    if (rc != SDYN_OK) return rc;
+    bounds[0] = std::min(u[0], u[4]);      /* mnMinX = min(mat(0,0), mat(2,0)) */
+    bounds[2] = std::max(u[2], u[6]);      /* mnMaxX = max(mat(1,0), mat(3,0)) */
+    bounds[1] = std::min(u[1], u[3]);      /* mnMinY = min(mat(0,1), mat(1,1)) */
+    bounds[3] = std::max(u[5], u[7]);      /* mnMaxY = max(mat(2,1), mat(3,1)) */
     return SDYN_OK;
 }
 

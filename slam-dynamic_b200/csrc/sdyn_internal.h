@@ -57,6 +57,13 @@ struct Candidate {           /* 4 bytes: x:12 | y:12 | score:8, window-relative 
     uint32_t v;
 };
 
+/* Pinhole + Brown distortion as Frame holds it (mK, mDistCoef: float values, used in double by OpenCV) */
+struct CameraModel {
+    float fx, fy, cx, cy;
+    float k[5];              /* k1 k2 p1 p2 k3 (k3 = 0 for 4-coefficient cameras) */
+    int enabled;             /* mDistCoef.at<float>(0) != 0 (src/Frame.cc:814) */
+};
+
 struct LevelKp {             /* output of the octree stage, per (frame, level, slot) */
     int16_t x, y;            /* level coordinates (border added) */
     int32_t score;
@@ -96,6 +103,8 @@ struct sdyn_ctx {
     sdyn_keypoint* dKp; uint8_t* dDesc;        /* [maxBatch][maxKp] */
     /* matcher / dynamic-mask arena (grown on demand, reused across calls) */
     uint8_t* dArena; size_t arenaCap;
+    sdyn::CameraModel camera;                  /* distortion model for mvKeysUn (sdyn_set_camera); disabled = mvKeysUn == mvKeys */
+    sdyn_keypoint* dKpUn;                      /* [maxBatch][maxKp], allocated when a distorted camera is set */
     void* track;                               /* TrackState of the batched front end (sdyn_track.cpp) */
     void* stereo;                              /* StereoState of ComputeStereoMatches (sdyn_stereo.cpp) */
     /* per-stage profiling */
@@ -152,6 +161,9 @@ cudaError_t launch_orient_describe(const Geom& g, const uint8_t* dPyr, const uin
                                    sdyn_keypoint* dKp, uint8_t* dDesc, int32_t* dCount, int maxKp,
                                    int nframes, cudaStream_t st);
 size_t octree_smem_bytes(int nodeCap);
+cudaError_t launch_undistort(const CameraModel& cam, const sdyn_keypoint* dKp, const int32_t* dCount, int cap,
+                             sdyn_keypoint* dKpUn, int nframes, cudaStream_t st);
+cudaError_t launch_undistort_xy(const CameraModel& cam, const float* dSrc, int n, float* dDst, cudaStream_t st);
 
 constexpr int kFastTileW = 126, kFastTileH = 30;   /* +2 halo = 128 x 32 score positions: 4 x 4 per thread, no idle lanes */
 constexpr int kBlurTileW = 128, kBlurTileH = 32;

@@ -189,7 +189,7 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
 
     for (int f = 0; f < nframes; ++f) {
         MatchJob J; std::memset(&J, 0, sizeof(J));
-        J.keysUn = c->dKp + (size_t)f * cap; J.desc = c->dDesc + (size_t)f * cap * 32; J.uRight = nullptr;
+        J.keysUn = (c->camera.enabled ? c->dKpUn : c->dKp) + (size_t)f * cap; J.desc = c->dDesc + (size_t)f * cap * 32; J.uRight = nullptr;
         J.nPtr = c->dCount + f; J.n = cap;
         J.minX = in->min_x; J.minY = in->min_y; J.maxX = in->max_x; J.maxY = in->max_y;
         J.gridWInv = static_cast<float>(SDYN_GRID_COLS) / static_cast<float>(in->max_x - in->min_x);

@@ -12,7 +12,9 @@
 
 #include "../../include/sdyn.h"
 #include <algorithm>
+#include <cmath>
 #include <cstring>
+#include <set>
 #include <vector>
 
 namespace sdyn_host {
@@ -175,6 +177,125 @@ inline int SearchByBoW(sdyn_ctx* ctx, KeyFrameT* pKF, FrameT& F, std::vector<Map
         if (assign[i] >= 0) vpMapPointMatches[i] = kfPoints[assign[i]];
     return n;
 }
+
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12)
+ * reference: src/ORBmatcher.cc:679-812 (LoopClosing.cc:266) */
+template <class KeyFrameT, class MapPointT>
+inline int SearchByBoW(sdyn_ctx* ctx, KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, float nnratio,
+                       bool checkOrientation)
+{
+    const std::vector<MapPointT*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+    vpMatches12.assign(mp1.size(), static_cast<MapPointT*>(nullptr));
+    std::vector<uint8_t> v1(mp1.size()), v2(mp2.size());
+    for (size_t i = 0; i < mp1.size(); ++i) v1[i] = mp1[i] && !mp1[i]->isBad();
+    for (size_t i = 0; i < mp2.size(); ++i) v2[i] = mp2[i] && !mp2[i]->isBad();
+    sdyn_frame_view a, b;
+    std::memset(&a, 0, sizeof(a)); std::memset(&b, 0, sizeof(b));
+    a.n = (int)mp1.size(); b.n = (int)mp2.size(); a.nlevels = b.nlevels = pKF1->mnScaleLevels;
+    a.keys = a.keys_un = reinterpret_cast<const sdyn_keypoint*>(pKF1->mvKeysUn.data()); a.desc = pKF1->mDescriptors.data;
+    b.keys = b.keys_un = reinterpret_cast<const sdyn_keypoint*>(pKF2->mvKeysUn.data()); b.desc = pKF2->mDescriptors.data;
+    a.max_x = a.max_y = b.max_x = b.max_y = 1.f;
+    FeatureVectorCSR fa(pKF1->mFeatVec), fb(pKF2->mFeatVec);
+    sdyn_feature_vector av = fa.view(), bv = fb.view();
+    std::vector<int32_t> m12(mp1.size(), -1);
+    int n = 0;
+    if (sdyn_match_bow_kf(ctx, &a, v1.data(), &av, &b, v2.data(), &bv, nnratio, checkOrientation, m12.data(), &n) != SDYN_OK)
+        return 0;
+    for (size_t i = 0; i < mp1.size(); ++i)
+        if (m12[i] >= 0) vpMatches12[i] = mp2[m12[i]];
+    return n;
+}
+
+#ifdef SDYN_HAVE_OPENCV
+/* One candidate MapPoint of the pose-projection searches.  MapPoint::mfMaxDistance is protected in the reference;
+ * INTEGRATION.md adds the one-line accessor GetMaxDistance() next to GetMaxDistanceInvariance(). */
+template <class MapPointT>
+inline void proj_point(MapPointT* pMP, bool valid, float angle, sdyn_proj_point& q)
+{
+    std::memset(&q, 0, sizeof(q));
+    q.valid = valid;
+    if (!valid) return;
+    const cv::Mat w = pMP->GetWorldPos(), nrm = pMP->GetNormal(), d = pMP->GetDescriptor();
+    for (int k = 0; k < 3; ++k) { q.world[k] = w.at<float>(k); q.normal[k] = nrm.at<float>(k); }
+    q.min_distance = pMP->GetMinDistanceInvariance(); q.max_distance = pMP->GetMaxDistanceInvariance();
+    q.max_distance_raw = pMP->GetMaxDistance();
+    q.angle = angle;
+    std::memcpy(q.desc, d.data, 32);
+}
+
+inline void pose_params(const cv::Mat& Rcw, const cv::Mat& tcw, const cv::Mat& Ow, sdyn_proj_params& p)
+{
+    for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 3; ++k) p.rcw[3 * r + k] = Rcw.at<float>(r, k);
+        p.tcw[r] = tcw.at<float>(r); p.ow[r] = Ow.at<float>(r);
+    }
+}
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+ * reference: src/ORBmatcher.cc:1629-1756 (Tracking::Relocalization, Tracking.cc:2323,2337) */
+template <class FrameT, class KeyFrameT, class SetT>
+inline int SearchByProjection(sdyn_ctx* ctx, FrameT& CurrentFrame, KeyFrameT* pKF, const SetT& sAlreadyFound, float th,
+                              int ORBdist, bool checkOrientation)
+{
+    const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);      /* :1633-1635, evaluated by OpenCV itself */
+    const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat Ow = -Rcw.t() * tcw;
+    const auto vpMPs = pKF->GetMapPointMatches();
+    std::vector<sdyn_proj_point> q(vpMPs.size());
+    for (size_t i = 0; i < vpMPs.size(); ++i)
+        proj_point(vpMPs[i], vpMPs[i] && !vpMPs[i]->isBad() && !sAlreadyFound.count(vpMPs[i]), pKF->mvKeysUn[i].angle, q[i]);
+    sdyn_proj_params p;
+    std::memset(&p, 0, sizeof(p));
+    pose_params(Rcw, tcw, Ow, p);
+    p.th = th; p.max_descriptor_distance = ORBdist; p.variant = SDYN_PROJ_FRAME_KEYFRAME; p.check_orientation = checkOrientation;
+    p.log_scale_factor = CurrentFrame.mfLogScaleFactor; p.nlevels = CurrentFrame.mnScaleLevels;
+    std::vector<int32_t> assign(CurrentFrame.N);
+    for (int i = 0; i < CurrentFrame.N; ++i) assign[i] = CurrentFrame.mvpMapPoints[i] ? -2 : -1;
+    sdyn_frame_view v = frame_view(CurrentFrame);
+    int n = 0;
+    if (sdyn_match_projection_pose(ctx, &v, q.data(), (int)q.size(), &p, assign.data(), &n) != SDYN_OK) return 0;
+    for (int i = 0; i < CurrentFrame.N; ++i)
+        if (assign[i] >= 0) CurrentFrame.mvpMapPoints[i] = vpMPs[assign[i]];
+    return n;
+}
+
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)
+ * reference: src/ORBmatcher.cc:290-403 (LoopClosing::ComputeSim3, LoopClosing.cc:376) */
+template <class KeyFrameT, class MapPointT>
+inline int SearchByProjection(sdyn_ctx* ctx, KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints,
+                              std::vector<MapPointT*>& vpMatched, int th)
+{
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);                          /* :300-304 */
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    cv::Mat Rcw = sRcw / scw;
+    cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+    cv::Mat Ow = -Rcw.t() * tcw;
+    std::set<MapPointT*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPointT*>(nullptr));
+    std::vector<sdyn_proj_point> q(vpPoints.size());
+    for (size_t i = 0; i < vpPoints.size(); ++i)
+        proj_point(vpPoints[i], !vpPoints[i]->isBad() && !spAlreadyFound.count(vpPoints[i]), 0.f, q[i]);
+    sdyn_proj_params p;
+    std::memset(&p, 0, sizeof(p));
+    pose_params(Rcw, tcw, Ow, p);
+    p.th = (float)th; p.max_descriptor_distance = SDYN_TH_LOW; p.variant = SDYN_PROJ_KEYFRAME_SIM3;
+    p.log_scale_factor = pKF->mfLogScaleFactor; p.nlevels = pKF->mnScaleLevels;
+    sdyn_frame_view v;
+    std::memset(&v, 0, sizeof(v));
+    v.n = pKF->N; v.nlevels = pKF->mnScaleLevels;
+    v.keys = v.keys_un = reinterpret_cast<const sdyn_keypoint*>(pKF->mvKeysUn.data());
+    v.desc = pKF->mDescriptors.data; v.scale_factors = pKF->mvScaleFactors.data();
+    v.min_x = pKF->mnMinX; v.min_y = pKF->mnMinY; v.max_x = pKF->mnMaxX; v.max_y = pKF->mnMaxY;
+    v.fx = pKF->fx; v.fy = pKF->fy; v.cx = pKF->cx; v.cy = pKF->cy;
+    std::vector<int32_t> assign(pKF->N);
+    for (int i = 0; i < pKF->N; ++i) assign[i] = vpMatched[i] ? -2 : -1;
+    int n = 0;
+    if (sdyn_match_projection_pose(ctx, &v, q.data(), (int)q.size(), &p, assign.data(), &n) != SDYN_OK) return 0;
+    for (int i = 0; i < pKF->N; ++i)
+        if (assign[i] >= 0) vpMatched[i] = vpPoints[assign[i]];
+    return n;
+}
+#endif  /* SDYN_HAVE_OPENCV */
 
 /* Frame::ComputeStereoMatches() — reference: src/Frame.cc:874-1048.  Called where the reference calls it, right
  * after the two ExtractORB threads joined (src/Frame.cc:151-160): it works on the keypoints, descriptors and

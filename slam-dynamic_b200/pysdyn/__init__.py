@@ -259,6 +259,35 @@ class Extractor:
         self._check(lib().sdyn_fetch_candidates(self._h, frame, l, out.ctypes.data, cap, C.byref(n)))
         return out[:n.value].copy()
 
+    def set_camera(self, fx, fy, cx, cy, dist_coef=()):
+        """mK / mDistCoef of the Frames built from this extractor; k1 != 0 turns on device-side mvKeysUn."""
+        d = np.ascontiguousarray(dist_coef, np.float32)
+        L = lib()
+        L.sdyn_set_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int]
+        self._check(L.sdyn_set_camera(self._h, fx, fy, cx, cy, d.ctypes.data if len(d) else None, len(d)))
+
+    def fetch_keypoints_un(self, nframes, stream=None):
+        out = np.zeros((nframes, self.cap), KP_DTYPE)
+        L = lib()
+        L.sdyn_fetch_keypoints_un.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        self._check(L.sdyn_fetch_keypoints_un(self._h, nframes, out.ctypes.data, self.cap, C.c_void_p(stream) if stream else None))
+        return out
+
+    def undistort_points(self, xy):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        out = np.empty_like(xy)
+        L = lib()
+        L.sdyn_undistort_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        self._check(L.sdyn_undistort_points(self._h, xy.ctypes.data, len(xy), out.ctypes.data))
+        return out
+
+    def image_bounds(self, width, height):
+        b = (C.c_float * 4)()
+        L = lib()
+        L.sdyn_image_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        self._check(L.sdyn_image_bounds(self._h, width, height, b))
+        return tuple(b)
+
     def sync(self):
         self._check(lib().sdyn_sync(self._h))
 

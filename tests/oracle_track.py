@@ -7,15 +7,16 @@ import pysdyn
 import scenario
 
 
-def track_frame(keys, desc, scale, W, H, arrays, f, params, last_stride):
+def track_frame(keys, desc, scale, W, H, arrays, f, params, last_stride, keys_un=None, bounds=None):
     """Returns (assign, locked, dyn_mask, counts[4]) for frame f of `arrays` (scenario.build_track_batch)."""
     cam = scenario.KITTI_CAM
-    cur = pysdyn.FrameView(keys, desc, scale, (0.0, 0.0, float(W), float(H)),
+    bounds = (0.0, 0.0, float(W), float(H)) if bounds is None else tuple(float(b) for b in bounds)
+    cur = pysdyn.FrameView(keys, desc, scale, bounds, keys_un=keys_un,
                            cam=(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["bf"], cam["bf"] / cam["fx"]),
                            tcw=params["tcw_cur"])
     n0 = int(arrays["n_last"][f])
     last = pysdyn.FrameView(arrays["last_keys"][f, :n0], np.zeros((n0, 32), np.uint8), scale,
-                            (0.0, 0.0, float(W), float(H)), keys_un=arrays["last_keys_un"][f, :n0],
+                            bounds, keys_un=arrays["last_keys_un"][f, :n0],
                             cam=cur.cam, tcw=params["tcw_last"])
     n1, assign, locked = orc.match_projection_frame(cur, last, arrays["last_points"][f, :n0], params["th_frame"],
                                                     bool(params["mono"]), bool(params["check_orientation"]))

@@ -112,6 +112,14 @@ def orb_descriptor(img, x, y, angle):
     return out
 
 
+def undistort_points(xy, fx, fy, cx, cy, dist):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); dist = np.ascontiguousarray(dist, np.float32)
+    out = np.empty_like(xy)
+    lib.orc_undistort_points.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _f32p, C.c_int, _f32p]
+    lib.orc_undistort_points(_p(xy, _f32p), len(xy), fx, fy, cx, cy, _p(dist, _f32p), len(dist), _p(out, _f32p))
+    return out
+
+
 class Extractor:
     """Oracle ORBextractor (reference: src/ORBextractor.cc)."""
 

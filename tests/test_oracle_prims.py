@@ -105,3 +105,24 @@ def test_descriptor_sampling_against_cv2_orb():
         x, y = int(round(p.pt[0])), int(round(p.pt[1]))
         same += np.array_equal(d, orc.orb_descriptor(blur, x, y, p.angle))
     assert same == len(kps) and same > 100
+
+
+CAMERAS = {   # Examples/RGB-D/TUM1.yaml, TUM2.yaml (5 coefficients), a 4-coefficient camera
+    "tum1": (517.306408, 516.469215, 318.643040, 255.313989, [0.262383, -0.953104, -0.005358, 0.002628, 1.163314]),
+    "tum2": (520.908620, 521.007327, 325.141442, 249.701764, [0.231222, -0.784899, -0.003257, -0.000105, 0.917205]),
+    "k4": (458.654, 457.296, 367.215, 248.375, [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]),
+}
+
+
+@pytest.mark.parametrize("cam", sorted(CAMERAS))
+def test_undistort_points_bitexact_vs_cv2(cam):
+    """Frame::UndistortKeyPoints / ComputeImageBounds call cv::undistortPoints(mat, mat, mK, mDistCoef, Mat(), mK)
+    (src/Frame.cc:812-872); the oracle's restatement must reproduce cv2 bit for bit."""
+    fx, fy, cx, cy, d = CAMERAS[cam]
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32); D = np.array(d, np.float32).reshape(-1, 1)
+    r = np.random.default_rng(1)
+    pts = np.concatenate([r.uniform(0, 640, (20000, 1)), r.uniform(0, 480, (20000, 1))], 1).astype(np.float32)
+    pts = np.concatenate([pts, np.array([[0, 0], [640, 0], [0, 480], [640, 480], [-50, 900]], np.float32)])
+    ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+    got = orc.undistort_points(pts, float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), D.reshape(-1))
+    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
