@@ -355,6 +355,21 @@ int sdyn_track_results(const sdyn_ctx* ctx, sdyn_track_view* out);
 int sdyn_track_fetch(sdyn_ctx* ctx, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dyn_mask,
                      int32_t* counts, int cap, void* stream);
 
+/* ---- detection boxes at the edge of the dynamic-keypoint path (host code) ---------------------------------------
+ * The detector's per-frame text file: one "id cx cy w h" line per detection (Examples/RGB-D/rgbd_my.cc:232-252);
+ * each becomes cv::Rect2d(MAX(cx - w/2, 0), MAX(cy - h/2, 0), w, h), written as 4 doubles.  Empty lines are skipped,
+ * as in the reference; lines with fewer than 5 numbers are skipped too (the reference reads uninitialised values).
+ * *n_out = detections found; SDYN_ERR_CAPACITY if more than cap.  A missing file is a frame without boxes. */
+int sdyn_boxes_parse(const char* text, size_t len, double* xywh, int cap, int* n_out);
+int sdyn_boxes_read(const char* path, double* xywh, int cap, int* n_out);
+/* Frame::boxTrack (src/Frame.cc:481-552): joins this frame's boxes with the last frame's objects by IoU, carries
+ * unmatched objects over once and numbers new ones.  boxes: in/out, nboxes valid of capacity cap (carried-over boxes
+ * are appended); last_*: objects, box_idx, omit, box_velocity of the last frame (nlast entries; nlast == 0 = the
+ * re-initialised case).  Outputs box_idx / omit / velocity (2 doubles per box) for *n_out boxes. */
+int sdyn_box_track(double* boxes, int nboxes, int cap, const double* last_objects, const int32_t* last_box_idx,
+                   const uint8_t* last_omit, const double* last_velocity, int nlast, int img_width, int img_height,
+                   int32_t* box_idx, uint8_t* omit, double* velocity, int* n_out);
+
 /* ---- Frame::UndistortKeyPoints / ComputeImageBounds -----------------------------------------------------------
  * Camera of the context: mK = (fx, fy, cx, cy) and mDistCoef = (k1, k2, p1, p2[, k3]) as floats (ncoef = 4 or 5; 0
  * = no distortion).  With k1 != 0 (the reference's test, src/Frame.cc:814,846) every extraction also produces

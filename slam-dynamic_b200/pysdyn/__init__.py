@@ -689,3 +689,47 @@ def stereo_match(left, right, nframes, mb, mbf):
     left._check(_bind_stereo(lib()).sdyn_stereo_match(left._h, right._h, nframes, mb, mbf, ur.ctypes.data,
                                                       dp.ctypes.data, cap, kept.ctypes.data))
     return ur, dp, kept
+
+
+# ---------------------------------------------------------------------------------------------------
+# detection boxes: file format and Frame::boxTrack (host code of the C ABI)
+# ---------------------------------------------------------------------------------------------------
+def boxes_parse(text, cap=64):
+    """'id cx cy w h' lines -> [n,4] float64 cv::Rect2d rows (Examples/RGB-D/rgbd_my.cc:232-252)."""
+    raw = text.encode() if isinstance(text, str) else bytes(text)
+    out = np.zeros((cap, 4), np.float64); n = C.c_int(0)
+    L = lib()
+    L.sdyn_boxes_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    rc = L.sdyn_boxes_parse(raw, len(raw), out.ctypes.data, cap, C.byref(n))
+    if rc != 0:
+        raise SdynError(rc, "sdyn_boxes_parse")
+    return out[:n.value].copy()
+
+
+def boxes_read(path, cap=64):
+    out = np.zeros((cap, 4), np.float64); n = C.c_int(0)
+    L = lib()
+    L.sdyn_boxes_read.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    rc = L.sdyn_boxes_read(str(path).encode(), out.ctypes.data, cap, C.byref(n))
+    if rc != 0:
+        raise SdynError(rc, "sdyn_boxes_read")
+    return out[:n.value].copy()
+
+
+def box_track(boxes, last_objects, last_box_idx, last_omit, last_vel, img_w, img_h):
+    """Frame::boxTrack. Returns (boxes, box_idx, omit, velocity)."""
+    boxes = np.asarray(boxes, np.float64).reshape(-1, 4)
+    lo = np.ascontiguousarray(last_objects, np.float64).reshape(-1, 4)
+    cap = len(boxes) + len(lo) + 1
+    b = np.zeros((cap, 4), np.float64); b[:len(boxes)] = boxes
+    li = np.ascontiguousarray(last_box_idx, np.int32); lom = np.ascontiguousarray(last_omit, np.uint8)
+    lv = np.ascontiguousarray(last_vel, np.float64).reshape(-1, 2)
+    bi = np.zeros(cap, np.int32); om = np.zeros(cap, np.uint8); vel = np.zeros((cap, 2), np.float64); n = C.c_int(0)
+    L = lib()
+    vp = C.c_void_p
+    L.sdyn_box_track.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.POINTER(C.c_int)]
+    rc = L.sdyn_box_track(b.ctypes.data, len(boxes), cap, lo.ctypes.data, li.ctypes.data, lom.ctypes.data, lv.ctypes.data, len(lo),
+                          img_w, img_h, bi.ctypes.data, om.ctypes.data, vel.ctypes.data, C.byref(n))
+    if rc != 0:
+        raise SdynError(rc, "sdyn_box_track")
+    return b[:n.value].copy(), bi[:n.value].copy(), om[:n.value].copy(), vel[:n.value].copy()
