@@ -406,12 +406,39 @@ int sdyn_stereo_fetch(sdyn_ctx* left, int nframes, float* u_right, float* depth,
 int sdyn_stereo_match(sdyn_ctx* left, sdyn_ctx* right, int nframes, float mb, float mbf, float* u_right, float* depth,
                       int cap, int32_t* kept);
 
+/* ---- Frame::ComputeBoW -------------------------------------------------------------------------------------------
+ * Replaces mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) (src/Frame.cc:803-810; DBoW2
+ * TemplatedVocabulary.h:1127-1263), the step in front of SearchByBoW.  The vocabulary tree is uploaded once.
+ * Nodes are given in DBoW2 node-id order, node 0 = root: parent[i] (< i), is_leaf[i], descriptor (32 bytes), weight —
+ * exactly the columns of ORBvoc.txt (loadFromTextFile, :1338-1425); children keep file order and word ids number the
+ * leaves in file order.  Scoring L1_NORM + weighting TF_IDF (the ORBvoc header "10 6 0 0") are what is implemented. */
+typedef struct sdyn_vocab sdyn_vocab;
+int sdyn_vocab_create(int device, int nnodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc,
+                      const double* weight, int k, int L, sdyn_vocab** out);
+int sdyn_vocab_load_text(int device, const char* path, sdyn_vocab** out);
+int sdyn_vocab_destroy(sdyn_vocab* voc);
+int sdyn_vocab_info(const sdyn_vocab* voc, int32_t info[4]);      /* nodes, words, k, L */
+/* Tree descent of every descriptor (TemplatedVocabulary::transform(feature, id, weight, nid, levelsup), :1210-1258):
+ * per feature the word id, the word's weight and the node id levelsup levels above the leaves.  Host-array form: */
+int sdyn_bow_transform(sdyn_ctx* ctx, const sdyn_vocab* voc, const uint8_t* desc, int n, int levelsup,
+                       uint32_t* word_id, double* weight, uint32_t* node_id);
+/* Device-resident form on the descriptors of the context's last extraction (results: sdyn_bow_fetch, [nframes][cap]). */
+int sdyn_bow_transform_device(sdyn_ctx* ctx, const sdyn_vocab* voc, int nframes, int levelsup, void* stream);
+int sdyn_bow_fetch(sdyn_ctx* ctx, int nframes, uint32_t* word_id, double* weight, uint32_t* node_id, int cap, void* stream);
+/* Host assembly of the two containers from those arrays, as transform(features, BowVector&, FeatureVector&, levelsup)
+ * does it: BowVector = ascending word ids with the TF-IDF weights summed in feature order and L1-normalised
+ * (bow_ids / bow_values, capacity n); FeatureVector = CSR over ascending node ids (fv_nodes capacity n, fv_offset n+1,
+ * fv_index n).  Host code — the containers are std::map in the drop-in. */
+int sdyn_bow_assemble(const uint32_t* word_id, const double* weight, const uint32_t* node_id, int n, uint32_t* bow_ids,
+                      double* bow_values, int* n_words, uint32_t* fv_nodes, int32_t* fv_offset, uint32_t* fv_index,
+                      int* n_fv_nodes);
+
 /* ---- per-stage device timing (CUDA events on the launching stream) -------------------------------
  * While enabled, every enqueue brackets each stage with events; sdyn_profile_read synchronises and
  * returns the accumulated milliseconds and launch counts since the last read. */
 enum { SDYN_STAGE_PYRAMID = 0, SDYN_STAGE_FAST, SDYN_STAGE_OCTREE, SDYN_STAGE_BLUR, SDYN_STAGE_DESCRIBE,
        SDYN_STAGE_MATCH, SDYN_STAGE_DYNAMIC, SDYN_STAGE_LEVEL0 /* clears + level 0; PYRAMID = the resize chain */,
-       SDYN_STAGE_STEREO,
+       SDYN_STAGE_STEREO, SDYN_STAGE_BOW,
        SDYN_STAGE_COUNT };
 typedef struct {
     double ms[SDYN_STAGE_COUNT];

@@ -107,6 +107,7 @@ struct sdyn_ctx {
     sdyn_keypoint* dKpUn;                      /* [maxBatch][maxKp], allocated when a distorted camera is set */
     void* track;                               /* TrackState of the batched front end (sdyn_track.cpp) */
     void* stereo;                              /* StereoState of ComputeStereoMatches (sdyn_stereo.cpp) */
+    void* bow;                                 /* BowState of ComputeBoW (sdyn_bow.cpp) */
     /* per-stage profiling */
     bool profiling;
     std::vector<cudaEvent_t> evPool;           /* free events */
@@ -135,6 +136,8 @@ struct StageTimer {          /* brackets a stage with CUDA events while profilin
 void free_track_state(sdyn_ctx* c);
 /* sdyn_stereo.cpp */
 void free_stereo_state(sdyn_ctx* c);
+/* sdyn_bow.cpp */
+void free_bow_state(sdyn_ctx* c);
 
 /* geometry.cpp */
 void compute_scale_info(const sdyn_orb_params& p, sdyn_scale_info& s, int umax[16]);

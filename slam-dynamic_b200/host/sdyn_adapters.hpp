@@ -297,6 +297,25 @@ inline int SearchByProjection(sdyn_ctx* ctx, KeyFrameT* pKF, cv::Mat Scw, const 
 }
 #endif  /* SDYN_HAVE_OPENCV */
 
+/* Frame::ComputeBoW() / KeyFrame::ComputeBoW() — reference: src/Frame.cc:803-810, src/KeyFrame.cc:76-86.  The tree
+ * descent of all descriptors runs on the device; the two DBoW2 containers are then filled through their own
+ * methods in the insertion order of TemplatedVocabulary::transform (TemplatedVocabulary.h:1147-1164, 1194), so
+ * mBowVec / mFeatVec are the reference's objects with the reference's values. */
+template <class FrameT>
+inline bool ComputeBoW(sdyn_ctx* ctx, const sdyn_vocab* voc, FrameT& F)
+{
+    if (!F.mBowVec.empty()) return true;
+    const int n = F.mDescriptors.rows;
+    std::vector<uint32_t> word((size_t)std::max(n, 1)), node((size_t)std::max(n, 1));
+    std::vector<double> weight((size_t)std::max(n, 1));
+    if (sdyn_bow_transform(ctx, voc, F.mDescriptors.data, n, 4, word.data(), weight.data(), node.data()) != SDYN_OK) return false;
+    F.mBowVec.clear(); F.mFeatVec.clear();
+    for (int i = 0; i < n; ++i)
+        if (weight[i] > 0) { F.mBowVec.addWeight(word[i], weight[i]); F.mFeatVec.addFeature(node[i], (unsigned)i); }
+    F.mBowVec.normalize(DBoW2::L1);
+    return true;
+}
+
 /* Frame::ComputeStereoMatches() — reference: src/Frame.cc:874-1048.  Called where the reference calls it, right
  * after the two ExtractORB threads joined (src/Frame.cc:151-160): it works on the keypoints, descriptors and
  * pyramids the left / right ORBextractor contexts still hold on the device, so mvImagePyramid is not read on the host. */

@@ -39,7 +39,7 @@ class DeviceView(C.Structure):
                 ("cap", C.c_int32), ("nlevels", C.c_int32), ("level", LevelInfo * MAX_LEVELS)]
 
 
-STAGES = ["pyramid", "fast", "octree", "blur", "describe", "match", "dynamic", "level0", "stereo"]
+STAGES = ["pyramid", "fast", "octree", "blur", "describe", "match", "dynamic", "level0", "stereo", "bow"]
 
 
 class StageTimes(C.Structure):
@@ -733,3 +733,84 @@ def box_track(boxes, last_objects, last_box_idx, last_omit, last_vel, img_w, img
     if rc != 0:
         raise SdynError(rc, "sdyn_box_track")
     return b[:n.value].copy(), bi[:n.value].copy(), om[:n.value].copy(), vel[:n.value].copy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Frame::ComputeBoW -> DBoW2 TemplatedVocabulary::transform
+# ---------------------------------------------------------------------------------------------------
+def _bind_bow(L):
+    if getattr(L, "_bow_bound", False):
+        return L
+    vp = C.c_void_p
+    L.sdyn_vocab_create.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.sdyn_vocab_load_text.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.sdyn_vocab_destroy.argtypes = [vp]
+    L.sdyn_vocab_info.argtypes = [vp, C.POINTER(C.c_int32 * 4)]
+    L.sdyn_bow_transform.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+    L.sdyn_bow_transform_device.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.sdyn_bow_fetch.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp]
+    L.sdyn_bow_assemble.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.POINTER(C.c_int), vp, vp, vp, C.POINTER(C.c_int)]
+    L._bow_bound = True
+    return L
+
+
+class Vocabulary:
+    """A DBoW2 vocabulary tree resident on one GPU (ORBvocabulary)."""
+
+    def __init__(self, parent=None, is_leaf=None, desc=None, weight=None, k=10, L=6, path=None, device=0):
+        lb = _bind_bow(lib())
+        self._h = C.c_void_p()
+        if path is not None:
+            rc = lb.sdyn_vocab_load_text(device, str(path).encode(), C.byref(self._h))
+        else:
+            p = np.ascontiguousarray(parent, np.int32); lf = np.ascontiguousarray(is_leaf, np.uint8)
+            d = np.ascontiguousarray(desc, np.uint8); w = np.ascontiguousarray(weight, np.float64)
+            rc = lb.sdyn_vocab_create(device, len(p), p.ctypes.data, lf.ctypes.data, d.ctypes.data, w.ctypes.data, k, L, C.byref(self._h))
+        if rc != 0:
+            raise SdynError(rc, "vocabulary could not be created")
+        info = (C.c_int32 * 4)()
+        lb.sdyn_vocab_info(self._h, C.byref(info))
+        self.nnodes, self.nwords, self.k, self.L = (int(v) for v in info)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().sdyn_vocab_destroy(self._h); self._h = C.c_void_p()
+
+    __del__ = close
+
+
+def bow_assemble(word, weight, node):
+    """transform(features, BowVector&, FeatureVector&, levelsup)'s containers from the per-feature arrays (host code)."""
+    lb = _bind_bow(lib())
+    word = np.ascontiguousarray(word, np.uint32); weight = np.ascontiguousarray(weight, np.float64); node = np.ascontiguousarray(node, np.uint32)
+    n = len(word); m = max(n, 1)
+    bi = np.zeros(m, np.uint32); bv = np.zeros(m, np.float64); fn = np.zeros(m, np.uint32)
+    fo = np.zeros(m + 1, np.int32); fi = np.zeros(m, np.uint32); nw, nn = C.c_int(0), C.c_int(0)
+    rc = lb.sdyn_bow_assemble(word.ctypes.data, weight.ctypes.data, node.ctypes.data, n, bi.ctypes.data, bv.ctypes.data, C.byref(nw),
+                              fn.ctypes.data, fo.ctypes.data, fi.ctypes.data, C.byref(nn))
+    if rc != 0:
+        raise SdynError(rc, "sdyn_bow_assemble")
+    return dict(bow_ids=bi[:nw.value], bow_values=bv[:nw.value], fv_nodes=fn[:nn.value], fv_offset=fo[:nn.value + 1],
+                fv_index=fi[:fo[nn.value] if n else 0])
+
+
+def bow_transform(ex, voc, desc, levelsup=4):
+    """Frame::ComputeBoW for host descriptors: per-feature (word, weight, node) from the device + host-assembled containers."""
+    lb = _bind_bow(lib())
+    d = np.ascontiguousarray(desc, np.uint8); n = len(d); m = max(n, 1)
+    word = np.zeros(m, np.uint32); w = np.zeros(m, np.float64); node = np.zeros(m, np.uint32)
+    ex._check(lb.sdyn_bow_transform(ex._h, voc._h, d.ctypes.data, n, levelsup, word.ctypes.data, w.ctypes.data, node.ctypes.data))
+    out = dict(word=word[:n], weight=w[:n], node=node[:n])
+    out.update(bow_assemble(word[:n], w[:n], node[:n]))
+    return out
+
+
+def bow_transform_device(ex, voc, nframes, levelsup=4, stream=None):
+    ex._check(_bind_bow(lib()).sdyn_bow_transform_device(ex._h, voc._h, nframes, levelsup, stream))
+
+
+def bow_fetch(ex, nframes, stream=None):
+    cap = ex.cap
+    word = np.zeros((nframes, cap), np.uint32); w = np.zeros((nframes, cap), np.float64); node = np.zeros((nframes, cap), np.uint32)
+    ex._check(_bind_bow(lib()).sdyn_bow_fetch(ex._h, nframes, word.ctypes.data, w.ctypes.data, node.ctypes.data, cap, stream))
+    return word, w, node

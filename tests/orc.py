@@ -326,3 +326,36 @@ def stereo_matches(ex_left, ex_right, keys_l, desc_l, keys_r, desc_r, mb, mbf):
     if rc < 0:
         raise ValueError("oracle stereo: input the reference cannot process (rc=%d)" % rc)
     return ur[:n], dp[:n], rc
+
+
+# ---------------------------------------------------------------------------------------------------
+# Frame::ComputeBoW -> DBoW2 TemplatedVocabulary::transform
+# ---------------------------------------------------------------------------------------------------
+class Vocabulary:
+    def __init__(self, parent, is_leaf, desc, weight, k, L):
+        self.parent = np.ascontiguousarray(parent, np.int32); self.is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        self.desc = np.ascontiguousarray(desc, np.uint8); self.weight = np.ascontiguousarray(weight, np.float64)
+        lib.orc_vocab_build.restype = C.c_void_p
+        lib.orc_vocab_build.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.orc_vocab_free.argtypes = [C.c_void_p]
+        self.h = lib.orc_vocab_build(len(self.parent), self.parent.ctypes.data, self.is_leaf.ctypes.data, self.desc.ctypes.data,
+                                     self.weight.ctypes.data, k, L)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.orc_vocab_free(self.h); self.h = None
+
+    def transform(self, features, levelsup=4):
+        """-> dict(word, weight, node per feature; bow_ids, bow_values; fv_nodes, fv_offset, fv_index)."""
+        f = np.ascontiguousarray(features, np.uint8); n = len(f)
+        m = max(n, 1)
+        word = np.zeros(m, np.uint32); w = np.zeros(m, np.float64); node = np.zeros(m, np.uint32)
+        bi = np.zeros(m, np.uint32); bv = np.zeros(m, np.float64); fn = np.zeros(m, np.uint32)
+        fo = np.zeros(m + 1, np.int32); fi = np.zeros(m, np.uint32)
+        nw, nn = C.c_int(0), C.c_int(0)
+        lib.orc_bow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_int)] + \
+                                        [C.c_void_p] * 3 + [C.POINTER(C.c_int)]
+        lib.orc_bow_transform(self.h, f.ctypes.data, n, levelsup, word.ctypes.data, w.ctypes.data, node.ctypes.data, bi.ctypes.data,
+                              bv.ctypes.data, C.byref(nw), fn.ctypes.data, fo.ctypes.data, fi.ctypes.data, C.byref(nn))
+        return dict(word=word[:n], weight=w[:n], node=node[:n], bow_ids=bi[:nw.value], bow_values=bv[:nw.value],
+                    fv_nodes=fn[:nn.value], fv_offset=fo[:nn.value + 1], fv_index=fi[:fo[nn.value]])

@@ -234,3 +234,37 @@ def proj_points(keys, desc, scale, R, tcw, ow, cam=KITTI_CAM, seed=0, p_valid=0.
     pp["angle"] = np.mod(keys["angle"] + r.normal(0, 8.0, n), 360).astype(np.float32)
     pp["desc"] = flip_bits(desc, r, r.integers(0, noise_bits + 1, n))
     return pp
+
+
+def synthetic_vocabulary(k=10, L=3, seed=0, ragged=0.0, stop=0.02, base_desc=None):
+    """A DBoW2-shaped vocabulary tree in node-id (file) order: (parent, is_leaf, desc, weight).  Children descriptors
+    are the parent's with a few flipped bits (so descents are decisive but ties occur), leaves get IDF-like weights,
+    `stop` of them weight 0 (stopped words) and `ragged` of the inner nodes end early (leaves above level L)."""
+    r = rng_for(seed + 505)
+    parent, leaf, desc, weight, level = [0], [0], [np.zeros(32, np.uint8) if base_desc is None else base_desc], [0.0], [0]
+    frontier = [0]
+    for lvl in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            for _ in range(k):
+                d = desc[p].copy()
+                for b in r.integers(0, 256, max(1, 48 >> lvl)):
+                    d[b >> 3] ^= np.uint8(1 << (b & 7))
+                nid = len(parent)
+                is_leaf = lvl == L or (lvl >= 2 and r.random() < ragged)
+                parent.append(p); leaf.append(int(is_leaf)); desc.append(d); level.append(lvl)
+                weight.append(0.0 if (is_leaf and r.random() < stop) else (float(r.uniform(0.5, 9.0)) if is_leaf else 0.0))
+                if not is_leaf:
+                    nxt.append(nid)
+        frontier = nxt
+    # DBoW2 writes nodes level by level, which is the order produced here (parents precede children)
+    return (np.array(parent, np.int32), np.array(leaf, np.uint8), np.stack(desc).astype(np.uint8), np.array(weight, np.float64))
+
+
+def write_vocabulary_text(path, parent, leaf, desc, weight, k, L):
+    """ORBvoc.txt layout (TemplatedVocabulary::saveToTextFile): header 'k L scoring weighting', then per node
+    'parent isLeaf d0 .. d31 weight'."""
+    with open(path, "w") as f:
+        f.write("%d %d 0 0\n" % (k, L))
+        for i in range(1, len(parent)):
+            f.write("%d %d %s %.17g\n" % (parent[i], leaf[i], " ".join(str(int(b)) for b in desc[i]), weight[i]))
