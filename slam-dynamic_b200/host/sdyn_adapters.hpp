@@ -301,8 +301,8 @@ inline int SearchByProjection(sdyn_ctx* ctx, KeyFrameT* pKF, cv::Mat Scw, const 
  * descent of all descriptors runs on the device; the two DBoW2 containers are then filled through their own
  * methods in the insertion order of TemplatedVocabulary::transform (TemplatedVocabulary.h:1147-1164, 1194), so
  * mBowVec / mFeatVec are the reference's objects with the reference's values. */
-template <class FrameT>
-inline bool ComputeBoW(sdyn_ctx* ctx, const sdyn_vocab* voc, FrameT& F)
+template <class FrameT, class LNormT>
+inline bool ComputeBoW(sdyn_ctx* ctx, const sdyn_vocab* voc, FrameT& F, LNormT l1Norm /* DBoW2::L1 */)
 {
     if (!F.mBowVec.empty()) return true;
     const int n = F.mDescriptors.rows;
@@ -312,7 +312,7 @@ inline bool ComputeBoW(sdyn_ctx* ctx, const sdyn_vocab* voc, FrameT& F)
     F.mBowVec.clear(); F.mFeatVec.clear();
     for (int i = 0; i < n; ++i)
         if (weight[i] > 0) { F.mBowVec.addWeight(word[i], weight[i]); F.mFeatVec.addFeature(node[i], (unsigned)i); }
-    F.mBowVec.normalize(DBoW2::L1);
+    F.mBowVec.normalize(l1Norm);
     return true;
 }
 
