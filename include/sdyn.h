@@ -246,6 +246,30 @@ int sdyn_match_projection_frame(sdyn_ctx* ctx, const sdyn_frame_view* cur, const
 int sdyn_match_projection_pose(sdyn_ctx* ctx, const sdyn_frame_view* target, const sdyn_proj_point* pts, int npts,
                                const sdyn_proj_params* params, int32_t* assign, int* nmatches);
 
+/* Independent best-keypoint search behind ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:
+ * 982-1130), ORBmatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (:1132-1257) and the two passes of
+ * ORBmatcher::SearchBySim3 (:1259-1483): every candidate MapPoint is projected, gated (depth, image, distance range,
+ * viewing angle, predicted level, reprojection chi-square) and given the keypoint of smallest descriptor distance in
+ * its window.  Nothing here depends on the other points, so the pointer-graph side effects of the reference (Replace,
+ * AddObservation, the mutual-agreement check) stay in the adapter and run over best_idx / best_dist.
+ * t1 (and t2 when use_t2): row-major [R|t] the point goes through, values of the reference's host expressions. */
+typedef struct {
+    float t1[12], t2[12];
+    int32_t use_t2;                 /* SearchBySim3: p3Dc2 = sR21*(R1w*p3Dw + t1w) + t21 */
+    float ow[3];                    /* camera centre (distance / viewing-angle gates) */
+    int32_t invz_double;            /* invz = 1.0/z in double (Fuse Scw, SearchBySim3) instead of float 1/z (Fuse) */
+    int32_t dist_from_camera;       /* dist3D = norm(p3Dc) (SearchBySim3) instead of norm(p3Dw - Ow) */
+    int32_t check_normal;           /* PO.dot(Pn) < 0.5*dist3D gate (both Fuse overloads) */
+    int32_t chi2_gate;              /* Fuse: e2*mvInvLevelSigma2[level] > 5.99 (mono) / 7.8 (stereo, target->u_right >= 0) */
+    float bf;                       /* mbf (stereo reprojection) */
+    float inv_level_sigma2[SDYN_MAX_LEVELS];
+    float th, log_scale_factor;
+    int32_t nlevels;
+} sdyn_best_params;
+/* best_idx[i] = keypoint of target or -1, best_dist[i] = its descriptor distance (256 when none). */
+int sdyn_match_projection_best(sdyn_ctx* ctx, const sdyn_frame_view* target, const sdyn_proj_point* pts, int npts,
+                               const sdyn_best_params* params, int32_t* best_idx, int32_t* best_dist);
+
 /* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:562-677.
  * prev_matched: f1->n x 2 floats, updated in place; matches12: f1->n. */
 int sdyn_match_init(sdyn_ctx* ctx, const sdyn_frame_view* f1, const sdyn_frame_view* f2, float* prev_matched,

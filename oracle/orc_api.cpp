@@ -181,6 +181,25 @@ int orc_match_projection_pose(const sdyn_frame_view* target, const sdyn_proj_poi
                                      prm->nlevels, assign);
 }
 
+/* which: 0 = Fuse(pKF, vpMapPoints, th), 1 = Fuse(pKF, Scw, ...) — search parts */
+void orc_fuse_search(int which, const sdyn_frame_view* kf, const float* invSigma2, const sdyn_proj_point* pts, int npts,
+                     const float* Rcw, const float* tcw, const float* Ow, float th, float logSf, int nlevels, int32_t* bestIdx, int32_t* bestDist)
+{
+    FrameView t = view_of(kf); Grid g; assign_features_to_grid(t, g);
+    const ProjPoint* pp = reinterpret_cast<const ProjPoint*>(pts);
+    if (which == 0) fuse_search(t, g, invSigma2, pp, npts, Rcw, tcw, Ow, th, logSf, nlevels, bestIdx, bestDist);
+    else fuse_sim3_search(t, g, pp, npts, Rcw, tcw, Ow, th, logSf, nlevels, bestIdx, bestDist);
+}
+
+int orc_search_by_sim3(const sdyn_frame_view* kf1, const sdyn_frame_view* kf2, const sdyn_proj_point* pts1, const sdyn_proj_point* pts2,
+                       const float* T1w, const float* T2w, const float* S12, const float* S21, float th, float logSf, int nlevels,
+                       int32_t* matches12)
+{
+    FrameView a = view_of(kf1), b = view_of(kf2); Grid g1, g2; assign_features_to_grid(a, g1); assign_features_to_grid(b, g2);
+    return search_by_sim3(a, g1, b, g2, reinterpret_cast<const ProjPoint*>(pts1), reinterpret_cast<const ProjPoint*>(pts2), T1w, T2w,
+                          S12, S21, th, logSf, nlevels, matches12);
+}
+
 /* ---- dynamic ----------------------------------------------------------------------------------- */
 void orc_box_mask(const sdyn_keypoint* keys, int n, const double* boxes, int nboxes, uint64_t* mask)
 {

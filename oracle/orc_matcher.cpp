@@ -486,4 +486,144 @@ int search_by_projection_sim3(const FrameView& KF, const Grid& gKF, const ProjPo
     return nmatches;
 }
 
+/* Search part of ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th),
+ * src/ORBmatcher.cc:982-1100: per MapPoint the keypoint Fuse would pick (bestIdx, bestDist); the Replace /
+ * AddObservation bookkeeping (:1103-1126) is pointer-graph code of the caller.  pts[i].valid stands for
+ * pMP && !pMP->isBad() && !pMP->IsInKeyFrame(pKF). */
+void fuse_search(const FrameView& KF, const Grid& gKF, const float* invLevelSigma2, const ProjPoint* pts, int npts,
+                 const float* Rcw, const float* tcw, const float* Ow, float th, float mfLogScaleFactor, int mnScaleLevels,
+                 int32_t* bestIdxOut, int32_t* bestDistOut)
+{
+    float T[12];
+    for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) T[4 * r + k] = Rcw[3 * r + k]; T[4 * r + 3] = tcw[r]; }
+    const float bf = KF.bf;
+    for (int i = 0; i < npts; ++i) {
+        bestIdxOut[i] = -1; bestDistOut[i] = 256;
+        if (!pts[i].valid) continue;
+        float p3Dc[3];
+        rx_plus_t(T, pts[i].world, p3Dc);
+        if (p3Dc[2] < 0.0f) continue;                                   /* :1015 */
+        const float invz = 1 / p3Dc[2];
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float u = KF.fx * x + KF.cx, v = KF.fy * y + KF.cy;
+        if (!(u >= KF.minX && u < KF.maxX && v >= KF.minY && v < KF.maxY)) continue;
+        const float ur = u - bf * invz;
+        float PO[3];
+        for (int k = 0; k < 3; ++k) PO[k] = pts[i].world[k] - Ow[k];
+        const float dist3D = (float)norm3(PO);
+        if (dist3D < pts[i].minDistance || dist3D > pts[i].maxDistance) continue;
+        if (dot3(PO, pts[i].normal) < 0.5 * dist3D) continue;           /* :1042 */
+        const int nPredictedLevel = predict_scale(pts[i].maxDistanceRaw, dist3D, mfLogScaleFactor, mnScaleLevels);
+        const float radius = th * KF.scaleFactors[nPredictedLevel];
+        const std::vector<int> vIndices = features_in_area(KF, gKF, u, v, radius, -1, -1);
+        if (vIndices.empty()) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            const KeyPoint& kp = KF.keysUn[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            if (KF.uRight && KF.uRight[idx] >= 0) {                     /* :1067-1080 */
+                const float kpx = kp.x, kpy = kp.y, kpr = KF.uRight[idx];
+                const float ex = u - kpx, ey = v - kpy, er = ur - kpr;
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * invLevelSigma2[kpLevel] > 7.8) continue;
+            } else {
+                const float kpx = kp.x, kpy = kp.y;
+                const float ex = u - kpx, ey = v - kpy;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * invLevelSigma2[kpLevel] > 5.99) continue;
+            }
+            const int dist = descriptor_distance(pts[i].desc, KF.desc + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        bestIdxOut[i] = bestIdx; bestDistOut[i] = bestDist;
+    }
+}
+
+/* Search part of ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw, const vector<MapPoint *> &vpPoints, float th,
+ * vector<MapPoint *> &vpReplacePoint), src/ORBmatcher.cc:1132-1237.  pts[i].valid: !isBad() && !spAlreadyFound.count(pMP). */
+void fuse_sim3_search(const FrameView& KF, const Grid& gKF, const ProjPoint* pts, int npts, const float* Rcw,
+                      const float* tcw, const float* Ow, float th, float mfLogScaleFactor, int mnScaleLevels,
+                      int32_t* bestIdxOut, int32_t* bestDistOut)
+{
+    float T[12];
+    for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) T[4 * r + k] = Rcw[3 * r + k]; T[4 * r + 3] = tcw[r]; }
+    for (int iMP = 0; iMP < npts; ++iMP) {
+        bestIdxOut[iMP] = -1; bestDistOut[iMP] = 256;
+        if (!pts[iMP].valid) continue;
+        float p3Dc[3];
+        rx_plus_t(T, pts[iMP].world, p3Dc);
+        if (p3Dc[2] < 0.0f) continue;
+        const float invz = (float)(1.0 / p3Dc[2]);                      /* :1176 */
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float u = KF.fx * x + KF.cx, v = KF.fy * y + KF.cy;
+        if (!(u >= KF.minX && u < KF.maxX && v >= KF.minY && v < KF.maxY)) continue;
+        float PO[3];
+        for (int k = 0; k < 3; ++k) PO[k] = pts[iMP].world[k] - Ow[k];
+        const float dist3D = (float)norm3(PO);
+        if (dist3D < pts[iMP].minDistance || dist3D > pts[iMP].maxDistance) continue;
+        if (dot3(PO, pts[iMP].normal) < 0.5 * dist3D) continue;
+        const int nPredictedLevel = predict_scale(pts[iMP].maxDistanceRaw, dist3D, mfLogScaleFactor, mnScaleLevels);
+        const float radius = th * KF.scaleFactors[nPredictedLevel];
+        const std::vector<int> vIndices = features_in_area(KF, gKF, u, v, radius, -1, -1);
+        if (vIndices.empty()) continue;
+        int bestDist = 0x7fffffff, bestIdx = -1;
+        for (int idx : vIndices) {
+            const int kpLevel = KF.keysUn[idx].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const int dist = descriptor_distance(pts[iMP].desc, KF.desc + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        bestIdxOut[iMP] = bestIdx; bestDistOut[iMP] = bestIdx >= 0 ? bestDist : 256;
+    }
+}
+
+/* ORBmatcher::SearchBySim3, src/ORBmatcher.cc:1259-1483.  pts1 / pts2: the MapPoints of KeyFrame 1 / 2 per keypoint
+ * (valid: pMP && !vbAlreadyMatched && !isBad()); T1w/T2w = [R|t] of the two keyframes; sR12|t12 and sR21|t21 the
+ * similarity in both directions as the reference derives them (:1276-1278).  matches12[i1] = i2 or -1 (only the NEW
+ * matches; the reference leaves earlier entries of vpMatches12 untouched). */
+int search_by_sim3(const FrameView& KF1, const Grid& g1, const FrameView& KF2, const Grid& g2, const ProjPoint* pts1,
+                   const ProjPoint* pts2, const float* T1w, const float* T2w, const float* S12, const float* S21, float th,
+                   float mfLogScaleFactor, int mnScaleLevels, int32_t* matches12)
+{
+    const int N1 = KF1.N, N2 = KF2.N;
+    std::vector<int> vnMatch1(N1, -1), vnMatch2(N2, -1);
+    auto pass = [&](const ProjPoint* pts, int n, const float* Tsrc, const float* S, const FrameView& dst, const Grid& g, std::vector<int>& out) {
+        for (int i = 0; i < n; ++i) {
+            if (!pts[i].valid) continue;
+            float pa[3], pb[3];
+            rx_plus_t(Tsrc, pts[i].world, pa);                          /* p3Dc1 = R1w*p3Dw + t1w */
+            rx_plus_t(S, pa, pb);                                       /* p3Dc2 = sR21*p3Dc1 + t21 */
+            if (pb[2] < 0.0) continue;
+            const float invz = (float)(1.0 / pb[2]);
+            const float x = pb[0] * invz, y = pb[1] * invz;
+            const float u = dst.fx * x + dst.cx, v = dst.fy * y + dst.cy;
+            if (!(u >= dst.minX && u < dst.maxX && v >= dst.minY && v < dst.maxY)) continue;
+            const float dist3D = (float)norm3(pb);
+            if (dist3D < pts[i].minDistance || dist3D > pts[i].maxDistance) continue;
+            const int nPredictedLevel = predict_scale(pts[i].maxDistanceRaw, dist3D, mfLogScaleFactor, mnScaleLevels);
+            const float radius = th * dst.scaleFactors[nPredictedLevel];
+            const std::vector<int> vIndices = features_in_area(dst, g, u, v, radius, -1, -1);
+            if (vIndices.empty()) continue;
+            int bestDist = 0x7fffffff, bestIdx = -1;
+            for (int idx : vIndices) {
+                const int oct = dst.keysUn[idx].octave;
+                if (oct < nPredictedLevel - 1 || oct > nPredictedLevel) continue;
+                const int dist = descriptor_distance(pts[i].desc, dst.desc + 32 * (size_t)idx);
+                if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+            }
+            if (bestDist <= TH_HIGH) out[i] = bestIdx;
+        }
+    };
+    pass(pts1, N1, T1w, S21, KF2, g2, vnMatch1);
+    pass(pts2, N2, T2w, S12, KF1, g1, vnMatch2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; ++i1) {                                   /* :1462-1478 */
+        matches12[i1] = -1;
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && vnMatch2[idx2] == i1) { matches12[i1] = idx2; ++nFound; }
+    }
+    return nFound;
+}
+
 }  // namespace orc

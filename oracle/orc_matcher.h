@@ -84,6 +84,17 @@ int search_by_projection_reloc(const FrameView& Cur, const Grid& gCur, const Pro
 int search_by_projection_sim3(const FrameView& KF, const Grid& gKF, const ProjPoint* pts, int npts, const float* Rcw,
                               const float* tcw, const float* Ow, int th, float mfLogScaleFactor, int mnScaleLevels, int32_t* assign);
 
+/* ORBmatcher.cc:982-1100 / 1132-1237 (search parts of the two Fuse overloads) and :1259-1483 */
+void fuse_search(const FrameView& KF, const Grid& gKF, const float* invLevelSigma2, const ProjPoint* pts, int npts,
+                 const float* Rcw, const float* tcw, const float* Ow, float th, float mfLogScaleFactor, int mnScaleLevels,
+                 int32_t* bestIdx, int32_t* bestDist);
+void fuse_sim3_search(const FrameView& KF, const Grid& gKF, const ProjPoint* pts, int npts, const float* Rcw,
+                      const float* tcw, const float* Ow, float th, float mfLogScaleFactor, int mnScaleLevels,
+                      int32_t* bestIdx, int32_t* bestDist);
+int search_by_sim3(const FrameView& KF1, const Grid& g1, const FrameView& KF2, const Grid& g2, const ProjPoint* pts1,
+                   const ProjPoint* pts2, const float* T1w, const float* T2w, const float* S12, const float* S21, float th,
+                   float mfLogScaleFactor, int mnScaleLevels, int32_t* matches12);
+
 struct FeatureVec {             /* DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>> as CSR */
     int nnodes = 0;
     const uint32_t* nodeId = nullptr;   /* ascending */

@@ -296,6 +296,56 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
                     load_desc(pp->desc, qd);
                 }
             }
+        } else if (J.mode == MM_BEST) {
+            /* Fuse(pKF, vpMapPoints, th) :982-1130, Fuse(pKF, Scw, ...) :1132-1257 and the two passes of SearchBySim3
+             * :1259-1483: project, gate, predict the level — the keypoint choice needs no claim bookkeeping */
+            const sdyn_proj_point* pp = reinterpret_cast<const sdyn_proj_point*>(J.queries) + q;
+            active = pp->valid;
+            if (active) {
+                float pc[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float s = __fadd_rn(__fadd_rn(__fmul_rn(J.Tcw[4 * k], pp->world[0]), __fmul_rn(J.Tcw[4 * k + 1], pp->world[1])),
+                                              __fmul_rn(J.Tcw[4 * k + 2], pp->world[2]));
+                    pc[k] = __fadd_rn(s, J.Tcw[4 * k + 3]);
+                }
+                if (J.useT2) {                           /* p3Dc2 = sR21*p3Dc1 + t21 */
+                    float p2[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float s = __fadd_rn(__fadd_rn(__fmul_rn(J.T2[4 * k], pc[0]), __fmul_rn(J.T2[4 * k + 1], pc[1])),
+                                                  __fmul_rn(J.T2[4 * k + 2], pc[2]));
+                        p2[k] = __fadd_rn(s, J.T2[4 * k + 3]);
+                    }
+                    pc[0] = p2[0]; pc[1] = p2[1]; pc[2] = p2[2];
+                }
+                if (pc[2] < 0.0f) active = false;
+                const float invz = J.invzDouble ? (float)(1.0 / (double)pc[2]) : __fdiv_rn(1.0f, pc[2]);
+                x = __fadd_rn(__fmul_rn(J.fx, __fmul_rn(pc[0], invz)), J.cx);
+                y = __fadd_rn(__fmul_rn(J.fy, __fmul_rn(pc[1], invz)), J.cy);
+                if (!(x >= J.minX && x < J.maxX && y >= J.minY && y < J.maxY)) active = false;    /* KeyFrame::IsInImage */
+                gateX = __fsub_rn(x, __fmul_rn(J.bf, invz));                                       /* ur = u - bf*invz */
+                float po0, po1, po2;
+                if (J.distFromCamera) { po0 = pc[0]; po1 = pc[1]; po2 = pc[2]; }
+                else { po0 = __fsub_rn(pp->world[0], J.Ow[0]); po1 = __fsub_rn(pp->world[1], J.Ow[1]); po2 = __fsub_rn(pp->world[2], J.Ow[2]); }
+                const double n2 = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)po0), __dmul_rn((double)po1, (double)po1)),
+                                            __dmul_rn((double)po2, (double)po2));
+                const float dist = (float)sqrt(n2);
+                if (dist < pp->min_distance || dist > pp->max_distance) active = false;
+                if (J.checkNormal) {
+                    const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)pp->normal[0]), __dmul_rn((double)po1, (double)pp->normal[1])),
+                                                 __dmul_rn((double)po2, (double)pp->normal[2]));
+                    if (dot < 0.5 * (double)dist) active = false;
+                }
+                if (active) {
+                    const float ratio = __fdiv_rn(pp->max_distance_raw, dist);
+                    int nScale = (int)ceilf(__fdiv_rn((float)log((double)ratio), J.logScaleFactor));
+                    nScale = nScale < 0 ? 0 : (nScale >= J.predLevels ? J.predLevels - 1 : nScale);
+                    r = __fmul_rn(J.th, J.scale[nScale]);
+                    minLevel = nScale - 1; maxLevel = nScale;
+                    load_desc(pp->desc, qd);
+                }
+            }
         } else if (J.mode == MM_MAP) {
             const sdyn_mappoint_query* mp = reinterpret_cast<const sdyn_mappoint_query*>(J.queries) + q;
             active = mp->track_in_view && !mp->bad;
@@ -365,6 +415,7 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
         const int loLevel = checkLevels ? minLevel : -0x7fffffff, hiLevel = (checkLevels && maxLevel >= 0) ? maxLevel : 0x7fffffff;
         const float* __restrict__ uRight = (J.mode == MM_FRAME || J.mode == MM_MAP) ? J.uRight : nullptr;
         const bool stereoGate = uRight != nullptr;
+        const bool chi2Gate = J.mode == MM_BEST && J.chi2Gate;
         /* Pass 1: walk the spans and keep what survives the level / window / stereo gates.  The entries of a span are
          * fetched four at a time before any of them is tested, so four loads are in flight per thread instead of one
          * dependent load per iteration (the walk is latency bound: ~45 entries per query, 2-3 survivors). */
@@ -385,18 +436,39 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
                         const float ur = ok ? uRight[io & 0xffffff] : -1.0f;
                         ok &= !(ur > 0 && fabsf(__fsub_rn(gateX, ur)) > gate);
                     }
+                    if (chi2Gate) {                         /* Fuse: reprojection error against the keypoint (:1067-1092) */
+                        const float kpr = (ok && J.uRight) ? J.uRight[io & 0xffffff] : -1.0f;
+                        const float ex = __fsub_rn(x, ge[k].x), ey = __fsub_rn(y, ge[k].y);
+                        float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                        const float s2 = J.invSigma2[oct & (SDYN_MAX_LEVELS - 1)];
+                        if (kpr >= 0) {
+                            const float er = __fsub_rn(gateX, kpr);
+                            e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                            ok &= !((double)__fmul_rn(e2, s2) > 7.8);
+                        } else {
+                            ok &= !((double)__fmul_rn(e2, s2) > 5.99);
+                        }
+                    }
                     if (ok) out[cnt] = (uint32_t)io;
                     cnt += ok;
                 }
             }
         }
         /* Pass 2: distances of the survivors (lanes with survivors left run together) */
+        uint32_t bestKey = 0xffffffffu;                   /* BEST: first candidate of smallest distance */
         for (int k = 0; k < cnt; ++k) {
             const int io = (int)out[k];
             const int idx = io & 0xffffff;
-            out[k] = pack_rec(idx, hamming256(qd, desc + 32 * (size_t)idx), io >> 24);
+            const int dist = hamming256(qd, desc + 32 * (size_t)idx);
+            out[k] = pack_rec(idx, dist, io >> 24);
+            bestKey = min(bestKey, ((uint32_t)dist << 20) | (uint32_t)k);
+        }
+        if (J.mode == MM_BEST) {
+            J.qAccepted[q] = bestKey != 0xffffffffu ? rec_idx(out[bestKey & 0xfffff]) : -1;
+            J.qBin[q] = bestKey != 0xffffffffu ? (int)(bestKey >> 20) : 256;
         }
     }
+    if (q < nq && J.mode == MM_BEST && !work) { J.qAccepted[q] = -1; J.qBin[q] = 256; }
     if (q < nq) J.qspan[q] = work ? make_int2(off, cnt) : make_int2(0, 0);
     /* distance evaluations (statistics): one atomic per warp */
     int ev = cnt;

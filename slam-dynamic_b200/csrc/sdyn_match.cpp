@@ -278,6 +278,61 @@ int sdyn_match_projection_pose(sdyn_ctx* c, const sdyn_frame_view* target, const
         });
 }
 
+int sdyn_match_projection_best(sdyn_ctx* c, const sdyn_frame_view* target, const sdyn_proj_point* pts, int npts,
+                               const sdyn_best_params* prm, int32_t* bestIdx, int32_t* bestDist)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (bad_view(target) || npts < 0 || (npts > 0 && (!pts || !bestIdx || !bestDist)) || !prm || !target->scale_factors ||
+        prm->nlevels < 1 || prm->nlevels > target->nlevels || !(prm->log_scale_factor > 0.0f))
+        return api_fail(c, SDYN_ERR_ARG, "sdyn_match_projection_best: bad argument");
+    for (int i = 0; i < npts; ++i) { bestIdx[i] = -1; bestDist[i] = 256; }
+    if (npts == 0 || target->n == 0) return SDYN_OK;
+    const size_t fixed = (size_t)target->n * 100 + (size_t)npts * (sizeof(sdyn_proj_point) + 16) + (kGridCells + 1) * 4;
+    MCU(c, cudaSetDevice(c->device));
+    int pool = 64 * npts;
+    const int poolMax = (int)std::min<long long>((long long)npts * target->n, 1 << 30);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        int rc = ensure_arena(c, fixed + (size_t)pool * 4 + (size_t)npts * 16 + sizeof(MatchJob) + (64 << 10));
+        if (rc != SDYN_OK) return rc;
+        Arena A(c);
+        MatchJob J; std::memset(&J, 0, sizeof(J));
+        J.mode = MM_BEST;
+        J.pool = A.take<uint32_t>(pool); J.poolCap = pool;
+        J.poolUsed = A.take<int32_t>(2); J.qNext = J.poolUsed + 1;
+        J.result = A.take<int32_t>(4);
+        J.qspan = A.take<int2>(npts); J.qAccepted = A.take<int32_t>(npts); J.qBin = A.take<int32_t>(npts);
+        MatchJob* dJob = A.take<MatchJob>(1);
+        stage_frame(A, target, J, true);
+        sdyn_proj_point* dq = A.take<sdyn_proj_point>(npts);
+        J.queries = dq; J.nq = npts; J.th = prm->th;
+        std::memcpy(J.Tcw, prm->t1, sizeof(J.Tcw)); std::memcpy(J.T2, prm->t2, sizeof(J.T2));
+        J.useT2 = prm->use_t2; J.invzDouble = prm->invz_double; J.distFromCamera = prm->dist_from_camera;
+        J.checkNormal = prm->check_normal; J.chi2Gate = prm->chi2_gate;
+        for (int k = 0; k < 3; ++k) J.Ow[k] = prm->ow[k];
+        for (int l = 0; l < SDYN_MAX_LEVELS; ++l) J.invSigma2[l] = prm->inv_level_sigma2[l];
+        J.fx = target->fx; J.fy = target->fy; J.cx = target->cx; J.cy = target->cy; J.bf = prm->bf;
+        J.logScaleFactor = prm->log_scale_factor; J.predLevels = prm->nlevels;
+        if (A.failed) { rc = ensure_arena(c, A.used + (1 << 20)); if (rc != SDYN_OK) return rc; continue; }
+        MCU(c, cudaMemsetAsync(J.poolUsed, 0, 2 * sizeof(int32_t), c->stream));
+        MCU(c, cudaMemsetAsync(J.result, 0, 4 * sizeof(int32_t), c->stream));
+        MCU(c, upload_frame(target, J, c->stream));
+        MCU(c, up(dq, pts, npts, c->stream));
+        MCU(c, cudaMemcpyAsync(dJob, &J, sizeof(J), cudaMemcpyHostToDevice, c->stream));
+        MCU(c, launch_grid_build(dJob, 1, c->stream));
+        MCU(c, launch_match_candidates(dJob, 1, npts, std::max(J.n, 1), c->stream));
+        c->launches += 2;
+        int32_t res[4];
+        MCU(c, cudaMemcpyAsync(res, J.result, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+        MCU(c, down(bestIdx, J.qAccepted, npts, c->stream));
+        MCU(c, down(bestDist, J.qBin, npts, c->stream));
+        MCU(c, cudaStreamSynchronize(c->stream));
+        if (res[2] && pool < poolMax) { pool = (int)std::min<long long>((long long)pool * 4, poolMax); continue; }
+        if (res[2]) return api_fail(c, SDYN_ERR_CAPACITY, "matcher candidate pool exhausted");
+        return SDYN_OK;
+    }
+    return api_fail(c, SDYN_ERR_CAPACITY, "matcher candidate pool exhausted");
+}
+
 int sdyn_match_init(sdyn_ctx* c, const sdyn_frame_view* f1, const sdyn_frame_view* f2, float* prevMatched,
                     int32_t* matches12, int window, float nnratio, int checkOri, int* nmatches)
 {

@@ -295,6 +295,146 @@ inline int SearchByProjection(sdyn_ctx* ctx, KeyFrameT* pKF, cv::Mat Scw, const 
         if (assign[i] >= 0) vpMatched[i] = vpPoints[assign[i]];
     return n;
 }
+template <class KeyFrameT>
+inline sdyn_frame_view keyframe_view(KeyFrameT* pKF)
+{
+    sdyn_frame_view v;
+    std::memset(&v, 0, sizeof(v));
+    v.n = pKF->N; v.nlevels = pKF->mnScaleLevels;
+    v.keys = v.keys_un = reinterpret_cast<const sdyn_keypoint*>(pKF->mvKeysUn.data());
+    v.desc = pKF->mDescriptors.data; v.scale_factors = pKF->mvScaleFactors.data();
+    v.u_right = pKF->mvuRight.empty() ? nullptr : pKF->mvuRight.data();
+    v.min_x = pKF->mnMinX; v.min_y = pKF->mnMinY; v.max_x = pKF->mnMaxX; v.max_y = pKF->mnMaxY;
+    v.fx = pKF->fx; v.fy = pKF->fy; v.cx = pKF->cx; v.cy = pKF->cy; v.bf = pKF->mbf;
+    return v;
+}
+
+inline void rigid_rows(const cv::Mat& R, const cv::Mat& t, float out[12])
+{
+    for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) out[4 * r + k] = R.at<float>(r, k); out[4 * r + 3] = t.at<float>(r); }
+}
+
+/* ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th)
+ * reference: src/ORBmatcher.cc:982-1130 (LocalMapping::SearchInNeighbors).  The keypoint choice of every MapPoint
+ * (:1000-1100) runs on the device; the Replace / AddObservation bookkeeping (:1103-1126) runs here in the
+ * reference's order, re-testing isBad() / IsInKeyFrame() at its turn because earlier iterations change them. */
+template <class KeyFrameT, class MapPointT>
+inline int Fuse(sdyn_ctx* ctx, KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, float th)
+{
+    const cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation(), Ow = pKF->GetCameraCenter();
+    std::vector<sdyn_proj_point> q(vpMapPoints.size());
+    for (size_t i = 0; i < vpMapPoints.size(); ++i)
+        proj_point(vpMapPoints[i], vpMapPoints[i] && !vpMapPoints[i]->isBad() && !vpMapPoints[i]->IsInKeyFrame(pKF), 0.f, q[i]);
+    sdyn_best_params p;
+    std::memset(&p, 0, sizeof(p));
+    rigid_rows(Rcw, tcw, p.t1);
+    for (int k = 0; k < 3; ++k) p.ow[k] = Ow.at<float>(k);
+    p.check_normal = 1; p.chi2_gate = 1; p.bf = pKF->mbf; p.th = th;
+    for (int l = 0; l < pKF->mnScaleLevels && l < SDYN_MAX_LEVELS; ++l) p.inv_level_sigma2[l] = pKF->mvInvLevelSigma2[l];
+    p.log_scale_factor = pKF->mfLogScaleFactor; p.nlevels = pKF->mnScaleLevels;
+    sdyn_frame_view v = keyframe_view(pKF);
+    std::vector<int32_t> bestIdx(q.size()), bestDist(q.size());
+    if (sdyn_match_projection_best(ctx, &v, q.data(), (int)q.size(), &p, bestIdx.data(), bestDist.data()) != SDYN_OK) return 0;
+    int nFused = 0;
+    for (size_t i = 0; i < vpMapPoints.size(); ++i) {
+        MapPointT* pMP = vpMapPoints[i];
+        if (!pMP || !q[i].valid) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;           /* state may have changed since the call started */
+        if (bestIdx[i] < 0 || bestDist[i] > SDYN_TH_LOW) continue;
+        MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx[i]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, bestIdx[i]);
+            pKF->AddMapPoint(pMP, bestIdx[i]);
+        }
+        ++nFused;
+    }
+    return nFused;
+}
+
+/* ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw, const vector<MapPoint *> &vpPoints, float th, vector<MapPoint *> &vpReplacePoint)
+ * reference: src/ORBmatcher.cc:1132-1257 (LoopClosing::SearchAndFuse) */
+template <class KeyFrameT, class MapPointT>
+inline int Fuse(sdyn_ctx* ctx, KeyFrameT* pKF, cv::Mat Scw, const std::vector<MapPointT*>& vpPoints, float th,
+                std::vector<MapPointT*>& vpReplacePoint)
+{
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    cv::Mat Rcw = sRcw / scw;
+    cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+    cv::Mat Ow = -Rcw.t() * tcw;
+    const std::set<MapPointT*> spAlreadyFound = pKF->GetMapPoints();
+    std::vector<sdyn_proj_point> q(vpPoints.size());
+    for (size_t i = 0; i < vpPoints.size(); ++i)
+        proj_point(vpPoints[i], !vpPoints[i]->isBad() && !spAlreadyFound.count(vpPoints[i]), 0.f, q[i]);
+    sdyn_best_params p;
+    std::memset(&p, 0, sizeof(p));
+    rigid_rows(Rcw, tcw, p.t1);
+    for (int k = 0; k < 3; ++k) p.ow[k] = Ow.at<float>(k);
+    p.invz_double = 1; p.check_normal = 1; p.th = th;
+    p.log_scale_factor = pKF->mfLogScaleFactor; p.nlevels = pKF->mnScaleLevels;
+    sdyn_frame_view v = keyframe_view(pKF);
+    v.u_right = nullptr;
+    std::vector<int32_t> bestIdx(q.size()), bestDist(q.size());
+    if (sdyn_match_projection_best(ctx, &v, q.data(), (int)q.size(), &p, bestIdx.data(), bestDist.data()) != SDYN_OK) return 0;
+    int nFused = 0;
+    for (size_t i = 0; i < vpPoints.size(); ++i) {
+        if (!q[i].valid || bestIdx[i] < 0 || bestDist[i] > SDYN_TH_LOW) continue;
+        MapPointT* pMPinKF = pKF->GetMapPoint(bestIdx[i]);
+        if (pMPinKF) { if (!pMPinKF->isBad()) vpReplacePoint[i] = pMPinKF; }
+        else { vpPoints[i]->AddObservation(pKF, bestIdx[i]); pKF->AddMapPoint(vpPoints[i], bestIdx[i]); }
+        ++nFused;
+    }
+    return nFused;
+}
+
+/* ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12, s12, R12, t12, th)
+ * reference: src/ORBmatcher.cc:1259-1483 (LoopClosing::ComputeSim3) */
+template <class KeyFrameT, class MapPointT>
+inline int SearchBySim3(sdyn_ctx* ctx, KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const float& s12,
+                        const cv::Mat& R12, const cv::Mat& t12, float th)
+{
+    cv::Mat R1w = pKF1->GetRotation(), t1w = pKF1->GetTranslation(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    cv::Mat sR12 = s12 * R12;                                           /* :1276-1278 */
+    cv::Mat sR21 = (1.0 / s12) * R12.t();
+    cv::Mat t21 = -sR21 * t12;
+    const std::vector<MapPointT*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)mp1.size(), N2 = (int)mp2.size();
+    std::vector<bool> done1(N1, false), done2(N2, false);
+    for (int i = 0; i < N1; ++i)
+        if (vpMatches12[i]) {
+            done1[i] = true;
+            const int idx2 = vpMatches12[i]->GetIndexInKeyFrame(pKF2);
+            if (idx2 >= 0 && idx2 < N2) done2[idx2] = true;
+        }
+    std::vector<sdyn_proj_point> q1(N1), q2(N2);
+    for (int i = 0; i < N1; ++i) proj_point(mp1[i], mp1[i] && !done1[i] && !mp1[i]->isBad(), 0.f, q1[i]);
+    for (int i = 0; i < N2; ++i) proj_point(mp2[i], mp2[i] && !done2[i] && !mp2[i]->isBad(), 0.f, q2[i]);
+    sdyn_best_params a, b;
+    std::memset(&a, 0, sizeof(a)); std::memset(&b, 0, sizeof(b));
+    rigid_rows(R1w, t1w, a.t1); rigid_rows(sR21, t21, a.t2);
+    rigid_rows(R2w, t2w, b.t1); rigid_rows(sR12, t12, b.t2);
+    a.use_t2 = b.use_t2 = 1; a.invz_double = b.invz_double = 1; a.dist_from_camera = b.dist_from_camera = 1; a.th = b.th = th;
+    a.log_scale_factor = pKF2->mfLogScaleFactor; a.nlevels = pKF2->mnScaleLevels;
+    b.log_scale_factor = pKF1->mfLogScaleFactor; b.nlevels = pKF1->mnScaleLevels;
+    sdyn_frame_view v1 = keyframe_view(pKF1), v2 = keyframe_view(pKF2);
+    v1.u_right = v2.u_right = nullptr;
+    std::vector<int32_t> i12(N1), d12(N1), i21(N2), d21(N2);
+    if (sdyn_match_projection_best(ctx, &v2, q1.data(), N1, &a, i12.data(), d12.data()) != SDYN_OK) return 0;
+    if (sdyn_match_projection_best(ctx, &v1, q2.data(), N2, &b, i21.data(), d21.data()) != SDYN_OK) return 0;
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; ++i1) {                                   /* :1462-1478 */
+        const int idx2 = (i12[i1] >= 0 && d12[i1] <= SDYN_TH_HIGH) ? i12[i1] : -1;
+        if (idx2 < 0) continue;
+        const int idx1 = (i21[idx2] >= 0 && d21[idx2] <= SDYN_TH_HIGH) ? i21[idx2] : -1;
+        if (idx1 == i1) { vpMatches12[i1] = mp2[idx2]; ++nFound; }
+    }
+    return nFound;
+}
 #endif  /* SDYN_HAVE_OPENCV */
 
 /* Frame::ComputeBoW() / KeyFrame::ComputeBoW() — reference: src/Frame.cc:803-810, src/KeyFrame.cc:76-86.  The tree

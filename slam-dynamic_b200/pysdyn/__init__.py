@@ -344,6 +344,33 @@ class ProjParamsC(C.Structure):
                 ("log_scale_factor", C.c_float), ("nlevels", C.c_int32)]
 
 
+class BestParamsC(C.Structure):
+    _fields_ = [("t1", C.c_float * 12), ("t2", C.c_float * 12), ("use_t2", C.c_int32), ("ow", C.c_float * 3),
+                ("invz_double", C.c_int32), ("dist_from_camera", C.c_int32), ("check_normal", C.c_int32), ("chi2_gate", C.c_int32),
+                ("bf", C.c_float), ("inv_level_sigma2", C.c_float * MAX_LEVELS), ("th", C.c_float), ("log_scale_factor", C.c_float),
+                ("nlevels", C.c_int32)]
+
+
+def best_params(t1, th, log_scale_factor, nlevels, t2=None, ow=(0, 0, 0), invz_double=False, dist_from_camera=False,
+                check_normal=False, chi2_gate=False, bf=0.0, inv_level_sigma2=None):
+    p = BestParamsC()
+    for i, v in enumerate(np.asarray(t1, np.float32).reshape(12)):
+        p.t1[i] = float(v)
+    if t2 is not None:
+        for i, v in enumerate(np.asarray(t2, np.float32).reshape(12)):
+            p.t2[i] = float(v)
+        p.use_t2 = 1
+    for i in range(3):
+        p.ow[i] = float(np.float32(ow[i]))
+    p.invz_double = int(invz_double); p.dist_from_camera = int(dist_from_camera); p.check_normal = int(check_normal)
+    p.chi2_gate = int(chi2_gate); p.bf = float(np.float32(bf))
+    if inv_level_sigma2 is not None:
+        for i, v in enumerate(inv_level_sigma2):
+            p.inv_level_sigma2[i] = float(np.float32(v))
+    p.th = th; p.log_scale_factor = float(np.float32(log_scale_factor)); p.nlevels = nlevels
+    return p
+
+
 def proj_params(rcw, tcw, ow, th, max_dist, variant, check_orientation, log_scale_factor, nlevels):
     p = ProjParamsC()
     for i, v in enumerate(np.asarray(rcw, np.float32).reshape(9)):
@@ -469,6 +496,27 @@ class Matcher:
         self.ex._check(self.L.sdyn_match_projection_pose(self.h, C.byref(target.c), pts.ctypes.data, len(pts), C.byref(params),
                                                          assign.ctypes.data, C.byref(n)))
         return n.value, assign
+
+    def ProjectionBest(self, target, points, params):
+        """Independent best keypoint per projected MapPoint (Fuse x2, SearchBySim3 passes): (best_idx, best_dist)."""
+        pts = np.ascontiguousarray(points, PROJPOINT_DTYPE)
+        bi = np.full(max(len(pts), 1), -1, np.int32); bd = np.full(max(len(pts), 1), 256, np.int32)
+        vp = C.c_void_p
+        self.L.sdyn_match_projection_best.argtypes = [vp, C.POINTER(FrameViewC), vp, C.c_int, C.POINTER(BestParamsC), vp, vp]
+        self.ex._check(self.L.sdyn_match_projection_best(self.h, C.byref(target.c), pts.ctypes.data, len(pts), C.byref(params),
+                                                         bi.ctypes.data, bd.ctypes.data))
+        return bi[:len(pts)], bd[:len(pts)]
+
+    def SearchBySim3(self, KF1, KF2, pts1, pts2, T1w, T2w, S12, S21, th, log_sf, nlevels):
+        """ORBmatcher::SearchBySim3 (:1259-1483): both projection passes on the device, TH_HIGH and the agreement check here."""
+        i12, d12 = self.ProjectionBest(KF2, pts1, best_params(T1w, th, log_sf, nlevels, t2=S21, invz_double=True, dist_from_camera=True))
+        i21, d21 = self.ProjectionBest(KF1, pts2, best_params(T2w, th, log_sf, nlevels, t2=S12, invz_double=True, dist_from_camera=True))
+        m1 = np.where(d12 <= 100, i12, -1); m2 = np.where(d21 <= 100, i21, -1)
+        out = np.full(KF1.n, -1, np.int32)
+        for i1 in range(KF1.n):
+            if m1[i1] >= 0 and m2[m1[i1]] == i1:
+                out[i1] = m1[i1]
+        return int((out >= 0).sum()), out
 
     def SearchForInitialization(self, F1, F2, prev_matched, window=100):
         prev = np.ascontiguousarray(prev_matched, np.float32).copy()

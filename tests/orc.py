@@ -251,6 +251,28 @@ def match_projection_pose(target, points, params, assign=None):
     return n, assign
 
 
+def fuse_search(which, KF, inv_sigma2, points, rcw, tcw, ow, th, log_sf, nlevels):
+    pts = np.ascontiguousarray(points, _structs().PROJPOINT_DTYPE)
+    bi = np.full(max(len(pts), 1), -1, np.int32); bd = np.full(max(len(pts), 1), 256, np.int32)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    r_, t_, o_, s_ = f(rcw).reshape(9), f(tcw), f(ow), f(inv_sigma2)
+    lib.orc_fuse_search.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    lib.orc_fuse_search(which, C.byref(KF.c), s_.ctypes.data, pts.ctypes.data, len(pts), r_.ctypes.data, t_.ctypes.data, o_.ctypes.data,
+                        th, float(np.float32(log_sf)), nlevels, bi.ctypes.data, bd.ctypes.data)
+    return bi[:len(pts)], bd[:len(pts)]
+
+
+def search_by_sim3(KF1, KF2, pts1, pts2, T1w, T2w, S12, S21, th, log_sf, nlevels):
+    p1 = np.ascontiguousarray(pts1, _structs().PROJPOINT_DTYPE); p2 = np.ascontiguousarray(pts2, _structs().PROJPOINT_DTYPE)
+    f = lambda a: np.ascontiguousarray(a, np.float32).reshape(12)
+    a, b, c, d = f(T1w), f(T2w), f(S12), f(S21)
+    m12 = np.full(KF1.n, -1, np.int32)
+    lib.orc_search_by_sim3.argtypes = [C.c_void_p] * 8 + [C.c_float, C.c_float, C.c_int, C.c_void_p]
+    n = lib.orc_search_by_sim3(C.byref(KF1.c), C.byref(KF2.c), p1.ctypes.data, p2.ctypes.data, a.ctypes.data, b.ctypes.data,
+                               c.ctypes.data, d.ctypes.data, th, float(np.float32(log_sf)), nlevels, m12.ctypes.data)
+    return n, m12
+
+
 def box_mask(keys, boxes):
     keys = np.ascontiguousarray(keys, KP_DTYPE)
     boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)

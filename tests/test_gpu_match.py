@@ -191,6 +191,51 @@ def test_search_by_projection_pose(ctx, request, data, variant, th, maxd):
     assert got[0] == ref[0] and np.array_equal(got[1], ref[1])
 
 
+def rt(R, t):
+    return np.concatenate([np.asarray(R, np.float32), np.asarray(t, np.float32).reshape(3, 1)], 1)
+
+
+@pytest.mark.parametrize("data", ["tum", "kitti"])
+@pytest.mark.parametrize("which,stereo", [(0, True), (0, False), (1, False)])
+def test_fuse_search(ctx, request, data, which, stereo):
+    """Search parts of the two ORBmatcher::Fuse overloads (:982-1100, :1132-1237)."""
+    p = request.getfixturevalue(data)
+    target, _ = views(p, stereo)
+    R, tcw, ow = scenario.pose_small(seed=5)
+    pts = scenario.proj_points(p["k1"], p["d1"], p["scale"], R, tcw, ow, seed=13, jitter=1.5)
+    inv_s2 = (1.0 / (p["scale"] * p["scale"])).astype(np.float32)
+    log_sf = np.log(np.float32(1.2))
+    prm = pysdyn.best_params(rt(R, tcw), 3.0, log_sf, 8, ow=ow, invz_double=(which == 1), check_normal=True, chi2_gate=(which == 0),
+                             bf=target.cam[4], inv_level_sigma2=inv_s2)
+    gi, gd = pysdyn.Matcher(ctx).ProjectionBest(target, pts, prm)
+    ri, rd = orc.fuse_search(which, target, inv_s2, pts, R, tcw, ow, 3.0, log_sf, 8)
+    assert np.array_equal(gi, ri) and np.array_equal(gd, rd)
+    assert ((ri >= 0) & (rd <= 50)).sum() > 100 and (ri < 0).sum() > 10
+
+
+@pytest.mark.parametrize("data", ["tum", "kitti"])
+def test_search_by_sim3(ctx, request, data):
+    """ORBmatcher::SearchBySim3 (:1259-1483): two chained transforms per point, both directions, agreement check."""
+    p = request.getfixturevalue(data)
+    kf2, kf1 = views(p, False)
+    eye = np.eye(3, dtype=np.float32)
+    R12, t12, _ = scenario.pose_small(seed=6, angle_deg=0.8, t=(0.03, 0.01, -0.05))
+    s12 = np.float32(1.03)
+    sR12 = (s12 * R12).astype(np.float32)
+    sR21 = ((np.float32(1.0) / s12) * R12.T).astype(np.float32)
+    t21 = (-(sR21 @ t12)).astype(np.float32)
+    zero = np.zeros(3, np.float32)
+    # MapPoints of each keyframe: back-projected through identity poses; the shift between the two synthetic frames
+    # plays the part of the similarity error the search has to absorb
+    pts1 = scenario.proj_points(p["k0"], p["d0"], p["scale"], eye, zero, zero, seed=21, p_valid=0.8)
+    pts2 = scenario.proj_points(p["k1"], p["d1"], p["scale"], eye, zero, zero, seed=22, p_valid=0.8)
+    log_sf = np.log(np.float32(1.2))
+    args = (kf1, kf2, pts1, pts2, rt(eye, zero), rt(eye, zero), rt(sR12, t12), rt(sR21, t21), 7.5, log_sf, 8)
+    got = pysdyn.Matcher(ctx).SearchBySim3(*args)
+    ref = orc.search_by_sim3(*args)
+    assert got[0] == ref[0] and got[0] > 50 and np.array_equal(got[1], ref[1])
+
+
 def test_empty_inputs(ctx, tum):
     p = tum
     cur, last = views(p, False)

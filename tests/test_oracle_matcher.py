@@ -385,3 +385,63 @@ def test_search_pose_oracle_vs_python(tum_pair, variant, th, maxd):
     assert got[0] == ref[0] and got[0] > 100 and np.array_equal(got[1], ref[1])
     # every gate of the reference must actually fire in this scenario
     assert (~pts["valid"].astype(bool)).any() and (got[1] == -2).any()
+
+
+def py_fuse_search(KF, inv_s2, pts, R, tcw, ow, th, log_sf, nlevels):
+    """Independent Python re-statement of the search part of Fuse(pKF, vpMapPoints, th), ORBmatcher.cc:982-1100."""
+    fx, fy, cx, cy, bf = (f32(v) for v in KF.cam[:5])
+    R = np.ascontiguousarray(R, np.float32); t = np.asarray(tcw, np.float32).reshape(3, 1); o = np.asarray(ow, np.float32).reshape(3, 1)
+    bi = np.full(len(pts), -1, np.int32); bd = np.full(len(pts), 256, np.int32)
+    for i, p in enumerate(pts):
+        if not p["valid"]:
+            continue
+        xw = p["world"].reshape(3, 1).astype(np.float32)
+        pc = cv2.gemm(R, xw, 1.0, t, 1.0).reshape(3)
+        if pc[2] < 0:
+            continue
+        invz = f32(f32(1) / pc[2])
+        u = f32(f32(fx * f32(pc[0] * invz)) + cx); v = f32(f32(fy * f32(pc[1] * invz)) + cy)
+        if not (u >= KF.bounds[0] and u < KF.bounds[2] and v >= KF.bounds[1] and v < KF.bounds[3]):
+            continue
+        ur = f32(u - f32(bf * invz))
+        po = cv2.subtract(xw, o)
+        dist = f32(cv2.norm(po))
+        if dist < p["min_distance"] or dist > p["max_distance"]:
+            continue
+        if float(po.reshape(3).astype(np.float64) @ p["normal"].astype(np.float64)) < 0.5 * float(dist):
+            continue
+        lvl = py_predict_scale(p["max_distance_raw"], dist, log_sf, nlevels)
+        radius = f32(f32(th) * KF.scale[lvl])
+        best, b = 256, -1
+        for j in py_features_in_area(KF, u, v, radius, -1, -1):
+            kp = KF.keys_un[j]
+            if not (lvl - 1 <= kp["octave"] <= lvl):
+                continue
+            ex = f32(u - kp["x"]); ey = f32(v - kp["y"])
+            if KF.u_right is not None and KF.u_right[j] >= 0:
+                er = f32(ur - KF.u_right[j])
+                e2 = f32(f32(f32(ex * ex) + f32(ey * ey)) + f32(er * er))
+                if float(f32(e2 * inv_s2[kp["octave"]])) > 7.8:
+                    continue
+            else:
+                e2 = f32(f32(ex * ex) + f32(ey * ey))
+                if float(f32(e2 * inv_s2[kp["octave"]])) > 5.99:
+                    continue
+            d = int(np.unpackbits(p["desc"] ^ KF.desc[j]).sum())
+            if d < best:
+                best, b = d, j
+        bi[i] = b; bd[i] = best
+    return bi, bd
+
+
+@pytest.mark.parametrize("stereo", [True, False])
+def test_fuse_search_oracle_vs_python(tum_pair, stereo):
+    p = tum_pair
+    KF = scenario.frame_view(p["k1"], p["d1"], p["scale"], p["W"], p["H"], stereo=stereo, seed=1)
+    R, tcw, ow = scenario.pose_small(seed=5)
+    pts = scenario.proj_points(p["k1"], p["d1"], p["scale"], R, tcw, ow, seed=13, jitter=1.5)[:400]
+    inv_s2 = (1.0 / (p["scale"] * p["scale"])).astype(np.float32)
+    log_sf = np.log(np.float32(1.2))
+    got = orc.fuse_search(0, KF, inv_s2, pts, R, tcw, ow, 3.0, log_sf, 8)
+    ref = py_fuse_search(KF, inv_s2, pts, R, tcw, ow, 3.0, log_sf, 8)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and (got[0] >= 0).sum() > 50
