@@ -270,6 +270,21 @@ typedef struct {
 int sdyn_match_projection_best(sdyn_ctx* ctx, const sdyn_frame_view* target, const sdyn_proj_point* pts, int npts,
                                const sdyn_best_params* params, int32_t* best_idx, int32_t* best_dist);
 
+/* ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, vector<pair<size_t,size_t>> &vMatchedPairs,
+ * const bool bOnlyStereo), src/ORBmatcher.cc:814-980 with CheckDistEpipolarLine (:140-157) — LocalMapping::CreateNewMapPoints.
+ * has_mp1 / has_mp2: pKF->GetMapPoint(idx) != NULL; u_right of the two views = mvuRight (NULL = monocular).  f12: row-major
+ * float F12; epipole: (ex, ey) of :823-829 as the reference's cv::Mat expressions give them; level_sigma2: pKF2->mvLevelSigma2.
+ * matches12[i1] = KeyFrame-2 index or -1 (vMatchedPairs = the pairs (i1, matches12[i1]) in ascending i1). */
+typedef struct {
+    float f12[9];
+    float epipole_x, epipole_y;
+    int32_t only_stereo, check_orientation;
+    float level_sigma2[SDYN_MAX_LEVELS];
+} sdyn_tri_params;
+int sdyn_match_triangulation(sdyn_ctx* ctx, const sdyn_frame_view* kf1, const uint8_t* has_mp1, const sdyn_feature_vector* fv1,
+                             const sdyn_frame_view* kf2, const uint8_t* has_mp2, const sdyn_feature_vector* fv2,
+                             const sdyn_tri_params* params, int32_t* matches12, int* nmatches);
+
 /* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:562-677.
  * prev_matched: f1->n x 2 floats, updated in place; matches12: f1->n. */
 int sdyn_match_init(sdyn_ctx* ctx, const sdyn_frame_view* f1, const sdyn_frame_view* f2, float* prev_matched,

@@ -200,6 +200,15 @@ int orc_search_by_sim3(const sdyn_frame_view* kf1, const sdyn_frame_view* kf2, c
                           S12, S21, th, logSf, nlevels, matches12);
 }
 
+int orc_match_triangulation(const sdyn_frame_view* kf1, const uint8_t* hasMp1, const sdyn_feature_vector* fa, const sdyn_frame_view* kf2,
+                            const uint8_t* hasMp2, const sdyn_feature_vector* fb, const sdyn_tri_params* prm, int32_t* matches12)
+{
+    FrameView a = view_of(kf1), b = view_of(kf2);
+    FeatureVec va{fa->nnodes, fa->node_id, fa->offset, fa->index}, vb{fb->nnodes, fb->node_id, fb->offset, fb->index};
+    return search_for_triangulation(a, hasMp1, va, b, hasMp2, vb, prm->f12, prm->epipole_x, prm->epipole_y, prm->level_sigma2,
+                                    prm->only_stereo != 0, prm->check_orientation != 0, matches12);
+}
+
 /* ---- dynamic ----------------------------------------------------------------------------------- */
 void orc_box_mask(const sdyn_keypoint* keys, int n, const double* boxes, int nboxes, uint64_t* mask)
 {

@@ -626,4 +626,77 @@ int search_by_sim3(const FrameView& KF1, const Grid& g1, const FrameView& KF2, c
     return nFound;
 }
 
+/* ORBmatcher::CheckDistEpipolarLine, src/ORBmatcher.cc:140-157 */
+static bool check_dist_epipolar_line(const KeyPoint& kp1, const KeyPoint& kp2, const float* F12, const float* mvLevelSigma2)
+{
+    const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+    const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+    const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+    const float num = a * kp2.x + b * kp2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * mvLevelSigma2[kp2.octave];
+}
+
+/* ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:814-980.  hasMp1/2: pKF->GetMapPoint(idx) != NULL; ex, ey: the
+ * epipole of :823-829.  matches12 = vMatches12 after the rotation cull (vMatchedPairs lists its non-negative entries). */
+int search_for_triangulation(const FrameView& KF1, const uint8_t* hasMp1, const FeatureVec& a, const FrameView& KF2,
+                             const uint8_t* hasMp2, const FeatureVec& b, const float* F12, float ex, float ey,
+                             const float* mvLevelSigma2, bool bOnlyStereo, bool checkOri, int32_t* matches12)
+{
+    int nmatches = 0;
+    std::vector<bool> vbMatched2(KF2.N, false);                         /* never set to true by the reference */
+    std::fill(matches12, matches12 + KF1.N, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int ia = 0, ib = 0;
+    while (ia < a.nnodes && ib < b.nnodes) {
+        if (a.nodeId[ia] == b.nodeId[ib]) {
+            for (int p = a.offset[ia]; p < a.offset[ia + 1]; ++p) {
+                const unsigned idx1 = a.index[p];
+                if (hasMp1[idx1]) continue;
+                const bool bStereo1 = KF1.uRight && KF1.uRight[idx1] >= 0;
+                if (bOnlyStereo) if (!bStereo1) continue;
+                const KeyPoint& kp1 = KF1.keysUn[idx1];
+                const uint8_t* d1 = KF1.desc + 32 * (size_t)idx1;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int q = b.offset[ib]; q < b.offset[ib + 1]; ++q) {
+                    const unsigned idx2 = b.index[q];
+                    if (vbMatched2[idx2] || hasMp2[idx2]) continue;
+                    const bool bStereo2 = KF2.uRight && KF2.uRight[idx2] >= 0;
+                    if (bOnlyStereo) if (!bStereo2) continue;
+                    const int dist = descriptor_distance(d1, KF2.desc + 32 * (size_t)idx2);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const KeyPoint& kp2 = KF2.keysUn[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2.x, distey = ey - kp2.y;
+                        if (distex * distex + distey * distey < 100 * KF2.scaleFactors[kp2.octave]) continue;
+                    }
+                    if (check_dist_epipolar_line(kp1, kp2, F12, mvLevelSigma2)) { bestIdx2 = (int)idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    matches12[idx1] = bestIdx2;
+                    ++nmatches;
+                    if (checkOri) rotHist[rot_bin(kp1.angle - KF2.keysUn[bestIdx2].angle)].push_back((int)idx1);
+                }
+            }
+            ++ia; ++ib;
+        } else if (a.nodeId[ia] < b.nodeId[ib]) {
+            ia = (int)(std::lower_bound(a.nodeId, a.nodeId + a.nnodes, b.nodeId[ib]) - a.nodeId);
+        } else {
+            ib = (int)(std::lower_bound(b.nodeId, b.nodeId + b.nnodes, a.nodeId[ia]) - b.nodeId);
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = (int)rotHist[i].size();
+        compute_three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx : rotHist[i]) { matches12[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
 }  // namespace orc

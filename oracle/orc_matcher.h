@@ -113,4 +113,9 @@ int search_by_bow_kf(const FrameView& KF1, const uint8_t* valid1, const FeatureV
 /* ORBmatcher.cc:1758-1799 */
 void compute_three_maxima(const int* histoSizes, int L, int& ind1, int& ind2, int& ind3);
 
+/* ORBmatcher.cc:814-980 (+ CheckDistEpipolarLine :140-157) */
+int search_for_triangulation(const FrameView& KF1, const uint8_t* hasMp1, const FeatureVec& fv1, const FrameView& KF2,
+                             const uint8_t* hasMp2, const FeatureVec& fv2, const float* F12, float ex, float ey,
+                             const float* mvLevelSigma2, bool bOnlyStereo, bool checkOri, int32_t* matches12);
+
 }  // namespace orc

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256)
 k_grid_build(const MatchJob* __restrict__ jobs)
 {
     const MatchJob& J = jobs[blockIdx.x];
-    if (J.mode == MM_BOW) return;
+    if (J.mode == MM_BOW || J.mode == MM_TRI) return;
     __shared__ int cnt[kGridCells];
     __shared__ int warpSum[8];
     const int tid = threadIdx.x, n = job_n(J);
@@ -181,7 +181,8 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
     const int32_t* cellOff = J.cellOff;
     const float4* gridEntry = J.gridEntry;
     const uint8_t* desc = J.desc;
-    if (J.mode != MM_BOW && stageGrid) {
+    const bool bowLike = J.mode == MM_BOW || J.mode == MM_TRI;     /* node-bucketed brute force: no grid */
+    if (!bowLike && stageGrid) {
         int32_t* sOff = reinterpret_cast<int32_t*>(smemC);
         float4* sEnt = reinterpret_cast<float4*>(smemC + kCellOffBytes);
         for (int i = threadIdx.x; i <= kGridCells; i += NT) sOff[i] = J.cellOff[i];
@@ -219,7 +220,7 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
     for (int k = 0; k < 8; ++k) qd[k] = 0;
 
     if (active) {
-        if (J.mode == MM_BOW) {
+        if (bowLike) {
             bq = reinterpret_cast<const BowQuery*>(J.queries)[q];
             load_desc(J.qDesc + 32 * (size_t)bq.kfIdx, qd);
         } else if (J.mode == MM_FRAME) {
@@ -371,7 +372,7 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
     }
 
     int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
-    if (active && J.mode != MM_BOW) {
+    if (active && !bowLike) {
         cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, J.minX), r), J.gridWInv)));
         cx1 = min(SDYN_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, J.minX), r), J.gridWInv)));
         cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, J.minY), r), J.gridHInv)));
@@ -382,7 +383,8 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
     /* upper bound of this query's list (all keypoints of the touched cells); ONE pool reservation per CTA */
     int bound = 0;
     if (active) {
-        if (J.mode == MM_BOW) bound = bq.fCnt;
+        if (J.mode == MM_TRI) bound = 0;
+        else if (J.mode == MM_BOW) bound = bq.fCnt;
         else
             for (int ix = cx0; ix <= cx1; ++ix)
                 bound += cellOff[ix * SDYN_GRID_ROWS + cy1 + 1] - cellOff[ix * SDYN_GRID_ROWS + cy0];
@@ -402,6 +404,44 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
     int cnt = 0;
 
     if (!work) {
+    } else if (J.mode == MM_TRI) {
+        /* ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:814-980: KeyFrame-1 feature q against the KeyFrame-2
+         * features of the same vocabulary node.  Nothing marks a feature as taken in the reference (vbMatched2 is never
+         * set), so every query is independent: the winner is the candidate of smallest distance that passes the gates,
+         * the LAST one among equals (`dist > bestDist` lets ties through).  Epipolar line l = x1' F12 (:140-157). */
+        const sdyn_keypoint kp1 = J.qKeys[bq.kfIdx];
+        const bool stereo1 = J.qURight && J.qURight[bq.kfIdx] >= 0;
+        const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, J.F12[0]), __fmul_rn(kp1.y, J.F12[3])), J.F12[6]);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, J.F12[1]), __fmul_rn(kp1.y, J.F12[4])), J.F12[7]);
+        const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, J.F12[2]), __fmul_rn(kp1.y, J.F12[5])), J.F12[8]);
+        const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+        uint32_t bestKey = 0xffffffffu;
+        for (int k = 0; k < bq.fCnt; ++k) {
+            const int idx2 = (int)J.fIndex[bq.fOff + k];
+            if (!J.fValid[idx2]) continue;                                   /* vbMatched2 (never set) || pMP2, bOnlyStereo */
+            const int dist = hamming256(qd, desc + 32 * (size_t)idx2);
+            if (dist > SDYN_TH_LOW) continue;
+            const sdyn_keypoint kp2 = J.keysUn[idx2];
+            const bool stereo2 = J.uRight && J.uRight[idx2] >= 0;
+            if (!stereo1 && !stereo2) {                                      /* too close to the epipole (:886-892) */
+                const float dx = __fsub_rn(J.epiX, kp2.x), dy = __fsub_rn(J.epiY, kp2.y);
+                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.0f, J.scale[kp2.octave & (SDYN_MAX_LEVELS - 1)])) continue;
+            }
+            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+            if (den == 0) continue;
+            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+            if (!((double)dsqr < 3.84 * (double)J.sigma2[kp2.octave & (SDYN_MAX_LEVELS - 1)])) continue;
+            bestKey = min(bestKey, ((uint32_t)dist << 20) | (uint32_t)(0xfffff - k));
+        }
+        int best = -1, bin = 0;
+        if (bestKey != 0xffffffffu) {
+            best = (int)J.fIndex[bq.fOff + (0xfffff - (int)(bestKey & 0xfffff))];
+            float rot = __fsub_rn(kp1.angle, J.keysUn[best].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            bin = (int)roundf(__fmul_rn(rot, 1.0f / SDYN_HISTO_LENGTH));
+            if (bin == SDYN_HISTO_LENGTH) bin = 0;
+        }
+        J.qAccepted[q] = best; J.qBin[q] = bin;
     } else if (J.mode == MM_BOW) {
         for (int k = 0; k < bq.fCnt; ++k) {
             const int idx = (int)J.fIndex[bq.fOff + k];
@@ -468,7 +508,7 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
             J.qBin[q] = bestKey != 0xffffffffu ? (int)(bestKey >> 20) : 256;
         }
     }
-    if (q < nq && J.mode == MM_BEST && !work) { J.qAccepted[q] = -1; J.qBin[q] = 256; }
+    if (q < nq && (J.mode == MM_BEST || J.mode == MM_TRI) && !work) { J.qAccepted[q] = -1; J.qBin[q] = 256; }
     if (q < nq) J.qspan[q] = work ? make_int2(off, cnt) : make_int2(0, 0);
     /* distance evaluations (statistics): one atomic per warp */
     int ev = cnt;

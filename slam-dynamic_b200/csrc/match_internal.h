@@ -6,7 +6,7 @@ namespace sdyn {
 
 constexpr int kGridCells = SDYN_GRID_COLS * SDYN_GRID_ROWS;   /* 3072 */
 
-enum MatchMode { MM_FRAME = 0, MM_MAP = 1, MM_INIT = 2, MM_BOW = 3, MM_POSE = 4, MM_BEST = 5 };
+enum MatchMode { MM_FRAME = 0, MM_MAP = 1, MM_INIT = 2, MM_BOW = 3, MM_POSE = 4, MM_BEST = 5, MM_TRI = 6 };
 
 /* query of the BoW search: one keyframe feature against the frame features of the same vocabulary node */
 struct BowQuery { int32_t kfIdx, fOff, fCnt; };
@@ -46,6 +46,10 @@ struct MatchJob {
     /* BEST (Fuse x2, SearchBySim3 passes): independent best keypoint per point, no claims */
     float T2[12]; int useT2, invzDouble, distFromCamera, checkNormal, chi2Gate;
     float invSigma2[SDYN_MAX_LEVELS];
+    /* TRI (SearchForTriangulation): F12 row-major, epipole, per-feature flags */
+    float F12[9], epiX, epiY, sigma2[SDYN_MAX_LEVELS];
+    const uint8_t* fValid;           /* searched feature may be matched (no MapPoint, stereo filter) */
+    const float* qURight;            /* mvuRight of the query keyframe, or null */
     int strictLow;                   /* BOW: accept best < TH_LOW (KeyFrame-KeyFrame overload) instead of <= (KeyFrame-Frame) */
     int assignBase;                  /* value written to assign[] = assignBase + query index (FRAME / MAP) */
     float Tcw[12], fx, fy, cx, cy, bf;

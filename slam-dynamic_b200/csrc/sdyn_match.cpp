@@ -468,6 +468,112 @@ int sdyn_match_bow_kf(sdyn_ctx* c, const sdyn_frame_view* kf1, const uint8_t* va
     return SDYN_OK;
 }
 
+int sdyn_match_triangulation(sdyn_ctx* c, const sdyn_frame_view* kf1, const uint8_t* hasMp1, const sdyn_feature_vector* a,
+                             const sdyn_frame_view* kf2, const uint8_t* hasMp2, const sdyn_feature_vector* b,
+                             const sdyn_tri_params* prm, int32_t* matches12, int* nmatches)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (!kf1 || !kf2 || !a || !b || !prm || !matches12 || !nmatches || kf1->n < 0 || kf2->n < 0 || kf2->n > 65535 ||
+        (kf1->n > 0 && (!hasMp1 || !kf1->desc || !kf1->keys_un)) || (kf2->n > 0 && (!hasMp2 || !kf2->desc || !kf2->keys_un)) ||
+        !kf2->scale_factors || kf2->nlevels < 1 || kf2->nlevels > SDYN_MAX_LEVELS)
+        return api_fail(c, SDYN_ERR_ARG, "sdyn_match_triangulation: bad argument");
+    *nmatches = 0;
+    for (int i = 0; i < kf1->n; ++i) matches12[i] = -1;
+    /* merge-join on node id (:850-946): one query per KeyFrame-1 feature without a MapPoint (and stereo if bOnlyStereo) */
+    std::vector<BowQuery> qs;
+    int ia = 0, ib = 0;
+    while (ia < a->nnodes && ib < b->nnodes) {
+        if (a->node_id[ia] == b->node_id[ib]) {
+            const int fo = b->offset[ib], fc = b->offset[ib + 1] - fo;
+            for (int p = a->offset[ia]; p < a->offset[ia + 1]; ++p) {
+                const uint32_t k = a->index[p];
+                if ((int)k >= kf1->n) return api_fail(c, SDYN_ERR_ARG, "feature vector index out of range");
+                if (hasMp1[k]) continue;
+                if (prm->only_stereo && !(kf1->u_right && kf1->u_right[k] >= 0)) continue;
+                qs.push_back({(int32_t)k, fo, fc});
+            }
+            ++ia; ++ib;
+        } else if (a->node_id[ia] < b->node_id[ib]) {
+            ia = (int)(std::lower_bound(a->node_id, a->node_id + a->nnodes, b->node_id[ib]) - a->node_id);
+        } else {
+            ib = (int)(std::lower_bound(b->node_id, b->node_id + b->nnodes, a->node_id[ia]) - b->node_id);
+        }
+    }
+    const int nq = (int)qs.size();
+    if (nq == 0 || kf2->n == 0) return SDYN_OK;
+    const int nIndex = b->offset[b->nnodes];
+    for (int i = 0; i < nIndex; ++i)
+        if ((int)b->index[i] >= kf2->n) return api_fail(c, SDYN_ERR_ARG, "feature vector index out of range");
+    std::vector<uint8_t> fValid((size_t)kf2->n);
+    for (int i = 0; i < kf2->n; ++i)
+        fValid[i] = !hasMp2[i] && (!prm->only_stereo || (kf2->u_right && kf2->u_right[i] >= 0));
+    MCU(c, cudaSetDevice(c->device));
+    const size_t need = (size_t)kf2->n * 110 + (size_t)kf1->n * 70 + (size_t)nq * 24 + (size_t)nIndex * 4 + sizeof(MatchJob) + (128 << 10);
+    std::vector<int32_t> acc((size_t)nq), bin((size_t)nq);
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        int rc = ensure_arena(c, need << attempt);
+        if (rc != SDYN_OK) return rc;
+        Arena A(c);
+        MatchJob J; std::memset(&J, 0, sizeof(J));
+        J.mode = MM_TRI;
+        J.pool = A.take<uint32_t>(64); J.poolCap = 64;
+        J.poolUsed = A.take<int32_t>(2); J.qNext = J.poolUsed + 1;
+        J.result = A.take<int32_t>(4);
+        J.qspan = A.take<int2>(nq); J.qAccepted = A.take<int32_t>(nq); J.qBin = A.take<int32_t>(nq);
+        MatchJob* dJob = A.take<MatchJob>(1);
+        sdyn_frame_view fv = *kf2;
+        if (!(fv.max_x > fv.min_x)) { fv.min_x = 0; fv.max_x = 1; }
+        if (!(fv.max_y > fv.min_y)) { fv.min_y = 0; fv.max_y = 1; }
+        stage_frame(A, &fv, J, false);
+        BowQuery* dq = A.take<BowQuery>(nq);
+        sdyn_keypoint* dk = A.take<sdyn_keypoint>(kf1->n);
+        uint8_t* dd = A.take<uint8_t>((size_t)32 * kf1->n);
+        uint32_t* di = A.take<uint32_t>(nIndex);
+        uint8_t* dv = A.take<uint8_t>(kf2->n);
+        float* dur = kf1->u_right ? A.take<float>(kf1->n) : nullptr;
+        if (A.failed) continue;
+        J.queries = dq; J.qKeys = dk; J.qDesc = dd; J.fIndex = di; J.nq = nq; J.fValid = dv; J.qURight = dur;
+        std::memcpy(J.F12, prm->f12, sizeof(J.F12)); J.epiX = prm->epipole_x; J.epiY = prm->epipole_y;
+        for (int l = 0; l < SDYN_MAX_LEVELS; ++l) J.sigma2[l] = prm->level_sigma2[l];
+        MCU(c, cudaMemsetAsync(J.poolUsed, 0, 2 * sizeof(int32_t), c->stream));
+        MCU(c, cudaMemsetAsync(J.result, 0, 4 * sizeof(int32_t), c->stream));
+        MCU(c, upload_frame(&fv, J, c->stream));
+        MCU(c, up(dq, qs.data(), nq, c->stream));
+        MCU(c, up(dk, kf1->keys_un, kf1->n, c->stream));
+        MCU(c, up(dd, kf1->desc, (size_t)32 * kf1->n, c->stream));
+        MCU(c, up(di, b->index, nIndex, c->stream));
+        MCU(c, up(dv, fValid.data(), kf2->n, c->stream));
+        if (dur) MCU(c, up(dur, kf1->u_right, kf1->n, c->stream));
+        MCU(c, cudaMemcpyAsync(dJob, &J, sizeof(J), cudaMemcpyHostToDevice, c->stream));
+        MCU(c, launch_match_candidates(dJob, 1, nq, std::max(J.n, 1), c->stream));
+        c->launches += 1;
+        MCU(c, down(acc.data(), J.qAccepted, nq, c->stream));
+        MCU(c, down(bin.data(), J.qBin, nq, c->stream));
+        MCU(c, cudaStreamSynchronize(c->stream));
+        /* rotation histogram and its three-maxima cull (:920-965) over at most N matches: host code */
+        int n = 0;
+        int hist[SDYN_HISTO_LENGTH] = {0};
+        for (int q = 0; q < nq; ++q)
+            if (acc[q] >= 0) { matches12[qs[q].kfIdx] = acc[q]; ++n; ++hist[bin[q]]; }
+        if (prm->check_orientation) {
+            int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < SDYN_HISTO_LENGTH; ++i) {
+                const int sz = hist[i];
+                if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; i3 = i2; i2 = i1; i1 = i; }
+                else if (sz > max2) { max3 = max2; max2 = sz; i3 = i2; i2 = i; }
+                else if (sz > max3) { max3 = sz; i3 = i; }
+            }
+            if ((float)max2 < 0.1f * (float)max1) { i2 = -1; i3 = -1; }
+            else if ((float)max3 < 0.1f * (float)max1) i3 = -1;
+            for (int q = 0; q < nq; ++q)
+                if (acc[q] >= 0 && bin[q] != i1 && bin[q] != i2 && bin[q] != i3) { matches12[qs[q].kfIdx] = -1; --n; }
+        }
+        *nmatches = n;
+        return SDYN_OK;
+    }
+    return api_fail(c, SDYN_ERR_NOMEM, "sdyn_match_triangulation: arena");
+}
+
 int sdyn_dyn_box_mask(sdyn_ctx* c, const sdyn_keypoint* keys, int n, const double* boxes, int nboxes, uint64_t* mask)
 {
     if (!c) return SDYN_ERR_ARG;

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstring>
 #include <set>
+#include <utility>
 #include <vector>
 
 namespace sdyn_host {
@@ -434,6 +435,39 @@ inline int SearchBySim3(sdyn_ctx* ctx, KeyFrameT* pKF1, KeyFrameT* pKF2, std::ve
         if (idx1 == i1) { vpMatches12[i1] = mp2[idx2]; ++nFound; }
     }
     return nFound;
+}
+
+/* ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, vector<pair<size_t,size_t>> &vMatchedPairs,
+ * const bool bOnlyStereo) — reference: src/ORBmatcher.cc:814-980 (LocalMapping::CreateNewMapPoints, LocalMapping.cc:269) */
+template <class KeyFrameT>
+inline int SearchForTriangulation(sdyn_ctx* ctx, KeyFrameT* pKF1, KeyFrameT* pKF2, cv::Mat F12,
+                                  std::vector<std::pair<size_t, size_t> >& vMatchedPairs, bool bOnlyStereo, bool checkOrientation)
+{
+    cv::Mat Cw = pKF1->GetCameraCenter();                               /* epipole in the second image, :823-829 */
+    cv::Mat R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    cv::Mat C2 = R2w * Cw + t2w;
+    const float invz = 1.0f / C2.at<float>(2);
+    sdyn_tri_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.epipole_x = pKF2->fx * C2.at<float>(0) * invz + pKF2->cx;
+    p.epipole_y = pKF2->fy * C2.at<float>(1) * invz + pKF2->cy;
+    for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) p.f12[3 * r + k] = F12.at<float>(r, k);
+    p.only_stereo = bOnlyStereo; p.check_orientation = checkOrientation;
+    for (int l = 0; l < pKF2->mnScaleLevels && l < SDYN_MAX_LEVELS; ++l) p.level_sigma2[l] = pKF2->mvLevelSigma2[l];
+    std::vector<uint8_t> h1(pKF1->N), h2(pKF2->N);
+    for (int i = 0; i < pKF1->N; ++i) h1[i] = pKF1->GetMapPoint(i) != nullptr;
+    for (int i = 0; i < pKF2->N; ++i) h2[i] = pKF2->GetMapPoint(i) != nullptr;
+    sdyn_frame_view a = keyframe_view(pKF1), b = keyframe_view(pKF2);
+    FeatureVectorCSR fa(pKF1->mFeatVec), fb(pKF2->mFeatVec);
+    sdyn_feature_vector av = fa.view(), bv = fb.view();
+    std::vector<int32_t> m12(pKF1->N, -1);
+    int n = 0;
+    vMatchedPairs.clear();
+    if (sdyn_match_triangulation(ctx, &a, h1.data(), &av, &b, h2.data(), &bv, &p, m12.data(), &n) != SDYN_OK) return 0;
+    vMatchedPairs.reserve(n);
+    for (size_t i = 0; i < m12.size(); ++i)
+        if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
+    return n;
 }
 #endif  /* SDYN_HAVE_OPENCV */
 

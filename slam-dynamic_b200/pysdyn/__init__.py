@@ -344,6 +344,22 @@ class ProjParamsC(C.Structure):
                 ("log_scale_factor", C.c_float), ("nlevels", C.c_int32)]
 
 
+class TriParamsC(C.Structure):
+    _fields_ = [("f12", C.c_float * 9), ("epipole_x", C.c_float), ("epipole_y", C.c_float), ("only_stereo", C.c_int32),
+                ("check_orientation", C.c_int32), ("level_sigma2", C.c_float * MAX_LEVELS)]
+
+
+def tri_params(f12, epipole, only_stereo, check_orientation, level_sigma2):
+    p = TriParamsC()
+    for i, v in enumerate(np.asarray(f12, np.float32).reshape(9)):
+        p.f12[i] = float(v)
+    p.epipole_x, p.epipole_y = float(np.float32(epipole[0])), float(np.float32(epipole[1]))
+    p.only_stereo = int(only_stereo); p.check_orientation = int(check_orientation)
+    for i, v in enumerate(level_sigma2):
+        p.level_sigma2[i] = float(np.float32(v))
+    return p
+
+
 class BestParamsC(C.Structure):
     _fields_ = [("t1", C.c_float * 12), ("t2", C.c_float * 12), ("use_t2", C.c_int32), ("ow", C.c_float * 3),
                 ("invz_double", C.c_int32), ("dist_from_camera", C.c_int32), ("check_normal", C.c_int32), ("chi2_gate", C.c_int32),
@@ -517,6 +533,17 @@ class Matcher:
             if m1[i1] >= 0 and m2[m1[i1]] == i1:
                 out[i1] = m1[i1]
         return int((out >= 0).sum()), out
+
+    def SearchForTriangulation(self, KF1, has_mp1, fv1, KF2, has_mp2, fv2, params):
+        """ORBmatcher::SearchForTriangulation (:814-980): (nmatches, matches12)."""
+        h1 = np.ascontiguousarray(has_mp1, np.uint8); h2 = np.ascontiguousarray(has_mp2, np.uint8)
+        m12 = np.full(KF1.n, -1, np.int32); n = C.c_int(0)
+        vp = C.c_void_p
+        self.L.sdyn_match_triangulation.argtypes = [vp, C.POINTER(FrameViewC), vp, C.POINTER(FeatureVectorC), C.POINTER(FrameViewC), vp,
+                                                    C.POINTER(FeatureVectorC), C.POINTER(TriParamsC), vp, C.POINTER(C.c_int)]
+        self.ex._check(self.L.sdyn_match_triangulation(self.h, C.byref(KF1.c), h1.ctypes.data, C.byref(fv1.c), C.byref(KF2.c),
+                                                       h2.ctypes.data, C.byref(fv2.c), C.byref(params), m12.ctypes.data, C.byref(n)))
+        return n.value, m12
 
     def SearchForInitialization(self, F1, F2, prev_matched, window=100):
         prev = np.ascontiguousarray(prev_matched, np.float32).copy()

@@ -273,6 +273,15 @@ def search_by_sim3(KF1, KF2, pts1, pts2, T1w, T2w, S12, S21, th, log_sf, nlevels
     return n, m12
 
 
+def match_triangulation(KF1, has_mp1, fv1, KF2, has_mp2, fv2, params):
+    h1 = np.ascontiguousarray(has_mp1, np.uint8); h2 = np.ascontiguousarray(has_mp2, np.uint8)
+    m12 = np.full(KF1.n, -1, np.int32)
+    lib.orc_match_triangulation.argtypes = [C.c_void_p] * 8
+    n = lib.orc_match_triangulation(C.byref(KF1.c), h1.ctypes.data, C.byref(fv1.c), C.byref(KF2.c), h2.ctypes.data, C.byref(fv2.c),
+                                    C.byref(params), m12.ctypes.data)
+    return n, m12
+
+
 def box_mask(keys, boxes):
     keys = np.ascontiguousarray(keys, KP_DTYPE)
     boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)

@@ -236,6 +236,36 @@ def test_search_by_sim3(ctx, request, data):
     assert got[0] == ref[0] and got[0] > 50 and np.array_equal(got[1], ref[1])
 
 
+@pytest.mark.parametrize("data", ["tum", "kitti"])
+@pytest.mark.parametrize("stereo,only_stereo", [(False, False), (True, False), (True, True)])
+def test_search_for_triangulation(ctx, request, data, stereo, only_stereo):
+    """ORBmatcher::SearchForTriangulation (:814-980) incl. CheckDistEpipolarLine and the epipole exclusion zone."""
+    p = request.getfixturevalue(data)
+    kf2, kf1 = views(p, stereo)
+    fa = pysdyn.FeatureVector(scenario.bow_nodes(p["d0"], 4)); fb = pysdyn.FeatureVector(scenario.bow_nodes(p["d1"], 4))
+    r = np.random.default_rng(8)
+    h1 = (r.random(kf1.n) < 0.3).astype(np.uint8); h2 = (r.random(kf2.n) < 0.3).astype(np.uint8)
+    # fundamental matrix of a pure image shift (dx, dy): lines through x1 + shift with direction along the shift, wide
+    # enough a band that both accepted and rejected pairs occur; epipole placed inside the image to exercise :886-892
+    dx, dy = p["shift"]
+    F12 = np.array([[0, 0, dy], [0, 0, -dx], [-dy, dx, 0]], np.float32) * np.float32(0.01)
+    sig2 = (p["scale"] * p["scale"]).astype(np.float32)
+    for check in (True, False):
+        prm = pysdyn.tri_params(F12, (p["W"] * 0.4, p["H"] * 0.5), only_stereo, check, sig2)
+        got = pysdyn.Matcher(ctx, 0.6, check).SearchForTriangulation(kf1, h1, fa, kf2, h2, fb, prm)
+        ref = orc.match_triangulation(kf1, h1, fa, kf2, h2, fb, prm)
+        assert got[0] == ref[0] and np.array_equal(got[1], ref[1])
+        assert got[0] > 20 and (h1[got[1] >= 0] == 0).all() and (h2[got[1][got[1] >= 0]] == 0).all()
+    # tie-heavy descriptors: the LAST candidate among equal distances wins (`dist > bestDist`)
+    d0 = scenario.degenerate_descriptors(kf1.n, 31, 30); d1 = scenario.degenerate_descriptors(kf2.n, 32, 30)
+    kf2, kf1 = views(p, stereo, d0=d0, d1=d1)
+    fa = pysdyn.FeatureVector(scenario.bow_nodes(d0, 2)); fb = pysdyn.FeatureVector(scenario.bow_nodes(d1, 2))
+    prm = pysdyn.tri_params(F12, (-500.0, -500.0), only_stereo, True, sig2)
+    got = pysdyn.Matcher(ctx, 0.6, True).SearchForTriangulation(kf1, h1, fa, kf2, h2, fb, prm)
+    ref = orc.match_triangulation(kf1, h1, fa, kf2, h2, fb, prm)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1])
+
+
 def test_empty_inputs(ctx, tum):
     p = tum
     cur, last = views(p, False)

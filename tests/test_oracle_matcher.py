@@ -445,3 +445,71 @@ def test_fuse_search_oracle_vs_python(tum_pair, stereo):
     got = orc.fuse_search(0, KF, inv_s2, pts, R, tcw, ow, 3.0, log_sf, 8)
     ref = py_fuse_search(KF, inv_s2, pts, R, tcw, ow, 3.0, log_sf, 8)
     assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and (got[0] >= 0).sum() > 50
+
+
+def py_search_triangulation(kf1, h1, nodes1, kf2, h2, nodes2, F12, epi, sig2, only_stereo, check_ori):
+    """Independent Python re-statement of SearchForTriangulation + CheckDistEpipolarLine, ORBmatcher.cc:814-980, 140-157."""
+    def fmap(nodes):
+        m = {}
+        for i, nd in enumerate(nodes):
+            m.setdefault(int(nd), []).append(i)
+        return m
+    f1, f2 = fmap(nodes1), fmap(nodes2)
+    F = np.asarray(F12, np.float32)
+    m12 = np.full(kf1.n, -1, np.int32); hist = [[] for _ in range(30)]; n = 0
+    st1 = (lambda i: kf1.u_right is not None and kf1.u_right[i] >= 0); st2 = (lambda i: kf2.u_right is not None and kf2.u_right[i] >= 0)
+    for node in sorted(set(f1) & set(f2)):
+        for i1 in f1[node]:
+            if h1[i1] or (only_stereo and not st1(i1)):
+                continue
+            k1 = kf1.keys_un[i1]
+            a = f32(f32(f32(k1["x"] * F[0, 0]) + f32(k1["y"] * F[1, 0])) + F[2, 0])
+            b = f32(f32(f32(k1["x"] * F[0, 1]) + f32(k1["y"] * F[1, 1])) + F[2, 1])
+            c = f32(f32(f32(k1["x"] * F[0, 2]) + f32(k1["y"] * F[1, 2])) + F[2, 2])
+            best, bi = 50, -1
+            for i2 in f2[node]:
+                if h2[i2] or (only_stereo and not st2(i2)):
+                    continue
+                d = int(np.unpackbits(kf1.desc[i1] ^ kf2.desc[i2]).sum())
+                if d > 50 or d > best:
+                    continue
+                k2 = kf2.keys_un[i2]
+                if not st1(i1) and not st2(i2):
+                    ex = f32(f32(epi[0]) - k2["x"]); ey = f32(f32(epi[1]) - k2["y"])
+                    if f32(f32(ex * ex) + f32(ey * ey)) < f32(f32(100) * kf2.scale[k2["octave"]]):
+                        continue
+                num = f32(f32(f32(a * k2["x"]) + f32(b * k2["y"])) + c)
+                den = f32(f32(a * a) + f32(b * b))
+                if den == 0:
+                    continue
+                dsqr = f32(f32(num * num) / den)
+                if float(dsqr) < 3.84 * float(sig2[k2["octave"]]):
+                    best, bi = d, i2
+            if bi >= 0:
+                m12[i1] = bi; n += 1
+                if check_ori:
+                    hist[py_rot_bin(k1["angle"], kf2.keys_un["angle"][bi])].append(i1)
+    if check_ori:
+        keep = py_three_maxima([len(h) for h in hist])
+        for i, h in enumerate(hist):
+            if i not in keep:
+                for idx in h:
+                    m12[idx] = -1; n -= 1
+    return n, m12
+
+
+@pytest.mark.parametrize("stereo,only_stereo", [(False, False), (True, True)])
+def test_search_triangulation_oracle_vs_python(tum_pair, stereo, only_stereo):
+    p = tum_pair
+    kf1 = scenario.frame_view(p["k0"], p["d0"], p["scale"], p["W"], p["H"], stereo=stereo, seed=0)
+    kf2 = scenario.frame_view(p["k1"], p["d1"], p["scale"], p["W"], p["H"], stereo=stereo, seed=1)
+    n1, n2 = scenario.bow_nodes(p["d0"], 4), scenario.bow_nodes(p["d1"], 4)
+    r = np.random.default_rng(8)
+    h1 = (r.random(kf1.n) < 0.3).astype(np.uint8); h2 = (r.random(kf2.n) < 0.3).astype(np.uint8)
+    F12 = np.array([[0, 0, 1], [0, 0, -4], [-1, 4, 0]], np.float32) * np.float32(0.01)
+    sig2 = (p["scale"] * p["scale"]).astype(np.float32)
+    epi = (p["W"] * 0.4, p["H"] * 0.5)
+    prm = pysdyn.tri_params(F12, epi, only_stereo, True, sig2)
+    got = orc.match_triangulation(kf1, h1, pysdyn.FeatureVector(n1), kf2, h2, pysdyn.FeatureVector(n2), prm)
+    ref = py_search_triangulation(kf1, h1, n1, kf2, h2, n2, F12, epi, sig2, only_stereo, True)
+    assert got[0] == ref[0] and got[0] > 50 and np.array_equal(got[1], ref[1])
