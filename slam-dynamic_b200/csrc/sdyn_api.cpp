@@ -175,6 +175,20 @@ int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frame
         StageTimer t(c, st, SDYN_STAGE_PYRAMID);
         for (int l = 1; l < g.nlevels; ++l) CU(c, launch_resize(g, l, c->dTables, c->dPyr, nframes, st));
     }
+    /* The blur only needs the pyramid, FAST + octree only need the pyramid: two branches on two streams, joined in
+     * front of the descriptor kernel (which reads the blurred levels and the selected keypoints). */
+    /* (while per-stage profiling is on, everything stays on one stream so that stage times are not inflated by overlap) */
+    const bool fork = !c->profiling;
+    cudaStream_t bs = fork ? c->aux : st;
+    if (fork) {
+        CU(c, cudaEventRecord(c->evFork, st));
+        CU(c, cudaStreamWaitEvent(c->aux, c->evFork, 0));
+    }
+    {
+        StageTimer t(c, bs, SDYN_STAGE_BLUR);
+        CU(c, launch_blur(g, c->dBlurTiles, c->nBlurTiles, c->dPyr, c->dBlur, nframes, bs));
+    }
+    if (fork) CU(c, cudaEventRecord(c->evJoin, c->aux));
     {
         StageTimer t(c, st, SDYN_STAGE_FAST);
         CU(c, launch_fast(g, c->dFastTiles, c->nFastTiles, c->dPyr, p.ini_th_fast, p.min_th_fast, c->dCellFlag,
@@ -185,10 +199,7 @@ int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frame
         CU(c, launch_octree(g, p.ini_th_fast, p.min_th_fast, c->dCellFlag, c->dCand, c->dCandCount, c->dCandNode,
                             c->dSelCount, c->dLevelKp, c->dLevelCount, c->dStatus, nframes, st));
     }
-    {
-        StageTimer t(c, st, SDYN_STAGE_BLUR);
-        CU(c, launch_blur(g, c->dBlurTiles, c->nBlurTiles, c->dPyr, c->dBlur, nframes, st));
-    }
+    if (fork) CU(c, cudaStreamWaitEvent(st, c->evJoin, 0));
     {
         StageTimer t(c, st, SDYN_STAGE_DESCRIBE);
         CU(c, launch_orient_describe(g, c->dPyr, c->dBlur, c->dLevelKp, c->dLevelCount, c->dKp, c->dDesc, c->dCount,
@@ -218,6 +229,11 @@ void free_all(sdyn_ctx* c)
     cudaFreeHost(c->hKp); cudaFreeHost(c->hDesc); cudaFreeHost(c->hCount); cudaFreeHost(c->hStatus);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->evPool) cudaEventDestroy(e);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
+    if (c->evFork2) cudaEventDestroy(c->evFork2);
+    if (c->evJoin2) cudaEventDestroy(c->evJoin2);
+    if (c->aux) cudaStreamDestroy(c->aux);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -265,6 +281,9 @@ int sdyn_create(const sdyn_orb_params* params, int maxW, int maxH, int maxBatch,
     cudaError_t ce = cudaSuccess;
     auto A = [&](cudaError_t r) { if (ce == cudaSuccess) ce = r; };
     A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    A(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming)); A(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&c->evFork2, cudaEventDisableTiming)); A(cudaEventCreateWithFlags(&c->evJoin2, cudaEventDisableTiming));
     A(dalloc(&c->dFastTiles, tileCap)); A(dalloc(&c->dBlurTiles, tileCap));
     A(dalloc(&c->dTables, c->tablesCap));
     A(dalloc(&c->dIn, c->inFrameCap * B));
@@ -298,6 +317,7 @@ int sdyn_destroy(sdyn_ctx* c)
     if (!c) return SDYN_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->aux) cudaStreamSynchronize(c->aux);
     free_all(c);
     delete c;
     return SDYN_OK;

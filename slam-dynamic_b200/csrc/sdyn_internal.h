@@ -78,6 +78,8 @@ struct sdyn_ctx {
     int maxW, maxH, maxBatch, device;
     int maxKp;                         /* per-frame output capacity */
     cudaStream_t stream;
+    cudaStream_t aux;                          /* second stream: stages without mutual dependence run beside the main one */
+    cudaEvent_t evFork, evJoin, evFork2, evJoin2;
     std::string err;
     long long launches;
 

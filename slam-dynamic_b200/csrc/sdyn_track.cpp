@@ -17,7 +17,6 @@ struct TrackState {
     uint64_t* mask; unsigned long long* has; int32_t* boxList; int32_t* nnQ; int32_t* nnT; uint8_t* readmit;
     int32_t* staticExit; uint8_t* dynMask; int32_t* counts;
     size_t zeroFrom = 0, zeroBytes = 0;     /* region cleared at the start of every step */
-    std::vector<MatchJob> hJobs;
     /* device staging of host inputs (sdyn_track_batch) */
     uint8_t* inBlock = nullptr; size_t inBytes = 0;
     /* asynchronous step in flight (sdyn_track_batch_async .. sdyn_track_wait) */
@@ -93,9 +92,31 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     t->poolUsed = reinterpret_cast<int32_t*>(b + oPoolUsed); t->qNext = reinterpret_cast<int32_t*>(b + oQNext); t->result = reinterpret_cast<int32_t*>(b + oResult);
     t->readmit = b + oReadmit; t->staticExit = reinterpret_cast<int32_t*>(b + oStatic);
     t->counts = reinterpret_cast<int32_t*>(b + oCounts);
-    t->hJobs.resize(J);
     c->track = t;
     return SDYN_OK;
+}
+
+/* The 2*B job descriptors of a step differ only in per-frame base pointers, which are affine in the frame index.
+ * They are built ON the device from the descriptors of frames 0 and 1 passed as kernel arguments: word-wise
+ * J(f) = J(0) + f * (J(1) - J(0)) reproduces every pointer and leaves every other field untouched.  No host-to-device
+ * copy of the job table is left in the step — the only per-step H2D traffic is the caller's data (a pageable
+ * cudaMemcpyAsync here would also synchronise the stream with the host). */
+struct JobPair { MatchJob j0, j1; };
+static_assert(sizeof(MatchJob) % 8 == 0, "MatchJob is copied as 64-bit words");
+
+__global__ void k_build_jobs(const __grid_constant__ JobPair F, const __grid_constant__ JobPair M, MatchJob* __restrict__ jobs,
+                             int B, int nframes)
+{
+    constexpr int W = (int)(sizeof(MatchJob) / 8);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * nframes * W) return;
+    const int w = i % W, jf = i / W;
+    const bool isMap = jf >= nframes;
+    const int f = isMap ? jf - nframes : jf;
+    const JobPair& P = isMap ? M : F;
+    const unsigned long long a = reinterpret_cast<const unsigned long long*>(&P.j0)[w];
+    const unsigned long long b = reinterpret_cast<const unsigned long long*>(&P.j1)[w];
+    reinterpret_cast<unsigned long long*>(jobs + (isMap ? B : 0) + f)[w] = a + (unsigned long long)f * (b - a);
 }
 
 __global__ void k_copy_match_counts(const int32_t* __restrict__ result, int B, int nframes, int32_t* __restrict__ counts)
@@ -187,7 +208,8 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
     }
     const int forward = (tlc[2] > in->b) && !in->mono, backward = (-tlc[2] > in->b) && !in->mono;
 
-    for (int f = 0; f < nframes; ++f) {
+    JobPair pF, pM;
+    for (int f = 0; f < 2; ++f) {
         MatchJob J; std::memset(&J, 0, sizeof(J));
         J.keysUn = (c->camera.enabled ? c->dKpUn : c->dKp) + (size_t)f * cap; J.desc = c->dDesc + (size_t)f * cap * 32; J.uRight = nullptr;
         J.nPtr = c->dCount + f; J.n = cap;
@@ -214,7 +236,7 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         const size_t jf = (size_t)f, jm = (size_t)B + f;
         F.qspan = t->qspan + jf * t->maxQ; F.qAccepted = t->qAccepted + jf * t->maxQ; F.qBin = t->qBin + jf * t->maxQ;
         F.pool = t->pool + jf * t->poolPerJob; F.poolUsed = t->poolUsed + jf; F.qNext = t->qNext + jf; F.result = t->result + jf * 4;
-        t->hJobs[f] = F;
+        (f ? pF.j1 : pF.j0) = F;
 
         MatchJob M = J;                      /* SearchByProjection(Frame, vpMapPoints, th) */
         M.mode = MM_MAP;
@@ -224,13 +246,32 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         M.qperm = t->qperm + (size_t)f * t->maxQ;
         M.qspan = t->qspan + jm * t->maxQ; M.qAccepted = t->qAccepted + jm * t->maxQ; M.qBin = t->qBin + jm * t->maxQ;
         M.pool = t->pool + jm * t->poolPerJob; M.poolUsed = t->poolUsed + jm; M.qNext = t->qNext + jm; M.result = t->result + jm * 4;
-        t->hJobs[B + f] = M;
+        (f ? pM.j1 : pM.j0) = M;
+    }
+    /* The dynamic-keypoint mask reads the extraction results only; the two searches do not read the mask: the mask
+     * runs on the second stream beside the searches and both join in front of the step's last kernel. */
+    TCU(c, cudaMemsetAsync(t->assign, 0xff, (size_t)B * cap * 4, st));
+    TCU(c, cudaMemsetAsync(t->block + t->zeroFrom, 0, t->zeroBytes, st));
+    const bool fork = !c->profiling;         /* per-stage profiling keeps one stream so stage times stay unmixed */
+    cudaStream_t ds = fork ? c->aux : st;
+    if (fork) {
+        TCU(c, cudaEventRecord(c->evFork2, st));
+        TCU(c, cudaStreamWaitEvent(c->aux, c->evFork2, 0));
     }
     {
+        StageTimer tm(c, ds, SDYN_STAGE_DYNAMIC);
+        TCU(c, launch_dyn_stage(*in, c->dKp, c->dDesc, c->dCount, cap, t->mask, t->has, t->boxList, t->nnQ, t->nnT,
+                                std::max(t->refStride, 1), t->readmit, t->staticExit, t->dynMask, t->counts, nframes, ds));
+        c->launches += 4;
+    }
+    if (fork) TCU(c, cudaEventRecord(c->evJoin2, c->aux));
+    {
         StageTimer tm(c, st, SDYN_STAGE_MATCH);
-        TCU(c, cudaMemsetAsync(t->assign, 0xff, (size_t)B * cap * 4, st));
-        TCU(c, cudaMemsetAsync(t->block + t->zeroFrom, 0, t->zeroBytes, st));
-        TCU(c, cudaMemcpyAsync(t->dJobs, t->hJobs.data(), t->hJobs.size() * sizeof(MatchJob), cudaMemcpyHostToDevice, st));
+        {
+            const int words = 2 * nframes * (int)(sizeof(MatchJob) / 8);
+            k_build_jobs<<<(words + 255) / 256, 256, 0, st>>>(pF, pM, t->dJobs, B, nframes);
+            TCU(c, cudaGetLastError());
+        }
         TCU(c, launch_grid_build(t->dJobs, nframes, st));
         if (in->map_stride > 0) TCU(c, launch_query_order(t->dJobs + B, nframes, st));
         /* candidate generation only applies static gates, so both searches of every frame go out in ONE launch
@@ -248,14 +289,10 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         }
         c->launches += 3 + (in->last_stride > 0 ? 2 : 0) + (in->map_stride > 0 ? 3 : 0);
     }
-    {
-        StageTimer tm(c, st, SDYN_STAGE_DYNAMIC);
-        TCU(c, launch_dyn_stage(*in, c->dKp, c->dDesc, c->dCount, cap, t->mask, t->has, t->boxList, t->nnQ, t->nnT,
-                                std::max(t->refStride, 1), t->readmit, t->staticExit, t->dynMask, t->counts, nframes, st));
-        k_copy_match_counts<<<(nframes + 63) / 64, 64, 0, st>>>(t->result, B, nframes, t->counts);
-        TCU(c, cudaGetLastError());
-        c->launches += 5;
-    }
+    if (fork) TCU(c, cudaStreamWaitEvent(st, c->evJoin2, 0));
+    k_copy_match_counts<<<(nframes + 63) / 64, 64, 0, st>>>(t->result, B, nframes, t->counts);
+    TCU(c, cudaGetLastError());
+    c->launches += 1;
     return SDYN_OK;
 }
 
