@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Digest an ncu report (made on the GPU box with `ncu --set full`) into the tracked evidence under profiles/:
-  python tools/ncu_digest.py gpurun_out/prof.ncu-rep profiles/r01
+  python tools/ncu_digest.py profiles/r01 gpurun_out/prof_a.ncu-rep [gpurun_out/prof_b.ncu-rep ...]
 writes <prefix>_ncu_summary.csv (one row per captured launch) and <prefix>_ncu_traffic.json (per kernel: mean
 duration and DRAM bytes per launch), which bench.py reads to fill roofline.traffic."""
 import collections
@@ -21,10 +21,18 @@ COLS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
 
 
 def main():
-    rep, prefix = sys.argv[1], sys.argv[2]
-    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"]).decode()
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
+    prefix, reps = sys.argv[1], sys.argv[2:]
+    hdr = units = None
+    rows = []
+    for rep in reps:                      # several captures of the same program (different -k filters) are concatenated
+        raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"]).decode()
+        part = list(csv.reader(raw.splitlines()))
+        if hdr is None:
+            hdr, units = part[0], part[1]
+            rows = part[:2]
+        col = {h: i for i, h in enumerate(part[0])}
+        for r in part[2:]:
+            rows.append([r[col[h]] if h in col else "" for h in hdr])
     idx = [hdr.index(c) for c in COLS if c in hdr]
     with open(prefix + "_ncu_summary.csv", "w", newline="") as f:
         w = csv.writer(f)
@@ -44,7 +52,10 @@ def main():
         agg[name].append({"grid": g, "us": dur, "dram_read": rd, "dram_write": wr})
     out = {}
     for k, v in agg.items():
-        big = [x for x in v if x["us"] >= 0.5 * max(y["us"] for y in v)]     # the batch-sized launches
+        def vol(x):
+            d = [int(t) for t in x["grid"].strip("() ").split(",")]
+            return d[0] * d[1] * d[2]
+        big = [x for x in v if vol(x) == max(vol(y) for y in v)]            # the batch-sized launches
         out[k] = {"launches": len(big), "grid": big[0]["grid"], "mean_us": sum(x["us"] for x in big) / len(big),
                   "dram_bytes_per_launch": sum(x["dram_read"] + x["dram_write"] for x in big) / len(big)}
     json.dump(out, open(prefix + "_ncu_traffic.json", "w"), indent=1)
