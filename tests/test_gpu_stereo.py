@@ -74,3 +74,22 @@ def test_stereo_rejects_mismatched_contexts():
     with pytest.raises(pysdyn.SdynError):
         pysdyn.stereo_match(L, R, 1, MB, MBF)
     L.close(); R.close()
+
+
+def test_stereo_featureless_views():
+    """No keypoints on one side (a blank image): every mvuRight / mvDepth stays -1 and nothing is kept, on both the
+    device and the oracle (the reference would read vDistIdx[0] of an empty vector here)."""
+    cfg = "small"
+    W, H, _, nf, ini, mn = common.CONFIGS[cfg]
+    textured = common.frame(cfg, 2)
+    blank = np.full((H, W), 127, np.uint8)
+    for left, right in ((textured, blank), (blank, textured)):
+        L = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H)
+        R = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H)
+        kl, _ = L(left); kr, _ = R(right)
+        assert len(kl) == 0 or len(kr) == 0
+        ur, dp, kept = pysdyn.stereo_match(L, R, 1, MB, MBF)
+        assert kept[0] == 0 and (ur[0, :len(kl)] == -1).all() and (dp[0, :len(kl)] == -1).all()
+        okl, our, odp, okept = oracle_pair(cfg, left, right)
+        assert okept == 0 and len(okl) == len(kl)
+        L.close(); R.close()
