@@ -63,6 +63,7 @@ def stage_alg_bytes(W, H, nkp, evals, queries):
         "describe": nkp * (749 + 512 + 60),
         "octree": nkp * 8,
         "match": 32 * evals + 56 * queries + 32 * nkp,
+        "candidates": 32 * evals + 56 * queries + 32 * nkp,
         "dynamic": 9 * nkp + 32 * 64,
     }
 
@@ -530,10 +531,13 @@ def main():
             per_step = sms / K
             ach = sab.get(name, 0) * B / (per_step * 1e-3) / 1e9
             stage_report[name] = {"ms_per_step": per_step, "share": sms / tot_stage_ms, "alg_gbs": ach, "hbm_frac": ach / peak}
-    dom = max(stage_report, key=lambda n: stage_report[n]["ms_per_step"]) if stage_report else None
+    # the dominant KERNEL: stages that are one kernel (or one kernel launched per level); "match" and "dynamic" are
+    # chains of small kernels and are represented by their largest member ("candidates")
+    single = [n for n in stage_report if n not in ("match", "dynamic")]
+    dom = max(single, key=lambda n: stage_report[n]["ms_per_step"]) if single else None
     roof = None
     # DRAM traffic per launch of the stage's main kernel, from the committed ncu --set full capture
-    stage_kernel = {"fast": "k_fast", "match": "k_match_candidates", "describe": "k_orient_describe", "blur": "k_blur",
+    stage_kernel = {"fast": "k_fast", "match": "k_match_candidates", "candidates": "k_match_candidates", "describe": "k_orient_describe", "blur": "k_blur",
                     "pyramid": "k_resize", "octree": "k_octree", "level0": "k_level0", "dynamic": "k_box_stage"}
     traffic = None
     try:
@@ -549,6 +553,21 @@ def main():
                 "alg_bytes_per_launch": sab.get(dom, 0) * B,
                 "note": "FAST scoring is integer-ALU bound, not HBM bound (DESIGN.md §Kernels)" if dom == "fast" else ""}
     balg = alg_bytes_extract(W, H, int(round(mean_kp)))
+    # what actually bounds these kernels: warp-instruction issue (148 SMs x 4 schedulers x SM clock).  Instruction
+    # counts per launch come from the committed ncu capture, the duration is the one measured live above.
+    issue = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        kname = stage_kernel.get(dom)
+        if dom and B == 64 and kname in tj and tj[kname].get("warp_inst_per_launch") and dom in ("fast", "blur", "describe", "level0"):
+            sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+            peak_i = 148 * 4 * sm_mhz * 1e6
+            ach = tj[kname]["warp_inst_per_launch"] / (stage_report[dom]["ms_per_step"] * 1e-3)
+            issue = {"kernel": kname, "warp_inst_per_launch": tj[kname]["warp_inst_per_launch"], "achieved_ginst_s": ach / 1e9,
+                     "peak_ginst_s": peak_i / 1e9, "frac": ach / peak_i,
+                     "note": "instruction-issue roofline of the dominant kernel: the path is issue bound, not HBM bound (DESIGN.md 4)"}
+    except Exception:
+        pass
 
     cpu = None
     if args.cpu_seconds > 0:
@@ -585,6 +604,7 @@ def main():
         "pipeline_roofline": {"alg_bytes_per_frame": balg, "achieved_gbs": balg * fps / world / 1e9, "peak": peak,
                               "frac": balg * fps / world / 1e9 / peak,
                               "note": "SURVEY §8(d) extraction bytes per frame x per-GPU frames/s"},
+        "issue_roofline": issue,
         "stages": stage_report,
         "per_frame": {"hamming_evals": evals_per_frame, "keypoints": float(g[:, 1].mean()), "matches_frame": float(g[:, 2].mean()),
                       "matches_map": float(g[:, 3].mean()), "dyn_masked": float(g[:, 4].mean())},

@@ -478,6 +478,7 @@ int sdyn_bow_assemble(const uint32_t* word_id, const double* weight, const uint3
 enum { SDYN_STAGE_PYRAMID = 0, SDYN_STAGE_FAST, SDYN_STAGE_OCTREE, SDYN_STAGE_BLUR, SDYN_STAGE_DESCRIBE,
        SDYN_STAGE_MATCH, SDYN_STAGE_DYNAMIC, SDYN_STAGE_LEVEL0 /* clears + level 0; PYRAMID = the resize chain */,
        SDYN_STAGE_STEREO, SDYN_STAGE_BOW,
+       SDYN_STAGE_CANDIDATES /* k_match_candidates alone; MATCH = the whole search stage around it */,
        SDYN_STAGE_COUNT };
 typedef struct {
     double ms[SDYN_STAGE_COUNT];

@@ -12,9 +12,11 @@
  *
  * Bound: integer ALU, not HBM (1 byte per pixel against a ~100-op min/max network).  The kernel therefore
  * spends its effort on NOT scoring: (A) a 4-point compass test that is an exact necessary condition for a
- * 9-arc at the low threshold rejects most pixels with 5 shared-memory reads; (B) survivors are compacted into a
- * dense list so the full 16-tap score (VIMNMX3 sliding-window network) runs with all lanes busy; (C) the 3x3
- * suppression only touches pixels with a non-zero score.  Tiles are staged with 16-byte aligned vector loads.
+ * 9-arc at the low threshold rejects most pixels; it runs on whole words (4 columns x 4 rows per thread, bytes
+ * widened to u16x2 lanes, two positions per VIMNMX.U16x2); (B) survivors are compacted into a dense list so the
+ * full 16-tap score (VIMNMX3 sliding-window network) runs with all lanes busy; (C) the 3x3 suppression only touches
+ * pixels with a non-zero score.  Tiles are staged with 16-byte aligned vector loads and shifted by 0-3 bytes so that
+ * score column 0 is word aligned.
  */
 #include "sdyn_internal.h"
 

@@ -277,8 +277,10 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
         /* candidate generation only applies static gates, so both searches of every frame go out in ONE launch
          * when their jobs are contiguous (full batch); the claims are then resolved frame search first */
         const bool both = in->last_stride > 0 && in->map_stride > 0 && nframes == B;
-        if (both)
+        if (both) {
+            StageTimer tc(c, st, SDYN_STAGE_CANDIDATES);
             TCU(c, launch_match_candidates(t->dJobs, 2 * B, std::max(in->last_stride, in->map_stride), cap, st));
+        }
         if (in->last_stride > 0) {
             if (!both) TCU(c, launch_match_candidates(t->dJobs, nframes, in->last_stride, cap, st));
             TCU(c, launch_match_resolve(t->dJobs, nframes, MM_FRAME, cap, in->last_stride, st));

@@ -39,7 +39,7 @@ class DeviceView(C.Structure):
                 ("cap", C.c_int32), ("nlevels", C.c_int32), ("level", LevelInfo * MAX_LEVELS)]
 
 
-STAGES = ["pyramid", "fast", "octree", "blur", "describe", "match", "dynamic", "level0", "stereo", "bow"]
+STAGES = ["pyramid", "fast", "octree", "blur", "describe", "match", "dynamic", "level0", "stereo", "bow", "candidates"]
 
 
 class StageTimes(C.Structure):

@@ -49,7 +49,9 @@ def main():
         dur = float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")) * scale.get(unit["gpu__time_duration.sum"], 1.0)
         rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", "")) * scale.get(unit["dram__bytes_read.sum"], 1.0)
         wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", "")) * scale.get(unit["dram__bytes_write.sum"], 1.0)
-        agg[name].append({"grid": g, "us": dur, "dram_read": rd, "dram_write": wr})
+        ins = float(r[hdr.index("smsp__inst_executed.sum")].replace(",", "") or 0)
+        issue = float(r[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")].replace(",", "") or 0)
+        agg[name].append({"grid": g, "us": dur, "dram_read": rd, "dram_write": wr, "inst": ins, "issue": issue})
     out = {}
     for k, v in agg.items():
         def vol(x):
@@ -57,7 +59,9 @@ def main():
             return d[0] * d[1] * d[2]
         big = [x for x in v if vol(x) == max(vol(y) for y in v)]            # the batch-sized launches
         out[k] = {"launches": len(big), "grid": big[0]["grid"], "mean_us": sum(x["us"] for x in big) / len(big),
-                  "dram_bytes_per_launch": sum(x["dram_read"] + x["dram_write"] for x in big) / len(big)}
+                  "dram_bytes_per_launch": sum(x["dram_read"] + x["dram_write"] for x in big) / len(big),
+                  "warp_inst_per_launch": sum(x["inst"] for x in big) / len(big),
+                  "issue_active_pct": sum(x["issue"] for x in big) / len(big)}
     json.dump(out, open(prefix + "_ncu_traffic.json", "w"), indent=1)
     for k, v in sorted(out.items(), key=lambda kv: -kv[1]["mean_us"]):
         print("%-24s %8.1f us  dram %8.2f MB  grid %s" % (k, v["mean_us"], v["dram_bytes_per_launch"] / 1e6, v["grid"]))
