@@ -1,6 +1,8 @@
 /* ORACLE — TEST INFRASTRUCTURE ONLY.  DBoW2 vocabulary tree and TemplatedVocabulary::transform as Frame::ComputeBoW
  * uses them (reference: src/Frame.cc:803-810; Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1258, 1338-1425;
- * BowVector.cpp:36-86; FeatureVector.cpp; FORB.cpp:81-101), restated with the same containers (std::map, std::vector). */
+ * BowVector.cpp:36-86; FeatureVector.cpp; FORB.cpp:81-101), restated with the same containers (std::map, std::vector).
+ * DBoW2 is vendored in the reference tree but needs OpenCV C++ to compile, so it cannot be built here; parity pin:
+ * tests/test_oracle_bow.py (independent pure-Python re-statement on synthetic trees, incl. ragged ones and stopped words). */
 #include <cmath>
 #include <cstdint>
 #include <cstring>

@@ -3,6 +3,10 @@
  *   Frame::boxTrack / firstSeparate / tail split / UpdateFrame   src/Frame.cc:481-653, :337-367
  *   Tracking::Separate / classifyH / classifyF                   src/Tracking.cc:1093-1367
  *   cv::BFMatcher(NORM_HAMMING, crossCheck=true)::match          SURVEY A-7 (OpenCV, un-vendored)
+ *
+ * Parity pin: BFMatcher cross-check and the 3x3 inverse are checked against cv2 (tests/test_oracle_matcher.py);
+ * firstSeparate's erase-while-iterating behaviour and boxTrack have hand-derived known answers there; classifyF/H and
+ * UpdateFrame are restatement-only ("parity unpinned": no reference binary, test or vector exists for them).
  */
 #pragma once
 #include "orc_extractor.h"

@@ -3,6 +3,13 @@
  * (reference: src/ORBmatcher.cc, src/Frame.cc).  Pointers of the reference become indices:
  *   MapPoint* stored in Frame::mvpMapPoints[i]   ->  assign[i]  (-1 = NULL, >= 0 = index of the query)
  *   pMP->Observations() > 0                      ->  a per-query flag; locked[i] mirrors it for the occupant
+ *
+ * Parity pin: the reference ships no tests or vectors for these functions and cannot be built here, so they are
+ * pinned by independent Python re-statements that run the OpenCV-dependent steps through cv2 itself
+ * (tests/test_oracle_matcher.py: GetFeaturesInArea, SearchByProjection(Cur,Last), SearchByBoW(KF,KF), both pose
+ * searches, the Fuse search, SearchForTriangulation; cv2.gemm / cv2.norm / BFMatcher / invert known answers) and by
+ * the regression hashes of tests/golden/match_oracle.json.  SearchByProjection(F,MPs), SearchForInitialization,
+ * SearchByBoW(KF,F) and SearchBySim3 are restatement-only ("parity unpinned" beyond those shared sub-steps).
  */
 #pragma once
 #include "orc_extractor.h"

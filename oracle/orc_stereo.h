@@ -1,5 +1,7 @@
 /* ORACLE — TEST INFRASTRUCTURE ONLY (see orc_prims.h).
- * CPU restatement of Frame::ComputeStereoMatches (reference: src/Frame.cc:874-1048). */
+ * CPU restatement of Frame::ComputeStereoMatches (reference: src/Frame.cc:874-1048).
+ * Parity pin: tests/test_oracle_stereo.py — an independent Python twin whose window arithmetic runs through cv2
+ * (convertTo, subtract, cv2.norm(NORM_L1)) must agree bit for bit (tests/stereo_twin.py). */
 #pragma once
 #include "orc_extractor.h"
 #include <cstdint>
