@@ -6,10 +6,11 @@
  *
  * Parity pin: the reference ships no tests or vectors for these functions and cannot be built here, so they are
  * pinned by independent Python re-statements that run the OpenCV-dependent steps through cv2 itself
- * (tests/test_oracle_matcher.py: GetFeaturesInArea, SearchByProjection(Cur,Last), SearchByBoW(KF,KF), both pose
- * searches, the Fuse search, SearchForTriangulation; cv2.gemm / cv2.norm / BFMatcher / invert known answers) and by
- * the regression hashes of tests/golden/match_oracle.json.  SearchByProjection(F,MPs), SearchForInitialization,
- * SearchByBoW(KF,F) and SearchBySim3 are restatement-only ("parity unpinned" beyond those shared sub-steps).
+ * (tests/test_oracle_matcher.py: GetFeaturesInArea, SearchByProjection(F,MPs), SearchByProjection(Cur,Last),
+ * SearchForInitialization, SearchByBoW(KF,F) and (KF,KF), both pose searches, the Fuse search, SearchForTriangulation;
+ * cv2.gemm / cv2.norm / BFMatcher / invert known answers) and by the regression hashes of
+ * tests/golden/match_oracle.json.  Fuse(Scw) and SearchBySim3 share every step with a pinned function (projection,
+ * gates, PredictScale, window walk) but have no twin of their own.
  */
 #pragma once
 #include "orc_extractor.h"

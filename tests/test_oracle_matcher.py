@@ -513,3 +513,140 @@ def test_search_triangulation_oracle_vs_python(tum_pair, stereo, only_stereo):
     got = orc.match_triangulation(kf1, h1, pysdyn.FeatureVector(n1), kf2, h2, pysdyn.FeatureVector(n2), prm)
     ref = py_search_triangulation(kf1, h1, n1, kf2, h2, n2, F12, epi, sig2, only_stereo, True)
     assert got[0] == ref[0] and got[0] > 50 and np.array_equal(got[1], ref[1])
+
+
+def py_search_map(F, mps, th, ratio, assign0, locked0, base=0):
+    """Independent Python re-statement of SearchByProjection(Frame&, vector<MapPoint*>&, th), ORBmatcher.cc:45-129."""
+    assign = np.asarray(assign0, np.int32).copy(); locked = np.asarray(locked0, np.uint8).copy()
+    n = 0
+    for i, mp in enumerate(mps):
+        if not mp["track_in_view"] or mp["bad"]:
+            continue
+        lvl = int(mp["level"])
+        r = f32(2.5) if float(mp["view_cos"]) > 0.998 else f32(4.0)
+        if th != 1.0:
+            r = f32(r * f32(th))
+        rad = f32(r * F.scale[lvl])
+        b1, l1, b2, l2, bi = 256, -1, 256, -1, -1
+        for j in py_features_in_area(F, mp["proj_x"], mp["proj_y"], rad, lvl - 1, lvl):
+            if assign[j] != -1 and locked[j]:
+                continue
+            if F.u_right is not None and F.u_right[j] > 0 and abs(f32(mp["proj_xr"] - F.u_right[j])) > rad:
+                continue
+            d = int(np.unpackbits(mp["desc"] ^ F.desc[j]).sum())
+            if d < b1:
+                b2, b1, l2, l1, bi = b1, d, l1, int(F.keys_un["octave"][j]), j
+            elif d < b2:
+                l2, b2 = int(F.keys_un["octave"][j]), d
+        if b1 <= 100:
+            if l1 == l2 and b1 > f32(ratio) * f32(b2):
+                continue
+            assign[bi] = base + i; locked[bi] = mp["obs_positive"]; n += 1
+    return n, assign, locked
+
+
+@pytest.mark.parametrize("stereo,th", [(True, 3.0), (False, 1.0)])
+def test_search_map_oracle_vs_python(tum_pair, stereo, th):
+    p = tum_pair
+    F = scenario.frame_view(p["k1"], p["d1"], p["scale"], p["W"], p["H"], stereo=stereo, seed=1)
+    mps = scenario.map_queries(p["k1"], p["d1"], 8, seed=5, count=900)
+    r = np.random.default_rng(3)
+    a0 = np.where(r.random(F.n) < 0.15, -2, -1).astype(np.int32); l0 = ((a0 != -1) & (r.random(F.n) < 0.7)).astype(np.uint8)
+    got = orc.match_projection_map(F, mps, th, 0.8, a0, l0)
+    ref = py_search_map(F, mps, th, 0.8, a0, l0)
+    assert got[0] == ref[0] and got[0] > 100 and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+def py_search_init(F1, F2, prev, window, ratio, check_ori):
+    """Independent Python re-statement of SearchForInitialization, ORBmatcher.cc:562-677."""
+    prev = np.asarray(prev, np.float32).copy()
+    m12 = np.full(F1.n, -1, np.int32); m21 = np.full(F2.n, -1, np.int32); mdist = np.full(F2.n, 2 ** 31 - 1, np.int64)
+    hist = [[] for _ in range(30)]; n = 0
+    for i1 in range(F1.n):
+        lvl = int(F1.keys_un["octave"][i1])
+        if lvl > 0:
+            continue
+        b1, b2, bi = 2 ** 31 - 1, 2 ** 31 - 1, -1
+        for i2 in py_features_in_area(F2, prev[i1, 0], prev[i1, 1], f32(window), lvl, lvl):
+            d = int(np.unpackbits(F1.desc[i1] ^ F2.desc[i2]).sum())
+            if mdist[i2] <= d:
+                continue
+            if d < b1:
+                b2, b1, bi = b1, d, i2
+            elif d < b2:
+                b2 = d
+        if b1 <= 50 and f32(b1) < f32(f32(b2) * f32(ratio)):
+            if m21[bi] >= 0:
+                m12[m21[bi]] = -1; n -= 1
+            m12[i1] = bi; m21[bi] = i1; mdist[bi] = b1; n += 1
+            if check_ori:
+                hist[py_rot_bin(F1.keys_un["angle"][i1], F2.keys_un["angle"][bi])].append(i1)
+    if check_ori:
+        keep = py_three_maxima([len(h) for h in hist])
+        for i, h in enumerate(hist):
+            if i not in keep:
+                for idx in h:
+                    if m12[idx] >= 0:
+                        m12[idx] = -1; n -= 1
+    for i1 in range(F1.n):
+        if m12[i1] >= 0:
+            prev[i1, 0] = F2.keys_un["x"][m12[i1]]; prev[i1, 1] = F2.keys_un["y"][m12[i1]]
+    return n, m12, prev
+
+
+@pytest.mark.parametrize("check", [True, False])
+def test_search_init_oracle_vs_python(tum_pair, check):
+    p = tum_pair
+    F1 = scenario.frame_view(p["k0"], p["d0"], p["scale"], p["W"], p["H"])
+    F2 = scenario.frame_view(p["k1"], p["d1"], p["scale"], p["W"], p["H"])
+    prev = np.stack([p["k0"]["x"], p["k0"]["y"]], 1).astype(np.float32)
+    got = orc.match_init(F1, F2, prev, 40, 0.9, check)
+    ref = py_search_init(F1, F2, prev, 40, 0.9, check)
+    assert got[0] == ref[0] and got[0] > 50 and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+def py_search_bow(KF, valid, nodes1, F, nodes2, ratio, check_ori):
+    """Independent Python re-statement of SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), ORBmatcher.cc:159-288."""
+    def fmap(nodes):
+        m = {}
+        for i, nd in enumerate(nodes):
+            m.setdefault(int(nd), []).append(i)
+        return m
+    f1, f2 = fmap(nodes1), fmap(nodes2)
+    assign = np.full(F.n, -1, np.int32); hist = [[] for _ in range(30)]; n = 0
+    for node in sorted(set(f1) & set(f2)):
+        for ik in f1[node]:
+            if not valid[ik]:
+                continue
+            b1, bi, b2 = 256, -1, 256
+            for jf in f2[node]:
+                if assign[jf] != -1:
+                    continue
+                d = int(np.unpackbits(KF.desc[ik] ^ F.desc[jf]).sum())
+                if d < b1:
+                    b2, b1, bi = b1, d, jf
+                elif d < b2:
+                    b2 = d
+            if b1 <= 50 and f32(b1) < f32(ratio) * f32(b2):
+                assign[bi] = ik; n += 1
+                if check_ori:
+                    hist[py_rot_bin(KF.keys_un["angle"][ik], F.keys["angle"][bi])].append(bi)
+    if check_ori:
+        keep = py_three_maxima([len(h) for h in hist])
+        for i, h in enumerate(hist):
+            if i not in keep:
+                for idx in h:
+                    assign[idx] = -1; n -= 1
+    return n, assign
+
+
+@pytest.mark.parametrize("check", [True, False])
+def test_search_bow_oracle_vs_python(tum_pair, check):
+    p = tum_pair
+    KF = scenario.frame_view(p["k0"], p["d0"], p["scale"], p["W"], p["H"])
+    F = scenario.frame_view(p["k1"], p["d1"], p["scale"], p["W"], p["H"])
+    n1, n2 = scenario.bow_nodes(p["d0"]), scenario.bow_nodes(p["d1"])
+    valid = (np.random.default_rng(2).random(KF.n) < 0.8).astype(np.uint8)
+    got = orc.match_bow(KF, valid, pysdyn.FeatureVector(n1), F, pysdyn.FeatureVector(n2), 0.7, check)
+    ref = py_search_bow(KF, valid, n1, F, n2, 0.7, check)
+    assert got[0] == ref[0] and got[0] > 30 and np.array_equal(got[1], ref[1])
