@@ -371,6 +371,14 @@ typedef struct {
 
 int sdyn_track_batch_device(sdyn_ctx* ctx, int nframes, const uint8_t* d_gray, size_t frame_stride,
                             int width, int height, int stride, const sdyn_track_inputs* in, void* stream);
+/* Stereo form of the same step (the stereo Frame constructor, src/Frame.cc:140-175, then the searches): both views are
+ * extracted side by side on the two contexts' streams, Frame::ComputeStereoMatches runs on the device, and the two
+ * searches apply their mvuRight gates (ORBmatcher.cc:94-99, 1567-1573) to the result.  Inputs are device pointers;
+ * in->mono must be 0 for the forward / backward level rule; results as for sdyn_track_batch_device plus
+ * sdyn_stereo_results on `ctx` (the left context). */
+int sdyn_track_batch_stereo_device(sdyn_ctx* ctx, sdyn_ctx* right, int nframes, const uint8_t* d_gray_left,
+                                   const uint8_t* d_gray_right, size_t frame_stride, int width, int height, int stride,
+                                   const sdyn_track_inputs* in, float mb, float mbf);
 /* Host-buffer form of the same step (what a caller holding frames and map data in host memory uses): every
  * pointer of `in` and `gray` is HOST memory (pinned memory copies asynchronously), results are written to the
  * host arrays (kp_out/desc_out: [nframes][cap], n_out: [nframes]; assign/locked/dyn_mask: [nframes][cap];

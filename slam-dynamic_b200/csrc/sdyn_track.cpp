@@ -173,15 +173,24 @@ using namespace sdyn;
 
 extern "C" {
 
+static bool bad_track_inputs(const sdyn_ctx* c, const sdyn_track_inputs* in, int nframes)
+{
+    return !in || nframes < 1 || nframes > c->maxBatch || in->last_stride < 0 ||
+           in->map_stride < 0 || in->ref_stride < 0 || !(in->max_x > in->min_x) || !(in->max_y > in->min_y) ||
+           (in->last_stride > 0 && (!in->last_points || !in->last_keys || !in->n_last)) ||
+           (in->map_stride > 0 && (!in->map_points || !in->n_map)) || !in->boxes || !in->n_boxes || !in->ref_box ||
+           !in->ref_off || !in->fmat || c->maxKp > 65535;
+}
+
+/* Steps 2-4 of the batched front end on the keypoints / descriptors the context's last extraction left on the device.
+ * uRight: mvuRight of the current frames ([B][cap], device) for the stereo gates of the two searches, or null. */
+static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs* in, const float* uRight, cudaStream_t st);
+
 int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frameStride, int W, int H, int stride,
                             const sdyn_track_inputs* in, void* stream)
 {
     if (!c) return SDYN_ERR_ARG;
-    if (!in || nframes < 1 || nframes > c->maxBatch || !dGray || W < 1 || H < 1 || stride < W || in->last_stride < 0 ||
-        in->map_stride < 0 || in->ref_stride < 0 || !(in->max_x > in->min_x) || !(in->max_y > in->min_y) ||
-        (in->last_stride > 0 && (!in->last_points || !in->last_keys || !in->n_last)) ||
-        (in->map_stride > 0 && (!in->map_points || !in->n_map)) || !in->boxes || !in->n_boxes || !in->ref_box ||
-        !in->ref_off || !in->fmat || c->maxKp > 65535)
+    if (bad_track_inputs(c, in, nframes) || !dGray || W < 1 || H < 1 || stride < W)
         return api_fail(c, SDYN_ERR_ARG, "sdyn_track_batch_device: bad argument");
     TCU(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
@@ -189,10 +198,39 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
     if (rc != SDYN_OK) return rc;
     rc = ensure_track_state(c, std::max(std::max(in->last_stride, in->map_stride), 1), in->ref_stride);
     if (rc != SDYN_OK) return rc;
-    TrackState* t = static_cast<TrackState*>(c->track);
     rc = enqueue_extract(c, nframes, dGray, frameStride, stride, st);
     if (rc != SDYN_OK) return rc;
+    return track_after_extract(c, nframes, in, nullptr, st);
+}
 
+int sdyn_track_batch_stereo_device(sdyn_ctx* c, sdyn_ctx* right, int nframes, const uint8_t* dGrayLeft, const uint8_t* dGrayRight,
+                                   size_t frameStride, int W, int H, int stride, const sdyn_track_inputs* in, float mb, float mbf)
+{
+    if (!c) return SDYN_ERR_ARG;
+    if (!right || bad_track_inputs(c, in, nframes) || nframes > right->maxBatch || !dGrayLeft || !dGrayRight || W < 1 || H < 1 ||
+        stride < W)
+        return api_fail(c, SDYN_ERR_ARG, "sdyn_track_batch_stereo_device: bad argument");
+    TCU(c, cudaSetDevice(c->device));
+    int rc = ensure_geometry(c, W, H);
+    if (rc == SDYN_OK) rc = ensure_geometry(right, W, H);
+    if (rc != SDYN_OK) return rc;
+    rc = ensure_track_state(c, std::max(std::max(in->last_stride, in->map_stride), 1), in->ref_stride);
+    if (rc != SDYN_OK) return rc;
+    /* the stereo Frame constructor (src/Frame.cc:140-175): both extractions side by side, ComputeStereoMatches, then the
+     * searches gate on mvuRight */
+    rc = enqueue_extract(c, nframes, dGrayLeft, frameStride, stride, c->stream);
+    if (rc == SDYN_OK) rc = enqueue_extract(right, nframes, dGrayRight, frameStride, stride, right->stream);
+    if (rc != SDYN_OK) return rc == SDYN_OK ? rc : api_fail(c, rc, "sdyn_track_batch_stereo_device: extraction failed");
+    rc = sdyn_stereo_match_device(c, right, nframes, mb, mbf, nullptr);
+    if (rc != SDYN_OK) return rc;
+    sdyn_stereo_view sv;
+    if (sdyn_stereo_results(c, &sv) != SDYN_OK) return api_fail(c, SDYN_ERR_ARG, "stereo results unavailable");
+    return track_after_extract(c, nframes, in, sv.u_right, c->stream);
+}
+
+static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs* in, const float* uRight, cudaStream_t st)
+{
+    TrackState* t = static_cast<TrackState*>(c->track);
     const int B = t->B, cap = t->cap;
     /* bForward / bBackward of ORBmatcher.cc:1497-1506 */
     float twc[3], tlc[3];
@@ -211,7 +249,8 @@ int sdyn_track_batch_device(sdyn_ctx* c, int nframes, const uint8_t* dGray, size
     JobPair pF, pM;
     for (int f = 0; f < 2; ++f) {
         MatchJob J; std::memset(&J, 0, sizeof(J));
-        J.keysUn = (c->camera.enabled ? c->dKpUn : c->dKp) + (size_t)f * cap; J.desc = c->dDesc + (size_t)f * cap * 32; J.uRight = nullptr;
+        J.keysUn = (c->camera.enabled ? c->dKpUn : c->dKp) + (size_t)f * cap; J.desc = c->dDesc + (size_t)f * cap * 32;
+        J.uRight = uRight ? uRight + (size_t)f * cap : nullptr;
         J.nPtr = c->dCount + f; J.n = cap;
         J.minX = in->min_x; J.minY = in->min_y; J.maxX = in->max_x; J.maxY = in->max_y;
         J.gridWInv = static_cast<float>(SDYN_GRID_COLS) / static_cast<float>(in->max_x - in->min_x);

@@ -672,6 +672,15 @@ def track_batch_device(ex, nframes, dptr, frame_stride, w, h, row_stride, tin, s
                                         C.c_void_p(stream) if stream else None))
 
 
+def track_batch_stereo_device(left, right, nframes, dptr_left, dptr_right, frame_stride, w, h, row_stride, tin, mb, mbf):
+    L = _bind_track(lib())
+    vp = C.c_void_p
+    L.sdyn_track_batch_stereo_device.argtypes = [vp, vp, C.c_int, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                                 C.POINTER(TrackInputsC), C.c_float, C.c_float]
+    left._check(L.sdyn_track_batch_stereo_device(left._h, right._h, nframes, C.c_void_p(dptr_left), C.c_void_p(dptr_right),
+                                                 frame_stride, w, h, row_stride, C.byref(tin), mb, mbf))
+
+
 def track_fetch(ex, nframes, stream=None, out=None):
     L = _bind_track(lib())
     if out is None:

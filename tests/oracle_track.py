@@ -7,11 +7,11 @@ import pysdyn
 import scenario
 
 
-def track_frame(keys, desc, scale, W, H, arrays, f, params, last_stride, keys_un=None, bounds=None):
+def track_frame(keys, desc, scale, W, H, arrays, f, params, last_stride, keys_un=None, bounds=None, u_right=None):
     """Returns (assign, locked, dyn_mask, counts[4]) for frame f of `arrays` (scenario.build_track_batch)."""
     cam = scenario.KITTI_CAM
     bounds = (0.0, 0.0, float(W), float(H)) if bounds is None else tuple(float(b) for b in bounds)
-    cur = pysdyn.FrameView(keys, desc, scale, bounds, keys_un=keys_un,
+    cur = pysdyn.FrameView(keys, desc, scale, bounds, keys_un=keys_un, u_right=u_right,
                            cam=(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["bf"], cam["bf"] / cam["fx"]),
                            tcw=params["tcw_cur"])
     n0 = int(arrays["n_last"][f])

@@ -73,3 +73,51 @@ def test_track_batch_matches_oracle(cfg, B):
             assert np.array_equal(outs[3][f, :n], assign[f, :n]) and np.array_equal(outs[4][f, :n], locked[f, :n])
             assert np.array_equal(outs[5][f, :n], mask[f, :n])
     gpu.close()
+
+
+def test_track_batch_stereo_matches_oracle():
+    """BASELINE config 3: stereo pairs — both extractions, ComputeStereoMatches and the two searches with their mvuRight
+    gates in one device-resident step (sdyn_track_batch_stereo_device) against the oracle composition."""
+    import torch
+    cfg, B = "kitti", 2
+    W, H, nrect, nf, ini, mn = common.CONFIGS[cfg]
+    cid = common.CONFIG_ID[cfg]
+    seq_seed = 1000 * cid + 7
+    idx = list(range(0, 1 + B))
+    left = np.stack([pysdyn.synth_frame(seq_seed, 1000 * cid + i, W, H, nrect, *scenario.sequence_offsets(i), scenario.sequence_time(i))
+                     for i in idx])
+    right = np.stack([pysdyn.synth_frame(seq_seed, 1000 * cid + 5000 + i, W, H, nrect, scenario.sequence_offsets(i)[0] + 9 + 2 * i,
+                                         scenario.sequence_offsets(i)[1], scenario.sequence_time(i)) for i in idx[1:]])
+    cpuL, cpuR = orc.Extractor(nf, 1.2, 8, ini, mn), orc.Extractor(nf, 1.2, 8, ini, mn)
+    kd = [cpuL(im) for im in left]
+    cam = scenario.KITTI_CAM
+    mb, mbf = cam["bf"] / cam["fx"], cam["bf"]
+    L = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=B)
+    R = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=B)
+    last_stride, map_stride, ref_stride = L.cap, 1500, 512
+    arrays = scenario.build_track_batch(kd, seq_seed, 1, W, H, nrect, 8, last_stride, map_stride, ref_stride, n_map=1500, seed=3)
+    params = scenario.track_params(W, H)
+    dev = {k: torch.from_numpy(v.view(np.uint8).reshape(v.shape[0], -1)).cuda() for k, v in arrays.items()}
+    ptrs = {k: (t.data_ptr(), t.shape[1]) for k, t in dev.items()}
+    tin = pysdyn.track_inputs(ptrs, 0, (last_stride, map_stride, ref_stride), params)
+    dl = torch.from_numpy(left[1:]).cuda(); dr = torch.from_numpy(right).cuda()
+    for _ in range(2):
+        pysdyn.track_batch_stereo_device(L, R, B, dl.data_ptr(), dr.data_ptr(), W * H, W, H, W, tin, mb, mbf)
+    kps, desc, counts = L.fetch(B)
+    ur, dp, kept = pysdyn.stereo_fetch(L, B)
+    assign, locked, mask, cnt = pysdyn.track_fetch(L, B)
+    for f in range(B):
+        k, d = kd[f + 1]
+        n = counts[f]
+        kr, dr_ = cpuR(right[f])
+        cpuL(left[f + 1])                                   # the oracle's left pyramid of THIS frame
+        our, odp, okept = orc.stereo_matches(cpuL, cpuR, k, d, kr, dr_, mb, mbf)
+        assert n == len(k) and np.array_equal(desc[f, :n], d)
+        assert np.array_equal(ur[f, :n].view(np.uint32), our.view(np.uint32)) and kept[f] == okept and okept > 300
+        ea, el, em, ec = oracle_track.track_frame(k, d, cpuL.scale, W, H, arrays, f, params, last_stride, u_right=our)
+        assert np.array_equal(cnt[f], ec), (f, cnt[f], ec)
+        assert np.array_equal(assign[f, :n], ea) and np.array_equal(locked[f, :n], el) and np.array_equal(mask[f, :n], em)
+        # the gates must have mattered: the monocular result differs
+        ma, _, _, mc = oracle_track.track_frame(k, d, cpuL.scale, W, H, arrays, f, params, last_stride)
+        assert not np.array_equal(ma, ea)
+    L.close(); R.close()
