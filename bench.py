@@ -72,8 +72,9 @@ def seq_seed(cfg, rank):
     return 1000 * WORKLOADS[cfg][6] + 100000 * rank + 7
 
 
-def make_frames(cfg, rank, first, count):
-    """Frames first..first+count-1 of this rank's sequence (consecutive frames shift by <= 8 px)."""
+def make_frames(cfg, rank, first, count, disparity=0):
+    """Frames first..first+count-1 of this rank's sequence (consecutive frames shift by <= 8 px); disparity > 0 renders
+    the right view of a rectified stereo rig (content shifted, its own sensor noise)."""
     import pysdyn
     import scenario
     W, H, nrect, _, _, _, cid = WORKLOADS[cfg]
@@ -84,8 +85,8 @@ def make_frames(cfg, rank, first, count):
         for j in range(t, count, nthreads):
             i = first + j
             ox, oy = scenario.sequence_offsets(i)
-            pysdyn.synth_frame(seq_seed(cfg, rank), 1000 * cid + 100000 * rank + i + (1 << 20), W, H, nrect, ox, oy,
-                               scenario.sequence_time(i), out=frames[j])
+            pysdyn.synth_frame(seq_seed(cfg, rank), 1000 * cid + 100000 * rank + i + (1 << 20) + (disparity << 22), W, H, nrect,
+                               ox + disparity, oy, scenario.sequence_time(i), out=frames[j])
 
     th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
     [t.start() for t in th]
@@ -227,7 +228,7 @@ def big_vocabulary(k=10, L=6, seed=1):
     return np.concatenate(parents), np.concatenate(leafs), np.concatenate(descs), np.concatenate(weights)
 
 
-def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps):
+def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptrs, strides, params, dev_frames):
     """Device timings of the SURVEY §8(f) rows built after the headline path (same parity bar, tests/test_gpu_*.py):
     ComputeStereoMatches per stereo pair and ComputeBoW per frame, with the oracle timed beside them.  Reported next
     to the headline, never part of it."""
@@ -268,6 +269,31 @@ def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps):
                      "stereo_points_per_pair": float(kept.mean()), "parity_frame0": bool(np.array_equal(ur[0, :len(our)], our)),
                      "cpu_oracle_ms_per_pair_stereo_match_only": cpu_ms,
                      "reference": "Frame::ComputeStereoMatches, src/Frame.cc:874-1048"}
+    # BASELINE config 3: stereo pairs through the whole step — both extractions, ComputeStereoMatches, the two searches
+    # with mvuRight gates, dynamic mask — on this rank's sequence (right views rendered with an 11 px disparity)
+    if strides[0] <= L.cap:
+        dright = torch.from_numpy(make_frames(cfg, rank, 1, Bs, disparity=11)).cuda()
+        sp = dict(params); sp["mono"] = 0
+        tin = pysdyn.track_inputs(dptrs, 0, strides, sp)
+
+        def stereo_track_step():
+            pysdyn.track_batch_stereo_device(L, R, Bs, dev_frames[0].data_ptr(), dright.data_ptr(), W * H, W, H, W, tin, mb, mbf)
+
+        for _ in range(3):
+            stereo_track_step()
+        L.sync(); R.sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            stereo_track_step()
+        L.sync(); R.sync()
+        dt3 = time.perf_counter() - t0
+        ur3, dp3, kept3 = pysdyn.stereo_fetch(L, Bs)
+        a3, l3, m3, c3 = pysdyn.track_fetch(L, Bs)
+        out["stereo_track_config3"] = {"pairs_per_s": Bs * steps / dt3, "ms_per_step": 1e3 * dt3 / steps, "pairs_per_step": Bs,
+                                       "stereo_points_per_pair": float(kept3.mean()), "matches_frame": float(c3[:, 0].mean()),
+                                       "matches_map": float(c3[:, 1].mean()),
+                                       "stages": "extract L + extract R + ComputeStereoMatches + SearchByProjection(cur,last) + "
+                                                 "SearchByProjection(F,map) + dynamic mask (one context pair, host clock)"}
     # ComputeBoW on the left frames with an ORBvoc-shaped vocabulary (k = 10, L = 6)
     parent, leaf, vdesc, weight = big_vocabulary()
     voc = pysdyn.Vocabulary(parent, leaf, vdesc, weight, 10, 6, device=local)
@@ -580,7 +606,7 @@ def main():
     extras = None
     if args.next_rows and world == 1 and cfg == "kitti":
         try:
-            extras = next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, max(K // 2, 5))
+            extras = next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, max(K // 2, 5), rank, dptrs, strides, params, dev_frames)
         except Exception as e:          # never lose the headline line to a side measurement
             extras = {"error": repr(e)}
 
