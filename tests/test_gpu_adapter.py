@@ -38,6 +38,15 @@ def test_adapter_library_exports_reference_symbols():
     assert "ORB_SLAM2::ORBextractor::operator()(cv::_InputArray const&, cv::_InputArray const&, std::vector<cv::KeyPoint" in syms
 
 
+def test_adapter_templates_typecheck():
+    """CPU check: every adapter template of host/sdyn_adapters.hpp — including the ones that need OpenCV's matrix algebra
+    and are therefore not instantiated by tests/cpp/test_adapter.cc — instantiates against declaration-only mocks with the
+    reference's member names (tests/cpp/adapter_syntax.cc)."""
+    src = os.path.join(ROOT, "tests", "cpp", "adapter_syntax.cc")
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-Wextra", src], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+
+
 @pytest.mark.gpu
 def test_adapter_classes_match_oracle(tmp_path):
     out = str(tmp_path / "adapter.bin")
