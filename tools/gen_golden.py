@@ -7,6 +7,9 @@ the oracle (CPU tests) and the CUDA path (GPU tests) must both reproduce these h
 Also writes tests/golden/match_oracle.json: regression hashes of the oracle's matcher / dynamic-mask outputs
 on seeded scenarios (these have no independent OpenCV counterpart; they guard against drift).
 
+Also writes tests/golden/next_rows.json (tests/next_cases.py): digests of the SURVEY 8(f) rows from the independent
+twins (cv2-backed) where they exist and from the oracle otherwise.
+
 Run in the build container:  python tools/gen_golden.py
 """
 import json
@@ -70,6 +73,14 @@ def main():
                            "bow": [n4, common.sha(ab)]})
         print(cfg, n1, n2, n3, n4)
     json.dump(m, open(os.path.join(ROOT, "tests", "golden", "match_oracle.json"), "w"), indent=1)
+
+    # independent twins where they exist (cv2-backed stereo windows, cv2.undistortPoints), oracle otherwise
+    import next_cases
+    nr = {"source": "stereo: tests/stereo_twin.py (cv2 window arithmetic); undistort: cv2.undistortPoints; others: oracle regression",
+          "stereo_small": next_cases.stereo_case("twin"), "undistort_tum1": next_cases.undistort_case("twin"),
+          "bow": next_cases.bow_case("oracle"), "matcher_tum": next_cases.matcher_cases(next_cases.Inputs("tum"), "oracle")}
+    json.dump(nr, open(os.path.join(ROOT, "tests", "golden", "next_rows.json"), "w"), indent=1)
+    print("next rows:", {k: (v if not isinstance(v, dict) else "...") for k, v in nr.items() if k != "source"})
 
 
 if __name__ == "__main__":
