@@ -54,13 +54,20 @@ __device__ int block_exscan(int* a, int n, int* warpTmp)
     __syncthreads();                       /* warpTmp may still be read from a previous call */
     if ((tid & 31) == 31) warpTmp[tid >> 5] = incl;
     __syncthreads();
-    int base = 0, total = 0;
+    /* the 16 warp totals are scanned by the first warp (two shared reads per thread afterwards instead of 16) */
+    if (tid < 32) {
+        const int v = tid < OT / 32 ? warpTmp[tid] : 0;
+        int wi = v;
 #pragma unroll
-    for (int w = 0; w < OT / 32; ++w) {
-        const int v = warpTmp[w];
-        if (w < (tid >> 5)) base += v;
-        total += v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, wi, o);
+            if (tid >= o) wi += u;
+        }
+        if (tid < OT / 32) warpTmp[tid] = wi - v;
+        if (tid == 31) warpTmp[OT / 32] = wi;
     }
+    __syncthreads();
+    const int base = warpTmp[tid >> 5], total = warpTmp[OT / 32];
     int run = base + incl - sum;
     for (int i = beg; i < end; ++i) { const int v = a[i]; a[i] = run; run += v; }
     __syncthreads();
@@ -90,7 +97,7 @@ k_octree(const __grid_constant__ Geom g, int iniTh, int minTh, const uint8_t* __
     int* byProc = proc + cap;        /* processing index -> node */
     int* scanA = byProc + cap;       /* scan scratch */
     int* scanB = scanA + cap;
-    __shared__ int warpTmp[OT / 32];
+    __shared__ int warpTmp[OT / 32 + 1];
     __shared__ int sN, sExpand, sErr;
 
     uint32_t* K = cand + (size_t)f * g.candPerFrame + L.candOff;
