@@ -65,7 +65,7 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     /* level sizes follow cvRound(size * invScale) like ComputePyramid; allocate the bordered owners and hand
      * their interiors out as mvImagePyramid, exactly the ROI-of-a-bordered-Mat shape of the reference */
     uint8_t* pyr[SDYN_MAX_LEVELS] = {nullptr};
-    for (int l = 0; l < mLevels; ++l) {
+    for (int l = 0; l < mLevels && mPyramidOnHost; ++l) {
         const float s = mvInvScaleFactor[l];
         const int w = (int)std::lrintf((float)image.cols * s), h = (int)std::lrintf((float)image.rows * s);
         mBordered[l].create(h + 2 * SDYN_EDGE, w + 2 * SDYN_EDGE, CV_8UC1);
@@ -77,7 +77,8 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     const int cap = (int)mStageKp.size();
     static_assert(sizeof(cv::KeyPoint) == sizeof(sdyn_keypoint), "cv::KeyPoint and sdyn_keypoint must share a layout");
     const int rc = sdyn_extract(mCtx, image.data, image.cols, image.rows, (int)image.step,
-                                reinterpret_cast<sdyn_keypoint*>(mStageKp.data()), mStageDesc.data(), cap, &n, pyr);
+                                reinterpret_cast<sdyn_keypoint*>(mStageKp.data()), mStageDesc.data(), cap, &n,
+                                mPyramidOnHost ? pyr : nullptr);
     if (rc != SDYN_OK) {
         std::fprintf(stderr, "ORBextractor: %s\n", sdyn_last_error(mCtx));
         assert(rc == SDYN_OK);

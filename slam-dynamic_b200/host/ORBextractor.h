@@ -47,6 +47,10 @@ public:
 
     /* GPU context of this extractor (one per instance: left and right extractors run concurrently). */
     sdyn_ctx* Context() { return mCtx; }
+    /* mvImagePyramid is the one output that costs a 1.4 MB device-to-host copy per image.  Its only host reader in the
+     * reference is Frame::ComputeStereoMatches (src/Frame.cc:881-988); once that runs on the device through
+     * sdyn_host::ComputeStereoMatches the copy can be switched off (the levels stay available via sdyn_fetch_level). */
+    void SetPyramidOnHost(bool on) { mPyramidOnHost = on; }
     /* Device the next context is created on (default 0); sharded deployments set it before the first frame. */
     static void SetDevice(int device);
 
@@ -60,6 +64,7 @@ protected:
 
     sdyn_ctx* mCtx;
     int mCtxW, mCtxH;
+    bool mPyramidOnHost = true;
     std::vector<cv::Mat> mBordered;          /* owners of the bordered level buffers */
     std::vector<cv::KeyPoint> mStageKp;      /* reused staging, sized once */
     std::vector<unsigned char> mStageDesc;
