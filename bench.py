@@ -319,6 +319,36 @@ def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptr
                   "cpu_oracle_ms_per_frame": cpu_ms,
                   "reference": "Frame::ComputeBoW -> DBoW2 transform, src/Frame.cc:803-810"}
     voc.close(); L.close(); R.close()
+    # the reference's own execution model: one frame per call through the drop-in entry points (host buffers in and out)
+    try:
+        import orc as _orc
+        one = pysdyn.Extractor(nf, SCALE, NLEVELS, ini, mn, max_width=W, max_height=H, max_batch=1, device=local)
+        img0, img1 = pairs[0][0], pairs[1][0]
+        for _ in range(5):
+            one(img0)
+        lat = []
+        for i in range(40):
+            t1 = time.perf_counter(); k1_, d1_ = one(img1 if i & 1 else img0); lat.append(time.perf_counter() - t1)
+        k0_, d0_ = one(img0); k1_, d1_ = one(img1)
+        scale = one.GetScaleFactors()
+        cur = scenario.frame_view(k1_, d1_, scale, W, H); last = scenario.frame_view(k0_, d0_, scale, W, H)
+        lp = scenario.last_points(k0_, d0_, (0, 0), seed=7)
+        mt = pysdyn.Matcher(one, 0.9, True)
+        for _ in range(3):
+            mt.SearchByProjectionFrame(cur, last, lp, 7.0, False)
+        lm = []
+        for _ in range(20):
+            t1 = time.perf_counter(); mt.SearchByProjectionFrame(cur, last, lp, 7.0, False); lm.append(time.perf_counter() - t1)
+        oe = _orc.Extractor(nf, SCALE, NLEVELS, ini, mn)
+        t1 = time.perf_counter(); oe(img0); cpu_ex = time.perf_counter() - t1
+        t1 = time.perf_counter(); _orc.match_projection_frame(cur, last, lp, 7.0, False, True); cpu_m = time.perf_counter() - t1
+        out["single_frame_latency"] = {"extract_ms": 1e3 * float(np.median(lat)), "search_by_projection_frame_ms": 1e3 * float(np.median(lm)),
+                                       "cpu_oracle_extract_ms": 1e3 * cpu_ex, "cpu_oracle_search_ms": 1e3 * cpu_m,
+                                       "note": "ORBextractor::operator() / SearchByProjection(cur,last) one call at a time, host arrays in "
+                                               "and out (H2D, kernels, D2H, synchronisation inside the call)"}
+        one.close()
+    except Exception as e:
+        out["single_frame_latency"] = {"error": repr(e)}
     return out
 
 
