@@ -122,35 +122,57 @@ k_resize(const __grid_constant__ Geom g, int level, const uint8_t* __restrict__ 
                 reinterpret_cast<uint4*>(src + r * srcPitch)[q2] = __ldg(reinterpret_cast<const uint4*>(sbase + (long long)r * P.pitch) + q2);
     }
     __syncthreads();
-    /* horizontal pass: thread = (column c of the tile, source rows r = tid/128, +2, ...) */
+    /* horizontal pass: thread = (column c of the tile, source rows r = tid/128, +2, ...), four rows per iteration so the
+     * loop and address arithmetic are paid once per four values */
     {
         const int c = tid & (RT_W - 1);
         const ResizeTap t = sx[c];
         const uint32_t c0 = (uint32_t)t.c0, c1 = (uint32_t)t.c1;
-        const uint8_t* s0 = src + (t.s0 - ax0), * s1 = src + (t.s1 - ax0);
-        uint16_t* h = hz + c;
-        for (int r = tid >> 7; r < nrows; r += 2)
-            h[r * RT_W] = (uint16_t)((s0[r * srcPitch] * c0 + s1[r * srcPitch] * c1) >> 4);
+        const int r0 = tid >> 7;
+        const uint8_t* s0 = src + (t.s0 - ax0) + r0 * srcPitch, * s1 = src + (t.s1 - ax0) + r0 * srcPitch;
+        uint16_t* h = hz + c + r0 * RT_W;
+        const int p2 = 2 * srcPitch, p4 = 4 * srcPitch, p6 = 6 * srcPitch;
+        int r = r0;
+        for (; r + 6 < nrows; r += 8) {
+            const uint32_t a0 = s0[0], a1 = s0[p2], a2 = s0[p4], a3 = s0[p6];
+            const uint32_t b0 = s1[0], b1 = s1[p2], b2 = s1[p4], b3 = s1[p6];
+            h[0] = (uint16_t)((a0 * c0 + b0 * c1) >> 4);
+            h[2 * RT_W] = (uint16_t)((a1 * c0 + b1 * c1) >> 4);
+            h[4 * RT_W] = (uint16_t)((a2 * c0 + b2 * c1) >> 4);
+            h[6 * RT_W] = (uint16_t)((a3 * c0 + b3 * c1) >> 4);
+            s0 += 8 * srcPitch; s1 += 8 * srcPitch; h += 8 * RT_W;
+        }
+        for (; r < nrows; r += 2) {
+            h[0] = (uint16_t)((s0[0] * c0 + s1[0] * c1) >> 4);
+            s0 += p2; s1 += p2; h += 2 * RT_W;
+        }
     }
     __syncthreads();
-    /* vertical pass: thread = (4 adjacent columns, output rows tid/32, +8, ...).  (b*H) >> 16 is the high half of
-     * H * (b << 16): one IMAD.HI per product instead of a multiply and a shift. */
+    /* vertical pass: thread = 4 adjacent columns of output rows tid/32 + {0, 8, 16, 24}.  (b*H) >> 16 is the high half
+     * of H * (b << 16): one IMAD.HI per product instead of a multiply and a shift. */
     const int gx = tid & 31;
     if (pc0 + gx * 4 >= L.pitch) return;
-    for (int rr = tid >> 5; rr < RT_H; rr += 8) {
-        const int row = row0 + rr;
-        if (row >= bh) break;
-        const ResizeTap ty = sy[rr];
-        const uint2 h0 = *reinterpret_cast<const uint2*>(hz + (ty.s0 - minR) * RT_W + gx * 4);
-        const uint2 h1 = *reinterpret_cast<const uint2*>(hz + (ty.s1 - minR) * RT_W + gx * 4);
-        const uint32_t b0 = (uint32_t)ty.c0 << 16, b1 = (uint32_t)ty.c1 << 16;
-        const uint32_t v0 = (__umulhi(h0.x & 0xffffu, b0) + __umulhi(h1.x & 0xffffu, b1) + 2) >> 2;
-        const uint32_t v1 = (__umulhi(h0.x >> 16, b0) + __umulhi(h1.x >> 16, b1) + 2) >> 2;
-        const uint32_t v2 = (__umulhi(h0.y & 0xffffu, b0) + __umulhi(h1.y & 0xffffu, b1) + 2) >> 2;
-        const uint32_t v3 = (__umulhi(h0.y >> 16, b0) + __umulhi(h1.y >> 16, b1) + 2) >> 2;
-        /* coefficients are non-negative and sum to 2048, so 0 <= v <= 255 without clamping */
-        uint8_t* dst = frame + L.off + (long long)(row - kEdge) * L.pitch - kLeftPad + pc0;
-        reinterpret_cast<uint32_t*>(dst)[gx] = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+    {
+        const int rr0 = tid >> 5;
+        uint8_t* dst = frame + L.off + (long long)(row0 + rr0 - kEdge) * L.pitch - kLeftPad + pc0 + gx * 4;
+        const long long dstep = 8LL * L.pitch;
+        const uint16_t* hcol = hz + gx * 4;
+#pragma unroll
+        for (int k = 0; k < RT_H / 8; ++k) {
+            const int rr = rr0 + 8 * k;
+            if (row0 + rr >= bh) break;
+            const ResizeTap ty = sy[rr];
+            const uint2 h0 = *reinterpret_cast<const uint2*>(hcol + (ty.s0 - minR) * RT_W);
+            const uint2 h1 = *reinterpret_cast<const uint2*>(hcol + (ty.s1 - minR) * RT_W);
+            const uint32_t b0 = (uint32_t)ty.c0 << 16, b1 = (uint32_t)ty.c1 << 16;
+            const uint32_t v0 = (__umulhi(h0.x & 0xffffu, b0) + __umulhi(h1.x & 0xffffu, b1) + 2) >> 2;
+            const uint32_t v1 = (__umulhi(h0.x >> 16, b0) + __umulhi(h1.x >> 16, b1) + 2) >> 2;
+            const uint32_t v2 = (__umulhi(h0.y & 0xffffu, b0) + __umulhi(h1.y & 0xffffu, b1) + 2) >> 2;
+            const uint32_t v3 = (__umulhi(h0.y >> 16, b0) + __umulhi(h1.y >> 16, b1) + 2) >> 2;
+            /* coefficients are non-negative and sum to 2048, so 0 <= v <= 255 without clamping */
+            *reinterpret_cast<uint32_t*>(dst + k * dstep) =
+                __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+        }
     }
 }
 
