@@ -834,11 +834,10 @@ cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQue
     const size_t gridBytes = (size_t)kCellOffBytes + (size_t)maxN * 16, descBytes = (size_t)maxN * 32;
     const int stageGrid = gridBytes <= kCandSmemBudget, stageDesc = (stageGrid ? gridBytes : 0) + descBytes <= kCandSmemBudget;
     const size_t smem = (stageGrid ? gridBytes : 0) + (stageDesc ? descBytes : 0);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    /* the opt-in is per device and cheap: no process-wide cache (contexts of several devices / threads share this code) */
+    if (smem + 2048 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_match_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCandSmemBudget);
         if (e != cudaSuccess) return e;
-        configured = kCandSmemBudget;
     }
     dim3 grid(ctasPerJob, njobs);
     k_match_candidates<<<grid, threads, smem, st>>>(dJobs, stageGrid, stageDesc, maxN);

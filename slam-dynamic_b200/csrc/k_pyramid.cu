@@ -75,7 +75,19 @@ k_level0(const __grid_constant__ Geom g, const uint8_t* __restrict__ in, size_t 
  * Consecutive output rows share source rows (scale 1.2), so the horizontal work is 1.2 rows per output row
  * instead of 2. */
 constexpr int RT_W = 128, RT_H = 32;
+constexpr int kResizePitch = 192;     /* staging pitch of the common case (128-column tile, scale >= ~1.15) */
 
+/* a*c0 + b*c1 as two IMADs (FMA pipe): the compiler's own choice, PRMT + PRMT + IDP.2A, loads the busier ALU pipe */
+__device__ __forceinline__ uint32_t mad2(uint32_t a, uint32_t c0, uint32_t b, uint32_t c1)
+{
+    uint32_t r;
+    asm("{ .reg .u32 t; mul.lo.u32 t, %3, %4; mad.lo.u32 %0, %1, %2, t; }" : "=r"(r) : "r"(a), "r"(c0), "r"(b), "r"(c1));
+    return r;
+}
+
+/* SPITCH > 0: the staging pitch as a compile-time constant (row offsets become immediates of the shared loads);
+ * SPITCH == 0: run-time pitch L.rsPitch (scale factors whose source window is wider than 192 bytes). */
+template <int SPITCH>
 __global__ void __launch_bounds__(256)
 k_resize(const __grid_constant__ Geom g, int level, const uint8_t* __restrict__ tables, uint8_t* __restrict__ pyr)
 {
@@ -87,7 +99,7 @@ k_resize(const __grid_constant__ Geom g, int level, const uint8_t* __restrict__ 
     const int tid = threadIdx.x;
     const int pc0 = blockIdx.x * RT_W, row0 = blockIdx.y * RT_H;     /* padded column / bordered row of the tile */
     const int bw = L.w + 2 * kEdge, bh = L.h + 2 * kEdge;
-    const int srcPitch = L.rsPitch;
+    const int srcPitch = SPITCH > 0 ? SPITCH : L.rsPitch;
     uint8_t* src = smemR;                                             /* rsRows x rsPitch bytes */
     uint16_t* hz = reinterpret_cast<uint16_t*>(smemR + (size_t)L.rsRows * srcPitch);   /* rsRows x RT_W */
     if (tid == 0) { sMinC = 1 << 30; sMaxC = -1; sMinR = 1 << 30; sMaxR = -1; }
@@ -136,10 +148,10 @@ k_resize(const __grid_constant__ Geom g, int level, const uint8_t* __restrict__ 
         for (; r + 6 < nrows; r += 8) {
             const uint32_t a0 = s0[0], a1 = s0[p2], a2 = s0[p4], a3 = s0[p6];
             const uint32_t b0 = s1[0], b1 = s1[p2], b2 = s1[p4], b3 = s1[p6];
-            h[0] = (uint16_t)((a0 * c0 + b0 * c1) >> 4);
-            h[2 * RT_W] = (uint16_t)((a1 * c0 + b1 * c1) >> 4);
-            h[4 * RT_W] = (uint16_t)((a2 * c0 + b2 * c1) >> 4);
-            h[6 * RT_W] = (uint16_t)((a3 * c0 + b3 * c1) >> 4);
+            h[0] = (uint16_t)(mad2(a0, c0, b0, c1) >> 4);
+            h[2 * RT_W] = (uint16_t)(mad2(a1, c0, b1, c1) >> 4);
+            h[4 * RT_W] = (uint16_t)(mad2(a2, c0, b2, c1) >> 4);
+            h[6 * RT_W] = (uint16_t)(mad2(a3, c0, b3, c1) >> 4);
             s0 += 8 * srcPitch; s1 += 8 * srcPitch; h += 8 * RT_W;
         }
         for (; r < nrows; r += 2) {
@@ -189,15 +201,18 @@ cudaError_t launch_level0(const Geom& g, const uint8_t* dIn, size_t inFrameStrid
 cudaError_t launch_resize(const Geom& g, int level, const uint8_t* dTables, uint8_t* dPyr, int nframes, cudaStream_t st)
 {
     const LevelGeom& L = g.L[level];
-    const size_t smem = (size_t)L.rsPitch * L.rsRows + (size_t)L.rsRows * RT_W * sizeof(uint16_t);
-    static size_t configured = 0;
-    if (smem + 2048 > 48 * 1024 && smem > configured) {      /* static shared memory counts against the 48 KB default */
-        cudaError_t e = cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool fixed = L.rsPitch <= kResizePitch;
+    const int pitch = fixed ? kResizePitch : L.rsPitch;
+    const size_t smem = (size_t)pitch * L.rsRows + (size_t)L.rsRows * RT_W * sizeof(uint16_t);
+    if (smem + 2048 > 48 * 1024) {      /* static shared memory counts against the 48 KB default; the opt-in is per device */
+        const int most = 200 * 1024;
+        cudaError_t e = fixed ? cudaFuncSetAttribute(k_resize<kResizePitch>, cudaFuncAttributeMaxDynamicSharedMemorySize, most)
+                              : cudaFuncSetAttribute(k_resize<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     dim3 grid((L.pitch + RT_W - 1) / RT_W, (L.h + 2 * kEdge + RT_H - 1) / RT_H, nframes);
-    k_resize<<<grid, 256, smem, st>>>(g, level, dTables, dPyr);
+    if (fixed) k_resize<kResizePitch><<<grid, 256, smem, st>>>(g, level, dTables, dPyr);
+    else k_resize<0><<<grid, 256, smem, st>>>(g, level, dTables, dPyr);
     return cudaGetLastError();
 }
 

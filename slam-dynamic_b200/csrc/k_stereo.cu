@@ -223,11 +223,9 @@ k_stereo_cull(StereoArgs a)
 cudaError_t launch_stereo(const Geom& g, const StereoArgs& a, int nframes, int maxKpL, cudaStream_t st)
 {
     const size_t smem = (size_t)(a.nRows + 1) * sizeof(int);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem + 2048 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     k_stereo_rows<<<nframes, 256, smem, st>>>(a);
     cudaError_t e = cudaGetLastError();
