@@ -123,3 +123,23 @@ def test_stereo_pair_two_contexts_concurrently():
         ok, od = cpu(im)
         check_frame(out[i][0], out[i][1], ok, od, ("stereo", i))
     [e.close() for e in exs]
+
+
+@pytest.mark.parametrize("nfeatures,scale,nlevels,ini,mn", [(800, 1.5, 5, 20, 7), (600, 2.0, 3, 15, 5), (1200, 1.1, 8, 20, 7),
+                                                            (300, 1.2, 1, 20, 7)])
+def test_other_orb_parameters(nfeatures, scale, nlevels, ini, mn):
+    """ORBextractor settings other than the shipped YAMLs: coarse pyramids (scale 1.5 / 2.0: the resize kernel's
+    run-time staging pitch), a fine one (1.1) and a single level."""
+    W, H = 640, 480
+    gpu = pysdyn.Extractor(nfeatures, scale, nlevels, ini, mn, max_width=W, max_height=H)
+    cpu = orc.Extractor(nfeatures, scale, nlevels, ini, mn)
+    assert np.array_equal(gpu.mvScaleFactor, cpu.scale) and np.array_equal(gpu.mnFeaturesPerLevel, cpu.quota)
+    for idx in range(2):
+        img = common.frame("tum", idx)
+        k, d = gpu(img)
+        ok, od = cpu(img)
+        for l in range(nlevels):
+            assert np.array_equal(gpu.level(0, l), cpu.level(l)), (scale, idx, l)
+        check_frame(k, d, ok, od, (scale, nlevels, idx))
+        assert len(ok) > 100
+    gpu.close()
