@@ -44,7 +44,7 @@ def main():
     scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1.0, "ns": 1e-3, "ms": 1e3}
     agg = collections.defaultdict(list)
     for r in rows[2:]:
-        name = r[hdr.index("Kernel Name")].split("(")[0]
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0].strip()
         g = r[hdr.index("Grid Size")]
         dur = float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")) * scale.get(unit["gpu__time_duration.sum"], 1.0)
         rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", "")) * scale.get(unit["dram__bytes_read.sum"], 1.0)
