@@ -205,7 +205,7 @@ int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frame
         CU(c, launch_orient_describe(g, c->dPyr, c->dBlur, c->dLevelKp, c->dLevelCount, c->dKp, c->dDesc, c->dCount,
                                      c->maxKp, nframes, st));
     }
-    c->launches += 2 + 1 + (g.nlevels - 1) + 4;
+    c->launches += 1 + (g.nlevels - 1) + 4;      /* kernels only: level 0, resizes, FAST, octree, blur, describe (memsets are not counted) */
     if (c->camera.enabled) {          /* Frame::UndistortKeyPoints follows ExtractORB in every Frame constructor */
         StageTimer t(c, st, SDYN_STAGE_DESCRIBE);
         CU(c, launch_undistort(c->camera, c->dKp, c->dCount, c->maxKp, c->dKpUn, nframes, st));

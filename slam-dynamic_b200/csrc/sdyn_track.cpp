@@ -328,7 +328,9 @@ static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs
             if (!both) TCU(c, launch_match_candidates(t->dJobs + B, nframes, in->map_stride, cap, st));
             TCU(c, launch_match_resolve(t->dJobs + B, nframes, MM_MAP, cap, in->map_stride, st));
         }
-        c->launches += 3 + (in->last_stride > 0 ? 2 : 0) + (in->map_stride > 0 ? 3 : 0);
+        /* kernels only: job table, grid, [query order], candidates (one launch for both searches of a full batch), resolves */
+        c->launches += 2 + (in->map_stride > 0 ? 1 : 0) + (both ? 1 : (in->last_stride > 0) + (in->map_stride > 0)) +
+                       (in->last_stride > 0) + (in->map_stride > 0);
     }
     if (fork) TCU(c, cudaStreamWaitEvent(st, c->evJoin2, 0));
     k_copy_match_counts<<<(nframes + 63) / 64, 64, 0, st>>>(t->result, B, nframes, t->counts);
