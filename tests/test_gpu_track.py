@@ -121,3 +121,48 @@ def test_track_batch_stereo_matches_oracle():
         ma, _, _, mc = oracle_track.track_frame(k, d, cpuL.scale, W, H, arrays, f, params, last_stride)
         assert not np.array_equal(ma, ea)
     L.close(); R.close()
+
+
+def test_track_partial_batch_and_single_search():
+    """nframes < max_batch (the two searches go out as separate candidate launches) and steps with only one of the
+    two searches (last_stride = 0 or map_stride = 0) give the same per-frame results as the full step."""
+    import torch
+    cfg, B, Bmax = "tum", 2, 4
+    W, H, nrect, nf, ini, mn = common.CONFIGS[cfg]
+    cid = common.CONFIG_ID[cfg]
+    seq_seed = 1000 * cid + 7
+    frames = np.stack([pysdyn.synth_frame(seq_seed, 1000 * cid + i, W, H, nrect, *scenario.sequence_offsets(i), scenario.sequence_time(i))
+                       for i in range(0, 1 + B)])
+    cpu = orc.Extractor(nf, 1.2, 8, ini, mn)
+    kd = [cpu(im) for im in frames]
+    gpu = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=Bmax)
+    last_stride, map_stride, ref_stride = gpu.cap, 1500, 512
+    arrays = scenario.build_track_batch(kd, seq_seed, 1, W, H, nrect, 8, last_stride, map_stride, ref_stride, n_map=1500, seed=3)
+    params = scenario.track_params(W, H)
+    dev = {k: torch.from_numpy(v.view(np.uint8).reshape(v.shape[0], -1)).cuda() for k, v in arrays.items()}
+    ptrs = {k: (t.data_ptr(), t.shape[1]) for k, t in dev.items()}
+    dframes = torch.from_numpy(frames[1:]).cuda()
+    tin = pysdyn.track_inputs(ptrs, 0, (last_stride, map_stride, ref_stride), params)
+    pysdyn.track_batch_device(gpu, B, dframes.data_ptr(), W * H, W, H, W, tin)
+    kps, desc, counts = gpu.fetch(B)
+    assign, locked, mask, cnt = pysdyn.track_fetch(gpu, B)
+    for f in range(B):
+        k, d = kd[f + 1]
+        n = counts[f]
+        ea, el, em, ec = oracle_track.track_frame(k, d, cpu.scale, W, H, arrays, f, params, last_stride)
+        assert np.array_equal(cnt[f], ec) and np.array_equal(assign[f, :n], ea) and np.array_equal(locked[f, :n], el)
+        assert np.array_equal(mask[f, :n], em)
+    # map search only: the frame search is switched off by last_stride = 0
+    tin2 = pysdyn.track_inputs(ptrs, 0, (0, map_stride, ref_stride), params)
+    pysdyn.track_batch_device(gpu, B, dframes.data_ptr(), W * H, W, H, W, tin2)
+    a2, l2, m2, c2 = pysdyn.track_fetch(gpu, B)
+    for f in range(B):
+        k, d = kd[f + 1]
+        F = scenario.frame_view(k, d, cpu.scale, W, H)
+        F = pysdyn.FrameView(k, d, cpu.scale, (0.0, 0.0, float(W), float(H)),
+                             cam=(scenario.KITTI_CAM["fx"], scenario.KITTI_CAM["fy"], scenario.KITTI_CAM["cx"], scenario.KITTI_CAM["cy"],
+                                  scenario.KITTI_CAM["bf"], scenario.KITTI_CAM["bf"] / scenario.KITTI_CAM["fx"]), tcw=params["tcw_cur"])
+        nm = int(arrays["n_map"][f])
+        n2, ea, el = orc.match_projection_map(F, arrays["map_points"][f, :nm], params["th_map"], params["nnratio_map"], assign_base=0)
+        assert c2[f, 0] == 0 and c2[f, 1] == n2 and np.array_equal(a2[f, :len(k)], ea) and np.array_equal(l2[f, :len(k)], el)
+    gpu.close()
