@@ -23,6 +23,7 @@
  *                      cull follow the reference literally.
  */
 #include "match_internal.h"
+#include <algorithm>
 
 namespace sdyn {
 
@@ -38,17 +39,22 @@ __device__ __forceinline__ int job_n(const MatchJob& J) { return J.nPtr ? min(*J
 __device__ __forceinline__ int job_nq(const MatchJob& J) { return J.nqPtr ? min(*J.nqPtr, J.nq) : J.nq; }
 
 /* ---------------------------------------------------------------------------------------------------- grid */
-__global__ void __launch_bounds__(256)
+constexpr int GB = 1024;   /* one CTA per frame: the kernel is a chain of short dependent phases, so it wants many threads */
+
+__global__ void __launch_bounds__(GB)
 k_grid_build(const MatchJob* __restrict__ jobs)
 {
     const MatchJob& J = jobs[blockIdx.x];
     if (J.mode == MM_BOW || J.mode == MM_TRI) return;
-    __shared__ int cnt[kGridCells];
-    __shared__ int warpSum[8];
+    extern __shared__ int smemG[];
+    int* cnt = smemG;                         /* kGridCells: counters, then insertion cursors */
+    int* start = smemG + kGridCells;          /* kGridCells + 1: CSR offsets */
+    int* sSorted = start + kGridCells + 1;    /* n: keypoint indices in cell order (sorted in shared memory) */
+    __shared__ int warpSum[GB / 32 + 1];
     const int tid = threadIdx.x, n = job_n(J);
-    for (int c = tid; c < kGridCells; c += 256) cnt[c] = 0;
+    for (int c = tid; c < kGridCells; c += GB) cnt[c] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid; i < n; i += GB) {
         const sdyn_keypoint kp = J.keysUn[i];
         /* PosInGrid: round() is half-away-from-zero; keypoints outside the grid are not indexed */
         const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, J.minX), J.gridWInv));
@@ -61,8 +67,9 @@ k_grid_build(const MatchJob* __restrict__ jobs)
         J.cellOf[i] = c;
     }
     __syncthreads();
-    /* exclusive scan of 3072 counters: 12 per thread */
-    constexpr int PER = kGridCells / 256;
+    /* exclusive scan of 3072 counters: 3 per thread */
+    constexpr int PER = kGridCells / GB;
+    static_assert(kGridCells % GB == 0, "cells per thread");
     int local[PER], sum = 0;
 #pragma unroll
     for (int k = 0; k < PER; ++k) { local[k] = cnt[tid * PER + k]; sum += local[k]; }
@@ -71,33 +78,42 @@ k_grid_build(const MatchJob* __restrict__ jobs)
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
     if ((tid & 31) == 31) warpSum[tid >> 5] = incl;
     __syncthreads();
-    int base = 0;
-    for (int w = 0; w < (tid >> 5); ++w) base += warpSum[w];
-    int run = base + incl - sum;
+    if (tid < 32) {
+        const int v = warpSum[tid];
+        int wi = v;
 #pragma unroll
-    for (int k = 0; k < PER; ++k) { J.cellOff[tid * PER + k] = run; cnt[tid * PER + k] = run; run += local[k]; }
-    if (tid == 255) J.cellOff[kGridCells] = run;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, wi, o); if (tid >= o) wi += u; }
+        warpSum[tid] = wi - v;
+        if (tid == 31) warpSum[32] = wi;
+    }
     __syncthreads();
-    for (int i = tid; i < n; i += 256) {
+    int run = warpSum[tid >> 5] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { start[tid * PER + k] = run; cnt[tid * PER + k] = run; run += local[k]; }
+    if (tid == GB - 1) start[kGridCells] = warpSum[32];
+    __syncthreads();
+    for (int i = tid; i < n; i += GB) {
         const int c = J.cellOf[i];
-        if (c >= 0) J.sorted[atomicAdd(&cnt[c], 1)] = i;
+        if (c >= 0) sSorted[atomicAdd(&cnt[c], 1)] = i;
     }
     __syncthreads();
     /* in-cell order = insertion order of AssignFeaturesToGrid = ascending index */
-    for (int c = tid; c < kGridCells; c += 256) {
-        const int b = J.cellOff[c], e = cnt[c];
+    for (int c = tid; c < kGridCells; c += GB) {
+        const int b = start[c], e = cnt[c];
         for (int i = b + 1; i < e; ++i) {
-            const int v = J.sorted[i];
+            const int v = sSorted[i];
             int j = i - 1;
-            while (j >= b && J.sorted[j] > v) { J.sorted[j + 1] = J.sorted[j]; --j; }
-            J.sorted[j + 1] = v;
+            while (j >= b && sSorted[j] > v) { sSorted[j + 1] = sSorted[j]; --j; }
+            sSorted[j + 1] = v;
         }
     }
     __syncthreads();
+    for (int c = tid; c <= kGridCells; c += GB) J.cellOff[c] = start[c];
     /* everything the window / level gates need, next to each other in enumeration order */
-    const int total = J.cellOff[kGridCells];
-    for (int p = tid; p < total; p += 256) {
-        const int idx = J.sorted[p];
+    const int total = start[kGridCells];
+    for (int p = tid; p < total; p += GB) {
+        const int idx = sSorted[p];
+        J.sorted[p] = idx;
         const sdyn_keypoint kp = J.keysUn[idx];
         J.gridEntry[p] = make_float4(kp.x, kp.y, __int_as_float(idx | (kp.octave << 24)), 0.f);
     }
@@ -670,7 +686,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs)
 constexpr int RF = 1024;
 
 __global__ void __launch_bounds__(RF)
-k_match_resolve_fix(const MatchJob* __restrict__ jobs)
+k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
 {
     extern __shared__ int smemFix[];
     const MatchJob& J = jobs[blockIdx.x];
@@ -690,25 +706,72 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
     auto locks = [&](int q) -> bool { return J.mode == MM_FRAME ? lps[q].obs_positive : (J.mode == MM_POSE ? true : mps[q].obs_positive); };
     auto query_angle = [&](int q) -> float { return J.mode == MM_POSE ? pps[q].angle : J.qKeysUn[q].angle; };
 
-    for (int q = tid; q < nq; q += RF) acc[q] = -2;
+    /* Everything a sweep reads is brought into shared memory once: the initial lock state of the keypoints, the
+     * "does this query lock" flags, and the candidate lists compacted back to back (a prefix sum over the list lengths
+     * gives the offsets).  A sweep then touches shared memory only — the sweeps were a chain of dependent L2 round
+     * trips before.  Lists that do not fit (pc records) stay in global memory and are read through the same code. */
+    int* baseT = acc + J.nq;               /* n: lock state on entry (-1 locked, INT_MAX free) */
+    int* sOff = baseT + J.n;               /* nq + 1: offsets of the compacted lists */
+    uint32_t* sPool = reinterpret_cast<uint32_t*>(sOff + J.nq + 1);
+    uint8_t* qLock = reinterpret_cast<uint8_t*>(sPool + poolCap);      /* nq */
+    __shared__ int sStaged;
+    for (int k = tid; k < n; k += RF) baseT[k] = (J.assign[k] != -1 && J.locked[k]) ? -1 : 0x7fffffff;
+    for (int q = tid; q < nq; q += RF) { acc[q] = -2; qLock[q] = locks(q); }
+    {
+        /* exclusive scan of the list lengths: a contiguous chunk of queries per thread */
+        const int per = (nq + RF - 1) / RF, q0 = min(tid * per, nq), q1 = min(q0 + per, nq);
+        int sum = 0;
+        for (int q = q0; q < q1; ++q) sum += J.qspan[q].y;
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+        if ((tid & 31) == 31) warpTot[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            const int v = warpTot[tid];
+            int wi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, wi, o); if (tid >= o) wi += u; }
+            warpTot[tid] = wi - v;
+            if (tid == 31) sStaged = wi <= poolCap;
+        }
+        __syncthreads();
+        int run = warpTot[tid >> 5] + incl - sum;
+        for (int q = q0; q < q1; ++q) { sOff[q] = run; run += J.qspan[q].y; }
+        if (q1 == nq && q0 < nq) sOff[nq] = run;
+        if (nq == 0 && tid == 0) sOff[0] = 0;
+    }
+    __syncthreads();
+    const bool staged = sStaged != 0;
+    if (staged)
+        for (int q = tid; q < nq; q += RF) {
+            const int2 span = J.qspan[q];
+            const int o = sOff[q];
+            for (int p = 0; p < span.y; ++p) sPool[o + p] = __ldg(J.pool + span.x + p);
+        }
+    __syncthreads();
+
     for (int sweep = 0; sweep <= nq; ++sweep) {
         /* T from the claims of the previous sweep */
-        for (int k = tid; k < n; k += RF) lockT[k] = (J.assign[k] != -1 && J.locked[k]) ? -1 : 0x7fffffff;
+        for (int k = tid; k < n; k += RF) lockT[k] = baseT[k];
         __syncthreads();
         if (sweep > 0)
             for (int q = tid; q < nq; q += RF) {
                 const int a = acc[q];
-                if (a >= 0 && locks(q)) atomicMin(&lockT[a], q);
+                if (a >= 0 && qLock[q]) atomicMin(&lockT[a], q);
             }
         __syncthreads();
         int changed = 0;
         for (int q = tid; q < nq; q += RF) {
-            const int2 span = J.qspan[q];
+            int2 span;
+            const uint32_t* P;
+            if (staged) { span.x = sOff[q]; span.y = sOff[q + 1] - span.x; P = sPool; }
+            else { span = J.qspan[q]; P = J.pool; }
             uint32_t a = NONE, b = NONE;
             for (int p0 = 0; p0 < span.y; p0 += 8) {
                 uint32_t rec[8];                       /* 8 independent loads in flight per thread */
 #pragma unroll
-                for (int k = 0; k < 8; ++k) rec[k] = p0 + k < span.y ? __ldg(J.pool + span.x + p0 + k) : NONE;
+                for (int k = 0; k < 8; ++k) rec[k] = p0 + k < span.y ? P[span.x + p0 + k] : NONE;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     if (rec[k] == NONE || lockT[rec_idx(rec[k])] < q) continue;
@@ -718,12 +781,12 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
             }
             int res = -1;
             if (a != NONE) {
-                const uint32_t r1 = J.pool[span.x + (a & 0xfffff)];
+                const uint32_t r1 = P[span.x + (a & 0xfffff)];
                 const int bestDist = (int)(a >> 20);
                 bool ok = bestDist <= J.distTh;
                 if (ok && J.mode == MM_MAP) {
                     int bestDist2 = 256, bestLevel2 = -1;
-                    if (b != NONE) { bestDist2 = (int)(b >> 20); bestLevel2 = rec_level(J.pool[span.x + (b & 0xfffff)]); }
+                    if (b != NONE) { bestDist2 = (int)(b >> 20); bestLevel2 = rec_level(P[span.x + (b & 0xfffff)]); }
                     ok = !(rec_level(r1) == bestLevel2 && (float)bestDist > __fmul_rn(J.nnratio, (float)bestDist2));
                 }
                 if (ok) res = rec_idx(r1);
@@ -759,7 +822,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
         const int q = lockT[k];
         if (q >= 0) {
             J.assign[k] = J.assignBase + q;
-            J.locked[k] = locks(q);
+            J.locked[k] = qLock[q];
         }
     }
     /* point pairs of the fork's overload, in query order (before the cull, Appendix B-8) */
@@ -812,9 +875,14 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs)
     if (tid == 0) { J.result[0] = sCount - sDec; J.result[1] = sCount; }
 }
 
-cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, cudaStream_t st)
+cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, int maxN, cudaStream_t st)
 {
-    k_grid_build<<<njobs, 256, 0, st>>>(dJobs);
+    const size_t smem = (size_t)(2 * kGridCells + 1 + std::max(maxN, 1)) * sizeof(int);
+    if (smem + 2048 > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_grid_build<<<njobs, GB, smem, st>>>(dJobs);
     return cudaGetLastError();
 }
 
@@ -847,10 +915,15 @@ cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQue
 cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st)
 {
     if (mode == MM_FRAME || mode == MM_MAP || mode == MM_POSE) {
-        const size_t smem = (size_t)(maxN + maxQ) * sizeof(int);
+        /* lockT + baseT (maxN each), acc + sOff (maxQ each), qLock bytes, and whatever is left for the compacted lists */
+        const size_t fixedB = (size_t)(2 * maxN + 2 * maxQ + 1) * sizeof(int) + (size_t)maxQ + 16;
+        const size_t budget = 200 * 1024;
+        if (fixedB + 4096 > budget) return cudaErrorInvalidValue;
+        const int poolCap = (int)((budget - fixedB) / 4);
+        const size_t smem = fixedB + (size_t)poolCap * 4;
         cudaError_t e = cudaFuncSetAttribute(k_match_resolve_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k_match_resolve_fix<<<njobs, RF, smem, st>>>(dJobs);
+        k_match_resolve_fix<<<njobs, RF, smem, st>>>(dJobs, poolCap);
     } else {
         k_match_resolve<<<njobs, 32, 0, st>>>(dJobs);
     }

@@ -71,7 +71,8 @@ struct MatchJob {
     int32_t* qNext;                  /* next unvisited query slot (k_match_candidates work counter), zero on entry */
 };
 
-cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, cudaStream_t st);
+/* maxN: largest MatchJob::n of the launch (sizes the shared-memory sort buffer) */
+cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, int maxN, cudaStream_t st);
 /* fills MatchJob::qperm of MM_MAP jobs that have one */
 cudaError_t launch_query_order(const MatchJob* dJobs, int njobs, cudaStream_t st);
 /* maxN: largest MatchJob::n of the launch (sizes the shared-memory staging of the searched frame) */

@@ -108,7 +108,7 @@ int run_job(sdyn_ctx* c, size_t fixedBytes, int nq, int poolGuess, int poolMax, 
         MCU(c, cudaMemsetAsync(J.poolUsed, 0, 2 * sizeof(int32_t), c->stream));
         MCU(c, cudaMemsetAsync(J.result, 0, 4 * sizeof(int32_t), c->stream));
         MCU(c, cudaMemcpyAsync(dJob, &J, sizeof(J), cudaMemcpyHostToDevice, c->stream));
-        MCU(c, launch_grid_build(dJob, 1, c->stream));
+        MCU(c, launch_grid_build(dJob, 1, std::max(J.n, 1), c->stream));
         MCU(c, launch_match_candidates(dJob, 1, nq, std::max(J.n, 1), c->stream));
         MCU(c, launch_match_resolve(dJob, 1, J.mode, std::max(J.n, 1), std::max(nq, 1), c->stream));
         c->launches += 3;
@@ -318,7 +318,7 @@ int sdyn_match_projection_best(sdyn_ctx* c, const sdyn_frame_view* target, const
         MCU(c, upload_frame(target, J, c->stream));
         MCU(c, up(dq, pts, npts, c->stream));
         MCU(c, cudaMemcpyAsync(dJob, &J, sizeof(J), cudaMemcpyHostToDevice, c->stream));
-        MCU(c, launch_grid_build(dJob, 1, c->stream));
+        MCU(c, launch_grid_build(dJob, 1, std::max(J.n, 1), c->stream));
         MCU(c, launch_match_candidates(dJob, 1, npts, std::max(J.n, 1), c->stream));
         c->launches += 2;
         int32_t res[4];

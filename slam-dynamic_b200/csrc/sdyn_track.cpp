@@ -311,7 +311,7 @@ static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs
             k_build_jobs<<<(words + 255) / 256, 256, 0, st>>>(pF, pM, t->dJobs, B, nframes);
             TCU(c, cudaGetLastError());
         }
-        TCU(c, launch_grid_build(t->dJobs, nframes, st));
+        TCU(c, launch_grid_build(t->dJobs, nframes, cap, st));
         if (in->map_stride > 0) TCU(c, launch_query_order(t->dJobs + B, nframes, st));
         /* candidate generation only applies static gates, so both searches of every frame go out in ONE launch
          * when their jobs are contiguous (full batch); the claims are then resolved frame search first */
