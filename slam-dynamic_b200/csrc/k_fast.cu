@@ -138,9 +138,11 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
                   ((uint32_t)(c0 + 1 >= xlo && c0 + 1 < xhi) << 31) | ((uint32_t)(c0 + 3 >= xlo && c0 + 3 < xhi) << 30);
     }
     uint32_t valid = 0;
+    /* a thread's four rows are ADJACENT (pitch 40 words: banks +0, +8, +16, +24).  Rows eight apart would put all 16
+     * positions of a thread — consecutive list entries, scored by adjacent lanes in (B) — in one bank */
 #pragma unroll
     for (int r = 0; r < ROWR; ++r) {
-        const int yy = warp + (FT / 32) * r;
+        const int yy = ROWR * warp + r;
         if (yy >= ylo && yy < yhi) valid |= colMask >> (2 * r);
         const uint32_t* rc = reinterpret_cast<const uint32_t*>(px + (yy + 3) * PWB + cbase) + lane;
         const uint32_t wl = rc[-1], wc = rc[0], wr = rc[1], wn = rc[-3 * (PWB / 4)], ws = rc[3 * (PWB / 4)];
@@ -172,7 +174,7 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
             const int k = 15 - (b & 15);                  /* 2r + (column >= 2) */
-            const int yy = warp + (FT / 32) * (k >> 1), xx = 4 * lane + 2 * (k & 1) + (b >> 4);
+            const int yy = ROWR * warp + (k >> 1), xx = 4 * lane + 2 * (k & 1) + (b >> 4);
             list[base++] = (uint16_t)(yy * SW + xx);
         }
     }
