@@ -378,7 +378,7 @@ def main():
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample length (0 = skip)")
-    ap.add_argument("--contexts", type=int, default=4, help="contexts (streams) per GPU taking steps round-robin")
+    ap.add_argument("--contexts", type=int, default=6, help="contexts (streams) per GPU taking steps round-robin")
     ap.add_argument("--next-rows", type=int, default=1, help="also time the SURVEY 8(f) rows (stereo, BoW) on rank 0 at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -492,13 +492,24 @@ def main():
     mean_kp = float(counts.mean())
 
     # ---- end to end through the C ABI with pinned host buffers ("e2e") ------------------------------------
-    pin = {k: pysdyn.PinnedArray((v.shape[0], int(np.prod(v.shape[1:])) * v.dtype.itemsize), np.uint8) for k, v in arrays.items()
-           if not (keys_un_alias and k == "last_keys_un")}
-    for k, p in pin.items():
-        p.array[:] = arrays[k].view(np.uint8).reshape(arrays[k].shape[0], -1)
-    hptrs = {k: (p.array.ctypes.data, p.array.shape[1]) for k, p in pin.items()}
-    if keys_un_alias:
-        hptrs["last_keys_un"] = hptrs["last_keys"]
+    # the query arrays of a step live in ONE pinned block at sdyn_track_input_layout's offsets: libsdyn uploads such a block
+    # with a single copy (a dozen small copies cost more PCIe time than their bytes)
+    layout, block_bytes = pysdyn.track_input_layout(B, strides, not keys_un_alias)
+    blocks, hptr_sets = [], []
+    for sset in range(nsets):
+        blk = pysdyn.PinnedArray((block_bytes,), np.uint8)
+        blk.array[:] = 0
+        ptrs = {}
+        for k, v in arrays.items():
+            rows = v.view(np.uint8).reshape(v.shape[0], -1)
+            if not (keys_un_alias and k == "last_keys_un"):
+                chunk = rows[sset * B:(sset + 1) * B].reshape(-1)
+                blk.array[layout[k]:layout[k] + chunk.size] = chunk
+            ptrs[k] = (blk.array.ctypes.data + layout[k], rows.shape[1])
+        if keys_un_alias:
+            ptrs["last_keys_un"] = ptrs["last_keys"]
+        blocks.append(blk)
+        hptr_sets.append(ptrs)
     pin_in = pysdyn.PinnedArray((POOL, H, W), np.uint8)
     pin_in.array[:] = cur_frames
     # the same NCTX contexts round-robin: a step's PCIe copies overlap the other contexts' kernels
@@ -511,7 +522,7 @@ def main():
 
     def step_host_async(s):
         base = (s % nsets) * B
-        tin = pysdyn.track_inputs(hptrs, base, strides, params)
+        tin = pysdyn.track_inputs(hptr_sets[s % nsets], 0, strides, params)
         pysdyn.track_batch_host_async(ctxs[s % NCTX], pin_in.array[base:base + B], tin, out_sets[s % NCTX][1])
 
     def run_host(first, count):
@@ -539,7 +550,7 @@ def main():
     if (last % nsets) == ((Wm + K - 1) % nsets):
         eo = out_sets[last % NCTX][1]
         assert np.array_equal(eo[2], counts) and np.array_equal(eo[6], cnt), "e2e and device-resident results differ"
-    h2d = B * W * H + sum(p.array.shape[1] for p in pin.values()) * B
+    h2d = B * W * H + block_bytes                       # bytes actually copied per step (block padding included)
     # what the host link delivers for one plain pinned copy of a step's input volume (context for the e2e number)
     link = None
     if rank == 0:

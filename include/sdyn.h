@@ -394,6 +394,16 @@ int sdyn_track_batch_async(sdyn_ctx* ctx, int nframes, const uint8_t* gray, size
                            int stride, const sdyn_track_inputs* in, sdyn_keypoint* kp_out, uint8_t* desc_out, int* n_out,
                            int32_t* assign, uint8_t* locked, uint8_t* dyn_mask, int32_t* counts, int cap);
 int sdyn_track_wait(sdyn_ctx* ctx);
+/* Layout of the host-buffer entry points' input staging block for `nframes` frames: offsets[i] is where array i of
+ * sdyn_track_inputs starts (order: last_points, last_keys, last_keys_un, n_last, map_points, n_map, boxes, n_boxes, ref_box,
+ * ref_desc, ref_xy, ref_off, fmat; each on a 256-byte boundary; last_keys_un takes no room unless separate_keys_un), *total
+ * the block size.  A caller that builds its arrays inside ONE host block at these offsets (pinned with sdyn_host_alloc) and
+ * passes base + offsets[i] as the array pointers has them uploaded with a single copy instead of one copy per array — the
+ * per-frame query data the reference keeps in MapPoint / Frame objects (src/ORBmatcher.cc:45-129, 1485-1627) is gathered
+ * by the caller either way. */
+#define SDYN_TRACK_INPUT_ARRAYS 13
+int sdyn_track_input_layout(int nframes, int last_stride, int map_stride, int ref_stride, int separate_keys_un,
+                            size_t offsets[SDYN_TRACK_INPUT_ARRAYS], size_t* total);
 /* Statistics of the last fetched step: Hamming-distance evaluations of the frame search and of the map search,
  * summed over the step's frames (the work the popc roofline is computed from). */
 int sdyn_track_stats(const sdyn_ctx* ctx, int nframes, long long evals[2]);

@@ -339,6 +339,54 @@ static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs
     return SDYN_OK;
 }
 
+/* The per-frame input arrays of a step, in upload order, and their offsets in the staging block for `n` frames (each
+ * array starts on a 256-byte boundary).  Returns the block size. */
+struct TrackItem { const void* src; size_t bytesPerFrame; size_t off; };
+
+static size_t track_items(const sdyn_track_inputs* in, size_t n, TrackItem* items)
+{
+    const TrackItem init[SDYN_TRACK_INPUT_ARRAYS] = {
+        {in->last_points, (size_t)in->last_stride * sizeof(sdyn_last_point), 0},
+        {in->last_keys, (size_t)in->last_stride * sizeof(sdyn_keypoint), 0},
+        /* mvKeysUn == mvKeys for an undistorted camera (src/Frame.cc:814-818): one upload serves both */
+        {(in->last_keys_un && in->last_keys_un != in->last_keys) ? in->last_keys_un : nullptr,
+         (in->last_keys_un && in->last_keys_un != in->last_keys) ? (size_t)in->last_stride * sizeof(sdyn_keypoint) : 0, 0},
+        {in->n_last, 4, 0},
+        {in->map_points, (size_t)in->map_stride * sizeof(sdyn_mappoint_query), 0},
+        {in->n_map, 4, 0},
+        {in->boxes, 64 * 4 * sizeof(double), 0},
+        {in->n_boxes, 4, 0},
+        {in->ref_box, 64 * 4, 0},
+        {in->ref_desc, (size_t)in->ref_stride * 32, 0},
+        {in->ref_xy, (size_t)in->ref_stride * 8, 0},
+        {in->ref_off, 65 * 4, 0},
+        {in->fmat, 9 * 4, 0},
+    };
+    size_t total = 0;
+    for (int i = 0; i < SDYN_TRACK_INPUT_ARRAYS; ++i) {
+        items[i] = init[i];
+        items[i].off = total;
+        total += (items[i].bytesPerFrame * n + 255) / 256 * 256;
+    }
+    return total;
+}
+
+int sdyn_track_input_layout(int nframes, int last_stride, int map_stride, int ref_stride, int separate_keys_un,
+                            size_t offsets[SDYN_TRACK_INPUT_ARRAYS], size_t* total)
+{
+    if (nframes < 1 || last_stride < 0 || map_stride < 0 || ref_stride < 0 || !offsets || !total) return SDYN_ERR_ARG;
+    sdyn_track_inputs in;
+    memset(&in, 0, sizeof in);
+    in.last_stride = last_stride; in.map_stride = map_stride; in.ref_stride = ref_stride;
+    /* only the NULL-ness of last_keys_un matters to the layout */
+    static const sdyn_keypoint kA = {}, kB = {};
+    in.last_keys = &kA; in.last_keys_un = separate_keys_un ? &kB : &kA;
+    TrackItem items[SDYN_TRACK_INPUT_ARRAYS];
+    *total = track_items(&in, (size_t)nframes, items);
+    for (int i = 0; i < SDYN_TRACK_INPUT_ARRAYS; ++i) offsets[i] = items[i].off;
+    return SDYN_OK;
+}
+
 int sdyn_track_batch(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frameStride, int W, int H, int stride,
                      const sdyn_track_inputs* in, sdyn_keypoint* kpOut, uint8_t* descOut, int* nOut, int32_t* assign,
                      uint8_t* locked, uint8_t* dynMask, int32_t* counts, int cap)
@@ -359,37 +407,32 @@ int sdyn_track_batch_async(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t
     int rc = ensure_track_state(c, std::max(std::max(in->last_stride, in->map_stride), 1), in->ref_stride);
     if (rc != SDYN_OK) return rc;
     TrackState* t = static_cast<TrackState*>(c->track);
-    /* device staging of the per-frame input arrays */
-    const size_t n = (size_t)nframes, B = (size_t)c->maxBatch;
-    struct Item { const void* src; size_t bytesPerFrame; size_t off; };
-    Item items[] = {
-        {in->last_points, (size_t)in->last_stride * sizeof(sdyn_last_point), 0},
-        {in->last_keys, (size_t)in->last_stride * sizeof(sdyn_keypoint), 0},
-        /* mvKeysUn == mvKeys for an undistorted camera (src/Frame.cc:814-818): one upload serves both */
-        {(in->last_keys_un && in->last_keys_un != in->last_keys) ? in->last_keys_un : nullptr, (size_t)in->last_stride * sizeof(sdyn_keypoint), 0},
-        {in->n_last, 4, 0},
-        {in->map_points, (size_t)in->map_stride * sizeof(sdyn_mappoint_query), 0},
-        {in->n_map, 4, 0},
-        {in->boxes, 64 * 4 * sizeof(double), 0},
-        {in->n_boxes, 4, 0},
-        {in->ref_box, 64 * 4, 0},
-        {in->ref_desc, (size_t)in->ref_stride * 32, 0},
-        {in->ref_xy, (size_t)in->ref_stride * 8, 0},
-        {in->ref_off, 65 * 4, 0},
-        {in->fmat, 9 * 4, 0},
-    };
-    size_t total = 0;
-    for (auto& it : items) { it.off = total; total += (it.bytesPerFrame * B + 255) / 256 * 256; }
+    /* device staging of the per-frame input arrays, laid out as sdyn_track_input_layout() describes */
+    const size_t n = (size_t)nframes;
+    TrackItem items[SDYN_TRACK_INPUT_ARRAYS];
+    const size_t total = track_items(in, n, items);
     if (total > t->inBytes) {
+        const size_t want = std::max(total, track_items(in, (size_t)c->maxBatch, items));
+        track_items(in, n, items);
         TCU(c, cudaStreamSynchronize(c->stream));
         cudaFree(t->inBlock); t->inBlock = nullptr; t->inBytes = 0;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&t->inBlock), total);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&t->inBlock), want);
         if (e != cudaSuccess) return api_fail(c, SDYN_ERR_NOMEM, std::string("track input staging: ") + cudaGetErrorString(e));
-        t->inBytes = total;
+        t->inBytes = want;
     }
-    for (auto& it : items)
-        if (it.src && it.bytesPerFrame)
-            TCU(c, cudaMemcpyAsync(t->inBlock + it.off, it.src, it.bytesPerFrame * n, cudaMemcpyHostToDevice, c->stream));
+    /* A caller that keeps its arrays in ONE host block at the layout's offsets gets ONE copy: a dozen small copies cost
+     * more PCIe time than their bytes (each pays the copy engine's set-up latency). */
+    const uint8_t* base = static_cast<const uint8_t*>(items[0].src);
+    bool packed = base != nullptr;
+    for (const auto& it : items)
+        if (it.src && it.bytesPerFrame && static_cast<const uint8_t*>(it.src) != base + it.off) packed = false;
+    if (packed) {
+        TCU(c, cudaMemcpyAsync(t->inBlock, base, total, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (const auto& it : items)
+            if (it.src && it.bytesPerFrame)
+                TCU(c, cudaMemcpyAsync(t->inBlock + it.off, it.src, it.bytesPerFrame * n, cudaMemcpyHostToDevice, c->stream));
+    }
     TCU(c, upload_frames(c, nframes, gray, frameStride, W, H, stride, c->stream));
     sdyn_track_inputs d = *in;
     d.last_points = reinterpret_cast<const sdyn_last_point*>(t->inBlock + items[0].off);

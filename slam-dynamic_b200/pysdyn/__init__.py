@@ -651,6 +651,19 @@ def track_inputs(ptrs, frame0, strides, params):
     return t
 
 
+def track_input_layout(nframes, strides, separate_keys_un=False):
+    """sdyn_track_input_layout: ({array name: offset}, block bytes) of the single-copy host staging block."""
+    L = lib()
+    L.sdyn_track_input_layout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t * len(TRACK_ARRAYS)),
+                                          C.POINTER(C.c_size_t)]
+    offs, total = (C.c_size_t * len(TRACK_ARRAYS))(), C.c_size_t()
+    rc = L.sdyn_track_input_layout(nframes, strides[0], strides[1], strides[2], int(bool(separate_keys_un)), C.byref(offs),
+                                   C.byref(total))
+    if rc != 0:
+        raise SdynError(rc, "sdyn_track_input_layout: bad argument")
+    return dict(zip(TRACK_ARRAYS, [int(o) for o in offs])), int(total.value)
+
+
 def _bind_track(L):
     if getattr(L, "_track_bound", False):
         return L

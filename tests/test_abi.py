@@ -83,3 +83,22 @@ def test_bad_arguments_are_rejected_before_touching_the_device():
                 pysdyn.OrbParams(1000, 1.2, 8, 0, 7)]:
         assert lib.sdyn_create(C.byref(bad), 640, 480, 1, 0, C.byref(h)) == -1 and not h.value
     assert lib.sdyn_destroy(None) == 0 and lib.sdyn_last_error(None) is not None
+
+
+def test_track_input_layout_offsets():
+    """sdyn_track_input_layout: arrays in upload order, each on a 256-byte boundary, last_keys_un only when separate."""
+    import pysdyn
+    for n, strides in [(1, (100, 50, 16)), (64, (2200, 3000, 256)), (3, (0, 0, 0))]:
+        for sep in (False, True):
+            lay, total = pysdyn.track_input_layout(n, strides, sep)
+            per_frame = {"last_points": strides[0] * 48, "last_keys": strides[0] * 28, "last_keys_un": strides[0] * 28 if sep else 0,
+                         "n_last": 4, "map_points": strides[1] * 56, "n_map": 4, "boxes": 64 * 32, "n_boxes": 4, "ref_box": 256,
+                         "ref_desc": strides[2] * 32, "ref_xy": strides[2] * 8, "ref_off": 260, "fmat": 36}
+            off = 0
+            for name in pysdyn.TRACK_ARRAYS:
+                assert lay[name] == off and off % 256 == 0, (name, lay[name], off)
+                off += (per_frame[name] * n + 255) // 256 * 256
+            assert total == off
+    import pytest
+    with pytest.raises(pysdyn.SdynError):
+        pysdyn.track_input_layout(0, (1, 1, 1))

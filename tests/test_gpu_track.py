@@ -56,13 +56,28 @@ def test_track_batch_matches_oracle(cfg, B):
     # host-buffer forms of the same step (sdyn_track_batch and its async + wait split) give identical results
     hptrs = {k: (v.ctypes.data, int(np.prod(v.shape[1:])) * v.dtype.itemsize) for k, v in arrays.items()}
     hin = pysdyn.track_inputs(hptrs, 0, (last_stride, map_stride, ref_stride), params)
-    for fn in ("sync", "async"):
+    # ... and so does the single-copy form: every array inside one block at sdyn_track_input_layout's offsets
+    separate = not np.array_equal(arrays["last_keys"], arrays["last_keys_un"])
+    layout, total = pysdyn.track_input_layout(B, (last_stride, map_stride, ref_stride), separate)
+    block = np.full(total, 0xA5, np.uint8)
+    pptrs = {}
+    for k, v in arrays.items():
+        rows = v.view(np.uint8).reshape(v.shape[0], -1)[:B]
+        if separate or k != "last_keys_un":
+            block[layout[k]:layout[k] + rows.size] = rows.reshape(-1)
+        pptrs[k] = (block.ctypes.data + layout[k], rows.shape[1])
+    if not separate:
+        pptrs["last_keys_un"] = pptrs["last_keys"]
+    pin = pysdyn.track_inputs(pptrs, 0, (last_stride, map_stride, ref_stride), params)
+    for fn in ("sync", "async", "packed"):
         outs = (np.zeros((B, gpu.cap), pysdyn.KP_DTYPE), np.zeros((B, gpu.cap, 32), np.uint8), np.zeros(B, np.int32),
                 np.zeros((B, gpu.cap), np.int32), np.zeros((B, gpu.cap), np.uint8), np.zeros((B, gpu.cap), np.uint8),
                 np.zeros((B, 4), np.int32))
         imgs = np.ascontiguousarray(frames[1:])
         if fn == "sync":
             pysdyn.track_batch_host(gpu, imgs, hin, outs)
+        elif fn == "packed":
+            pysdyn.track_batch_host(gpu, imgs, pin, outs)
         else:
             pysdyn.track_batch_host_async(gpu, imgs, hin, outs)
             pysdyn.track_wait(gpu)
