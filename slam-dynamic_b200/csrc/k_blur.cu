@@ -15,12 +15,13 @@
  *               bits 16-23 (max 65280*256 + 32768 < 2^24), extracted with PRMT.
  */
 #include "sdyn_internal.h"
+#include "tma.h"
 
 namespace sdyn {
 
 constexpr int BW = kBlurTileW, BH = kBlurTileH;
-constexpr int PXB = BW + 32;                 /* staged bytes per row: columns x0-16 .. x0+BW+15, 16-byte aligned */
-constexpr int PR = BH + 6;                   /* staged rows y0-3 .. y0+BH+2 */
+constexpr int PXB = kBlurStageW;             /* staged bytes per row: columns x0-16 .. x0+BW+15, 16-byte aligned */
+constexpr int PR = kBlurStageH;              /* staged rows y0-3 .. y0+BH+2 */
 static_assert(BW % 16 == 0 && BH % 4 == 0 && PR % 2 == 0, "tile shape");
 
 /* taps k0..k6 = 18 34 48 56 48 34 18 laid over three aligned words (bytes x-4..x-1 | x..x+3 | x+4..x+7) for the
@@ -36,23 +37,25 @@ __device__ __forceinline__ void hpass4(uint32_t w0, uint32_t w1, uint32_t w2, ui
 }
 
 __global__ void __launch_bounds__(256)
-k_blur(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const uint8_t* __restrict__ pyr,
+k_blur(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const __grid_constant__ LevelMaps maps,
        uint8_t* __restrict__ blur)
 {
-    __shared__ __align__(16) uint8_t px[PR * PXB];
+    __shared__ __align__(128) uint8_t px[PR * PXB];
     __shared__ __align__(16) uint32_t hz2[(PR / 2) * BW];     /* [row pair][column]: row 2p in the low half, 2p+1 in the high half */
+    __shared__ __align__(8) uint64_t bar;
     const TileRef t = tiles[blockIdx.x];
     const LevelGeom& L = g.L[t.level];
     const int x0 = t.tx * BW, y0 = t.ty * BH, tid = threadIdx.x;
-    const uint8_t* img = pyr + (size_t)blockIdx.y * g.frameBytes + L.off;
-    /* rows y0-3 .. y0+BH+2 (clamped to the bordered extent), 16-byte vector loads; the frame supplies the halo */
-    for (int i = tid; i < PR * (PXB / 16); i += 256) {
-        const int yy = i / (PXB / 16), q = i - yy * (PXB / 16);
-        const int gy = min(y0 - 3 + yy, L.h + kEdge - 1);
-        reinterpret_cast<uint4*>(px + yy * PXB)[q] =
-            __ldg(reinterpret_cast<const uint4*>(img + (long long)gy * L.pitch + x0 - 16) + q);
+    /* rows y0-3 .. y0+BH+2, columns x0-16 .. x0+BW+15 of the bordered level: ONE TMA box load (the x origin is a multiple
+     * of 16 bytes because tiles sit on a 128-column grid and interior column 0 is 32-byte aligned); the level's frame
+     * supplies the halo, parts of the box beyond the bordered extent are zero-filled and only feed unwritten outputs */
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, PR * PXB);
+        tma_load_3d(px, &maps.m[t.level], kLeftPad + x0 - 16, kEdge + y0 - 3, blockIdx.y, &bar);
     }
     __syncthreads();
+    mbar_wait(&bar, 0);
     /* horizontal pass: 2 rows x 4 adjacent outputs per thread, one 16-byte store */
     for (int i = tid; i < (PR / 2) * (BW / 4); i += 256) {
         const int rp = i / (BW / 4), xq = i - rp * (BW / 4);
@@ -102,11 +105,11 @@ k_blur(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
 }
 #undef CW4
 
-cudaError_t launch_blur(const Geom& g, const TileRef* tiles, int ntiles, const uint8_t* dPyr,
+cudaError_t launch_blur(const Geom& g, const TileRef* tiles, int ntiles, const void* tmaMaps,
                         uint8_t* dBlur, int nframes, cudaStream_t st)
 {
     dim3 grid(ntiles, nframes);
-    k_blur<<<grid, 256, 0, st>>>(g, tiles, dPyr, dBlur);
+    k_blur<<<grid, 256, 0, st>>>(g, tiles, static_cast<const TmaMaps*>(tmaMaps)->blurTile, dBlur);
     return cudaGetLastError();
 }
 

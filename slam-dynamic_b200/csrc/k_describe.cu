@@ -11,6 +11,7 @@
  * reproduces the reference's level-major concatenation.
  */
 #include "sdyn_internal.h"
+#include "tma.h"
 
 namespace sdyn {
 
@@ -42,20 +43,20 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 
 constexpr int DW = 8;    /* warps per CTA */
 constexpr int KW = 4;    /* keypoints per warp */
-constexpr int SP = 80;   /* shared patch pitch: 64 staged bytes, 16-byte aligned rows, rows 20 banks apart */
-constexpr int PR_ = 37;  /* patch rows / columns: rotated pattern coordinates reach +-18 (|p| <= 18.39) */
+constexpr int SP = kPatchPitch;   /* shared patch pitch = box width: 64 needed bytes, rows 20 banks apart */
+constexpr int PR_ = kDescRows;    /* patch rows / columns: rotated pattern coordinates reach +-18 (|p| <= 18.39) */
+constexpr int PBUF = (PR_ * SP + 127) / 128 * 128;   /* per-warp patch buffer: 128-byte aligned (TMA destination) */
+static_assert(SP % 16 == 0, "TMA box rows are 16-byte multiples");
 
-/* Stage rows [y0, y0+nrows) x 64 bytes starting at the 16-byte aligned column ax of one level into a warp's patch
- * buffer with 16-byte loads.  ax >= -16 and ax+63 <= w+28, i.e. inside the padded row or the next row's left
- * padding; the patch never touches the last bordered row, so every load is inside the frame's block. */
-__device__ __forceinline__ void stage_patch(const uint8_t* __restrict__ lvl, int pitch, int y0, int ax, int nrows,
-                                            uint8_t* __restrict__ buf, int lane)
+/* A patch = rows [y0, y0+nrows) x SP bytes starting at the 16-byte aligned interior column ax of one level, brought into
+ * a warp's buffer by ONE TMA box load issued by lane 0 (tma.h; ax is a multiple of 16 as the TMA unit requires).
+ * ax >= -16 and the patch never leaves the bordered rows; bytes past the padded row are zero-filled and never sampled. */
+__device__ __forceinline__ void patch_load(const CUtensorMap* map, int ax, int y0, int f, uint8_t* buf, uint64_t* bar,
+                                           int bytes, int lane)
 {
-    const uint8_t* base = lvl + (long long)y0 * pitch + ax;
-    for (int i = lane; i < nrows * 4; i += 32) {
-        const int row = i >> 2, q = i & 3;
-        *reinterpret_cast<uint4*>(buf + row * SP + 16 * q) =
-            __ldg(reinterpret_cast<const uint4*>(base + (long long)row * pitch) + q);
+    if (lane == 0) {
+        mbar_expect_tx(bar, bytes);
+        tma_load_3d(buf, map, kLeftPad + ax, kEdge + y0, f, bar);
     }
 }
 
@@ -66,13 +67,15 @@ __device__ __forceinline__ void stage_patch(const uint8_t* __restrict__ lvl, int
  *      warp instead of one per keypoint;
  *   C. per keypoint: the blurred 37-row patch is staged and lane i builds descriptor byte i from 16 LDS gathers. */
 __global__ void __launch_bounds__(DW * 32)
-k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
+k_orient_describe(const __grid_constant__ Geom g, const __grid_constant__ LevelMaps orientMaps,
+                  const __grid_constant__ LevelMaps descMaps,
                   const LevelKp* __restrict__ levelKp, const int32_t* __restrict__ levelCount,
                   sdyn_keypoint* __restrict__ kpOut, uint8_t* __restrict__ descOut, int32_t* __restrict__ countOut,
                   int maxKp)
 {
     __shared__ __align__(16) float4 sPat[256];                 /* pair j of descriptor byte i at [j*32 + i] */
-    __shared__ __align__(16) uint8_t sPatch[DW][PR_ * SP];
+    __shared__ __align__(128) uint8_t sPatch[DW][PBUF];
+    __shared__ __align__(8) uint64_t sBar[DW];
     const int f = blockIdx.z, level = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     {
@@ -96,10 +99,11 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     nk = min(nk, maxKp - (before + k0));                         /* output capacity */
     if (nk <= 0) return;
 
-    const int pitch = L.pitch;
-    const uint8_t* img = pyr + (size_t)f * g.frameBytes + L.off;
-    const uint8_t* bl = blur + (size_t)f * g.frameBytes + L.off;
     uint8_t* buf = sPatch[warp];
+    uint64_t* bar = &sBar[warp];              /* one barrier per warp; load j completes its phase j & 1 */
+    uint32_t phase = 0;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
     LevelKp kp = {0, 0, 0};
     if (lane < nk) kp = levelKp[(size_t)f * g.kpPerFrame + L.kpOff + k0 + lane];
 
@@ -108,9 +112,9 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     for (int i = 0; i < nk; ++i) {
         const int kx = __shfl_sync(0xffffffffu, (int)kp.x, i), ky = __shfl_sync(0xffffffffu, (int)kp.y, i);
         const int ax = (kx - 18) & ~15, dx = kx - ax;
-        __syncwarp();
-        stage_patch(img, pitch, ky - 15, ax, 31, buf, lane);
-        __syncwarp();
+        __syncwarp();                         /* every lane is done with the previous patch */
+        patch_load(&orientMaps.m[level], ax, ky - 15, f, buf, bar, kOrientRows * SP, lane);
+        mbar_wait(bar, phase); phase ^= 1;
         const int u = lane - 15;
         int m10 = 0, m01 = 0;
         if (lane < 31) {
@@ -152,8 +156,8 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
         const float a = __shfl_sync(0xffffffffu, ca, i), b = __shfl_sync(0xffffffffu, sb, i);
         const int ax = (kx - 18) & ~15, dx = kx - ax;
         __syncwarp();
-        stage_patch(bl, pitch, ky - 18, ax, PR_, buf, lane);
-        __syncwarp();
+        patch_load(&descMaps.m[level], ax, ky - 18, f, buf, bar, PR_ * SP, lane);
+        mbar_wait(bar, phase); phase ^= 1;
         const uint8_t* c = buf + 18 * SP + dx;
         unsigned val = 0;
 #pragma unroll
@@ -182,13 +186,14 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     }
 }
 
-cudaError_t launch_orient_describe(const Geom& g, const uint8_t* dPyr, const uint8_t* dBlur,
+cudaError_t launch_orient_describe(const Geom& g, const void* tmaMaps,
                                    const LevelKp* dLevelKp, const int32_t* dLevelCount,
                                    sdyn_keypoint* dKp, uint8_t* dDesc, int32_t* dCount, int maxKp,
                                    int nframes, cudaStream_t st)
 {
     dim3 grid((g.maxNodeCap + DW * KW - 1) / (DW * KW), g.nlevels, nframes);
-    k_orient_describe<<<grid, DW * 32, 0, st>>>(g, dPyr, dBlur, dLevelKp, dLevelCount, dKp, dDesc, dCount, maxKp);
+    k_orient_describe<<<grid, DW * 32, 0, st>>>(g, static_cast<const TmaMaps*>(tmaMaps)->orientPatch,
+                                               static_cast<const TmaMaps*>(tmaMaps)->descPatch, dLevelKp, dLevelCount, dKp, dDesc, dCount, maxKp);
     return cudaGetLastError();
 }
 

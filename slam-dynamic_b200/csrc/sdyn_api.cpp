@@ -1,6 +1,7 @@
 /* C-ABI of libsdyn: context management and the ORBextractor::operator() replacement.
  * See include/sdyn.h for the contract; kernels live in k_*.cu. */
 #include "sdyn_internal.h"
+#include "tma.h"
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -67,6 +68,14 @@ int ensure_geometry(sdyn_ctx* c, int W, int H)
     CU(c, cudaMemcpy(c->dTables, tables.data(), tables.size(), cudaMemcpyHostToDevice));
     CU(c, cudaMemcpy(c->dFastTiles, ft.data(), ft.size() * sizeof(TileRef), cudaMemcpyHostToDevice));
     CU(c, cudaMemcpy(c->dBlurTiles, bt.data(), bt.size() * sizeof(TileRef), cudaMemcpyHostToDevice));
+    {
+        const char* why = "";
+        TmaMaps* tm = static_cast<TmaMaps*>(c->tma);
+        cudaError_t e = encode_level_maps(g, c->dPyr, c->maxBatch, kBlurStageW, kBlurStageH, &tm->blurTile, &why);
+        if (e == cudaSuccess) e = encode_level_maps(g, c->dPyr, c->maxBatch, kPatchPitch, kOrientRows, &tm->orientPatch, &why);
+        if (e == cudaSuccess) e = encode_level_maps(g, c->dBlur, c->maxBatch, kPatchPitch, kDescRows, &tm->descPatch, &why);
+        if (e != cudaSuccess) return fail(c, SDYN_ERR_CUDA, std::string("tensor maps: ") + why + ": " + cudaGetErrorString(e));
+    }
     c->geom = g; c->nFastTiles = (int)ft.size(); c->nBlurTiles = (int)bt.size();
     c->geomValid = true;
     return SDYN_OK;
@@ -186,7 +195,7 @@ int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frame
     }
     {
         StageTimer t(c, bs, SDYN_STAGE_BLUR);
-        CU(c, launch_blur(g, c->dBlurTiles, c->nBlurTiles, c->dPyr, c->dBlur, nframes, bs));
+        CU(c, launch_blur(g, c->dBlurTiles, c->nBlurTiles, c->tma, c->dBlur, nframes, bs));
     }
     if (fork) CU(c, cudaEventRecord(c->evJoin, c->aux));
     {
@@ -202,7 +211,7 @@ int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frame
     if (fork) CU(c, cudaStreamWaitEvent(st, c->evJoin, 0));
     {
         StageTimer t(c, st, SDYN_STAGE_DESCRIBE);
-        CU(c, launch_orient_describe(g, c->dPyr, c->dBlur, c->dLevelKp, c->dLevelCount, c->dKp, c->dDesc, c->dCount,
+        CU(c, launch_orient_describe(g, c->tma, c->dLevelKp, c->dLevelCount, c->dKp, c->dDesc, c->dCount,
                                      c->maxKp, nframes, st));
     }
     c->launches += 1 + (g.nlevels - 1) + 4;      /* kernels only: level 0, resizes, FAST, octree, blur, describe (memsets are not counted) */
@@ -222,7 +231,7 @@ void free_all(sdyn_ctx* c)
     sdyn::free_track_state(c);
     sdyn::free_stereo_state(c);
     sdyn::free_bow_state(c);
-    cudaFree(c->dFastTiles); cudaFree(c->dBlurTiles); cudaFree(c->dTables); cudaFree(c->dIn); cudaFree(c->dPyr);
+    cudaFree(c->dFastTiles); cudaFree(c->dBlurTiles); cudaFree(c->dTables); cudaFree(c->dIn); cudaFree(c->dPyr); delete static_cast<TmaMaps*>(c->tma); c->tma = nullptr;
     cudaFree(c->dBlur); cudaFree(c->dCellFlag); cudaFree(c->dCand); cudaFree(c->dCandNode); cudaFree(c->dCandCount); cudaFree(c->dSelCount);
     cudaFree(c->dLevelKp); cudaFree(c->dLevelCount); cudaFree(c->dCount); cudaFree(c->dStatus); cudaFree(c->dKp);
     cudaFree(c->dDesc); cudaFree(c->dArena); cudaFree(c->dKpUn);
@@ -288,6 +297,8 @@ int sdyn_create(const sdyn_orb_params* params, int maxW, int maxH, int maxBatch,
     A(dalloc(&c->dTables, c->tablesCap));
     A(dalloc(&c->dIn, c->inFrameCap * B));
     A(dalloc(&c->dPyr, c->pyrFrameCap * B)); A(dalloc(&c->dBlur, c->pyrFrameCap * B));
+    c->tma = new (std::nothrow) TmaMaps();
+    if (!c->tma) A(cudaErrorMemoryAllocation);
     A(dalloc(&c->dCellFlag, (size_t)c->cellCap * B));
     A(dalloc(&c->dCand, (size_t)c->candCap * B)); A(dalloc(&c->dCandNode, (size_t)c->candCap * B));
     A(dalloc(&c->dCandCount, SDYN_MAX_LEVELS * B)); A(dalloc(&c->dSelCount, SDYN_MAX_LEVELS * B));

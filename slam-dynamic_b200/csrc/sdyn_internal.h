@@ -94,6 +94,7 @@ struct sdyn_ctx {
     /* device buffers sized at create() for (maxW, maxH, maxBatch) */
     uint8_t* dIn;  size_t inFrameCap;          /* staged input frames (host entry points) */
     uint8_t* dPyr; uint8_t* dBlur; size_t pyrFrameCap;
+    void* tma;                                 /* host TmaMaps (tma.h): per-level tensor maps of the blur tiles and descriptor patches */
     uint8_t* dCellFlag; int cellCap;           /* per frame */
     uint32_t* dCand; int32_t* dCandNode; int candCap;   /* per frame */
     int32_t* dCandCount;                       /* [maxBatch][SDYN_MAX_LEVELS] maxima emitted by FAST */
@@ -159,9 +160,9 @@ cudaError_t launch_fast(const Geom& g, const TileRef* tiles, int ntiles, const u
 cudaError_t launch_octree(const Geom& g, int iniTh, int minTh, const uint8_t* dCellFlag, uint32_t* dCand,
                           const int32_t* dCandCount, int32_t* dCandNode, int32_t* dSelCount, LevelKp* dLevelKp,
                           int32_t* dLevelCount, int32_t* dStatus, int nframes, cudaStream_t st);
-cudaError_t launch_blur(const Geom& g, const TileRef* tiles, int ntiles, const uint8_t* dPyr,
+cudaError_t launch_blur(const Geom& g, const TileRef* tiles, int ntiles, const void* tmaMaps,
                         uint8_t* dBlur, int nframes, cudaStream_t st);
-cudaError_t launch_orient_describe(const Geom& g, const uint8_t* dPyr, const uint8_t* dBlur,
+cudaError_t launch_orient_describe(const Geom& g, const void* tmaMaps,
                                    const LevelKp* dLevelKp, const int32_t* dLevelCount,
                                    sdyn_keypoint* dKp, uint8_t* dDesc, int32_t* dCount, int maxKp,
                                    int nframes, cudaStream_t st);
@@ -172,5 +173,8 @@ cudaError_t launch_undistort_xy(const CameraModel& cam, const float* dSrc, int n
 
 constexpr int kFastTileW = 126, kFastTileH = 30;   /* +2 halo = 128 x 32 score positions: 4 x 4 per thread, no idle lanes */
 constexpr int kBlurTileW = 128, kBlurTileH = 32;
+constexpr int kBlurStageW = kBlurTileW + 32, kBlurStageH = kBlurTileH + 6;   /* staged box: columns x0-16 .. x0+W+15, rows y0-3 .. y0+H+2 */
+constexpr int kPatchPitch = 80;            /* descriptor-stage patch box: 64 needed bytes, rows 20 banks apart */
+constexpr int kOrientRows = 31, kDescRows = 37;
 
 }  // namespace sdyn
