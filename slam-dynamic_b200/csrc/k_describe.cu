@@ -41,6 +41,8 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
+/* umax[v], v = 0..15, one nibble each: 15 15 15 15 14 14 14 13 13 12 11 10 9 8 6 3 */
+constexpr unsigned long long kDiscHalfWidth = 0x3689ABCDDEEEFFFFull;
 constexpr int DW = 8;    /* warps per CTA */
 constexpr int KW = 4;    /* keypoints per warp */
 constexpr int SP = kPatchPitch;   /* shared patch pitch = box width: 64 needed bytes, rows 20 banks apart */
@@ -109,27 +111,63 @@ k_orient_describe(const __grid_constant__ Geom g, const __grid_constant__ LevelM
 
     /* ---- A. intensity centroid ---------------------------------------------------------------------------- */
     int my10 = 0, my01 = 0;
+    /* byte masks of this lane's disc row over the 32-byte window u = -15 .. 16: |u| <= umax[|v|] (umax[] of
+     * ORBextractor.cc:454-469 for HALF_PATCH_SIZE = 15; geometry.cpp recomputes it and tests/test_abi.py checks the two
+     * agree).  Lane 31 owns no row. */
+    uint32_t discMask[8];
+    {
+        const int av = abs(lane - 15);
+        const int hw = lane < 31 ? (int)((kDiscHalfWidth >> (4 * av)) & 15) : -1;
+        const uint32_t bits = hw < 0 ? 0u : ((2u << (2 * hw)) - 1u) << (15 - hw);      /* bit b = pixel u = b - 15 */
+#pragma unroll
+        for (int k = 0; k < 8; ++k) discMask[k] = ((((bits >> (4 * k)) & 15u) * 0x00204081u) & 0x01010101u) * 0xffu;
+    }
     for (int i = 0; i < nk; ++i) {
         const int kx = __shfl_sync(0xffffffffu, (int)kp.x, i), ky = __shfl_sync(0xffffffffu, (int)kp.y, i);
         const int ax = (kx - 18) & ~15, dx = kx - ax;
         __syncwarp();                         /* every lane is done with the previous patch */
         patch_load(&orientMaps.m[level], ax, ky - 15, f, buf, bar, kOrientRows * SP, lane);
         mbar_wait(bar, phase); phase ^= 1;
-        const int u = lane - 15;
+        /* lane r owns disc row v = r - 15: three aligned 16-byte loads cover its 31 pixels (rows are 20 banks apart, so a
+         * quarter-warp's loads are conflict-free), a funnel shift brings pixel u = -15 to byte 0, and the two moments
+         * are byte dot products: m10 += sum u * I (IDP.4A against constant signed weights), m01 += v * sum I */
         int m10 = 0, m01 = 0;
-        if (lane < 31) {
-            const int au = abs(u);
-            /* umax[] of ORBextractor.cc:454-469 for HALF_PATCH_SIZE = 15 (geometry.cpp recomputes it; tests/test_abi.py
-             * checks the two agree) */
-            constexpr int HW[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-            const uint8_t* c = buf + 15 * SP + dx + u;
-            int rowsum = 0;
+        {
+            const int o = dx - 15;                                 /* byte of u = -15 in the staged row: 3 .. 18 */
+            const uint4* rowp = reinterpret_cast<const uint4*>(buf + min(lane, kOrientRows - 1) * SP + (o & ~15));
+            const uint4 q0 = rowp[0], q1 = rowp[1], q2 = rowp[2];
+            const uint32_t W[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            const int sh = 8 * (o & 3);
+            uint32_t A[8];
+            switch ((o & 15) >> 2) {                               /* warp-uniform */
+            case 0:
 #pragma unroll
-            for (int v = -15; v <= 15; ++v) {
-                const int val = au <= HW[v < 0 ? -v : v] ? (int)c[v * SP] : 0;
-                rowsum += val; m01 += v * val;
+                for (int k = 0; k < 8; ++k) A[k] = __funnelshift_r(W[k], W[k + 1], sh);
+                break;
+            case 1:
+#pragma unroll
+                for (int k = 0; k < 8; ++k) A[k] = __funnelshift_r(W[k + 1], W[k + 2], sh);
+                break;
+            case 2:
+#pragma unroll
+                for (int k = 0; k < 8; ++k) A[k] = __funnelshift_r(W[k + 2], W[k + 3], sh);
+                break;
+            default:
+#pragma unroll
+                for (int k = 0; k < 8; ++k) A[k] = __funnelshift_r(W[k + 3], k + 4 < 12 ? W[k + 4] : 0u, sh);
+                break;
             }
-            m10 = u * rowsum;
+            uint32_t rowsum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t a = A[k] & discMask[k];
+                /* weights u = 4k-15 .. 4k-12 as signed bytes */
+                const uint32_t wt = (uint32_t)((4 * k - 15) & 0xff) | ((uint32_t)((4 * k - 14) & 0xff) << 8) |
+                                        ((uint32_t)((4 * k - 13) & 0xff) << 16) | ((uint32_t)((4 * k - 12) & 0xff) << 24);
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(a), "r"(wt));
+                rowsum = __dp4a(a, 0x01010101u, rowsum);
+            }
+            m01 = (lane - 15) * (int)rowsum;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
