@@ -132,7 +132,7 @@ int compute_geometry(const sdyn_orb_params& p, const sdyn_scale_info& s, int W, 
         L.patchSize = (float)(int)(31 * s.scale[l]);
 
         /* bilinear tables, indexed by bordered destination coordinate */
-        L.xtab = L.ytab = -1;
+        L.xtab = L.ytab = L.xTile = L.yTile = -1;
         if (l > 0) {
             const LevelGeom& P = g.L[l - 1];
             auto build = [&](int dn, int sn, bool clampCoef) {
@@ -178,6 +178,28 @@ int compute_geometry(const sdyn_orb_params& p, const sdyn_scale_info& s, int W, 
             /* tiles start at padded column multiples of 128, i.e. bordered column -(kLeftPad-kEdge) + 128k */
             L.rsPitch = (int)align_up((size_t)span(L.xtab, L.w + 2 * kEdge, 128, kLeftPad - kEdge) + 16, 16);
             L.rsRows = span(L.ytab, L.h + 2 * kEdge, 32, 0) + 16;
+            /* per tile column / row: first source column (16-byte aligned) / first source row and row count — the
+             * origin of the TMA box k_resize stages */
+            auto origins = [&](int tabOff, int n, int tile, int lead, int align, bool withCount) {
+                const ResizeTap* t = reinterpret_cast<const ResizeTap*>(tables.data() + tabOff);
+                std::vector<int16_t> o;
+                for (int b0 = -lead; b0 < n; b0 += tile) {
+                    int lo = 1 << 30, hi = -1;
+                    for (int b = b0; b < b0 + tile; ++b) {
+                        const ResizeTap& r = t[std::min(std::max(b, 0), n - 1)];
+                        lo = std::min(lo, (int)std::min(r.s0, r.s1)); hi = std::max(hi, (int)std::max(r.s0, r.s1));
+                    }
+                    lo &= ~(align - 1);
+                    o.push_back((int16_t)lo);
+                    if (withCount) o.push_back((int16_t)(hi - lo + 1));
+                }
+                const size_t at = align_up(tables.size(), 16);
+                tables.resize(at + o.size() * sizeof(int16_t));
+                std::memcpy(tables.data() + at, o.data(), o.size() * sizeof(int16_t));
+                return (int)at;
+            };
+            L.xTile = origins(L.xtab, L.w + 2 * kEdge, 128, kLeftPad - kEdge, 16, false);
+            L.yTile = origins(L.ytab, L.h + 2 * kEdge, 32, 0, 1, true);
         }
     }
     g.frameBytes = (long long)align_up(off, 256);

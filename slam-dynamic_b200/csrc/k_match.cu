@@ -701,10 +701,13 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
     const sdyn_last_point* lps = reinterpret_cast<const sdyn_last_point*>(J.queries);
     const sdyn_mappoint_query* mps = reinterpret_cast<const sdyn_mappoint_query*>(J.queries);
     const sdyn_proj_point* pps = reinterpret_cast<const sdyn_proj_point*>(J.queries);
-    const bool frameLike = J.mode == MM_FRAME || J.mode == MM_POSE;      /* best-only acceptance + rotation histogram */
+    /* job fields the loops test: read once (every barrier is a memory fence, so `J.x` inside a loop is a fresh global load) */
+    const int mode = J.mode, distTh = J.distTh, checkOri = J.checkOri, assignBase = J.assignBase;
+    const float nnratio = J.nnratio;
+    const bool frameLike = mode == MM_FRAME || mode == MM_POSE;      /* best-only acceptance + rotation histogram */
     /* does query q lock the keypoint it takes (the MapPoint has observations; every claim of the pose searches does) */
-    auto locks = [&](int q) -> bool { return J.mode == MM_FRAME ? lps[q].obs_positive : (J.mode == MM_POSE ? true : mps[q].obs_positive); };
-    auto query_angle = [&](int q) -> float { return J.mode == MM_POSE ? pps[q].angle : J.qKeysUn[q].angle; };
+    auto locks = [&](int q) -> bool { return mode == MM_FRAME ? lps[q].obs_positive : (mode == MM_POSE ? true : mps[q].obs_positive); };
+    auto query_angle = [&](int q) -> float { return mode == MM_POSE ? pps[q].angle : J.qKeysUn[q].angle; };
 
     /* Everything a sweep reads is brought into shared memory once: the initial lock state of the keypoints, the
      * "does this query lock" flags, and the candidate lists compacted back to back (a prefix sum over the list lengths
@@ -721,7 +724,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
         /* exclusive scan of the list lengths: a contiguous chunk of queries per thread */
         const int per = (nq + RF - 1) / RF, q0 = min(tid * per, nq), q1 = min(q0 + per, nq);
         int sum = 0;
-        for (int q = q0; q < q1; ++q) sum += J.qspan[q].y;
+        for (int q = q0; q < q1; ++q) { const int len = J.qspan[q].y; sOff[q] = len; sum += len; }
         int incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
@@ -737,7 +740,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
         }
         __syncthreads();
         int run = warpTot[tid >> 5] + incl - sum;
-        for (int q = q0; q < q1; ++q) { sOff[q] = run; run += J.qspan[q].y; }
+        for (int q = q0; q < q1; ++q) { const int len = sOff[q]; sOff[q] = run; run += len; }
         if (q1 == nq && q0 < nq) sOff[nq] = run;
         if (nq == 0 && tid == 0) sOff[0] = 0;
     }
@@ -747,6 +750,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
         for (int q = tid; q < nq; q += RF) {
             const int2 span = J.qspan[q];
             const int o = sOff[q];
+#pragma unroll 4
             for (int p = 0; p < span.y; ++p) sPool[o + p] = __ldg(J.pool + span.x + p);
         }
     __syncthreads();
@@ -767,27 +771,24 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
             const uint32_t* P;
             if (staged) { span.x = sOff[q]; span.y = sOff[q + 1] - span.x; P = sPool; }
             else { span = J.qspan[q]; P = J.pool; }
+            /* best and second-best unlocked candidate as keys distance << 20 | list position (first of equals wins);
+             * the lists are short (a few entries), so a plain loop beats an unrolled, predicated one */
             uint32_t a = NONE, b = NONE;
-            for (int p0 = 0; p0 < span.y; p0 += 8) {
-                uint32_t rec[8];                       /* 8 independent loads in flight per thread */
-#pragma unroll
-                for (int k = 0; k < 8; ++k) rec[k] = p0 + k < span.y ? P[span.x + p0 + k] : NONE;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (rec[k] == NONE || lockT[rec_idx(rec[k])] < q) continue;
-                    const uint32_t key = ((uint32_t)rec_dist(rec[k]) << 20) | (uint32_t)(p0 + k);
-                    if (key < a) { b = a; a = key; } else if (key < b) b = key;
-                }
+            for (int p = 0; p < span.y; ++p) {
+                const uint32_t rec = P[span.x + p];
+                if (rec == NONE || lockT[rec_idx(rec)] < q) continue;
+                const uint32_t key = ((uint32_t)rec_dist(rec) << 20) | (uint32_t)p;
+                if (key < a) { b = a; a = key; } else if (key < b) b = key;
             }
             int res = -1;
             if (a != NONE) {
                 const uint32_t r1 = P[span.x + (a & 0xfffff)];
                 const int bestDist = (int)(a >> 20);
-                bool ok = bestDist <= J.distTh;
-                if (ok && J.mode == MM_MAP) {
+                bool ok = bestDist <= distTh;
+                if (ok && mode == MM_MAP) {
                     int bestDist2 = 256, bestLevel2 = -1;
                     if (b != NONE) { bestDist2 = (int)(b >> 20); bestLevel2 = rec_level(P[span.x + (b & 0xfffff)]); }
-                    ok = !(rec_level(r1) == bestLevel2 && (float)bestDist > __fmul_rn(J.nnratio, (float)bestDist2));
+                    ok = !(rec_level(r1) == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2));
                 }
                 if (ok) res = rec_idx(r1);
             }
@@ -807,7 +808,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
         if (a < 0) { if (frameLike) J.qBin[q] = -1; continue; }
         ++mine;
         atomicMax(&lockT[a], q);
-        if (frameLike && J.checkOri) {
+        if (frameLike && checkOri) {
             float rot = __fsub_rn(query_angle(q), J.keysUn[a].angle);
             if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
             int bin = (int)roundf(__fmul_rn(rot, 1.0f / SDYN_HISTO_LENGTH));
@@ -821,12 +822,12 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
     for (int k = tid; k < n; k += RF) {
         const int q = lockT[k];
         if (q >= 0) {
-            J.assign[k] = J.assignBase + q;
+            J.assign[k] = assignBase + q;
             J.locked[k] = qLock[q];
         }
     }
     /* point pairs of the fork's overload, in query order (before the cull, Appendix B-8) */
-    if (J.mode == MM_FRAME && J.pairs) {
+    if (mode == MM_FRAME && J.pairs) {
         int base = 0;
         for (int q0 = 0; q0 < nq; q0 += RF) {
             const int q = q0 + tid;
@@ -847,7 +848,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
         }
     }
     __syncthreads();
-    if (frameLike && J.checkOri) {
+    if (frameLike && checkOri) {
         if (tid == 0) {
             int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
             for (int i = 0; i < SDYN_HISTO_LENGTH; ++i) {

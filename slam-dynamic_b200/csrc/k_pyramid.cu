@@ -8,6 +8,7 @@
  * 32-bit store; the rows of a level are 32-byte aligned at interior column 0.
  */
 #include "sdyn_internal.h"
+#include "tma.h"
 
 namespace sdyn {
 
@@ -68,14 +69,13 @@ k_level0(const __grid_constant__ Geom g, const uint8_t* __restrict__ in, size_t 
 
 /* Bilinear resize of one level, tile-staged and separable.  A CTA produces RT_W x RT_H bytes of the bordered (and
  * left-padded) destination:
- *   1. the source rectangle its taps touch — found with a block min/max over the tile's column and row taps, so
- *      mirrored border tiles need no special case — is staged in shared memory with aligned 16-byte loads;
+ *   1. the source rectangle its taps touch (mirrored border tiles included: the rectangle comes from the taps, tabulated
+ *      per tile column / row on the host) is staged in shared memory by one TMA box load;
  *   2. horizontal pass ONCE per source row: H = (S[s0]*c0 + S[s1]*c1) >> 4 as uint16 (fits: 255*2048 >> 4);
  *   3. vertical pass per output: ((b0*H0) >> 16) + ((b1*H1) >> 16) + 2 >> 2, four bytes per 32-bit store.
  * Consecutive output rows share source rows (scale 1.2), so the horizontal work is 1.2 rows per output row
  * instead of 2. */
 constexpr int RT_W = 128, RT_H = 32;
-constexpr int kResizePitch = 192;     /* staging pitch of the common case (128-column tile, scale >= ~1.15) */
 
 /* a*c0 + b*c1 as two IMADs (FMA pipe): the compiler's own choice, PRMT + PRMT + IDP.2A, loads the busier ALU pipe */
 __device__ __forceinline__ uint32_t mad2(uint32_t a, uint32_t c0, uint32_t b, uint32_t c1)
@@ -89,11 +89,13 @@ __device__ __forceinline__ uint32_t mad2(uint32_t a, uint32_t c0, uint32_t b, ui
  * SPITCH == 0: run-time pitch L.rsPitch (scale factors whose source window is wider than 192 bytes). */
 template <int SPITCH>
 __global__ void __launch_bounds__(256)
-k_resize(const __grid_constant__ Geom g, int level, const uint8_t* __restrict__ tables, uint8_t* __restrict__ pyr)
+k_resize(const __grid_constant__ Geom g, int level, const uint8_t* __restrict__ tables, const __grid_constant__ LevelMaps maps,
+         uint8_t* __restrict__ pyr)
 {
-    extern __shared__ __align__(16) uint8_t smemR[];
+    extern __shared__ __align__(128) uint8_t smemR[];
     __shared__ ResizeTap sx[RT_W], sy[RT_H];
     __shared__ int sMinC, sMaxC, sMinR, sMaxR;
+    __shared__ __align__(8) uint64_t bar;
     const LevelGeom& L = g.L[level];
     const LevelGeom& P = g.L[level - 1];
     const int tid = threadIdx.x;
@@ -102,38 +104,56 @@ k_resize(const __grid_constant__ Geom g, int level, const uint8_t* __restrict__ 
     const int srcPitch = SPITCH > 0 ? SPITCH : L.rsPitch;
     uint8_t* src = smemR;                                             /* rsRows x rsPitch bytes */
     uint16_t* hz = reinterpret_cast<uint16_t*>(smemR + (size_t)L.rsRows * srcPitch);   /* rsRows x RT_W */
-    if (tid == 0) { sMinC = 1 << 30; sMaxC = -1; sMinR = 1 << 30; sMaxR = -1; }
-    __syncthreads();
-    if (tid < RT_W) {
-        const int bc = max(0, min(pc0 + tid - (kLeftPad - kEdge), bw - 1));   /* padding bytes replicate the frame edge */
-        const ResizeTap t = reinterpret_cast<const ResizeTap*>(tables + L.xtab)[bc];
-        sx[tid] = t;
-        int lo = min((int)t.s0, (int)t.s1), hi = max((int)t.s0, (int)t.s1);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-        if ((tid & 31) == 0) { atomicMin(&sMinC, lo); atomicMax(&sMaxC, hi); }
-    } else if (tid < RT_W + RT_H) {
-        const int r = min(row0 + tid - RT_W, bh - 1);
-        const ResizeTap t = reinterpret_cast<const ResizeTap*>(tables + L.ytab)[r];
-        sy[tid - RT_W] = t;
-        atomicMin(&sMinR, min((int)t.s0, (int)t.s1)); atomicMax(&sMaxR, max((int)t.s0, (int)t.s1));
-    }
-    __syncthreads();
     uint8_t* frame = pyr + (size_t)blockIdx.z * g.frameBytes;
-    const int ax0 = sMinC & ~15, minR = sMinR;
-    const int n16 = (sMaxC - ax0) / 16 + 1, nrows = sMaxR - minR + 1;
-    const uint8_t* sbase = frame + P.off + (long long)minR * P.pitch + ax0;
-    /* 16 lanes per source row (n16 <= 12 for a 128-column tile at scale 1.2): no runtime division in the copy loop */
-    {
-        const int q = tid & 15;
-        if (q < n16)
+    int ax0, minR, nrows;
+    if (SPITCH > 0) {
+        /* common case: the source rectangle is a fixed SPITCH x rsRows box whose origin the host tabulated per tile column
+         * and tile row (xTile / yTile) — ONE TMA load, issued before the taps are fetched so the two overlap */
+        ax0 = reinterpret_cast<const int16_t*>(tables + L.xTile)[blockIdx.x];
+        const int16_t* yt = reinterpret_cast<const int16_t*>(tables + L.yTile) + 2 * blockIdx.y;
+        minR = yt[0]; nrows = yt[1];
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, (uint32_t)(SPITCH * L.rsRows));
+            tma_load_3d(src, &maps.m[level], kLeftPad + ax0, kEdge + minR, blockIdx.z, &bar);
+        }
+        if (tid < RT_W) {
+            const int bc = max(0, min(pc0 + tid - (kLeftPad - kEdge), bw - 1));   /* padding bytes replicate the frame edge */
+            sx[tid] = reinterpret_cast<const ResizeTap*>(tables + L.xtab)[bc];
+        } else if (tid < RT_W + RT_H) {
+            sy[tid - RT_W] = reinterpret_cast<const ResizeTap*>(tables + L.ytab)[min(row0 + tid - RT_W, bh - 1)];
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+    } else {
+        /* wide source windows (other scale factors): rectangle from a block min/max over the tile's taps, staged with
+         * aligned 16-byte loads */
+        if (tid == 0) { sMinC = 1 << 30; sMaxC = -1; sMinR = 1 << 30; sMaxR = -1; }
+        __syncthreads();
+        if (tid < RT_W) {
+            const int bc = max(0, min(pc0 + tid - (kLeftPad - kEdge), bw - 1));
+            const ResizeTap t = reinterpret_cast<const ResizeTap*>(tables + L.xtab)[bc];
+            sx[tid] = t;
+            int lo = min((int)t.s0, (int)t.s1), hi = max((int)t.s0, (int)t.s1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+            if ((tid & 31) == 0) { atomicMin(&sMinC, lo); atomicMax(&sMaxC, hi); }
+        } else if (tid < RT_W + RT_H) {
+            const int r = min(row0 + tid - RT_W, bh - 1);
+            const ResizeTap t = reinterpret_cast<const ResizeTap*>(tables + L.ytab)[r];
+            sy[tid - RT_W] = t;
+            atomicMin(&sMinR, min((int)t.s0, (int)t.s1)); atomicMax(&sMaxR, max((int)t.s0, (int)t.s1));
+        }
+        __syncthreads();
+        ax0 = sMinC & ~15; minR = sMinR;
+        const int n16 = (sMaxC - ax0) / 16 + 1;
+        nrows = sMaxR - minR + 1;
+        const uint8_t* sbase = frame + P.off + (long long)minR * P.pitch + ax0;
+        for (int q = tid & 15; q < n16; q += 16)
             for (int r = tid >> 4; r < nrows; r += 16)
                 reinterpret_cast<uint4*>(src + r * srcPitch)[q] = __ldg(reinterpret_cast<const uint4*>(sbase + (long long)r * P.pitch) + q);
-        for (int q2 = 16 + q; q2 < n16; q2 += 16)                             /* wider windows (other scale factors) */
-            for (int r = tid >> 4; r < nrows; r += 16)
-                reinterpret_cast<uint4*>(src + r * srcPitch)[q2] = __ldg(reinterpret_cast<const uint4*>(sbase + (long long)r * P.pitch) + q2);
+        __syncthreads();
     }
-    __syncthreads();
     /* horizontal pass: thread = (column c of the tile, source rows r = tid/128, +2, ...), four rows per iteration so the
      * loop and address arithmetic are paid once per four values */
     {
@@ -198,7 +218,8 @@ cudaError_t launch_level0(const Geom& g, const uint8_t* dIn, size_t inFrameStrid
     return cudaGetLastError();
 }
 
-cudaError_t launch_resize(const Geom& g, int level, const uint8_t* dTables, uint8_t* dPyr, int nframes, cudaStream_t st)
+cudaError_t launch_resize(const Geom& g, int level, const uint8_t* dTables, const void* tmaMaps, uint8_t* dPyr, int nframes,
+                          cudaStream_t st)
 {
     const LevelGeom& L = g.L[level];
     const bool fixed = L.rsPitch <= kResizePitch;
@@ -210,9 +231,10 @@ cudaError_t launch_resize(const Geom& g, int level, const uint8_t* dTables, uint
                               : cudaFuncSetAttribute(k_resize<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
         if (e != cudaSuccess) return e;
     }
+    const LevelMaps& maps = static_cast<const TmaMaps*>(tmaMaps)->resizeSrc;
     dim3 grid((L.pitch + RT_W - 1) / RT_W, (L.h + 2 * kEdge + RT_H - 1) / RT_H, nframes);
-    if (fixed) k_resize<kResizePitch><<<grid, 256, smem, st>>>(g, level, dTables, dPyr);
-    else k_resize<0><<<grid, 256, smem, st>>>(g, level, dTables, dPyr);
+    if (fixed) k_resize<kResizePitch><<<grid, 256, smem, st>>>(g, level, dTables, maps, dPyr);
+    else k_resize<0><<<grid, 256, smem, st>>>(g, level, dTables, maps, dPyr);
     return cudaGetLastError();
 }
 

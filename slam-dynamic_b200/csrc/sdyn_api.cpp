@@ -74,6 +74,7 @@ int ensure_geometry(sdyn_ctx* c, int W, int H)
         cudaError_t e = encode_level_maps(g, c->dPyr, c->maxBatch, kBlurStageW, kBlurStageH, &tm->blurTile, &why);
         if (e == cudaSuccess) e = encode_level_maps(g, c->dPyr, c->maxBatch, kPatchPitch, kOrientRows, &tm->orientPatch, &why);
         if (e == cudaSuccess) e = encode_level_maps(g, c->dBlur, c->maxBatch, kPatchPitch, kDescRows, &tm->descPatch, &why);
+        if (e == cudaSuccess) e = encode_resize_maps(g, c->dPyr, c->maxBatch, &tm->resizeSrc, &why);
         if (e != cudaSuccess) return fail(c, SDYN_ERR_CUDA, std::string("tensor maps: ") + why + ": " + cudaGetErrorString(e));
     }
     c->geom = g; c->nFastTiles = (int)ft.size(); c->nBlurTiles = (int)bt.size();
@@ -182,7 +183,7 @@ int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frame
     }
     {
         StageTimer t(c, st, SDYN_STAGE_PYRAMID);
-        for (int l = 1; l < g.nlevels; ++l) CU(c, launch_resize(g, l, c->dTables, c->dPyr, nframes, st));
+        for (int l = 1; l < g.nlevels; ++l) CU(c, launch_resize(g, l, c->dTables, c->tma, c->dPyr, nframes, st));
     }
     /* The blur only needs the pyramid, FAST + octree only need the pyramid: two branches on two streams, joined in
      * front of the descriptor kernel (which reads the blurred levels and the selected keypoints). */

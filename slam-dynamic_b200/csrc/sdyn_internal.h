@@ -35,6 +35,9 @@ struct LevelGeom {
     int xtab, ytab;
     /* shared-memory staging of the resize kernel: worst-case source rectangle of a 128 x 32 output tile */
     int rsPitch, rsRows;
+    /* int16 tables (byte offsets into the blob): first staged source column of every tile column; (first staged source row,
+     * row count) of every tile row */
+    int xTile, yTile;
 };
 
 struct Geom {
@@ -152,7 +155,7 @@ int max_keypoints_per_frame(const sdyn_orb_params& p, const sdyn_scale_info& s, 
 /* kernels (each returns the cudaError_t of its launch) */
 cudaError_t launch_level0(const Geom& g, const uint8_t* dIn, size_t inFrameStride, int inRowStride,
                           uint8_t* dPyr, int nframes, cudaStream_t st);
-cudaError_t launch_resize(const Geom& g, int level, const uint8_t* dTables, uint8_t* dPyr,
+cudaError_t launch_resize(const Geom& g, int level, const uint8_t* dTables, const void* tmaMaps, uint8_t* dPyr,
                           int nframes, cudaStream_t st);
 cudaError_t launch_fast(const Geom& g, const TileRef* tiles, int ntiles, const uint8_t* dPyr,
                         int iniTh, int minTh, uint8_t* dCellFlag, uint32_t* dCand, int32_t* dCandCount,
@@ -176,5 +179,6 @@ constexpr int kBlurTileW = 128, kBlurTileH = 32;
 constexpr int kBlurStageW = kBlurTileW + 32, kBlurStageH = kBlurTileH + 6;   /* staged box: columns x0-16 .. x0+W+15, rows y0-3 .. y0+H+2 */
 constexpr int kPatchPitch = 80;            /* descriptor-stage patch box: 64 needed bytes, rows 20 banks apart */
 constexpr int kOrientRows = 31, kDescRows = 37;
+constexpr int kResizePitch = 192;          /* staging pitch of k_resize's common case (128-column tile, scale >= ~1.15) = its TMA box width */
 
 }  // namespace sdyn

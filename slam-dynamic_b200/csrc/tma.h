@@ -54,11 +54,14 @@ struct TmaMaps {
     LevelMaps blurTile;     /* over the pyramid: kBlurStageW x kBlurStageH (tile + 7x7 halo) */
     LevelMaps orientPatch;  /* over the pyramid: kPatchPitch x 31 rows (IC_Angle disc) */
     LevelMaps descPatch;    /* over the blurred pyramid: kPatchPitch x 37 rows (rotated pattern reach) */
+    LevelMaps resizeSrc;    /* m[l], l >= 1: over level l-1 of the pyramid, kResizePitch x rsRows(l) (source rectangle of a tile) */
 };
 
 /* host: encodes the maps of boxW x boxH x 1 byte boxes over a pyramid buffer of maxBatch frames */
 struct Geom;
 cudaError_t encode_level_maps(const Geom& g, const uint8_t* dBuffer, int maxBatch, int boxW, int boxH, LevelMaps* out,
                               const char** why);
+/* m[l] = boxes of kResizePitch x L[l].rsRows bytes over level l-1 (levels whose window is wider keep a zeroed map) */
+cudaError_t encode_resize_maps(const Geom& g, const uint8_t* dBuffer, int maxBatch, LevelMaps* out, const char** why);
 
 }  // namespace sdyn
