@@ -15,17 +15,20 @@
  * 9-arc at the low threshold rejects most pixels; it runs on whole words (4 columns x 4 rows per thread, bytes
  * widened to u16x2 lanes, two positions per VIMNMX.U16x2); (B) survivors are compacted into a dense list so the
  * full 16-tap score (VIMNMX3 sliding-window network) runs with all lanes busy; (C) the 3x3 suppression only touches
- * pixels with a non-zero score.  Tiles are staged with 16-byte aligned vector loads and shifted by 0-3 bytes so that
- * score column 0 is word aligned.
+ * pixels with a non-zero score.  The tile is staged by ONE TMA box load; the tile grid (sdyn_internal.h) keeps score
+ * column 0 word aligned in the staged rows.
  */
 #include "sdyn_internal.h"
+#include "tma.h"
 
 namespace sdyn {
 
 constexpr int TW = kFastTileW, TH = kFastTileH;
-constexpr int PH = TH + 8;                  /* pixel rows: tile + 1 (NMS halo) + 3 (ring) on each side */
-constexpr int PWB = ((TW + 8 + 15 + 15) / 16) * 16;   /* staged bytes per row: 16-byte aligned superset of TW+8 */
-constexpr int SW = TW + 2, SH = TH + 2;     /* scores: tile + NMS halo */
+constexpr int PH = kFastStageH;             /* pixel rows: tile + 1 (NMS halo) + 3 (ring) on each side */
+constexpr int PWB = kFastStageW;            /* staged bytes per row */
+constexpr int SW = 128, SH = TH + 2;        /* score positions a CTA computes: tile + NMS halo (+ 2 spare columns) */
+static_assert(TW + 2 <= SW && TW % 4 == 0 && (kFastLead & 3) == 3, "tile grid keeps score column 0 word aligned");
+static_assert(PWB % 16 == 0 && PWB >= 16 + SW + 4, "box covers the aligned lead-in, the positions and the last lane's right word");
 constexpr int FT = 256;                     /* threads */
 
 /* V(p) = max over the 16 contiguous 9-arcs of max(min d, min -d) - 1, d_k = I(p) - I(ring_k).
@@ -64,12 +67,13 @@ static_assert(SW % 32 == 0 && SH % (FT / 32) == 0, "score positions tile the CTA
 static_assert(ROWR == 4 && COLR == 4, "the compass test owns 4 columns x 4 rows per thread");
 static_assert(SW + 3 + 1 <= SWP && SWP % 4 == 0, "score row pitch");
 
-__global__ void __launch_bounds__(FT)
-k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const uint8_t* __restrict__ pyr,
+__global__ void __launch_bounds__(FT, 8)
+k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const __grid_constant__ LevelMaps maps,
        int iniTh, int lowTh, uint8_t* __restrict__ cellFlag, uint32_t* __restrict__ cand,
        int32_t* __restrict__ candCount)
 {
-    __shared__ __align__(16) uint8_t px[PH * PWB];
+    __shared__ __align__(128) uint8_t px[PH * PWB];
+    __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(16) uint8_t sc[SH * SWP];
     __shared__ uint16_t list[SH * SW];          /* survivors of the compass test */
     __shared__ uint16_t corners[TH * TW];       /* tile positions with V >= lowTh (input of the suppression) */
@@ -79,30 +83,22 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
     const TileRef t = tiles[blockIdx.x];
     const int f = blockIdx.y;
     const LevelGeom& L = g.L[t.level];
-    const int x0 = t.tx * TW, y0 = t.ty * TH;                 /* window-relative origin of the tile */
-    const uint8_t* img = pyr + (size_t)f * g.frameBytes + L.off;   /* interior pixel (0,0): 32-byte aligned */
+    const int x0 = t.tx * TW - kFastLead, y0 = t.ty * TH;     /* window-relative origin of the tile */
     const int tid = threadIdx.x, lane = tid & 31;
 
-    /* stage rows [gy0, gy0+PH) x bytes [ax0, ax0+PWB): ax0 is the 16-byte aligned column at or before the
-     * first needed pixel (window x0-4 = interior column 12+x0).  Rows are clamped to the bordered extent;
-     * columns past the row end read pad / next-row bytes that only feed masked-out positions. */
-    const int gx0 = kFastBorder + x0 - 4, gy0 = kFastBorder + y0 - 4;
-    const int ax0 = gx0 & ~15, shift = gx0 - ax0;
-    /* the centre of score column 0 sits at byte shift + 3 of a staged row; the rows are shifted right by rho bytes
-     * while they are staged so that it lands on the 4-byte boundary cbase: the compass test then reads whole words */
-    const int cbase = (shift + 3 + 3) & ~3, rho8 = 8 * (cbase - (shift + 3));
-    if (tid == 0) { nList = 0; nCorners = 0; }
-    for (int i = tid; i < PH * (PWB / 16); i += FT) {
-        const int yy = i / (PWB / 16), q = i - yy * (PWB / 16);
-        const int gy = min(gy0 + yy, L.h + kEdge - 1);
-        const uint4* src = reinterpret_cast<const uint4*>(img + (long long)gy * L.pitch + ax0) + q;
-        uint4 v = __ldg(src);
-        if (rho8) {
-            const uint32_t prev = q ? __ldg(reinterpret_cast<const uint32_t*>(src) - 1) : 0u;
-            v = make_uint4(__funnelshift_l(prev, v.x, rho8), __funnelshift_l(v.x, v.y, rho8),
-                           __funnelshift_l(v.y, v.z, rho8), __funnelshift_l(v.z, v.w, rho8));
-        }
-        reinterpret_cast<uint4*>(px + yy * PWB)[q] = v;
+    /* stage rows [gy0, gy0+PH) of the bordered level, PWB bytes from the 16-byte aligned padded column at or before the
+     * word left of score column 0's centre: that centre (window x0-1 = padded column 47+x0, a multiple of 4 by the tile
+     * grid) lands at byte cbase = 4, 8, 12 or 16 of a staged row and the compass test reads whole words.  One thread
+     * issues the TMA box load; parts of the box beyond the bordered level are zero-filled and only feed masked-out
+     * positions. */
+    const int gy0 = kFastBorder + y0 - 4;
+    const int xc = kLeftPad + kFastBorder + x0 - 1;           /* padded column of score column 0's centre */
+    const int bx0 = (xc - 4) & ~15, cbase = xc - bx0;
+    if (tid == 0) {
+        nList = 0; nCorners = 0;
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, PH * PWB);
+        tma_load_3d(px, &maps.m[t.level], bx0, kEdge + gy0, f, &bar);
     }
     for (int i = tid; i < SH * SWP / 4; i += FT) reinterpret_cast<uint32_t*>(sc)[i] = 0;
     /* which neighbours of a tile column / row lie in the same cell interior (interiors start at 3 + j*wCell):
@@ -116,7 +112,8 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
         const int cy = max(h3, 0) / L.hCell, ly = h3 - cy * L.hCell;
         rowInfo[r] = (uint16_t)(cy | ((ly > 0) << 14) | ((ly < L.hCell - 1) << 15));
     }
-    __syncthreads();
+    __syncthreads();                 /* barrier initialised, scores cleared */
+    mbar_wait(&bar, 0);              /* tile landed */
 
     /* (A) compass test at the low threshold on [x0-1, x0+TW+1) x [y0-1, y0+TH+1): a contiguous 9-arc contains one
      * pixel of every antipodal pair, so  min(max(N,S), max(E,W)) > c + t  (bright arc)  or
@@ -125,7 +122,7 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
      * u16x2 lanes with PRMT and evaluates two positions per VIMNMX.U16x2 — ~11 instructions per position instead of
      * ~30 scalar.  The comparisons use bit 15 of each lane as a borrow guard: ((X | 0x8000) - M) keeps bit 15 iff
      * X >= M.  Survivors are kept as bits; ONE warp scan + one shared atomic per warp reserves list space. */
-    const int xlo = max(0, 3 - (x0 - 1)), xhi = min(SW, L.fw - 3 - (x0 - 1));    /* valid score columns */
+    const int xlo = max(0, 3 - (x0 - 1)), xhi = min(TW + 2, L.fw - 3 - (x0 - 1));    /* valid score columns */
     const int ylo = max(0, 3 - (y0 - 1)), yhi = min(SH, L.fh - 3 - (y0 - 1));
     const uint32_t tG = (uint32_t)lowTh * 0x10001u + 0x80008000u;
     uint32_t bits = 0;
@@ -232,12 +229,12 @@ k_fast(const __grid_constant__ Geom g, const TileRef* __restrict__ tiles, const 
     }
 }
 
-cudaError_t launch_fast(const Geom& g, const TileRef* tiles, int ntiles, const uint8_t* dPyr,
+cudaError_t launch_fast(const Geom& g, const TileRef* tiles, int ntiles, const void* tmaMaps,
                         int iniTh, int minTh, uint8_t* dCellFlag, uint32_t* dCand, int32_t* dCandCount,
                         int nframes, cudaStream_t st)
 {
     dim3 grid(ntiles, nframes);
-    k_fast<<<grid, FT, 0, st>>>(g, tiles, dPyr, iniTh, iniTh < minTh ? iniTh : minTh, dCellFlag, dCand, dCandCount);
+    k_fast<<<grid, FT, 0, st>>>(g, tiles, static_cast<const TmaMaps*>(tmaMaps)->fastTile, iniTh, iniTh < minTh ? iniTh : minTh, dCellFlag, dCand, dCandCount);
     return cudaGetLastError();
 }
 

@@ -39,7 +39,7 @@ void build_tiles(const Geom& g, std::vector<TileRef>& fast, std::vector<TileRef>
     for (int l = 0; l < g.nlevels; ++l) {
         const LevelGeom& L = g.L[l];
         for (int ty = 0; ty * kFastTileH < L.fh; ++ty)
-            for (int tx = 0; tx * kFastTileW < L.fw; ++tx) fast.push_back({(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
+            for (int tx = 0; tx * kFastTileW - kFastLead < L.fw; ++tx) fast.push_back({(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
         for (int ty = 0; ty * kBlurTileH < L.h; ++ty)
             for (int tx = 0; tx * kBlurTileW < L.w; ++tx) blur.push_back({(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
     }
@@ -72,6 +72,7 @@ int ensure_geometry(sdyn_ctx* c, int W, int H)
         const char* why = "";
         TmaMaps* tm = static_cast<TmaMaps*>(c->tma);
         cudaError_t e = encode_level_maps(g, c->dPyr, c->maxBatch, kBlurStageW, kBlurStageH, &tm->blurTile, &why);
+        if (e == cudaSuccess) e = encode_level_maps(g, c->dPyr, c->maxBatch, kFastStageW, kFastStageH, &tm->fastTile, &why);
         if (e == cudaSuccess) e = encode_level_maps(g, c->dPyr, c->maxBatch, kPatchPitch, kOrientRows, &tm->orientPatch, &why);
         if (e == cudaSuccess) e = encode_level_maps(g, c->dBlur, c->maxBatch, kPatchPitch, kDescRows, &tm->descPatch, &why);
         if (e == cudaSuccess) e = encode_resize_maps(g, c->dPyr, c->maxBatch, &tm->resizeSrc, &why);
@@ -201,7 +202,7 @@ int enqueue_extract(sdyn_ctx* c, int nframes, const uint8_t* dGray, size_t frame
     if (fork) CU(c, cudaEventRecord(c->evJoin, c->aux));
     {
         StageTimer t(c, st, SDYN_STAGE_FAST);
-        CU(c, launch_fast(g, c->dFastTiles, c->nFastTiles, c->dPyr, p.ini_th_fast, p.min_th_fast, c->dCellFlag,
+        CU(c, launch_fast(g, c->dFastTiles, c->nFastTiles, c->tma, p.ini_th_fast, p.min_th_fast, c->dCellFlag,
                           c->dCand, c->dCandCount, nframes, st));
     }
     {

@@ -157,7 +157,7 @@ cudaError_t launch_level0(const Geom& g, const uint8_t* dIn, size_t inFrameStrid
                           uint8_t* dPyr, int nframes, cudaStream_t st);
 cudaError_t launch_resize(const Geom& g, int level, const uint8_t* dTables, const void* tmaMaps, uint8_t* dPyr,
                           int nframes, cudaStream_t st);
-cudaError_t launch_fast(const Geom& g, const TileRef* tiles, int ntiles, const uint8_t* dPyr,
+cudaError_t launch_fast(const Geom& g, const TileRef* tiles, int ntiles, const void* tmaMaps,
                         int iniTh, int minTh, uint8_t* dCellFlag, uint32_t* dCand, int32_t* dCandCount,
                         int nframes, cudaStream_t st);
 cudaError_t launch_octree(const Geom& g, int iniTh, int minTh, const uint8_t* dCellFlag, uint32_t* dCand,
@@ -174,7 +174,12 @@ cudaError_t launch_undistort(const CameraModel& cam, const sdyn_keypoint* dKp, c
                              sdyn_keypoint* dKpUn, int nframes, cudaStream_t st);
 cudaError_t launch_undistort_xy(const CameraModel& cam, const float* dSrc, int n, float* dDst, cudaStream_t st);
 
-constexpr int kFastTileW = 126, kFastTileH = 30;   /* +2 halo = 128 x 32 score positions: 4 x 4 per thread, no idle lanes */
+/* FAST tiles: 124 x 30 window pixels (+ halo = 126 x 32 of the 128 x 32 score positions a CTA computes: 4 x 4 per thread).
+ * Tile tx starts at window column 124 tx - kFastLead: 124 = 0 and -3 = 1 (mod 4) put the centre pixel of score column 0
+ * on a 4-byte boundary of the padded row for every tile, so a TMA box (x origin a multiple of 16) delivers the tile with
+ * the compass test's words aligned. */
+constexpr int kFastTileW = 124, kFastTileH = 30, kFastLead = 3;
+constexpr int kFastStageW = 160, kFastStageH = kFastTileH + 8;   /* staged box: 16 + 128 + 4 needed bytes; tile + 1 (NMS halo) + 3 (ring) rows each side */
 constexpr int kBlurTileW = 128, kBlurTileH = 32;
 constexpr int kBlurStageW = kBlurTileW + 32, kBlurStageH = kBlurTileH + 6;   /* staged box: columns x0-16 .. x0+W+15, rows y0-3 .. y0+H+2 */
 constexpr int kPatchPitch = 80;            /* descriptor-stage patch box: 64 needed bytes, rows 20 banks apart */

@@ -48,10 +48,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int x, 
 struct LevelMaps { CUtensorMap m[SDYN_MAX_LEVELS]; };
 
 /* the tensor maps of a context (host copies, re-encoded when the geometry changes).  The x coordinate of a box must be a
- * multiple of 16 bytes (the TMA unit faults otherwise), which the blur tiles (128-column grid) and the 16-byte aligned
- * patch origins of the descriptor stage satisfy by construction. */
+ * multiple of 16 bytes (the TMA unit faults otherwise): the blur tiles (128-column grid), the patch origins of the
+ * descriptor stage and the resize source rectangles are 16-byte aligned by construction, and the FAST box starts at the
+ * aligned column at or before the tile (the tile grid keeps the remainder a multiple of 4). */
 struct TmaMaps {
     LevelMaps blurTile;     /* over the pyramid: kBlurStageW x kBlurStageH (tile + 7x7 halo) */
+    LevelMaps fastTile;     /* over the pyramid: kFastStageW x kFastStageH (tile + NMS halo + ring) */
     LevelMaps orientPatch;  /* over the pyramid: kPatchPitch x 31 rows (IC_Angle disc) */
     LevelMaps descPatch;    /* over the blurred pyramid: kPatchPitch x 37 rows (rotated pattern reach) */
     LevelMaps resizeSrc;    /* m[l], l >= 1: over level l-1 of the pyramid, kResizePitch x rsRows(l) (source rectangle of a tile) */
