@@ -222,7 +222,7 @@ cudaError_t launch_resize(const Geom& g, int level, const uint8_t* dTables, cons
                           cudaStream_t st)
 {
     const LevelGeom& L = g.L[level];
-    const bool fixed = L.rsPitch <= kResizePitch;
+    const bool fixed = L.rsPitch <= kResizePitch && L.rsRows <= 256;      /* a TMA box is at most 256 rows (tma_host.cpp) */
     const int pitch = fixed ? kResizePitch : L.rsPitch;
     const size_t smem = (size_t)pitch * L.rsRows + (size_t)L.rsRows * RT_W * sizeof(uint16_t);
     if (smem + 2048 > 48 * 1024) {      /* static shared memory counts against the 48 KB default; the opt-in is per device */

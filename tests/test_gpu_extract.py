@@ -74,6 +74,22 @@ def test_strided_input_and_size_change():
     check_frame(k, d, ok, od)
 
 
+@pytest.mark.parametrize("w,h", [(333, 251), (517, 243), (1023, 301), (641, 479)])
+def test_odd_sizes_tile_edges(w, h):
+    """Sizes that are multiples of nothing: the last tile of every level hangs over the bordered extent, so the TMA box
+    loads of k_fast / k_blur / k_resize / k_orient_describe run into their zero-filled out-of-range parts, and the pyramid
+    (incl. frames) must still equal the oracle's byte for byte."""
+    gpu = pysdyn.Extractor(700, 1.2, 8, 15, 7, max_width=w, max_height=h)
+    cpu = orc.Extractor(700, 1.2, 8, 15, 7)
+    img = np.ascontiguousarray(common.frame("kitti", 11)[:h, :w])
+    k, d = gpu(img)
+    ok, od = cpu(img)
+    check_frame(k, d, ok, od, (w, h))
+    for level in (0, 3, 7):
+        assert np.array_equal(gpu.level(0, level), cpu.level(level)), (w, h, level)
+    gpu.close()
+
+
 def test_edge_cases():
     gpu, cpu = make("small")
     k, d = gpu(np.zeros((0, 0), np.uint8))                   # empty image: silent no-op (ORBextractor.cc:1046)
