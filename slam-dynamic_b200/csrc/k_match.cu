@@ -685,7 +685,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs)
  * One CTA per search; T and the per-query decisions live in shared memory. */
 constexpr int RF = 1024;
 
-__global__ void __launch_bounds__(RF)
+__global__ void __launch_bounds__(RF, 1)
 k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
 {
     extern __shared__ int smemFix[];
@@ -717,9 +717,11 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
     int* sOff = baseT + J.n;               /* nq + 1: offsets of the compacted lists */
     uint32_t* sPool = reinterpret_cast<uint32_t*>(sOff + J.nq + 1);
     uint8_t* qLock = reinterpret_cast<uint8_t*>(sPool + poolCap);      /* nq */
-    __shared__ int sStaged;
+    uint16_t* act = reinterpret_cast<uint16_t*>(qLock + ((J.nq + 1) & ~1));   /* queries with a non-empty list (any order) */
+    __shared__ int sStaged, sNAct;
     for (int k = tid; k < n; k += RF) baseT[k] = (J.assign[k] != -1 && J.locked[k]) ? -1 : 0x7fffffff;
     for (int q = tid; q < nq; q += RF) { acc[q] = -2; qLock[q] = locks(q); }
+    if (tid == 0) sNAct = 0;
     {
         /* exclusive scan of the list lengths: a contiguous chunk of queries per thread */
         const int per = (nq + RF - 1) / RF, q0 = min(tid * per, nq), q1 = min(q0 + per, nq);
@@ -746,6 +748,18 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
     }
     __syncthreads();
     const bool staged = sStaged != 0;
+    /* only queries that have candidates take part in the sweeps (the others are decided: no match); one shared atomic
+     * per warp appends them to the active list */
+    for (int q0 = 0; q0 < nq; q0 += RF) {
+        const int q = q0 + tid;
+        const bool has = q < nq && sOff[q + 1] > sOff[q];
+        if (q < nq && !has) acc[q] = -1;
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        int base = 0;
+        if ((tid & 31) == 0 && m) base = atomicAdd(&sNAct, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (has) act[base + __popc(m & ((1u << (tid & 31)) - 1))] = (uint16_t)q;
+    }
     if (staged)
         for (int q = tid; q < nq; q += RF) {
             const int2 span = J.qspan[q];
@@ -754,6 +768,7 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
             for (int p = 0; p < span.y; ++p) sPool[o + p] = __ldg(J.pool + span.x + p);
         }
     __syncthreads();
+    const int nAct = sNAct;
 
     for (int sweep = 0; sweep <= nq; ++sweep) {
         /* T from the claims of the previous sweep */
@@ -766,7 +781,8 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
             }
         __syncthreads();
         int changed = 0;
-        for (int q = tid; q < nq; q += RF) {
+        for (int i = tid; i < nAct; i += RF) {
+            const int q = act[i];
             int2 span;
             const uint32_t* P;
             if (staged) { span.x = sOff[q]; span.y = sOff[q + 1] - span.x; P = sPool; }
@@ -916,8 +932,9 @@ cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQue
 cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st)
 {
     if (mode == MM_FRAME || mode == MM_MAP || mode == MM_POSE) {
-        /* lockT + baseT (maxN each), acc + sOff (maxQ each), qLock bytes, and whatever is left for the compacted lists */
-        const size_t fixedB = (size_t)(2 * maxN + 2 * maxQ + 1) * sizeof(int) + (size_t)maxQ + 16;
+        /* lockT + baseT (maxN each), acc + sOff (maxQ each), qLock bytes, the active list, and whatever is left for the
+         * compacted lists */
+        const size_t fixedB = (size_t)(2 * maxN + 2 * maxQ + 1) * sizeof(int) + (size_t)maxQ * 3 + 16;   /* + qLock bytes + active list */
         const size_t budget = 200 * 1024;
         if (fixedB + 4096 > budget) return cudaErrorInvalidValue;
         const int poolCap = (int)((budget - fixedB) / 4);
