@@ -414,14 +414,16 @@ def main():
         chunk = frames[s:s + B]
         k, d, n = ex.extract_batch(chunk)
         kd += [(k[i, :n[i]].copy(), d[i, :n[i]].copy()) for i in range(len(chunk))]
-    arrays = scenario.build_track_batch(kd, seq_seed(cfg, rank), 1, W, H, nrect, NLEVELS, cap, N_MAP, REF_STRIDE,
+    # LastFrame arrays are sized by the data (largest keypoint count of the sequence, rounded up), like the reference's vectors
+    last_stride = min(cap, (max(len(k) for k, _ in kd) + 63) // 64 * 64)
+    arrays = scenario.build_track_batch(kd, seq_seed(cfg, rank), 1, W, H, nrect, NLEVELS, last_stride, N_MAP, REF_STRIDE,
                                         n_map=N_MAP, seed=3)
     params = scenario.track_params(W, H)
     # the reference frame's in-box keypoint block is sized by the data (largest per-frame total, rounded up)
     ref_stride = min(REF_STRIDE, max(64, (int(arrays["ref_off"].reshape(len(arrays["ref_off"]), -1)[:, -1].max()) + 63) // 64 * 64))
     arrays["ref_desc"] = np.ascontiguousarray(arrays["ref_desc"].reshape(len(arrays["ref_desc"]), REF_STRIDE, 32)[:, :ref_stride])
     arrays["ref_xy"] = np.ascontiguousarray(arrays["ref_xy"].reshape(len(arrays["ref_xy"]), REF_STRIDE, 2)[:, :ref_stride])
-    strides = (cap, N_MAP, ref_stride)
+    strides = (last_stride, N_MAP, ref_stride)
     # undistorted camera: mvKeysUn is mvKeys (src/Frame.cc:814-818) -> pass the same array for both
     keys_un_alias = np.array_equal(arrays["last_keys"], arrays["last_keys_un"])
     cur_frames = frames[1:]
