@@ -1,14 +1,14 @@
-/* Orientation (K4), rotated-BRIEF descriptors (K6) and final keypoint assembly: one warp per keypoint.
+/* Orientation (K4), rotated-BRIEF descriptors (K6) and final keypoint assembly: a warp per group of keypoints.
  *   reference: IC_Angle                 src/ORBextractor.cc:77-104   (on the UNBLURRED level)
  *              computeOrbDescriptor     src/ORBextractor.cc:107-147  (on the blurred level)
  *              operator() output loop   src/ORBextractor.cc:1072-1103 (level-major order, pt *= scale)
  *   arithmetic: cv::fastAtan2 (SURVEY A-5), cvRound = round-half-even (A-6); float rotate without FMA
  *              contraction (Appendix B-3)
  *
- * Orientation: lane u+15 owns disc column u (31 lanes) of a shared-memory copy of the patch and the two int32
- * moments are combined with warp shuffles.  Descriptor: lane i owns byte i (8 point pairs, 16 gathers from a
- * shared-memory copy of the blurred patch).  Output slot = (keypoints of lower levels) + list position, which
- * reproduces the reference's level-major concatenation.
+ * Patches arrive in shared memory by TMA box loads (tma.h), one per keypoint and stage.  Orientation: lane v+15 owns
+ * disc row v (31 lanes), its pixels are three 16-byte loads, the two int32 moments are byte dot products combined with
+ * warp shuffles.  Descriptor: lane i owns byte i (8 point pairs, 16 gathers from the blurred patch).  Output slot =
+ * (keypoints of lower levels) + list position, which reproduces the reference's level-major concatenation.
  */
 #include "sdyn_internal.h"
 #include "tma.h"
@@ -63,11 +63,10 @@ __device__ __forceinline__ void patch_load(const CUtensorMap* map, int ax, int y
 }
 
 /* A warp owns KW consecutive keypoints of one (frame, level).
- *   A. per keypoint: the unblurred 31-row patch is staged in shared memory (constant pitch: the 31 disc-row reads
- *      of a lane are LDS with immediate offsets, no 64-bit address arithmetic) and reduced to (m01, m10);
+ *   A. per keypoint: the unblurred 31-row patch is loaded (TMA) and reduced to (m01, m10), one disc row per lane;
  *   B. lanes 0..KW-1 evaluate fastAtan2 / cos / sin for one keypoint each — the scalar tail costs one pass per
  *      warp instead of one per keypoint;
- *   C. per keypoint: the blurred 37-row patch is staged and lane i builds descriptor byte i from 16 LDS gathers. */
+ *   C. per keypoint: the blurred 37-row patch is loaded (TMA) and lane i builds descriptor byte i from 16 LDS gathers. */
 __global__ void __launch_bounds__(DW * 32)
 k_orient_describe(const __grid_constant__ Geom g, const __grid_constant__ LevelMaps orientMaps,
                   const __grid_constant__ LevelMaps descMaps,

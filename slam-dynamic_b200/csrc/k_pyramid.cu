@@ -3,7 +3,8 @@
  *   reference: ORBextractor::ComputePyramid, src/ORBextractor.cc:1107-1132
  *   arithmetic: cv::resize INTER_LINEAR 8-bit path + cv::copyMakeBorder REFLECT_101 (SURVEY A-1, A-2)
  *
- * Bound: HBM/L2 bandwidth.  Algorithmic bytes per frame: read W*H once, write every bordered level once.
+ * Bound: instruction issue first (60-75 % issue-active at 15-25 % of DRAM throughput), HBM second.  Algorithmic bytes
+ * per frame: read W*H once, write every bordered level once.
  * Every thread produces 4 horizontally adjacent bytes of a bordered row and stores them with one aligned
  * 32-bit store; the rows of a level are 32-byte aligned at interior column 0.
  */
