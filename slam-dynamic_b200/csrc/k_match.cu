@@ -770,6 +770,40 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
     __syncthreads();
     const int nAct = sNAct;
 
+    /* Best-only searches (FRAME, POSE) are monotone: a keypoint, once unavailable to a query, stays unavailable, so a
+     * query only ever moves DOWN its list (or to "no match") and never returns.  T can then be kept in place with
+     * atomicMin — a claim a query has since abandoned is harmless, because it abandoned the keypoint only after an
+     * earlier query locked it — and a sweep merely re-checks "is my keypoint still mine to take" (two shared loads),
+     * re-picking for the few queries that lost theirs.  The map search's ratio test against the second-best candidate
+     * is not monotone (a query can go from accepted to rejected while its keypoint stays free), so it rebuilds T from
+     * the current claims every sweep (below). */
+    if (frameLike) {
+        for (int k = tid; k < n; k += RF) lockT[k] = baseT[k];
+        __syncthreads();
+        for (int sweep = 0; sweep <= nq; ++sweep) {
+            int changed = 0;
+            for (int i = tid; i < nAct; i += RF) {
+                const int q = act[i], cur = acc[q];
+                if (cur == -1 || (cur >= 0 && lockT[cur] >= q)) continue;      /* rejected for good / still holds */
+                int2 span;
+                const uint32_t* P;
+                if (staged) { span.x = sOff[q]; span.y = sOff[q + 1] - span.x; P = sPool; }
+                else { span = J.qspan[q]; P = J.pool; }
+                uint32_t a = NONE;                 /* best unlocked candidate: distance << 20 | list position */
+                for (int p = 0; p < span.y; ++p) {
+                    const uint32_t rec = P[span.x + p];
+                    if (rec == NONE || lockT[rec_idx(rec)] < q) continue;
+                    a = min(a, ((uint32_t)rec_dist(rec) << 20) | (uint32_t)p);
+                }
+                int res = -1;
+                if (a != NONE && (int)(a >> 20) <= distTh) res = rec_idx(P[span.x + (a & 0xfffff)]);
+                acc[q] = res;
+                changed = 1;
+                if (res >= 0 && qLock[q]) atomicMin(&lockT[res], q);
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+    } else
     for (int sweep = 0; sweep <= nq; ++sweep) {
         /* T from the claims of the previous sweep */
         for (int k = tid; k < n; k += RF) lockT[k] = baseT[k];
