@@ -715,7 +715,8 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
      * trips before.  Lists that do not fit (pc records) stay in global memory and are read through the same code. */
     int* baseT = acc + J.nq;               /* n: lock state on entry (-1 locked, INT_MAX free) */
     int* sOff = baseT + J.n;               /* nq + 1: offsets of the compacted lists */
-    uint32_t* sPool = reinterpret_cast<uint32_t*>(sOff + J.nq + 1);
+    uint32_t* seen = reinterpret_cast<uint32_t*>(sOff + J.nq + 1);       /* nq: best | second-best keypoint of the last evaluation (map search) */
+    uint32_t* sPool = seen + J.nq;
     uint8_t* qLock = reinterpret_cast<uint8_t*>(sPool + poolCap);      /* nq */
     uint16_t* act = reinterpret_cast<uint16_t*>(qLock + ((J.nq + 1) & ~1));   /* queries with a non-empty list (any order) */
     __shared__ int sStaged, sNAct;
@@ -803,48 +804,74 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
             }
             if (!__syncthreads_or(changed)) break;
         }
-    } else
-    for (int sweep = 0; sweep <= nq; ++sweep) {
-        /* T from the claims of the previous sweep */
-        for (int k = tid; k < n; k += RF) lockT[k] = baseT[k];
-        __syncthreads();
-        if (sweep > 0)
-            for (int q = tid; q < nq; q += RF) {
-                const int a = acc[q];
-                if (a >= 0 && qLock[q]) atomicMin(&lockT[a], q);
-            }
-        __syncthreads();
-        int changed = 0;
-        for (int i = tid; i < nAct; i += RF) {
-            const int q = act[i];
-            int2 span;
-            const uint32_t* P;
-            if (staged) { span.x = sOff[q]; span.y = sOff[q + 1] - span.x; P = sPool; }
-            else { span = J.qspan[q]; P = J.pool; }
-            /* best and second-best unlocked candidate as keys distance << 20 | list position (first of equals wins);
-             * the lists are short (a few entries), so a plain loop beats an unrolled, predicated one */
-            uint32_t a = NONE, b = NONE;
-            for (int p = 0; p < span.y; ++p) {
-                const uint32_t rec = P[span.x + p];
-                if (rec == NONE || lockT[rec_idx(rec)] < q) continue;
-                const uint32_t key = ((uint32_t)rec_dist(rec) << 20) | (uint32_t)p;
-                if (key < a) { b = a; a = key; } else if (key < b) b = key;
-            }
-            int res = -1;
-            if (a != NONE) {
-                const uint32_t r1 = P[span.x + (a & 0xfffff)];
-                const int bestDist = (int)(a >> 20);
-                bool ok = bestDist <= distTh;
-                if (ok && mode == MM_MAP) {
-                    int bestDist2 = 256, bestLevel2 = -1;
-                    if (b != NONE) { bestDist2 = (int)(b >> 20); bestLevel2 = rec_level(P[span.x + (b & 0xfffff)]); }
-                    ok = !(rec_level(r1) == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2));
+    } else {
+        /* Map search.  T is rebuilt from the current claims only when it has to be: a query that gives up a keypoint it
+         * was the FIRST to lock (possible only through the ratio test, when its second-best candidate gets locked)
+         * leaves T too low, so the next sweep starts from a rebuilt T and re-evaluates every query.  All other sweeps
+         * are incremental: T only decreases (atomicMin of new claims), and a query whose best and second-best candidates
+         * of its last evaluation are both still available has nothing to re-decide (availability only shrinks between
+         * rebuilds).  When a sweep changes nothing and no rebuild is pending, the smallest claim ever made on each
+         * keypoint is a current one, i.e. T is exact and the state is the fixpoint. */
+        bool rebuild = true;
+        for (int sweep = 0; sweep <= 2 * nq + 1; ++sweep) {
+            const bool full = rebuild;
+            if (rebuild) {
+                for (int k = tid; k < n; k += RF) lockT[k] = baseT[k];
+                __syncthreads();
+                for (int q = tid; q < nq; q += RF) {
+                    const int a = acc[q];
+                    if (a >= 0 && qLock[q]) atomicMin(&lockT[a], q);
                 }
-                if (ok) res = rec_idx(r1);
+                __syncthreads();
+                rebuild = false;
             }
-            if (res != acc[q]) { acc[q] = res; changed = 1; }
+            int changed = 0, retract = 0;
+            for (int i = tid; i < nAct; i += RF) {
+                const int q = act[i], cur = acc[q];
+                if (!full && cur != -2) {
+                    const uint32_t s2 = seen[q];
+                    const int b1 = (int)(s2 & 0xffffu), b2 = (int)(s2 >> 16);
+                    if ((b1 == 0xffff || lockT[b1] >= q) && (b2 == 0xffff || lockT[b2] >= q)) continue;
+                }
+                int2 span;
+                const uint32_t* P;
+                if (staged) { span.x = sOff[q]; span.y = sOff[q + 1] - span.x; P = sPool; }
+                else { span = J.qspan[q]; P = J.pool; }
+                /* best and second-best unlocked candidate as keys distance << 20 | list position (first of equals wins) */
+                uint32_t a = NONE, b = NONE;
+                for (int p = 0; p < span.y; ++p) {
+                    const uint32_t rec = P[span.x + p];
+                    if (rec == NONE || lockT[rec_idx(rec)] < q) continue;
+                    const uint32_t key = ((uint32_t)rec_dist(rec) << 20) | (uint32_t)p;
+                    if (key < a) { b = a; a = key; } else if (key < b) b = key;
+                }
+                int res = -1;
+                uint32_t s2 = 0xffffffffu;
+                if (a != NONE) {
+                    const uint32_t r1 = P[span.x + (a & 0xfffff)];
+                    const int bestDist = (int)(a >> 20);
+                    int bestDist2 = 256, bestLevel2 = -1;
+                    s2 = (uint32_t)rec_idx(r1) | 0xffff0000u;
+                    if (b != NONE) {
+                        const uint32_t r2 = P[span.x + (b & 0xfffff)];
+                        bestDist2 = (int)(b >> 20); bestLevel2 = rec_level(r2);
+                        s2 = (uint32_t)rec_idx(r1) | ((uint32_t)rec_idx(r2) << 16);
+                    }
+                    if (bestDist <= distTh && !(rec_level(r1) == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)))
+                        res = rec_idx(r1);
+                }
+                seen[q] = s2;
+                if (res != cur) {
+                    if (cur >= 0 && qLock[q] && lockT[cur] == q) retract = 1;      /* gives up a keypoint it was first to lock */
+                    acc[q] = res;
+                    changed = 1;
+                    if (res >= 0 && qLock[q]) atomicMin(&lockT[res], q);
+                }
+            }
+            const int anyChanged = __syncthreads_or(changed);
+            rebuild = __syncthreads_or(retract) != 0;
+            if (!anyChanged) break;
         }
-        if (!__syncthreads_or(changed)) break;
     }
 
     /* final owners: the last accepted claimant of every keypoint */
@@ -966,9 +993,9 @@ cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQue
 cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st)
 {
     if (mode == MM_FRAME || mode == MM_MAP || mode == MM_POSE) {
-        /* lockT + baseT (maxN each), acc + sOff (maxQ each), qLock bytes, the active list, and whatever is left for the
-         * compacted lists */
-        const size_t fixedB = (size_t)(2 * maxN + 2 * maxQ + 1) * sizeof(int) + (size_t)maxQ * 3 + 16;   /* + qLock bytes + active list */
+        /* lockT + baseT (maxN each), acc + sOff + seen (maxQ each), qLock bytes, the active list, and whatever is left for
+         * the compacted lists */
+        const size_t fixedB = (size_t)(2 * maxN + 3 * maxQ + 1) * sizeof(int) + (size_t)maxQ * 3 + 16;   /* + qLock bytes + active list */
         const size_t budget = 200 * 1024;
         if (fixedB + 4096 > budget) return cudaErrorInvalidValue;
         const int poolCap = (int)((budget - fixedB) / 4);
