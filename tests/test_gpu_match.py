@@ -109,6 +109,30 @@ def test_search_by_projection_map_tie_heavy(ctx, tum):
     assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
 
 
+@pytest.mark.parametrize("distinct,flip,nnratio", [(6, 3, 0.8), (10, 6, 0.6), (4, 2, 0.9), (16, 10, 0.7)])
+def test_search_by_projection_map_contention(ctx, tum, distinct, flip, nnratio):
+    """Many map points per keypoint, descriptors a few bit flips away from a handful of patterns, every point locking:
+    long claim chains, and queries whose second-best candidate gets locked so that the ratio test flips (the case in
+    which the parallel resolution has to rebuild its lock times)."""
+    p = tum
+    r = np.random.default_rng(100 + distinct)
+    n = len(p["k1"])
+    d1 = scenario.degenerate_descriptors(n, 20 + distinct, distinct).copy()
+    noise = r.integers(0, 256, d1.shape, dtype=np.uint8) & (r.random(d1.shape) < flip / 256.0 * 8).astype(np.uint8) * 0xff
+    d1 ^= noise & r.integers(0, 256, d1.shape, dtype=np.uint8)
+    cur, _ = views(p, False, d1=d1)
+    mp = scenario.map_queries(p["k1"], d1, 8, seed=40 + distinct, count=6000, jitter=9.0)
+    md = d1[r.integers(0, n, len(mp))].copy()
+    md ^= (r.random(md.shape) < 0.03).astype(np.uint8) * r.integers(0, 256, md.shape, dtype=np.uint8)
+    mp["desc"] = md
+    mp["obs_positive"] = r.random(len(mp)) < 0.9
+    for th in (1.0, 6.0):
+        got = pysdyn.Matcher(ctx, nnratio).SearchByProjectionMap(cur, mp, th)
+        ref = orc.match_projection_map(cur, mp, th, nnratio)
+        assert got[0] == ref[0] and got[0] > 20, (got[0], ref[0])
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
 @pytest.mark.parametrize("data", ["tum", "kitti"])
 def test_search_for_initialization(ctx, request, data):
     p = request.getfixturevalue(data)
