@@ -372,7 +372,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sdyn", choices=["sdyn", "reference"])
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
