@@ -95,30 +95,48 @@ def make_frames(cfg, rank, first, count, disparity=0):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms by a process started BEFORE the warm-up (nvidia-smi needs
+    ~0.1 s to produce its first line) and killed after the last timed region; only samples whose host time stamp falls
+    between the start of the device-timed region and the end of the end-to-end regions are reported (the GPU is under
+    load throughout: device pass, per-stage pass, end-to-end passes)."""
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_ms=20):
+        import threading
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        self.lines = []
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q,
-                                       "--format=csv,noheader,nounits", "-lms", "50"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "--format=csv,noheader,nounits", "-lms", str(period_ms)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
         except Exception:
             self.p = None
 
-    def stop(self):
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append((time.perf_counter(), line))
+
+    def wait_started(self, timeout=3.0):
+        t_end = time.perf_counter() + timeout
+        while self.p and not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.005)
+
+    def stop(self, t0, t1):
         if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
         try:
-            out = self.p.communicate(timeout=5)[0]
+            self.p.wait(timeout=5)
         except Exception:
-            out = ""
+            pass
+        self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
+        for t, line in list(self.lines):
+            if t < t0 or t > t1:
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 6:
                 continue
@@ -130,7 +148,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "window": "device-timed region .. end of the end-to-end regions (GPU under load throughout)"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -462,11 +481,14 @@ def main():
         tin = pysdyn.track_inputs(dptrs, base, strides, params)
         pysdyn.track_batch_device(ctxs[c], B, dev_frames[base].data_ptr(), W * H, W, H, W, tin, streams[c].cuda_stream)
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_started()
     for s in range(Wm * NCTX):
         step_device_on(s, s % NCTX)
     barrier()
     launches0 = sum(c.launch_count() for c in ctxs)
-    sampler = ClockSampler(local) if rank == 0 else None
+    t_clk0 = time.perf_counter()
     e0 = [torch.cuda.Event(enable_timing=True) for _ in streams]
     e1 = [torch.cuda.Event(enable_timing=True) for _ in streams]
     for c, st in enumerate(streams):
@@ -477,7 +499,6 @@ def main():
         e1[c].record(st)
     barrier()
     ms = max(e0[0].elapsed_time(e1[c]) for c in range(NCTX))     # first start .. last finish, on the device
-    clocks = sampler.stop() if sampler else None
     launches = sum(c.launch_count() for c in ctxs) - launches0
     launches_per_step = launches // max(K, 1)
 
@@ -547,6 +568,7 @@ def main():
         barrier()
         e2e_runs.append(time.perf_counter() - t0)
     e2e_s = float(np.median(e2e_runs))
+    clocks = sampler.stop(t_clk0, time.perf_counter()) if sampler else None
     # the e2e outputs of the last step must equal the device-resident run's results for the same frames
     last = Wm + K - 1
     if (last % nsets) == ((Wm + K - 1) % nsets):
