@@ -1,0 +1,2 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY: forwards to minicv.hpp (oracle/ref_shim), no OpenCV here. */
+#include "../minicv.hpp"
