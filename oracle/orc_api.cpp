@@ -288,4 +288,57 @@ int orc_first_separate(const sdyn_keypoint* keys, int N, double* boxes, int* box
     return (int)b.size();
 }
 
+/* Tracking::classifyF (flag 2) / classifyH (flag 1) on explicit matches */
+void orc_classify(int flag, const float* M, const float* curXY, const float* refXY, const int* query, const int* train, int nm, int* falseDyn)
+{
+    std::vector<Match> m(nm);
+    for (int i = 0; i < nm; ++i) m[i] = {query[i], train[i], 0};
+    std::vector<int> fd(nm, -1);
+    if (flag == 1) classify_h(M, curXY, refXY, m, fd); else classify_f(M, curXY, refXY, m, fd);
+    for (int i = 0; i < nm; ++i) falseDyn[i] = fd[i];
+}
+
+static void boxes_from_csr(int nb, const int* off, const float* xy, const uint8_t* desc, std::vector<BoxKeys>& out)
+{
+    out.resize(nb);
+    for (int b = 0; b < nb; ++b) {
+        out[b].xy.assign(xy + 2 * (size_t)off[b], xy + 2 * (size_t)off[b + 1]);
+        out[b].desc.assign(desc + 32 * (size_t)off[b], desc + 32 * (size_t)off[b + 1]);
+    }
+}
+
+/* Tracking::Separate (Tracking.cc:1093-1239) on flat arrays: per-box keypoints of the current / reference frame as CSR
+ * (off[nboxes+1], xy = mvdynKeysUn, desc = mdynDescriptors).  dynStatus comes back as CSR; curBoxStatus is updated. */
+int orc_separate(int ncur, const int* curOff, const float* curXY, const uint8_t* curDesc, const int* curBoxIdx, int* curBoxStatus,
+                 int nref, const int* refOff, const float* refXY, const uint8_t* refDesc, const int* refBoxIdx,
+                 int nlast, const int* lastBoxIdx, const int* lastBoxStatus, const float* HorF, int flag, int* dsOff, int* dsVal, int cap)
+{
+    std::vector<BoxKeys> cur, ref;
+    boxes_from_csr(ncur, curOff, curXY, curDesc, cur);
+    boxes_from_csr(nref, refOff, refXY, refDesc, ref);
+    std::vector<int> cbi(curBoxIdx, curBoxIdx + ncur), cbs(curBoxStatus, curBoxStatus + ncur), rbi(refBoxIdx, refBoxIdx + nref);
+    std::vector<int> lbi(lastBoxIdx, lastBoxIdx + nlast), lbs(lastBoxStatus, lastBoxStatus + nlast);
+    std::vector<std::vector<int>> ds;
+    std::vector<std::vector<Match>> matches;
+    const int r = separate(cur, cbi, cbs, ref, rbi, lbi, lbs, HorF, flag, ds, matches);
+    int n = 0;
+    for (int b = 0; b < ncur; ++b) {
+        dsOff[b] = n;
+        for (int v : ds[b]) { if (n < cap) dsVal[n] = v; ++n; }
+        curBoxStatus[b] = cbs[b];
+    }
+    dsOff[ncur] = n;
+    return r;
+}
+
+/* Frame::UpdateFrame (Frame.cc:607-641): which (box, k) entries are appended, in push order */
+int orc_update_frame(int nboxes, const int* dsOff, const int* dsVal, const int* cidOff, const int* cid, int* outBox, int* outK, int cap)
+{
+    std::vector<std::vector<int>> ds(nboxes), ci(nboxes);
+    for (int b = 0; b < nboxes; ++b) { ds[b].assign(dsVal + dsOff[b], dsVal + dsOff[b + 1]); ci[b].assign(cid + cidOff[b], cid + cidOff[b + 1]); }
+    const auto pushed = update_frame(ds, ci);
+    for (size_t i = 0; i < pushed.size() && (int)i < cap; ++i) { outBox[i] = pushed[i].first; outK[i] = pushed[i].second; }
+    return (int)pushed.size();
+}
+
 }  // extern "C"

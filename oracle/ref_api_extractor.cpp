@@ -12,13 +12,14 @@
  */
 #include <opencv2/core/core.hpp>
 #include "ORBextractor.h"
+#include "ref_shim/ref_arena.h"
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <sys/mman.h>
 
 namespace {
-constexpr size_t ARENA_BYTES = (size_t)4 << 30;   /* address space only (MAP_NORESERVE) */
+constexpr size_t ARENA_BYTES = (size_t)64 << 30;   /* address space only (MAP_NORESERVE) */
 char* g_arena = nullptr;
 thread_local size_t t_off = 0;
 thread_local bool t_bump = false;
@@ -38,26 +39,32 @@ void* ref_alloc(size_t n)
 }
 void ref_free(void* p) { if (p && !in_arena(p)) std::free(p); }
 
-struct BumpScope {
-    bool on;
-    BumpScope() : on(g_mode == 1)
-    {
-        if (!on) return;
-        if (!g_arena) {
-            void* m = mmap(nullptr, ARENA_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-            if (m == MAP_FAILED) { on = false; return; }
-            g_arena = (char*)m;
-        }
-        t_off = 0; t_bump = true;
-    }
-    ~BumpScope()
-    {
-        if (!on) return;
-        t_bump = false;
-        madvise(g_arena, (t_off + 4095) & ~(size_t)4095, MADV_DONTNEED);   /* give the pages back */
-    }
-};
+size_t g_persist = 0;      /* arena bytes below this offset belong to objects that outlive their scope (Frames) */
 }  // namespace
+
+namespace refapi {
+BumpScope::BumpScope(bool persist_) : on(g_mode == 1), persist(persist_)
+{
+    if (!on) return;
+    if (!g_arena) {
+        void* m = mmap(nullptr, ARENA_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (m == MAP_FAILED) { on = false; return; }
+        g_arena = (char*)m;
+    }
+    t_off = g_persist; t_bump = true;
+}
+BumpScope::~BumpScope()
+{
+    if (!on) return;
+    t_bump = false;
+    const size_t end = (t_off + 4095) & ~(size_t)4095;
+    if (persist) g_persist = end;
+    else madvise(g_arena + g_persist, end - g_persist, MADV_DONTNEED);   /* give the pages back */
+}
+void BumpScope::pause(bool p) { if (on) t_bump = !p; }
+size_t arena_used() { return t_off; }
+}  // namespace refapi
+using refapi::BumpScope;
 
 void* operator new(size_t n) { return ref_alloc(n); }
 void* operator new[](size_t n) { return ref_alloc(n); }
@@ -72,6 +79,7 @@ extern "C" {
 
 /* 0 = glibc malloc (the reference's real behaviour on this libc), 1 = monotonic arena during extraction */
 void ref_set_alloc_mode(int mode) { g_mode = mode; }
+double ref_arena_used_mb() { return refapi::arena_used() / 1048576.0; }
 
 void* ref_extractor_create(int nf, float sf, int nl, int ini, int mn) { return new ORBextractor(nf, sf, nl, ini, mn); }
 void ref_extractor_destroy(void* e) { delete (ORBextractor*)e; }
@@ -98,14 +106,14 @@ int ref_extractor_run(void* e, const uint8_t* img, int w, int h, int stride, cv:
             }
             if (scope.on) {
                 /* the pyramid Mats were allocated from the arena: re-home them on the heap before it is recycled */
-                t_bump = false;
+                scope.pause(true);
                 for (auto& lvl : E->mvImagePyramid) {
                     if (lvl.empty()) continue;
                     cv::Mat whole(lvl.rows + 38, lvl.cols + 38, lvl.type());
                     for (int r = 0; r < whole.rows; ++r) std::memcpy(whole.ptr(r), lvl.data - 19 * (ptrdiff_t)lvl.step - 19 + r * (ptrdiff_t)lvl.step, whole.cols);
                     lvl = whole(cv::Rect(19, 19, lvl.cols, lvl.rows));
                 }
-                t_bump = true;
+                scope.pause(false);
             }
         }
     }

@@ -10,6 +10,7 @@
 #include "Frame.h"
 #include "ORBmatcher.h"
 #include "ORBextractor.h"
+#include "ref_shim/ref_arena.h"
 #include <cstring>
 #include <iostream>
 #include <map>
@@ -28,8 +29,8 @@ void classify(int flag, const cv::Mat& M, const std::vector<cv::KeyPoint>& cur, 
 namespace {
 
 struct Quiet {      /* the reference prints progress lines to std::cout */
+    std::ostringstream sink;        /* declared first: it must exist before cout is pointed at it */
     std::streambuf* old;
-    std::ostringstream sink;
     Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
     ~Quiet() { std::cout.rdbuf(old); }
 };
@@ -110,6 +111,7 @@ void* ref_frame_rgbd_boxes(void* extractor, const uint8_t* gray, int w, int h, c
     for (int i = 0; i < ndist; ++i) D.at<float>(i) = dist[i];
     Frame empty;
     Frame& lastF = last ? *((FrameBox*)last)->f : empty;
+    refapi::BumpScope arena(true);      /* the extraction inside the constructor sees the pinned allocation order (B-1) */
     fb->f.reset(new Frame(im, rgb, dep, mask, bx, lastF, 0.0, (ORBextractor*)extractor, &fb->voc, K, D, bf, thDepth));
     fb->f->mpORBvocabulary = nullptr;
     return fb;
@@ -124,7 +126,13 @@ void* ref_frame_stereo(void* exL, void* exR, const uint8_t* left, const uint8_t*
     cv::Mat K = cv::Mat::eye(3, 3, CV_32F);
     K.at<float>(0, 0) = K4[0]; K.at<float>(1, 1) = K4[1]; K.at<float>(0, 2) = K4[2]; K.at<float>(1, 2) = K4[3];
     cv::Mat D = cv::Mat::zeros(4, 1, CV_32F);
-    fb->f.reset(new Frame(imL, imR, rgb, 0.0, (ORBextractor*)exL, (ORBextractor*)exR, &fb->voc, K, D, bf, thDepth));
+    /* The constructor calls ComputeStereoMatches (Frame.cc:99), which reads `mb`, before it assigns `mb = mbf/fx` (:124).  In
+     * the reference the Frame is a stack temporary that lands on the previous frame's bytes, so the field still holds the
+     * previous (identical) baseline; here the value is planted in the raw storage before the constructor runs. */
+    void* mem = ::operator new(sizeof(Frame));
+    std::memset(mem, 0, sizeof(Frame));
+    reinterpret_cast<Frame*>(mem)->mb = bf / K4[0];
+    fb->f.reset(new (mem) Frame(imL, imR, rgb, 0.0, (ORBextractor*)exL, (ORBextractor*)exR, &fb->voc, K, D, bf, thDepth));
     fb->f->mpORBvocabulary = nullptr;
     return fb;
 }
@@ -429,32 +437,74 @@ int ref_search_by_projection_sim3(void* kf, const float* Scw16, void* points, in
 {
     FrameBox* K = (FrameBox*)kf;
     PointList& L = **(std::shared_ptr<PointList>*)points;
+    static MapPoint dummy(mat3x1(Scw16), mat3x1(Scw16), descRow((const uint8_t*)"0123456789012345678901234567890123"), 0, 0, 1, false);
     std::vector<MapPoint*> vpMatched(K->kf->N, nullptr);
+    for (int i = 0; i < K->kf->N; ++i) if (matched[i] == -2) vpMatched[i] = &dummy;      /* in: -2 = already matched elsewhere */
     ORBmatcher matcher(nnratio, true);
-    const int n = matcher.SearchByProjection(K->kf.get(), matRows(Scw16, 4, 4), L.ptrs, vpMatched, th);
-    for (int i = 0; i < K->kf->N; ++i) { auto it = L.index.find(vpMatched[i]); matched[i] = vpMatched[i] && it != L.index.end() ? it->second : -1; }
+    std::vector<MapPoint*> v;
+    for (MapPoint* m : L.ptrs) if (m) v.push_back(m);      /* the reference's list never holds NULL (no check at :318) */
+    const int n = matcher.SearchByProjection(K->kf.get(), matRows(Scw16, 4, 4), v, vpMatched, th);
+    for (int i = 0; i < K->kf->N; ++i) {
+        auto it = L.index.find(vpMatched[i]);
+        matched[i] = !vpMatched[i] ? -1 : it != L.index.end() ? it->second : -2;
+    }
     return n;
 }
 
-/* ORBmatcher.cc:982-1130 Fuse(pKF, vpMapPoints, th): reports per candidate what happened:
- * out[i] = keypoint index the point was added to / replaced at, or -1; replaced[i] = 1 when an existing point was involved */
-int ref_fuse(void* kf, void* points, float th, float nnratio, int* outIdx, uint8_t* replaced)
+/* ORBmatcher.cc:982-1130 Fuse(pKF, vpMapPoints, th) on a keyframe whose keypoints are all free and candidates without
+ * observations: a fused candidate either gets AddObservation(pKF, bestIdx) or, when an earlier candidate already sits
+ * there, is Replace()d by it — both reveal bestIdx.  outIdx[i] = bestIdx | -1. */
+int ref_fuse(void* kf, void* points, float th, float nnratio, int* outIdx)
 {
     FrameBox* K = (FrameBox*)kf;
     PointList& L = **(std::shared_ptr<PointList>*)points;
-    const std::vector<MapPoint*> before = K->kf->mvpMapPoints;
+    K->kf->mvpMapPoints.assign(K->kf->N, nullptr);
     ORBmatcher matcher(nnratio, true);
     const int n = matcher.Fuse(K->kf.get(), L.ptrs, th);
-    for (size_t i = 0; i < L.ptrs.size(); ++i) { outIdx[i] = -1; replaced[i] = 0; }
     for (size_t i = 0; i < L.ptrs.size(); ++i) {
         MapPoint* m = L.ptrs[i];
+        outIdx[i] = -1;
         if (!m) continue;
-        for (int k = 0; k < K->kf->N; ++k)
-            if (K->kf->mvpMapPoints[k] == m && before[k] != m) outIdx[i] = k;      /* AddMapPoint on a free keypoint */
-        if (m->mpReplaced) { replaced[i] = 1; for (int k = 0; k < K->kf->N; ++k) if (before[k] == m->mpReplaced) outIdx[i] = k; }
-        for (int k = 0; k < K->kf->N; ++k)
-            if (before[k] && before[k]->mpReplaced == m) { replaced[i] = 1; outIdx[i] = k; }
+        if (m->mObservations.count(K->kf.get())) outIdx[i] = (int)m->mObservations[K->kf.get()];
+        else if (m->mpReplaced && m->mpReplaced->mObservations.count(K->kf.get())) outIdx[i] = (int)m->mpReplaced->mObservations[K->kf.get()];
     }
+    return n;
+}
+
+/* ORBmatcher.cc:1132-1257 Fuse(pKF, Scw, vpPoints, th, vpReplacePoint), same set-up: outIdx[i] = bestIdx | -1 */
+int ref_fuse_sim3(void* kf, const float* Scw16, void* points, float th, float nnratio, int* outIdx)
+{
+    FrameBox* K = (FrameBox*)kf;
+    PointList& L = **(std::shared_ptr<PointList>*)points;
+    K->kf->mvpMapPoints.assign(K->kf->N, nullptr);
+    std::vector<MapPoint*> v;
+    std::vector<int> at;
+    for (size_t i = 0; i < L.ptrs.size(); ++i) if (L.ptrs[i]) { v.push_back(L.ptrs[i]); at.push_back((int)i); }   /* no NULL check at :1163 */
+    std::vector<MapPoint*> repl(v.size(), nullptr);
+    ORBmatcher matcher(nnratio, true);
+    const int n = matcher.Fuse(K->kf.get(), matRows(Scw16, 4, 4), v, th, repl);
+    for (size_t i = 0; i < L.ptrs.size(); ++i) outIdx[i] = -1;
+    for (size_t c = 0; c < v.size(); ++c) {
+        MapPoint* m = v[c];
+        if (m->mObservations.count(K->kf.get())) outIdx[at[c]] = (int)m->mObservations[K->kf.get()];
+        else if (repl[c] && repl[c]->mObservations.count(K->kf.get())) outIdx[at[c]] = (int)repl[c]->mObservations[K->kf.get()];
+    }
+    return n;
+}
+
+/* ORBmatcher.cc:1259-1483: matches12[idx1] = idx2 | -1 (in: -2 = already matched to something else) */
+int ref_search_by_sim3(void* kf1, void* kf2, int* matches12, float s12, const float* R12, const float* t12, float th, float nnratio)
+{
+    FrameBox* A = (FrameBox*)kf1;
+    FrameBox* B = (FrameBox*)kf2;
+    static MapPoint dummy(mat3x1(R12), mat3x1(R12), descRow((const uint8_t*)"0123456789012345678901234567890123"), 0, 0, 1, false);
+    std::vector<MapPoint*> m12(A->kf->N, nullptr);
+    for (int i = 0; i < A->kf->N; ++i) if (matches12[i] == -2) m12[i] = &dummy;
+    ORBmatcher matcher(nnratio, true);
+    const int n = matcher.SearchBySim3(A->kf.get(), B->kf.get(), m12, s12, matRows(R12, 3, 3), matRows(t12, 3, 1), th);
+    std::map<MapPoint*, int> where;
+    for (int i = 0; i < B->kf->N; ++i) if (B->kf->mvpMapPoints[i]) where[B->kf->mvpMapPoints[i]] = i;
+    for (int i = 0; i < A->kf->N; ++i) matches12[i] = !m12[i] ? -1 : m12[i] == &dummy ? -2 : where[m12[i]];
     return n;
 }
 

@@ -297,6 +297,60 @@ def separate_pairs(pairs, M, mode):
     return S.separate_pairs(None, pairs, M, mode, fn=lambda arr, n, m, md: lib.orc_separate_pairs(arr, n, m, md))
 
 
+def classify(flag, M, cur_xy, ref_xy, query, train):
+    """Tracking::classifyH (flag 1) / classifyF (flag 2) on explicit matches -> falseDyn."""
+    c = np.ascontiguousarray(cur_xy, np.float32).reshape(-1, 2); r = np.ascontiguousarray(ref_xy, np.float32).reshape(-1, 2)
+    q = np.ascontiguousarray(query, np.int32); t = np.ascontiguousarray(train, np.int32)
+    m = np.ascontiguousarray(M, np.float32).reshape(9); out = np.full(len(q), -1, np.int32)
+    lib.orc_classify.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+    lib.orc_classify(flag, m.ctypes.data, c.ctypes.data, r.ctypes.data, q.ctypes.data, t.ctypes.data, len(q), out.ctypes.data)
+    return out
+
+
+def _box_csr(state):
+    """state: dict(ku = mvKeysUn-like keys per ORIGINAL index, d = descriptors, per_box = [[original indices]], box_idx)."""
+    off = np.zeros(len(state["per_box"]) + 1, np.int32)
+    off[1:] = np.cumsum([len(m) for m in state["per_box"]])
+    flat = [i for m in state["per_box"] for i in m]
+    xy = np.ascontiguousarray(np.stack([state["ku"]["x"][flat], state["ku"]["y"][flat]], 1), np.float32).reshape(-1, 2)
+    desc = np.ascontiguousarray(state["d"][flat], np.uint8).reshape(-1, 32)
+    return off, xy, desc
+
+
+def separate_frames(cur, ref, HorF, mode, last=None, cur_status=None, last_status=None):
+    """Tracking::Separate for two frames described by their per-box dynamic lists.  mode 0 = classifyF, 1 = classifyH.
+    Returns dict(ret, dyn_status=[array per box], status)."""
+    last = ref if last is None else last
+    co, cx, cd = _box_csr(cur); ro, rx, rd = _box_csr(ref)
+    nb = len(cur["per_box"])
+    cbi = np.ascontiguousarray(cur["box_idx"], np.int32); rbi = np.ascontiguousarray(ref["box_idx"], np.int32)
+    lbi = np.ascontiguousarray(last["box_idx"], np.int32)
+    cbs = np.full(nb, -1, np.int32) if cur_status is None else np.ascontiguousarray(cur_status, np.int32).copy()
+    lbs = np.zeros(len(lbi), np.int32) if last_status is None else np.ascontiguousarray(last_status, np.int32)
+    m = np.ascontiguousarray(HorF, np.float32).reshape(9)
+    cap = max(len(cx), 1) + 16
+    off = np.zeros(nb + 1, np.int32); val = np.zeros(cap, np.int32)
+    lib.orc_separate.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    ret = lib.orc_separate(nb, co.ctypes.data, cx.ctypes.data, cd.ctypes.data, cbi.ctypes.data, cbs.ctypes.data,
+                           len(ref["per_box"]), ro.ctypes.data, rx.ctypes.data, rd.ctypes.data, rbi.ctypes.data,
+                           len(lbi), lbi.ctypes.data, lbs.ctypes.data, m.ctypes.data, 1 if mode == 1 else 2, off.ctypes.data, val.ctypes.data, cap)
+    return dict(ret=ret, dyn_status=[val[off[b]:off[b + 1]].copy() for b in range(nb)], status=cbs)
+
+
+def update_frame_list(dyn_status, dyn_class_id):
+    """Frame::UpdateFrame: the (box, k) entries appended to the frame, in push order."""
+    nb = len(dyn_status)
+    so = np.zeros(nb + 1, np.int32); so[1:] = np.cumsum([len(d) for d in dyn_status])
+    co = np.zeros(nb + 1, np.int32); co[1:] = np.cumsum([len(c) for c in dyn_class_id])
+    sv = np.ascontiguousarray(np.concatenate([np.asarray(d, np.int32) for d in dyn_status] + [np.zeros(0, np.int32)]), np.int32)
+    cv = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32) for c in dyn_class_id] + [np.zeros(0, np.int32)]), np.int32)
+    cap = len(sv) + 1
+    ob = np.zeros(cap, np.int32); ok = np.zeros(cap, np.int32)
+    lib.orc_update_frame.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int]
+    n = lib.orc_update_frame(nb, so.ctypes.data, sv.ctypes.data, co.ctypes.data, cv.ctypes.data, ob.ctypes.data, ok.ctypes.data, cap)
+    return list(zip(ob[:n].tolist(), ok[:n].tolist()))
+
+
 def invert3x3(m):
     m = np.ascontiguousarray(m, np.float32).reshape(9)
     out = np.zeros(9, np.float32)

@@ -135,6 +135,9 @@ lib.ref_search_by_bow_kf.argtypes = [_vp, _vp, C.c_float, C.c_int, _vp]
 lib.ref_search_for_triangulation.argtypes = [_vp, _vp, _vp, C.c_int, C.c_float, C.c_int, _vp]
 lib.ref_search_by_projection_reloc.argtypes = [_vp, _vp, C.c_float, C.c_int, C.c_float, C.c_int, _vp]
 lib.ref_search_by_projection_sim3.argtypes = [_vp, _vp, _vp, C.c_int, C.c_float, _vp]
+lib.ref_fuse.argtypes = [_vp, _vp, C.c_float, C.c_float, _vp]
+lib.ref_fuse_sim3.argtypes = [_vp, _vp, _vp, C.c_float, C.c_float, _vp]
+lib.ref_search_by_sim3.argtypes = [_vp, _vp, _vp, C.c_float, _vp, _vp, C.c_float, C.c_float]
 lib.ref_frame_update.argtypes = [_vp, _vp, _vp, C.c_int]
 lib.ref_tracking_separate.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]
 lib.ref_classify.argtypes = [C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp]
@@ -380,10 +383,29 @@ def search_by_projection_reloc(cur, KF, th, orb_dist, nnratio=0.9, check_ori=Tru
     return n, assign
 
 
-def search_by_projection_sim3(KF, Scw, points, th, nnratio=0.75):
-    s = _f32(Scw).reshape(16); matched = np.full(KF.n, -1, np.int32)
+def search_by_projection_sim3(KF, Scw, points, th, nnratio=0.75, matched=None):
+    s = _f32(Scw).reshape(16)
+    matched = np.full(KF.n, -1, np.int32) if matched is None else np.ascontiguousarray(matched, np.int32).copy()
     n = lib.ref_search_by_projection_sim3(KF.h, s.ctypes.data, points.h, th, nnratio, matched.ctypes.data)
     return n, matched
+
+
+def fuse(KF, points, th, nnratio=0.6):
+    out = np.full(points.n, -1, np.int32)
+    n = lib.ref_fuse(KF.h, points.h, th, nnratio, out.ctypes.data)
+    return n, out
+
+
+def fuse_sim3(KF, Scw, points, th, nnratio=0.6):
+    s = _f32(Scw).reshape(16); out = np.full(points.n, -1, np.int32)
+    n = lib.ref_fuse_sim3(KF.h, s.ctypes.data, points.h, th, nnratio, out.ctypes.data)
+    return n, out
+
+
+def search_by_sim3(KF1, KF2, matches12, s12, R12, t12, th, nnratio=0.6):
+    m = np.ascontiguousarray(matches12, np.int32).copy(); R = _f32(R12).reshape(9); t = _f32(t12).reshape(3)
+    n = lib.ref_search_by_sim3(KF1.h, KF2.h, m.ctypes.data, s12, R.ctypes.data, t.ctypes.data, th, nnratio)
+    return n, m
 
 
 def tracking_separate(cur, ref_frame, last, HorF, flag):
