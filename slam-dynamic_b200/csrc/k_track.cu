@@ -38,7 +38,8 @@ constexpr int BS = 128;
 
 /* one CTA per (box slot, frame) */
 __global__ void __launch_bounds__(BS)
-k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, const uint8_t* __restrict__ desc,
+k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, const sdyn_keypoint* __restrict__ kpUn,
+            const uint8_t* __restrict__ desc,
             const int32_t* __restrict__ count, int cap, const uint64_t* __restrict__ mask,
             const unsigned long long* __restrict__ has, int32_t* __restrict__ boxList, int32_t* __restrict__ nnQ,
             int32_t* __restrict__ nnT, int nnTStride, uint8_t* __restrict__ readmit, int32_t* __restrict__ staticExit)
@@ -68,7 +69,8 @@ k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, co
     const int r = in.ref_box[f * 64 + surv];
     if (r < 0) return;                               /* box id not present in the reference frame */
     const int n = min(count[f], cap);
-    const sdyn_keypoint* K = kp + (size_t)f * cap;
+    /* classifyF reads mvdynKeysUn (Tracking.cc:1129-1131: undistorted points); the box test above used mvKeys (Frame.cc:562) */
+    const sdyn_keypoint* K = kpUn + (size_t)f * cap;
     const uint8_t* D = desc + (size_t)f * cap * 32;
     const uint64_t* M = mask + (size_t)f * cap;
     int32_t* list = boxList + ((size_t)f * 64 + s) * cap;
@@ -169,7 +171,7 @@ k_dyn_finalize(const uint64_t* __restrict__ mask, const uint8_t* __restrict__ re
     if (threadIdx.x == 0) { counts[f * 4 + 2] = a[0]; counts[f * 4 + 3] = a[1]; }
 }
 
-cudaError_t launch_dyn_stage(const sdyn_track_inputs& in, const sdyn_keypoint* kp, const uint8_t* desc, const int32_t* count,
+cudaError_t launch_dyn_stage(const sdyn_track_inputs& in, const sdyn_keypoint* kp, const sdyn_keypoint* kpUn, const uint8_t* desc, const int32_t* count,
                              int cap, uint64_t* mask, unsigned long long* has, int32_t* boxList, int32_t* nnQ, int32_t* nnT,
                              int nnTStride, uint8_t* readmit, int32_t* staticExit, uint8_t* dynMask, int32_t* counts,
                              int nframes, cudaStream_t st)
@@ -178,7 +180,7 @@ cudaError_t launch_dyn_stage(const sdyn_track_inputs& in, const sdyn_keypoint* k
     if (e != cudaSuccess) return e;
     k_box_occupancy<<<nframes, 256, 0, st>>>(mask, count, cap, has);
     dim3 grid(64, nframes);
-    k_box_stage<<<grid, BS, 0, st>>>(in, kp, desc, count, cap, mask, has, boxList, nnQ, nnT, nnTStride, readmit, staticExit);
+    k_box_stage<<<grid, BS, 0, st>>>(in, kp, kpUn, desc, count, cap, mask, has, boxList, nnQ, nnT, nnTStride, readmit, staticExit);
     k_dyn_finalize<<<nframes, 256, 0, st>>>(mask, readmit, staticExit, count, cap, dynMask, counts);
     return cudaGetLastError();
 }

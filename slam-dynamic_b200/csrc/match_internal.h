@@ -91,7 +91,8 @@ struct BoxPairJob {
 cudaError_t launch_box_mask(const sdyn_keypoint* dKeys, const int32_t* nPtr, int n, int keyStride,
                             const double* dBoxes, const int32_t* nBoxesPtr, int nboxes, int boxStride,
                             uint64_t* dMask, int njobs, cudaStream_t st);
-cudaError_t launch_dyn_stage(const sdyn_track_inputs& in, const sdyn_keypoint* kp, const uint8_t* desc, const int32_t* count,
+/* kp = mvKeys (box containment, Frame.cc:562), kpUn = mvKeysUn (classifyF coordinates, Tracking.cc:1129-1131) */
+cudaError_t launch_dyn_stage(const sdyn_track_inputs& in, const sdyn_keypoint* kp, const sdyn_keypoint* kpUn, const uint8_t* desc, const int32_t* count,
                              int cap, uint64_t* mask, unsigned long long* has, int32_t* boxList, int32_t* nnQ, int32_t* nnT,
                              int nnTStride, uint8_t* readmit, int32_t* staticExit, uint8_t* dynMask, int32_t* counts,
                              int nframes, cudaStream_t st);

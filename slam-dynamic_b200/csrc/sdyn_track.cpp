@@ -299,7 +299,7 @@ static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs
     }
     {
         StageTimer tm(c, ds, SDYN_STAGE_DYNAMIC);
-        TCU(c, launch_dyn_stage(*in, c->dKp, c->dDesc, c->dCount, cap, t->mask, t->has, t->boxList, t->nnQ, t->nnT,
+        TCU(c, launch_dyn_stage(*in, c->dKp, c->camera.enabled ? c->dKpUn : c->dKp, c->dDesc, c->dCount, cap, t->mask, t->has, t->boxList, t->nnQ, t->nnT,
                                 std::max(t->refStride, 1), t->readmit, t->staticExit, t->dynMask, t->counts, nframes, ds));
         c->launches += 4;
     }

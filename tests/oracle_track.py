@@ -42,7 +42,8 @@ def track_frame(keys, desc, scale, W, H, arrays, f, params, last_stride, keys_un
         o0, o1 = int(arrays["ref_off"][f, r]), int(arrays["ref_off"][f, r + 1])
         if o1 == o0:
             continue
-        qd = desc[ks]; qx = np.stack([keys["x"][ks], keys["y"][ks]], 1)
+        ku = keys if keys_un is None else keys_un      # classifyF reads mvdynKeysUn (Tracking.cc:1129-1131)
+        qd = desc[ks]; qx = np.stack([ku["x"][ks], ku["y"][ks]], 1)
         mq, mt, md, fd = orc.separate_pairs([(qd, qx, arrays["ref_desc"][f, o0:o1], arrays["ref_xy"][f, o0:o1])],
                                             arrays["fmat"][f], 0)[0]
         good = len(mq)
