@@ -36,6 +36,32 @@ REF_STRIDE = 1024   # capacity for the reference frame's in-box keypoints
 METRIC = "frames/sec ORB extract+match+dyn-mask @KITTI 1241x376 2k feats; % HBM roofline"
 
 
+def csrc_sha():
+    """Digest of the kernel sources: the committed ncu figures (profiles/*_ncu_traffic.json) are stamped with it and ignored
+    when the kernels have changed since the capture."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "slam-dynamic_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cpp", ".h")):
+            h.update(name.encode()); h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_ncu_figures():
+    """(figures per kernel, note).  Newest profiles/rNN_ncu_traffic.json whose csrc_sha matches the tree."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")), reverse=True):
+        try:
+            tj = json.load(open(path))
+        except Exception:
+            continue
+        if tj.get("csrc_sha") == csrc_sha():
+            return tj, os.path.basename(path)
+        return None, "%s is stale (captured for csrc %s, tree is %s)" % (os.path.basename(path), tj.get("csrc_sha"), csrc_sha())
+    return None, "no ncu capture committed"
+
+
 def level_sizes(W, H):
     s, out = np.float32(1.0), []
     for _ in range(NLEVELS):
@@ -72,9 +98,22 @@ def seq_seed(cfg, rank):
     return 1000 * WORKLOADS[cfg][6] + 100000 * rank + 7
 
 
+def pool_offsets(i):
+    """Camera offset of pool frame i.  Periodic in POOL (frame POOL is frame 0 again), consecutive frames shift by <= 8 px:
+    every batch slot can follow the pool round and round as ONE sequence whose LastFrame is always its previous frame."""
+    j = i % POOL
+    m = j % 32
+    return 3 * (m if m <= 16 else 32 - m), (j * 5) % 8
+
+
+def pool_time(i):
+    m = (i % POOL) % 32
+    return m if m <= 16 else 32 - m
+
+
 def make_frames(cfg, rank, first, count, disparity=0):
-    """Frames first..first+count-1 of this rank's sequence (consecutive frames shift by <= 8 px); disparity > 0 renders
-    the right view of a rectified stereo rig (content shifted, its own sensor noise)."""
+    """Frames first..first+count-1 (mod POOL) of this rank's cyclic sequence; disparity > 0 renders the right view of a
+    rectified stereo rig (content shifted, its own sensor noise)."""
     import pysdyn
     import scenario
     W, H, nrect, _, _, _, cid = WORKLOADS[cfg]
@@ -83,15 +122,50 @@ def make_frames(cfg, rank, first, count, disparity=0):
 
     def work(t):
         for j in range(t, count, nthreads):
-            i = first + j
-            ox, oy = scenario.sequence_offsets(i)
+            i = (first + j) % POOL
+            ox, oy = pool_offsets(i)
             pysdyn.synth_frame(seq_seed(cfg, rank), 1000 * cid + 100000 * rank + i + (1 << 20) + (disparity << 22), W, H, nrect,
-                               ox + disparity, oy, scenario.sequence_time(i), out=frames[j])
+                               ox + disparity, oy, pool_time(i), out=frames[j])
 
     th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
     [t.start() for t in th]
     [t.join() for t in th]
     return frames
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host thread(s) and its future (pinned) allocations to the NUMA node its GPU hangs off: the H2D path
+    of N ranks otherwise crosses the inter-socket link for half of them and they all draw on node 0's memory controllers
+    (round 1: GPUs 0-3 saturated near 100 GB/s aggregate).  Best effort; returns what was done for the result line."""
+    info = {"gpu_node": None, "cpus": None, "mempolicy": None}
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                      text=True, stderr=subprocess.DEVNULL).strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        info["gpu_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = "%d cpus of node %d" % (len(allowed), node)
+        else:
+            info["cpus"] = "node %d has no cpu in this process's affinity mask (%d allowed)" % (node, len(os.sched_getaffinity(0)))
+        # set_mempolicy(MPOL_PREFERRED, {node}): pinned buffers allocated from here on come from the GPU's node
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+        info["mempolicy"] = "preferred node %d" % node if rc == 0 else "set_mempolicy failed (errno %d)" % ctypes.get_errno()
+    except Exception as e:
+        info["error"] = repr(e)
+    return info
 
 
 class ClockSampler:
@@ -156,21 +230,30 @@ class ClockSampler:
 # CPU arm: the reference's CPU implementation of the path.  The reference itself cannot be built here (needs
 # OpenCV C++ >= 3.4 + contrib, Eigen, Pangolin, PCL, Boost), so this runs its restatement in oracle/ ("port").
 # ------------------------------------------------------------------------------------------------------------
-def cpu_prepare(cfg, nframes):
-    """Inputs of the CPU arm: a short sequence, extracted once to build the track queries."""
+def cpu_prepare(cfg, nframes, threads=1):
+    """Inputs of the CPU arm: the first `nframes` frame inputs of rank 0's pool (frame i tracked against frame i-1),
+    extracted once (frame-parallel) to build the track queries."""
     import orc
     import scenario
     W, H, nrect, nf, ini, mn, _ = WORKLOADS[cfg]
-    frames = make_frames(cfg, 0, 0, nframes + 1)
-    ex = orc.Extractor(nf, SCALE, NLEVELS, ini, mn)
-    kd = [ex(im) for im in frames]
+    frames = make_frames(cfg, 0, -1, nframes + 1)              # frame -1 (= POOL-1) is the LastFrame of frame 0
+    kd = [None] * len(frames)
+
+    def work(t):
+        ex = orc.Extractor(nf, SCALE, NLEVELS, ini, mn)
+        for i in range(t, len(frames), threads):
+            kd[i] = ex(frames[i])
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
     cap = nf + 200
-    arrays = scenario.build_track_batch(kd, seq_seed(cfg, 0), 1, W, H, nrect, NLEVELS, cap, N_MAP, REF_STRIDE,
-                                        n_map=N_MAP, seed=3)
+    arrays = scenario.build_track_batch(kd, seq_seed(cfg, 0), 0, W, H, nrect, NLEVELS, cap, N_MAP, REF_STRIDE,
+                                        n_map=N_MAP, seed=3, offsets=pool_offsets, time=pool_time)
     return frames[1:], arrays, scenario.track_params(W, H), cap
 
 
-def cpu_run(cfg, frames, arrays, params, cap, threads, seconds=None, count=None):
+def cpu_run(cfg, frames, arrays, params, cap, threads, seconds=None, count=None, first=0):
     """Runs the full per-frame hot path (extract + 2 searches + dynamic mask) on the CPU oracle, frame-parallel
     over `threads` host threads, for `seconds` or for `count` frames.  Returns (fps, frames_done)."""
     import orc
@@ -187,7 +270,7 @@ def cpu_run(cfg, frames, arrays, params, cap, threads, seconds=None, count=None)
                 break
             if count is not None and i >= count:
                 break
-            f = i % len(frames)
+            f = (first + i) % len(frames)
             k, d = ex(frames[f])
             oracle_track.track_frame(k, d, ex.scale, W, H, arrays, f, params, cap)
             done[t] += 1
@@ -200,31 +283,43 @@ def cpu_run(cfg, frames, arrays, params, cap, threads, seconds=None, count=None)
     return sum(done) / dt, sum(done)
 
 
+def workload_config(cfg, B, nctx=None):
+    """The `config` object of the result line — identical in both arms (same workload string, pool, frames per step)."""
+    W, H, _, nf, ini, mn, _ = WORKLOADS[cfg]
+    c = {"workload": "%s %dx%d nfeatures=%d levels=%d scale=%.1f iniTh=%d minTh=%d" % (cfg, W, H, nf, NLEVELS, SCALE, ini, mn),
+         "frames_per_step_per_gpu": B, "map_points_per_frame": N_MAP, "pool_frames": POOL,
+         "stages": "extract + SearchByProjection(cur,last) + SearchByProjection(F,map) + dynamic mask",
+         "sharding": "one set of sequences per rank, no data-path collective; NCCL all_gather of run statistics only"}
+    return c
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the path on all host threads: the C++ oracle ("port" — the reference itself
+    needs OpenCV C++/Eigen/Pangolin/PCL to build; oracle/_ref holds its hot-path TUs compiled over a stand-in OpenCV and
+    tests/test_oracle_ref.py shows the port equals them bit for bit).  Same pool, same frames per step as the sdyn arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = args.workload
-    W, H = WORKLOADS[cfg][:2]
     threads = os.cpu_count() or 1
-    frames, arrays, params, cap = cpu_prepare(cfg, 16)
-    per_step = 2 * threads                      # bounded sample per step
+    B = args.batch
+    frames, arrays, params, cap = cpu_prepare(cfg, POOL, threads)
     if args.warmup > 0:
         cpu_run(cfg, frames, arrays, params, cap, threads, count=threads)
     t0 = time.perf_counter()
     total = 0
-    for _ in range(args.steps):
-        total += cpu_run(cfg, frames, arrays, params, cap, threads, count=per_step)[1]
+    for s in range(args.steps):
+        total += cpu_run(cfg, frames, arrays, params, cap, threads, count=B, first=(s * B) % POOL)[1]
     dt = time.perf_counter() - t0
     fps = total / dt
     emit(({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "%s %dx%d" % (cfg, W, H), "frames_per_step": per_step,
-                   "stages": "extract + SearchByProjection(frame) + SearchByProjection(map) + dynamic mask"},
+        "config": workload_config(cfg, B),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d frames per step, frame-parallel C++ oracle (restated reference CPU path)" % per_step},
+                         "sample": "%d steps x %d frames of the %d-frame pool, frame-parallel C++ oracle (restated reference CPU "
+                                   "path; equals the reference's own code bit for bit, tests/test_oracle_ref.py)" % (args.steps, B, POOL)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -247,7 +342,7 @@ def big_vocabulary(k=10, L=6, seed=1):
     return np.concatenate(parents), np.concatenate(leafs), np.concatenate(descs), np.concatenate(weights)
 
 
-def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptrs, strides, params, dev_frames):
+def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptrs, strides, params, dev_frames, mtab, pitch):
     """Device timings of the SURVEY §8(f) rows built after the headline path (same parity bar, tests/test_gpu_*.py):
     ComputeStereoMatches per stereo pair and ComputeBoW per frame, with the oracle timed beside them.  Reported next
     to the headline, never part of it."""
@@ -291,9 +386,9 @@ def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptr
     # BASELINE config 3: stereo pairs through the whole step — both extractions, ComputeStereoMatches, the two searches
     # with mvuRight gates, dynamic mask — on this rank's sequence (right views rendered with an 11 px disparity)
     if strides[0] <= L.cap:
-        dright = torch.from_numpy(make_frames(cfg, rank, 1, Bs, disparity=11)).cuda()
+        dright = torch.from_numpy(make_frames(cfg, rank, 0, Bs, disparity=11)).cuda()
         sp = dict(params); sp["mono"] = 0
-        tin = pysdyn.track_inputs(dptrs, 0, strides, sp)
+        tin = pysdyn.track_inputs(dptrs, 0, strides, sp, map_table=mtab, frame_pitch=pitch)
 
         def stereo_track_step():
             pysdyn.track_batch_stereo_device(L, R, Bs, dev_frames[0].data_ptr(), dright.data_ptr(), W * H, W, H, W, tin, mb, mbf)
@@ -398,6 +493,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample length (0 = skip)")
     ap.add_argument("--contexts", type=int, default=6, help="contexts (streams) per GPU taking steps round-robin")
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="repeat the K-step timed regions until each arm has run this long")
     ap.add_argument("--next-rows", type=int, default=1, help="also time the SURVEY 8(f) rows (stereo, BoW) on rank 0 at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -414,6 +510,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the sdyn path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)                     # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -421,46 +518,68 @@ def main():
     W, H, nrect, nf, ini, mn, _ = WORKLOADS[cfg]
     B = args.batch
     K, Wm = args.steps, max(args.warmup, 3)
-    nsets = POOL // B
-    assert nsets >= 1
+    assert POOL % B == 0 or B <= POOL
 
-    # ---- inputs: this rank's sequence (sharded by sequence: no data-path collective) ----------------------
-    frames = make_frames(cfg, rank, 0, POOL + 1)                # frame 0 only serves as LastFrame of frame 1
+    # ---- inputs: this rank's cyclic sequence (sharded by sequence: no data-path collective) ----------------------
+    # Frame input i = (frame i as CurrentFrame, frame i-1 as LastFrame), i in 0..POOL-1, cyclic.  Every batch slot is one
+    # sequence that walks the pool round and round, one frame per step, so the keypoints a slot extracted in its previous
+    # step ARE its LastFrame (resident on the device, as the reference keeps mLastFrame), and what the reference keeps in
+    # MapPoint objects lives in a device-resident table.  A step consumes, per frame: the image, LastFrame's MapPoint ids +
+    # flag bytes, the local map's ids + projection records (Frame::isInFrustum's outputs), boxes + the reference frame's
+    # in-box keypoints, F21 and the pose pair.
+    frames = make_frames(cfg, rank, 0, POOL)
     ex = pysdyn.Extractor(nf, SCALE, NLEVELS, ini, mn, max_width=W, max_height=H, max_batch=B, device=local)
     cap = ex.cap
     kd = []
-    for s in range(0, POOL + 1, B):                             # untimed pre-pass: LastFrame / map / box inputs
+    for s in range(0, POOL, B):                                 # untimed pre-pass: LastFrame / map / box inputs
         chunk = frames[s:s + B]
         k, d, n = ex.extract_batch(chunk)
         kd += [(k[i, :n[i]].copy(), d[i, :n[i]].copy()) for i in range(len(chunk))]
-    # LastFrame arrays are sized by the data (largest keypoint count of the sequence, rounded up), like the reference's vectors
+    # per-keypoint arrays are sized by the data (largest keypoint count of the sequence, rounded up), like the reference's vectors
     last_stride = min(cap, (max(len(k) for k, _ in kd) + 63) // 64 * 64)
-    arrays = scenario.build_track_batch(kd, seq_seed(cfg, rank), 1, W, H, nrect, NLEVELS, last_stride, N_MAP, REF_STRIDE,
-                                        n_map=N_MAP, seed=3)
+    arrays = scenario.build_track_batch([kd[-1]] + kd, seq_seed(cfg, rank), 0, W, H, nrect, NLEVELS, last_stride, N_MAP, REF_STRIDE,
+                                        n_map=N_MAP, seed=3, offsets=pool_offsets, time=pool_time)
     params = scenario.track_params(W, H)
     # the reference frame's in-box keypoint block is sized by the data (largest per-frame total, rounded up)
     ref_stride = min(REF_STRIDE, max(64, (int(arrays["ref_off"].reshape(len(arrays["ref_off"]), -1)[:, -1].max()) + 63) // 64 * 64))
     arrays["ref_desc"] = np.ascontiguousarray(arrays["ref_desc"].reshape(len(arrays["ref_desc"]), REF_STRIDE, 32)[:, :ref_stride])
     arrays["ref_xy"] = np.ascontiguousarray(arrays["ref_xy"].reshape(len(arrays["ref_xy"]), REF_STRIDE, 2)[:, :ref_stride])
     strides = (last_stride, N_MAP, ref_stride)
-    # undistorted camera: mvKeysUn is mvKeys (src/Frame.cc:814-818) -> pass the same array for both
-    keys_un_alias = np.array_equal(arrays["last_keys"], arrays["last_keys_un"])
-    cur_frames = frames[1:]
+    table, res = scenario.resident_forms(arrays)
+    FORMS = pysdyn.FORM_RESIDENT_LAST | pysdyn.FORM_RESIDENT_MAP
+    step_arrays = {k: arrays[k] for k in ("n_map", "boxes", "n_boxes", "ref_box", "ref_desc", "ref_xy", "ref_off", "fmat", "poses")}
+    step_arrays.update(res)
+    # frame-major record pool (one record per frame input), cyclically extended by one batch: any batch is one contiguous run
+    pin_pool = None
+    layout, pitch = pysdyn.track_record_layout(strides, FORMS)
+    pin_pool = pysdyn.PinnedArray((POOL + B, pitch), np.uint8)
+    pysdyn.pack_records(step_arrays, strides, FORMS, out=pin_pool.array[:POOL])
+    pin_pool.array[POOL:] = pin_pool.array[:B]
+    pin_in = pysdyn.PinnedArray((POOL + B, H, W), np.uint8)
+    pin_in.array[:POOL] = frames; pin_in.array[POOL:] = frames[:B]
 
     # a real (non-legacy) stream: libsdyn launches on it and the torch events below are recorded on it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    dev_frames = torch.from_numpy(cur_frames).cuda()            # resident in HBM for the device-timed number
-    dev = {k: torch.from_numpy(v.view(np.uint8).reshape(v.shape[0], -1)).cuda() for k, v in arrays.items()}
-    dptrs = {k: (t.data_ptr(), t.shape[1]) for k, t in dev.items()}
-    if keys_un_alias:
-        dptrs["last_keys_un"] = dptrs["last_keys"]
+    dev_frames = torch.from_numpy(pin_in.array).cuda()          # resident in HBM for the device-timed number
+    dev_pool = torch.from_numpy(pin_pool.array).cuda()
+    dptrs = {k: (dev_pool.data_ptr() + layout[k], 0) for k in step_arrays}
+    hptrs = {k: (pin_pool.array.ctypes.data + layout[k], 0) for k in step_arrays}
+    mtab = pysdyn.MapTable(len(table), device=local)
+    mtab.update(0, table)
     torch.cuda.synchronize()
 
-    def step_device(s):
-        base = (s % nsets) * B
-        tin = pysdyn.track_inputs(dptrs, base, strides, params)
-        pysdyn.track_batch_device(ex, B, dev_frames[base].data_ptr(), W * H, W, H, W, tin, stream.cuda_stream)
+    NCTX = max(1, args.contexts)
+    CTX_OFF = 37                                                # contexts start at different places of the pool
+
+    def first_input(s, c):
+        """Pool index of slot 0 of context c's step (s // NCTX): every step advances each slot's sequence by one frame."""
+        return (c * CTX_OFF + s // NCTX) % POOL
+
+    def step_device_on(s, c):
+        i0 = first_input(s, c)
+        tin = pysdyn.track_inputs(dptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch)
+        pysdyn.track_batch_device(ctxs[c], B, dev_frames[i0].data_ptr(), W * H, W, H, W, tin, streams[c].cuda_stream)
 
     def barrier():
         if world > 1:
@@ -471,41 +590,48 @@ def main():
     # NCTX contexts, each with its own stream, take the steps round-robin: the kernels of this path are latency-
     # rather than throughput-bound, so independent batches in flight fill each other's idle issue slots (the same
     # arrangement the end-to-end pass uses to overlap PCIe copies).
-    NCTX = max(1, args.contexts)
     ctxs = [ex] + [pysdyn.Extractor(nf, SCALE, NLEVELS, ini, mn, max_width=W, max_height=H, max_batch=B, device=local)
                    for _ in range(NCTX - 1)]
     streams = [stream] + [torch.cuda.Stream() for _ in range(NCTX - 1)]
 
-    def step_device_on(s, c):
-        base = (s % nsets) * B
-        tin = pysdyn.track_inputs(dptrs, base, strides, params)
-        pysdyn.track_batch_device(ctxs[c], B, dev_frames[base].data_ptr(), W * H, W, H, W, tin, streams[c].cuda_stream)
-
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.wait_started()
+    step_no = 0
     for s in range(Wm * NCTX):
-        step_device_on(s, s % NCTX)
+        step_device_on(step_no, step_no % NCTX); step_no += 1
     barrier()
     launches0 = sum(c.launch_count() for c in ctxs)
     t_clk0 = time.perf_counter()
+    # The K-step region is timed REPS times back to back (>= ~0.5 s of GPU work in total, so the driver's samplers see load);
+    # value / ms_per_step are the median region, all regions are reported.
     e0 = [torch.cuda.Event(enable_timing=True) for _ in streams]
     e1 = [torch.cuda.Event(enable_timing=True) for _ in streams]
-    for c, st in enumerate(streams):
-        e0[c].record(st)
-    for s in range(K):
-        step_device_on(Wm + s, s % NCTX)
-    for c, st in enumerate(streams):
-        e1[c].record(st)
-    barrier()
-    ms = max(e0[0].elapsed_time(e1[c]) for c in range(NCTX))     # first start .. last finish, on the device
-    launches = sum(c.launch_count() for c in ctxs) - launches0
+
+    def device_region():
+        nonlocal step_no
+        for c, st in enumerate(streams):
+            e0[c].record(st)
+        for s in range(K):
+            step_device_on(step_no, step_no % NCTX); step_no += 1
+        for c, st in enumerate(streams):
+            e1[c].record(st)
+        barrier()
+        return max(e0[0].elapsed_time(e1[c]) for c in range(NCTX))     # first start .. last finish, on the device
+
+    dev_runs = [device_region()]
+    reps = int(min(max(1, np.ceil(500.0 / max(dev_runs[0], 1e-3))), 40)) if args.min_seconds > 0 else 1
+    reps = max(reps, int(np.ceil(args.min_seconds * 1e3 / max(dev_runs[0], 1e-3)))) if args.min_seconds > 0 else 1
+    reps = min(reps, 60)
+    dev_runs += [device_region() for _ in range(reps - 1)]
+    ms = float(np.median(dev_runs))
+    launches = (sum(c.launch_count() for c in ctxs) - launches0) // len(dev_runs)
     launches_per_step = launches // max(K, 1)
 
-    # per-stage device times: a separate single-stream pass (stages of concurrent streams would overlap)
+    # per-stage device times: a separate single-stream pass on context 0 (stages of concurrent streams would overlap)
     ex.profile(True)
     for s in range(K):
-        step_device(Wm + s)
+        step_device_on(step_no, 0); step_no += NCTX
     barrier()
     stages = ex.profile_read()
     ex.profile(False)
@@ -515,27 +641,12 @@ def main():
     mean_kp = float(counts.mean())
 
     # ---- end to end through the C ABI with pinned host buffers ("e2e") ------------------------------------
-    # the query arrays of a step live in ONE pinned block at sdyn_track_input_layout's offsets: libsdyn uploads such a block
-    # with a single copy (a dozen small copies cost more PCIe time than their bytes)
-    layout, block_bytes = pysdyn.track_input_layout(B, strides, not keys_un_alias)
-    blocks, hptr_sets = [], []
-    for sset in range(nsets):
-        blk = pysdyn.PinnedArray((block_bytes,), np.uint8)
-        blk.array[:] = 0
-        ptrs = {}
-        for k, v in arrays.items():
-            rows = v.view(np.uint8).reshape(v.shape[0], -1)
-            if not (keys_un_alias and k == "last_keys_un"):
-                chunk = rows[sset * B:(sset + 1) * B].reshape(-1)
-                blk.array[layout[k]:layout[k] + chunk.size] = chunk
-            ptrs[k] = (blk.array.ctypes.data + layout[k], rows.shape[1])
-        if keys_un_alias:
-            ptrs["last_keys_un"] = ptrs["last_keys"]
-        blocks.append(blk)
-        hptr_sets.append(ptrs)
-    pin_in = pysdyn.PinnedArray((POOL, H, W), np.uint8)
-    pin_in.array[:] = cur_frames
-    # the same NCTX contexts round-robin: a step's PCIe copies overlap the other contexts' kernels
+    # Per step the call uploads B frames and ONE run of B frame records (ids, flag bytes, projection records, boxes, the
+    # reference frame's in-box keypoints, F21, poses) and downloads keypoints, descriptors, match indices, lock flags, mask and
+    # counts.  LocalMapping's work on the map reaches the device as table updates: NEW_POINTS_PER_FRAME MapPoint records per
+    # frame are uploaded with every step as well (the reference creates a few hundred MapPoints per keyframe).
+    NEW_POINTS_PER_FRAME = 64
+    new_pts = pysdyn.PinnedArray((B * NEW_POINTS_PER_FRAME,), pysdyn.MAP_POINT_DTYPE)
     out_sets = []
     for _ in ctxs:
         o = tuple(pysdyn.PinnedArray(shape, dt) for shape, dt in
@@ -544,9 +655,13 @@ def main():
         out_sets.append((o, tuple(a.array for a in o)))
 
     def step_host_async(s):
-        base = (s % nsets) * B
-        tin = pysdyn.track_inputs(hptr_sets[s % nsets], 0, strides, params)
-        pysdyn.track_batch_host_async(ctxs[s % NCTX], pin_in.array[base:base + B], tin, out_sets[s % NCTX][1])
+        c = s % NCTX
+        i0 = first_input(s, c)
+        # the table rows rewritten here are rows whose content is identical (the synthetic map is static): the transfer is real
+        new_pts.array[:] = table[:len(new_pts.array)]
+        mtab.update(0, new_pts.array, stream=ctxs[c].stream_handle())
+        tin = pysdyn.track_inputs(hptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch)
+        pysdyn.track_batch_host_async(ctxs[c], pin_in.array[i0:i0 + B], tin, out_sets[c][1])
 
     def run_host(first, count):
         for s in range(first, first + count):
@@ -556,28 +671,47 @@ def main():
         for s in range(max(first, first + count - NCTX), first + count):
             pysdyn.track_wait(ctxs[s % NCTX])
 
-    run_host(0, 2 * NCTX)
+    run_host(step_no, 3 * NCTX); step_no += 3 * NCTX
     barrier()
-    # K steps take ~25 ms, short enough for a single host hiccup to move the number by 20 %: the K-step region is
-    # timed five times back to back and the median is reported (all five are in e2e.runs_ms)
     e2e_runs = []
-    for rep in range(5):
+    t_e2e0 = time.perf_counter()
+    while len(e2e_runs) < 5 or (time.perf_counter() - t_e2e0 < args.min_seconds and len(e2e_runs) < 60):
         barrier()
         t0 = time.perf_counter()
-        run_host(Wm, K)
+        run_host(step_no, K); step_no += K
         barrier()
         e2e_runs.append(time.perf_counter() - t0)
     e2e_s = float(np.median(e2e_runs))
     clocks = sampler.stop(t_clk0, time.perf_counter()) if sampler else None
-    # the e2e outputs of the last step must equal the device-resident run's results for the same frames
-    last = Wm + K - 1
-    if (last % nsets) == ((Wm + K - 1) % nsets):
-        eo = out_sets[last % NCTX][1]
-        assert np.array_equal(eo[2], counts) and np.array_equal(eo[6], cnt), "e2e and device-resident results differ"
-    h2d = B * W * H + block_bytes                       # bytes actually copied per step (block padding included)
+
+    # ---- one verification step, untimed: the same frame inputs through the device-pointer and the host-buffer entry points,
+    # and a digest of this rank's results for them (rank r's digest must not depend on the number of GPUs) ----------------
+    def verify_pair(host):
+        outs = []
+        for k in (0, 1):                    # step 0 primes the resident LastFrame, step 1 is compared
+            i0 = (11 + k) % POOL
+            if host:
+                tin = pysdyn.track_inputs(hptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch)
+                pysdyn.track_batch_host(ex, pin_in.array[i0:i0 + B], tin, out_sets[0][1])
+                o = out_sets[0][1]
+                outs = [o[2].copy(), o[6].copy(), o[3].copy(), o[5].copy()]
+            else:
+                tin = pysdyn.track_inputs(dptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch)
+                pysdyn.track_batch_device(ex, B, dev_frames[i0].data_ptr(), W * H, W, H, W, tin, stream.cuda_stream)
+                kk, dd, nn = ex.fetch(B)
+                aa, ll, mm, cc = pysdyn.track_fetch(ex, B)
+                outs = [nn.copy(), cc.copy(), aa.copy(), mm.copy()]
+        return outs
+    v_dev, v_host = verify_pair(False), verify_pair(True)
+    for a, b_ in zip(v_dev, v_host):
+        assert np.array_equal(a, b_), "e2e and device-resident results differ"
+    import hashlib
+    rank_digest = hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in v_dev)).hexdigest()[:16]
+
+    h2d = B * W * H + B * pitch + new_pts.array.nbytes      # bytes actually copied per step (record padding included)
     # what the host link delivers for one plain pinned copy of a step's input volume (context for the e2e number)
     link = None
-    if rank == 0:
+    if True:
         nb = int(h2d)
         src = torch.empty(nb, dtype=torch.uint8).pin_memory(); dst = torch.empty(nb, dtype=torch.uint8, device="cuda")
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -595,7 +729,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)               # timing: max over ranks
     # NCCL all_gather of the per-rank run statistics: the only collective, off the hot path
     g = shard.gather_stats([float(B * K), mean_kp, float(cnt[:, 0].mean()), float(cnt[:, 1].mean()), float(cnt[:, 3].mean()),
-                            float(shard.result_hash(counts, cnt))])
+                            float(int(rank_digest[:12], 16)), float(link["h2d_gbs_pinned_copy"]), float(B * K / e2e_s),
+                            float(-1 if numa.get("gpu_node") is None else numa["gpu_node"])])
     ms_max, e2e_ms_max = float(t[0]), float(t[1])
     if rank != 0:
         if world > 1:
@@ -631,16 +766,13 @@ def main():
     stage_kernel = {"fast": "k_fast", "match": "k_match_candidates", "candidates": "k_match_candidates", "describe": "k_orient_describe", "blur": "k_blur",
                     "pyramid": "k_resize", "octree": "k_octree", "level0": "k_level0", "dynamic": "k_box_stage"}
     traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        if dom and B == 64 and stage_kernel.get(dom) in tj:
-            traffic = tj[stage_kernel[dom]]["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    tj, ncu_note = load_ncu_figures()
+    if tj and dom and B == 64 and stage_kernel.get(dom) in tj:
+        traffic = tj[stage_kernel[dom]]["dram_bytes_per_launch"]
     if dom:
         r = stage_report[dom]
         roof = {"kernel": dom, "bound": "hbm", "achieved": r["alg_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": r["hbm_frac"], "traffic": traffic, "peak_source": peak_src,
+                "frac": r["hbm_frac"], "traffic": traffic, "traffic_source": ncu_note, "peak_source": peak_src,
                 "alg_bytes_per_launch": sab.get(dom, 0) * B,
                 "note": "FAST scoring is integer-ALU bound, not HBM bound (DESIGN.md §Kernels)" if dom == "fast" else ""}
     balg = alg_bytes_extract(W, H, int(round(mean_kp)))
@@ -648,9 +780,8 @@ def main():
     # counts per launch come from the committed ncu capture, the duration is the one measured live above.
     issue = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
         kname = stage_kernel.get(dom)
-        if dom and B == 64 and kname in tj and tj[kname].get("warp_inst_per_launch") and dom in ("fast", "blur", "describe", "level0"):
+        if tj and dom and B == 64 and kname in tj and tj[kname].get("warp_inst_per_launch") and dom in ("fast", "blur", "describe", "level0", "pyramid"):
             sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
             peak_i = 148 * 4 * sm_mhz * 1e6
             ach = tj[kname]["warp_inst_per_launch"] / (stage_report[dom]["ms_per_step"] * 1e-3)
@@ -671,24 +802,32 @@ def main():
     extras = None
     if args.next_rows and world == 1 and cfg == "kitti":
         try:
-            extras = next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, max(K // 2, 5), rank, dptrs, strides, params, dev_frames)
+            extras = next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, max(K // 2, 5), rank, dptrs, strides, params, dev_frames,
+                               mtab, pitch)
         except Exception as e:          # never lose the headline line to a side measurement
             extras = {"error": repr(e)}
 
+    config = workload_config(cfg, B)
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": "%s %dx%d nfeatures=%d levels=%d scale=%.1f iniTh=%d minTh=%d" % (cfg, W, H, nf, NLEVELS, SCALE, ini, mn),
-                   "frames_per_step_per_gpu": B, "map_points_per_frame": N_MAP, "contexts_per_gpu": NCTX,
-                   "stages": "extract + SearchByProjection(cur,last) + SearchByProjection(F,map) + dynamic mask",
-                   "sharding": "one sequence per rank, no data-path collective; NCCL all_gather of run statistics only",
-                   "l2": "inputs cycle through a %d-frame pool (%.0f MB of frames) and each step's working set "
-                         "(~%.0f MB) exceeds the 126 MB L2" % (POOL, POOL * W * H / 1e6, B * 7.0)},
+        "config": config,
+        "run": {"contexts_per_gpu": NCTX, "sequences_per_gpu": NCTX * B,
+                "inputs": "resident MapPoint table (%.0f MB) + resident LastFrame; per frame: image, ids, flag bytes, projection "
+                          "records, boxes, reference in-box keypoints, F21, pose pair (one %d-byte record)" % (table.nbytes / 1e6, pitch),
+                "l2": "inputs cycle through a %d-frame pool (%.0f MB of frames) and each step's working set "
+                      "(~%.0f MB) exceeds the 126 MB L2" % (POOL, POOL * W * H / 1e6, B * 7.0),
+                "device_regions_ms": [round(v, 3) for v in dev_runs],
+                "timing": "K steps per region, regions repeated back to back for >= %.1f s per arm; value / e2e = median region" % args.min_seconds},
+        "rank_digests": ["%012x" % int(v) for v in g[:, 5]],
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "runs_ms": [round(1e3 * v, 3) for v in e2e_runs], "timing": "median of 5 back-to-back K-step regions (host clock, "
-                "barrier + cudaDeviceSynchronize on both sides)"},
+                "runs_ms": [round(1e3 * v, 3) for v in e2e_runs], "timing": "median of %d back-to-back K-step regions (host clock, "
+                "barrier + cudaDeviceSynchronize on both sides)" % len(e2e_runs),
+                "map_updates_per_step": "%d MapPoint records (%d B)" % (len(new_pts.array), new_pts.array.nbytes)},
         "host_link": link,
+        "per_rank": {"h2d_gbs_pinned_copy_alone": [round(float(v), 1) for v in g[:, 6]], "e2e_frames_per_s": [round(float(v)) for v in g[:, 7]],
+                     "gpu_numa_node": [int(v) for v in g[:, 8]], "numa_binding_rank0": numa},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,

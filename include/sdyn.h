@@ -142,6 +142,8 @@ int sdyn_fetch_level(sdyn_ctx* ctx, int frame, int level, uint8_t* out, int* wid
  * threshold fallback, as (x, y, response) int triples in level coordinates relative to the FAST window
  * origin (minBorderX/Y = 16).  Order is unspecified (the selection stage is order-independent). */
 int sdyn_fetch_candidates(sdyn_ctx* ctx, int frame, int level, int32_t* xyv, int cap, int* n_out);
+/* The context's own stream (a cudaStream_t), for ordering caller-side copies (e.g. sdyn_map_update) with its steps. */
+void* sdyn_stream(sdyn_ctx* ctx);
 /* Blocks until all work enqueued on the context's stream has finished. */
 int sdyn_sync(sdyn_ctx* ctx);
 /* Number of kernel launches enqueued by this context since creation (bench.py's gpu_launches). */
@@ -340,13 +342,45 @@ int sdyn_dyn_separate(sdyn_ctx* ctx, sdyn_box_pair* pairs, int npairs, const flo
  *   4. dynamic mask: Frame::firstSeparate's box test, Tracking::Separate's per-box BFMatcher + classifyF and
  *      Frame::UpdateFrame's re-admission:  mask[i] = in_box(i) && !readmitted(i)
  * Searches see every extracted keypoint (the stereo constructor's behaviour, where firstSeparate is disabled,
- * src/Frame.cc:166).  All pointers are DEVICE pointers; per-frame arrays are `*_stride` elements apart. */
+ * src/Frame.cc:166) unless rgbd_split is set (below).  All pointers are DEVICE pointers; per-frame arrays are `*_stride`
+ * elements apart.
+ *
+ * What persists across frames in the reference stays on the device here.  In the reference the query data of the two
+ * searches lives in MapPoint objects (world position, normal, descriptor, scale-invariance distances) and in LastFrame
+ * (its keypoints); only the per-frame bookkeeping changes.  Two resident forms mirror that:
+ *   - `map`: a device-resident MapPoint table (sdyn_map_create / sdyn_map_update), addressed by point id;
+ *   - resident LastFrame: the keypoints each batch slot extracted in the PREVIOUS step of this context (slot f of step k is
+ *     the LastFrame of slot f of step k+1: one sequence per slot).
+ * With them a step uploads, per frame, the image, the ids / flag bytes / projection records and the pose. */
 typedef struct {
-    /* LastFrame of every current frame.  last_keys_un may be NULL or equal to last_keys (mvKeysUn == mvKeys for an
-     * undistorted camera, src/Frame.cc:814-818): the host-buffer entry points then upload the array once. */
+    float world[3];                 /* GetWorldPos() */
+    float normal[3];                /* GetNormal() */
+    float min_distance, max_distance;   /* mfMinDistance, mfMaxDistance (the 0.8 / 1.2 factors are applied on the device) */
+    uint8_t desc[32];               /* GetDescriptor() */
+} sdyn_map_point;                   /* 64 bytes */
+typedef struct sdyn_map sdyn_map;
+int sdyn_map_create(int device, int capacity, sdyn_map** out);
+int sdyn_map_destroy(sdyn_map* map);
+/* points[0..count) become ids first_id .. first_id+count-1.  HOST array; the copy is ordered on `stream` (NULL = default). */
+int sdyn_map_update(sdyn_map* map, int first_id, int count, const sdyn_map_point* points, void* stream);
+int sdyn_map_capacity(const sdyn_map* map);
+
+/* per LastFrame keypoint in the resident form: bit flags next to the MapPoint id (-1 = mvpMapPoints[i] == NULL) */
+enum { SDYN_LP_OUTLIER = 1, SDYN_LP_OBS_POSITIVE = 2 };
+/* per local-map point in the resident form: what Frame::isInFrustum left in the MapPoint for this frame
+ * (src/Frame.cc:718-727) plus the two per-frame state bits; = sdyn_mappoint_query without the descriptor */
+typedef struct {
+    float proj_x, proj_y, proj_xr, view_cos;
+    int32_t level;
+    uint8_t track_in_view, bad, obs_positive, pad;
+} sdyn_map_proj;                    /* 24 bytes */
+
+typedef struct {
+    /* LastFrame of every current frame, explicit form.  last_keys_un may be NULL or equal to last_keys (mvKeysUn == mvKeys
+     * for an undistorted camera, src/Frame.cc:814-818): the host-buffer entry points then upload the array once. */
     const sdyn_last_point* last_points; const sdyn_keypoint* last_keys; const sdyn_keypoint* last_keys_un;
     const int32_t* n_last; int32_t last_stride;
-    /* local map of every current frame */
+    /* local map of every current frame, explicit form */
     const sdyn_mappoint_query* map_points; const int32_t* n_map; int32_t map_stride;
     /* detection boxes (cv::Rect2d, 64 x 4 doubles per frame) and, per box, the reference frame's box joined by
      * Frame::boxTrack (ref_box[f*64+b] = index into that frame's reference boxes or -1) */
@@ -355,11 +389,31 @@ typedef struct {
      * [ref_off[f*65+r], ref_off[f*65+r+1]) of that frame's ref_desc / ref_xy block */
     const uint8_t* ref_desc; const float* ref_xy; const int32_t* ref_off; int32_t ref_stride;
     const float* fmat;              /* F21 per frame, 9 floats (classifyF) */
-    /* camera / pose / search parameters shared by the batch */
+    /* camera and search parameters shared by the batch */
     float min_x, min_y, max_x, max_y, fx, fy, cx, cy, bf, b;
-    float tcw_cur[12], tcw_last[12];
     float th_frame, th_map, nnratio_map;
     int32_t mono, check_orientation;
+    /* poses: per frame rows 0..2 of CurrentFrame.mTcw then of LastFrame.mTcw (24 floats).  The forward / backward level
+     * rule of ORBmatcher.cc:1497-1506 is evaluated per frame on the device. */
+    const float* poses;
+    /* resident forms (see above); each replaces the explicit array of the same search when that array is NULL:
+     *   last_points == NULL: last_ids[f*last_stride + i] / last_flags[..] describe keypoint i of slot f's previous frame,
+     *                        whose keypoints (and count) are taken from the previous step; last_keys / n_last are unused;
+     *   map_points == NULL:  map_ids / map_proj [f*map_stride + q], n_map as before. */
+    const sdyn_map* map;
+    const int32_t* last_ids; const uint8_t* last_flags;
+    const int32_t* map_ids; const sdyn_map_proj* map_proj;
+    /* 0: stereo-constructor semantics (above).  1: RGB-D-constructor semantics (src/Frame.cc:297-403 followed by
+     * Tracking::Separate and Frame::UpdateFrame :607-653): the searches run on the frame the reference tracks with — the
+     * keypoints outside every box in extraction order, then the re-admitted in-box keypoints in UpdateFrame's push order —
+     * and assign / locked / the resident LastFrame of the next step index THAT list (sdyn_track_frame_order gives the
+     * extraction index of each entry). */
+    int32_t rgbd_split;
+    /* 0: array-major — array X of frame f starts X_stride elements after frame f-1's (every array contiguous over the batch).
+     * > 0: frame-major records — array X of frame f starts at (char*)X + f * frame_pitch: each frame's inputs form one
+     * contiguous record of frame_pitch bytes (sdyn_track_record_layout), so any run of consecutive frames of a host-side
+     * pool uploads with ONE copy. */
+    int64_t frame_pitch;
 } sdyn_track_inputs;
 
 typedef struct {
@@ -396,18 +450,29 @@ int sdyn_track_batch_async(sdyn_ctx* ctx, int nframes, const uint8_t* gray, size
 int sdyn_track_wait(sdyn_ctx* ctx);
 /* Layout of the host-buffer entry points' input staging block for `nframes` frames: offsets[i] is where array i of
  * sdyn_track_inputs starts (order: last_points, last_keys, last_keys_un, n_last, map_points, n_map, boxes, n_boxes, ref_box,
- * ref_desc, ref_xy, ref_off, fmat; each on a 256-byte boundary; last_keys_un takes no room unless separate_keys_un), *total
+ * ref_desc, ref_xy, ref_off, fmat, poses, last_ids, last_flags, map_ids, map_proj; each on a 256-byte boundary; an array takes
+ * no room when its form is not in use: `forms` bit 0 = separate last_keys_un, bit 1 = resident LastFrame (last_ids /
+ * last_flags instead of last_points / last_keys), bit 2 = resident map (map_ids / map_proj instead of map_points)), *total
  * the block size.  A caller that builds its arrays inside ONE host block at these offsets (pinned with sdyn_host_alloc) and
  * passes base + offsets[i] as the array pointers has them uploaded with a single copy instead of one copy per array — the
  * per-frame query data the reference keeps in MapPoint / Frame objects (src/ORBmatcher.cc:45-129, 1485-1627) is gathered
  * by the caller either way. */
-#define SDYN_TRACK_INPUT_ARRAYS 13
-int sdyn_track_input_layout(int nframes, int last_stride, int map_stride, int ref_stride, int separate_keys_un,
+#define SDYN_TRACK_INPUT_ARRAYS 18
+enum { SDYN_FORM_SEPARATE_KEYS_UN = 1, SDYN_FORM_RESIDENT_LAST = 2, SDYN_FORM_RESIDENT_MAP = 4 };
+int sdyn_track_input_layout(int nframes, int last_stride, int map_stride, int ref_stride, int forms,
                             size_t offsets[SDYN_TRACK_INPUT_ARRAYS], size_t* total);
+/* Frame-major counterpart: offsets[i] = where array i starts inside ONE frame's record, *pitch = the record size (a multiple
+ * of 256).  A host pool of records (pinned) hands any run of consecutive frames to the host-buffer entry points as one copy:
+ * pass array_i = pool + first_frame * pitch + offsets[i] and frame_pitch = pitch. */
+int sdyn_track_record_layout(int last_stride, int map_stride, int ref_stride, int forms,
+                             size_t offsets[SDYN_TRACK_INPUT_ARRAYS], size_t* pitch);
 /* Statistics of the last fetched step: Hamming-distance evaluations of the frame search and of the map search,
  * summed over the step's frames (the work the popc roofline is computed from). */
 int sdyn_track_stats(const sdyn_ctx* ctx, int nframes, long long evals[2]);
 int sdyn_track_results(const sdyn_ctx* ctx, sdyn_track_view* out);
+/* rgbd_split steps: order[f*cap + j] = extraction index of entry j of frame f's tracked keypoint list, n[f] its length
+ * (N after UpdateFrame), n_static[f] = N_s.  HOST arrays ([nframes][cap], [nframes], [nframes]); synchronises the stream. */
+int sdyn_track_frame_order(sdyn_ctx* ctx, int nframes, int32_t* order, int32_t* n, int32_t* n_static, int cap);
 /* D2H of the step results next to sdyn_fetch_results (host arrays sized [nframes][cap] / [nframes][4]). */
 int sdyn_track_fetch(sdyn_ctx* ctx, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dyn_mask,
                      int32_t* counts, int cap, void* stream);

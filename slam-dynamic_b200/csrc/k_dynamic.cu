@@ -12,13 +12,14 @@ namespace sdyn {
 __global__ void __launch_bounds__(256)
 k_box_mask(const sdyn_keypoint* __restrict__ keys, const int32_t* __restrict__ nPtr, int n, int keyStride,
            const double* __restrict__ boxes, const int32_t* __restrict__ nBoxesPtr, int nboxes, int boxStride,
-           uint64_t* __restrict__ mask)
+           uint64_t* __restrict__ mask, size_t boxPitch, size_t nbPitch)
 {
     __shared__ double sb[64 * 4];
     const int job = blockIdx.y;
-    const int nb = min(nBoxesPtr ? nBoxesPtr[job] : nboxes, 64);
+    const int nb = min(nBoxesPtr ? *frame_part(nBoxesPtr, job, 4, (long long)nbPitch) : nboxes, 64);
     const int nk = nPtr ? min(nPtr[job], n) : n;
-    for (int i = threadIdx.x; i < nb * 4; i += blockDim.x) sb[i] = boxes[(size_t)job * boxStride * 4 + i];
+    const double* jb = frame_part(boxes, job, (size_t)boxStride * 32, (long long)boxPitch);
+    for (int i = threadIdx.x; i < nb * 4; i += blockDim.x) sb[i] = jb[i];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nk) return;
@@ -127,11 +128,11 @@ k_box_pairs(const BoxPairJob* __restrict__ jobs, const float* __restrict__ M, co
 
 cudaError_t launch_box_mask(const sdyn_keypoint* dKeys, const int32_t* nPtr, int n, int keyStride,
                             const double* dBoxes, const int32_t* nBoxesPtr, int nboxes, int boxStride,
-                            uint64_t* dMask, int njobs, cudaStream_t st)
+                            uint64_t* dMask, int njobs, cudaStream_t st, size_t boxPitch, size_t nbPitch)
 {
     if (n <= 0 || njobs <= 0) return cudaSuccess;
     dim3 grid((n + 255) / 256, njobs);
-    k_box_mask<<<grid, 256, 0, st>>>(dKeys, nPtr, n, keyStride, dBoxes, nBoxesPtr, nboxes, boxStride, dMask);
+    k_box_mask<<<grid, 256, 0, st>>>(dKeys, nPtr, n, keyStride, dBoxes, nBoxesPtr, nboxes, boxStride, dMask, boxPitch, nbPitch);
     return cudaGetLastError();
 }
 

@@ -189,6 +189,25 @@ k_match_candidates(const MatchJob* __restrict__ jobs, int stageGrid, int stageDe
         for (int i = threadIdx.x; i < (int)(sizeof(MatchJob) / 4); i += NT) dstw[i] = srcw[i];
     }
     __syncthreads();
+    if (sJ.pose && threadIdx.x == 0) {
+        /* per-frame pose of the batched front end: Tcw, and bForward / bBackward of ORBmatcher.cc:1495-1506 —
+         * twc = -Rcw^T tcw (transposed operand: double accumulation), tlc = Rlw twc + tlw (3x3 float path) */
+        const float* Tc = sJ.pose; const float* Tl = sJ.pose + 12;
+        float twc[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            double a = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a = __dadd_rn(a, __dmul_rn((double)Tc[4 * k + r], (double)Tc[4 * k + 3]));
+            twc[r] = (float)(-1.0 * a);
+        }
+        const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tl[8], twc[0]), __fmul_rn(Tl[9], twc[1])), __fmul_rn(Tl[10], twc[2])), Tl[11]);
+        sJ.forward = (tz > sJ.mb) && !sJ.mono;
+        sJ.backward = (-tz > sJ.mb) && !sJ.mono;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) sJ.Tcw[k] = Tc[k];
+    }
+    if (sJ.pose) __syncthreads();
     const MatchJob& J = sJ;
     const int lane = threadIdx.x & 31;
     const int nq = job_nq(J);

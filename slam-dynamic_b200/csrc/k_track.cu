@@ -8,6 +8,7 @@
  * join of the s-th SURVIVING box and the keypoints of the s-th OCCUPIED box, exactly as the reference does.
  */
 #include "match_internal.h"
+#include <algorithm>
 
 namespace sdyn {
 
@@ -42,10 +43,11 @@ k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, co
             const uint8_t* __restrict__ desc,
             const int32_t* __restrict__ count, int cap, const uint64_t* __restrict__ mask,
             const unsigned long long* __restrict__ has, int32_t* __restrict__ boxList, int32_t* __restrict__ nnQ,
-            int32_t* __restrict__ nnT, int nnTStride, uint8_t* __restrict__ readmit, int32_t* __restrict__ staticExit)
+            int32_t* __restrict__ nnT, int nnTStride, int32_t* __restrict__ readmit, int32_t* __restrict__ staticExit)
 {
     const int s = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
-    const int nb = min(in.n_boxes[f], 64);
+    const long long P = in.frame_pitch;
+    const int nb = min(*frame_part(in.n_boxes, f, 4, P), 64);
     if (s >= nb) return;
     __shared__ int sSurv, sOcc, sCount, sBase, warpCnt[BS / 32], sStatic;
     if (tid == 0) {
@@ -66,7 +68,7 @@ k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, co
     __syncthreads();
     const int surv = sSurv, occ = sOcc;
     if (surv < 0 || occ < 0) return;                 /* slot beyond objects.size(), or no keypoints in it */
-    const int r = in.ref_box[f * 64 + surv];
+    const int r = frame_part(in.ref_box, f, 64 * 4, P)[surv];
     if (r < 0) return;                               /* box id not present in the reference frame */
     const int n = min(count[f], cap);
     /* classifyF reads mvdynKeysUn (Tracking.cc:1129-1131: undistorted points); the box test above used mvKeys (Frame.cc:562) */
@@ -92,10 +94,11 @@ k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, co
         __syncthreads();
     }
     const int nq = sBase;
-    const int to = in.ref_off[f * 65 + r], nt = min(in.ref_off[f * 65 + r + 1] - to, nnTStride);
+    const int32_t* refOff = frame_part(in.ref_off, f, 65 * 4, P);
+    const int to = refOff[r], nt = min(refOff[r + 1] - to, nnTStride);
     if (nq == 0 || nt == 0) return;                  /* mdynDescriptors[..].cols == 0 */
-    const uint8_t* TD = in.ref_desc + ((size_t)f * in.ref_stride + to) * 32;
-    const float* TX = in.ref_xy + ((size_t)f * in.ref_stride + to) * 2;
+    const uint8_t* TD = frame_part(in.ref_desc, f, (size_t)in.ref_stride * 32, P) + (size_t)to * 32;
+    const float* TX = frame_part(in.ref_xy, f, (size_t)in.ref_stride * 8, P) + (size_t)to * 2;
 
     /* BFMatcher(NORM_HAMMING, crossCheck = true) */
     for (int i = tid; i < nq; i += BS) {
@@ -115,7 +118,7 @@ k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, co
     /* classifyF on the mutual matches; num0 = #static */
     float m[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) m[k] = in.fmat[f * 9 + k];
+    for (int k = 0; k < 9; ++k) m[k] = frame_part(in.fmat, f, 36, P)[k];
     int nmatch = 0, nstatic = 0;
     for (int i = tid; i < nq; i += BS) {
         const int tr = nq_[i];
@@ -145,12 +148,12 @@ k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, co
     /* gates of Tracking::Separate (:1125, :1151) */
     if (good < 3 || (double)good < 0.2 * (double)nq) return;
     for (int i = tid; i < nq; i += BS)
-        if (nq_[i] <= -2) readmit[(size_t)f * cap + list[i]] = 1;       /* dynStatus[slot][m] != -1 */
+        if (nq_[i] <= -2) atomicMax(&readmit[(size_t)f * cap + list[i]], 64 - s);   /* dynStatus[slot][m] != -1; keeps the FIRST slot */
     if (tid == 0 && (double)num0 > fmax(1.0, 0.2 * (double)good)) atomicOr(&staticExit[f], 1);
 }
 
 __global__ void __launch_bounds__(256)
-k_dyn_finalize(const uint64_t* __restrict__ mask, const uint8_t* __restrict__ readmit,
+k_dyn_finalize(const uint64_t* __restrict__ mask, const int32_t* __restrict__ readmit,
                const int32_t* __restrict__ staticExit, const int32_t* __restrict__ count, int cap,
                uint8_t* __restrict__ dynMask, int32_t* __restrict__ counts)
 {
@@ -173,15 +176,159 @@ k_dyn_finalize(const uint64_t* __restrict__ mask, const uint8_t* __restrict__ re
 
 cudaError_t launch_dyn_stage(const sdyn_track_inputs& in, const sdyn_keypoint* kp, const sdyn_keypoint* kpUn, const uint8_t* desc, const int32_t* count,
                              int cap, uint64_t* mask, unsigned long long* has, int32_t* boxList, int32_t* nnQ, int32_t* nnT,
-                             int nnTStride, uint8_t* readmit, int32_t* staticExit, uint8_t* dynMask, int32_t* counts,
+                             int nnTStride, int32_t* readmit, int32_t* staticExit, uint8_t* dynMask, int32_t* counts,
                              int nframes, cudaStream_t st)
 {
-    cudaError_t e = launch_box_mask(kp, count, cap, cap, in.boxes, in.n_boxes, 64, 64, mask, nframes, st);
+    cudaError_t e = launch_box_mask(kp, count, cap, cap, in.boxes, in.n_boxes, 64, 64, mask, nframes, st,
+                                    in.frame_pitch > 0 ? (size_t)in.frame_pitch : 0, in.frame_pitch > 0 ? (size_t)in.frame_pitch : 0);
     if (e != cudaSuccess) return e;
     k_box_occupancy<<<nframes, 256, 0, st>>>(mask, count, cap, has);
     dim3 grid(64, nframes);
     k_box_stage<<<grid, BS, 0, st>>>(in, kp, kpUn, desc, count, cap, mask, has, boxList, nnQ, nnT, nnTStride, readmit, staticExit);
     k_dyn_finalize<<<nframes, 256, 0, st>>>(mask, readmit, staticExit, count, cap, dynMask, counts);
+    return cudaGetLastError();
+}
+
+/* ---- RGB-D-constructor form: the frame the reference tracks with ------------------------------------------------------
+ * Frame::firstSeparate reorders the keypoints "static first" and the tail split moves the in-box ones out of the frame
+ * (src/Frame.cc:555-604, 337-367); after Tracking::Separate, Frame::UpdateFrame appends the re-admitted ones (:607-641) in
+ * push order: box slot ascending, position in the box's list ascending, first occurrence wins (the class_id set).  A box
+ * list is in extraction order, so the push order is the lexicographic order of (first re-admitting slot, extraction index).
+ * One CTA per frame writes that list: order[], keypoints (class_id = extraction index for re-admitted ones, Frame.cc:565-568),
+ * undistorted keypoints, descriptors, N and N_s. */
+constexpr int FC = 256;
+
+__global__ void __launch_bounds__(FC)
+k_frame_compact(const sdyn_keypoint* __restrict__ kp, const sdyn_keypoint* __restrict__ kpUn, const uint8_t* __restrict__ desc,
+                const int32_t* __restrict__ count, int cap, const uint64_t* __restrict__ mask, const int32_t* __restrict__ readmit,
+                const int32_t* __restrict__ staticExit, sdyn_keypoint* __restrict__ fKp, sdyn_keypoint* __restrict__ fKpUn,
+                uint8_t* __restrict__ fDesc, int32_t* __restrict__ fOrder, int32_t* __restrict__ fCount, int32_t* __restrict__ fStatic)
+{
+    extern __shared__ int32_t sR[];                 /* re-admitted: idx[cap], slot[cap] */
+    __shared__ int warpCnt[FC / 32], sBase;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = min(count[f], cap);
+    const uint64_t* M = mask + (size_t)f * cap;
+    const int32_t* RA = readmit + (size_t)f * cap;
+    int32_t* ord = fOrder + (size_t)f * cap;
+    const bool upd = staticExit[f] != 0;
+    int32_t* rIdx = sR; int32_t* rSlot = sR + cap;
+    /* two stable compactions in extraction order: pass 0 = outside every box, pass 1 = re-admitted */
+    int ns = 0, nr = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (tid == 0) sBase = 0;
+        __syncthreads();
+        if (pass == 1 && !upd) break;
+        for (int i0 = 0; i0 < n; i0 += FC) {
+            const int i = i0 + tid;
+            const bool ok = i < n && (pass == 0 ? M[i] == 0 : (M[i] != 0 && RA[i] != 0));
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) warpCnt[wid] = __popc(bal);
+            __syncthreads();
+            int pos = sBase;
+            for (int w = 0; w < wid; ++w) pos += warpCnt[w];
+            pos += __popc(bal & ((1u << lane) - 1));
+            if (ok) { if (pass == 0) ord[pos] = i; else { rIdx[pos] = i; rSlot[pos] = 64 - RA[i]; } }
+            __syncthreads();
+            if (tid == 0) { int t = 0; for (int w = 0; w < FC / 32; ++w) t += warpCnt[w]; sBase += t; }
+            __syncthreads();
+        }
+        if (pass == 0) ns = sBase; else nr = sBase;
+        __syncthreads();
+    }
+    /* rank of every re-admitted keypoint in (slot, index) order */
+    for (int t = tid; t < nr; t += FC) {
+        const int st = rSlot[t];
+        int rank = 0;
+        for (int u = 0; u < nr; ++u) rank += (rSlot[u] < st) || (rSlot[u] == st && u < t);
+        ord[ns + rank] = rIdx[t];
+    }
+    __syncthreads();
+    const int N = ns + nr;
+    if (tid == 0) { fCount[f] = N; fStatic[f] = ns; }
+    const sdyn_keypoint* K = kp + (size_t)f * cap; const sdyn_keypoint* KU = kpUn + (size_t)f * cap;
+    for (int j = tid; j < N; j += FC) {
+        const int src = ord[j];
+        sdyn_keypoint a = K[src], b = KU[src];
+        if (j >= ns) { a.class_id = src; b.class_id = src; }
+        fKp[(size_t)f * cap + j] = a;
+        if (fKpUn != fKp) fKpUn[(size_t)f * cap + j] = b;
+    }
+    const uint4* D = reinterpret_cast<const uint4*>(desc + (size_t)f * cap * 32);
+    uint4* FD = reinterpret_cast<uint4*>(fDesc + (size_t)f * cap * 32);
+    for (int w = tid; w < 2 * N; w += FC) FD[w] = D[2 * ord[w >> 1] + (w & 1)];
+}
+
+cudaError_t launch_frame_compact(const sdyn_keypoint* kp, const sdyn_keypoint* kpUn, const uint8_t* desc, const int32_t* count, int cap,
+                                 const uint64_t* mask, const int32_t* readmit, const int32_t* staticExit, sdyn_keypoint* fKp,
+                                 sdyn_keypoint* fKpUn, uint8_t* fDesc, int32_t* fOrder, int32_t* fCount, int32_t* fStatic, int nframes,
+                                 cudaStream_t st)
+{
+    const size_t smem = (size_t)cap * 8;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_frame_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_frame_compact<<<nframes, FC, smem, st>>>(kp, kpUn, desc, count, cap, mask, readmit, staticExit, fKp, fKpUn, fDesc, fOrder, fCount, fStatic);
+    return cudaGetLastError();
+}
+
+/* ---- resident query forms: materialise the searches' query records from ids + the MapPoint table --------------------
+ * blockIdx.y = frame; blockIdx.z = 0: LastFrame points (sdyn_last_point), 1: local-map points (sdyn_mappoint_query). */
+__global__ void __launch_bounds__(256)
+k_gather_queries(const sdyn_map_point* __restrict__ table, int tableCap,
+                 const int32_t* __restrict__ lastIds, const uint8_t* __restrict__ lastFlags, const int32_t* __restrict__ nLast, int lastStride,
+                 sdyn_last_point* __restrict__ gLast,
+                 const int32_t* __restrict__ mapIds, const sdyn_map_proj* __restrict__ mapProj, const int32_t* __restrict__ nMap, int mapStride,
+                 sdyn_mappoint_query* __restrict__ gMap, long long P)
+{
+    const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    if (blockIdx.z == 0) {
+        if (!lastIds || i >= min(nLast[f], lastStride)) return;          /* nLast: the resident LastFrame's own counts */
+        const size_t at = (size_t)f * lastStride + i;
+        const int id = frame_part(lastIds, f, (size_t)lastStride * 4, P)[i];
+        sdyn_last_point o;
+        const uint8_t fl = frame_part(lastFlags, f, (size_t)lastStride, P)[i];
+        const bool has = id >= 0 && id < tableCap;
+        o.has_mp = has; o.outlier = fl & SDYN_LP_OUTLIER ? 1 : 0; o.obs_positive = fl & SDYN_LP_OBS_POSITIVE ? 1 : 0; o.pad = 0;
+        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+        o.world[0] = o.world[1] = o.world[2] = 0.f;
+        if (has) {
+            const sdyn_map_point* p = table + id;
+            o.world[0] = p->world[0]; o.world[1] = p->world[1]; o.world[2] = p->world[2];
+            d0 = *reinterpret_cast<const uint4*>(p->desc); d1 = *reinterpret_cast<const uint4*>(p->desc + 16);
+        }
+        uint32_t* w = reinterpret_cast<uint32_t*>(o.desc);
+        w[0] = d0.x; w[1] = d0.y; w[2] = d0.z; w[3] = d0.w; w[4] = d1.x; w[5] = d1.y; w[6] = d1.z; w[7] = d1.w;
+        gLast[at] = o;
+    } else {
+        if (!mapIds || i >= min(*frame_part(nMap, f, 4, P), mapStride)) return;
+        const size_t at = (size_t)f * mapStride + i;
+        const int id = frame_part(mapIds, f, (size_t)mapStride * 4, P)[i];
+        const sdyn_map_proj pr = frame_part(mapProj, f, (size_t)mapStride * sizeof(sdyn_map_proj), P)[i];
+        sdyn_mappoint_query o;
+        o.proj_x = pr.proj_x; o.proj_y = pr.proj_y; o.proj_xr = pr.proj_xr; o.view_cos = pr.view_cos; o.level = pr.level;
+        const bool has = id >= 0 && id < tableCap;
+        o.track_in_view = has ? pr.track_in_view : 0; o.bad = pr.bad; o.obs_positive = pr.obs_positive; o.pad = 0;
+        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+        if (has) { d0 = *reinterpret_cast<const uint4*>(table[id].desc); d1 = *reinterpret_cast<const uint4*>(table[id].desc + 16); }
+        uint32_t* w = reinterpret_cast<uint32_t*>(o.desc);
+        w[0] = d0.x; w[1] = d0.y; w[2] = d0.z; w[3] = d0.w; w[4] = d1.x; w[5] = d1.y; w[6] = d1.z; w[7] = d1.w;
+        gMap[at] = o;
+    }
+}
+
+cudaError_t launch_gather_queries(const sdyn_map_point* table, int tableCap, const int32_t* lastIds, const uint8_t* lastFlags,
+                                  const int32_t* nLast, int lastStride, sdyn_last_point* gLast, const int32_t* mapIds,
+                                  const sdyn_map_proj* mapProj, const int32_t* nMap, int mapStride, sdyn_mappoint_query* gMap,
+                                  int nframes, long long framePitch, cudaStream_t st)
+{
+    const int m = std::max(lastIds ? lastStride : 0, mapIds ? mapStride : 0);
+    if (m == 0) return cudaSuccess;
+    dim3 grid((m + 255) / 256, nframes, 2);
+    k_gather_queries<<<grid, 256, 0, st>>>(table, tableCap, lastIds, lastFlags, nLast, lastStride, gLast, mapIds, mapProj, nMap, mapStride, gMap, framePitch);
     return cudaGetLastError();
 }
 

@@ -53,6 +53,9 @@ struct MatchJob {
     int strictLow;                   /* BOW: accept best < TH_LOW (KeyFrame-KeyFrame overload) instead of <= (KeyFrame-Frame) */
     int assignBase;                  /* value written to assign[] = assignBase + query index (FRAME / MAP) */
     float Tcw[12], fx, fy, cx, cy, bf;
+    /* FRAME, batched front end: per-frame pose table entry (24 floats: rows 0..2 of CurrentFrame.mTcw, then of LastFrame.mTcw).
+     * When set, Tcw / forward / backward above are derived from it on the device (ORBmatcher.cc:1495-1506). */
+    const float* pose; float mb; int mono;
     /* state / outputs */
     int32_t* assign;                 /* FRAME/MAP/BOW: per searched keypoint; INIT: matches12 per query */
     uint8_t* locked;                 /* FRAME/MAP */
@@ -80,6 +83,14 @@ cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQue
 /* mode: all jobs of one launch share a mode; maxN / maxQ: largest MatchJob::n / ::nq of the launch */
 cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st);
 
+/* per-frame array of the batched front end: frame f's part of array `base` (array-major: `bytes` apart; frame-major records:
+ * `pitch` apart — sdyn_track_inputs::frame_pitch) */
+template <class T>
+__host__ __device__ __forceinline__ const T* frame_part(const T* base, int f, size_t bytes, long long pitch)
+{
+    return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + (size_t)f * (pitch > 0 ? (size_t)pitch : bytes));
+}
+
 /* dynamic-keypoint kernels (k_dynamic.cu) */
 struct BoxPairJob {
     int nq, nt;
@@ -88,14 +99,25 @@ struct BoxPairJob {
     int32_t* nnQ; int32_t* dQ; int32_t* nnT;          /* scratch: nq, nq, nt */
     int32_t* outQuery; int32_t* outTrain; int32_t* outDist; int32_t* outFalseDyn; int32_t* outCount;
 };
+/* boxPitch / nbPitch: bytes between two jobs' box arrays / box counts (0 = boxStride * 32 / 4) */
 cudaError_t launch_box_mask(const sdyn_keypoint* dKeys, const int32_t* nPtr, int n, int keyStride,
                             const double* dBoxes, const int32_t* nBoxesPtr, int nboxes, int boxStride,
-                            uint64_t* dMask, int njobs, cudaStream_t st);
+                            uint64_t* dMask, int njobs, cudaStream_t st, size_t boxPitch = 0, size_t nbPitch = 0);
 /* kp = mvKeys (box containment, Frame.cc:562), kpUn = mvKeysUn (classifyF coordinates, Tracking.cc:1129-1131) */
 cudaError_t launch_dyn_stage(const sdyn_track_inputs& in, const sdyn_keypoint* kp, const sdyn_keypoint* kpUn, const uint8_t* desc, const int32_t* count,
                              int cap, uint64_t* mask, unsigned long long* has, int32_t* boxList, int32_t* nnQ, int32_t* nnT,
-                             int nnTStride, uint8_t* readmit, int32_t* staticExit, uint8_t* dynMask, int32_t* counts,
+                             int nnTStride, int32_t* readmit, int32_t* staticExit, uint8_t* dynMask, int32_t* counts,
                              int nframes, cudaStream_t st);
+/* RGB-D-constructor form of the tracked frame (k_track.cu) */
+cudaError_t launch_frame_compact(const sdyn_keypoint* kp, const sdyn_keypoint* kpUn, const uint8_t* desc, const int32_t* count, int cap,
+                                 const uint64_t* mask, const int32_t* readmit, const int32_t* staticExit, sdyn_keypoint* fKp,
+                                 sdyn_keypoint* fKpUn, uint8_t* fDesc, int32_t* fOrder, int32_t* fCount, int32_t* fStatic, int nframes,
+                                 cudaStream_t st);
+/* resident query forms: ids + MapPoint table -> the searches' query records (k_track.cu) */
+cudaError_t launch_gather_queries(const sdyn_map_point* table, int tableCap, const int32_t* lastIds, const uint8_t* lastFlags,
+                                  const int32_t* nLast, int lastStride, sdyn_last_point* gLast, const int32_t* mapIds,
+                                  const sdyn_map_proj* mapProj, const int32_t* nMap, int mapStride, sdyn_mappoint_query* gMap,
+                                  int nframes, long long framePitch, cudaStream_t st);
 cudaError_t launch_box_pairs(const BoxPairJob* dJobs, int njobs, const float* dM, const float* dMinv, int mode,
                              cudaStream_t st);
 

@@ -303,6 +303,13 @@ class Extractor:
     def launch_count(self):
         return lib().sdyn_launch_count(self._h)
 
+    def stream_handle(self):
+        """The context's cudaStream_t as an integer (sdyn_stream)."""
+        L = lib()
+        L.sdyn_stream.restype = C.c_void_p
+        L.sdyn_stream.argtypes = [C.c_void_p]
+        return L.sdyn_stream(self._h) or 0
+
 
 # ---------------------------------------------------------------------------------------------------
 # ORBmatcher / dynamic-keypoint entry points
@@ -625,43 +632,122 @@ class TrackInputsC(C.Structure):
                 ("fmat", C.c_void_p),
                 ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float), ("b", C.c_float),
-                ("tcw_cur", C.c_float * 12), ("tcw_last", C.c_float * 12),
                 ("th_frame", C.c_float), ("th_map", C.c_float), ("nnratio_map", C.c_float),
-                ("mono", C.c_int32), ("check_orientation", C.c_int32)]
+                ("mono", C.c_int32), ("check_orientation", C.c_int32),
+                ("poses", C.c_void_p),
+                ("map", C.c_void_p), ("last_ids", C.c_void_p), ("last_flags", C.c_void_p),
+                ("map_ids", C.c_void_p), ("map_proj", C.c_void_p),
+                ("rgbd_split", C.c_int32), ("frame_pitch", C.c_int64)]
 
 
 TRACK_ARRAYS = ["last_points", "last_keys", "last_keys_un", "n_last", "map_points", "n_map", "boxes", "n_boxes",
-                "ref_box", "ref_desc", "ref_xy", "ref_off", "fmat"]
+                "ref_box", "ref_desc", "ref_xy", "ref_off", "fmat", "poses", "last_ids", "last_flags", "map_ids", "map_proj"]
+FORM_SEPARATE_KEYS_UN, FORM_RESIDENT_LAST, FORM_RESIDENT_MAP = 1, 2, 4
+LP_OUTLIER, LP_OBS_POSITIVE = 1, 2
+MAP_POINT_DTYPE = np.dtype([("world", "<f4", (3,)), ("normal", "<f4", (3,)), ("min_distance", "<f4"), ("max_distance", "<f4"),
+                            ("desc", "u1", (32,))])
+MAP_PROJ_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
+                           ("track_in_view", "u1"), ("bad", "u1"), ("obs_positive", "u1"), ("pad", "u1")])
+assert MAP_POINT_DTYPE.itemsize == 64 and MAP_PROJ_DTYPE.itemsize == 24
 
 
-def track_inputs(ptrs, frame0, strides, params):
-    """ptrs: {name: (device base address, bytes per frame)}; frame0: first frame of the batch in those arrays."""
+def track_inputs(ptrs, frame0, strides, params, map_table=None, rgbd_split=False, frame_pitch=0):
+    """ptrs: {name: (base address, bytes per frame)}; frame0: first frame of the batch in those arrays.  Arrays missing from
+    `ptrs` stay NULL (that is how the resident forms are selected: no last_points / map_points, but last_ids / map_ids).
+    frame_pitch > 0: frame-major records (every array's frames are frame_pitch bytes apart)."""
     t = TrackInputsC()
     for name in TRACK_ARRAYS:
-        base, per_frame = ptrs[name]
-        setattr(t, name, base + frame0 * per_frame)
+        if name in ptrs and ptrs[name] is not None:
+            base, per_frame = ptrs[name]
+            setattr(t, name, base + frame0 * (frame_pitch if frame_pitch else per_frame))
+    t.frame_pitch = int(frame_pitch)
     t.last_stride, t.map_stride, t.ref_stride = strides
     for k, v in params.items():
         if k in ("tcw_cur", "tcw_last"):
-            arr = getattr(t, k)
-            for i in range(12):
-                arr[i] = float(v[i])
-        else:
-            setattr(t, k, v)
+            continue                         # per-frame now: the "poses" array
+        setattr(t, k, v)
+    if map_table is not None:
+        t.map = map_table._h
+    t.rgbd_split = int(bool(rgbd_split))
     return t
 
 
-def track_input_layout(nframes, strides, separate_keys_un=False):
+def track_input_layout(nframes, strides, forms=0):
     """sdyn_track_input_layout: ({array name: offset}, block bytes) of the single-copy host staging block."""
     L = lib()
     L.sdyn_track_input_layout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t * len(TRACK_ARRAYS)),
                                           C.POINTER(C.c_size_t)]
     offs, total = (C.c_size_t * len(TRACK_ARRAYS))(), C.c_size_t()
-    rc = L.sdyn_track_input_layout(nframes, strides[0], strides[1], strides[2], int(bool(separate_keys_un)), C.byref(offs),
-                                   C.byref(total))
+    rc = L.sdyn_track_input_layout(nframes, strides[0], strides[1], strides[2], int(forms), C.byref(offs), C.byref(total))
     if rc != 0:
         raise SdynError(rc, "sdyn_track_input_layout: bad argument")
     return dict(zip(TRACK_ARRAYS, [int(o) for o in offs])), int(total.value)
+
+
+def track_record_layout(strides, forms=0):
+    """sdyn_track_record_layout: ({array name: offset inside one frame's record}, record bytes)."""
+    L = lib()
+    L.sdyn_track_record_layout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t * len(TRACK_ARRAYS)), C.POINTER(C.c_size_t)]
+    offs, pitch = (C.c_size_t * len(TRACK_ARRAYS))(), C.c_size_t()
+    rc = L.sdyn_track_record_layout(strides[0], strides[1], strides[2], int(forms), C.byref(offs), C.byref(pitch))
+    if rc != 0:
+        raise SdynError(rc, "sdyn_track_record_layout: bad argument")
+    return dict(zip(TRACK_ARRAYS, [int(o) for o in offs])), int(pitch.value)
+
+
+def pack_records(arrays, strides, forms, out=None):
+    """Frame-major record pool from per-array host arrays ([nframes, ...] each): -> (uint8 [nframes, pitch], layout, pitch)."""
+    layout, pitch = track_record_layout(strides, forms)
+    n = len(next(iter(arrays.values())))
+    pool = np.zeros((n, pitch), np.uint8) if out is None else out
+    for name in TRACK_ARRAYS:
+        if name not in arrays:
+            continue
+        rows = arrays[name].view(np.uint8).reshape(n, -1)
+        pool[:, layout[name]:layout[name] + rows.shape[1]] = rows
+    return pool, layout, pitch
+
+
+class MapTable:
+    """Device-resident MapPoint table (sdyn_map_*): id -> world position, normal, scale-invariance distances, descriptor."""
+
+    def __init__(self, capacity, device=0):
+        L = lib()
+        L.sdyn_map_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.sdyn_map_destroy.argtypes = [C.c_void_p]
+        L.sdyn_map_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        h = C.c_void_p()
+        rc = L.sdyn_map_create(device, capacity, C.byref(h))
+        if rc != 0:
+            raise SdynError(rc, "sdyn_map_create")
+        self._h, self.capacity = h, capacity
+
+    def update(self, first_id, points, stream=None):
+        pts = np.ascontiguousarray(points, MAP_POINT_DTYPE)
+        rc = lib().sdyn_map_update(self._h, first_id, len(pts), pts.ctypes.data, C.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise SdynError(rc, "sdyn_map_update")
+        self._keep = pts                     # the copy is asynchronous on pinned memory
+
+    def close(self):
+        if self._h:
+            lib().sdyn_map_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def track_frame_order(ex, nframes):
+    """rgbd_split steps: (order [nframes, cap], N [nframes], N_s [nframes]) of the tracked keypoint lists."""
+    L = lib()
+    L.sdyn_track_frame_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    order = np.zeros((nframes, ex.cap), np.int32); n = np.zeros(nframes, np.int32); ns = np.zeros(nframes, np.int32)
+    ex._check(L.sdyn_track_frame_order(ex._h, nframes, order.ctypes.data, n.ctypes.data, ns.ctypes.data, ex.cap))
+    return order, n, ns
 
 
 def _bind_track(L):

@@ -38,9 +38,10 @@ def flip_bits(desc, r, nbits):
     return d
 
 
-def last_points(last_keys, last_desc, shift, cam=KITTI_CAM, seed=0, p_mp=0.85, p_outlier=0.05, p_obs=0.9, noise_bits=6):
+def last_points(last_keys, last_desc, shift, cam=KITTI_CAM, seed=0, p_mp=0.85, p_outlier=0.05, p_obs=0.9, noise_bits=6, tcw=None):
     """LastFrame map points: back-project every last-frame keypoint at a seeded depth so that, with the
-    current pose = identity, it projects onto its position in the current frame (content shifted by `shift`)."""
+    current pose `tcw` (identity rotation + translation; default identity), it projects onto its position in the current
+    frame (content shifted by `shift`)."""
     r = rng_for(seed + 101)
     n = len(last_keys)
     lp = np.zeros(n, pysdyn.LASTPOINT_DTYPE)
@@ -55,6 +56,8 @@ def last_points(last_keys, last_desc, shift, cam=KITTI_CAM, seed=0, p_mp=0.85, p
     lp["world"][:, 2] = z
     behind = r.random(n) < 0.02
     lp["world"][behind, 2] *= -1                              # a few points behind the camera (invzc < 0)
+    if tcw is not None:                                       # x3Dc = x3Dw + t  ->  x3Dw = x3Dc - t
+        lp["world"] -= np.asarray(tcw, np.float32).reshape(3, 4)[:, 3]
     lp["desc"] = flip_bits(last_desc, r, r.integers(0, noise_bits + 1, n))
     return lp
 
@@ -117,8 +120,17 @@ def translation_fmat(dx, dy):
     return np.float32([[0, 0, dy], [0, 0, -dx], [-dy, dx, 0]])
 
 
+def frame_pose(i):
+    """Pose pair of frame i of a synthetic sequence: the camera advances, retreats or stands still along z in turn, so the
+    forward / backward / neutral level rules of SearchByProjection(cur, last) (ORBmatcher.cc:1505-1506) all occur in a batch
+    and every frame of a batch has its own pose."""
+    cur = np.eye(4, dtype=np.float32)[:3].copy(); last = np.eye(4, dtype=np.float32)[:3].copy()
+    cur[:, 3] = [0.01 * (i % 5), -0.02 * (i % 3), (0.0, 1.5, -1.5, 0.25)[i % 4]]
+    return np.concatenate([cur.reshape(12), last.reshape(12)])
+
+
 def build_track_batch(kd, seq_seed, first_index, W, H, nrect, nlevels, last_stride, map_stride, ref_stride,
-                      n_map=3000, seed=0):
+                      n_map=3000, seed=0, offsets=None, time=None):
     """kd: list of (keys, desc) for frames first_index-1 .. first_index+B-1 of one sequence (B = len(kd)-1).
     Returns dict of numpy arrays laid out as sdyn_track_inputs expects ([B, stride, ...])."""
     B = len(kd) - 1
@@ -136,22 +148,26 @@ def build_track_batch(kd, seq_seed, first_index, W, H, nrect, nlevels, last_stri
         "ref_xy": np.zeros((B, ref_stride, 2), np.float32),
         "ref_off": np.zeros((B, 65), np.int32),
         "fmat": np.zeros((B, 9), np.float32),
+        "poses": np.zeros((B, 24), np.float32),
     }
+    offsets = offsets or sequence_offsets
+    time = time or sequence_time
     for f in range(B):
         i = first_index + f
         (k0, d0), (k1, d1) = kd[f], kd[f + 1]
-        ox0, oy0 = sequence_offsets(i - 1); ox1, oy1 = sequence_offsets(i)
+        out["poses"][f] = frame_pose(i)
+        ox0, oy0 = offsets(i - 1); ox1, oy1 = offsets(i)
         shift = (ox1 - ox0, oy1 - oy0)
         n0 = min(len(k0), last_stride)
-        out["last_points"][f, :n0] = last_points(k0[:n0], d0[:n0], shift, seed=seed + 31 * i)
+        out["last_points"][f, :n0] = last_points(k0[:n0], d0[:n0], shift, seed=seed + 31 * i, tcw=out["poses"][f, :12])
         out["last_keys"][f, :n0] = k0[:n0]; out["last_keys_un"][f, :n0] = k0[:n0]
         out["n_last"][f] = n0
         nm = min(n_map, map_stride)
         out["map_points"][f, :nm] = map_queries(k1, d1, nlevels, seed=seed + 57 * i, count=nm)
         out["n_map"][f] = nm
         # detection boxes of the current frame and of the reference (= previous) frame, joined on rectangle id
-        b1, id1 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox1, oy1, sequence_time(i), margin=8)
-        b0, id0 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox0, oy0, sequence_time(i - 1), margin=8)
+        b1, id1 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox1, oy1, time(i), margin=8)
+        b0, id0 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox0, oy0, time(i - 1), margin=8)
         nb = min(len(b1), 62)
         out["boxes"][f, :nb] = b1[:nb]
         out["boxes"][f, nb] = [W + 50.0, H + 50.0, 10.0, 10.0]      # a detection without keypoints (gets erased)
@@ -175,10 +191,30 @@ def build_track_batch(kd, seq_seed, first_index, W, H, nrect, nlevels, last_stri
 
 
 def track_params(W, H, cam=KITTI_CAM, th_frame=7.0, th_map=3.0, nnratio_map=0.8, mono=0, check_orientation=1):
-    eye = np.eye(4, dtype=np.float32)[:3].reshape(12)
     return dict(min_x=0.0, min_y=0.0, max_x=float(W), max_y=float(H), fx=cam["fx"], fy=cam["fy"], cx=cam["cx"],
-                cy=cam["cy"], bf=cam["bf"], b=cam["bf"] / cam["fx"], tcw_cur=eye, tcw_last=eye, th_frame=th_frame,
+                cy=cam["cy"], bf=cam["bf"], b=cam["bf"] / cam["fx"], th_frame=th_frame,
                 th_map=th_map, nnratio_map=nnratio_map, mono=mono, check_orientation=check_orientation)
+
+
+def resident_forms(arrays):
+    """The same step inputs in the resident forms of sdyn_track_inputs: one MapPoint table (every LastFrame point and every
+    local-map point of every frame gets an id) plus, per frame, ids / flag bytes / projection records.
+    -> (table [MAP_POINT_DTYPE], {last_ids, last_flags, map_ids, map_proj})."""
+    lp, mp = arrays["last_points"], arrays["map_points"]
+    B, ls = lp.shape; ms = mp.shape[1]
+    table = np.zeros(B * (ls + ms), pysdyn.MAP_POINT_DTYPE)
+    out = {"last_ids": np.full((B, ls), -1, np.int32), "last_flags": np.zeros((B, ls), np.uint8),
+           "map_ids": np.full((B, ms), -1, np.int32), "map_proj": np.zeros((B, ms), pysdyn.MAP_PROJ_DTYPE)}
+    for f in range(B):
+        base = f * (ls + ms)
+        table["world"][base:base + ls] = lp["world"][f]; table["desc"][base:base + ls] = lp["desc"][f]
+        out["last_ids"][f] = np.where(lp["has_mp"][f] != 0, base + np.arange(ls), -1)
+        out["last_flags"][f] = (lp["outlier"][f] != 0) * pysdyn.LP_OUTLIER + (lp["obs_positive"][f] != 0) * pysdyn.LP_OBS_POSITIVE
+        table["desc"][base + ls:base + ls + ms] = mp["desc"][f]
+        out["map_ids"][f] = base + ls + np.arange(ms)
+        for name in ("proj_x", "proj_y", "proj_xr", "view_cos", "level", "track_in_view", "bad", "obs_positive"):
+            out["map_proj"][name][f] = mp[name][f]
+    return table, out
 
 
 def stereo_pair(cfg, idx, disparities=(5, 11, 23), seq=0):

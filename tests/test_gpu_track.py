@@ -58,7 +58,7 @@ def test_track_batch_matches_oracle(cfg, B):
     hin = pysdyn.track_inputs(hptrs, 0, (last_stride, map_stride, ref_stride), params)
     # ... and so does the single-copy form: every array inside one block at sdyn_track_input_layout's offsets
     separate = not np.array_equal(arrays["last_keys"], arrays["last_keys_un"])
-    layout, total = pysdyn.track_input_layout(B, (last_stride, map_stride, ref_stride), separate)
+    layout, total = pysdyn.track_input_layout(B, (last_stride, map_stride, ref_stride), pysdyn.FORM_SEPARATE_KEYS_UN if separate else 0)
     block = np.full(total, 0xA5, np.uint8)
     pptrs = {}
     for k, v in arrays.items():
@@ -176,8 +176,140 @@ def test_track_partial_batch_and_single_search():
         F = scenario.frame_view(k, d, cpu.scale, W, H)
         F = pysdyn.FrameView(k, d, cpu.scale, (0.0, 0.0, float(W), float(H)),
                              cam=(scenario.KITTI_CAM["fx"], scenario.KITTI_CAM["fy"], scenario.KITTI_CAM["cx"], scenario.KITTI_CAM["cy"],
-                                  scenario.KITTI_CAM["bf"], scenario.KITTI_CAM["bf"] / scenario.KITTI_CAM["fx"]), tcw=params["tcw_cur"])
+                                  scenario.KITTI_CAM["bf"], scenario.KITTI_CAM["bf"] / scenario.KITTI_CAM["fx"]), tcw=arrays["poses"][f, :12])
         nm = int(arrays["n_map"][f])
         n2, ea, el = orc.match_projection_map(F, arrays["map_points"][f, :nm], params["th_map"], params["nnratio_map"], assign_base=0)
         assert c2[f, 0] == 0 and c2[f, 1] == n2 and np.array_equal(a2[f, :len(k)], ea) and np.array_equal(l2[f, :len(k)], el)
+    gpu.close()
+
+
+def _sequence(cfg, count):
+    W, H, nrect, nf, ini, mn = common.CONFIGS[cfg]
+    cid = common.CONFIG_ID[cfg]
+    seq_seed = 1000 * cid + 7
+    frames = np.stack([pysdyn.synth_frame(seq_seed, 1000 * cid + i, W, H, nrect, *scenario.sequence_offsets(i), scenario.sequence_time(i))
+                       for i in range(count)])
+    cpu = orc.Extractor(nf, 1.2, 8, ini, mn)
+    return W, H, nrect, nf, ini, mn, seq_seed, frames, cpu, [cpu(im) for im in frames]
+
+
+def _dev(arrays):
+    import torch
+    dev = {k: torch.from_numpy(v.view(np.uint8).reshape(v.shape[0], -1)).cuda() for k, v in arrays.items()}
+    return dev, {k: (t.data_ptr(), t.shape[1]) for k, t in dev.items()}
+
+
+def test_per_frame_poses_change_the_level_rule():
+    """Every frame of a batch carries its own pose pair: the forward / backward / neutral branch of ORBmatcher.cc:1505-1506 is
+    taken per frame on the device (one pose per batch cannot express independent sequences)."""
+    poses = np.stack([scenario.frame_pose(i) for i in range(1, 5)])
+    tz = poses[:, 11]
+    assert (tz > 1).any() and (tz < -1).any() and (np.abs(tz) < 0.5).any()
+
+
+@pytest.mark.parametrize("cfg,B", [("tum", 3)])
+def test_track_resident_forms_match_explicit(cfg, B):
+    """Resident LastFrame (this slot's previous step) + resident MapPoint table + per-frame ids / flags / projection records
+    give the results of the explicit arrays — device pointers and the host-buffer single-block upload."""
+    import torch
+    W, H, nrect, nf, ini, mn, seq_seed, frames, cpu, kd = _sequence(cfg, B + 2)
+    gpu = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=B)
+    last_stride, map_stride, ref_stride = gpu.cap, 1500, 512
+    strides = (last_stride, map_stride, ref_stride)
+    params = scenario.track_params(W, H)
+    a1 = scenario.build_track_batch(kd[:B + 1], seq_seed, 1, W, H, nrect, 8, *strides, n_map=1500, seed=3)
+    a2 = scenario.build_track_batch(kd[1:B + 2], seq_seed, 2, W, H, nrect, 8, *strides, n_map=1500, seed=3)
+    d1, p1 = _dev(a1); d2, p2 = _dev(a2)
+    f1 = torch.from_numpy(frames[1:B + 1]).cuda(); f2 = torch.from_numpy(frames[2:B + 2]).cuda()
+    # explicit reference run of step 2
+    pysdyn.track_batch_device(gpu, B, f2.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(p2, 0, strides, params))
+    want = [x.copy() for x in pysdyn.track_fetch(gpu, B)]
+    for f in range(B):                    # ... which is the oracle's result
+        k, d = kd[f + 2]
+        ea, el, em, ec = oracle_track.track_frame(k, d, cpu.scale, W, H, a2, f, params, last_stride)
+        assert np.array_equal(want[3][f], ec) and np.array_equal(want[0][f, :len(k)], ea) and np.array_equal(want[2][f, :len(k)], em)
+    # step 1 (explicit) leaves every slot's keypoints resident; step 2 then names its LastFrame points by id
+    table, res = scenario.resident_forms(a2)
+    mt = pysdyn.MapTable(len(table)); mt.update(0, table)
+    torch.cuda.synchronize()
+    dr, pr = _dev(res)
+    rp = {k: v for k, v in p2.items() if k not in ("last_points", "last_keys", "last_keys_un", "n_last", "map_points")}
+    rp.update(pr)
+    pysdyn.track_batch_device(gpu, B, f1.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(p1, 0, strides, params))
+    pysdyn.track_batch_device(gpu, B, f2.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(rp, 0, strides, params, map_table=mt))
+    got = pysdyn.track_fetch(gpu, B)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    assert want[3][:, 0].min() > 100 and want[3][:, 1].min() > 50
+    # host-buffer form: one pinned block with the resident layout (ids, flags, projection records, poses, boxes ...)
+    forms = pysdyn.FORM_RESIDENT_LAST | pysdyn.FORM_RESIDENT_MAP
+    layout, total = pysdyn.track_input_layout(B, strides, forms)
+    block = np.full(total, 0xA5, np.uint8)
+    hp = {}
+    host = dict(a2); host.update(res)
+    for name in pysdyn.TRACK_ARRAYS:
+        if name in ("last_points", "last_keys", "last_keys_un", "n_last", "map_points"):
+            continue
+        rows = host[name].view(np.uint8).reshape(host[name].shape[0], -1)[:B]
+        block[layout[name]:layout[name] + rows.size] = rows.reshape(-1)
+        hp[name] = (block.ctypes.data + layout[name], rows.shape[1])
+    outs = (np.zeros((B, gpu.cap), pysdyn.KP_DTYPE), np.zeros((B, gpu.cap, 32), np.uint8), np.zeros(B, np.int32),
+            np.zeros((B, gpu.cap), np.int32), np.zeros((B, gpu.cap), np.uint8), np.zeros((B, gpu.cap), np.uint8), np.zeros((B, 4), np.int32))
+    pysdyn.track_batch_device(gpu, B, f1.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(p1, 0, strides, params))
+    pysdyn.track_batch_host(gpu, np.ascontiguousarray(frames[2:B + 2]), pysdyn.track_inputs(hp, 0, strides, params, map_table=mt), outs)
+    assert np.array_equal(outs[6], want[3])
+    for f in range(B):
+        n = outs[2][f]
+        assert np.array_equal(outs[3][f, :n], want[0][f, :n]) and np.array_equal(outs[5][f, :n], want[2][f, :n])
+    mt.close(); gpu.close()
+
+
+@pytest.mark.parametrize("cfg,B,cam", [("tum", 3, None), ("tum", 2, "tum1")])
+def test_track_rgbd_split_matches_oracle(cfg, B, cam):
+    """BASELINE config 2 as the reference runs it (RGB-D constructor): firstSeparate moves the in-box keypoints out of the frame,
+    Separate + UpdateFrame re-admit the static ones, and the searches run on that list."""
+    import torch
+    W, H, nrect, nf, ini, mn, seq_seed, frames, cpu, kd = _sequence(cfg, B + 1)
+    gpu = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=B)
+    bounds = (0.0, 0.0, float(W), float(H))
+    und = lambda k: k
+    if cam:
+        fx, fy, cx, cy, dist = np.float32(517.306408), np.float32(516.469215), np.float32(318.643040), np.float32(255.313989), \
+            np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
+        gpu.set_camera(fx, fy, cx, cy, dist)
+        bounds = gpu.image_bounds(W, H)
+
+        def und(k):
+            xy = orc.undistort_points(np.stack([k["x"], k["y"]], 1), fx, fy, cx, cy, dist)
+            ku = k.copy(); ku["x"] = xy[:, 0]; ku["y"] = xy[:, 1]
+            return ku
+    last_stride, map_stride, ref_stride = gpu.cap, 1500, 512
+    strides = (last_stride, map_stride, ref_stride)
+    arrays = scenario.build_track_batch(kd, seq_seed, 1, W, H, nrect, 8, *strides, n_map=1500, seed=3)
+    for f in range(B):
+        n0 = int(arrays["n_last"][f])
+        arrays["last_keys_un"][f, :n0] = und(arrays["last_keys"][f, :n0])
+    params = scenario.track_params(W, H)
+    params.update(min_x=bounds[0], min_y=bounds[1], max_x=bounds[2], max_y=bounds[3])
+    dev, ptrs = _dev(arrays)
+    dframes = torch.from_numpy(frames[1:]).cuda()
+    pysdyn.track_batch_device(gpu, B, dframes.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(ptrs, 0, strides, params, rgbd_split=True))
+    kps, desc, counts = gpu.fetch(B)
+    assign, locked, mask, cnt = pysdyn.track_fetch(gpu, B)
+    order, n_all, n_static = pysdyn.track_frame_order(gpu, B)
+    readmitted = 0
+    for f in range(B):
+        k, d = kd[f + 1]
+        eo, ens, ea, el, em, ec, _ = oracle_track.track_frame_rgbd(k, d, cpu.scale, W, H, arrays, f, params, last_stride, keys_un=und(k),
+                                                                   bounds=bounds)
+        assert n_all[f] == len(eo) and n_static[f] == ens and np.array_equal(order[f, :len(eo)], eo)
+        assert np.array_equal(cnt[f], ec), (f, cnt[f], ec)
+        assert np.array_equal(assign[f, :len(eo)], ea) and np.array_equal(locked[f, :len(eo)], el)
+        assert np.array_equal(mask[f, :len(k)], em)
+        assert ens < len(k) and ec[0] > 80
+        readmitted += len(eo) - ens
+        # the split must matter: the stereo-constructor result differs
+        sa, _, _, sc = oracle_track.track_frame(k, d, cpu.scale, W, H, arrays, f, params, last_stride, keys_un=und(k), bounds=bounds)
+        assert not np.array_equal(sc[:2], ec[:2]) or len(sa) != len(ea)
+    assert readmitted > 0
     gpu.close()

@@ -62,7 +62,13 @@ def main():
                   "dram_bytes_per_launch": sum(x["dram_read"] + x["dram_write"] for x in big) / len(big),
                   "warp_inst_per_launch": sum(x["inst"] for x in big) / len(big),
                   "issue_active_pct": sum(x["issue"] for x in big) / len(big)}
+    # stamp with the digest of the kernel sources the capture was made from: bench.py ignores a stale file
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    out["csrc_sha"] = bench.csrc_sha()
     json.dump(out, open(prefix + "_ncu_traffic.json", "w"), indent=1)
+    del out["csrc_sha"]
     for k, v in sorted(out.items(), key=lambda kv: -kv[1]["mean_us"]):
         print("%-24s %8.1f us  dram %8.2f MB  grid %s" % (k, v["mean_us"], v["dram_bytes_per_launch"] / 1e6, v["grid"]))
 
