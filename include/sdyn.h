@@ -367,6 +367,7 @@ int sdyn_map_capacity(const sdyn_map* map);
 
 /* per LastFrame keypoint in the resident form: bit flags next to the MapPoint id (-1 = mvpMapPoints[i] == NULL) */
 enum { SDYN_LP_OUTLIER = 1, SDYN_LP_OBS_POSITIVE = 2 };
+enum { SDYN_MP_BAD = 1, SDYN_MP_OBS_POSITIVE = 2, SDYN_MP_SKIP = 4 };
 /* per local-map point in the resident form: what Frame::isInFrustum left in the MapPoint for this frame
  * (src/Frame.cc:718-727) plus the two per-frame state bits; = sdyn_mappoint_query without the descriptor */
 typedef struct {
@@ -403,6 +404,11 @@ typedef struct {
     const sdyn_map* map;
     const int32_t* last_ids; const uint8_t* last_flags;
     const int32_t* map_ids; const sdyn_map_proj* map_proj;
+    /* map_points == NULL and map_proj == NULL: Frame::isInFrustum (src/Frame.cc:677-733, viewing-cosine limit below; 0.5 in
+     * Tracking::SearchLocalPoints) runs on the device for every local-map id from the table entry and the frame's pose, and
+     * only one state byte per point travels: SDYN_MP_BAD | SDYN_MP_OBS_POSITIVE | SDYN_MP_SKIP (SKIP = the point is not to be
+     * searched in this frame: mnLastFrameSeen == mCurrentFrame.mnId in SearchLocalPoints). */
+    const uint8_t* map_flags; float viewing_cos_limit;
     /* 0: stereo-constructor semantics (above).  1: RGB-D-constructor semantics (src/Frame.cc:297-403 followed by
      * Tracking::Separate and Frame::UpdateFrame :607-653): the searches run on the frame the reference tracks with — the
      * keypoints outside every box in extraction order, then the re-admitted in-box keypoints in UpdateFrame's push order —
@@ -450,15 +456,16 @@ int sdyn_track_batch_async(sdyn_ctx* ctx, int nframes, const uint8_t* gray, size
 int sdyn_track_wait(sdyn_ctx* ctx);
 /* Layout of the host-buffer entry points' input staging block for `nframes` frames: offsets[i] is where array i of
  * sdyn_track_inputs starts (order: last_points, last_keys, last_keys_un, n_last, map_points, n_map, boxes, n_boxes, ref_box,
- * ref_desc, ref_xy, ref_off, fmat, poses, last_ids, last_flags, map_ids, map_proj; each on a 256-byte boundary; an array takes
+ * ref_desc, ref_xy, ref_off, fmat, poses, last_ids, last_flags, map_ids, map_proj, map_flags; each on a 256-byte boundary; an array takes
  * no room when its form is not in use: `forms` bit 0 = separate last_keys_un, bit 1 = resident LastFrame (last_ids /
  * last_flags instead of last_points / last_keys), bit 2 = resident map (map_ids / map_proj instead of map_points)), *total
  * the block size.  A caller that builds its arrays inside ONE host block at these offsets (pinned with sdyn_host_alloc) and
  * passes base + offsets[i] as the array pointers has them uploaded with a single copy instead of one copy per array — the
  * per-frame query data the reference keeps in MapPoint / Frame objects (src/ORBmatcher.cc:45-129, 1485-1627) is gathered
  * by the caller either way. */
-#define SDYN_TRACK_INPUT_ARRAYS 18
-enum { SDYN_FORM_SEPARATE_KEYS_UN = 1, SDYN_FORM_RESIDENT_LAST = 2, SDYN_FORM_RESIDENT_MAP = 4 };
+#define SDYN_TRACK_INPUT_ARRAYS 19
+enum { SDYN_FORM_SEPARATE_KEYS_UN = 1, SDYN_FORM_RESIDENT_LAST = 2, SDYN_FORM_RESIDENT_MAP = 4,
+       SDYN_FORM_DEVICE_FRUSTUM = 8 /* with RESIDENT_MAP: map_flags instead of map_proj */ };
 int sdyn_track_input_layout(int nframes, int last_stride, int map_stride, int ref_stride, int forms,
                             size_t offsets[SDYN_TRACK_INPUT_ARRAYS], size_t* total);
 /* Frame-major counterpart: offsets[i] = where array i starts inside ONE frame's record, *pitch = the record size (a multiple

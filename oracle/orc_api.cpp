@@ -341,4 +341,16 @@ int orc_update_frame(int nboxes, const int* dsOff, const int* dsVal, const int* 
     return (int)pushed.size();
 }
 
+/* Frame::isInFrustum for n points: world / normal 3 floats each; outputs per point */
+void orc_in_frustum(const sdyn_frame_view* v, float logSf, int n, const float* world, const float* normal, const float* minDist,
+                    const float* maxDist, float cosLimit, uint8_t* inView, float* projX, float* projY, float* projXR, int* level, float* viewCos)
+{
+    FrameView f = view_of(v);
+    for (int i = 0; i < n; ++i) {
+        projX[i] = projY[i] = projXR[i] = viewCos[i] = 0.f; level[i] = 0;
+        inView[i] = is_in_frustum(f, logSf, world + 3 * i, normal + 3 * i, minDist[i], maxDist[i], cosLimit, projX + i, projY + i,
+                                  projXR + i, level + i, viewCos + i);
+    }
+}
+
 }  // extern "C"

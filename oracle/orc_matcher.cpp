@@ -394,6 +394,42 @@ static inline int predict_scale(float mfMaxDistance, float currentDist, float mf
     return nScale;
 }
 
+/* Frame::isInFrustum, src/Frame.cc:677-733 */
+bool is_in_frustum(const FrameView& F, float mfLogScaleFactor, const float* world, const float* normal, float mfMinDistance,
+                   float mfMaxDistance, float viewingCosLimit, float* projX, float* projY, float* projXR, int* level, float* viewCos)
+{
+    /* Pc = mRcw*P + mtcw: cv::Mat's fused 3x3 product (float products left to right, addend joined in double) */
+    float Pc[3];
+    for (int r = 0; r < 3; ++r) {
+        const float t = F.Tcw[4 * r] * world[0] + F.Tcw[4 * r + 1] * world[1] + F.Tcw[4 * r + 2] * world[2];
+        Pc[r] = (float)((double)t * 1.0 + (double)F.Tcw[4 * r + 3] * 1.0);
+    }
+    const float PcX = Pc[0], PcY = Pc[1], PcZ = Pc[2];
+    if (PcZ < 0.0f) return false;
+    const float invz = 1.0f / PcZ;
+    const float u = F.fx * PcX * invz + F.cx;
+    const float v = F.fy * PcY * invz + F.cy;
+    if (u < F.minX || u > F.maxX) return false;
+    if (v < F.minY || v > F.maxY) return false;
+    const float maxDistance = 1.2f * mfMaxDistance;        /* GetMaxDistanceInvariance */
+    const float minDistance = 0.8f * mfMinDistance;        /* GetMinDistanceInvariance */
+    /* mOw = -mRcw.t()*mtcw (Frame::UpdatePoseMatrices :670-676; transposed operand: double accumulation) */
+    float Ow[3];
+    for (int r = 0; r < 3; ++r) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += (double)F.Tcw[4 * k + r] * (double)F.Tcw[4 * k + 3];
+        Ow[r] = (float)(-1.0 * s);
+    }
+    const float PO[3] = {world[0] - Ow[0], world[1] - Ow[1], world[2] - Ow[2]};
+    const float dist = (float)norm3(PO);
+    if (dist < minDistance || dist > maxDistance) return false;
+    const float vc = (float)(dot3(PO, normal) / dist);
+    if (vc < viewingCosLimit) return false;
+    *level = predict_scale(mfMaxDistance, dist, mfLogScaleFactor, F.nlevels);
+    *projX = u; *projXR = u - F.bf * invz; *projY = v; *viewCos = vc;
+    return true;
+}
+
 /* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
  * src/ORBmatcher.cc:1629-1756.  Rcw/tcw/Ow: the three cv::Mat values of :1633-1635 as computed by the caller. */
 int search_by_projection_reloc(const FrameView& Cur, const Grid& gCur, const ProjPoint* pts, int npts, const float* Rcw,

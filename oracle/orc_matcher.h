@@ -118,6 +118,12 @@ int search_by_bow(const FrameView& KF, const uint8_t* kfValid, const FeatureVec&
 int search_by_bow_kf(const FrameView& KF1, const uint8_t* valid1, const FeatureVec& fv1, const FrameView& KF2,
                      const uint8_t* valid2, const FeatureVec& fv2, float nnratio, bool checkOri, int32_t* matches12);
 
+/* Frame::isInFrustum, src/Frame.cc:677-733 (+ MapPoint::PredictScale, GetMin/MaxDistanceInvariance, MapPoint.cc:373-417) for one
+ * MapPoint: world / normal, mfMinDistance / mfMaxDistance; the frame's pose (rows 0..2 of mTcw), camera and pyramid constants.
+ * Returns mbTrackInView and fills the five tracking fields when true. */
+bool is_in_frustum(const FrameView& F, float mfLogScaleFactor, const float* world, const float* normal, float mfMinDistance,
+                   float mfMaxDistance, float viewingCosLimit, float* projX, float* projY, float* projXR, int* level, float* viewCos);
+
 /* ORBmatcher.cc:1758-1799 */
 void compute_three_maxima(const int* histoSizes, int L, int& ind1, int& ind2, int& ind3);
 

@@ -282,7 +282,8 @@ k_gather_queries(const sdyn_map_point* __restrict__ table, int tableCap,
                  const int32_t* __restrict__ lastIds, const uint8_t* __restrict__ lastFlags, const int32_t* __restrict__ nLast, int lastStride,
                  sdyn_last_point* __restrict__ gLast,
                  const int32_t* __restrict__ mapIds, const sdyn_map_proj* __restrict__ mapProj, const int32_t* __restrict__ nMap, int mapStride,
-                 sdyn_mappoint_query* __restrict__ gMap, long long P)
+                 sdyn_mappoint_query* __restrict__ gMap, const uint8_t* __restrict__ mapFlags, const float* __restrict__ poses,
+                 const FrustumParams fp, long long P)
 {
     const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
     if (blockIdx.z == 0) {
@@ -307,7 +308,57 @@ k_gather_queries(const sdyn_map_point* __restrict__ table, int tableCap,
         if (!mapIds || i >= min(*frame_part(nMap, f, 4, P), mapStride)) return;
         const size_t at = (size_t)f * mapStride + i;
         const int id = frame_part(mapIds, f, (size_t)mapStride * 4, P)[i];
-        const sdyn_map_proj pr = frame_part(mapProj, f, (size_t)mapStride * sizeof(sdyn_map_proj), P)[i];
+        sdyn_map_proj pr;
+        if (mapProj) pr = frame_part(mapProj, f, (size_t)mapStride * sizeof(sdyn_map_proj), P)[i];
+        else {
+            /* Frame::isInFrustum (src/Frame.cc:677-733) for table entry `id` under this frame's pose */
+            const uint8_t fl = frame_part(mapFlags, f, (size_t)mapStride, P)[i];
+            pr.proj_x = pr.proj_y = pr.proj_xr = pr.view_cos = 0.f; pr.level = 0; pr.pad = 0;
+            pr.bad = fl & SDYN_MP_BAD ? 1 : 0; pr.obs_positive = fl & SDYN_MP_OBS_POSITIVE ? 1 : 0;
+            bool in = !(fl & SDYN_MP_SKIP) && id >= 0 && id < tableCap;
+            if (in) {
+                const float* T = frame_part(poses, f, 96, P);
+                const sdyn_map_point* p = table + id;
+                const float X = p->world[0], Y = p->world[1], Z = p->world[2];
+                /* Pc = mRcw*P + mtcw: 3x3 float product left to right, the addend joined in double (cv::gemm small-matrix path) */
+                float pc[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float t = __fadd_rn(__fadd_rn(__fmul_rn(T[4 * k], X), __fmul_rn(T[4 * k + 1], Y)), __fmul_rn(T[4 * k + 2], Z));
+                    pc[k] = (float)__dadd_rn((double)t, (double)T[4 * k + 3]);
+                }
+                if (pc[2] < 0.0f) in = false;
+                const float invz = __fdiv_rn(1.0f, pc[2]);
+                const float u = __fadd_rn(__fmul_rn(__fmul_rn(fp.fx, pc[0]), invz), fp.cx);
+                const float v = __fadd_rn(__fmul_rn(__fmul_rn(fp.fy, pc[1]), invz), fp.cy);
+                if (u < fp.minX || u > fp.maxX || v < fp.minY || v > fp.maxY) in = false;
+                /* mOw = -mRcw.t()*mtcw (transposed operand: double accumulation) */
+                float ow[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    double a = 0;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) a = __dadd_rn(a, __dmul_rn((double)T[4 * k + r], (double)T[4 * k + 3]));
+                    ow[r] = (float)(-1.0 * a);
+                }
+                const float po0 = __fsub_rn(X, ow[0]), po1 = __fsub_rn(Y, ow[1]), po2 = __fsub_rn(Z, ow[2]);
+                const double n2 = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)po0), __dmul_rn((double)po1, (double)po1)), __dmul_rn((double)po2, (double)po2));
+                const float dist = (float)sqrt(n2);
+                const float maxD = __fmul_rn(1.2f, p->max_distance), minD = __fmul_rn(0.8f, p->min_distance);
+                if (dist < minD || dist > maxD) in = false;
+                const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)po0, (double)p->normal[0]), __dmul_rn((double)po1, (double)p->normal[1])),
+                                             __dmul_rn((double)po2, (double)p->normal[2]));
+                const float viewCos = (float)__ddiv_rn(dot, (double)dist);
+                if (viewCos < fp.cosLimit) in = false;
+                if (in) {
+                    const float ratio = __fdiv_rn(p->max_distance, dist);
+                    int nScale = (int)ceilf(__fdiv_rn((float)log((double)ratio), fp.logScaleFactor));      /* MapPoint::PredictScale */
+                    nScale = nScale < 0 ? 0 : (nScale >= fp.nlevels ? fp.nlevels - 1 : nScale);
+                    pr.proj_x = u; pr.proj_y = v; pr.proj_xr = __fsub_rn(u, __fmul_rn(fp.bf, invz)); pr.view_cos = viewCos; pr.level = nScale;
+                }
+            }
+            pr.track_in_view = in;
+        }
         sdyn_mappoint_query o;
         o.proj_x = pr.proj_x; o.proj_y = pr.proj_y; o.proj_xr = pr.proj_xr; o.view_cos = pr.view_cos; o.level = pr.level;
         const bool has = id >= 0 && id < tableCap;
@@ -323,12 +374,13 @@ k_gather_queries(const sdyn_map_point* __restrict__ table, int tableCap,
 cudaError_t launch_gather_queries(const sdyn_map_point* table, int tableCap, const int32_t* lastIds, const uint8_t* lastFlags,
                                   const int32_t* nLast, int lastStride, sdyn_last_point* gLast, const int32_t* mapIds,
                                   const sdyn_map_proj* mapProj, const int32_t* nMap, int mapStride, sdyn_mappoint_query* gMap,
+                                  const uint8_t* mapFlags, const float* poses, const FrustumParams& fp,
                                   int nframes, long long framePitch, cudaStream_t st)
 {
     const int m = std::max(lastIds ? lastStride : 0, mapIds ? mapStride : 0);
     if (m == 0) return cudaSuccess;
     dim3 grid((m + 255) / 256, nframes, 2);
-    k_gather_queries<<<grid, 256, 0, st>>>(table, tableCap, lastIds, lastFlags, nLast, lastStride, gLast, mapIds, mapProj, nMap, mapStride, gMap, framePitch);
+    k_gather_queries<<<grid, 256, 0, st>>>(table, tableCap, lastIds, lastFlags, nLast, lastStride, gLast, mapIds, mapProj, nMap, mapStride, gMap, mapFlags, poses, fp, framePitch);
     return cudaGetLastError();
 }
 

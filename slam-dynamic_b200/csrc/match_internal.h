@@ -113,10 +113,13 @@ cudaError_t launch_frame_compact(const sdyn_keypoint* kp, const sdyn_keypoint* k
                                  const uint64_t* mask, const int32_t* readmit, const int32_t* staticExit, sdyn_keypoint* fKp,
                                  sdyn_keypoint* fKpUn, uint8_t* fDesc, int32_t* fOrder, int32_t* fCount, int32_t* fStatic, int nframes,
                                  cudaStream_t st);
+/* camera / pyramid constants of Frame::isInFrustum on the device */
+struct FrustumParams { float fx, fy, cx, cy, bf, minX, minY, maxX, maxY, cosLimit, logScaleFactor; int nlevels; };
 /* resident query forms: ids + MapPoint table -> the searches' query records (k_track.cu) */
 cudaError_t launch_gather_queries(const sdyn_map_point* table, int tableCap, const int32_t* lastIds, const uint8_t* lastFlags,
                                   const int32_t* nLast, int lastStride, sdyn_last_point* gLast, const int32_t* mapIds,
                                   const sdyn_map_proj* mapProj, const int32_t* nMap, int mapStride, sdyn_mappoint_query* gMap,
+                                  const uint8_t* mapFlags, const float* poses, const FrustumParams& fp,
                                   int nframes, long long framePitch, cudaStream_t st);
 cudaError_t launch_box_pairs(const BoxPairJob* dJobs, int njobs, const float* dM, const float* dMinv, int mode,
                              cudaStream_t st);

@@ -221,7 +221,7 @@ static bool bad_track_inputs(const sdyn_ctx* c, const sdyn_track_inputs* in, int
     }
     if (in->map_stride > 0) {
         const bool explicitForm = in->map_points && in->n_map;
-        const bool residentForm = !in->map_points && in->map_ids && in->map_proj && in->map && in->n_map;
+        const bool residentForm = !in->map_points && in->map_ids && (in->map_proj || in->map_flags) && in->map && in->n_map;
         if (!explicitForm && !residentForm) return true;
     }
     return false;
@@ -340,9 +340,12 @@ static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs
     TCU(c, cudaMemsetAsync(t->block + t->zeroFrom, 0, t->zeroBytes, st));
     if (residentLast || residentMap) {
         /* query records of the two searches from ids + the resident MapPoint table */
+        FrustumParams fp = {in->fx, in->fy, in->cx, in->cy, in->bf, in->min_x, in->min_y, in->max_x, in->max_y, in->viewing_cos_limit,
+                            logf((float)c->params.scale_factor), c->scales.nlevels};      /* Frame::mfLogScaleFactor = log(mfScaleFactor) */
         TCU(c, launch_gather_queries(sdyn_map_table(in->map), sdyn_map_capacity(in->map),
                                      residentLast ? in->last_ids : nullptr, in->last_flags, t->pCount, in->last_stride, t->gLast,
-                                     residentMap ? in->map_ids : nullptr, in->map_proj, in->n_map, in->map_stride, t->gMap, nframes, in->frame_pitch, st));
+                                     residentMap ? in->map_ids : nullptr, in->map_proj, in->n_map, in->map_stride, t->gMap,
+                                     in->map_flags, in->poses, fp, nframes, in->frame_pitch, st));
         c->launches += 1;
     }
     /* The dynamic-keypoint mask reads the extraction results only.  With stereo-constructor semantics the two searches do
@@ -434,7 +437,8 @@ static size_t track_items(const sdyn_track_inputs* in, size_t n, TrackItem* item
         {residentLast ? in->last_ids : nullptr, residentLast ? ls * 4 : 0, 0},
         {residentLast ? in->last_flags : nullptr, residentLast ? ls : 0, 0},
         {residentMap ? in->map_ids : nullptr, residentMap ? ms * 4 : 0, 0},
-        {residentMap ? in->map_proj : nullptr, residentMap ? ms * sizeof(sdyn_map_proj) : 0, 0},
+        {residentMap ? in->map_proj : nullptr, (residentMap && in->map_proj) ? ms * sizeof(sdyn_map_proj) : 0, 0},
+        {(residentMap && !in->map_proj) ? in->map_flags : nullptr, (residentMap && !in->map_proj) ? ms : 0, 0},
     };
     size_t total = 0;
     for (int i = 0; i < SDYN_TRACK_INPUT_ARRAYS; ++i) {
@@ -459,7 +463,7 @@ int sdyn_track_input_layout(int nframes, int last_stride, int map_stride, int re
     static const int32_t ids = 0; static const uint8_t fl = 0; static const sdyn_map_proj pr = {};
     if (forms & SDYN_FORM_RESIDENT_LAST) { in.last_ids = &ids; in.last_flags = &fl; }
     else { in.last_points = &lp; in.last_keys = &kA; in.last_keys_un = (forms & SDYN_FORM_SEPARATE_KEYS_UN) ? &kB : &kA; }
-    if (forms & SDYN_FORM_RESIDENT_MAP) { in.map_ids = &ids; in.map_proj = &pr; }
+    if (forms & SDYN_FORM_RESIDENT_MAP) { in.map_ids = &ids; if (forms & SDYN_FORM_DEVICE_FRUSTUM) in.map_flags = &fl; else in.map_proj = &pr; }
     else in.map_points = &mq;
     TrackItem items[SDYN_TRACK_INPUT_ARRAYS];
     *total = track_items(&in, (size_t)nframes, items);
@@ -544,6 +548,7 @@ int sdyn_track_batch_async(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t
     d.poses = reinterpret_cast<const float*>(dev(13));
     d.last_ids = reinterpret_cast<const int32_t*>(dev(14)); d.last_flags = dev(15);
     d.map_ids = reinterpret_cast<const int32_t*>(dev(16)); d.map_proj = reinterpret_cast<const sdyn_map_proj*>(dev(17));
+    d.map_flags = dev(18);
     d.boxes = reinterpret_cast<const double*>(t->inBlock + items[6].off);
     d.n_boxes = reinterpret_cast<const int32_t*>(t->inBlock + items[7].off);
     d.ref_box = reinterpret_cast<const int32_t*>(t->inBlock + items[8].off);

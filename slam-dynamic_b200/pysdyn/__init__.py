@@ -637,13 +637,15 @@ class TrackInputsC(C.Structure):
                 ("poses", C.c_void_p),
                 ("map", C.c_void_p), ("last_ids", C.c_void_p), ("last_flags", C.c_void_p),
                 ("map_ids", C.c_void_p), ("map_proj", C.c_void_p),
+                ("map_flags", C.c_void_p), ("viewing_cos_limit", C.c_float),
                 ("rgbd_split", C.c_int32), ("frame_pitch", C.c_int64)]
 
 
 TRACK_ARRAYS = ["last_points", "last_keys", "last_keys_un", "n_last", "map_points", "n_map", "boxes", "n_boxes",
-                "ref_box", "ref_desc", "ref_xy", "ref_off", "fmat", "poses", "last_ids", "last_flags", "map_ids", "map_proj"]
-FORM_SEPARATE_KEYS_UN, FORM_RESIDENT_LAST, FORM_RESIDENT_MAP = 1, 2, 4
+                "ref_box", "ref_desc", "ref_xy", "ref_off", "fmat", "poses", "last_ids", "last_flags", "map_ids", "map_proj", "map_flags"]
+FORM_SEPARATE_KEYS_UN, FORM_RESIDENT_LAST, FORM_RESIDENT_MAP, FORM_DEVICE_FRUSTUM = 1, 2, 4, 8
 LP_OUTLIER, LP_OBS_POSITIVE = 1, 2
+MP_BAD, MP_OBS_POSITIVE, MP_SKIP = 1, 2, 4
 MAP_POINT_DTYPE = np.dtype([("world", "<f4", (3,)), ("normal", "<f4", (3,)), ("min_distance", "<f4"), ("max_distance", "<f4"),
                             ("desc", "u1", (32,))])
 MAP_PROJ_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
@@ -661,6 +663,7 @@ def track_inputs(ptrs, frame0, strides, params, map_table=None, rgbd_split=False
             base, per_frame = ptrs[name]
             setattr(t, name, base + frame0 * (frame_pitch if frame_pitch else per_frame))
     t.frame_pitch = int(frame_pitch)
+    t.viewing_cos_limit = 0.5            # Tracking::SearchLocalPoints: isInFrustum(pMP, 0.5)
     t.last_stride, t.map_stride, t.ref_stride = strides
     for k, v in params.items():
         if k in ("tcw_cur", "tcw_last"):

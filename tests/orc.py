@@ -282,6 +282,18 @@ def match_triangulation(KF1, has_mp1, fv1, KF2, has_mp2, fv2, params):
     return n, m12
 
 
+def in_frustum(F, log_sf, world, normal, min_dist, max_dist, cos_limit=0.5):
+    """Frame::isInFrustum for every point -> dict(in_view, proj_x, proj_y, proj_xr, level, view_cos)."""
+    w = np.ascontiguousarray(world, np.float32).reshape(-1, 3); nrm = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    mn = np.ascontiguousarray(min_dist, np.float32); mx = np.ascontiguousarray(max_dist, np.float32)
+    n = len(w)
+    iv = np.zeros(n, np.uint8); px, py, pxr, vc = (np.zeros(n, np.float32) for _ in range(4)); lv = np.zeros(n, np.int32)
+    lib.orc_in_frustum.argtypes = [C.c_void_p, C.c_float, C.c_int] + [C.c_void_p] * 4 + [C.c_float] + [C.c_void_p] * 6
+    lib.orc_in_frustum(C.byref(F.c), float(np.float32(log_sf)), n, w.ctypes.data, nrm.ctypes.data, mn.ctypes.data, mx.ctypes.data, cos_limit,
+                       iv.ctypes.data, px.ctypes.data, py.ctypes.data, pxr.ctypes.data, lv.ctypes.data, vc.ctypes.data)
+    return dict(in_view=iv, proj_x=px, proj_y=py, proj_xr=pxr, level=lv, view_cos=vc)
+
+
 def box_mask(keys, boxes):
     keys = np.ascontiguousarray(keys, KP_DTYPE)
     boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)

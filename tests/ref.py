@@ -408,6 +408,14 @@ def search_by_sim3(KF1, KF2, matches12, s12, R12, t12, th, nnratio=0.6):
     return n, m
 
 
+def points_in_frustum(F, points, cos_limit=0.5):
+    """Frame::isInFrustum of the reference on every point of the list."""
+    n = points.n
+    iv = np.zeros(n, np.uint8); px, py, pxr, vc = (np.zeros(n, np.float32) for _ in range(4)); lv = np.zeros(n, np.int32)
+    lib.ref_points_in_frustum(F.h, points.h, cos_limit, iv.ctypes.data, px.ctypes.data, py.ctypes.data, pxr.ctypes.data, lv.ctypes.data, vc.ctypes.data)
+    return dict(in_view=iv, proj_x=px, proj_y=py, proj_xr=pxr, level=lv, view_cos=vc)
+
+
 def tracking_separate(cur, ref_frame, last, HorF, flag):
     """Tracking::Separate.  Returns (ret, dynStatus per box, box_status of the current frame afterwards)."""
     nb = len(cur.boxes()["box_idx"])

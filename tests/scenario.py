@@ -82,6 +82,50 @@ def map_queries(keys, desc, nlevels, seed=0, count=None, jitter=2.0):
     return mp
 
 
+def map_points_3d(keys, desc, scale, tcw, cam=KITTI_CAM, seed=0, count=None, jitter=2.0):
+    """Local-map MapPoints as the reference holds them (world position, mean viewing direction, scale-invariance distances,
+    descriptor) placed so that, under pose `tcw` (rows 0..2 of mTcw), they project next to keypoints of the frame — plus the
+    per-frame state bits.  Frame::isInFrustum then derives the projection records.  -> (MAP_POINT_DTYPE[n], flags uint8[n])."""
+    r = rng_for(seed + 606)
+    n = len(keys) if count is None else count
+    src = r.integers(0, len(keys), n)
+    T = np.asarray(tcw, np.float64).reshape(3, 4)
+    R, t = T[:, :3], T[:, 3]
+    z = r.uniform(4.0, 40.0, n)
+    u = keys["x"][src].astype(np.float64) + r.normal(0, jitter, n); v = keys["y"][src].astype(np.float64) + r.normal(0, jitter, n)
+    pc = np.stack([(u - cam["cx"]) * z / cam["fx"], (v - cam["cy"]) * z / cam["fy"], z], 1)
+    pc[r.random(n) < 0.03, 2] *= -1                              # behind the camera
+    pw = (pc - t) @ R                                           # Rcw^T (pc - tcw)
+    pts = np.zeros(n, pysdyn.MAP_POINT_DTYPE)
+    pts["world"] = pw.astype(np.float32)
+    ow = -(R.T @ t)
+    po = pts["world"].astype(np.float64) - ow
+    dist = np.linalg.norm(po, axis=1)
+    nrm = po / dist[:, None] + r.normal(0, 0.45, (n, 3))        # spread: some fail the 60 degree test
+    pts["normal"] = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    lvl = np.clip(keys["octave"][src] + r.integers(0, 2, n), 0, len(scale) - 1)
+    ref_dist = dist * r.uniform(0.6, 1.5, n)                    # distance at which the point was created: some fall outside [0.8 min, 1.2 max]
+    pts["max_distance"] = (ref_dist * scale[lvl]).astype(np.float32)
+    pts["min_distance"] = (pts["max_distance"] / scale[-1]).astype(np.float32)
+    pts["desc"] = flip_bits(desc[src], r, r.integers(0, 9, n))
+    flags = ((r.random(n) < 0.03) * pysdyn.MP_BAD + (r.random(n) < 0.9) * pysdyn.MP_OBS_POSITIVE + (r.random(n) < 0.05) * pysdyn.MP_SKIP).astype(np.uint8)
+    return pts, flags
+
+
+def map_queries_from_frustum(view, pts, flags, log_sf, cos_limit=0.5):
+    """SearchByProjection(F, vpMapPoints)'s view of those MapPoints: Frame::isInFrustum (oracle) fills the tracking fields."""
+    import orc
+    fr = orc.in_frustum(view, log_sf, pts["world"], pts["normal"], pts["min_distance"], pts["max_distance"], cos_limit)
+    mp = np.zeros(len(pts), pysdyn.MAPPOINT_DTYPE)
+    for name in ("proj_x", "proj_y", "proj_xr", "view_cos", "level"):
+        mp[name] = fr[name]
+    mp["track_in_view"] = (fr["in_view"] != 0) & ((flags & pysdyn.MP_SKIP) == 0)
+    mp["bad"] = (flags & pysdyn.MP_BAD) != 0
+    mp["obs_positive"] = (flags & pysdyn.MP_OBS_POSITIVE) != 0
+    mp["desc"] = pts["desc"]
+    return mp
+
+
 def bow_nodes(desc, bits=6):
     """Stand-in for DBoW2's node assignment (the vocabulary file is absent): a node id from descriptor bits,
     so that similar descriptors share a node often, as in a real vocabulary."""
@@ -130,7 +174,7 @@ def frame_pose(i):
 
 
 def build_track_batch(kd, seq_seed, first_index, W, H, nrect, nlevels, last_stride, map_stride, ref_stride,
-                      n_map=3000, seed=0, offsets=None, time=None):
+                      n_map=3000, seed=0, offsets=None, time=None, frustum=False, scale=None, cam=KITTI_CAM):
     """kd: list of (keys, desc) for frames first_index-1 .. first_index+B-1 of one sequence (B = len(kd)-1).
     Returns dict of numpy arrays laid out as sdyn_track_inputs expects ([B, stride, ...])."""
     B = len(kd) - 1
@@ -163,7 +207,16 @@ def build_track_batch(kd, seq_seed, first_index, W, H, nrect, nlevels, last_stri
         out["last_keys"][f, :n0] = k0[:n0]; out["last_keys_un"][f, :n0] = k0[:n0]
         out["n_last"][f] = n0
         nm = min(n_map, map_stride)
-        out["map_points"][f, :nm] = map_queries(k1, d1, nlevels, seed=seed + 57 * i, count=nm)
+        if frustum:
+            # 3-D MapPoints + Frame::isInFrustum: the projection records are derived, not drawn
+            pts, fl = map_points_3d(k1, d1, scale, out["poses"][f, :12], cam=cam, seed=seed + 57 * i, count=nm)
+            view = pysdyn.FrameView(k1, d1, scale, (0.0, 0.0, float(W), float(H)),
+                                    cam=(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["bf"], cam["bf"] / cam["fx"]), tcw=out["poses"][f, :12])
+            out["map_points"][f, :nm] = map_queries_from_frustum(view, pts, fl, np.log(np.float32(1.2)))
+            out.setdefault("map_table", np.zeros((B, map_stride), pysdyn.MAP_POINT_DTYPE))[f, :nm] = pts
+            out.setdefault("map_flags", np.zeros((B, map_stride), np.uint8))[f, :nm] = fl
+        else:
+            out["map_points"][f, :nm] = map_queries(k1, d1, nlevels, seed=seed + 57 * i, count=nm)
         out["n_map"][f] = nm
         # detection boxes of the current frame and of the reference (= previous) frame, joined on rectangle id
         b1, id1 = pysdyn.synth_boxes_ids(seq_seed, W, H, nrect, ox1, oy1, time(i), margin=8)
@@ -205,11 +258,15 @@ def resident_forms(arrays):
     table = np.zeros(B * (ls + ms), pysdyn.MAP_POINT_DTYPE)
     out = {"last_ids": np.full((B, ls), -1, np.int32), "last_flags": np.zeros((B, ls), np.uint8),
            "map_ids": np.full((B, ms), -1, np.int32), "map_proj": np.zeros((B, ms), pysdyn.MAP_PROJ_DTYPE)}
+    if "map_flags" in arrays:              # frustum scenarios: the table carries the full MapPoint, the device derives map_proj
+        out["map_flags"] = arrays["map_flags"].copy()
     for f in range(B):
         base = f * (ls + ms)
         table["world"][base:base + ls] = lp["world"][f]; table["desc"][base:base + ls] = lp["desc"][f]
         out["last_ids"][f] = np.where(lp["has_mp"][f] != 0, base + np.arange(ls), -1)
         out["last_flags"][f] = (lp["outlier"][f] != 0) * pysdyn.LP_OUTLIER + (lp["obs_positive"][f] != 0) * pysdyn.LP_OBS_POSITIVE
+        if "map_table" in arrays:
+            table[base + ls:base + ls + ms] = arrays["map_table"][f]
         table["desc"][base + ls:base + ls + ms] = mp["desc"][f]
         out["map_ids"][f] = base + ls + np.arange(ms)
         for name in ("proj_x", "proj_y", "proj_xr", "view_cos", "level", "track_in_view", "bad", "obs_positive"):

@@ -89,15 +89,16 @@ def test_track_input_layout_offsets():
     """sdyn_track_input_layout: arrays in upload order, each on a 256-byte boundary; an array takes room only in its form."""
     import pysdyn
     for n, strides in [(1, (100, 50, 16)), (64, (2200, 3000, 256)), (3, (0, 0, 0))]:
-        for forms in (0, 1, 2, 4, 6):
-            sep, rl, rm = bool(forms & 1) and not forms & 2, bool(forms & 2), bool(forms & 4)
+        for forms in (0, 1, 2, 4, 6, 14):
+            sep, rl, rm, fr = bool(forms & 1) and not forms & 2, bool(forms & 2), bool(forms & 4), bool(forms & 8)
             lay, total = pysdyn.track_input_layout(n, strides, forms)
             per_frame = {"last_points": 0 if rl else strides[0] * 48, "last_keys": 0 if rl else strides[0] * 28,
                          "last_keys_un": strides[0] * 28 if sep else 0, "n_last": 0 if rl else 4,
                          "map_points": 0 if rm else strides[1] * 56, "n_map": 4, "boxes": 64 * 32, "n_boxes": 4, "ref_box": 256,
                          "ref_desc": strides[2] * 32, "ref_xy": strides[2] * 8, "ref_off": 260, "fmat": 36, "poses": 96,
                          "last_ids": strides[0] * 4 if rl else 0, "last_flags": strides[0] if rl else 0,
-                         "map_ids": strides[1] * 4 if rm else 0, "map_proj": strides[1] * 24 if rm else 0}
+                         "map_ids": strides[1] * 4 if rm else 0, "map_proj": strides[1] * 24 if rm and not fr else 0,
+                         "map_flags": strides[1] if rm and fr else 0}
             off = 0
             for name in pysdyn.TRACK_ARRAYS:
                 assert lay[name] == off and off % 256 == 0, (name, lay[name], off)

@@ -238,8 +238,11 @@ def test_track_resident_forms_match_explicit(cfg, B):
     pysdyn.track_batch_device(gpu, B, f1.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(p1, 0, strides, params))
     pysdyn.track_batch_device(gpu, B, f2.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(rp, 0, strides, params, map_table=mt))
     got = pysdyn.track_fetch(gpu, B)
-    for a, b in zip(got, want):
-        assert np.array_equal(a, b)
+    assert np.array_equal(got[3], want[3])
+    for f in range(B):                    # (entries past a frame's keypoint count are unspecified)
+        n = len(kd[f + 2][0])
+        for a, b in zip(got[:3], want[:3]):
+            assert np.array_equal(a[f, :n], b[f, :n])
     assert want[3][:, 0].min() > 100 and want[3][:, 1].min() > 50
     # host-buffer form: one pinned block with the resident layout (ids, flags, projection records, poses, boxes ...)
     forms = pysdyn.FORM_RESIDENT_LAST | pysdyn.FORM_RESIDENT_MAP
@@ -313,3 +316,40 @@ def test_track_rgbd_split_matches_oracle(cfg, B, cam):
         assert not np.array_equal(sc[:2], ec[:2]) or len(sa) != len(ea)
     assert readmitted > 0
     gpu.close()
+
+
+def test_track_device_frustum_matches_explicit():
+    """Frame::isInFrustum on the device (map_flags form): local-map ids + one state byte per point; the projection records
+    the explicit form uploads are derived from the resident MapPoint table and the frame's pose."""
+    import torch
+    cfg, B = "kitti", 2
+    W, H, nrect, nf, ini, mn, seq_seed, frames, cpu, kd = _sequence(cfg, B + 1)
+    gpu = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=B)
+    last_stride, map_stride, ref_stride = gpu.cap, 2000, 512
+    strides = (last_stride, map_stride, ref_stride)
+    params = scenario.track_params(W, H)
+    arrays = scenario.build_track_batch(kd, seq_seed, 1, W, H, nrect, 8, *strides, n_map=2000, seed=3, frustum=True, scale=cpu.scale)
+    assert 0.3 < arrays["map_points"]["track_in_view"].mean() < 0.95
+    step = {k: v for k, v in arrays.items() if k not in ("map_table", "map_flags")}
+    dev, ptrs = _dev(step)
+    dframes = torch.from_numpy(frames[1:]).cuda()
+    pysdyn.track_batch_device(gpu, B, dframes.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(ptrs, 0, strides, params))
+    want = [x.copy() for x in pysdyn.track_fetch(gpu, B)]
+    for f in range(B):                    # the explicit form is the oracle's result
+        k, d = kd[f + 1]
+        ea, el, em, ec = oracle_track.track_frame(k, d, cpu.scale, W, H, arrays, f, params, last_stride)
+        assert np.array_equal(want[3][f], ec) and np.array_equal(want[0][f, :len(k)], ea) and ec[1] > 50
+    table, res = scenario.resident_forms(arrays)
+    mt = pysdyn.MapTable(len(table)); mt.update(0, table)
+    torch.cuda.synchronize()
+    dr, pr = _dev({"map_ids": res["map_ids"], "map_flags": res["map_flags"]})
+    rp = {k: v for k, v in ptrs.items() if k != "map_points"}
+    rp.update(pr)
+    pysdyn.track_batch_device(gpu, B, dframes.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(rp, 0, strides, params, map_table=mt))
+    got = pysdyn.track_fetch(gpu, B)
+    assert np.array_equal(got[3], want[3])
+    for f in range(B):
+        n = len(kd[f + 1][0])
+        for a, b in zip(got[:3], want[:3]):
+            assert np.array_equal(a[f, :n], b[f, :n])
+    mt.close(); gpu.close()

@@ -201,6 +201,31 @@ def test_search_by_projection_map(pair, stereo, th):
     assert n == want[0] and n > 100 and np.array_equal(F.assignment(), want[1])
 
 
+def test_is_in_frustum(pair):
+    """Frame::isInFrustum (+ MapPoint::PredictScale and the distance-invariance getters, cut from MapPoint.cc) on the reference's
+    Frame against the oracle: the flag and, for points in view, the five tracking fields bit for bit."""
+    p = pair
+    log_sf = np.log(f32(1.2))
+    total = 0
+    for i in (1, 2, 3, 4):
+        pose = scenario.frame_pose(i)
+        R, t, _ = scenario.pose_small(seed=i, angle_deg=2.0, t=(0.1 * i, -0.05, 0.3 * (i - 2)))
+        tcw = _pose12(R, t) if i % 2 else pose[:12].reshape(3, 4)
+        V = scenario.frame_view(p["k1"], p["d1"], p["scale"], p["W"], p["H"], tcw=tcw)
+        pts, flags = scenario.map_points_3d(p["k1"], p["d1"], p["scale"], tcw, seed=40 + i, count=1500)
+        want = orc.in_frustum(V, log_sf, pts["world"], pts["normal"], pts["min_distance"], pts["max_distance"], 0.5)
+        F = ref.Frame.from_view(p["RE"], V)
+        plist = ref.Points(pts["world"], pts["desc"], normal=pts["normal"], min_dist=pts["min_distance"], max_dist=pts["max_distance"])
+        got = ref.points_in_frustum(F, plist, 0.5)
+        assert np.array_equal(got["in_view"], want["in_view"])
+        iv = want["in_view"] != 0
+        for name in ("proj_x", "proj_y", "proj_xr", "level", "view_cos"):
+            assert got[name][iv].tobytes() == want[name][iv].tobytes(), name
+        assert 0.3 * len(iv) < iv.sum() < 0.97 * len(iv)       # every gate fires on some points
+        total += int(iv.sum())
+    assert total > 2000
+
+
 @pytest.mark.parametrize("check,window", [(True, 40), (False, 40), (True, 100)])
 def test_search_for_initialization(pair, check, window):
     p = pair
