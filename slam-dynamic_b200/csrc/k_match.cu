@@ -41,12 +41,9 @@ __device__ __forceinline__ int job_nq(const MatchJob& J) { return J.nqPtr ? min(
 /* ---------------------------------------------------------------------------------------------------- grid */
 constexpr int GB = 1024;   /* one CTA per frame: the kernel is a chain of short dependent phases, so it wants many threads */
 
-__global__ void __launch_bounds__(GB)
-k_grid_build(const MatchJob* __restrict__ jobs)
+__device__ __forceinline__ void grid_build_body(const MatchJob& J, int* smemG)
 {
-    const MatchJob& J = jobs[blockIdx.x];
     if (J.mode == MM_BOW || J.mode == MM_TRI) return;
-    extern __shared__ int smemG[];
     int* cnt = smemG;                         /* kGridCells: counters, then insertion cursors */
     int* start = smemG + kGridCells;          /* kGridCells + 1: CSR offsets */
     int* sSorted = start + kGridCells + 1;    /* n: keypoint indices in cell order (sorted in shared memory) */
@@ -119,6 +116,19 @@ k_grid_build(const MatchJob* __restrict__ jobs)
     }
 }
 
+__device__ __forceinline__ void query_order_body(const MatchJob& J);
+
+/* One launch prepares a step's searches: CTAs [0, nGrid) build the grids of jobs[0..nGrid), CTAs [nGrid, nGrid + nOrder) sort
+ * the map queries of orderJobs[0..nOrder) by window class — the two are independent and each is a chain of short dependent
+ * phases, so they overlap instead of queueing behind each other. */
+__global__ void __launch_bounds__(GB)
+k_grid_build(const MatchJob* __restrict__ jobs, int nGrid, const MatchJob* __restrict__ orderJobs)
+{
+    extern __shared__ int smemG[];
+    if ((int)blockIdx.x < nGrid) grid_build_body(jobs[blockIdx.x], smemG);
+    else query_order_body(orderJobs[blockIdx.x - nGrid]);
+}
+
 /* ---------------------------------------------------------------------------------------------- candidates */
 __device__ __forceinline__ int hamming256(const uint32_t (&q)[8], const uint8_t* d)
 {
@@ -138,14 +148,12 @@ __device__ __forceinline__ void load_desc(const uint8_t* p, uint32_t (&q)[8])
  * Counting sort of the map-point queries of a job by search-window size class (level, narrow / wide viewing-cosine
  * radius), largest windows first, inactive queries last.  Only the visiting order of k_match_candidates changes:
  * every result is stored under the query's own index. */
-__global__ void __launch_bounds__(256)
-k_query_order(const MatchJob* __restrict__ jobs)
+__device__ __forceinline__ void query_order_body(const MatchJob& J)
 {
-    const MatchJob& J = jobs[blockIdx.x];
     if (J.mode != MM_MAP || !J.qperm) return;
     constexpr int NB = 2 * SDYN_MAX_LEVELS + 1;
     __shared__ int hist[NB];
-    const int tid = threadIdx.x, nq = job_nq(J);
+    const int tid = threadIdx.x, nq = job_nq(J), NT = blockDim.x;
     const sdyn_mappoint_query* mps = reinterpret_cast<const sdyn_mappoint_query*>(J.queries);
     if (tid < NB) hist[tid] = 0;
     __syncthreads();
@@ -155,12 +163,15 @@ k_query_order(const MatchJob* __restrict__ jobs)
         const int lvl = min(max(m.level, 0), SDYN_MAX_LEVELS - 1);
         return 2 * (SDYN_MAX_LEVELS - 1 - lvl) + (((double)m.view_cos > 0.998) ? 1 : 0);
     };
-    for (int q = tid; q < nq; q += 256) atomicAdd(&hist[key(q)], 1);
+    for (int q = tid; q < nq; q += NT) atomicAdd(&hist[key(q)], 1);
     __syncthreads();
     if (tid == 0) { int run = 0; for (int k = 0; k < NB; ++k) { const int c = hist[k]; hist[k] = run; run += c; } }
     __syncthreads();
-    for (int q = tid; q < nq; q += 256) J.qperm[atomicAdd(&hist[key(q)], 1)] = q;
+    for (int q = tid; q < nq; q += NT) J.qperm[atomicAdd(&hist[key(q)], 1)] = q;
 }
+
+__global__ void __launch_bounds__(256)
+k_query_order(const MatchJob* __restrict__ jobs) { query_order_body(jobs[blockIdx.x]); }
 
 constexpr int kCandMaxThreads = 1024;
 constexpr size_t kCandSmemBudget = 200 * 1024;
@@ -704,11 +715,8 @@ k_match_resolve(const MatchJob* __restrict__ jobs)
  * One CTA per search; T and the per-query decisions live in shared memory. */
 constexpr int RF = 1024;
 
-__global__ void __launch_bounds__(RF, 1)
-k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
+__device__ __forceinline__ void resolve_fix_body(const MatchJob& J, int poolCap, int* smemFix)
 {
-    extern __shared__ int smemFix[];
-    const MatchJob& J = jobs[blockIdx.x];
     const int tid = threadIdx.x;
     const int n = job_n(J), nq = job_nq(J);
     int* lockT = smemFix;                 /* n */
@@ -972,14 +980,27 @@ k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap)
     if (tid == 0) { J.result[0] = sCount - sDec; J.result[1] = sCount; }
 }
 
-cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, int maxN, cudaStream_t st)
+/* second > 0: the CTA resolves jobs[b] and then jobs[b + second] — the frame search and the map search of the same frame,
+ * which only interact through that frame's assign / locked arrays (one launch instead of two dependent ones). */
+__global__ void __launch_bounds__(RF, 1)
+k_match_resolve_fix(const MatchJob* __restrict__ jobs, int poolCap, int second)
+{
+    extern __shared__ int smemFix[];
+    resolve_fix_body(jobs[blockIdx.x], poolCap, smemFix);
+    if (second > 0) {
+        __syncthreads();                   /* assign / locked of the first search are visible to the whole CTA */
+        resolve_fix_body(jobs[blockIdx.x + second], poolCap, smemFix);
+    }
+}
+
+cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, int maxN, cudaStream_t st, const MatchJob* orderJobs, int nOrder)
 {
     const size_t smem = (size_t)(2 * kGridCells + 1 + std::max(maxN, 1)) * sizeof(int);
     if (smem + 2048 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_grid_build<<<njobs, GB, smem, st>>>(dJobs);
+    k_grid_build<<<njobs + (orderJobs ? nOrder : 0), GB, smem, st>>>(dJobs, njobs, orderJobs);
     return cudaGetLastError();
 }
 
@@ -1009,7 +1030,7 @@ cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQue
     return cudaGetLastError();
 }
 
-cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st)
+cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st, int second)
 {
     if (mode == MM_FRAME || mode == MM_MAP || mode == MM_POSE) {
         /* lockT + baseT (maxN each), acc + sOff + seen (maxQ each), qLock bytes, the active list, and whatever is left for
@@ -1021,7 +1042,7 @@ cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int
         const size_t smem = fixedB + (size_t)poolCap * 4;
         cudaError_t e = cudaFuncSetAttribute(k_match_resolve_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k_match_resolve_fix<<<njobs, RF, smem, st>>>(dJobs, poolCap);
+        k_match_resolve_fix<<<njobs, RF, smem, st>>>(dJobs, poolCap, second);
     } else {
         k_match_resolve<<<njobs, 32, 0, st>>>(dJobs);
     }

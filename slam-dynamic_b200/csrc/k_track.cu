@@ -14,7 +14,7 @@ namespace sdyn {
 
 __global__ void __launch_bounds__(256)
 k_box_occupancy(const uint64_t* __restrict__ mask, const int32_t* __restrict__ count, int cap,
-                unsigned long long* __restrict__ has)
+                unsigned long long* __restrict__ has, const int32_t* __restrict__ nBoxes, long long pitch, int8_t* __restrict__ slotMap)
 {
     const int f = blockIdx.x, n = min(count[f], cap);
     unsigned long long m = 0;
@@ -24,7 +24,26 @@ k_box_occupancy(const uint64_t* __restrict__ mask, const int32_t* __restrict__ c
     __shared__ unsigned long long w[8];
     if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = m;
     __syncthreads();
-    if (threadIdx.x == 0) { for (int k = 1; k < 8; ++k) m |= w[k]; has[f] = m; }
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) m |= w[k];
+        has[f] = m;
+        /* replay of firstSeparate's erase loop (Frame.cc:585-592), once per frame: `i` advances after an erase and hasKpts keeps
+         * its indexing, so slot s of Tracking::Separate gets the geometry / reference join of the s-th SURVIVING box
+         * (slotMap[s]) and the keypoints of the s-th OCCUPIED box (slotMap[64 + s]); -1 = no such slot */
+        const int nb = min(*frame_part(nBoxes, f, 4, pitch), 64);
+        int8_t* sm = slotMap + (size_t)f * 128;
+        int8_t ids[64];
+        int size = nb;
+        for (int i = 0; i < nb; ++i) ids[i] = (int8_t)i;
+        for (int i = 0; i < size; ++i) {
+            if ((m >> i) & 1ull) continue;
+            for (int k = i; k + 1 < size; ++k) ids[k] = ids[k + 1];
+            --size;
+        }
+        int seen = 0;
+        for (int s = 0; s < 64; ++s) { sm[s] = s < size ? ids[s] : (int8_t)-1; sm[64 + s] = -1; }
+        for (int b = 0; b < nb; ++b) if ((m >> b) & 1ull) sm[64 + seen++] = (int8_t)b;
+    }
 }
 
 __device__ __forceinline__ int hamming_bytes2(const uint8_t* a, const uint8_t* b)
@@ -42,32 +61,18 @@ __global__ void __launch_bounds__(BS)
 k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, const sdyn_keypoint* __restrict__ kpUn,
             const uint8_t* __restrict__ desc,
             const int32_t* __restrict__ count, int cap, const uint64_t* __restrict__ mask,
-            const unsigned long long* __restrict__ has, int32_t* __restrict__ boxList, int32_t* __restrict__ nnQ,
+            const int8_t* __restrict__ slotMap, int32_t* __restrict__ boxList, int32_t* __restrict__ nnQ,
             int32_t* __restrict__ nnT, int nnTStride, int32_t* __restrict__ readmit, int32_t* __restrict__ staticExit)
 {
     const int s = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
     const long long P = in.frame_pitch;
     const int nb = min(*frame_part(in.n_boxes, f, 4, P), 64);
     if (s >= nb) return;
-    __shared__ int sSurv, sOcc, sCount, sBase, warpCnt[BS / 32], sStatic;
-    if (tid == 0) {
-        /* replay of the erase loop (Frame.cc:585-592): `i` advances after an erase, hasKpts keeps its indexing */
-        const unsigned long long h = has[f];
-        int ids[64], size = nb;
-        for (int i = 0; i < nb; ++i) ids[i] = i;
-        for (int i = 0; i < size; ++i) {
-            if ((h >> i) & 1ull) continue;
-            for (int k = i; k + 1 < size; ++k) ids[k] = ids[k + 1];
-            --size;
-        }
-        sSurv = s < size ? ids[s] : -1;
-        int occ = -1, seen = 0;
-        for (int b = 0; b < nb; ++b) if ((h >> b) & 1ull) { if (seen == s) { occ = b; break; } ++seen; }
-        sOcc = occ; sCount = 0; sBase = 0; sStatic = 0;
-    }
-    __syncthreads();
-    const int surv = sSurv, occ = sOcc;
+    __shared__ int sCount, sBase, warpCnt[BS / 32], sStatic;
+    const int surv = slotMap[(size_t)f * 128 + s], occ = slotMap[(size_t)f * 128 + 64 + s];
     if (surv < 0 || occ < 0) return;                 /* slot beyond objects.size(), or no keypoints in it */
+    if (tid == 0) { sCount = 0; sBase = 0; sStatic = 0; }
+    __syncthreads();
     const int r = frame_part(in.ref_box, f, 64 * 4, P)[surv];
     if (r < 0) return;                               /* box id not present in the reference frame */
     const int n = min(count[f], cap);
@@ -175,16 +180,16 @@ k_dyn_finalize(const uint64_t* __restrict__ mask, const int32_t* __restrict__ re
 }
 
 cudaError_t launch_dyn_stage(const sdyn_track_inputs& in, const sdyn_keypoint* kp, const sdyn_keypoint* kpUn, const uint8_t* desc, const int32_t* count,
-                             int cap, uint64_t* mask, unsigned long long* has, int32_t* boxList, int32_t* nnQ, int32_t* nnT,
+                             int cap, uint64_t* mask, unsigned long long* has, int8_t* slotMap, int32_t* boxList, int32_t* nnQ, int32_t* nnT,
                              int nnTStride, int32_t* readmit, int32_t* staticExit, uint8_t* dynMask, int32_t* counts,
                              int nframes, cudaStream_t st)
 {
     cudaError_t e = launch_box_mask(kp, count, cap, cap, in.boxes, in.n_boxes, 64, 64, mask, nframes, st,
                                     in.frame_pitch > 0 ? (size_t)in.frame_pitch : 0, in.frame_pitch > 0 ? (size_t)in.frame_pitch : 0);
     if (e != cudaSuccess) return e;
-    k_box_occupancy<<<nframes, 256, 0, st>>>(mask, count, cap, has);
+    k_box_occupancy<<<nframes, 256, 0, st>>>(mask, count, cap, has, in.n_boxes, in.frame_pitch, slotMap);
     dim3 grid(64, nframes);
-    k_box_stage<<<grid, BS, 0, st>>>(in, kp, kpUn, desc, count, cap, mask, has, boxList, nnQ, nnT, nnTStride, readmit, staticExit);
+    k_box_stage<<<grid, BS, 0, st>>>(in, kp, kpUn, desc, count, cap, mask, slotMap, boxList, nnQ, nnT, nnTStride, readmit, staticExit);
     k_dyn_finalize<<<nframes, 256, 0, st>>>(mask, readmit, staticExit, count, cap, dynMask, counts);
     return cudaGetLastError();
 }

@@ -75,13 +75,15 @@ struct MatchJob {
 };
 
 /* maxN: largest MatchJob::n of the launch (sizes the shared-memory sort buffer) */
-cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, int maxN, cudaStream_t st);
+/* orderJobs / nOrder: MM_MAP jobs whose query order (k_query_order) is produced by the same launch */
+cudaError_t launch_grid_build(const MatchJob* dJobs, int njobs, int maxN, cudaStream_t st, const MatchJob* orderJobs = nullptr, int nOrder = 0);
 /* fills MatchJob::qperm of MM_MAP jobs that have one */
 cudaError_t launch_query_order(const MatchJob* dJobs, int njobs, cudaStream_t st);
 /* maxN: largest MatchJob::n of the launch (sizes the shared-memory staging of the searched frame) */
 cudaError_t launch_match_candidates(const MatchJob* dJobs, int njobs, int maxQueries, int maxN, cudaStream_t st);
 /* mode: all jobs of one launch share a mode; maxN / maxQ: largest MatchJob::n / ::nq of the launch */
-cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st);
+/* second > 0 (FRAME / MAP / POSE): job b + second is resolved by the same CTA right after job b */
+cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int maxN, int maxQ, cudaStream_t st, int second = 0);
 
 /* per-frame array of the batched front end: frame f's part of array `base` (array-major: `bytes` apart; frame-major records:
  * `pitch` apart — sdyn_track_inputs::frame_pitch) */
@@ -105,7 +107,7 @@ cudaError_t launch_box_mask(const sdyn_keypoint* dKeys, const int32_t* nPtr, int
                             uint64_t* dMask, int njobs, cudaStream_t st, size_t boxPitch = 0, size_t nbPitch = 0);
 /* kp = mvKeys (box containment, Frame.cc:562), kpUn = mvKeysUn (classifyF coordinates, Tracking.cc:1129-1131) */
 cudaError_t launch_dyn_stage(const sdyn_track_inputs& in, const sdyn_keypoint* kp, const sdyn_keypoint* kpUn, const uint8_t* desc, const int32_t* count,
-                             int cap, uint64_t* mask, unsigned long long* has, int32_t* boxList, int32_t* nnQ, int32_t* nnT,
+                             int cap, uint64_t* mask, unsigned long long* has, int8_t* slotMap, int32_t* boxList, int32_t* nnQ, int32_t* nnT,
                              int nnTStride, int32_t* readmit, int32_t* staticExit, uint8_t* dynMask, int32_t* counts,
                              int nframes, cudaStream_t st);
 /* RGB-D-constructor form of the tracked frame (k_track.cu) */

@@ -18,7 +18,7 @@ struct TrackState {
     /* carved from block */
     MatchJob* dJobs; int32_t* cellOff; int32_t* sorted; int32_t* cellOf; float4* gridEntry; int32_t* assign; uint8_t* locked;
     int2* qspan; int32_t* qperm; int32_t* qAccepted; int32_t* qBin; uint32_t* pool; int32_t* poolUsed; int32_t* qNext; int32_t* result;
-    uint64_t* mask; unsigned long long* has; int32_t* boxList; int32_t* nnQ; int32_t* nnT; int32_t* readmit;
+    uint64_t* mask; unsigned long long* has; int8_t* slotMap; int32_t* boxList; int32_t* nnQ; int32_t* nnT; int32_t* readmit;
     int32_t* staticExit; uint8_t* dynMask; int32_t* counts;
     /* the frame the searches ran on in the last step when it was an rgbd_split step (Frame.cc:297-403 + UpdateFrame) */
     sdyn_keypoint* fKp; sdyn_keypoint* fKpUn; uint8_t* fDesc; int32_t* fOrder; int32_t* fCount; int32_t* fStatic;
@@ -71,7 +71,7 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     const size_t oQperm = take((size_t)B * maxQ * 4);
     const size_t oQspan = take(J * maxQ * sizeof(int2)), oQAcc = take(J * maxQ * 4), oQBin = take(J * maxQ * 4);
     const size_t oPool = take(J * (size_t)t->poolPerJob * 4);
-    const size_t oMask = take((size_t)B * cap * 8), oHas = take((size_t)B * 8);
+    const size_t oMask = take((size_t)B * cap * 8), oHas = take((size_t)B * 8), oSlotMap = take((size_t)B * 128);
     const size_t oBoxList = take((size_t)B * 64 * cap * 4), oNnQ = take((size_t)B * 64 * cap * 4);
     const size_t oNnT = take((size_t)B * 64 * std::max(refStride, 1) * 4);
     const size_t oDynMask = take((size_t)B * cap);
@@ -111,7 +111,7 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     t->qperm = reinterpret_cast<int32_t*>(b + oQperm);
     t->qspan = reinterpret_cast<int2*>(b + oQspan); t->qAccepted = reinterpret_cast<int32_t*>(b + oQAcc);
     t->qBin = reinterpret_cast<int32_t*>(b + oQBin); t->pool = reinterpret_cast<uint32_t*>(b + oPool);
-    t->mask = reinterpret_cast<uint64_t*>(b + oMask); t->has = reinterpret_cast<unsigned long long*>(b + oHas);
+    t->mask = reinterpret_cast<uint64_t*>(b + oMask); t->has = reinterpret_cast<unsigned long long*>(b + oHas); t->slotMap = reinterpret_cast<int8_t*>(b + oSlotMap);
     t->boxList = reinterpret_cast<int32_t*>(b + oBoxList); t->nnQ = reinterpret_cast<int32_t*>(b + oNnQ);
     t->nnT = reinterpret_cast<int32_t*>(b + oNnT); t->dynMask = b + oDynMask;
     t->assign = reinterpret_cast<int32_t*>(b + oAssign); t->locked = b + oLocked;
@@ -359,7 +359,7 @@ static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs
     }
     {
         StageTimer tm(c, ds, SDYN_STAGE_DYNAMIC);
-        TCU(c, launch_dyn_stage(*in, c->dKp, keysUn0, c->dDesc, c->dCount, cap, t->mask, t->has, t->boxList, t->nnQ, t->nnT,
+        TCU(c, launch_dyn_stage(*in, c->dKp, keysUn0, c->dDesc, c->dCount, cap, t->mask, t->has, t->slotMap, t->boxList, t->nnQ, t->nnT,
                                 std::max(t->refStride, 1), t->readmit, t->staticExit, t->dynMask, t->counts, nframes, ds));
         c->launches += 4;
         if (split) {
@@ -377,8 +377,8 @@ static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs
             k_build_jobs<<<(words + 255) / 256, 256, 0, st>>>(pF, pM, t->dJobs, B, nframes);
             TCU(c, cudaGetLastError());
         }
-        TCU(c, launch_grid_build(t->dJobs, nframes, cap, st));
-        if (in->map_stride > 0) TCU(c, launch_query_order(t->dJobs + B, nframes, st));
+        /* grids of the B frames + visiting order of the B map searches: one launch */
+        TCU(c, launch_grid_build(t->dJobs, nframes, cap, st, in->map_stride > 0 ? t->dJobs + B : nullptr, nframes));
         /* candidate generation only applies static gates, so both searches of every frame go out in ONE launch
          * when their jobs are contiguous (full batch); the claims are then resolved frame search first */
         const bool both = in->last_stride > 0 && in->map_stride > 0 && nframes == B;
@@ -386,17 +386,15 @@ static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs
             StageTimer tc(c, st, SDYN_STAGE_CANDIDATES);
             TCU(c, launch_match_candidates(t->dJobs, 2 * B, std::max(in->last_stride, in->map_stride), cap, st));
         }
-        if (in->last_stride > 0) {
-            if (!both) TCU(c, launch_match_candidates(t->dJobs, nframes, in->last_stride, cap, st));
-            TCU(c, launch_match_resolve(t->dJobs, nframes, MM_FRAME, cap, in->last_stride, st));
-        }
-        if (in->map_stride > 0) {
-            if (!both) TCU(c, launch_match_candidates(t->dJobs + B, nframes, in->map_stride, cap, st));
-            TCU(c, launch_match_resolve(t->dJobs + B, nframes, MM_MAP, cap, in->map_stride, st));
-        }
+        const bool two = in->last_stride > 0 && in->map_stride > 0;
+        if (!both && in->last_stride > 0) TCU(c, launch_match_candidates(t->dJobs, nframes, in->last_stride, cap, st));
+        if (!both && in->map_stride > 0) TCU(c, launch_match_candidates(t->dJobs + B, nframes, in->map_stride, cap, st));
+        /* the claims: frame search first, then the map search on the mvpMapPoints it left — per frame, so one CTA does both */
+        if (two) TCU(c, launch_match_resolve(t->dJobs, nframes, MM_FRAME, cap, std::max(in->last_stride, in->map_stride), st, B));
+        else if (in->last_stride > 0) TCU(c, launch_match_resolve(t->dJobs, nframes, MM_FRAME, cap, in->last_stride, st));
+        else if (in->map_stride > 0) TCU(c, launch_match_resolve(t->dJobs + B, nframes, MM_MAP, cap, in->map_stride, st));
         /* kernels only: job table, grid, [query order], candidates (one launch for both searches of a full batch), resolves */
-        c->launches += 2 + (in->map_stride > 0 ? 1 : 0) + (both ? 1 : (in->last_stride > 0) + (in->map_stride > 0)) +
-                       (in->last_stride > 0) + (in->map_stride > 0);
+        c->launches += 2 + (both ? 1 : (in->last_stride > 0) + (in->map_stride > 0)) + ((in->last_stride > 0 || in->map_stride > 0) ? 1 : 0);
     }
     if (fork) TCU(c, cudaStreamWaitEvent(st, c->evJoin2, 0));
     k_copy_match_counts<<<(nframes + 63) / 64, 64, 0, st>>>(t->result, B, nframes, t->counts);

@@ -251,7 +251,7 @@ def test_track_resident_forms_match_explicit(cfg, B):
     hp = {}
     host = dict(a2); host.update(res)
     for name in pysdyn.TRACK_ARRAYS:
-        if name in ("last_points", "last_keys", "last_keys_un", "n_last", "map_points"):
+        if name in ("last_points", "last_keys", "last_keys_un", "n_last", "map_points") or name not in host:
             continue
         rows = host[name].view(np.uint8).reshape(host[name].shape[0], -1)[:B]
         block[layout[name]:layout[name] + rows.size] = rows.reshape(-1)
