@@ -13,12 +13,23 @@
 #include "../../include/sdyn.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <set>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
 namespace sdyn_host {
+
+/* ---- error reporting of the adapters: a failed device call is not "no matches" --------------------------------------------
+ * Every adapter returns what the reference function returns; a device failure is additionally reported on stderr with
+ * sdyn_last_error (the reference has no error channel of its own: its functions return a match count). */
+inline void report(sdyn_ctx* ctx, const char* where)
+{
+    std::fprintf(stderr, "sdyn: %s failed: %s\n", where, sdyn_last_error(ctx));
+}
+
 
 /* The Frame members the searches read, gathered into the ABI struct.  FrameT: the reference's Frame. */
 template <class FrameT>
@@ -73,8 +84,10 @@ inline int SearchByProjection(sdyn_ctx* ctx, FrameT& F, const std::vector<MapPoi
     occupancy(F, assign, locked);
     sdyn_frame_view v = frame_view(F);
     int n = 0;
-    if (sdyn_match_projection_map(ctx, &v, q.data(), (int)q.size(), th, nnratio, assign.data(), locked.data(), &n) != SDYN_OK)
+    if (sdyn_match_projection_map(ctx, &v, q.data(), (int)q.size(), th, nnratio, assign.data(), locked.data(), &n) != SDYN_OK) {
+        report(ctx, __func__);
         return 0;
+    }
     for (int i = 0; i < F.N; ++i)
         if (assign[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[assign[i]];
     return n;
@@ -104,8 +117,10 @@ inline int SearchByProjection(sdyn_ctx* ctx, FrameT& Cur, const FrameT& Last, fl
     std::vector<float> pairs(pointsLast ? (size_t)4 * std::max(Last.N, 1) : 0);
     int n = 0, np = 0;
     if (sdyn_match_projection_frame(ctx, &c, &l, lp.data(), th, bMono, checkOrientation, assign.data(), locked.data(), &n,
-                                    pointsLast ? pairs.data() : nullptr, pointsLast ? &np : nullptr) != SDYN_OK)
+                                    pointsLast ? pairs.data() : nullptr, pointsLast ? &np : nullptr) != SDYN_OK) {
+        report(ctx, __func__);
         return 0;
+    }
     for (int i = 0; i < Cur.N; ++i) {
         if (assign[i] >= 0) Cur.mvpMapPoints[i] = Last.mvpMapPoints[assign[i]];
         else if (assign[i] == -1) Cur.mvpMapPoints[i] = nullptr;      /* nulled by the rotation cull */
@@ -130,8 +145,10 @@ inline int SearchForInitialization(sdyn_ctx* ctx, FrameT& F1, FrameT& F2, std::v
     sdyn_frame_view a = frame_view(F1), b = frame_view(F2);
     int n = 0;
     static_assert(sizeof(int) == sizeof(int32_t), "int32 matches");
-    if (sdyn_match_init(ctx, &a, &b, prev.data(), vnMatches12.data(), windowSize, nnratio, checkOrientation, &n) != SDYN_OK)
+    if (sdyn_match_init(ctx, &a, &b, prev.data(), vnMatches12.data(), windowSize, nnratio, checkOrientation, &n) != SDYN_OK) {
+        report(ctx, __func__);
         return 0;
+    }
     for (int i = 0; i < n1; ++i) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
     return n;
 }
@@ -172,8 +189,10 @@ inline int SearchByBoW(sdyn_ctx* ctx, KeyFrameT* pKF, FrameT& F, std::vector<Map
     sdyn_feature_vector av = a.view(), bv = b.view();
     std::vector<int32_t> assign(F.N, -1);
     int n = 0;
-    if (sdyn_match_bow(ctx, &kv, valid.data(), &av, &fv, &bv, nnratio, checkOrientation, assign.data(), &n) != SDYN_OK)
+    if (sdyn_match_bow(ctx, &kv, valid.data(), &av, &fv, &bv, nnratio, checkOrientation, assign.data(), &n) != SDYN_OK) {
+        report(ctx, __func__);
         return 0;
+    }
     for (int i = 0; i < F.N; ++i)
         if (assign[i] >= 0) vpMapPointMatches[i] = kfPoints[assign[i]];
     return n;
@@ -200,16 +219,26 @@ inline int SearchByBoW(sdyn_ctx* ctx, KeyFrameT* pKF1, KeyFrameT* pKF2, std::vec
     sdyn_feature_vector av = fa.view(), bv = fb.view();
     std::vector<int32_t> m12(mp1.size(), -1);
     int n = 0;
-    if (sdyn_match_bow_kf(ctx, &a, v1.data(), &av, &b, v2.data(), &bv, nnratio, checkOrientation, m12.data(), &n) != SDYN_OK)
+    if (sdyn_match_bow_kf(ctx, &a, v1.data(), &av, &b, v2.data(), &bv, nnratio, checkOrientation, m12.data(), &n) != SDYN_OK) {
+        report(ctx, __func__);
         return 0;
+    }
     for (size_t i = 0; i < mp1.size(); ++i)
         if (m12[i] >= 0) vpMatches12[i] = mp2[m12[i]];
     return n;
 }
 
 #ifdef SDYN_HAVE_OPENCV
-/* One candidate MapPoint of the pose-projection searches.  MapPoint::mfMaxDistance is protected in the reference;
- * INTEGRATION.md adds the one-line accessor GetMaxDistance() next to GetMaxDistanceInvariance(). */
+/* MapPoint::mfMaxDistance (PredictScale divides it by the current distance, src/MapPoint.cc:385-418) is a protected member
+ * of the reference's MapPoint and only 1.2f * mfMaxDistance is published.  No header of the reference is edited for it: a
+ * pointer to the member, named through a derived class, is legal C++ and reads the field of any MapPoint (the value is
+ * written once at creation / UpdateNormalAndDepth; the float read is as atomic as the reference's own locked read). */
+template <class MapPointT>
+struct MaxDistancePeek : MapPointT {
+    static float get(MapPointT* p) { return p->*(&MaxDistancePeek::mfMaxDistance); }
+};
+
+/* One candidate MapPoint of the pose-projection searches. */
 template <class MapPointT>
 inline void proj_point(MapPointT* pMP, bool valid, float angle, sdyn_proj_point& q)
 {
@@ -219,7 +248,7 @@ inline void proj_point(MapPointT* pMP, bool valid, float angle, sdyn_proj_point&
     const cv::Mat w = pMP->GetWorldPos(), nrm = pMP->GetNormal(), d = pMP->GetDescriptor();
     for (int k = 0; k < 3; ++k) { q.world[k] = w.at<float>(k); q.normal[k] = nrm.at<float>(k); }
     q.min_distance = pMP->GetMinDistanceInvariance(); q.max_distance = pMP->GetMaxDistanceInvariance();
-    q.max_distance_raw = pMP->GetMaxDistance();
+    q.max_distance_raw = MaxDistancePeek<MapPointT>::get(pMP);
     q.angle = angle;
     std::memcpy(q.desc, d.data, 32);
 }
@@ -254,7 +283,7 @@ inline int SearchByProjection(sdyn_ctx* ctx, FrameT& CurrentFrame, KeyFrameT* pK
     for (int i = 0; i < CurrentFrame.N; ++i) assign[i] = CurrentFrame.mvpMapPoints[i] ? -2 : -1;
     sdyn_frame_view v = frame_view(CurrentFrame);
     int n = 0;
-    if (sdyn_match_projection_pose(ctx, &v, q.data(), (int)q.size(), &p, assign.data(), &n) != SDYN_OK) return 0;
+    if (sdyn_match_projection_pose(ctx, &v, q.data(), (int)q.size(), &p, assign.data(), &n) != SDYN_OK) { report(ctx, __func__); return 0; }
     for (int i = 0; i < CurrentFrame.N; ++i)
         if (assign[i] >= 0) CurrentFrame.mvpMapPoints[i] = vpMPs[assign[i]];
     return n;
@@ -291,7 +320,7 @@ inline int SearchByProjection(sdyn_ctx* ctx, KeyFrameT* pKF, cv::Mat Scw, const 
     std::vector<int32_t> assign(pKF->N);
     for (int i = 0; i < pKF->N; ++i) assign[i] = vpMatched[i] ? -2 : -1;
     int n = 0;
-    if (sdyn_match_projection_pose(ctx, &v, q.data(), (int)q.size(), &p, assign.data(), &n) != SDYN_OK) return 0;
+    if (sdyn_match_projection_pose(ctx, &v, q.data(), (int)q.size(), &p, assign.data(), &n) != SDYN_OK) { report(ctx, __func__); return 0; }
     for (int i = 0; i < pKF->N; ++i)
         if (assign[i] >= 0) vpMatched[i] = vpPoints[assign[i]];
     return n;
@@ -335,7 +364,7 @@ inline int Fuse(sdyn_ctx* ctx, KeyFrameT* pKF, const std::vector<MapPointT*>& vp
     p.log_scale_factor = pKF->mfLogScaleFactor; p.nlevels = pKF->mnScaleLevels;
     sdyn_frame_view v = keyframe_view(pKF);
     std::vector<int32_t> bestIdx(q.size()), bestDist(q.size());
-    if (sdyn_match_projection_best(ctx, &v, q.data(), (int)q.size(), &p, bestIdx.data(), bestDist.data()) != SDYN_OK) return 0;
+    if (sdyn_match_projection_best(ctx, &v, q.data(), (int)q.size(), &p, bestIdx.data(), bestDist.data()) != SDYN_OK) { report(ctx, __func__); return 0; }
     int nFused = 0;
     for (size_t i = 0; i < vpMapPoints.size(); ++i) {
         MapPointT* pMP = vpMapPoints[i];
@@ -381,7 +410,7 @@ inline int Fuse(sdyn_ctx* ctx, KeyFrameT* pKF, cv::Mat Scw, const std::vector<Ma
     sdyn_frame_view v = keyframe_view(pKF);
     v.u_right = nullptr;
     std::vector<int32_t> bestIdx(q.size()), bestDist(q.size());
-    if (sdyn_match_projection_best(ctx, &v, q.data(), (int)q.size(), &p, bestIdx.data(), bestDist.data()) != SDYN_OK) return 0;
+    if (sdyn_match_projection_best(ctx, &v, q.data(), (int)q.size(), &p, bestIdx.data(), bestDist.data()) != SDYN_OK) { report(ctx, __func__); return 0; }
     int nFused = 0;
     for (size_t i = 0; i < vpPoints.size(); ++i) {
         if (!q[i].valid || bestIdx[i] < 0 || bestDist[i] > SDYN_TH_LOW) continue;
@@ -425,8 +454,8 @@ inline int SearchBySim3(sdyn_ctx* ctx, KeyFrameT* pKF1, KeyFrameT* pKF2, std::ve
     sdyn_frame_view v1 = keyframe_view(pKF1), v2 = keyframe_view(pKF2);
     v1.u_right = v2.u_right = nullptr;
     std::vector<int32_t> i12(N1), d12(N1), i21(N2), d21(N2);
-    if (sdyn_match_projection_best(ctx, &v2, q1.data(), N1, &a, i12.data(), d12.data()) != SDYN_OK) return 0;
-    if (sdyn_match_projection_best(ctx, &v1, q2.data(), N2, &b, i21.data(), d21.data()) != SDYN_OK) return 0;
+    if (sdyn_match_projection_best(ctx, &v2, q1.data(), N1, &a, i12.data(), d12.data()) != SDYN_OK) { report(ctx, __func__); return 0; }
+    if (sdyn_match_projection_best(ctx, &v1, q2.data(), N2, &b, i21.data(), d21.data()) != SDYN_OK) { report(ctx, __func__); return 0; }
     int nFound = 0;
     for (int i1 = 0; i1 < N1; ++i1) {                                   /* :1462-1478 */
         const int idx2 = (i12[i1] >= 0 && d12[i1] <= SDYN_TH_HIGH) ? i12[i1] : -1;
@@ -463,7 +492,7 @@ inline int SearchForTriangulation(sdyn_ctx* ctx, KeyFrameT* pKF1, KeyFrameT* pKF
     std::vector<int32_t> m12(pKF1->N, -1);
     int n = 0;
     vMatchedPairs.clear();
-    if (sdyn_match_triangulation(ctx, &a, h1.data(), &av, &b, h2.data(), &bv, &p, m12.data(), &n) != SDYN_OK) return 0;
+    if (sdyn_match_triangulation(ctx, &a, h1.data(), &av, &b, h2.data(), &bv, &p, m12.data(), &n) != SDYN_OK) { report(ctx, __func__); return 0; }
     vMatchedPairs.reserve(n);
     for (size_t i = 0; i < m12.size(); ++i)
         if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
@@ -512,6 +541,115 @@ inline bool BoxMask(sdyn_ctx* ctx, const std::vector<KeyPointT>& keys, const std
     mask.assign(keys.size(), 0);
     return sdyn_dyn_box_mask(ctx, reinterpret_cast<const sdyn_keypoint*>(keys.data()), (int)keys.size(),
                              reinterpret_cast<const double*>(boxes.data()), (int)boxes.size(), mask.data()) == SDYN_OK;
+}
+
+/* Frame::firstSeparate (src/Frame.cc:555-604) as a whole: box test on the device (one 64-bit word per keypoint), then the
+ * reference's own bookkeeping on the host — class_id stamping, the static-first reorder of keys and descriptors, the erase of
+ * boxes without keypoints with its erase-while-iterating behaviour (the loop index advances after an erase and hasKpts is not
+ * erased in step) and N_d.  Members touched are exactly those the reference function touches.  <= 64 boxes per frame. */
+template <class FrameT, class RectT>
+inline bool FirstSeparate(sdyn_ctx* ctx, FrameT& F, std::vector<RectT>& boxes, std::vector<std::vector<int>>& index,
+                          std::vector<bool>& hasKpts)
+{
+    std::vector<uint64_t> mask;
+    if (boxes.size() > 64 || !BoxMask(ctx, F.mvKeys, boxes, mask)) { report(ctx, "Frame::firstSeparate (box mask)"); mask.assign(F.mvKeys.size(), 0); }
+    typedef typename std::remove_reference<decltype(F.mvKeys)>::type KeyVec;
+    KeyVec statKeys, dynKeys;
+    std::vector<int> statRows, dynRows;
+    for (size_t i = 0; i < F.mvKeys.size(); ++i) {
+        std::vector<int> idx;
+        for (size_t j = 0; j < boxes.size(); ++j)
+            if ((mask[i] >> j) & 1ull) {
+                hasKpts[j] = true;
+                idx.push_back((int)j);
+                if (F.mvKeys[i].class_id == -1) F.mvKeys[i].class_id = (int)i;
+            }
+        if (!idx.empty()) { index.push_back(idx); dynKeys.push_back(F.mvKeys[i]); dynRows.push_back((int)i); }
+        else { statKeys.push_back(F.mvKeys[i]); statRows.push_back((int)i); }
+    }
+    bool empty_box = false;
+    for (size_t i = 0; i < boxes.size(); i++) {
+        if (hasKpts[i] == true) continue;
+        boxes.erase(boxes.begin() + i);
+        F.box_idx.erase(F.box_idx.begin() + i);
+        F.omit.erase(F.omit.begin() + i);
+        F.box_velocity.erase(F.box_velocity.begin() + i);
+        empty_box = true;
+    }
+    F.N_d = (int)index.size();
+    if (F.N_d > 0) {
+        F.mvKeys = statKeys;
+        F.mvKeys.insert(F.mvKeys.end(), dynKeys.begin(), dynKeys.end());
+        decltype(F.mDescriptors) D(F.mDescriptors.rows, 32, F.mDescriptors.type());
+        int r = 0;
+        for (int src : statRows) std::memcpy(D.ptr(r++), F.mDescriptors.ptr(src), 32);
+        for (int src : dynRows) std::memcpy(D.ptr(r++), F.mDescriptors.ptr(src), 32);
+        F.mDescriptors = D;
+    }
+    return empty_box;
+}
+
+/* Tracking::Separate (src/Tracking.cc:1093-1239): per current box joined to a box of the reference frame, cv::BFMatcher
+ * cross-check + classifyF / classifyH run on the device for ALL boxes in one call (sdyn_dyn_separate); the >= 3 / 20 %
+ * gates, the "static if more than max(1, 20 %) survive" rule and the box_status bookkeeping are the reference's, on the host.
+ * Debug output of the reference (drawMatches, imwrite, putText) is not reproduced.  Returns what Separate returns. */
+template <class FrameT, class MatT>
+inline int Separate(sdyn_ctx* ctx, FrameT& Cur, FrameT& Ref, FrameT& Last, const MatT& HorF, int flag, std::vector<std::vector<int>>& dynStatus)
+{
+    const size_t nb = Cur.objects.size();
+    dynStatus.resize(nb);
+    struct Job { size_t box, ref; std::vector<float> qxy, txy; std::vector<int32_t> mq, mt, md, fd; };
+    std::vector<Job> jobs;
+    std::vector<sdyn_box_pair> pairs;
+    for (size_t b = 0; b < nb; ++b) {
+        auto it = std::find(Ref.box_idx.begin(), Ref.box_idx.end(), Cur.box_idx[b]);
+        if (it == Ref.box_idx.end()) continue;
+        const size_t r = it - Ref.box_idx.begin();
+        if (Cur.mdynDescriptors[b].cols == 0 || Ref.mdynDescriptors[r].cols == 0) continue;
+        Job j; j.box = b; j.ref = r;
+        const auto& ck = Cur.mvdynKeysUn[b]; const auto& rk = Ref.mvdynKeysUn[r];
+        for (const auto& k : ck) { j.qxy.push_back(k.pt.x); j.qxy.push_back(k.pt.y); }
+        for (const auto& k : rk) { j.txy.push_back(k.pt.x); j.txy.push_back(k.pt.y); }
+        const size_t cap = std::max<size_t>(ck.size(), 1);
+        j.mq.assign(cap, -1); j.mt.assign(cap, -1); j.md.assign(cap, 0); j.fd.assign(cap, -1);
+        jobs.push_back(std::move(j));
+    }
+    pairs.resize(jobs.size());
+    std::vector<MatT> keepQ(jobs.size()), keepT(jobs.size());
+    for (size_t k = 0; k < jobs.size(); ++k) {
+        Job& j = jobs[k];
+        /* mdynDescriptors is built row by row (Mat::push_back): take continuous copies */
+        keepQ[k] = Cur.mdynDescriptors[j.box].clone(); keepT[k] = Ref.mdynDescriptors[j.ref].clone();
+        sdyn_box_pair& p = pairs[k];
+        p.nq = keepQ[k].rows; p.nt = keepT[k].rows;
+        p.q_desc = keepQ[k].data; p.t_desc = keepT[k].data;
+        p.q_xy = j.qxy.data(); p.t_xy = j.txy.data();
+        p.match_query = j.mq.data(); p.match_train = j.mt.data(); p.match_dist = j.md.data(); p.false_dyn = j.fd.data();
+        p.nmatches = 0;
+    }
+    float m[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) m[3 * r + c] = HorF.template at<float>(r, c);
+    if (!pairs.empty() && sdyn_dyn_separate(ctx, pairs.data(), (int)pairs.size(), m, flag == 1 ? 1 : 0) != SDYN_OK) {
+        report(ctx, "Tracking::Separate");
+        return 0;
+    }
+    bool static_exit = false;
+    for (size_t k = 0; k < jobs.size(); ++k) {
+        const Job& j = jobs[k];
+        const size_t good = (size_t)pairs[k].nmatches;
+        if (good < 3 || good < 0.2 * Cur.mvdynKeys[j.box].size()) continue;
+        std::vector<int>& st = dynStatus[j.box];
+        st.assign(j.fd.begin(), j.fd.begin() + good);
+        const int num0 = (int)st.size() - (int)std::count(st.begin(), st.end(), -1);
+        if (num0 > std::max((double)1, 0.2 * good)) {
+            static_exit = true;          /* `mCurrentFrame.box_status[n_box] == 1;` is a comparison in the reference (Tracking.cc:1188) */
+        } else {
+            const size_t last_idx = std::find(Last.box_idx.begin(), Last.box_idx.end(), Cur.box_idx[j.box]) - Last.box_idx.begin();
+            const int ls = last_idx < Last.box_status.size() ? Last.box_status[last_idx] : -1;   /* the reference reads past the end here */
+            Cur.box_status[j.box] = (ls == 0 || ls == 2) ? 2 : 0;
+        }
+    }
+    return static_exit ? 1 : 0;
 }
 
 }  // namespace sdyn_host

@@ -45,7 +45,10 @@ struct KeyFrame;
 struct MapPoint {
     bool mbTrackInView; int mnTrackScaleLevel; float mTrackViewCos, mTrackProjX, mTrackProjY, mTrackProjXR;
     bool isBad(); int Observations(); cv::Mat GetDescriptor(); cv::Mat GetWorldPos(); cv::Mat GetNormal();
-    float GetMinDistanceInvariance(); float GetMaxDistanceInvariance(); float GetMaxDistance();
+    float GetMinDistanceInvariance(); float GetMaxDistanceInvariance();
+protected:
+    float mfMaxDistance;
+public:
     bool IsInKeyFrame(KeyFrame*); void Replace(MapPoint*); void AddObservation(KeyFrame*, size_t); int GetIndexInKeyFrame(KeyFrame*);
 };
 struct Extractor { sdyn_ctx* Context(); };

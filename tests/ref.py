@@ -7,7 +7,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
-LIB_PATH = os.path.join(_ORACLE_DIR, "_ref", "libref.so")
+# SDYN_REF_VARIANT = "dropin" selects oracle/_ref/libdropin.so: the reference's Frame.cc linked against the PRODUCT's host classes
+# (same C entry points); see load_variant().
+VARIANT = os.environ.get("SDYN_REF_VARIANT", "ref")
+LIB_PATH = os.path.join(_ORACLE_DIR, "_ref", "lib%s.so" % VARIANT)
 REFERENCE_TREE = "/root/reference"
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
@@ -24,8 +27,25 @@ def available():
 
 def _load():
     if os.path.isdir(REFERENCE_TREE):
-        subprocess.check_call(["make", "-s", "-C", _ORACLE_DIR, "ref"])
+        subprocess.check_call(["make", "-s", "-C", _ORACLE_DIR, VARIANT])
     return C.CDLL(LIB_PATH)
+
+
+def load_variant(name):
+    """A second, independent copy of this binding over oracle/_ref/lib<name>.so (module object)."""
+    import importlib.util
+    old = os.environ.get("SDYN_REF_VARIANT")
+    os.environ["SDYN_REF_VARIANT"] = name
+    try:
+        spec = importlib.util.spec_from_file_location("ref_" + name, os.path.abspath(__file__))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if old is None:
+            os.environ.pop("SDYN_REF_VARIANT", None)
+        else:
+            os.environ["SDYN_REF_VARIANT"] = old
+    return mod
 
 
 lib = _load()
