@@ -33,6 +33,11 @@ POOL = 256          # distinct frames per GPU (frame_idx 0..255)
 NLEVELS, SCALE = 8, 1.2
 N_MAP = 3000        # local-map points per frame (2000-5000)
 REF_STRIDE = 1024   # capacity for the reference frame's in-box keypoints
+POPC_PEAK = 4.65e12  # __popc results per second: 148 SMs x 16 / clk x 1.965 GHz (replaced by the tools/popc_probe measurement when committed)
+try:
+    POPC_PEAK = json.load(open(os.path.join(ROOT, "profiles", "r02_popc_probe.json")))["popc_gops"] * 1e9
+except Exception:
+    pass
 METRIC = "frames/sec ORB extract+match+dyn-mask @KITTI 1241x376 2k feats; % HBM roofline"
 
 
@@ -434,6 +439,31 @@ def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptr
                   "cpu_oracle_ms_per_frame": cpu_ms,
                   "reference": "Frame::ComputeBoW -> DBoW2 transform, src/Frame.cc:803-810"}
     voc.close(); L.close(); R.close()
+    # the heavy matcher case: monocular initialisation — the 2 x nFeatures extractor (Tracking.cc:128) and
+    # SearchForInitialization with a 100-px window on level 0 (Tracking.cc:1461, ORBmatcher.cc:562-677)
+    try:
+        ini2 = pysdyn.Extractor(2 * nf, SCALE, NLEVELS, ini, mn, max_width=W, max_height=H, max_batch=1, device=local)
+        ia, ib = pairs[0][0], pairs[1][0]
+        ka, da = ini2(ia); kb, db = ini2(ib)
+        sc = ini2.GetScaleFactors()
+        F1 = scenario.frame_view(ka, da, sc, W, H); F2 = scenario.frame_view(kb, db, sc, W, H)
+        prevm = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+        mi = pysdyn.Matcher(ini2, 0.9, True)
+        for _ in range(3):
+            mi.SearchForInitialization(F1, F2, prevm, 100)
+        li = []
+        for _ in range(20):
+            t1 = time.perf_counter(); nmi, _, _ = mi.SearchForInitialization(F1, F2, prevm, 100); li.append(time.perf_counter() - t1)
+        ev = mi.last_evals()
+        t1 = time.perf_counter(); orc.match_init(F1, F2, prevm, 100, 0.9, True); cpu_i = time.perf_counter() - t1
+        out["init_search"] = {"keypoints": [int(len(ka)), int(len(kb))], "level0_queries": int((ka["octave"] == 0).sum()), "matches": int(nmi),
+                              "hamming_evals": ev, "ms_per_call": 1e3 * float(np.median(li)), "evals_per_s_through_the_call": ev / float(np.median(li)),
+                              "cpu_oracle_ms": 1e3 * cpu_i,
+                              "note": "one SearchForInitialization call through the C ABI with host arrays (H2D of both frames, grid, "
+                                      "candidates, sequential resolve, D2H inside the call)"}
+        ini2.close()
+    except Exception as e:
+        out["init_search"] = {"error": repr(e)}
     # the reference's own execution model: one frame per call through the drop-in entry points (host buffers in and out)
     try:
         import orc as _orc
@@ -804,8 +834,47 @@ def main():
         cframes, carrays, cparams, ccap = cpu_prepare(cfg, 8)
         cpu1, n1 = cpu_run(cfg, cframes, carrays, cparams, ccap, 1, seconds=args.cpu_seconds)
         cpu = {"value": cpu1, "unit": "frames/s", "cores": 1, "kind": "port",
-               "sample": "%d KITTI frames, full path (extract + 2 searches + dynamic mask) on the C++ oracle, 1 thread "
+               "sample": "%d frames of the pool, full path (extract + 2 searches + dynamic mask) on the C++ oracle, 1 thread "
                          "(the reference's execution model, Frame.cc:259,318,424)" % n1}
+        # BASELINE.md §5 run (2): the stereo constructor's two extraction threads (Frame.cc:151-154) — pairs/s on 2 threads
+        try:
+            import orc
+            t0 = time.perf_counter(); npairs = 0
+
+            def one(img):
+                orc.Extractor(nf, SCALE, NLEVELS, ini, mn)(img)
+            while time.perf_counter() - t0 < min(4.0, args.cpu_seconds):
+                th2 = [threading.Thread(target=one, args=(cframes[(npairs + j) % len(cframes)],)) for j in range(2)]
+                [t.start() for t in th2]; [t.join() for t in th2]
+                npairs += 1
+            cpu["stereo_pairs_per_s_2_threads_extraction_only"] = npairs / (time.perf_counter() - t0)
+        except Exception as e:
+            cpu["stereo_pairs_error"] = repr(e)
+        # run (4): the same primitives through OpenCV's own SIMD code (cv2), to show the restated primitives are not unfairly slow
+        try:
+            import cv2
+            cv2.setNumThreads(1)
+            img = cframes[0]
+            oe = orc.Extractor(nf, SCALE, NLEVELS, ini, mn)
+            t0 = time.perf_counter(); oe(img); t_orc = time.perf_counter() - t0
+            sizes = level_sizes(W, H)
+            t0 = time.perf_counter()
+            lv = [img]
+            for (w_, h_) in sizes[1:]:
+                lv.append(cv2.resize(lv[-1], (w_, h_), interpolation=cv2.INTER_LINEAR))
+            fast = cv2.FastFeatureDetector_create(mn, True)
+            nk = 0
+            for l in lv:
+                b_ = cv2.copyMakeBorder(l, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
+                nk += len(fast.detect(l))
+                cv2.GaussianBlur(l, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+            t_cv = time.perf_counter() - t0
+            cpu["cv2_primitives"] = {"ms_per_frame_pyramid_fast_blur_via_cv2_%s" % cv2.__version__: 1e3 * t_cv,
+                                     "ms_per_frame_whole_extraction_oracle": 1e3 * t_orc,
+                                     "note": "cv2: 8-level resize chain + borders + whole-level FAST(minTh, NMS) + 7x7 blur, 1 thread, SIMD; "
+                                             "the oracle figure also contains the per-cell FAST calls, octree, orientation and descriptors"}
+        except Exception as e:
+            cpu["cv2_primitives"] = {"error": repr(e)}
 
     extras = None
     if args.next_rows and world == 1 and cfg == "kitti":
@@ -845,6 +914,13 @@ def main():
                               "note": "SURVEY §8(d) extraction bytes per frame x per-GPU frames/s"},
         "issue_roofline": issue,
         "stages": stage_report,
+        "matching": {"hamming_evals_per_frame": evals_per_frame, "evals_per_s": evals_per_frame * fps / world,
+                     "popc_per_s": 8 * evals_per_frame * fps / world, "match_stage_ms_per_step": stage_report.get("match", {}).get("ms_per_step"),
+                     "evals_per_s_inside_the_match_stage": (evals_per_frame * B / (stage_report["match"]["ms_per_step"] * 1e-3)) if "match" in stage_report else None,
+                     "popc_peak_per_s": POPC_PEAK, "popc_pipe_frac_inside_the_match_stage":
+                         (8 * evals_per_frame * B / (stage_report["match"]["ms_per_step"] * 1e-3) / POPC_PEAK) if "match" in stage_report else None,
+                     "note": "8 POPC.B32 per 256-bit distance (ORBmatcher.cc:1804-1820); peak = measured by tools/popc_probe (profiles/r02_popc_probe.json). "
+                             "The searches are bound by their dependent gather chains, not by the popc pipe (DESIGN.md 4)"},
         "per_frame": {"hamming_evals": evals_per_frame, "keypoints": float(g[:, 1].mean()), "matches_frame": float(g[:, 2].mean()),
                       "matches_map": float(g[:, 3].mean()), "dyn_masked": float(g[:, 4].mean())},
         "cpu_baseline": cpu,

@@ -226,6 +226,10 @@ typedef struct {
  * searches below do their distance work on the device. */
 int sdyn_hamming(const uint8_t* a, const uint8_t* b);
 
+/* Hamming-distance evaluations (ORBmatcher::DescriptorDistance calls of the reference loop, src/ORBmatcher.cc:1804-1820) the
+ * LAST search call on this context performed: the unit of the popc roofline. */
+long long sdyn_match_last_evals(const sdyn_ctx* ctx);
+
 /* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th),
  * src/ORBmatcher.cc:45-129.  *nmatches = return value. */
 int sdyn_match_projection_map(sdyn_ctx* ctx, const sdyn_frame_view* frame, const sdyn_mappoint_query* mps,

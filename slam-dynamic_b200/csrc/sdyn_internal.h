@@ -85,6 +85,7 @@ struct sdyn_ctx {
     cudaEvent_t evFork, evJoin, evFork2, evJoin2;
     std::string err;
     long long launches;
+    long long lastEvals;                       /* Hamming evaluations of the last single-search call (sdyn_match_last_evals) */
 
     /* geometry for the current image size */
     sdyn::Geom geom;

@@ -117,6 +117,7 @@ int run_job(sdyn_ctx* c, size_t fixedBytes, int nq, int poolGuess, int poolMax, 
         MCU(c, cudaStreamSynchronize(c->stream));
         if (res[2] && pool < poolMax) { pool = (int)std::min<long long>((long long)pool * 4, poolMax); continue; }
         if (res[2]) return api_fail(c, SDYN_ERR_CAPACITY, "matcher candidate pool exhausted");
+        c->lastEvals = res[3];
         return fetch(J, res);
     }
     return api_fail(c, SDYN_ERR_CAPACITY, "matcher candidate pool exhausted");
@@ -125,6 +126,8 @@ int run_job(sdyn_ctx* c, size_t fixedBytes, int nq, int poolGuess, int poolMax, 
 }  // namespace sdyn
 
 extern "C" {
+
+long long sdyn_match_last_evals(const sdyn_ctx* c) { return c ? c->lastEvals : 0; }
 
 int sdyn_hamming(const uint8_t* a, const uint8_t* b)
 {

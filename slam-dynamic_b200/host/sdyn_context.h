@@ -18,8 +18,9 @@ inline sdyn_ctx* ThreadContext()
     };
     static thread_local Holder h;
     if (!h.ctx) {
-        const sdyn_orb_params p = {1000, 1.2f, 8, 20, 7};      /* the ORB parameters are irrelevant to the searches */
-        if (sdyn_create(&p, 64, 64, 1, DefaultDevice(), &h.ctx) != SDYN_OK) {
+        /* the ORB parameters are irrelevant to the searches: the smallest legal extractor (one level, 128 x 128) */
+        const sdyn_orb_params p = {500, 1.2f, 1, 20, 7};
+        if (sdyn_create(&p, 128, 128, 1, DefaultDevice(), &h.ctx) != SDYN_OK) {
             std::fprintf(stderr, "sdyn: no GPU context for the matcher: %s\n", sdyn_last_error(nullptr));
             h.ctx = nullptr;
         }

@@ -560,6 +560,12 @@ class Matcher:
                                               window, self.nnratio, int(self.check), C.byref(n)))
         return n.value, m12, prev
 
+    def last_evals(self):
+        """Hamming evaluations of the last search call (sdyn_match_last_evals)."""
+        self.L.sdyn_match_last_evals.restype = C.c_longlong
+        self.L.sdyn_match_last_evals.argtypes = [C.c_void_p]
+        return int(self.L.sdyn_match_last_evals(self.h))
+
     def SearchByBoW(self, KF, kf_valid, fv_kf, F, fv_f):
         kv = np.ascontiguousarray(kf_valid, np.uint8)
         assign = np.full(F.n, -1, np.int32)
