@@ -142,6 +142,10 @@ int sdyn_fetch_level(sdyn_ctx* ctx, int frame, int level, uint8_t* out, int* wid
  * threshold fallback, as (x, y, response) int triples in level coordinates relative to the FAST window
  * origin (minBorderX/Y = 16).  Order is unspecified (the selection stage is order-independent). */
 int sdyn_fetch_candidates(sdyn_ctx* ctx, int frame, int level, int32_t* xyv, int cap, int* n_out);
+/* Latency mode of one-frame contexts (max_batch == 1, the drop-in ORBextractor): sdyn_extract / sdyn_extract_batch(1 frame)
+ * replay the whole call as ONE CUDA graph captured per image size (on by default; 0 switches back to stream launches).
+ * Outputs are bit-identical either way. */
+int sdyn_set_latency_mode(sdyn_ctx* ctx, int on);
 /* The context's own stream (a cudaStream_t), for ordering caller-side copies (e.g. sdyn_map_update) with its steps. */
 void* sdyn_stream(sdyn_ctx* ctx);
 /* Blocks until all work enqueued on the context's stream has finished. */

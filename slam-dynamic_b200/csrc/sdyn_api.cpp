@@ -80,6 +80,7 @@ int ensure_geometry(sdyn_ctx* c, int W, int H)
     }
     c->geom = g; c->nFastTiles = (int)ft.size(); c->nBlurTiles = (int)bt.size();
     c->geomValid = true;
+    if (c->graph1) { cudaGraphExecDestroy(c->graph1); c->graph1 = nullptr; }      /* captured for the previous geometry */
     return SDYN_OK;
 }
 
@@ -237,7 +238,8 @@ void free_all(sdyn_ctx* c)
     cudaFree(c->dBlur); cudaFree(c->dCellFlag); cudaFree(c->dCand); cudaFree(c->dCandNode); cudaFree(c->dCandCount); cudaFree(c->dSelCount);
     cudaFree(c->dLevelKp); cudaFree(c->dLevelCount); cudaFree(c->dCount); cudaFree(c->dStatus); cudaFree(c->dKp);
     cudaFree(c->dDesc); cudaFree(c->dArena); cudaFree(c->dKpUn);
-    cudaFreeHost(c->hKp); cudaFreeHost(c->hDesc); cudaFreeHost(c->hCount); cudaFreeHost(c->hStatus);
+    cudaFreeHost(c->hKp); cudaFreeHost(c->hDesc); cudaFreeHost(c->hCount); cudaFreeHost(c->hStatus); cudaFreeHost(c->hIn);
+    if (c->graph1) cudaGraphExecDestroy(c->graph1);
     for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : c->evPool) cudaEventDestroy(e);
     if (c->evFork) cudaEventDestroy(c->evFork);
@@ -458,6 +460,68 @@ int sdyn_fetch_results(sdyn_ctx* c, int nframes, sdyn_keypoint* kpOut, uint8_t* 
     return sdyn::fetch_finish(c, nframes, kpOut, descOut, cap, nOut);
 }
 
+/* Latency mode (one frame per call, the reference's own execution model): the whole call — H2D of the frame from pinned
+ * staging, the 14 kernels on two streams, D2H of counts / keypoints / descriptors into pinned staging — is captured once per
+ * image size as a CUDA graph and replayed with one launch; the call then costs one memcpy into the staging buffer, one graph
+ * launch, one synchronisation and the copy-out.  Same kernels, same order: outputs are bit-identical to the stream path. */
+static int extract_one_graph(sdyn_ctx* c, const uint8_t* gray, int W, int H, int stride, sdyn_keypoint* kpOut, uint8_t* descOut,
+                             int cap, int* nOut)
+{
+    const size_t bytes = (size_t)W * H;
+    if (bytes > c->hInCap) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFreeHost(c->hIn); c->hIn = nullptr; c->hInCap = 0;
+        if (cudaMallocHost(reinterpret_cast<void**>(&c->hIn), (size_t)c->maxW * c->maxH) != cudaSuccess)
+            return fail(c, SDYN_ERR_NOMEM, "pinned frame staging");
+        c->hInCap = (size_t)c->maxW * c->maxH;
+        if (c->graph1) { cudaGraphExecDestroy(c->graph1); c->graph1 = nullptr; }
+    }
+    if (c->graph1 && (c->graphW != W || c->graphH != H || c->graphCam != c->camera.enabled)) {
+        cudaGraphExecDestroy(c->graph1); c->graph1 = nullptr;
+    }
+    if (!c->graph1) {
+        cudaGraph_t g = nullptr;
+        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaMemcpyAsync(c->dIn, c->hIn, bytes, cudaMemcpyHostToDevice, c->stream);
+        int rc = e == cudaSuccess ? enqueue_extract(c, 1, c->dIn, bytes, W, c->stream) : SDYN_ERR_CUDA;
+        if (rc == SDYN_OK) rc = sdyn::fetch_enqueue(c, 1, c->hKp, c->hDesc, c->maxKp > 0 ? c->maxKp - 1 : 0, c->stream);   /* cap != maxKp: stage in pinned memory */
+        cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+        if (rc != SDYN_OK || e2 != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            return fail(c, SDYN_ERR_CUDA, std::string("graph capture of the one-frame extraction failed: ") + cudaGetErrorString(e2 != cudaSuccess ? e2 : e));
+        }
+        e = cudaGraphInstantiate(&c->graph1, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { c->graph1 = nullptr; return cuda_fail(c, e, "cudaGraphInstantiate"); }
+        c->graphW = W; c->graphH = H; c->graphCam = c->camera.enabled;
+    } else {
+        c->launches += 1 + (c->geom.nlevels - 1) + 4 + (c->camera.enabled ? 1 : 0);       /* the kernels one replay launches */
+    }
+    if (stride == W) std::memcpy(c->hIn, gray, bytes);
+    else for (int y = 0; y < H; ++y) std::memcpy(c->hIn + (size_t)y * W, gray + (size_t)y * stride, W);
+    CU(c, cudaGraphLaunch(c->graph1, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    /* results are in the pinned staging (hKp / hDesc / hCount / hStatus): scatter like fetch_finish's staged path */
+    if (c->hStatus[0]) return fail(c, SDYN_ERR_CAPACITY, "internal candidate/node capacity exceeded");
+    const int n = c->hCount[0];
+    nOut[0] = n;
+    const int m = std::min(n, cap);
+    if (m > 0) {
+        std::memcpy(kpOut, c->hKp, sizeof(sdyn_keypoint) * (size_t)m);
+        std::memcpy(descOut, c->hDesc, (size_t)32 * m);
+    }
+    if (n > cap) return fail(c, SDYN_ERR_CAPACITY, "output capacity too small (see sdyn_max_keypoints)");
+    return SDYN_OK;
+}
+
+int sdyn_set_latency_mode(sdyn_ctx* c, int on)
+{
+    if (!c) return SDYN_ERR_ARG;
+    c->latencyMode = on ? 1 : -1;
+    return SDYN_OK;
+}
+
 int sdyn_extract_batch(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t frameStride, int W, int H, int stride,
                        sdyn_keypoint* kpOut, uint8_t* descOut, int cap, int* nOut)
 {
@@ -472,6 +536,9 @@ int sdyn_extract_batch(sdyn_ctx* c, int nframes, const uint8_t* gray, size_t fra
     CU(c, cudaSetDevice(c->device));
     int rc = ensure_geometry(c, W, H);
     if (rc != SDYN_OK) return rc;
+    /* one frame per call on a one-frame context: the graph-captured path (default; sdyn_set_latency_mode(ctx, 0) disables) */
+    if (nframes == 1 && c->maxBatch == 1 && c->latencyMode >= 0 && !c->profiling && cap > 0 && kpOut && descOut)
+        return extract_one_graph(c, gray, W, H, stride, kpOut, descOut, cap, nOut);
     CU(c, upload_frames(c, nframes, gray, frameStride, W, H, stride, c->stream));
     rc = enqueue_extract(c, nframes, c->dIn, (size_t)W * H, W, c->stream);
     if (rc != SDYN_OK) return rc;

@@ -85,6 +85,8 @@ struct sdyn_ctx {
     cudaEvent_t evFork, evJoin, evFork2, evJoin2;
     std::string err;
     long long launches;
+    /* latency mode: the one-frame extraction (pinned staging -> kernels -> pinned results) as ONE CUDA graph */
+    cudaGraphExec_t graph1; int graphW, graphH, graphCam; uint8_t* hIn; size_t hInCap; int latencyMode;
     long long lastEvals;                       /* Hamming evaluations of the last single-search call (sdyn_match_last_evals) */
 
     /* geometry for the current image size */

@@ -303,6 +303,12 @@ class Extractor:
     def launch_count(self):
         return lib().sdyn_launch_count(self._h)
 
+    def set_latency_mode(self, on):
+        """One-frame contexts: replay the whole extraction call as one CUDA graph (default on)."""
+        L = lib()
+        L.sdyn_set_latency_mode.argtypes = [C.c_void_p, C.c_int]
+        self._check(L.sdyn_set_latency_mode(self._h, int(bool(on))))
+
     def stream_handle(self):
         """The context's cudaStream_t as an integer (sdyn_stream)."""
         L = lib()

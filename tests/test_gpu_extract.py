@@ -159,3 +159,35 @@ def test_other_orb_parameters(nfeatures, scale, nlevels, ini, mn):
         check_frame(k, d, ok, od, (scale, nlevels, idx))
         assert len(ok) > 100
     gpu.close()
+
+
+def test_latency_mode_graph_is_bit_identical():
+    """One-frame contexts replay the call as a CUDA graph (sdyn_set_latency_mode): same outputs as the stream path, across image
+    sizes (re-capture), strided inputs and a distorted camera (mvKeysUn kernel inside the graph)."""
+    import time
+    cfg = "tum"
+    W, H, _, nf, ini, mn = common.CONFIGS[cfg]
+    g = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=1)
+    s = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=1)
+    s.set_latency_mode(False)
+    for idx, crop in [(0, None), (1, None), (2, (400, 600)), (3, None), (4, (333, 301))]:
+        img = common.frame(cfg, idx)
+        if crop:
+            img = img[:crop[0], :crop[1]]          # a view with a row stride: the staging copy handles it
+        for rep in range(2):
+            kg, dg = g(img); ks, ds = s(img)
+            assert len(kg) > 100 and kg.tobytes() == ks.tobytes() and np.array_equal(dg, ds)
+    ok, od = orc.Extractor(nf, 1.2, 8, ini, mn)(common.frame(cfg, 3))
+    kg, dg = g(common.frame(cfg, 3))
+    assert kg.tobytes() == ok.tobytes() and np.array_equal(dg, od)
+    img = common.frame(cfg, 0)
+    t = []
+    for e in (g, s):
+        for _ in range(5):
+            e(img)
+        t0 = time.perf_counter()
+        for _ in range(30):
+            e(img)
+        t.append((time.perf_counter() - t0) / 30)
+    print("one-frame extraction: graph %.3f ms, stream launches %.3f ms" % (1e3 * t[0], 1e3 * t[1]))
+    g.close(); s.close()
