@@ -579,92 +579,145 @@ __device__ __forceinline__ Top2 warp_top2(uint32_t a, uint32_t b)
     return {a, b};
 }
 
-__global__ void __launch_bounds__(32)
-k_match_resolve(const MatchJob* __restrict__ jobs)
+/* Sequential claim logic of SearchForInitialization (:562-677) and SearchByBoW (:159-288, :679-812): a query's decision depends
+ * on what every earlier query did to vMatchedDistance / the matched flags, so queries are walked in order by ONE warp (the scan
+ * of a query's candidate list is lane-parallel).  What made this slow was not the walk but its memory chain — per query a
+ * dependent global load of the span, of the records and of the per-keypoint state.  Now: the per-keypoint state lives in shared
+ * memory; a second warp streams the records of the NEXT group of 32 queries (contiguous in the pool: one reservation per
+ * warp batch of k_match_candidates) into a double buffer while the walker works on the current group; empty queries (the
+ * non-level-0 keypoints of SearchForInitialization) are skipped with one ballot per group. */
+constexpr int RS_BUF = 8192;                 /* records per buffer */
+
+__global__ void __launch_bounds__(64)
+k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
 {
+    extern __shared__ int smemRes[];
     const MatchJob& J = jobs[blockIdx.x];
-    const int lane = threadIdx.x;
-    const int nq = job_nq(J);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nq = job_nq(J), n = job_n(J);
     __shared__ int hist[SDYN_HISTO_LENGTH];
     __shared__ int keep[3];
+    __shared__ int2 sSpan[2][32];
+    __shared__ int sLo[2], sStagedOk[2];
+    __shared__ int sNmatches, sNpairs;
     constexpr uint32_t NONE = 0xffffffffu;
-    int nmatches = 0, npairs = 0;
-    volatile int32_t* assign = J.assign;
-    volatile uint8_t* locked = J.locked;
-    volatile int32_t* mdist = J.matchedDist;
-    volatile int32_t* m21 = J.m21;
+    const int mode = J.mode;
     const float histFactor = 1.0f / SDYN_HISTO_LENGTH;
-
-    for (int q = 0; q < nq; ++q) {
-        const int2 span = J.qspan[q];
-        uint32_t a = NONE, b = NONE;
-        for (int p = lane; p < span.y; p += 32) {
-            const uint32_t rec = J.pool[span.x + p];
-            const int idx = rec_idx(rec), dist = rec_dist(rec);
-            bool ok;
-            if (J.mode == MM_INIT) ok = !(mdist[idx] <= dist);
-            else if (J.mode == MM_BOW) ok = assign[idx] == -1;
-            else ok = !(assign[idx] != -1 && locked[idx]);
-            if (ok) {
-                const uint32_t key = ((uint32_t)dist << 20) | (uint32_t)p;
-                if (key < a) { b = a; a = key; } else if (key < b) b = key;
-            }
+    /* per-keypoint state of the searched frame: INIT: vMatchedDistance + vnMatches21; BOW: the matched flag (assign != -1) */
+    uint32_t* buf0 = reinterpret_cast<uint32_t*>(smemRes);
+    uint32_t* buf1 = buf0 + RS_BUF;
+    int* stA = smemRes + 2 * RS_BUF;                       /* INIT: mdist, BOW: assign */
+    int* stB = stA + (stageState ? J.n : 0);               /* INIT: m21 */
+    int* mdist = mode == MM_INIT ? (stageState ? stA : J.matchedDist) : nullptr;
+    int* m21 = mode == MM_INIT ? (stageState ? stB : J.m21) : nullptr;
+    int* occ = mode == MM_INIT ? nullptr : (stageState ? stA : J.assign);
+    if (stageState) {
+        for (int k = threadIdx.x; k < n; k += 64) {
+            if (mode == MM_INIT) { stA[k] = J.matchedDist[k]; stB[k] = J.m21[k]; }
+            else stA[k] = J.assign[k];
         }
-        const Top2 t = warp_top2(a, b);
-        int accepted = -1, bin = 0;
-        if (t.a != NONE) {
-            const uint32_t r1 = J.pool[span.x + (t.a & 0xfffff)];
-            const int bestDist = (int)(t.a >> 20), bestIdx = rec_idx(r1);
-            /* second best: the reference starts from 256 (INT_MAX in SearchForInitialization), level -1 */
-            int bestDist2 = J.mode == MM_INIT ? 0x7fffffff : 256, bestLevel2 = -1;
-            if (t.b != NONE) { bestDist2 = (int)(t.b >> 20); bestLevel2 = rec_level(J.pool[span.x + (t.b & 0xfffff)]); }
-            bool ok;
-            if (J.mode == MM_FRAME) ok = bestDist <= SDYN_TH_HIGH;
-            else if (J.mode == MM_MAP)
-                ok = bestDist <= SDYN_TH_HIGH &&
-                     !(rec_level(r1) == bestLevel2 && (float)bestDist > __fmul_rn(J.nnratio, (float)bestDist2));
-            else if (J.mode == MM_INIT) ok = bestDist <= SDYN_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, J.nnratio);
-            else ok = (J.strictLow ? bestDist < SDYN_TH_LOW : bestDist <= SDYN_TH_LOW) &&
-                      (float)bestDist < __fmul_rn(J.nnratio, (float)bestDist2);
-            if (ok) {
-                accepted = bestIdx;
-                float rot = 0.f;
-                if (lane == 0) {
-                    if (J.mode == MM_FRAME) {
-                        const sdyn_last_point* lp = reinterpret_cast<const sdyn_last_point*>(J.queries) + q;
-                        assign[bestIdx] = J.assignBase + q; locked[bestIdx] = lp->obs_positive;
-                        if (J.pairs) {
-                            J.pairs[4 * npairs] = J.qKeysUn[q].x; J.pairs[4 * npairs + 1] = J.qKeysUn[q].y;
-                            J.pairs[4 * npairs + 2] = J.keysUn[bestIdx].x; J.pairs[4 * npairs + 3] = J.keysUn[bestIdx].y;
-                        }
-                    } else if (J.mode == MM_MAP) {
-                        const sdyn_mappoint_query* mp = reinterpret_cast<const sdyn_mappoint_query*>(J.queries) + q;
-                        assign[bestIdx] = J.assignBase + q; locked[bestIdx] = mp->obs_positive;
-                    } else if (J.mode == MM_INIT) {
-                        const int prev = m21[bestIdx];
-                        if (prev >= 0) { assign[prev] = -1; --nmatches; }
-                        assign[q] = bestIdx; m21[bestIdx] = q; mdist[bestIdx] = bestDist;
-                    } else {
-                        assign[bestIdx] = reinterpret_cast<const BowQuery*>(J.queries)[q].kfIdx;
+    }
+    if (threadIdx.x == 0) { sNmatches = 0; sNpairs = 0; }
+    __syncthreads();
+
+    const int ngroups = (nq + 31) / 32;
+    auto prefetch = [&](int g) {                           /* warp 1: spans + records of group g -> buffer g & 1 */
+        const int q = g * 32 + lane;
+        const int2 sp = q < nq ? J.qspan[q] : make_int2(0, 0);
+        int lo = sp.y > 0 ? sp.x : 0x7fffffff, hi = sp.y > 0 ? sp.x + sp.y : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        sSpan[g & 1][lane] = sp;
+        const bool fits = hi > lo && hi - lo <= RS_BUF;
+        if (lane == 0) { sLo[g & 1] = lo; sStagedOk[g & 1] = fits; }
+        if (fits) {
+            uint32_t* dst = (g & 1) ? buf1 : buf0;
+            for (int i = lane; i < hi - lo; i += 32) dst[i] = __ldg(J.pool + lo + i);
+        }
+    };
+    if (warp == 1 && ngroups > 0) prefetch(0);
+    __syncthreads();
+
+    int nmatches = 0, npairs = 0;
+    for (int g = 0; g < ngroups; ++g) {
+        if (warp == 1) { if (g + 1 < ngroups) prefetch(g + 1); }
+        else {
+            const int2 mySpan = sSpan[g & 1][lane];
+            const uint32_t* recs = sStagedOk[g & 1] ? ((g & 1) ? buf1 : buf0) - sLo[g & 1] : J.pool;   /* indexable by pool offset */
+            unsigned todo = __ballot_sync(0xffffffffu, mySpan.y > 0);
+            if (lane == 0 && ~todo) { }                    /* (queries without candidates keep qAccepted = -1 below) */
+            const int qme = g * 32 + lane;
+            if (qme < nq && mySpan.y == 0) { J.qAccepted[qme] = -1; J.qBin[qme] = 0; }
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int q = g * 32 + j;
+                const int sx = __shfl_sync(0xffffffffu, mySpan.x, j), sy = __shfl_sync(0xffffffffu, mySpan.y, j);
+                uint32_t a = NONE, b = NONE;
+                for (int p = lane; p < sy; p += 32) {
+                    const uint32_t rec = recs[sx + p];
+                    const int idx = rec_idx(rec), dist = rec_dist(rec);
+                    const bool ok = mode == MM_INIT ? !(mdist[idx] <= dist) : occ[idx] == -1;
+                    if (ok) {
+                        const uint32_t key = ((uint32_t)dist << 20) | (uint32_t)p;
+                        if (key < a) { b = a; a = key; } else if (key < b) b = key;
                     }
                 }
-                ++nmatches; ++npairs;
-                if (J.checkOri && J.mode != MM_MAP) {
-                    if (J.mode == MM_FRAME) rot = __fsub_rn(J.qKeysUn[q].angle, J.keysUn[bestIdx].angle);
-                    else if (J.mode == MM_INIT) rot = __fsub_rn(J.qKeys[q].angle, J.keysUn[bestIdx].angle);
-                    else rot = __fsub_rn(J.qKeys[reinterpret_cast<const BowQuery*>(J.queries)[q].kfIdx].angle, J.keysUn[bestIdx].angle);
-                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                    bin = (int)roundf(__fmul_rn(rot, histFactor));
-                    if (bin == SDYN_HISTO_LENGTH) bin = 0;
+                const Top2 t = warp_top2(a, b);
+                int accepted = -1, bin = 0;
+                if (t.a != NONE) {
+                    const uint32_t r1 = recs[sx + (t.a & 0xfffff)];
+                    const int bestDist = (int)(t.a >> 20), bestIdx = rec_idx(r1);
+                    /* second best: the reference starts from INT_MAX in SearchForInitialization, 256 in SearchByBoW */
+                    int bestDist2 = mode == MM_INIT ? 0x7fffffff : 256;
+                    if (t.b != NONE) bestDist2 = (int)(t.b >> 20);
+                    bool ok;
+                    if (mode == MM_INIT) ok = bestDist <= SDYN_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, J.nnratio);
+                    else ok = (J.strictLow ? bestDist < SDYN_TH_LOW : bestDist <= SDYN_TH_LOW) &&
+                              (float)bestDist < __fmul_rn(J.nnratio, (float)bestDist2);
+                    if (ok) {
+                        accepted = bestIdx;
+                        if (lane == 0) {
+                            if (mode == MM_INIT) {
+                                const int prev = m21[bestIdx];
+                                if (prev >= 0) { J.assign[prev] = -1; --nmatches; }
+                                J.assign[q] = bestIdx; m21[bestIdx] = q; mdist[bestIdx] = bestDist;
+                            } else {
+                                occ[bestIdx] = reinterpret_cast<const BowQuery*>(J.queries)[q].kfIdx;
+                            }
+                        }
+                        ++nmatches; ++npairs;
+                        if (J.checkOri) {
+                            float rot;
+                            if (mode == MM_INIT) rot = __fsub_rn(J.qKeys[q].angle, J.keysUn[bestIdx].angle);
+                            else rot = __fsub_rn(J.qKeys[reinterpret_cast<const BowQuery*>(J.queries)[q].kfIdx].angle, J.keysUn[bestIdx].angle);
+                            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                            bin = (int)roundf(__fmul_rn(rot, histFactor));
+                            if (bin == SDYN_HISTO_LENGTH) bin = 0;
+                        }
+                    }
                 }
+                if (lane == 0) { J.qAccepted[q] = accepted; J.qBin[q] = bin; }
+                __syncwarp();
             }
         }
-        if (lane == 0) { J.qAccepted[q] = accepted; J.qBin[q] = bin; }
-        __syncwarp();
+        __syncthreads();                                   /* buffer (g + 1) & 1 is filled, buffer g & 1 is free */
     }
+    if (warp == 0 && lane == 0) { sNmatches = nmatches; sNpairs = npairs; }
+    __syncthreads();
+    /* write the staged per-keypoint state back (the walk is over: both warps help) */
+    if (stageState) {
+        for (int k = threadIdx.x; k < n; k += 64) {
+            if (mode == MM_INIT) { J.matchedDist[k] = stA[k]; J.m21[k] = stB[k]; }
+            else J.assign[k] = stA[k];
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    nmatches = sNmatches; npairs = sNpairs;
 
     /* rotation-consistency cull (ComputeThreeMaxima) */
-    if (J.checkOri && J.mode != MM_MAP) {
+    if (J.checkOri) {
         for (int i = lane; i < SDYN_HISTO_LENGTH; i += 32) hist[i] = 0;
         __syncwarp();
         for (int q = lane; q < nq; q += 32) if (J.qAccepted[q] >= 0) atomicAdd(&hist[J.qBin[q]], 1);
@@ -672,10 +725,10 @@ k_match_resolve(const MatchJob* __restrict__ jobs)
         if (lane == 0) {
             int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
             for (int i = 0; i < SDYN_HISTO_LENGTH; ++i) {
-                const int s = hist[i];
-                if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
-                else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
-                else if (s > max3) { max3 = s; i3 = i; }
+                const int sz = hist[i];
+                if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; i3 = i2; i2 = i1; i1 = i; }
+                else if (sz > max2) { max3 = max2; max2 = sz; i3 = i2; i2 = i; }
+                else if (sz > max3) { max3 = sz; i3 = i; }
             }
             if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
             else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) i3 = -1;
@@ -688,7 +741,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs)
             if (acc < 0) continue;
             const int bin = J.qBin[q];
             if (bin == keep[0] || bin == keep[1] || bin == keep[2]) continue;
-            if (J.mode == MM_INIT) { if (J.assign[q] >= 0) { J.assign[q] = -1; ++dec; } }
+            if (mode == MM_INIT) { if (J.assign[q] >= 0) { J.assign[q] = -1; ++dec; } }
             else { J.assign[acc] = -1; if (J.locked) J.locked[acc] = 0; ++dec; }
         }
 #pragma unroll
@@ -696,7 +749,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs)
         nmatches -= dec;
     }
     __syncwarp();
-    if (J.mode == MM_INIT) {   /* update vbPrevMatched (:671-674) */
+    if (mode == MM_INIT) {   /* update vbPrevMatched (:671-674) */
         for (int q = lane; q < nq; q += 32) {
             const int m = J.assign[q];
             if (m >= 0) { J.prevMatched[2 * q] = J.keysUn[m].x; J.prevMatched[2 * q + 1] = J.keysUn[m].y; }
@@ -1044,7 +1097,13 @@ cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int
         if (e != cudaSuccess) return e;
         k_match_resolve_fix<<<njobs, RF, smem, st>>>(dJobs, poolCap, second);
     } else {
-        k_match_resolve<<<njobs, 32, 0, st>>>(dJobs);
+        /* record double buffer + the per-keypoint state (2 ints per keypoint for SearchForInitialization) when it fits */
+        const size_t stateB = (size_t)2 * maxN * sizeof(int);
+        const int stage = 2 * RS_BUF * 4 + stateB <= 200 * 1024;
+        const size_t smem = (size_t)2 * RS_BUF * 4 + (stage ? stateB : 0);
+        cudaError_t e = cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_match_resolve<<<njobs, 64, smem, st>>>(dJobs, stage);
     }
     return cudaGetLastError();
 }
