@@ -392,12 +392,15 @@ def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptr
     # BASELINE config 3: stereo pairs through the whole step — both extractions, ComputeStereoMatches, the two searches
     # with mvuRight gates, dynamic mask — on this rank's sequence (right views rendered with an 11 px disparity)
     if strides[0] <= L.cap:
-        dright = torch.from_numpy(make_frames(cfg, rank, 0, Bs, disparity=11)).cuda()
+        NS = 8                                    # the slots advance one frame per step, like the headline run (resident LastFrame)
+        dright = torch.from_numpy(make_frames(cfg, rank, 0, Bs + NS, disparity=11)).cuda()
         sp = dict(params); sp["mono"] = 0
-        tin = pysdyn.track_inputs(dptrs, 0, strides, sp, map_table=mtab, frame_pitch=pitch)
+        kstep = [0]
 
         def stereo_track_step():
-            pysdyn.track_batch_stereo_device(L, R, Bs, dev_frames[0].data_ptr(), dright.data_ptr(), W * H, W, H, W, tin, mb, mbf)
+            i0 = kstep[0] % NS; kstep[0] += 1
+            tin = pysdyn.track_inputs(dptrs, i0, strides, sp, map_table=mtab, frame_pitch=pitch)
+            pysdyn.track_batch_stereo_device(L, R, Bs, dev_frames[i0].data_ptr(), dright[i0].data_ptr(), W * H, W, H, W, tin, mb, mbf)
 
         for _ in range(3):
             stereo_track_step()
@@ -407,6 +410,9 @@ def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptr
             stereo_track_step()
         L.sync(); R.sync()
         dt3 = time.perf_counter() - t0
+        while kstep[0] % NS in (0, 1):            # report the counts of a step whose LastFrame was the slot's previous frame
+            stereo_track_step()
+        L.sync(); R.sync()
         ur3, dp3, kept3 = pysdyn.stereo_fetch(L, Bs)
         a3, l3, m3, c3 = pysdyn.track_fetch(L, Bs)
         out["stereo_track_config3"] = {"pairs_per_s": Bs * steps / dt3, "ms_per_step": 1e3 * dt3 / steps, "pairs_per_step": Bs,

@@ -601,7 +601,14 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
     __shared__ int sLo[2], sStagedOk[2];
     __shared__ int sNmatches, sNpairs;
     constexpr uint32_t NONE = 0xffffffffu;
-    const int mode = J.mode;
+    /* job fields the walk reads: copied out once (`J.x` inside the loop would be a dependent global load per query) */
+    const int mode = J.mode, checkOri = J.checkOri, strictLow = J.strictLow;
+    const float nnratio = J.nnratio;
+    const uint32_t* pool = J.pool;
+    const int2* qspan = J.qspan;
+    int32_t* qAccepted = J.qAccepted; int32_t* qBin = J.qBin; int32_t* assignOut = J.assign;
+    const sdyn_keypoint* qKeys = J.qKeys; const sdyn_keypoint* keysUn = J.keysUn;
+    const BowQuery* bowq = reinterpret_cast<const BowQuery*>(J.queries);
     const float histFactor = 1.0f / SDYN_HISTO_LENGTH;
     /* per-keypoint state of the searched frame: INIT: vMatchedDistance + vnMatches21; BOW: the matched flag (assign != -1) */
     uint32_t* buf0 = reinterpret_cast<uint32_t*>(smemRes);
@@ -623,7 +630,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
     const int ngroups = (nq + 31) / 32;
     auto prefetch = [&](int g) {                           /* warp 1: spans + records of group g -> buffer g & 1 */
         const int q = g * 32 + lane;
-        const int2 sp = q < nq ? J.qspan[q] : make_int2(0, 0);
+        const int2 sp = q < nq ? qspan[q] : make_int2(0, 0);
         int lo = sp.y > 0 ? sp.x : 0x7fffffff, hi = sp.y > 0 ? sp.x + sp.y : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
@@ -632,7 +639,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
         if (lane == 0) { sLo[g & 1] = lo; sStagedOk[g & 1] = fits; }
         if (fits) {
             uint32_t* dst = (g & 1) ? buf1 : buf0;
-            for (int i = lane; i < hi - lo; i += 32) dst[i] = __ldg(J.pool + lo + i);
+            for (int i = lane; i < hi - lo; i += 32) dst[i] = __ldg(pool + lo + i);
         }
     };
     if (warp == 1 && ngroups > 0) prefetch(0);
@@ -643,11 +650,10 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
         if (warp == 1) { if (g + 1 < ngroups) prefetch(g + 1); }
         else {
             const int2 mySpan = sSpan[g & 1][lane];
-            const uint32_t* recs = sStagedOk[g & 1] ? ((g & 1) ? buf1 : buf0) - sLo[g & 1] : J.pool;   /* indexable by pool offset */
+            const uint32_t* recs = sStagedOk[g & 1] ? ((g & 1) ? buf1 : buf0) - sLo[g & 1] : pool;   /* indexable by pool offset */
             unsigned todo = __ballot_sync(0xffffffffu, mySpan.y > 0);
-            if (lane == 0 && ~todo) { }                    /* (queries without candidates keep qAccepted = -1 below) */
             const int qme = g * 32 + lane;
-            if (qme < nq && mySpan.y == 0) { J.qAccepted[qme] = -1; J.qBin[qme] = 0; }
+            if (qme < nq && mySpan.y == 0) { qAccepted[qme] = -1; qBin[qme] = 0; }
             while (todo) {
                 const int j = __ffs(todo) - 1;
                 todo &= todo - 1;
@@ -672,32 +678,25 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
                     int bestDist2 = mode == MM_INIT ? 0x7fffffff : 256;
                     if (t.b != NONE) bestDist2 = (int)(t.b >> 20);
                     bool ok;
-                    if (mode == MM_INIT) ok = bestDist <= SDYN_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, J.nnratio);
-                    else ok = (J.strictLow ? bestDist < SDYN_TH_LOW : bestDist <= SDYN_TH_LOW) &&
-                              (float)bestDist < __fmul_rn(J.nnratio, (float)bestDist2);
+                    if (mode == MM_INIT) ok = bestDist <= SDYN_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, nnratio);
+                    else ok = (strictLow ? bestDist < SDYN_TH_LOW : bestDist <= SDYN_TH_LOW) &&
+                              (float)bestDist < __fmul_rn(nnratio, (float)bestDist2);
                     if (ok) {
                         accepted = bestIdx;
                         if (lane == 0) {
                             if (mode == MM_INIT) {
                                 const int prev = m21[bestIdx];
-                                if (prev >= 0) { J.assign[prev] = -1; --nmatches; }
-                                J.assign[q] = bestIdx; m21[bestIdx] = q; mdist[bestIdx] = bestDist;
+                                if (prev >= 0) { assignOut[prev] = -1; --nmatches; }
+                                assignOut[q] = bestIdx; m21[bestIdx] = q; mdist[bestIdx] = bestDist;
                             } else {
-                                occ[bestIdx] = reinterpret_cast<const BowQuery*>(J.queries)[q].kfIdx;
+                                occ[bestIdx] = bowq[q].kfIdx;
                             }
                         }
                         ++nmatches; ++npairs;
-                        if (J.checkOri) {
-                            float rot;
-                            if (mode == MM_INIT) rot = __fsub_rn(J.qKeys[q].angle, J.keysUn[bestIdx].angle);
-                            else rot = __fsub_rn(J.qKeys[reinterpret_cast<const BowQuery*>(J.queries)[q].kfIdx].angle, J.keysUn[bestIdx].angle);
-                            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                            bin = (int)roundf(__fmul_rn(rot, histFactor));
-                            if (bin == SDYN_HISTO_LENGTH) bin = 0;
-                        }
                     }
                 }
-                if (lane == 0) { J.qAccepted[q] = accepted; J.qBin[q] = bin; }
+                if (lane == 0) qAccepted[q] = accepted;      /* the rotation bin follows after the walk, in parallel */
+                (void)bin;
                 __syncwarp();
             }
         }
@@ -705,6 +704,18 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
     }
     if (warp == 0 && lane == 0) { sNmatches = nmatches; sNpairs = npairs; }
     __syncthreads();
+    /* rotation bin of every accepted query (an entry stays in the histogram even if the keypoint is stolen later, as in the
+     * reference's rotHist): the two angle loads are off the sequential walk */
+    if (checkOri)
+        for (int q = threadIdx.x; q < nq; q += 64) {
+            const int acc = qAccepted[q];
+            if (acc < 0) { qBin[q] = 0; continue; }
+            float rot = __fsub_rn(mode == MM_INIT ? qKeys[q].angle : qKeys[bowq[q].kfIdx].angle, keysUn[acc].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, histFactor));
+            if (bin == SDYN_HISTO_LENGTH) bin = 0;
+            qBin[q] = bin;
+        }
     /* write the staged per-keypoint state back (the walk is over: both warps help) */
     if (stageState) {
         for (int k = threadIdx.x; k < n; k += 64) {
@@ -717,7 +728,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
     nmatches = sNmatches; npairs = sNpairs;
 
     /* rotation-consistency cull (ComputeThreeMaxima) */
-    if (J.checkOri) {
+    if (checkOri) {
         for (int i = lane; i < SDYN_HISTO_LENGTH; i += 32) hist[i] = 0;
         __syncwarp();
         for (int q = lane; q < nq; q += 32) if (J.qAccepted[q] >= 0) atomicAdd(&hist[J.qBin[q]], 1);
