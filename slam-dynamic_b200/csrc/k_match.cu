@@ -588,7 +588,10 @@ __device__ __forceinline__ Top2 warp_top2(uint32_t a, uint32_t b)
  * non-level-0 keypoints of SearchForInitialization) are skipped with one ballot per group. */
 constexpr int RS_BUF = 8192;                 /* records per buffer */
 
-__global__ void __launch_bounds__(64)
+constexpr int RS_PW = 8;                    /* prefetch warps */
+constexpr int RS_T = 32 * (1 + RS_PW);
+
+__global__ void __launch_bounds__(RS_T)
 k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
 {
     extern __shared__ int smemRes[];
@@ -597,8 +600,8 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
     const int nq = job_nq(J), n = job_n(J);
     __shared__ int hist[SDYN_HISTO_LENGTH];
     __shared__ int keep[3];
-    __shared__ int2 sSpan[2][32];
-    __shared__ int sLo[2], sStagedOk[2];
+    __shared__ int2 sSpan[2][32];            /* per query of the group: (offset into the packed buffer | pool, count) */
+    __shared__ int sStagedOk[2];
     __shared__ int sNmatches, sNpairs;
     constexpr uint32_t NONE = 0xffffffffu;
     /* job fields the walk reads: copied out once (`J.x` inside the loop would be a dependent global load per query) */
@@ -619,7 +622,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
     int* m21 = mode == MM_INIT ? (stageState ? stB : J.m21) : nullptr;
     int* occ = mode == MM_INIT ? nullptr : (stageState ? stA : J.assign);
     if (stageState) {
-        for (int k = threadIdx.x; k < n; k += 64) {
+        for (int k = threadIdx.x; k < n; k += RS_T) {
             if (mode == MM_INIT) { stA[k] = J.matchedDist[k]; stB[k] = J.m21[k]; }
             else stA[k] = J.assign[k];
         }
@@ -628,29 +631,37 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
     __syncthreads();
 
     const int ngroups = (nq + 31) / 32;
-    auto prefetch = [&](int g) {                           /* warp 1: spans + records of group g -> buffer g & 1 */
+    /* prefetch warps 1..RS_PW: the candidate records of group g, PACKED back to back (a query's pool slot is as large as its
+     * un-gated bound, its written records are few), into buffer g & 1; warp w copies queries 4(w-1) .. 4(w-1)+3 */
+    auto prefetch = [&](int g) {
         const int q = g * 32 + lane;
         const int2 sp = q < nq ? qspan[q] : make_int2(0, 0);
-        int lo = sp.y > 0 ? sp.x : 0x7fffffff, hi = sp.y > 0 ? sp.x + sp.y : 0;
+        int incl = sp.y;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-        sSpan[g & 1][lane] = sp;
-        const bool fits = hi > lo && hi - lo <= RS_BUF;
-        if (lane == 0) { sLo[g & 1] = lo; sStagedOk[g & 1] = fits; }
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - sp.y;
+        const bool fits = total <= RS_BUF;
+        if (warp == 1) {
+            sSpan[g & 1][lane] = make_int2(fits ? off : sp.x, sp.y);
+            if (lane == 0) sStagedOk[g & 1] = fits;
+        }
         if (fits) {
             uint32_t* dst = (g & 1) ? buf1 : buf0;
-            for (int i = lane; i < hi - lo; i += 32) dst[i] = __ldg(pool + lo + i);
+            for (int j = 4 * (warp - 1); j < 4 * warp; ++j) {
+                const int sx = __shfl_sync(0xffffffffu, sp.x, j), sy = __shfl_sync(0xffffffffu, sp.y, j), so = __shfl_sync(0xffffffffu, off, j);
+                for (int i = lane; i < sy; i += 32) dst[so + i] = __ldg(pool + sx + i);
+            }
         }
     };
-    if (warp == 1 && ngroups > 0) prefetch(0);
+    if (warp >= 1 && ngroups > 0) prefetch(0);
     __syncthreads();
 
     int nmatches = 0, npairs = 0;
     for (int g = 0; g < ngroups; ++g) {
-        if (warp == 1) { if (g + 1 < ngroups) prefetch(g + 1); }
+        if (warp >= 1) { if (g + 1 < ngroups) prefetch(g + 1); }
         else {
             const int2 mySpan = sSpan[g & 1][lane];
-            const uint32_t* recs = sStagedOk[g & 1] ? ((g & 1) ? buf1 : buf0) - sLo[g & 1] : pool;   /* indexable by pool offset */
+            const uint32_t* recs = sStagedOk[g & 1] ? ((g & 1) ? buf1 : buf0) : pool;   /* sSpan offsets index whichever it is */
             unsigned todo = __ballot_sync(0xffffffffu, mySpan.y > 0);
             const int qme = g * 32 + lane;
             if (qme < nq && mySpan.y == 0) { qAccepted[qme] = -1; qBin[qme] = 0; }
@@ -707,7 +718,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
     /* rotation bin of every accepted query (an entry stays in the histogram even if the keypoint is stolen later, as in the
      * reference's rotHist): the two angle loads are off the sequential walk */
     if (checkOri)
-        for (int q = threadIdx.x; q < nq; q += 64) {
+        for (int q = threadIdx.x; q < nq; q += RS_T) {
             const int acc = qAccepted[q];
             if (acc < 0) { qBin[q] = 0; continue; }
             float rot = __fsub_rn(mode == MM_INIT ? qKeys[q].angle : qKeys[bowq[q].kfIdx].angle, keysUn[acc].angle);
@@ -718,7 +729,7 @@ k_match_resolve(const MatchJob* __restrict__ jobs, int stageState)
         }
     /* write the staged per-keypoint state back (the walk is over: both warps help) */
     if (stageState) {
-        for (int k = threadIdx.x; k < n; k += 64) {
+        for (int k = threadIdx.x; k < n; k += RS_T) {
             if (mode == MM_INIT) { J.matchedDist[k] = stA[k]; J.m21[k] = stB[k]; }
             else J.assign[k] = stA[k];
         }
@@ -1114,7 +1125,7 @@ cudaError_t launch_match_resolve(const MatchJob* dJobs, int njobs, int mode, int
         const size_t smem = (size_t)2 * RS_BUF * 4 + (stage ? stateB : 0);
         cudaError_t e = cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k_match_resolve<<<njobs, 64, smem, st>>>(dJobs, stage);
+        k_match_resolve<<<njobs, RS_T, smem, st>>>(dJobs, stage);
     }
     return cudaGetLastError();
 }
