@@ -23,38 +23,7 @@ def track_frame(keys, desc, scale, W, H, arrays, f, params, last_stride, keys_un
     nm = int(arrays["n_map"][f])
     n2, assign, locked = orc.match_projection_map(cur, arrays["map_points"][f, :nm], params["th_map"],
                                                   params["nnratio_map"], assign, locked, assign_base=last_stride)
-    # dynamic mask: firstSeparate (+ erase bug) -> Separate (BF + classifyF + gates) -> UpdateFrame
-    nb = int(arrays["n_boxes"][f])
-    boxes = arrays["boxes"][f, :nb]
-    in_box = orc.box_mask(keys, boxes) != 0
-    sep = orc.first_separate(keys, boxes, np.arange(nb))
-    slots = {}
-    for s, k in sep["dyn"]:
-        slots.setdefault(s, []).append(k)
-    readmit = np.zeros(len(keys), bool)
-    static_exit = False
-    for s in range(len(sep["boxes"])):
-        surv = int(sep["box_idx"][s])                  # original id of the box now in slot s
-        r = int(arrays["ref_box"][f, surv])
-        ks = slots.get(s, [])
-        if r < 0 or not ks:
-            continue
-        o0, o1 = int(arrays["ref_off"][f, r]), int(arrays["ref_off"][f, r + 1])
-        if o1 == o0:
-            continue
-        ku = keys if keys_un is None else keys_un      # classifyF reads mvdynKeysUn (Tracking.cc:1129-1131)
-        qd = desc[ks]; qx = np.stack([ku["x"][ks], ku["y"][ks]], 1)
-        mq, mt, md, fd = orc.separate_pairs([(qd, qx, arrays["ref_desc"][f, o0:o1], arrays["ref_xy"][f, o0:o1])],
-                                            arrays["fmat"][f], 0)[0]
-        good = len(mq)
-        if good < 3 or good < 0.2 * len(ks):
-            continue
-        num0 = int((fd != -1).sum())
-        for q in fd[fd != -1]:
-            readmit[ks[int(q)]] = True
-        if num0 > max(1.0, 0.2 * good):
-            static_exit = True
-    dyn = in_box & ~(readmit & static_exit)
+    in_box, dyn = dyn_mask(keys, desc, arrays, f, keys_un)
     return assign, locked, dyn.astype(np.uint8), np.array([n1, n2, int(in_box.sum()), int(dyn.sum())], np.int32)
 
 
@@ -114,3 +83,41 @@ def track_frame_rgbd(keys, desc, scale, W, H, arrays, f, params, last_stride, la
                                                   assign_base=last_stride)
     dyn = in_box & ~readmit
     return order, ns, assign, locked, dyn.astype(np.uint8), np.array([n1, n2, int(in_box.sum()), int(dyn.sum())], np.int32), cur
+
+
+def dyn_mask(keys, desc, arrays, f, keys_un=None):
+    """(in_box, masked) per extracted keypoint: firstSeparate's box test, Separate's per-box BFMatcher + classifyF with its gates,
+    UpdateFrame's re-admission (stereo-constructor bookkeeping: the frame keeps every keypoint)."""
+    # dynamic mask: firstSeparate (+ erase bug) -> Separate (BF + classifyF + gates) -> UpdateFrame
+    nb = int(arrays["n_boxes"][f])
+    boxes = arrays["boxes"][f, :nb]
+    in_box = orc.box_mask(keys, boxes) != 0
+    sep = orc.first_separate(keys, boxes, np.arange(nb))
+    slots = {}
+    for s, k in sep["dyn"]:
+        slots.setdefault(s, []).append(k)
+    readmit = np.zeros(len(keys), bool)
+    static_exit = False
+    for s in range(len(sep["boxes"])):
+        surv = int(sep["box_idx"][s])                  # original id of the box now in slot s
+        r = int(arrays["ref_box"][f, surv])
+        ks = slots.get(s, [])
+        if r < 0 or not ks:
+            continue
+        o0, o1 = int(arrays["ref_off"][f, r]), int(arrays["ref_off"][f, r + 1])
+        if o1 == o0:
+            continue
+        ku = keys if keys_un is None else keys_un      # classifyF reads mvdynKeysUn (Tracking.cc:1129-1131)
+        qd = desc[ks]; qx = np.stack([ku["x"][ks], ku["y"][ks]], 1)
+        mq, mt, md, fd = orc.separate_pairs([(qd, qx, arrays["ref_desc"][f, o0:o1], arrays["ref_xy"][f, o0:o1])],
+                                            arrays["fmat"][f], 0)[0]
+        good = len(mq)
+        if good < 3 or good < 0.2 * len(ks):
+            continue
+        num0 = int((fd != -1).sum())
+        for q in fd[fd != -1]:
+            readmit[ks[int(q)]] = True
+        if num0 > max(1.0, 0.2 * good):
+            static_exit = True
+    dyn = in_box & ~(readmit & static_exit)
+    return in_box, dyn
