@@ -606,7 +606,9 @@ def main():
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa_node(local)                     # before any pinned allocation
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a rank that dies (assert, CUDA error) must not leave the others waiting for the default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
 
     cfg = args.workload
     W, H, nrect, nf, ini, mn, _ = WORKLOADS[cfg]
@@ -716,9 +718,8 @@ def main():
         return max(e0[0].elapsed_time(e1[c]) for c in range(NCTX))     # first start .. last finish, on the device
 
     dev_runs = [device_region()]
-    reps = int(min(max(1, np.ceil(500.0 / max(dev_runs[0], 1e-3))), 40)) if args.min_seconds > 0 else 1
-    reps = max(reps, int(np.ceil(args.min_seconds * 1e3 / max(dev_runs[0], 1e-3)))) if args.min_seconds > 0 else 1
-    reps = min(reps, 60)
+    from pysdyn import shard
+    reps = shard.region_count(dev_runs[0] * 1e-3, args.min_seconds, 1, 60)            # identical on every rank
     dev_runs += [device_region() for _ in range(reps - 1)]
     ms = float(np.median(dev_runs))
     launches = (sum(c.launch_count() for c in ctxs) - launches0) // len(dev_runs)
@@ -770,13 +771,18 @@ def main():
     run_host(step_no, 3 * NCTX); step_no += 3 * NCTX
     barrier()
     e2e_runs = []
-    t_e2e0 = time.perf_counter()
-    while len(e2e_runs) < 5 or (time.perf_counter() - t_e2e0 < args.min_seconds and len(e2e_runs) < 60):
+
+    def e2e_region():
+        nonlocal step_no
         barrier()
         t0 = time.perf_counter()
         run_host(step_no, K); step_no += K
         barrier()
-        e2e_runs.append(time.perf_counter() - t0)
+        return time.perf_counter() - t0
+
+    e2e_runs.append(e2e_region())
+    ereps = shard.region_count(e2e_runs[0], args.min_seconds, 5, 60)                  # identical on every rank
+    e2e_runs += [e2e_region() for _ in range(ereps - 1)]
     e2e_s = float(np.median(e2e_runs))
     clocks = sampler.stop(t_clk0, time.perf_counter()) if sampler else None
 
@@ -824,7 +830,6 @@ def main():
         del src, dst
     d2h = B * (cap * (28 + 32) + 4 + cap * 6 + 16)
 
-    from pysdyn import shard
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)               # timing: max over ranks
@@ -833,9 +838,11 @@ def main():
                             float(int(rank_digest[:12], 16)), float(link["h2d_gbs_pinned_copy"]), float(B * K / e2e_s),
                             float(-1 if numa.get("gpu_node") is None else numa["gpu_node"])])
     ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    if world > 1:                       # every collective of the run is behind us: all ranks tear the communicator down together
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     total_frames = float(g[:, 0].sum())
@@ -893,7 +900,7 @@ def main():
         pass
 
     cpu = None
-    if args.cpu_seconds > 0:
+    if args.cpu_seconds > 0 and world == 1:             # the CPU baseline is a rank-0, N=1 measurement
         cframes, carrays, cparams, ccap = cpu_prepare(cfg, 8)
         cpre = ref_prebuild(cfg, None, carrays, cparams) if ref_available() else None
         cpu1, n1 = cpu_run(cfg, cframes, carrays, cparams, ccap, 1, seconds=args.cpu_seconds, pre=cpre)
@@ -993,8 +1000,6 @@ def main():
         "next_rows": extras,
     }
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -31,3 +31,25 @@ def gather_stats(vec):
     out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
     dist.all_gather(out, t)
     return torch.stack(out).cpu().numpy()
+
+
+def agree_max(x):
+    """max over ranks of a scalar — the same value on every rank (identity when not distributed)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(x)
+    v = torch.tensor([float(x)], dtype=torch.float64)
+    if dist.get_backend() == "nccl":
+        v = v.cuda()
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    return float(v[0])
+
+
+def region_count(first_region_seconds, min_seconds, lo=1, hi=60):
+    """How many times a timed region is repeated so that it covers min_seconds.  The count comes from a rank's own clock, so
+    it is agreed over the ranks (max of the first region's time) before use: every region contains barriers, and ranks that
+    ran different numbers of regions would issue different numbers of collectives and hang."""
+    t = agree_max(first_region_seconds)
+    n = int(np.ceil(min_seconds / max(t, 1e-9))) if min_seconds > 0 else lo
+    return int(min(max(lo, n), hi))

@@ -67,3 +67,34 @@ def test_shard_units_partition():
     for world in (1, 2, 4, 8):
         seen = sorted(u for r in range(world) for u in shard.shard_units(13, r, world))
         assert seen == list(range(13))
+
+
+def region_worker(rank, world, port, q):
+    """bench.py's timed regions: each rank measures its own first region, the repetition count must still be the same."""
+    import torch.distributed as dist
+    from pysdyn import shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = shard.region_count(0.011 * (1 + 3 * rank), 0.5, 5, 60)       # rank 1 is 4x slower than rank 0
+    for _ in range(n):                                                  # a different n per rank would deadlock here
+        dist.barrier()
+    g = shard.gather_stats([float(n)])
+    if rank == 0:
+        q.put(g[:, 0].tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_region_count_is_agreed_over_ranks():
+    from pysdyn import shard
+    assert shard.region_count(0.011, 0.5, 5, 60) == 46 and shard.region_count(10.0, 0.5, 5, 60) == 5
+    assert shard.region_count(1e-6, 0.5, 1, 60) == 60 and shard.region_count(0.1, 0.0, 1, 60) == 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=region_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    counts = q.get(timeout=120)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert counts == [12.0, 12.0]                                        # ceil(0.5 / 0.044), from the slower rank
