@@ -29,6 +29,7 @@ WORKLOADS = {
     "tum": (640, 480, 120, 1000, 20, 7, 1),         # Examples/RGB-D/TUM3.yaml
     "4k": (3840, 2160, 2800, 8000, 20, 7, 4),       # stress config
 }
+RGBD_CTOR = {"tum"}  # workloads tracked with RGB-D-constructor semantics (rgbd_split: static keypoints + re-admitted ones, Frame.cc:297-403)
 POOL = 256          # distinct frames per GPU (frame_idx 0..255)
 NLEVELS, SCALE = 8, 1.2
 N_MAP = 3000        # local-map points per frame (2000-5000)
@@ -256,6 +257,11 @@ def cpu_prepare(cfg, nframes, threads=1):
     arrays = scenario.build_track_batch(kd, seq_seed(cfg, 0), 0, W, H, nrect, NLEVELS, cap, N_MAP, REF_STRIDE,
                                         n_map=N_MAP, seed=3, offsets=pool_offsets, time=pool_time, frustum=True,
                                         scale=orc.Extractor(nf, SCALE, NLEVELS, ini, mn).scale)
+    if cfg in RGBD_CTOR:                   # LastFrame of input f = the list frame f-1 was tracked with (input f-1's own product)
+        import oracle_track
+        orders = [oracle_track.rgbd_order(kd[f + 1][0], kd[f + 1][1], arrays, f)[0] for f in range(len(kd) - 2)]
+        for f, o in enumerate(orders):
+            scenario.reorder_last(arrays, f + 1, o)
     return frames[1:], arrays, scenario.track_params(W, H), cap
 
 
@@ -300,6 +306,7 @@ def cpu_run(cfg, frames, arrays, params, cap, threads, seconds=None, count=None,
     import orc
     import oracle_track
     W, H, _, nf, ini, mn, _ = WORKLOADS[cfg]
+    split = cfg in RGBD_CTOR
     done = [0] * threads
     t0 = time.perf_counter()
 
@@ -320,15 +327,20 @@ def cpu_run(cfg, frames, arrays, params, cap, threads, seconds=None, count=None,
                 _, prebuilt, camt = pre
                 last, lpts, mpts = prebuilt[f]
                 k, d = RE(frames[f])                                                  # src/ORBextractor.cc
+                if split:                 # the RGB-D constructor's list: firstSeparate + Separate + UpdateFrame (the port, small)
+                    order, _, in_box, _ = oracle_track.rgbd_order(k, d, arrays, f)
+                    cid = np.where(in_box, np.arange(len(k)), -1).astype(np.int32)
+                    k = k[order].copy(); k["class_id"] = cid[order]; d = np.ascontiguousarray(d[order])
                 cur = ref.Frame.from_arrays(RE, k, d, (0.0, 0.0, float(W), float(H)), camt, tcw=arrays["poses"][f, :12])   # Frame.cc:463-478
                 ref.search_by_projection_frame(cur, last, params["th_frame"], bool(params["mono"]), 0.9, bool(params["check_orientation"]))
                 ref.points_in_frustum(cur, mpts, 0.5)                                 # Frame.cc:677-733 for every local-map point
                 ref.search_by_projection_map(cur, mpts, params["th_map"], params["nnratio_map"])
-                oracle_track.dyn_mask(k, d, arrays, f)                                # per-box BFMatcher + classifyF: the port (small)
+                if not split:
+                    oracle_track.dyn_mask(k, d, arrays, f)                            # per-box BFMatcher + classifyF: the port (small)
                 cur.close()
             else:
                 k, d = ex(frames[f])
-                oracle_track.track_frame(k, d, ex.scale, W, H, arrays, f, params, cap)
+                (oracle_track.track_frame_rgbd if split else oracle_track.track_frame)(k, d, ex.scale, W, H, arrays, f, params, cap)
             done[t] += 1
             i += threads
 
@@ -349,7 +361,9 @@ def workload_config(cfg, B, nctx=None):
     W, H, _, nf, ini, mn, _ = WORKLOADS[cfg]
     c = {"workload": "%s %dx%d nfeatures=%d levels=%d scale=%.1f iniTh=%d minTh=%d" % (cfg, W, H, nf, NLEVELS, SCALE, ini, mn),
          "frames_per_step_per_gpu": B, "map_points_per_frame": N_MAP, "pool_frames": POOL,
-         "stages": "extract + SearchByProjection(cur,last) + isInFrustum + SearchByProjection(F,map) + dynamic mask",
+         "stages": "extract + firstSeparate/tail split + Separate + UpdateFrame (RGB-D constructor) + SearchByProjection(cur,last) + "
+                   "isInFrustum + SearchByProjection(F,map) on the static + re-admitted keypoints" if cfg in RGBD_CTOR else
+                   "extract + SearchByProjection(cur,last) + isInFrustum + SearchByProjection(F,map) + dynamic mask",
          "sharding": "one set of sequences per rank, no data-path collective; NCCL all_gather of run statistics only"}
     return c
 
@@ -462,11 +476,18 @@ def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptr
         for _ in range(3):
             stereo_track_step()
         L.sync(); R.sync()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            stereo_track_step()
-        L.sync(); R.sync()
-        dt3 = time.perf_counter() - t0
+        smp = ClockSampler(local); smp.wait_started()
+        tc0 = time.perf_counter()
+        runs3 = []
+        while len(runs3) < 3 or (time.perf_counter() - tc0 < 0.6 and len(runs3) < 40):     # >= 0.5 s under load for the clock record
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                stereo_track_step()
+            L.sync(); R.sync()
+            runs3.append(time.perf_counter() - t0)
+        clk3 = smp.stop(tc0, time.perf_counter())
+        clk3["window"] = "the stereo-pair regions"
+        dt3 = float(np.median(runs3))
         while kstep[0] % NS in (0, 1):            # report the counts of a step whose LastFrame was the slot's previous frame
             stereo_track_step()
         L.sync(); R.sync()
@@ -474,7 +495,8 @@ def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptr
         a3, l3, m3, c3 = pysdyn.track_fetch(L, Bs)
         out["stereo_track_config3"] = {"pairs_per_s": Bs * steps / dt3, "ms_per_step": 1e3 * dt3 / steps, "pairs_per_step": Bs,
                                        "stereo_points_per_pair": float(kept3.mean()), "matches_frame": float(c3[:, 0].mean()),
-                                       "matches_map": float(c3[:, 1].mean()),
+                                       "matches_map": float(c3[:, 1].mean()), "clocks": clk3,
+                                       "regions_ms": [round(1e3 * v, 3) for v in runs3],
                                        "stages": "extract L + extract R + ComputeStereoMatches + SearchByProjection(cur,last) + "
                                                  "SearchByProjection(F,map) + dynamic mask (one context pair, host clock)"}
     # ComputeBoW on the left frames with an ORBvoc-shaped vocabulary (k = 10, L = 6)
@@ -612,6 +634,7 @@ def main():
 
     cfg = args.workload
     W, H, nrect, nf, ini, mn, _ = WORKLOADS[cfg]
+    split = cfg in RGBD_CTOR
     B = args.batch
     K, Wm = args.steps, max(args.warmup, 3)
     assert POOL % B == 0 or B <= POOL
@@ -666,6 +689,29 @@ def main():
     mtab = pysdyn.MapTable(len(table), device=local)
     mtab.update(0, table)
     torch.cuda.synchronize()
+    if split:
+        # RGB-D constructor semantics: a slot's LastFrame is the list its previous frame was TRACKED with (static keypoints +
+        # re-admitted ones), so the per-keypoint id / flag rows of input j follow that list's order.  The order is a product of
+        # frame j-1's own inputs (boxes, reference keypoints, F21): one untimed pass over the pool fetches it.
+        orders = [None] * POOL
+        for i0 in range(0, POOL, B):
+            nb_ = min(B, POOL - i0)
+            tin = pysdyn.track_inputs(dptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch, rgbd_split=True)
+            pysdyn.track_batch_device(ex, nb_, dev_frames[i0].data_ptr(), W * H, W, H, W, tin, stream.cuda_stream)
+            torch.cuda.synchronize()
+            o, n_all, _ = pysdyn.track_frame_order(ex, nb_)
+            for b in range(nb_):
+                orders[i0 + b] = o[b, :n_all[b]].copy()
+        for name, empty in (("last_ids", -1), ("last_flags", 0)):
+            src = step_arrays[name].copy()
+            step_arrays[name][:] = empty
+            for j in range(POOL):
+                o = orders[(j - 1) % POOL]
+                step_arrays[name][j, :len(o)] = src[j, o]
+        pysdyn.pack_records(step_arrays, strides, FORMS, out=pin_pool.array[:POOL])
+        pin_pool.array[POOL:] = pin_pool.array[:B]
+        dev_pool.copy_(torch.from_numpy(pin_pool.array))
+        torch.cuda.synchronize()
 
     NCTX = max(1, args.contexts)
     CTX_OFF = 37                                                # contexts start at different places of the pool
@@ -676,7 +722,7 @@ def main():
 
     def step_device_on(s, c):
         i0 = first_input(s, c)
-        tin = pysdyn.track_inputs(dptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch)
+        tin = pysdyn.track_inputs(dptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch, rgbd_split=split)
         pysdyn.track_batch_device(ctxs[c], B, dev_frames[i0].data_ptr(), W * H, W, H, W, tin, streams[c].cuda_stream)
 
     def barrier():
@@ -757,7 +803,7 @@ def main():
         # the table rows rewritten here are rows whose content is identical (the synthetic map is static): the transfer is real
         new_pts.array[:] = table[:len(new_pts.array)]
         mtab.update(0, new_pts.array, stream=ctxs[c].stream_handle())
-        tin = pysdyn.track_inputs(hptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch)
+        tin = pysdyn.track_inputs(hptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch, rgbd_split=split)
         pysdyn.track_batch_host_async(ctxs[c], pin_in.array[i0:i0 + B], tin, out_sets[c][1])
 
     def run_host(first, count):
@@ -793,12 +839,12 @@ def main():
         for k in (0, 1):                    # step 0 primes the resident LastFrame, step 1 is compared
             i0 = (11 + k) % POOL
             if host:
-                tin = pysdyn.track_inputs(hptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch)
+                tin = pysdyn.track_inputs(hptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch, rgbd_split=split)
                 pysdyn.track_batch_host(ex, pin_in.array[i0:i0 + B], tin, out_sets[0][1])
                 o = out_sets[0][1]
                 outs = [o[2].copy(), o[6].copy(), o[3].copy(), o[5].copy()]
             else:
-                tin = pysdyn.track_inputs(dptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch)
+                tin = pysdyn.track_inputs(dptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch, rgbd_split=split)
                 pysdyn.track_batch_device(ex, B, dev_frames[i0].data_ptr(), W * H, W, H, W, tin, stream.cuda_stream)
                 torch.cuda.synchronize()                    # the fetches below run on the context's own stream
                 kk, dd, nn = ex.fetch(B)

@@ -2,6 +2,7 @@
  * sdyn_extract; errors of the C ABI become the reference's behaviour (silent return / assert). */
 #include "ORBextractor.h"
 #include "../../include/sdyn.h"
+#include <algorithm>
 #include <cassert>
 #include <cmath>
 #include <cstdio>
@@ -37,6 +38,9 @@ ORBextractor::~ORBextractor() { sdyn_destroy(mCtx); }
 void ORBextractor::EnsureContext(int width, int height)
 {
     if (mCtx && width <= mCtxW && height <= mCtxH) return;
+    /* grow to the envelope of everything seen so far: inputs alternating between a wide and a tall image settle after one
+     * re-creation instead of thrashing */
+    if (mCtx) { width = std::max(width, mCtxW); height = std::max(height, mCtxH); }
     sdyn_destroy(mCtx);
     mCtx = nullptr;
     sdyn_orb_params p = {mFeatures, (float)mScaleFactor, mLevels, mIniTh, mMinTh};
@@ -47,9 +51,20 @@ void ORBextractor::EnsureContext(int width, int height)
         return;
     }
     mCtxW = width; mCtxH = height;
+    if (mHaveCamera &&
+        sdyn_set_camera(mCtx, mCamera[0], mCamera[1], mCamera[2], mCamera[3], mDistCoef.data(), (int)mDistCoef.size()) != SDYN_OK)
+        std::fprintf(stderr, "ORBextractor: camera model lost on context re-creation: %s\n", sdyn_last_error(mCtx));
     const int cap = sdyn_max_keypoints(mCtx);
     mStageKp.resize(cap);
     mStageDesc.resize((size_t)cap * 32);
+}
+
+int ORBextractor::SetCamera(float fx, float fy, float cx, float cy, const float* distCoef, int nCoef)
+{
+    mHaveCamera = true;
+    mCamera[0] = fx; mCamera[1] = fy; mCamera[2] = cx; mCamera[3] = cy;
+    mDistCoef.assign(distCoef, distCoef + (distCoef ? nCoef : 0));
+    return mCtx ? sdyn_set_camera(mCtx, fx, fy, cx, cy, mDistCoef.data(), (int)mDistCoef.size()) : SDYN_OK;   /* else applied on creation */
 }
 
 void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& _keypoints,

@@ -45,8 +45,13 @@ public:
      * (Frame::ComputeStereoMatches reads it on the host). */
     std::vector<cv::Mat> mvImagePyramid;
 
-    /* GPU context of this extractor (one per instance: left and right extractors run concurrently). */
+    /* GPU context of this extractor (one per instance: left and right extractors run concurrently).  The pointer is valid
+     * until the next operator() call: an image larger than every earlier one re-creates the context (EnsureContext), so
+     * callers fetch it per frame and do not cache it. */
     sdyn_ctx* Context() { return mCtx; }
+    /* Camera model for the device-side undistortion (Frame::UndistortKeyPoints).  Set it here rather than on Context()
+     * directly: the extractor re-applies it whenever it has to re-create its context. */
+    int SetCamera(float fx, float fy, float cx, float cy, const float* distCoef, int nCoef);
     /* mvImagePyramid is the one output that costs a 1.4 MB device-to-host copy per image.  Its only host reader in the
      * reference is Frame::ComputeStereoMatches (src/Frame.cc:881-988); once that runs on the device through
      * sdyn_host::ComputeStereoMatches the copy can be switched off (the levels stay available via sdyn_fetch_level). */
@@ -65,6 +70,9 @@ protected:
     sdyn_ctx* mCtx;
     int mCtxW, mCtxH;
     bool mPyramidOnHost = true;
+    bool mHaveCamera = false;
+    float mCamera[4] = {0, 0, 0, 0};
+    std::vector<float> mDistCoef;
     std::vector<cv::Mat> mBordered;          /* owners of the bordered level buffers */
     std::vector<cv::KeyPoint> mStageKp;      /* reused staging, sized once */
     std::vector<unsigned char> mStageDesc;

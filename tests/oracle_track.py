@@ -27,13 +27,9 @@ def track_frame(keys, desc, scale, W, H, arrays, f, params, last_stride, keys_un
     return assign, locked, dyn.astype(np.uint8), np.array([n1, n2, int(in_box.sum()), int(dyn.sum())], np.int32)
 
 
-def track_frame_rgbd(keys, desc, scale, W, H, arrays, f, params, last_stride, last_view=None, keys_un=None, bounds=None):
-    """The same frame with RGB-D-constructor semantics (rgbd_split): Frame::firstSeparate + tail split (src/Frame.cc:555-604,
-    337-367), Tracking::Separate (Tracking.cc:1093-1239), Frame::UpdateFrame (Frame.cc:607-653), THEN the two searches on the
-    frame the reference tracks with (static keypoints + re-admitted ones).
-    Returns (order, N_s, assign, locked, dyn_mask, counts): assign / locked index the tracked list, order[j] = extraction index."""
-    cam = scenario.KITTI_CAM
-    bounds = (0.0, 0.0, float(W), float(H)) if bounds is None else tuple(float(b) for b in bounds)
+def rgbd_order(keys, desc, arrays, f, keys_un=None):
+    """The list the RGB-D constructor path tracks with: firstSeparate + tail split, Separate per surviving box, UpdateFrame.
+    -> (order [extraction indices: static keypoints, then the re-admitted ones], N_s, in_box, readmit)."""
     ku = keys if keys_un is None else keys_un
     nb = int(arrays["n_boxes"][f])
     boxes = arrays["boxes"][f, :nb]
@@ -66,7 +62,18 @@ def track_frame_rgbd(keys, desc, scale, W, H, arrays, f, params, last_stride, la
     if static_exit:                       # if (Separate(...) == 1) mCurrentFrame.UpdateFrame(dynSatus)
         for s, q in orc.update_frame_list(dyn_status, [slots.get(s, []) for s in range(nslots)]):
             order.append(slots[s][q]); readmit[slots[s][q]] = True
-    order = np.asarray(order, np.int64)
+    return np.asarray(order, np.int64), ns, in_box, readmit
+
+
+def track_frame_rgbd(keys, desc, scale, W, H, arrays, f, params, last_stride, last_view=None, keys_un=None, bounds=None):
+    """The same frame with RGB-D-constructor semantics (rgbd_split): Frame::firstSeparate + tail split (src/Frame.cc:555-604,
+    337-367), Tracking::Separate (Tracking.cc:1093-1239), Frame::UpdateFrame (Frame.cc:607-653), THEN the two searches on the
+    frame the reference tracks with (static keypoints + re-admitted ones).
+    Returns (order, N_s, assign, locked, dyn_mask, counts): assign / locked index the tracked list, order[j] = extraction index."""
+    cam = scenario.KITTI_CAM
+    bounds = (0.0, 0.0, float(W), float(H)) if bounds is None else tuple(float(b) for b in bounds)
+    ku = keys if keys_un is None else keys_un
+    order, ns, in_box, readmit = rgbd_order(keys, desc, arrays, f, keys_un)
     cid = np.where(in_box, np.arange(len(keys)), -1).astype(np.int32)
     fk = keys[order].copy(); fk["class_id"] = cid[order]
     fku = ku[order].copy(); fku["class_id"] = cid[order]

@@ -249,6 +249,19 @@ def track_params(W, H, cam=KITTI_CAM, th_frame=7.0, th_map=3.0, nnratio_map=0.8,
                 th_map=th_map, nnratio_map=nnratio_map, mono=mono, check_orientation=check_orientation)
 
 
+def reorder_last(arrays, f, order):
+    """LastFrame of frame input f becomes the list `order` of its keypoints (what an rgbd_split step leaves behind: the static
+    keypoints followed by the re-admitted ones, src/Frame.cc:337-367,607-653) — per-keypoint rows move with their keypoint."""
+    order = np.asarray(order, np.int64)
+    n = len(order)
+    for name in ("last_keys", "last_keys_un", "last_points"):
+        if name in arrays:
+            rows = arrays[name][f, order].copy()
+            arrays[name][f] = np.zeros((), arrays[name].dtype)
+            arrays[name][f, :n] = rows
+    arrays["n_last"][f] = n
+
+
 def resident_forms(arrays):
     """The same step inputs in the resident forms of sdyn_track_inputs: one MapPoint table (every LastFrame point and every
     local-map point of every frame gets an id) plus, per frame, ids / flag bytes / projection records.

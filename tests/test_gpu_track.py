@@ -318,6 +318,48 @@ def test_track_rgbd_split_matches_oracle(cfg, B, cam):
     gpu.close()
 
 
+def test_track_rgbd_split_with_resident_last():
+    """Two consecutive rgbd_split steps of the same slots: the list step 1 tracked with (static + re-admitted keypoints) IS
+    step 2's LastFrame, resident on the device, and step 2 names its MapPoints by id in that list's order."""
+    import torch
+    cfg, B = "tum", 3
+    W, H, nrect, nf, ini, mn, seq_seed, frames, cpu, kd = _sequence(cfg, B + 2)
+    gpu = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=B)
+    last_stride, map_stride, ref_stride = gpu.cap, 1500, 512
+    strides = (last_stride, map_stride, ref_stride)
+    params = scenario.track_params(W, H)
+    a1 = scenario.build_track_batch(kd[:B + 1], seq_seed, 1, W, H, nrect, 8, *strides, n_map=1500, seed=3)
+    a2 = scenario.build_track_batch(kd[1:B + 2], seq_seed, 2, W, H, nrect, 8, *strides, n_map=1500, seed=3)
+    d1, p1 = _dev(a1)
+    f1 = torch.from_numpy(frames[1:B + 1]).cuda(); f2 = torch.from_numpy(frames[2:B + 2]).cuda()
+    pysdyn.track_batch_device(gpu, B, f1.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(p1, 0, strides, params, rgbd_split=True))
+    order1, n_all1, n_static1 = pysdyn.track_frame_order(gpu, B)
+    shorter = 0
+    for f in range(B):
+        eo = oracle_track.track_frame_rgbd(kd[f + 1][0], kd[f + 1][1], cpu.scale, W, H, a1, f, params, last_stride)[0]
+        assert np.array_equal(order1[f, :n_all1[f]], eo)
+        scenario.reorder_last(a2, f, order1[f, :n_all1[f]])
+        shorter += int(n_all1[f] < len(kd[f + 1][0]))
+    assert shorter > 0                        # the tracked list really differs from the extraction list
+    table, res = scenario.resident_forms(a2)
+    mt = pysdyn.MapTable(len(table)); mt.update(0, table)
+    torch.cuda.synchronize()
+    d2, p2 = _dev(a2); dr, pr = _dev(res)
+    rp = {k: v for k, v in p2.items() if k not in ("last_points", "last_keys", "last_keys_un", "n_last", "map_points")}
+    rp.update(pr)
+    pysdyn.track_batch_device(gpu, B, f2.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(rp, 0, strides, params, map_table=mt, rgbd_split=True))
+    assign, locked, mask, cnt = pysdyn.track_fetch(gpu, B)
+    order2, n_all2, n_static2 = pysdyn.track_frame_order(gpu, B)
+    for f in range(B):
+        k, d = kd[f + 2]
+        eo, ens, ea, el, em, ec, _ = oracle_track.track_frame_rgbd(k, d, cpu.scale, W, H, a2, f, params, last_stride)
+        assert n_all2[f] == len(eo) and n_static2[f] == ens and np.array_equal(order2[f, :len(eo)], eo)
+        assert np.array_equal(cnt[f], ec), (f, cnt[f], ec)
+        assert np.array_equal(assign[f, :len(eo)], ea) and np.array_equal(locked[f, :len(eo)], el)
+        assert np.array_equal(mask[f, :len(k)], em) and ec[0] > 80
+    mt.close(); gpu.close()
+
+
 def test_track_device_frustum_matches_explicit():
     """Frame::isInFrustum on the device (map_flags form): local-map ids + one state byte per point; the projection records
     the explicit form uploads are derived from the resident MapPoint table and the frame's pose."""
