@@ -843,6 +843,7 @@ def main():
                 pysdyn.track_batch_host(ex, pin_in.array[i0:i0 + B], tin, out_sets[0][1])
                 o = out_sets[0][1]
                 outs = [o[2].copy(), o[6].copy(), o[3].copy(), o[5].copy()]
+                lim = pysdyn.track_frame_order(ex, B)[1].copy() if split else outs[0]
             else:
                 tin = pysdyn.track_inputs(dptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch, rgbd_split=split)
                 pysdyn.track_batch_device(ex, B, dev_frames[i0].data_ptr(), W * H, W, H, W, tin, stream.cuda_stream)
@@ -850,15 +851,21 @@ def main():
                 kk, dd, nn = ex.fetch(B)
                 aa, ll, mm, cc = pysdyn.track_fetch(ex, B)
                 outs = [nn.copy(), cc.copy(), aa.copy(), mm.copy()]
-        return outs
+                lim = pysdyn.track_frame_order(ex, B)[1].copy() if split else outs[0]
+        return outs + [lim]                 # lim: how many entries of a frame's match list are specified (the tracked list's length)
     v_dev, v_host = verify_pair(False), verify_pair(True)
-    for name, a, b_ in zip(("n", "counts", "assign", "dyn_mask"), v_dev, v_host):
-        if a.ndim == 2 and a.shape[1] == cap:                # per-keypoint arrays: entries past a frame's keypoint count are unspecified
-            a = np.where(np.arange(cap)[None, :] < v_dev[0][:, None], a, 0); b_ = np.where(np.arange(cap)[None, :] < v_dev[0][:, None], b_, 0)
+    digest_parts = []
+    for name, a, b_ in zip(("n", "counts", "assign", "dyn_mask", "tracked_list_length"), v_dev, v_host):
+        if a.ndim == 2 and a.shape[1] == cap:                # per-keypoint arrays: entries past a frame's list length are unspecified
+            lim = (v_dev[4] if name == "assign" else v_dev[0])[:, None]
+            a = np.where(np.arange(cap)[None, :] < lim, a, 0); b_ = np.where(np.arange(cap)[None, :] < lim, b_, 0)
         assert np.array_equal(a, b_), "e2e and device-resident results differ in %s: %d entries, first %s" % (
             name, int((a != b_).sum()), np.argwhere(a != b_)[:4].tolist())
+        digest_parts.append(np.ascontiguousarray(a).tobytes())
     import hashlib
-    rank_digest = hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in v_dev)).hexdigest()[:16]
+    # over the SPECIFIED entries only (the unspecified tails hold whatever earlier steps left there, which depends on how many
+    # regions the run repeated): rank r's digest is then a function of rank r's inputs alone, the same at every N
+    rank_digest = hashlib.sha256(b"".join(digest_parts)).hexdigest()[:16]
 
     h2d = B * W * H + B * pitch + new_pts.array.nbytes      # bytes actually copied per step (record padding included)
     # what the host link delivers for one plain pinned copy of a step's input volume (context for the e2e number)
