@@ -596,7 +596,7 @@ def emit(line):
 
 def main():
     # Libraries (NCCL's version banner, torchrun notices) write to fd 1; keep stdout for the result line only.
-    global _RESULT_FD
+    global _RESULT_FD, POOL
     sys.stdout.flush()
     _RESULT_FD = os.dup(1)
     os.dup2(2, 1)
@@ -611,7 +611,9 @@ def main():
     ap.add_argument("--contexts", type=int, default=6, help="contexts (streams) per GPU taking steps round-robin")
     ap.add_argument("--min-seconds", type=float, default=0.5, help="repeat the K-step timed regions until each arm has run this long")
     ap.add_argument("--next-rows", type=int, default=1, help="also time the SURVEY 8(f) rows (stereo, BoW) on rank 0 at N=1")
+    ap.add_argument("--pool", type=int, default=POOL, help="distinct frames per GPU (256 = the survey's; smaller only for smoke tests)")
     args = ap.parse_args()
+    POOL = args.pool
     if args.impl == "reference":
         return run_reference(args)
 

@@ -15,6 +15,7 @@
 #include <iostream>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
 
 using namespace ORB_SLAM2;
@@ -28,11 +29,20 @@ void classify(int flag, const cv::Mat& M, const std::vector<cv::KeyPoint>& cur, 
 
 namespace {
 
-struct Quiet {      /* the reference prints progress lines to std::cout */
-    std::ostringstream sink;        /* declared first: it must exist before cout is pointed at it */
-    std::streambuf* old;
-    Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
-    ~Quiet() { std::cout.rdbuf(old); }
+/* The reference prints progress lines to std::cout.  While any call is inside the reference's code, cout is pointed at a
+ * process-lifetime null buffer (counted under a mutex: bench.py's CPU arm calls in from many threads, and a per-call sink whose
+ * restore races with another thread's save leaves cout holding a dead stack buffer). */
+struct NullBuf : std::streambuf {
+    int overflow(int c) override { return c == EOF ? 0 : c; }
+    std::streamsize xsputn(const char*, std::streamsize n) override { return n; }
+};
+NullBuf g_null;
+std::mutex g_quietMutex;
+int g_quietDepth = 0;
+std::streambuf* g_quietOld = nullptr;
+struct Quiet {
+    Quiet() { std::lock_guard<std::mutex> l(g_quietMutex); if (g_quietDepth++ == 0) g_quietOld = std::cout.rdbuf(&g_null); }
+    ~Quiet() { std::lock_guard<std::mutex> l(g_quietMutex); if (--g_quietDepth == 0) std::cout.rdbuf(g_quietOld); }
 };
 
 struct PointList {
