@@ -18,7 +18,7 @@ def run(extra, env=None):
 
 
 @pytest.mark.parametrize("workload", ["kitti", "tum"])
-def test_reference_arm_prints_one_contract_line(workload):
+def test_reference_arm_prints_one_contract_line(workload, monkeypatch):
     r = run(["--workload", workload])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -32,7 +32,7 @@ def test_reference_arm_prints_one_contract_line(workload):
     # the same config object as the GPU arm (bench.workload_config): workload string, frames per step, pool
     sys.path.insert(0, ROOT)
     import bench
-    bench.POOL = 8
+    monkeypatch.setattr(bench, "POOL", 8)          # other tests read bench.POOL (the 256-frame sweep)
     assert d["config"] == bench.workload_config(workload, 4)
     assert ("RGB-D constructor" in d["config"]["stages"]) == (workload == "tum")
 
