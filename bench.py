@@ -419,7 +419,7 @@ def big_vocabulary(k=10, L=6, seed=1):
     return np.concatenate(parents), np.concatenate(leafs), np.concatenate(descs), np.concatenate(weights)
 
 
-def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptrs, strides, params, dev_frames, mtab, pitch):
+def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptrs, strides, params, dev_frames, mtab, pitch, host=None):
     """Device timings of the SURVEY §8(f) rows built after the headline path (same parity bar, tests/test_gpu_*.py):
     ComputeStereoMatches per stereo pair and ComputeBoW per frame, with the oracle timed beside them.  Reported next
     to the headline, never part of it."""
@@ -572,7 +572,26 @@ def next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, steps, rank, dptr
         oe = _orc.Extractor(nf, SCALE, NLEVELS, ini, mn)
         t1 = time.perf_counter(); oe(img0); cpu_ex = time.perf_counter() - t1
         t1 = time.perf_counter(); _orc.match_projection_frame(cur, last, lp, 7.0, False, True); cpu_m = time.perf_counter() - t1
+        full = None
+        if host is not None:
+            # the whole per-frame path as ONE call on a one-frame context: image + frame record up, keypoints, descriptors, match
+            # indices, lock flags and mask down (the slot's LastFrame is the previous call's frame, resident)
+            hptrs, pin_in = host
+            cap1 = one.cap
+            pinned1 = [pysdyn.PinnedArray(shape, dt) for shape, dt in
+                       [((1, cap1), pysdyn.KP_DTYPE), ((1, cap1, 32), np.uint8), ((1,), np.int32), ((1, cap1), np.int32),
+                        ((1, cap1), np.uint8), ((1, cap1), np.uint8), ((1, 4), np.int32)]]       # kept alive: they own the memory
+            o1 = tuple(a.array for a in pinned1)
+            lf = []
+            for i in range(45):
+                i0 = 20 + i
+                tin = pysdyn.track_inputs(hptrs, i0, strides, params, map_table=mtab, frame_pitch=pitch)
+                t1 = time.perf_counter(); pysdyn.track_batch_host(one, pin_in.array[i0:i0 + 1], tin, o1); lf.append(time.perf_counter() - t1)
+            full = {"ms": 1e3 * float(np.median(lf[5:])), "matches_frame": int(o1[6][0, 0]), "matches_map": int(o1[6][0, 1]),
+                    "note": "extract + SearchByProjection(cur,last) + isInFrustum + SearchByProjection(F,map) + dynamic mask for ONE frame "
+                            "through sdyn_track_batch (host buffers in and out, synchronous)"}
         out["single_frame_latency"] = {"extract_ms": 1e3 * float(np.median(lat)), "search_by_projection_frame_ms": 1e3 * float(np.median(lm)),
+                                       "full_path_one_call": full,
                                        "cpu_oracle_extract_ms": 1e3 * cpu_ex, "cpu_oracle_search_ms": 1e3 * cpu_m,
                                        "note": "ORBextractor::operator() / SearchByProjection(cur,last) one call at a time, host arrays in "
                                                "and out (H2D, kernels, D2H, synchronisation inside the call)"}
@@ -1027,7 +1046,7 @@ def main():
     if args.next_rows and world == 1 and cfg == "kitti":
         try:
             extras = next_rows(pysdyn, torch, cfg, W, H, nf, ini, mn, local, B, max(K // 2, 5), rank, dptrs, strides, params, dev_frames,
-                               mtab, pitch)
+                               mtab, pitch, host=(hptrs, pin_in))
         except Exception as e:          # never lose the headline line to a side measurement
             extras = {"error": repr(e)}
 

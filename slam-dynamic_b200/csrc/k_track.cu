@@ -54,7 +54,7 @@ __device__ __forceinline__ int hamming_bytes2(const uint8_t* a, const uint8_t* b
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
-constexpr int BS = 128;
+constexpr int BS = 256;
 
 /* one CTA per (box slot, frame) */
 __global__ void __launch_bounds__(BS)
@@ -84,18 +84,35 @@ k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, co
     int32_t* nq_ = nnQ + ((size_t)f * 64 + s) * cap;
     int32_t* nt_ = nnT + ((size_t)f * 64 + s) * nnTStride;
 
-    /* keypoints of box `occ`, ascending index = order of mvdynKeys[slot] */
-    for (int i0 = 0; i0 < n; i0 += BS) {
-        const int i = i0 + tid;
-        const bool ok = i < n && ((M[i] >> occ) & 1ull);
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if ((tid & 31) == 0) warpCnt[tid >> 5] = __popc(bal);
+    /* keypoints of box `occ`, ascending index = order of mvdynKeys[slot].  A thread owns a contiguous run of the frame's
+     * keypoints: count, one block scan, write — the mask words are independent loads (a strided loop with a barrier per
+     * 128 keypoints paid one global-memory latency per iteration and was most of this kernel's time) */
+    {
+        const int run = (n + BS - 1) / BS, i0 = tid * run, i1 = min(i0 + run, n);
+        int mine = 0;
+        unsigned long long flags = 0;                /* bit k: keypoint i0 + k is in the box (runs of up to 64 keypoints) */
+        for (int b = i0; b < i1; b += 8) {
+            uint64_t m[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m[k] = b + k < i1 ? M[b + k] : 0ull;     /* eight loads in flight */
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const unsigned long long in = (m[k] >> occ) & 1ull;
+                mine += (int)in;
+                if (b - i0 + k < 64) flags |= in << (b - i0 + k);
+            }
+        }
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+        if ((tid & 31) == 31) warpCnt[tid >> 5] = incl;
         __syncthreads();
-        int pos = sBase;
+        int pos = incl - mine;
         for (int w = 0; w < (tid >> 5); ++w) pos += warpCnt[w];
-        if (ok) list[pos + __popc(bal & ((1u << (tid & 31)) - 1))] = i;
-        __syncthreads();
-        if (tid == 0) { int t = 0; for (int w = 0; w < BS / 32; ++w) t += warpCnt[w]; sBase += t; }
+        while (flags) { const int k = __ffsll((long long)flags) - 1; flags &= flags - 1; list[pos++] = i0 + k; }
+        for (int i = i0 + 64; i < i1; ++i)           /* only for runs longer than 64 keypoints */
+            if ((M[i] >> occ) & 1ull) list[pos++] = i;
+        if (tid == BS - 1) sBase = pos;
         __syncthreads();
     }
     const int nq = sBase;
@@ -105,18 +122,41 @@ k_box_stage(const sdyn_track_inputs in, const sdyn_keypoint* __restrict__ kp, co
     const uint8_t* TD = frame_part(in.ref_desc, f, (size_t)in.ref_stride * 32, P) + (size_t)to * 32;
     const float* TX = frame_part(in.ref_xy, f, (size_t)in.ref_stride * 8, P) + (size_t)to * 2;
 
-    /* BFMatcher(NORM_HAMMING, crossCheck = true) */
-    for (int i = tid; i < nq; i += BS) {
-        int best = 1 << 30, bj = -1;
-        const uint8_t* q = D + 32 * (size_t)list[i];
-        for (int j = 0; j < nt; ++j) { const int d = hamming_bytes2(q, TD + 32 * (size_t)j); if (d < best) { best = d; bj = j; } }
-        nq_[i] = bj;
-    }
-    for (int j = tid; j < nt; j += BS) {
-        int best = 1 << 30, bi = -1;
-        const uint8_t* t = TD + 32 * (size_t)j;
-        for (int i = 0; i < nq; ++i) { const int d = hamming_bytes2(D + 32 * (size_t)list[i], t); if (d < best) { best = d; bi = i; } }
-        nt_[j] = bi;
+    /* BFMatcher(NORM_HAMMING, crossCheck = true).  A warp owns a query (then a target) and its lanes share out the other side:
+     * the best match is the minimum of (distance << 20 | index) — smallest distance, then smallest index, which is what the
+     * sequential scan with a strict comparison keeps — reduced over the warp by shuffles. */
+    {
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int i = wid; i < nq; i += BS / 32) {
+            const uint4* q = reinterpret_cast<const uint4*>(D + 32 * (size_t)list[i]);
+            const uint4 q0 = q[0], q1 = q[1];
+            unsigned best = 0xffffffffu;
+            for (int j = lane; j < nt; j += 32) {
+                const uint4* t = reinterpret_cast<const uint4*>(TD + 32 * (size_t)j);
+                const uint4 t0 = t[0], t1 = t[1];
+                const int d = __popc(q0.x ^ t0.x) + __popc(q0.y ^ t0.y) + __popc(q0.z ^ t0.z) + __popc(q0.w ^ t0.w) +
+                              __popc(q1.x ^ t1.x) + __popc(q1.y ^ t1.y) + __popc(q1.z ^ t1.z) + __popc(q1.w ^ t1.w);
+                best = min(best, ((unsigned)d << 20) | (unsigned)j);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0) nq_[i] = (int)(best & 0xfffffu);
+        }
+        for (int j = wid; j < nt; j += BS / 32) {
+            const uint4* t = reinterpret_cast<const uint4*>(TD + 32 * (size_t)j);
+            const uint4 t0 = t[0], t1 = t[1];
+            unsigned best = 0xffffffffu;
+            for (int i = lane; i < nq; i += 32) {
+                const uint4* q = reinterpret_cast<const uint4*>(D + 32 * (size_t)list[i]);
+                const uint4 q0 = q[0], q1 = q[1];
+                const int d = __popc(q0.x ^ t0.x) + __popc(q0.y ^ t0.y) + __popc(q0.z ^ t0.z) + __popc(q0.w ^ t0.w) +
+                              __popc(q1.x ^ t1.x) + __popc(q1.y ^ t1.y) + __popc(q1.z ^ t1.z) + __popc(q1.w ^ t1.w);
+                best = min(best, ((unsigned)d << 20) | (unsigned)i);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0) nt_[j] = (int)(best & 0xfffffu);
+        }
     }
     __syncthreads();
 
