@@ -613,6 +613,103 @@ def emit(line):
         os.write(_RESULT_FD, data)
 
 
+def run_init(args):
+    """--workload init: the heavy matcher case as its own line.  A step is one monocular-initialisation attempt of
+    the reference (Tracking::MonocularInitialization, Tracking.cc:586-660): the 2 x nFeatures extractor (Tracking.cc:128) on two
+    KITTI-shaped frames, then SearchForInitialization with a 100-px window on level 0 (Tracking.cc:1461, ORBmatcher.cc:562-677),
+    every call through the C ABI with host arrays in and out — so `value` IS the end-to-end number (host clock around
+    synchronous calls).  One GPU; under torchrun only rank 0 works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    import pysdyn
+    import scenario
+    import orc
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sdyn path has no CPU fallback")
+    torch.cuda.set_device(local)
+    W, H, nrect, nf, ini, mn, _ = WORKLOADS["kitti"]
+    K, Wm = args.steps, max(args.warmup, 3)
+    npairs = 16
+    frames = make_frames("kitti", 0, 0, npairs + 1)
+    ex = pysdyn.Extractor(2 * nf, SCALE, NLEVELS, ini, mn, max_width=W, max_height=H, max_batch=1, device=local)
+    mt = pysdyn.Matcher(ex, 0.9, True)
+    sc = ex.GetScaleFactors()
+    stats = {"evals": 0, "matches": 0, "queries": 0, "kp": 0}
+
+    def step(i):
+        a, b = frames[i % npairs], frames[i % npairs + 1]
+        ka, da = ex(a); kb, db = ex(b)
+        F1 = scenario.frame_view(ka, da, sc, W, H); F2 = scenario.frame_view(kb, db, sc, W, H)
+        prevm = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)           # vbPrevMatched = F1's keypoints (Tracking.cc:606-608)
+        n, _, _ = mt.SearchForInitialization(F1, F2, prevm, 100)
+        stats["evals"] += mt.last_evals(); stats["matches"] += int(n); stats["queries"] += int((ka["octave"] == 0).sum())
+        stats["kp"] += len(ka) + len(kb)
+
+    sampler = ClockSampler(local); sampler.wait_started()
+    for i in range(Wm):
+        step(i)
+    torch.cuda.synchronize()
+    l0 = ex.launch_count()
+    for k_ in stats:
+        stats[k_] = 0
+    t_clk0 = time.perf_counter()
+    runs, nsteps = [], 0
+    while len(runs) < 3 or (time.perf_counter() - t_clk0 < args.min_seconds and len(runs) < 60):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for i in range(K):
+            step(nsteps + i)
+        torch.cuda.synchronize(); runs.append(time.perf_counter() - t0); nsteps += K
+    clocks = sampler.stop(t_clk0, time.perf_counter())
+    launches = (ex.launch_count() - l0) // len(runs)
+    dt = float(np.median(runs))
+    fps = 2 * K / dt
+    ev_step = stats["evals"] / nsteps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    kp_frame = stats["kp"] / (2 * nsteps)
+    alg = 2 * alg_bytes_extract(W, H, int(kp_frame)) + ev_step * 64          # two extractions + two 32-byte descriptors per evaluation
+    cpu = None
+    if args.cpu_seconds > 0:
+        oe = orc.Extractor(2 * nf, SCALE, NLEVELS, ini, mn)
+        t0 = time.perf_counter(); n_cpu = 0; t_search = 0.0
+        while time.perf_counter() - t0 < args.cpu_seconds:
+            a, b = frames[n_cpu % npairs], frames[n_cpu % npairs + 1]
+            ka, da = oe(a); kb, db = oe(b)
+            F1 = scenario.frame_view(ka, da, oe.scale, W, H); F2 = scenario.frame_view(kb, db, oe.scale, W, H)
+            t1 = time.perf_counter()
+            orc.match_init(F1, F2, np.stack([ka["x"], ka["y"]], 1).astype(np.float32), 100, 0.9, True)
+            t_search += time.perf_counter() - t1
+            n_cpu += 1
+        cpu = {"value": 2 * n_cpu / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
+               "search_ms_per_call": 1e3 * t_search / max(n_cpu, 1),
+               "sample": "%d initialisation attempts (2 extractions with %d features + SearchForInitialization) on the C++ oracle, 1 thread"
+                         % (n_cpu, 2 * nf)}
+    h2d = 2 * W * H + int(kp_frame) * (2 * (28 + 32) + 8)
+    emit({"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": K, "warmup": Wm, "ms_per_step": 1e3 * dt / K,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+          "config": {"workload": "init: kitti %dx%d, 2 x nFeatures = %d, levels=%d scale=%.1f, SearchForInitialization windowSize=100" % (W, H, 2 * nf, NLEVELS, SCALE),
+                     "frames_per_step_per_gpu": 2, "stages": "extract(F1) + extract(F2) + SearchForInitialization, one call each through the C ABI",
+                     "l2": "the two frames of a step change every step (16 pairs); calls are synchronous, so caches are cold in the sense the call pattern makes them"},
+          "run": {"regions_ms": [round(1e3 * v, 3) for v in runs], "timing": "host clock around K synchronous steps, regions repeated for >= %.1f s; median region" % args.min_seconds},
+          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * kp_frame * 60 + kp_frame * 4),
+                  "note": "the calls take and return host arrays: value is already end to end"},
+          "gpu_launches": int(launches), "clocks": clocks,
+          "roofline": {"kernel": "whole step (latency-bound chain of one-frame kernels)", "bound": "hbm", "achieved": alg / (dt / K) / 1e9, "peak": peak,
+                       "unit": "GB/s", "frac": alg / (dt / K) / 1e9 / peak, "traffic": None,
+                       "alg_bytes_per_launch": alg},
+          "matching": {"hamming_evals_per_step": ev_step, "level0_queries_per_step": stats["queries"] / nsteps, "matches_per_step": stats["matches"] / nsteps,
+                       "evals_per_s": ev_step * K / dt, "popc_per_s": 8 * ev_step * K / dt, "popc_peak_per_s": POPC_PEAK,
+                       "popc_pipe_frac": 8 * ev_step * K / dt / POPC_PEAK},
+          "cpu_baseline": cpu})
+    ex.close()
+
+
 def main():
     # Libraries (NCCL's version banner, torchrun notices) write to fd 1; keep stdout for the result line only.
     global _RESULT_FD, POOL
@@ -624,7 +721,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sdyn", choices=["sdyn", "reference"])
-    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS) + ["init"])
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample length (0 = skip)")
     ap.add_argument("--contexts", type=int, default=6, help="contexts (streams) per GPU taking steps round-robin")
@@ -633,6 +730,10 @@ def main():
     ap.add_argument("--pool", type=int, default=POOL, help="distinct frames per GPU (256 = the survey's; smaller only for smoke tests)")
     args = ap.parse_args()
     POOL = args.pool
+    if args.workload == "init":
+        if args.impl == "reference":
+            raise SystemExit("--workload init has no reference arm: its line carries the CPU oracle as cpu_baseline")
+        return run_init(args)
     if args.impl == "reference":
         return run_reference(args)
 
