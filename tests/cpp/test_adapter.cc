@@ -134,6 +134,33 @@ int main(int argc, char** argv)
         dump("stereo_uright", S.mvuRight.data(), S.mvuRight.size() * 4);
         dump("stereo_depth", S.mvDepth.data(), S.mvDepth.size() * 4);
     }
+    /* context re-creation: a larger image re-creates the extractor's GPU context; the camera model set through the
+     * extractor must survive it, and a wide-then-tall sequence must settle on the envelope instead of thrashing */
+    {
+        ORB_SLAM2::ORBextractor ex2(500, 1.2f, 8, 20, 7);
+        const float dist[5] = {0.262383f, -0.953104f, -0.005358f, 0.002628f, 1.163314f};
+        if (ex2.SetCamera(517.306408f, 516.469215f, 318.643040f, 255.313989f, dist, 5) != SDYN_OK) { fprintf(stderr, "SetCamera failed\n"); return 1; }
+        cv::Mat wide(240, 640, CV_8UC1), tall(480, 320, CV_8UC1);
+        sdyn_synth_frame(1007, 3001, 640, 240, 60, 0, 0, 0, wide.data, 640);
+        sdyn_synth_frame(1007, 3002, 320, 480, 60, 0, 0, 0, tall.data, 320);
+        std::vector<cv::KeyPoint> k; cv::Mat d;
+        ex2(wide, cv::Mat(), k, d);
+        sdyn_ctx* c1 = ex2.Context();
+        ex2(tall, cv::Mat(), k, d);                       /* taller than anything seen: re-created as 640 x 480 */
+        sdyn_ctx* c2 = ex2.Context();
+        ex2(wide, cv::Mat(), k, d);                       /* fits the envelope: no re-creation */
+        if (!c1 || !c2 || ex2.Context() != c2 || k.empty()) { fprintf(stderr, "context envelope: unexpected re-creation\n"); return 1; }
+        std::vector<cv::KeyPoint> ku(k.size());
+        if (sdyn_fetch_keypoints_un(ex2.Context(), 1, reinterpret_cast<sdyn_keypoint*>(ku.data()), (int)ku.size(), nullptr) != SDYN_OK) {
+            fprintf(stderr, "fetch_keypoints_un: %s\n", sdyn_last_error(ex2.Context())); return 1;
+        }
+        size_t moved = 0;
+        for (size_t i = 0; i < k.size(); ++i) moved += ku[i].pt.x != k[i].pt.x || ku[i].pt.y != k[i].pt.y;
+        if (moved * 2 < k.size()) { fprintf(stderr, "camera model lost on context re-creation (%zu of %zu keypoints undistorted)\n", moved, k.size()); return 1; }
+        dump("recreate_keys", k.data(), k.size() * sizeof(cv::KeyPoint));
+        dump("recreate_keys_un", ku.data(), ku.size() * sizeof(cv::KeyPoint));
+        dump("recreate_img", wide.data, (size_t)640 * 240);
+    }
     fclose(g_out);
     printf("adapter ok: %d keypoints, %d frame matches, %d map matches\n", cur.N, n1, n2);
     return 0;

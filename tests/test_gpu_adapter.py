@@ -85,6 +85,15 @@ def test_adapter_classes_match_oracle(tmp_path):
     assert struct.unpack("<i", d["map_n"])[0] == n2 and n2 > 50
     assert np.array_equal(np.frombuffer(d["map_assign"], np.int32), expect)
 
+    # context re-creation keeps the camera model: undistorted keypoints of the wide image after wide -> tall -> wide
+    rk = np.frombuffer(d["recreate_keys"], pysdyn.KP_DTYPE); rku = np.frombuffer(d["recreate_keys_un"], pysdyn.KP_DTYPE)
+    rimg = np.frombuffer(d["recreate_img"], np.uint8).reshape(240, 640)
+    ek, _ = orc.Extractor(500, 1.2, 8, 20, 7)(rimg)
+    assert len(ek) == len(rk) and np.array_equal(ek["x"], rk["x"]) and np.array_equal(ek["y"], rk["y"])
+    exy = orc.undistort_points(np.stack([ek["x"], ek["y"]], 1), np.float32(517.306408), np.float32(516.469215), np.float32(318.643040),
+                               np.float32(255.313989), np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32))
+    assert np.array_equal(rku["x"].view(np.uint32), exy[:, 0].view(np.uint32)) and np.array_equal(rku["y"].view(np.uint32), exy[:, 1].view(np.uint32))
+
     # stereo constructor path: Frame::ComputeStereoMatches through the adapter
     imgR = np.frombuffer(d["imgR"], np.uint8).reshape(H, W)
     EL, ER = orc.Extractor(1000, 1.2, 8, 20, 7), orc.Extractor(1000, 1.2, 8, 20, 7)
