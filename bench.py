@@ -54,8 +54,26 @@ def csrc_sha():
     return h.hexdigest()[:16]
 
 
-def load_ncu_figures():
-    """(figures per kernel, note).  Newest profiles/rNN_ncu_traffic.json whose csrc_sha matches the tree."""
+def csrc_file_sha():
+    """Per-file digests of the kernel sources (the ncu figures carry them too: a kernel's figures stay valid while ITS files do)."""
+    import hashlib
+    d = os.path.join(ROOT, "slam-dynamic_b200", "csrc")
+    return {name: hashlib.sha256(open(os.path.join(d, name), "rb").read()).hexdigest()[:16]
+            for name in sorted(os.listdir(d)) if name.endswith((".cu", ".cpp", ".h"))}
+
+
+# the source files a kernel's instruction count and traffic depend on (its own file + the headers it is built from)
+KERNEL_FILES = {
+    "k_fast": ["k_fast.cu", "sdyn_internal.h", "tma.h"], "k_blur": ["k_blur.cu", "sdyn_internal.h", "tma.h"],
+    "k_resize": ["k_pyramid.cu", "sdyn_internal.h", "tma.h"], "k_level0": ["k_pyramid.cu", "sdyn_internal.h"],
+    "k_octree": ["k_octree.cu", "sdyn_internal.h"], "k_orient_describe": ["k_describe.cu", "sdyn_internal.h", "tma.h"],
+    "k_match_candidates": ["k_match.cu", "match_internal.h", "sdyn_internal.h"], "k_box_stage": ["k_track.cu", "match_internal.h", "sdyn_internal.h"],
+}
+
+
+def load_ncu_figures(kernel=None):
+    """(figures per kernel, note).  Newest profiles/rNN_ncu_traffic.json whose csrc_sha matches the tree; failing that, the
+    figures of `kernel` are still accepted when every source file that kernel is built from is unchanged since the capture."""
     import glob
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")), reverse=True):
         try:
@@ -64,6 +82,10 @@ def load_ncu_figures():
             continue
         if tj.get("csrc_sha") == csrc_sha():
             return tj, os.path.basename(path)
+        then, now = tj.get("file_sha") or {}, csrc_file_sha()
+        files = KERNEL_FILES.get(kernel)
+        if files and all(then.get(f) is not None and then.get(f) == now.get(f) for f in files):
+            return tj, "%s (captured for csrc %s; %s unchanged since)" % (os.path.basename(path), tj.get("csrc_sha"), ", ".join(files))
         return None, "%s is stale (captured for csrc %s, tree is %s)" % (os.path.basename(path), tj.get("csrc_sha"), csrc_sha())
     return None, "no ncu capture committed"
 
@@ -1067,7 +1089,7 @@ def main():
     stage_kernel = {"fast": "k_fast", "match": "k_match_candidates", "candidates": "k_match_candidates", "describe": "k_orient_describe", "blur": "k_blur",
                     "pyramid": "k_resize", "octree": "k_octree", "level0": "k_level0", "dynamic": "k_box_stage"}
     traffic = None
-    tj, ncu_note = load_ncu_figures()
+    tj, ncu_note = load_ncu_figures(stage_kernel.get(dom))
     captured = cfg == "kitti" and B == 64               # the committed ncu capture is of the headline workload's launches
     if tj and dom and captured and stage_kernel.get(dom) in tj:
         traffic = tj[stage_kernel[dom]]["dram_bytes_per_launch"]

@@ -310,11 +310,9 @@ cudaError_t launch_frame_compact(const sdyn_keypoint* kp, const sdyn_keypoint* k
                                  cudaStream_t st)
 {
     const size_t smem = (size_t)cap * 8;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024) {             /* the opt-in is per device and per function: set whenever it is needed */
         cudaError_t e = cudaFuncSetAttribute(k_frame_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     k_frame_compact<<<nframes, FC, smem, st>>>(kp, kpUn, desc, count, cap, mask, readmit, staticExit, fKp, fKpUn, fDesc, fOrder, fCount, fStatic);
     return cudaGetLastError();

@@ -38,14 +38,18 @@ struct TrackState {
     int32_t* hAssign = nullptr; uint8_t* hLocked = nullptr; uint8_t* hMask = nullptr; int32_t* hCounts = nullptr; int32_t* hResult = nullptr;
 };
 
-void free_track_state(sdyn_ctx* c)
+static void release_track_state(TrackState* t)
 {
-    TrackState* t = static_cast<TrackState*>(c->track);
     if (!t) return;
     cudaFree(t->block); cudaFree(t->inBlock);
     cudaFreeHost(t->hAssign); cudaFreeHost(t->hLocked); cudaFreeHost(t->hMask); cudaFreeHost(t->hCounts); cudaFreeHost(t->hResult);
     cudaFreeHost(t->hOrder); cudaFreeHost(t->hFCount);
     delete t;
+}
+
+void free_track_state(sdyn_ctx* c)
+{
+    release_track_state(static_cast<TrackState*>(c->track));
     c->track = nullptr;
 }
 
@@ -58,7 +62,9 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     if (t) { maxQ = std::max(maxQ, t->maxQ); refStride = std::max(refStride, t->refStride); }
     if (t && t->pending.active)
         return api_fail(c, SDYN_ERR_ARG, "track state would have to grow while an asynchronous step is in flight: call sdyn_track_wait first");
-    if (t) { cudaStreamSynchronize(c->stream); free_track_state(c); }
+    /* the state is re-allocated larger; what it carries from step to step — every slot's resident LastFrame — moves over */
+    TrackState* old = t;
+    if (old) { cudaStreamSynchronize(c->stream); c->track = nullptr; }
     t = new TrackState();
     t->B = B; t->cap = cap; t->maxQ = maxQ; t->refStride = refStride; t->distorted = c->camera.enabled != 0;
     t->poolPerJob = std::max(std::max(64 * maxQ, 1 << 16), wantPool);      /* grown after an overflow (track_fetch_finish) */
@@ -100,7 +106,8 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&t->hFCount), (size_t)B * 8);
     if (e == cudaSuccess) e = cudaMemset(t->block + oPCount, 0, (size_t)B * 4);
     if (e != cudaSuccess) {
-        c->track = t; free_track_state(c);
+        release_track_state(t);
+        c->track = old;                     /* the smaller state stays usable */
         return api_fail(c, SDYN_ERR_NOMEM, std::string("track state: ") + cudaGetErrorString(e));
     }
     uint8_t* b = t->block;
@@ -122,6 +129,19 @@ static int ensure_track_state(sdyn_ctx* c, int maxQ, int refStride)
     t->gLast = reinterpret_cast<sdyn_last_point*>(b + oGLast); t->gMap = reinterpret_cast<sdyn_mappoint_query*>(b + oGMap);
     t->readmit = reinterpret_cast<int32_t*>(b + oReadmit); t->staticExit = reinterpret_cast<int32_t*>(b + oStatic);
     t->counts = reinterpret_cast<int32_t*>(b + oCounts);
+    if (old) {
+        const size_t kb = (size_t)B * cap * sizeof(sdyn_keypoint);
+        e = cudaMemcpy(t->pKp, old->pKp, kb, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess && t->pKpUn != t->pKp)
+            e = cudaMemcpy(t->pKpUn, old->pKpUn != old->pKp ? old->pKpUn : old->pKp, kb, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(t->pCount, old->pCount, (size_t)B * 4, cudaMemcpyDeviceToDevice);
+        t->lastWasSplit = old->lastWasSplit;
+        release_track_state(old);
+        if (e != cudaSuccess) {
+            release_track_state(t);
+            return api_fail(c, SDYN_ERR_CUDA, std::string("track state: ") + cudaGetErrorString(e));
+        }
+    }
     c->track = t;
     return SDYN_OK;
 }

@@ -264,7 +264,20 @@ def test_track_resident_forms_match_explicit(cfg, B):
     for f in range(B):
         n = outs[2][f]
         assert np.array_equal(outs[3][f, :n], want[0][f, :n]) and np.array_equal(outs[5][f, :n], want[2][f, :n])
-    mt.close(); gpu.close()
+    gpu.close()
+    # the resident LastFrame survives a re-allocation of the track state: step 1 runs without a map search (state sized for
+    # `cap` queries), step 2 brings 1500 map points (> cap: the state grows) and still finds its LastFrame on the device
+    gpu2 = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=B)
+    assert map_stride > gpu2.cap
+    pysdyn.track_batch_device(gpu2, B, f1.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(p1, 0, (last_stride, 0, ref_stride), params))
+    pysdyn.track_batch_device(gpu2, B, f2.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(rp, 0, strides, params, map_table=mt))
+    got2 = pysdyn.track_fetch(gpu2, B)
+    assert np.array_equal(got2[3], want[3])
+    for f in range(B):
+        n = len(kd[f + 2][0])
+        for a, b in zip(got2[:3], want[:3]):
+            assert np.array_equal(a[f, :n], b[f, :n])
+    mt.close(); gpu2.close()
 
 
 @pytest.mark.parametrize("cfg,B,cam", [("tum", 3, None), ("tum", 2, "tum1")])

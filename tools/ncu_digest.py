@@ -67,8 +67,9 @@ def main():
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
     out["csrc_sha"] = bench.csrc_sha()
+    out["file_sha"] = bench.csrc_file_sha()          # per file: a kernel's figures stay valid while its own sources do
     json.dump(out, open(prefix + "_ncu_traffic.json", "w"), indent=1)
-    del out["csrc_sha"]
+    del out["csrc_sha"], out["file_sha"]
     for k, v in sorted(out.items(), key=lambda kv: -kv[1]["mean_us"]):
         print("%-24s %8.1f us  dram %8.2f MB  grid %s" % (k, v["mean_us"], v["dram_bytes_per_launch"] / 1e6, v["grid"]))
 
