@@ -169,12 +169,33 @@ __global__ void k_build_jobs(const __grid_constant__ JobPair F, const __grid_con
     reinterpret_cast<unsigned long long*>(jobs + (isMap ? B : 0) + f)[w] = a + (unsigned long long)f * (b - a);
 }
 
-__global__ void k_copy_match_counts(const int32_t* __restrict__ result, int B, int nframes, int32_t* __restrict__ counts)
+/* Last kernel of a step.  CTA 0 copies the two match counts of every frame; then the step's tracked keypoint lists become the
+ * resident LastFrame of the next step (one sequence per slot) — unless a search ran out of candidate pool: that step's matches
+ * are incomplete, the host is told to repeat it (track_fetch_finish), and every slot must still hold the LastFrame it had. */
+__global__ void __launch_bounds__(256)
+k_copy_match_counts(const int32_t* __restrict__ result, int B, int nframes, int32_t* __restrict__ counts,
+                    const uint32_t* __restrict__ sKp, const uint32_t* __restrict__ sKpUn, const int32_t* __restrict__ sCount,
+                    uint32_t* __restrict__ pKp, uint32_t* __restrict__ pKpUn, int32_t* __restrict__ pCount, unsigned long long words)
 {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nframes) return;
-    counts[f * 4] = result[f * 4];                 /* SearchByProjection(cur, last) */
-    counts[f * 4 + 1] = result[(B + f) * 4];       /* SearchByProjection(F, map points) */
+    __shared__ int overflow;
+    if (threadIdx.x == 0) overflow = 0;
+    __syncthreads();
+    for (int f = threadIdx.x; f < nframes; f += 256)
+        if (result[f * 4 + 2] | result[(B + f) * 4 + 2]) overflow = 1;
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int f = threadIdx.x; f < nframes; f += 256) {
+            counts[f * 4] = result[f * 4];                 /* SearchByProjection(cur, last) */
+            counts[f * 4 + 1] = result[(B + f) * 4];       /* SearchByProjection(F, map points) */
+        }
+    if (overflow) return;
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < words; i += stride) {
+        pKp[i] = sKp[i];
+        if (pKpUn) pKpUn[i] = sKpUn[i];
+    }
+    if (blockIdx.x == 0)
+        for (int f = threadIdx.x; f < nframes; f += 256) pCount[f] = sCount[f];
 }
 
 int track_fetch_enqueue(sdyn_ctx* c, int nframes, int32_t* assign, uint8_t* locked, uint8_t* dynMask, int32_t* counts, int cap,
@@ -203,7 +224,7 @@ int track_fetch_finish(sdyn_ctx* c, int nframes, int32_t* assign, uint8_t* locke
              * window can exceed it.  The step's matches are incomplete; the pool is doubled for the next call, so repeating
              * the step succeeds (the single-search entry points retry internally, sdyn_match.cpp). */
             t->wantPool = 2 * t->poolPerJob;
-            return api_fail(c, SDYN_ERR_CAPACITY, "matcher candidate pool exhausted in the batched front end: pool doubled, repeat the step");
+            return api_fail(c, SDYN_ERR_CAPACITY, "matcher candidate pool exhausted in the batched front end: pool doubled, repeat the step (no slot's resident LastFrame was advanced)");
         }
     if (cap != kc) {
         const int m = std::min(cap, kc);
@@ -417,13 +438,16 @@ static int track_after_extract(sdyn_ctx* c, int nframes, const sdyn_track_inputs
         c->launches += 2 + (both ? 1 : (in->last_stride > 0) + (in->map_stride > 0)) + ((in->last_stride > 0 || in->map_stride > 0) ? 1 : 0);
     }
     if (fork) TCU(c, cudaStreamWaitEvent(st, c->evJoin2, 0));
-    k_copy_match_counts<<<(nframes + 63) / 64, 64, 0, st>>>(t->result, B, nframes, t->counts);
-    TCU(c, cudaGetLastError());
-    c->launches += 1;
-    /* this step's tracked keypoint lists become the resident LastFrame of the next step (one sequence per slot) */
-    TCU(c, cudaMemcpyAsync(t->pKp, sKp, (size_t)nframes * cap * sizeof(sdyn_keypoint), cudaMemcpyDeviceToDevice, st));
-    if (t->pKpUn != t->pKp) TCU(c, cudaMemcpyAsync(t->pKpUn, sKpUn, (size_t)nframes * cap * sizeof(sdyn_keypoint), cudaMemcpyDeviceToDevice, st));
-    TCU(c, cudaMemcpyAsync(t->pCount, sCount, (size_t)nframes * 4, cudaMemcpyDeviceToDevice, st));
+    {
+        static_assert(sizeof(sdyn_keypoint) % 4 == 0, "keypoint lists are committed as 32-bit words");
+        const unsigned long long words = (unsigned long long)nframes * cap * (sizeof(sdyn_keypoint) / 4);
+        const int ctas = (int)std::min<unsigned long long>((words + 255) / 256, 4 * 148);
+        k_copy_match_counts<<<std::max(ctas, 1), 256, 0, st>>>(
+            t->result, B, nframes, t->counts, reinterpret_cast<const uint32_t*>(sKp), reinterpret_cast<const uint32_t*>(sKpUn), sCount,
+            reinterpret_cast<uint32_t*>(t->pKp), t->pKpUn != t->pKp ? reinterpret_cast<uint32_t*>(t->pKpUn) : nullptr, t->pCount, words);
+        TCU(c, cudaGetLastError());
+        c->launches += 1;
+    }
     return SDYN_OK;
 }
 

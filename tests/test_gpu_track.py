@@ -373,6 +373,49 @@ def test_track_rgbd_split_with_resident_last():
     mt.close(); gpu.close()
 
 
+def test_track_pool_overflow_keeps_last_frame_and_repeat_succeeds():
+    """A search window wide enough to exhaust the candidate pool: the step reports SDYN_ERR_CAPACITY, the pool is doubled, NO
+    slot's resident LastFrame has advanced, and repeating the step gives the oracle's result."""
+    import torch
+    cfg, B = "tum", 2
+    W, H, nrect, nf, ini, mn, seq_seed, frames, cpu, kd = _sequence(cfg, B + 2)
+    gpu = pysdyn.Extractor(nf, 1.2, 8, ini, mn, max_width=W, max_height=H, max_batch=B)
+    last_stride, map_stride, ref_stride = gpu.cap, 1500, 512
+    strides = (last_stride, map_stride, ref_stride)
+    params = scenario.track_params(W, H)
+    wide = dict(params); wide["th_frame"] = 120.0           # hundreds of un-gated candidates per query against a pool of ~96 per query
+    a1 = scenario.build_track_batch(kd[:B + 1], seq_seed, 1, W, H, nrect, 8, *strides, n_map=1500, seed=3)
+    a2 = scenario.build_track_batch(kd[1:B + 2], seq_seed, 2, W, H, nrect, 8, *strides, n_map=1500, seed=3)
+    d1, p1 = _dev(a1); d2, p2 = _dev(a2)
+    f1 = torch.from_numpy(frames[1:B + 1]).cuda(); f2 = torch.from_numpy(frames[2:B + 2]).cuda()
+    table, res = scenario.resident_forms(a2)
+    mt = pysdyn.MapTable(len(table)); mt.update(0, table)
+    torch.cuda.synchronize()
+    dr, pr = _dev(res)
+    rp = {k: v for k, v in p2.items() if k not in ("last_points", "last_keys", "last_keys_un", "n_last", "map_points")}
+    rp.update(pr)
+    pysdyn.track_batch_device(gpu, B, f1.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(p1, 0, strides, params))   # primes LastFrame
+    pysdyn.track_fetch(gpu, B)
+    failures = 0
+    for attempt in range(6):
+        pysdyn.track_batch_device(gpu, B, f2.data_ptr(), W * H, W, H, W, pysdyn.track_inputs(rp, 0, strides, wide, map_table=mt))
+        try:
+            got = pysdyn.track_fetch(gpu, B)
+            break
+        except pysdyn.SdynError as e:
+            assert e.code == -3 and "pool" in str(e), str(e)             # SDYN_ERR_CAPACITY
+            failures += 1
+    else:
+        raise AssertionError("the pool never became large enough")
+    assert failures >= 1                                                  # the overflow path really ran
+    for f in range(B):
+        k, d = kd[f + 2]
+        ea, el, em, ec = oracle_track.track_frame(k, d, cpu.scale, W, H, a2, f, wide, last_stride)
+        assert np.array_equal(got[3][f], ec), (f, got[3][f], ec)
+        assert np.array_equal(got[0][f, :len(k)], ea) and np.array_equal(got[1][f, :len(k)], el) and np.array_equal(got[2][f, :len(k)], em)
+    mt.close(); gpu.close()
+
+
 def test_track_device_frustum_matches_explicit():
     """Frame::isInFrustum on the device (map_flags form): local-map ids + one state byte per point; the projection records
     the explicit form uploads are derived from the resident MapPoint table and the frame's pose."""
