@@ -461,6 +461,9 @@ int sdyn_track_batch(sdyn_ctx* ctx, int nframes, const uint8_t* gray, size_t fra
 int sdyn_track_batch_async(sdyn_ctx* ctx, int nframes, const uint8_t* gray, size_t frame_stride, int width, int height,
                            int stride, const sdyn_track_inputs* in, sdyn_keypoint* kp_out, uint8_t* desc_out, int* n_out,
                            int32_t* assign, uint8_t* locked, uint8_t* dyn_mask, int32_t* counts, int cap);
+/* sdyn_track_batch / sdyn_track_wait / sdyn_track_fetch return SDYN_ERR_CAPACITY when a search of the step ran out of candidate
+ * pool (a very dense frame or a very wide window): that step's matches are incomplete, the pool has been doubled for the next
+ * call, and NO slot's resident LastFrame was advanced by the failed step — submit the same step again. */
 int sdyn_track_wait(sdyn_ctx* ctx);
 /* Layout of the host-buffer entry points' input staging block for `nframes` frames: offsets[i] is where array i of
  * sdyn_track_inputs starts (order: last_points, last_keys, last_keys_un, n_last, map_points, n_map, boxes, n_boxes, ref_box,
